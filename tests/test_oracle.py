@@ -1,0 +1,176 @@
+"""CPU tests pinning the oracle (`-m "not gpu"`).
+
+ * host-side functions: bit-exact against golden vectors produced by the REAL reference code
+   (oracle/gen_golden.py), and live against /root/reference where it exists;
+ * network arithmetic (parity unpinned by the reference): finite differences, torch autograd as
+   an independent second opinion, and a frozen self-pin.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_np as onp
+from oracle.oracle_torch import TorchNetworkVP
+
+
+# ---------------------------------------------------------------- geometry / rounding
+def test_same_padding_geometry():
+    assert (onp.H1, onp.P1_LO, onp.P1_HI) == (21, 2, 2)
+    assert (onp.H2, onp.P2_LO, onp.P2_HI) == (11, 1, 2)          # asymmetric
+    assert onp.FLAT == 3872
+    n = sum(int(np.prod(s)) for s in onp.param_shapes(6).values())
+    assert n == 1005623
+
+
+def test_bf16_round_matches_torch():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.normal(size=4096), rng.normal(size=64) * 1e-30, [0.0, -0.0, 1.0, 65280.0]]).astype(np.float32)
+    ref = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+    assert np.array_equal(onp.bf16_round(x), ref)
+
+
+def test_synthetic_frames_are_exact_in_bf16():
+    x = onp.synth_frames(np.random.default_rng(1), 2)
+    assert np.array_equal(onp.bf16_round(x), x)                     # k/128-1 needs 8 significand bits
+    assert x.min() >= -1.0 and x.max() <= 127 / 128
+
+
+# ---------------------------------------------------------------- golden: real reference outputs
+def test_returns_golden_bit_exact(golden_dir):
+    cases = json.load(open(os.path.join(golden_dir, "returns.json")))
+    assert len(cases) == 48
+    for c in cases:
+        f = c["flags"]
+        out = onp.accumulate_rewards(c["rewards"], c["gamma"], c["terminal"], discounting=f["DISCOUNTING"],
+                                     use_intermediate_reward=f["USE_INTERMEDIATE_REWARD"],
+                                     reward_clipping=f["REWARD_CLIPPING"])
+        assert [float(r).hex() for r in out] == c["out"]
+
+
+def test_returns_default_closed_form(golden_dir):
+    """R_t = gamma^(n-1-t) * r_last by repeated multiplication."""
+    out = onp.accumulate_rewards([0.3, -2.0, 0.7, 0.25], 0.99, 0.25)
+    assert out[3] == 0.25 and out[2] == 0.99 * 0.25 and out[1] == 0.99 * (0.99 * 0.25)
+    assert onp.accumulate_rewards([], 0.99, 1.0) == [] and onp.accumulate_rewards([5.0], 0.99, 5.0) == [5.0]
+
+
+def test_sampling_golden_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "sampling.npz"))
+    got = onp.select_actions(g["p"], g["u"])
+    assert np.array_equal(got, g["chosen"])
+
+
+def test_convert_data_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "convert_data.npz"))
+    assert g["r_"].dtype == np.float64 and g["a_"].dtype == np.float32
+    assert np.array_equal(np.eye(6)[g["actions"]].astype(np.float32), g["a_"])
+    assert np.array_equal(g["states"], g["x_"]) and np.array_equal(g["rewards"], g["r_"])
+
+
+# ---------------------------------------------------------------- live against the reference
+@pytest.mark.reference
+def test_returns_live_against_reference():
+    from oracle.gen_golden import import_reference_agent
+    ProcessAgent, Config, Experience = import_reference_agent()
+    rng = np.random.default_rng(99)
+    for n in (1, 2, 5, 64, 300):
+        rewards = [float(r) for r in rng.uniform(-2, 2, size=n)]
+        exps = [Experience(None, 0, None, r, None, False) for r in rewards]
+        ref = [e.reward for e in ProcessAgent._accumulate_rewards(exps, Config.DISCOUNT, rewards[-1])]
+        assert ref == onp.accumulate_rewards(rewards, Config.DISCOUNT, rewards[-1])
+
+
+# ---------------------------------------------------------------- network arithmetic
+@pytest.fixture(scope="module")
+def small():
+    rng = np.random.default_rng(12345)
+    params = onp.init_params(rng, 6)
+    x = onp.synth_frames(rng, 4)
+    y_r, a = onp.synth_targets(rng, 4)
+    return params, x, y_r, a
+
+
+def test_backward_matches_torch_autograd_fp64(small):
+    params, x, y_r, a = small
+    losses, grads = onp.loss_and_grads(params, x, y_r, a, beta=0.01)
+    tl, tg = TorchNetworkVP(params, dtype=torch.float64).grads(x, y_r, a, 0.01)
+    for k in losses:
+        assert abs(losses[k] - tl[k]) <= 1e-12 * max(1.0, abs(tl[k]))
+    for k in grads:
+        assert np.abs(grads[k] - tg[k]).max() <= 1e-12, k
+
+
+def test_backward_matches_torch_with_min_policy_and_floor(small):
+    """MIN_POLICY mixing and an epsilon floor large enough to be active (mask branches of A.4)."""
+    params, x, y_r, a = small
+    kw = dict(beta=0.05, log_eps=0.12, min_policy=0.02)
+    losses, grads = onp.loss_and_grads(params, x, y_r, a, **kw)
+    tn = TorchNetworkVP(params, dtype=torch.float64, log_eps=0.12, min_policy=0.02)
+    tl, tg = tn.grads(x, y_r, a, 0.05)
+    assert abs(losses["cost_all"] - tl["cost_all"]) < 1e-12
+    for k in grads:
+        assert np.abs(grads[k] - tg[k]).max() <= 1e-12, k
+
+
+def test_backward_finite_differences(small):
+    params, x, y_r, a = small
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    _, grads = onp.loss_and_grads(p64, x, y_r, a)
+    _, v0 = onp.forward(p64, x)
+
+    def f(pm):
+        p, v = onp.forward(pm, x)
+        return onp.losses_from_heads(p, v, y_r.astype(np.float64), a.astype(np.float64), 0.01, 1e-6, v_stop=v0)["cost_all"]
+
+    rng = np.random.default_rng(5)
+    for k in p64:
+        for _ in range(3):
+            idx = tuple(int(rng.integers(0, s)) for s in p64[k].shape)
+            if grads[k][idx] == 0.0:
+                continue
+            h = 1e-5
+            pp = {n: v.copy() for n, v in p64.items()}
+            pm = {n: v.copy() for n, v in p64.items()}
+            pp[k][idx] += h
+            pm[k][idx] -= h
+            fd = (f(pp) - f(pm)) / (2 * h)
+            assert abs(fd - grads[k][idx]) <= 1e-6 * max(1.0, abs(fd)), (k, idx, fd, grads[k][idx])
+
+
+def test_rmsprop_tf_semantics():
+    """eps inside the sqrt, ms initialised to 1.0."""
+    w = {"w": np.array([1.0, -2.0], dtype=np.float32)}
+    g = {"w": np.array([0.5, 4.0], dtype=np.float32)}
+    ms, mom = onp.rmsprop_init(w)
+    w2, ms2, _ = onp.rmsprop_update(w, g, ms, mom, lr=0.1, dtype=np.float64)
+    exp_ms = 0.99 * 1.0 + 0.01 * np.array([0.25, 16.0])
+    assert np.allclose(ms2["w"], exp_ms, rtol=0, atol=1e-7)
+    assert np.allclose(w2["w"], np.array([1.0, -2.0]) - 0.1 * np.array([0.5, 4.0]) / np.sqrt(exp_ms + 0.1), atol=1e-7)
+
+
+def test_network_self_pin(small, golden_dir):
+    params, x, y_r, a = small
+    g = np.load(os.path.join(golden_dir, "network_b4.npz"))
+    for tag, kw in (("f64", {}), ("bf16", dict(quant="bf16"))):
+        p, v = onp.forward(params, x, **kw)
+        assert np.allclose(p, g[f"{tag}_p"], rtol=0, atol=1e-12)
+        assert np.allclose(v, g[f"{tag}_v"], rtol=0, atol=1e-12)
+        losses, grads = onp.loss_and_grads(params, x, y_r, a, **kw)
+        got = np.array([losses[k] for k in ("cost_p_1", "cost_p_2", "cost_p", "cost_v", "cost_all")])
+        assert np.allclose(got, g[f"{tag}_losses"], rtol=1e-12)
+        dig = json.loads(str(g[f"{tag}_digests"]))
+        for k, d in dig.items():
+            flat = grads[k].ravel()
+            assert np.allclose(flat[d["idx"]], d["val"], rtol=1e-9, atol=1e-14), k
+            assert abs(flat.sum() - d["sum"]) <= 1e-9 * max(1.0, abs(d["sum"]))
+
+
+def test_bf16_mode_is_close_to_fp64(small):
+    params, x, _, _ = small
+    p, v = onp.forward(params, x)
+    pq, vq = onp.forward(params, x, quant="bf16")
+    assert np.abs(p - pq).max() < 5e-3 and np.abs(v - vq).max() < 5e-3
+    assert np.abs(p.sum(axis=1) - 1).max() < 1e-12
