@@ -1,0 +1,75 @@
+"""ctypes binding of include/ga3c_b200.h.  Loading fails loudly: there is no fallback path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libga3c_b200.so")
+
+
+class ga3c_config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("num_actions", C.c_int32), ("max_batch", C.c_int32),
+                ("rmsprop_decay", C.c_float), ("rmsprop_momentum", C.c_float), ("rmsprop_epsilon", C.c_float),
+                ("log_epsilon", C.c_float), ("min_policy", C.c_float)]
+
+
+# name -> (restype, argtypes); the single source the symbol-export test checks against the header
+SIGNATURES = {
+    "ga3c_last_error": (C.c_char_p, []),
+    "ga3c_abi_version": (C.c_int, []),
+    "ga3c_create": (C.c_int, [C.POINTER(ga3c_config), C.POINTER(C.c_void_p)]),
+    "ga3c_destroy": (C.c_int, [C.c_void_p]),
+    "ga3c_reserve": (C.c_int, [C.c_void_p, C.c_int32]),
+    "ga3c_param_count": (C.c_int, [C.c_void_p]),
+    "ga3c_param_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64),
+                                  C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "ga3c_arena_floats": (C.c_int64, [C.c_void_p]),
+    "ga3c_arena_ptrs": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_void_p)] * 4),
+    "ga3c_arena_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+    "ga3c_arena_download": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+    "ga3c_global_step": (C.c_int64, [C.c_void_p]),
+    "ga3c_set_global_step": (C.c_int, [C.c_void_p, C.c_int64]),
+    "ga3c_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ga3c_forward_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                                        C.c_void_p, C.c_void_p]),
+    "ga3c_apply_rmsprop": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p]),
+    "ga3c_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,
+                                  C.c_void_p, C.c_void_p]),
+    "ga3c_returns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_int32, C.c_double,
+                               C.c_double, C.c_void_p, C.c_void_p]),
+    "ga3c_select_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ga3c_workspace_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "ga3c_launch_count": (C.c_int64, [C.c_void_p]),
+}
+
+RET_DISCOUNTING, RET_INTERMEDIATE, RET_CLIPPING, RET_NSTEP = 1, 2, 4, 8
+
+_lib = None
+
+
+class Ga3cError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the C-ABI library (ctypes.CDLL releases the GIL around every call)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Ga3cError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().ga3c_last_error()
+        raise Ga3cError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")

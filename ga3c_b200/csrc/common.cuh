@@ -1,0 +1,122 @@
+// Shared device helpers for the sm_100a kernels of the GA3C hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace ga3c {
+
+// ---- geometry of the conv NetworkVP (NetworkDNav.py:81-90; SAME padding) ----
+constexpr int IMG = 84, IMG_C = 4, STATE_DIM = IMG * IMG * IMG_C;      // 28224
+constexpr int C1_OUT = 16, H1 = 21, N1_POS = H1 * H1;                  // conv11: 8x8 s4 pad (2,2) -> 21x21x16
+constexpr int C2_OUT = 32, H2 = 11, N2_POS = H2 * H2;                  // conv12: 4x4 s2 pad (1,2) -> 11x11x32
+constexpr int FLAT = N2_POS * C2_OUT;                                  // 3872
+constexpr int FC = 256;
+constexpr int MAX_ACTIONS = 18;
+
+// padded bf16 image in shared memory: 88x88 pixels x 4 channels (8 B / pixel), zero border of 2
+constexpr int XS_W = 88, XS_ROW_BYTES = XS_W * 8, XS_BYTES = XS_W * XS_ROW_BYTES;   // 61952
+// padded conv11 output in shared memory: 24x24 pixels x 16 channels (32 B / pixel), pad (1 before, 2 after)
+constexpr int N1P_W = 24, N1P_BYTES = N1P_W * N1P_W * 32;                            // 18432
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// D(16x8,f32) += A(16x16,bf16,row) * B(16x8,bf16,col)
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void lds64(uint32_t& a, uint32_t& b, uint32_t addr) {
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];\n" : "=r"(a), "=r"(b) : "r"(addr));
+}
+__device__ __forceinline__ void lds128(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(addr), "r"(v));
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.u32 [%0], {%1,%2};\n" ::"r"(addr), "r"(a), "r"(b));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+
+// 16-byte async copy global -> shared; src_bytes in {0,16}: 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// streaming 128-bit global load that does not pollute L1 (frames are read exactly once)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- swizzles shared by producer and consumer kernels -----------------------------------------
+// padded conv11 output (n1p): pixel (py, px) in 24x24, 32 B per pixel, two 16-B chunks.
+//   slot(px): rotate the low 3 bits of px right by one, so px, px+2, px+4, px+6 land in four
+//   different 32-B bank groups; the 16-B chunk is XORed with bit 3 of px so 8 stride-2 pixels
+//   reading one chunk each are conflict-free under ldmatrix.
+__device__ __forceinline__ int n1p_slot(int px) { return (px & ~7) | ((px >> 1) & 3) | ((px & 1) << 2); }
+__device__ __forceinline__ int n1p_off(int py, int px, int chunk) {
+  return ((py * N1P_W + n1p_slot(px)) << 5) + (((chunk ^ (px >> 3)) & 1) << 4);
+}
+
+// stage one fp32 frame (28224 floats, NHWC) into the padded bf16 smem image; NT threads cooperate
+template <int NT>
+__device__ __forceinline__ void stage_frame_bf16(const float* __restrict__ x, uint32_t xs_base, int tid) {
+  const float4* src = reinterpret_cast<const float4*>(x);
+  constexpr int NPIX = IMG * IMG;          // 7056 pixels, one float4 each
+  constexpr int UNROLL = 7;
+  for (int base = 0; base < NPIX; base += NT * UNROLL) {
+    float4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      int i = base + u * NT + tid;
+      if (i < NPIX) v[u] = ldg_stream(src + i);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      int i = base + u * NT + tid;
+      if (i < NPIX) {
+        int y = i / IMG, xx = i - y * IMG;
+        sts64(xs_base + (y + 2) * XS_ROW_BYTES + (xx + 2) * 8, pack_bf16(v[u].x, v[u].y), pack_bf16(v[u].z, v[u].w));
+      }
+    }
+  }
+}
+
+}  // namespace ga3c

@@ -1,0 +1,170 @@
+// Fused conv11 (8x8 s4, 16) -> conv12 (4x4 s2, 32) forward for one frame per CTA iteration.
+//
+// Reference op: tf.nn.conv2d(..., padding='SAME') + b, relu  (NetworkVP.py:224-226), wired as
+// NetworkDNav.py:81-82.  Implicit GEMM on bf16 tensor-core tiles, fp32 accumulate:
+//   conv11: M = 441 positions, N = 16, K = 256 = (kh, kw, c)      -- A from the padded smem image
+//   conv12: M = 121 positions, N = 32, K = 256 = (kh, kw, ci)     -- A from the padded smem conv11 output
+// Both N are too narrow for a tcgen05 tile to be anything but shared-memory-read bound (A-operand
+// bytes per MMA are fixed while N shrinks the math), and the im2col duplication (4x) would have to be
+// materialised in shared memory for a UMMA descriptor.  Warp-level mma.sync reads the *un-duplicated*
+// image straight out of shared memory with conflict-free 8-byte fragment loads, so the frame is
+// converted once, stays on chip, and conv11's output never leaves the SM before conv12 consumes it.
+// The kernel is bound by the HBM read of the fp32 frame (112,896 B / sample); see DESIGN.md.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ga3c {
+
+constexpr int CF_THREADS = 256;
+constexpr int CF_OFF_XS = 0;
+constexpr int CF_OFF_N1P = CF_OFF_XS + XS_BYTES;          // 61952
+constexpr int CF_OFF_W12F = CF_OFF_N1P + N1P_BYTES;       // 80384
+constexpr int CF_OFF_N2S = CF_OFF_W12F + 16 * 2 * 32 * 16;  // 96768
+constexpr int CF_OFF_BIAS = CF_OFF_N2S + N2_POS * 64;     // 104512
+constexpr int CF_SMEM = CF_OFF_BIAS + (C1_OUT + C2_OUT) * 4;  // 104704
+
+__global__ void __launch_bounds__(CF_THREADS, 2)
+conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, const float* __restrict__ b11,
+                const float* __restrict__ w12, const float* __restrict__ b12,
+                uint16_t* __restrict__ n1_out, uint16_t* __restrict__ n2_out, int batch) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t xs = sbase + CF_OFF_XS, n1p = sbase + CF_OFF_N1P, w12f = sbase + CF_OFF_W12F,
+                 n2s = sbase + CF_OFF_N2S;
+  float* bias_s = reinterpret_cast<float*>(smem + CF_OFF_BIAS);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+
+  // zero the padded buffers once: the borders are never written again
+  for (int i = tid; i < (XS_BYTES + N1P_BYTES) / 16; i += CF_THREADS) sts128(sbase + i * 16, make_uint4(0, 0, 0, 0));
+  // conv12 weights in mma B-fragment order: [kstep = tap][n-tile pair][lane] -> {b0,b1 (tile 2np), b0,b1 (tile 2np+1)}
+  // K permutation inside a k16 step (one tap, 16 ci): logical cols (2t,2t+1,2t+8,2t+9) <-> ci (4t..4t+3)
+  for (int i = tid; i < 16 * 2 * 32; i += CF_THREADS) {
+    const int ks = i >> 6, np = (i >> 5) & 1, ln = i & 31, gg = ln >> 2, tt = ln & 3;
+    uint32_t r[4];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int n = 8 * (2 * np + q) + gg;
+      const float* w = w12 + (ks * 16 + 4 * tt) * C2_OUT + n;
+      r[2 * q] = pack_bf16(w[0], w[C2_OUT]);
+      r[2 * q + 1] = pack_bf16(w[2 * C2_OUT], w[3 * C2_OUT]);
+    }
+    sts128(w12f + i * 16, make_uint4(r[0], r[1], r[2], r[3]));
+  }
+  if (tid < C1_OUT) bias_s[tid] = b11[tid];
+  if (tid < C2_OUT) bias_s[C1_OUT + tid] = b12[tid];
+  // conv11 weights as register-resident B fragments: k16 step = (kh, half): pixels kw = 4*half + t, 4 channels
+  uint32_t wb[16][2][2];
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks) {
+    const int kh = ks >> 1, kw = 4 * (ks & 1) + t;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const float* w = w11 + ((kh * 8 + kw) * 4) * C1_OUT + 8 * nt + g;
+      wb[ks][nt][0] = pack_bf16(w[0], w[C1_OUT]);
+      wb[ks][nt][1] = pack_bf16(w[2 * C1_OUT], w[3 * C1_OUT]);
+    }
+  }
+  __syncthreads();
+
+  for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+    stage_frame_bf16<CF_THREADS>(x + (size_t)b * STATE_DIM, xs, tid);
+    __syncthreads();
+
+    // ---------------- conv11: 28 m16 tiles over 8 warps ----------------
+    for (int tile = warp; tile < 28; tile += 8) {
+      const int r0 = tile * 16 + g, r1 = r0 + 8;
+      const int p0 = min(r0, N1_POS - 1), p1 = min(r1, N1_POS - 1);
+      const int oy0 = p0 / H1, ox0 = p0 - oy0 * H1, oy1 = p1 / H1, ox1 = p1 - oy1 * H1;
+      const uint32_t a0 = xs + (4 * oy0) * XS_ROW_BYTES + (4 * ox0 + t) * 8;
+      const uint32_t a1 = xs + (4 * oy1) * XS_ROW_BYTES + (4 * ox1 + t) * 8;
+      float acc[2][4] = {};
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks) {
+        const int off = (ks >> 1) * XS_ROW_BYTES + (ks & 1) * 32;
+        uint32_t a[4];
+        lds64(a[0], a[2], a0 + off);
+        lds64(a[1], a[3], a1 + off);
+        mma_bf16_16816(acc[0], a, wb[ks][0][0], wb[ks][0][1]);
+        mma_bf16_16816(acc[1], a, wb[ks][1][0], wb[ks][1][1]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const float bz0 = bias_s[8 * nt + 2 * t], bz1 = bias_s[8 * nt + 2 * t + 1];
+        if (r0 < N1_POS)
+          sts32(n1p + n1p_off(oy0 + 1, ox0 + 1, nt) + 4 * t,
+                pack_bf16(fmaxf(acc[nt][0] + bz0, 0.f), fmaxf(acc[nt][1] + bz1, 0.f)));
+        if (r1 < N1_POS)
+          sts32(n1p + n1p_off(oy1 + 1, ox1 + 1, nt) + 4 * t,
+                pack_bf16(fmaxf(acc[nt][2] + bz0, 0.f), fmaxf(acc[nt][3] + bz1, 0.f)));
+      }
+    }
+    __syncthreads();
+
+    // conv11 output to HBM (training only): coalesced 16-B chunks, un-swizzled
+    if (n1_out != nullptr) {
+      uint4* dst = reinterpret_cast<uint4*>(n1_out + (size_t)b * N1_POS * C1_OUT);
+      for (int i = tid; i < N1_POS * 2; i += CF_THREADS) {
+        const int pos = i >> 1, oy = pos / H1, ox = pos - oy * H1;
+        uint32_t r[4];
+        lds128(r, n1p + n1p_off(oy + 1, ox + 1, i & 1));
+        dst[i] = make_uint4(r[0], r[1], r[2], r[3]);
+      }
+    }
+
+    // ---------------- conv12: 8 m16 tiles, one per warp ----------------
+    {
+      const int r0 = warp * 16 + g, r1 = r0 + 8;
+      const int p0 = min(r0, N2_POS - 1), p1 = min(r1, N2_POS - 1);
+      const int oy0 = p0 / H2, ox0 = p0 - oy0 * H2, oy1 = p1 / H2, ox1 = p1 - oy1 * H2;
+      float acc[4][4] = {};
+#pragma unroll
+      for (int kh = 0; kh < 4; ++kh) {
+#pragma unroll
+        for (int kw = 0; kw < 4; ++kw) {
+          const int ks = kh * 4 + kw;
+          uint32_t a[4], bw[4];
+          lds64(a[0], a[2], n1p + n1p_off(2 * oy0 + kh, 2 * ox0 + kw, t >> 1) + (t & 1) * 8);
+          lds64(a[1], a[3], n1p + n1p_off(2 * oy1 + kh, 2 * ox1 + kw, t >> 1) + (t & 1) * 8);
+          lds128(bw, w12f + ((ks * 2 + 0) * 32 + lane) * 16);
+          mma_bf16_16816(acc[0], a, bw[0], bw[1]);
+          mma_bf16_16816(acc[1], a, bw[2], bw[3]);
+          lds128(bw, w12f + ((ks * 2 + 1) * 32 + lane) * 16);
+          mma_bf16_16816(acc[2], a, bw[0], bw[1]);
+          mma_bf16_16816(acc[3], a, bw[2], bw[3]);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float bz0 = bias_s[C1_OUT + 8 * nt + 2 * t], bz1 = bias_s[C1_OUT + 8 * nt + 2 * t + 1];
+        if (r0 < N2_POS)
+          sts32(n2s + r0 * 64 + (8 * nt + 2 * t) * 2, pack_bf16(fmaxf(acc[nt][0] + bz0, 0.f), fmaxf(acc[nt][1] + bz1, 0.f)));
+        if (r1 < N2_POS)
+          sts32(n2s + r1 * 64 + (8 * nt + 2 * t) * 2, pack_bf16(fmaxf(acc[nt][2] + bz0, 0.f), fmaxf(acc[nt][3] + bz1, 0.f)));
+      }
+    }
+    __syncthreads();
+    {
+      uint4* dst = reinterpret_cast<uint4*>(n2_out + (size_t)b * FLAT);
+      for (int i = tid; i < FLAT * 2 / 16; i += CF_THREADS) {
+        uint32_t r[4];
+        lds128(r, n2s + i * 16);
+        dst[i] = make_uint4(r[0], r[1], r[2], r[3]);
+      }
+    }
+    // no barrier needed here: the next iteration's staging only writes xs (last read before two
+    // barriers ago) and its conv11 writes n1p only after the barrier that follows staging.
+  }
+}
+
+int configure_conv_fwd() {
+  return (int)cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM);
+}
+
+int launch_conv_fwd(const float* x, const float* w11, const float* b11, const float* w12, const float* b12,
+                    uint16_t* n1_out, uint16_t* n2_out, int batch, int num_sms, cudaStream_t stream) {
+  const int grid = min(batch, 2 * num_sms);
+  conv_fwd_kernel<<<grid, CF_THREADS, CF_SMEM, stream>>>(x, w11, b11, w12, b12, n1_out, n2_out, batch);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ga3c

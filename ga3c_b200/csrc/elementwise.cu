@@ -1,0 +1,130 @@
+// HBM-bound elementwise kernels: RMSProp over the flat arena, bf16 shadow refresh, discounted
+// returns, action sampling.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ga3c {
+
+// ---- RMSProp, TensorFlow semantics (tf.train.RMSPropOptimizer, NetworkVP_discrate.py:101-105) ----
+//   ms  <- rho*ms + (1-rho)*g^2 ; mom <- mu*mom + lr*g/sqrt(ms + eps) ; w <- w - mom       [TF-SEMANTICS]
+// One float4 per thread per iteration over the whole arena (all 10 variables in one launch instead
+// of TF's 10 ApplyRMSProp launches).  With mu == 0 (Config.RMSPROP_MOMENTUM) the mom slot is dead:
+// 20 B/param of traffic (read w,g,ms; write w,ms) + 2 B/param for the bf16 shadow of dense1/w.
+template <bool HAS_MOM>
+__global__ void __launch_bounds__(256) rmsprop_kernel(RmsPropArgs a) {
+  const int64_t n4 = a.n_floats >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float one_m_rho = 1.f - a.decay;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 g = reinterpret_cast<const float4*>(a.g)[i];
+    float4 w = reinterpret_cast<float4*>(a.w)[i];
+    float4 ms = reinterpret_cast<float4*>(a.ms)[i];
+    float4 mo = HAS_MOM ? reinterpret_cast<float4*>(a.mom)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#define GA3C_RMS(c)                                                          \
+  ms.c = a.decay * ms.c + one_m_rho * g.c * g.c;                             \
+  mo.c = a.momentum * mo.c + a.lr * g.c / sqrtf(ms.c + a.eps);              \
+  w.c -= mo.c;
+    GA3C_RMS(x) GA3C_RMS(y) GA3C_RMS(z) GA3C_RMS(w)
+#undef GA3C_RMS
+    reinterpret_cast<float4*>(a.w)[i] = w;
+    reinterpret_cast<float4*>(a.ms)[i] = ms;
+    if (HAS_MOM) reinterpret_cast<float4*>(a.mom)[i] = mo;
+    const int64_t e = i << 2;
+    if (e >= a.w1_offset && e < a.w1_offset + a.w1_count)
+      reinterpret_cast<uint2*>(a.w1_shadow)[(e - a.w1_offset) >> 2] = make_uint2(pack_bf16(w.x, w.y), pack_bf16(w.z, w.w));
+  }
+}
+
+int launch_rmsprop(const RmsPropArgs& a, cudaStream_t stream) {
+  const int64_t n4 = a.n_floats >> 2;
+  const int grid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+  if (a.momentum != 0.f) rmsprop_kernel<true><<<grid, 256, 0, stream>>>(a);
+  else rmsprop_kernel<false><<<grid, 256, 0, stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int64_t n4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+int launch_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cudaStream_t stream) {
+  const int64_t n4 = n >> 2;
+  const int grid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+  f32_to_bf16_kernel<<<grid, 256, 0, stream>>>(src, dst, n4);
+  return (int)cudaGetLastError();
+}
+
+// ---- discounted returns (ProcessAgent.py:70-84) -------------------------------------------------
+// One thread per segment, sequential over time in fp64 with the reference's exact operation order
+// (explicit __dmul_rn / __dadd_rn: no FMA contraction), so the result is bit-identical to the Python
+// loop.  Parallel across agents; a parallel scan over time would reassociate and lose bit-exactness.
+__global__ void __launch_bounds__(128)
+returns_kernel(const double* __restrict__ rewards, const int64_t* __restrict__ seg, int n_segments,
+               const double* __restrict__ terminal, double discount, int flags, double rmin, double rmax,
+               double* __restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_segments) return;
+  const int64_t lo = seg[s], hi = seg[s + 1];
+  if (hi <= lo) return;
+  const bool discounting = flags & 1, intermediate = flags & 2, clipping = flags & 4, nstep = flags & 8;
+  double run = terminal[s];
+  if (nstep) {
+    out[hi - 1] = run;
+    for (int64_t t = hi - 2; t >= lo; --t) {
+      double r = rewards[t];
+      if (clipping) r = fmin(fmax(r, rmin), rmax);
+      run = __dadd_rn(__dmul_rn(discount, run), r);
+      out[t] = run;
+    }
+    return;
+  }
+  out[hi - 1] = rewards[hi - 1];
+  for (int64_t t = hi - 2; t >= lo; --t) {
+    double r = rewards[t];
+    if (clipping) r = fmin(fmax(r, rmin), rmax);
+    double o = rewards[t];
+    if (discounting) {
+      run = __dmul_rn(discount, run);
+      if (intermediate) run = __dadd_rn(__dmul_rn(discount, run), r);
+      else o = run;
+    }
+    out[t] = o;
+  }
+}
+
+int launch_returns(const double* rewards, const int64_t* seg_offsets, int n_segments, const double* terminal,
+                   double discount, int flags, double rmin, double rmax, double* out, cudaStream_t stream) {
+  if (n_segments <= 0) return 0;
+  returns_kernel<<<(n_segments + 127) / 128, 128, 0, stream>>>(rewards, seg_offsets, n_segments, terminal, discount,
+                                                                 flags, rmin, rmax, out);
+  return (int)cudaGetLastError();
+}
+
+// ---- action sampling (ProcessAgent.py:110-115) ---------------------------------------------------
+// np.random.choice(actions, p=p) == searchsorted(cumsum(float64(p)) / cumsum[-1], u, side='right')
+__global__ void __launch_bounds__(128)
+select_actions_kernel(const float* __restrict__ p, const double* __restrict__ u, int batch, int na, int32_t* __restrict__ action) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  double cdf[MAX_ACTIONS];
+  double run = 0.0;
+  for (int k = 0; k < na; ++k) { run = __dadd_rn(run, (double)p[(size_t)i * na + k]); cdf[k] = run; }
+  const double tot = cdf[na - 1], ui = u[i];
+  int idx = 0;
+  for (int k = 0; k < na; ++k) idx += (__ddiv_rn(cdf[k], tot) <= ui) ? 1 : 0;   // side='right': count of cdf <= u
+  action[i] = idx;
+}
+
+int launch_select_actions(const float* p, const double* u, int batch, int num_actions, int32_t* action,
+                          cudaStream_t stream) {
+  if (batch <= 0) return 0;
+  if (num_actions < 1 || num_actions > MAX_ACTIONS) return (int)cudaErrorInvalidValue;
+  select_actions_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(p, u, batch, num_actions, action);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ga3c

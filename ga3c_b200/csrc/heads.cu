@@ -1,0 +1,194 @@
+// Value / policy heads, softmax, A3C loss and its backward, fused.  All fp32.
+//
+// Reference graph (NetworkVP_discrate.py:60-85, :100):
+//   v = d1.Wv + bv ; z = d1.Wp + bp ; s = softmax(z) ; p = (s + MIN_POLICY) / (1 + MIN_POLICY*A)
+//   cost_p_1 = log(max(sum(p*a), eps)) * (R - stop_gradient(v)) ; cost_p_2 = -beta * sum(log(max(p, eps)) * p)
+//   cost_v = 0.5 * (R - v)^2 ; every batch reduction is a SUM.
+// Phase 1: one warp per sample, warp-shuffle reductions for the A+1 dot products, then the whole
+//          softmax / loss / dlogits chain in registers; writes p, v, dd1 (bf16) and stages (dz, dv).
+// Phase 2: one thread per dense1 feature j accumulates dWp[j,:], dWv[j], db1[j] over the chunk.
+// Gradient / loss accumulators live in registers across chunks; one atomicAdd per element per CTA.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ga3c {
+
+constexpr int HD_THREADS = 256, HD_CHUNK = 16;
+
+template <int A>
+__global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
+  constexpr int A1 = A + 1;
+  __shared__ __align__(16) float wt[A1][FC];           // wt[k][j]: k < A -> Wp[j][k]; k == A -> Wv[j]
+  __shared__ float dzs[HD_CHUNK][A1];                  // (dz_0..dz_{A-1}, dv) per sample of the chunk
+  __shared__ __align__(16) uint16_t dd1s[HD_CHUNK][FC];
+  __shared__ float bias_s[A1];
+  __shared__ float loss_s[3];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int i = tid; i < A1 * FC; i += HD_THREADS) {
+    const int k = i / FC, jx = i - k * FC;
+    wt[k][jx] = (k < A) ? p.wp[jx * A + k] : p.wv[jx];
+  }
+  if (tid < A1) bias_s[tid] = (tid < A) ? p.bp[tid] : p.bv[0];
+  if (tid < 3) loss_s[tid] = 0.f;
+  __syncthreads();
+
+  float acc[A1] = {};      // thread j: dWp[j][0..A-1], dWv[j]
+  float acc_b1 = 0.f;      // thread j: db1[j]
+  float acc_bh = 0.f;      // thread k <= A: dbp[k] / dbv
+  float l1 = 0.f, l2 = 0.f, lv = 0.f;   // lane 0 of each warp
+  const float inv_mix = 1.f / (1.f + p.min_policy * (float)A);
+
+  const int n_chunks = (p.batch + HD_CHUNK - 1) / HD_CHUNK;
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    // ---------------- phase 1: warp per sample ----------------
+#pragma unroll
+    for (int i = 0; i < HD_CHUNK / 8; ++i) {
+      const int sl = warp * (HD_CHUNK / 8) + i;
+      const int b = c * HD_CHUNK + sl;
+      if (b < p.batch) {
+        const float4 fa = *reinterpret_cast<const float4*>(p.d1 + (size_t)b * FC + 4 * lane);
+        const float4 fb = *reinterpret_cast<const float4*>(p.d1 + (size_t)b * FC + 128 + 4 * lane);
+        float z[A1];
+#pragma unroll
+        for (int k = 0; k < A1; ++k) {
+          const float4 wa = *reinterpret_cast<const float4*>(&wt[k][4 * lane]);
+          const float4 wb = *reinterpret_cast<const float4*>(&wt[k][128 + 4 * lane]);
+          float s = fa.x * wa.x;
+          s = fmaf(fa.y, wa.y, s); s = fmaf(fa.z, wa.z, s); s = fmaf(fa.w, wa.w, s);
+          s = fmaf(fb.x, wb.x, s); s = fmaf(fb.y, wb.y, s); s = fmaf(fb.z, wb.z, s); s = fmaf(fb.w, wb.w, s);
+          z[k] = warp_sum(s) + bias_s[k];
+        }
+        const float v = z[A];
+        float mx = z[0];
+#pragma unroll
+        for (int k = 1; k < A; ++k) mx = fmaxf(mx, z[k]);
+        float sm[A], den = 0.f;
+#pragma unroll
+        for (int k = 0; k < A; ++k) { sm[k] = expf(z[k] - mx); den += sm[k]; }
+        const float inv_den = 1.f / den;
+        float pr[A];
+#pragma unroll
+        for (int k = 0; k < A; ++k) { sm[k] *= inv_den; pr[k] = (sm[k] + p.min_policy) * inv_mix; }
+        if (p.p_out != nullptr) {
+#pragma unroll
+          for (int k = 0; k < A; ++k) if (lane == k) p.p_out[(size_t)b * A + k] = pr[k];
+          if (lane == 0) p.v_out[b] = v;
+        }
+        if (p.train) {
+          const float yr = p.yr[b];
+          float av[A], sel = 0.f;
+#pragma unroll
+          for (int k = 0; k < A; ++k) { av[k] = p.a[(size_t)b * A + k]; sel = fmaf(pr[k], av[k], sel); }
+          const float adv = yr - v, dv = v - yr;
+          const float coef = (sel >= p.log_eps) ? adv / sel : 0.f;
+          float h[A], sh = 0.f, ent = 0.f;
+#pragma unroll
+          for (int k = 0; k < A; ++k) {
+            const float lg = logf(fmaxf(pr[k], p.log_eps));
+            ent = fmaf(lg, pr[k], ent);
+            const float gk = -av[k] * coef + p.beta * (lg + (pr[k] >= p.log_eps ? 1.f : 0.f));
+            h[k] = gk * inv_mix;
+            sh = fmaf(sm[k], h[k], sh);
+          }
+          float dz[A];
+#pragma unroll
+          for (int k = 0; k < A; ++k) dz[k] = sm[k] * (h[k] - sh);
+          if (lane == 0) {
+            l1 += logf(fmaxf(sel, p.log_eps)) * adv;
+            l2 += -p.beta * ent;
+            lv += 0.5f * (yr - v) * (yr - v);
+#pragma unroll
+            for (int k = 0; k < A; ++k) dzs[sl][k] = dz[k];
+            dzs[sl][A] = dv;
+          }
+          // dd1[j] = relu'(d1[j]) * (sum_k dz_k Wp[j][k] + dv Wv[j]) for this lane's 8 features
+          float da[4], db[4];
+          {
+            const float4 wa = *reinterpret_cast<const float4*>(&wt[A][4 * lane]);
+            const float4 wb = *reinterpret_cast<const float4*>(&wt[A][128 + 4 * lane]);
+            da[0] = dv * wa.x; da[1] = dv * wa.y; da[2] = dv * wa.z; da[3] = dv * wa.w;
+            db[0] = dv * wb.x; db[1] = dv * wb.y; db[2] = dv * wb.z; db[3] = dv * wb.w;
+          }
+#pragma unroll
+          for (int k = 0; k < A; ++k) {
+            const float4 wa = *reinterpret_cast<const float4*>(&wt[k][4 * lane]);
+            const float4 wb = *reinterpret_cast<const float4*>(&wt[k][128 + 4 * lane]);
+            da[0] = fmaf(dz[k], wa.x, da[0]); da[1] = fmaf(dz[k], wa.y, da[1]);
+            da[2] = fmaf(dz[k], wa.z, da[2]); da[3] = fmaf(dz[k], wa.w, da[3]);
+            db[0] = fmaf(dz[k], wb.x, db[0]); db[1] = fmaf(dz[k], wb.y, db[1]);
+            db[2] = fmaf(dz[k], wb.z, db[2]); db[3] = fmaf(dz[k], wb.w, db[3]);
+          }
+          const uint2 qa = make_uint2(pack_bf16(fa.x > 0.f ? da[0] : 0.f, fa.y > 0.f ? da[1] : 0.f),
+                                      pack_bf16(fa.z > 0.f ? da[2] : 0.f, fa.w > 0.f ? da[3] : 0.f));
+          const uint2 qb = make_uint2(pack_bf16(fb.x > 0.f ? db[0] : 0.f, fb.y > 0.f ? db[1] : 0.f),
+                                      pack_bf16(fb.z > 0.f ? db[2] : 0.f, fb.w > 0.f ? db[3] : 0.f));
+          *reinterpret_cast<uint2*>(&dd1s[sl][4 * lane]) = qa;
+          *reinterpret_cast<uint2*>(&dd1s[sl][128 + 4 * lane]) = qb;
+          *reinterpret_cast<uint2*>(p.dd1 + (size_t)b * FC + 4 * lane) = qa;
+          *reinterpret_cast<uint2*>(p.dd1 + (size_t)b * FC + 128 + 4 * lane) = qb;
+        }
+      } else if (p.train) {
+        if (lane < A1) dzs[sl][lane] = 0.f;
+        *reinterpret_cast<uint2*>(&dd1s[sl][4 * lane]) = make_uint2(0, 0);
+        *reinterpret_cast<uint2*>(&dd1s[sl][128 + 4 * lane]) = make_uint2(0, 0);
+      }
+    }
+    if (!p.train) continue;
+    __syncthreads();
+    // ---------------- phase 2: thread per feature ----------------
+    {
+      const int jx = tid;
+#pragma unroll 4
+      for (int s = 0; s < HD_CHUNK; ++s) {
+        const int b = c * HD_CHUNK + s;
+        const float dval = (b < p.batch) ? p.d1[(size_t)b * FC + jx] : 0.f;
+#pragma unroll
+        for (int k = 0; k < A1; ++k) acc[k] = fmaf(dval, dzs[s][k], acc[k]);
+        acc_b1 += __uint_as_float((uint32_t)dd1s[s][jx] << 16);
+      }
+      if (tid < A1) {
+#pragma unroll 4
+        for (int s = 0; s < HD_CHUNK; ++s) acc_bh += dzs[s][tid];
+      }
+    }
+    __syncthreads();
+  }
+
+  if (!p.train) return;
+  {
+    const int jx = tid;
+#pragma unroll
+    for (int k = 0; k < A; ++k) atomicAdd(p.g_wp + jx * A + k, acc[k]);
+    atomicAdd(p.g_wv + jx, acc[A]);
+    atomicAdd(p.g_b1 + jx, acc_b1);
+    if (tid < A) atomicAdd(p.g_bp + tid, acc_bh);
+    if (tid == A) atomicAdd(p.g_bv, acc_bh);
+  }
+  if (p.loss != nullptr) {
+    if (lane == 0) { atomicAdd(&loss_s[0], l1); atomicAdd(&loss_s[1], l2); atomicAdd(&loss_s[2], lv); }
+    __syncthreads();
+    if (tid < 3) atomicAdd(p.loss + tid, loss_s[tid]);
+  }
+}
+
+template <int A>
+static int launch_heads_t(const HeadsArgs& args, int grid, cudaStream_t stream) {
+  heads_kernel<A><<<grid, HD_THREADS, 0, stream>>>(args);
+  return (int)cudaGetLastError();
+}
+
+int launch_heads(const HeadsArgs& args, int num_sms, cudaStream_t stream) {
+  const int n_chunks = (args.batch + HD_CHUNK - 1) / HD_CHUNK;
+  const int grid = min(n_chunks, 2 * num_sms);
+  switch (args.num_actions) {
+#define GA3C_CASE(N) case N: return launch_heads_t<N>(args, grid, stream);
+    GA3C_CASE(1) GA3C_CASE(2) GA3C_CASE(3) GA3C_CASE(4) GA3C_CASE(5) GA3C_CASE(6) GA3C_CASE(7) GA3C_CASE(8)
+    GA3C_CASE(9) GA3C_CASE(10) GA3C_CASE(11) GA3C_CASE(12) GA3C_CASE(13) GA3C_CASE(14) GA3C_CASE(15)
+    GA3C_CASE(16) GA3C_CASE(17) GA3C_CASE(18)
+#undef GA3C_CASE
+    default: return (int)cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace ga3c

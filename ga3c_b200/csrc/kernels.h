@@ -1,0 +1,65 @@
+// Internal launch interface between the C-ABI host layer (net.cu) and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ga3c {
+
+// one-time per-process function-attribute setup (dynamic smem opt-in); returns cudaError_t as int
+int configure_conv_fwd();
+int configure_conv_bwd();
+int configure_dense();
+
+// conv_fwd.cu -- x fp32 [B,28224] -> n1 bf16 [B,441,16] (optional), n2 bf16 [B,3872]
+int launch_conv_fwd(const float* x, const float* w11, const float* b11, const float* w12, const float* b12,
+                    uint16_t* n1_out, uint16_t* n2_out, int batch, int num_sms, cudaStream_t stream);
+
+// dense.cu -- the three dense1 GEMMs (NetworkDNav.py:90 and its autodiff)
+//   fwd  : d1[B,256]      = relu(n2[B,3872] @ w1bf[3872,256] + b1)                 fp32 out
+//   dgrad: dn2[B,3872]    = (dd1[B,256] @ w1bf^T) masked by n2 > 0                  bf16 out
+//   wgrad: g_w1[3872,256] = n2^T @ dd1                                              fp32 out (overwrites)
+int launch_dense_fwd(const uint16_t* n2, const uint16_t* w1bf, const float* b1, float* d1, int batch, cudaStream_t stream);
+int launch_dense_dgrad(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint16_t* dn2, int batch,
+                       cudaStream_t stream);
+int launch_dense_wgrad(const uint16_t* n2, const uint16_t* dd1, float* g_w1, int batch, cudaStream_t stream);
+
+// heads.cu -- value / policy heads, softmax, A3C loss and its backward (NetworkVP_discrate.py:60-85)
+struct HeadsArgs {
+  const float* d1;      // [B,256]
+  const float *wp, *bp, *wv, *bv;
+  const float *yr, *a;  // train only
+  int batch, num_actions;
+  float beta, log_eps, min_policy;
+  float *p_out, *v_out;        // may be null in train mode
+  uint16_t* dd1;               // [B,256] bf16, train only
+  float *g_wp, *g_bp, *g_wv, *g_bv, *g_b1;   // accumulated with atomics, train only
+  float* loss;                 // [4] accumulated with atomics, may be null
+  int train;
+};
+int launch_heads(const HeadsArgs& args, int num_sms, cudaStream_t stream);
+
+// conv_bwd.cu
+//   conv12 backward: dn1 = dgrad(dn2, w12) masked by n1 > 0 (bf16 out); g_w12 += wgrad; g_b12 += colsum(dn2)
+int launch_conv12_bwd(const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1, float* g_w12,
+                      float* g_b12, int batch, int num_sms, cudaStream_t stream);
+//   conv11 wgrad: g_w11 += patches(x)^T dn1 ; g_b11 += colsum(dn1)
+int launch_conv11_wgrad(const float* x, const uint16_t* dn1, float* g_w11, float* g_b11, int batch, int num_sms,
+                        cudaStream_t stream);
+
+// elementwise.cu
+struct RmsPropArgs {
+  float *w, *ms, *mom;
+  const float* g;
+  uint16_t* w1_shadow;     // bf16 shadow of dense1/w
+  int64_t n_floats;        // arena size (multiple of 4)
+  int64_t w1_offset, w1_count;
+  float lr, decay, momentum, eps;
+};
+int launch_rmsprop(const RmsPropArgs& a, cudaStream_t stream);
+int launch_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cudaStream_t stream);
+int launch_returns(const double* rewards, const int64_t* seg_offsets, int n_segments, const double* terminal,
+                   double discount, int flags, double rmin, double rmax, double* out, cudaStream_t stream);
+int launch_select_actions(const float* p, const double* u, int batch, int num_actions, int32_t* action,
+                          cudaStream_t stream);
+
+}  // namespace ga3c

@@ -1,0 +1,346 @@
+// C-ABI host layer: handle, flat arenas, workspace, and the launch sequences of the hot path.
+// See include/ga3c_b200.h for the contract and the reference call sites each entry replaces.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ga3c_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace ga3c;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* where, cudaError_t e) {
+  g_err = std::string(where) + ": " + cudaGetErrorString(e);
+  return (int)e ? (int)e : -1;
+}
+int fail_msg(const std::string& m) { g_err = m; return -1; }
+
+#define CK(call)                                            \
+  do {                                                      \
+    cudaError_t _e = (call);                                \
+    if (_e != cudaSuccess) return fail(#call, _e);          \
+  } while (0)
+#define CKL(call)                                           \
+  do {                                                      \
+    int _r = (call);                                        \
+    if (_r != 0) return fail(#call, (cudaError_t)_r);       \
+  } while (0)
+
+struct ParamDesc {
+  std::string name;
+  int64_t offset;
+  int32_t ndim;
+  int64_t shape[4];
+  int64_t count;
+};
+
+constexpr int64_t ALIGN_FLOATS = 64;
+int64_t align_up(int64_t v) { return (v + ALIGN_FLOATS - 1) / ALIGN_FLOATS * ALIGN_FLOATS; }
+
+}  // namespace
+
+struct ga3c_net {
+  ga3c_config cfg;
+  int num_sms = 148;
+  std::vector<ParamDesc> params;   // TF creation order
+  int64_t arena_floats = 0;
+  int64_t small_floats = 0;        // prefix holding every tensor except dense1/w (grads zeroed per step)
+  float *w = nullptr, *g = nullptr, *ms = nullptr, *mom = nullptr;
+  uint16_t* w1_shadow = nullptr;   // bf16 [3872,256]
+  // workspace
+  uint16_t *n1 = nullptr, *n2 = nullptr, *dd1 = nullptr, *dn2 = nullptr, *dn1 = nullptr;
+  float* d1 = nullptr;
+  int64_t global_step = 0;
+  int64_t launches = 0;
+  int last_batch = 0;
+
+  int64_t off(int i) const { return params[i].offset; }
+};
+
+enum { P_C11W = 0, P_C11B, P_C12W, P_C12B, P_D1W, P_D1B, P_VW, P_VB, P_PW, P_PB, P_COUNT };
+
+static int alloc_workspace(ga3c_net* n, int max_batch);
+
+extern "C" const char* ga3c_last_error(void) { return g_err.c_str(); }
+extern "C" int ga3c_abi_version(void) { return 1; }
+
+extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
+  if (!cfg || !out) return fail_msg("ga3c_create: null argument");
+  *out = nullptr;
+  if (cfg->num_actions < 1 || cfg->num_actions > MAX_ACTIONS) return fail_msg("ga3c_create: num_actions must be 1..18");
+  if (cfg->max_batch < 1) return fail_msg("ga3c_create: max_batch must be >= 1");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail_msg("ga3c_create: no CUDA device (there is no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail_msg("ga3c_create: device ordinal out of range");
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail_msg("ga3c_create: kernels are built for sm_100a only; device is sm_" +
+                                        std::to_string(prop.major) + std::to_string(prop.minor));
+  ga3c_net* n = new ga3c_net();
+  n->cfg = *cfg;
+  n->num_sms = prop.multiProcessorCount;
+  const int A = cfg->num_actions;
+  // TF creation order (NetworkVP.py:284-285 would list them so); offsets pack the small tensors first
+  struct { const char* name; int nd; int64_t s[4]; } spec[P_COUNT] = {
+      {"conv11/w:0", 4, {8, 8, 4, 16}}, {"conv11/b:0", 1, {16, 0, 0, 0}},
+      {"conv12/w:0", 4, {4, 4, 16, 32}}, {"conv12/b:0", 1, {32, 0, 0, 0}},
+      {"dense1/w:0", 2, {FLAT, FC, 0, 0}}, {"dense1/b:0", 1, {FC, 0, 0, 0}},
+      {"logits_v/w:0", 2, {FC, 1, 0, 0}}, {"logits_v/b:0", 1, {1, 0, 0, 0}},
+      {"logits_p/w:0", 2, {FC, A, 0, 0}}, {"logits_p/b:0", 1, {A, 0, 0, 0}}};
+  n->params.resize(P_COUNT);
+  for (int i = 0; i < P_COUNT; ++i) {
+    ParamDesc& d = n->params[i];
+    d.name = spec[i].name;
+    d.ndim = spec[i].nd;
+    d.count = 1;
+    for (int k = 0; k < 4; ++k) { d.shape[k] = spec[i].s[k]; if (k < d.ndim) d.count *= d.shape[k]; }
+  }
+  int64_t cur = 0;
+  const int order[P_COUNT] = {P_C11W, P_C11B, P_C12W, P_C12B, P_D1B, P_VW, P_VB, P_PW, P_PB, P_D1W};
+  for (int k = 0; k < P_COUNT; ++k) {
+    if (order[k] == P_D1W) n->small_floats = cur;
+    n->params[order[k]].offset = cur;
+    cur = align_up(cur + n->params[order[k]].count);
+  }
+  n->arena_floats = cur;
+
+  const size_t ab = (size_t)n->arena_floats * sizeof(float);
+#define GA3C_ALLOC(ptr, bytes)                                                   \
+  do {                                                                           \
+    cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));                        \
+    if (_e != cudaSuccess) { ga3c_destroy(n); return fail("cudaMalloc", _e); }   \
+  } while (0)
+  GA3C_ALLOC(n->w, ab); GA3C_ALLOC(n->g, ab); GA3C_ALLOC(n->ms, ab); GA3C_ALLOC(n->mom, ab);
+  GA3C_ALLOC(n->w1_shadow, (size_t)FLAT * FC * 2);
+#undef GA3C_ALLOC
+  if (int r = alloc_workspace(n, cfg->max_batch)) { ga3c_destroy(n); return r; }
+  cudaMemset(n->w, 0, ab); cudaMemset(n->g, 0, ab); cudaMemset(n->mom, 0, ab);
+  cudaMemset(n->w1_shadow, 0, (size_t)FLAT * FC * 2);
+  {  // ms slot starts at 1.0 [TF-SEMANTICS]
+    std::vector<float> ones((size_t)n->arena_floats, 1.0f);
+    cudaMemcpy(n->ms, ones.data(), ab, cudaMemcpyHostToDevice);
+  }
+  int r;
+  if ((r = configure_conv_fwd()) || (r = configure_conv_bwd()) || (r = configure_dense())) {
+    ga3c_destroy(n);
+    return fail("cudaFuncSetAttribute", (cudaError_t)r);
+  }
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { ga3c_destroy(n); return fail("ga3c_create sync", e); }
+  *out = n;
+  return 0;
+}
+
+static void free_workspace(ga3c_net* n) {
+  cudaFree(n->n1); cudaFree(n->n2); cudaFree(n->d1); cudaFree(n->dd1); cudaFree(n->dn2); cudaFree(n->dn1);
+  n->n1 = n->n2 = n->dd1 = n->dn2 = n->dn1 = nullptr; n->d1 = nullptr;
+}
+
+static int alloc_workspace(ga3c_net* n, int max_batch) {
+  const size_t mb = (size_t)max_batch;
+  CK(cudaMalloc((void**)&n->n1, mb * N1_POS * C1_OUT * 2)); CK(cudaMalloc((void**)&n->n2, mb * FLAT * 2));
+  CK(cudaMalloc((void**)&n->d1, mb * FC * 4)); CK(cudaMalloc((void**)&n->dd1, mb * FC * 2));
+  CK(cudaMalloc((void**)&n->dn2, mb * FLAT * 2)); CK(cudaMalloc((void**)&n->dn1, mb * N1_POS * C1_OUT * 2));
+  n->cfg.max_batch = max_batch;
+  return 0;
+}
+
+extern "C" int ga3c_reserve(ga3c_net* n, int32_t max_batch) {
+  if (!n) return fail_msg("ga3c_reserve: null handle");
+  if (max_batch <= n->cfg.max_batch) return 0;
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaDeviceSynchronize());
+  free_workspace(n);
+  if (int r = alloc_workspace(n, max_batch)) { n->cfg.max_batch = 0; return r; }
+  return 0;
+}
+
+extern "C" int ga3c_destroy(ga3c_net* n) {
+  if (!n) return 0;
+  cudaFree(n->w); cudaFree(n->g); cudaFree(n->ms); cudaFree(n->mom); cudaFree(n->w1_shadow);
+  free_workspace(n);
+  delete n;
+  return 0;
+}
+
+extern "C" int ga3c_param_count(const ga3c_net* n) { return n ? (int)n->params.size() : 0; }
+
+extern "C" int ga3c_param_info(const ga3c_net* n, int i, const char** name, int64_t* offset, int32_t* ndim,
+                               int64_t shape[4]) {
+  if (!n || i < 0 || i >= (int)n->params.size()) return fail_msg("ga3c_param_info: bad index");
+  const ParamDesc& d = n->params[i];
+  if (name) *name = d.name.c_str();
+  if (offset) *offset = d.offset;
+  if (ndim) *ndim = d.ndim;
+  if (shape) for (int k = 0; k < 4; ++k) shape[k] = d.shape[k];
+  return 0;
+}
+
+extern "C" int64_t ga3c_arena_floats(const ga3c_net* n) { return n ? n->arena_floats : 0; }
+
+extern "C" int ga3c_arena_ptrs(ga3c_net* n, float** p, float** g, float** ms, float** mom) {
+  if (!n) return fail_msg("ga3c_arena_ptrs: null handle");
+  if (p) *p = n->w;
+  if (g) *g = n->g;
+  if (ms) *ms = n->ms;
+  if (mom) *mom = n->mom;
+  return 0;
+}
+
+static float* arena_of(ga3c_net* n, int which) {
+  switch (which) { case 0: return n->w; case 1: return n->g; case 2: return n->ms; case 3: return n->mom; }
+  return nullptr;
+}
+
+extern "C" int ga3c_arena_upload(ga3c_net* n, int which, const float* host, int64_t nf) {
+  if (!n || !host) return fail_msg("ga3c_arena_upload: null argument");
+  float* dst = arena_of(n, which);
+  if (!dst || nf != n->arena_floats) return fail_msg("ga3c_arena_upload: bad arena id or size");
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaMemcpy(dst, host, (size_t)nf * 4, cudaMemcpyHostToDevice));
+  if (which == 0) {
+    CKL(launch_f32_to_bf16(n->w + n->off(P_D1W), n->w1_shadow, (int64_t)FLAT * FC, 0));
+    n->launches++;
+    CK(cudaDeviceSynchronize());
+  }
+  return 0;
+}
+
+extern "C" int ga3c_arena_download(ga3c_net* n, int which, float* host, int64_t nf) {
+  if (!n || !host) return fail_msg("ga3c_arena_download: null argument");
+  float* src = arena_of(n, which);
+  if (!src || nf != n->arena_floats) return fail_msg("ga3c_arena_download: bad arena id or size");
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(host, src, (size_t)nf * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int64_t ga3c_global_step(const ga3c_net* n) { return n ? n->global_step : -1; }
+extern "C" int ga3c_set_global_step(ga3c_net* n, int64_t s) { if (!n) return -1; n->global_step = s; return 0; }
+
+static int check_batch(ga3c_net* n, int batch, const char* who) {
+  if (!n) return fail_msg(std::string(who) + ": null handle");
+  if (batch < 1 || batch > n->cfg.max_batch)
+    return fail_msg(std::string(who) + ": batch " + std::to_string(batch) + " outside 1.." + std::to_string(n->cfg.max_batch));
+  return 0;
+}
+
+static HeadsArgs heads_args(ga3c_net* n, int batch) {
+  HeadsArgs h{};
+  h.d1 = n->d1;
+  h.wp = n->w + n->off(P_PW); h.bp = n->w + n->off(P_PB);
+  h.wv = n->w + n->off(P_VW); h.bv = n->w + n->off(P_VB);
+  h.batch = batch; h.num_actions = n->cfg.num_actions;
+  h.log_eps = n->cfg.log_epsilon; h.min_policy = n->cfg.min_policy;
+  return h;
+}
+
+extern "C" int ga3c_predict(ga3c_net* n, const float* x, int32_t batch, float* p_out, float* v_out, void* stream) {
+  if (int r = check_batch(n, batch, "ga3c_predict")) return r;
+  if (!x || !p_out || !v_out) return fail_msg("ga3c_predict: null buffer");
+  CK(cudaSetDevice(n->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* w = n->w;
+  CKL(launch_conv_fwd(x, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W), w + n->off(P_C12B), nullptr, n->n2,
+                      batch, n->num_sms, st));
+  CKL(launch_dense_fwd(n->n2, n->w1_shadow, w + n->off(P_D1B), n->d1, batch, st));
+  HeadsArgs h = heads_args(n, batch);
+  h.p_out = p_out; h.v_out = v_out; h.train = 0;
+  CKL(launch_heads(h, n->num_sms, st));
+  n->launches += 3;
+  n->last_batch = batch;
+  return 0;
+}
+
+extern "C" int ga3c_forward_backward(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch,
+                                     float beta, float* loss, void* stream) {
+  if (int r = check_batch(n, batch, "ga3c_forward_backward")) return r;
+  if (!x || !yr || !a) return fail_msg("ga3c_forward_backward: null buffer");
+  CK(cudaSetDevice(n->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* w = n->w;
+  float* g = n->g;
+  // small-tensor gradients are accumulated with atomics -> zero them; dense1/w is overwritten by its GEMM
+  CK(cudaMemsetAsync(g, 0, (size_t)n->small_floats * 4, st));
+  if (loss) CK(cudaMemsetAsync(loss, 0, 4 * sizeof(float), st));
+  CKL(launch_conv_fwd(x, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W), w + n->off(P_C12B), n->n1, n->n2,
+                      batch, n->num_sms, st));
+  CKL(launch_dense_fwd(n->n2, n->w1_shadow, w + n->off(P_D1B), n->d1, batch, st));
+  HeadsArgs h = heads_args(n, batch);
+  h.yr = yr; h.a = a; h.beta = beta; h.train = 1; h.dd1 = n->dd1; h.loss = loss;
+  h.g_wp = g + n->off(P_PW); h.g_bp = g + n->off(P_PB); h.g_wv = g + n->off(P_VW); h.g_bv = g + n->off(P_VB);
+  h.g_b1 = g + n->off(P_D1B);
+  CKL(launch_heads(h, n->num_sms, st));
+  CKL(launch_dense_wgrad(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
+  CKL(launch_dense_dgrad(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
+  CKL(launch_conv12_bwd(n->n1, n->dn2, w + n->off(P_C12W), n->dn1, g + n->off(P_C12W), g + n->off(P_C12B), batch,
+                        n->num_sms, st));
+  CKL(launch_conv11_wgrad(x, n->dn1, g + n->off(P_C11W), g + n->off(P_C11B), batch, n->num_sms, st));
+  n->launches += 7;
+  n->last_batch = batch;
+  return 0;
+}
+
+extern "C" int ga3c_apply_rmsprop(ga3c_net* n, float lr, void* stream) {
+  if (!n) return fail_msg("ga3c_apply_rmsprop: null handle");
+  CK(cudaSetDevice(n->cfg.device));
+  RmsPropArgs a{};
+  a.w = n->w; a.ms = n->ms; a.mom = n->mom; a.g = n->g; a.w1_shadow = n->w1_shadow;
+  a.n_floats = n->arena_floats; a.w1_offset = n->off(P_D1W); a.w1_count = (int64_t)FLAT * FC;
+  a.lr = lr; a.decay = n->cfg.rmsprop_decay; a.momentum = n->cfg.rmsprop_momentum; a.eps = n->cfg.rmsprop_epsilon;
+  CKL(launch_rmsprop(a, (cudaStream_t)stream));
+  n->launches += 1;
+  n->global_step += 1;   // opt.minimize(..., global_step=self.global_step), NetworkVP_discrate.py:130
+  return 0;
+}
+
+extern "C" int ga3c_train_step(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch, float lr,
+                               float beta, float* loss, void* stream) {
+  if (int r = ga3c_forward_backward(n, x, yr, a, batch, beta, loss, stream)) return r;
+  return ga3c_apply_rmsprop(n, lr, stream);
+}
+
+extern "C" int ga3c_returns(const double* rewards, const int64_t* seg, int32_t n_segments, const double* terminal,
+                            double discount, int32_t flags, double rmin, double rmax, double* out, void* stream) {
+  if (n_segments < 0) return fail_msg("ga3c_returns: negative segment count");
+  if (n_segments == 0) return 0;
+  if (!rewards || !seg || !terminal || !out) return fail_msg("ga3c_returns: null buffer");
+  CKL(launch_returns(rewards, seg, n_segments, terminal, discount, flags, rmin, rmax, out, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int ga3c_select_actions(const float* p, const double* u, int32_t batch, int32_t na, int32_t* action,
+                                   void* stream) {
+  if (batch < 0) return fail_msg("ga3c_select_actions: negative batch");
+  if (batch == 0) return 0;
+  if (!p || !u || !action) return fail_msg("ga3c_select_actions: null buffer");
+  if (na < 1 || na > MAX_ACTIONS) return fail_msg("ga3c_select_actions: num_actions must be 1..18");
+  CKL(launch_select_actions(p, u, batch, na, action, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int ga3c_workspace_ptr(ga3c_net* n, int which, void** ptr, int64_t* bytes) {
+  if (!n || !ptr) return fail_msg("ga3c_workspace_ptr: null argument");
+  const int64_t b = n->last_batch;
+  switch (which) {
+    case 0: *ptr = n->n1; if (bytes) *bytes = b * N1_POS * C1_OUT * 2; break;
+    case 1: *ptr = n->n2; if (bytes) *bytes = b * FLAT * 2; break;
+    case 2: *ptr = n->d1; if (bytes) *bytes = b * FC * 4; break;
+    case 3: *ptr = n->dd1; if (bytes) *bytes = b * FC * 2; break;
+    case 4: *ptr = n->dn2; if (bytes) *bytes = b * FLAT * 2; break;
+    case 5: *ptr = n->dn1; if (bytes) *bytes = b * N1_POS * C1_OUT * 2; break;
+    default: return fail_msg("ga3c_workspace_ptr: bad id");
+  }
+  return 0;
+}
+
+extern "C" int64_t ga3c_launch_count(const ga3c_net* n) { return n ? n->launches : 0; }

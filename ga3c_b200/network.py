@@ -1,0 +1,381 @@
+"""`Network` -- drop-in for the reference's Network plugin (NetworkVP.py:36-288) on the conv
+NetworkVP (conv11 8x8s4/16 -> conv12 4x4s2/32 -> dense1 256 -> value + policy heads;
+NetworkDNav.py:81-90 trunk, NetworkVP_discrate.py:60-130 heads/loss/optimizer).
+
+Same constructor, attributes and methods as the reference class:
+    Network(device, model_name, num_actions, state_dim)
+    .learning_rate, .beta          mutable, read at every train() (NetworkVP.py:230-231; Server.py:174-175)
+    predict_p_and_v(x) -> [p, v]   (NetworkVP.py:248-252)
+    train(x, y_r, a, x2, done, trainer_id)   (NetworkVP.py:254-257)
+    log / save / load / predict_single / predict_p / predict_v / get_global_step /
+    get_variables_names / get_variable_value
+
+PyTorch is used for pinned host staging, device buffers, streams and torch.distributed only; every
+kernel is launched by the C-ABI library (include/ga3c_b200.h).  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import threading
+
+import numpy as np
+import torch
+
+from . import _capi
+from .config import Config as _DefaultConfig
+
+STATE_DIM = 84 * 84 * 4
+
+
+def _parse_device(device) -> int:
+    """Config.DEVICE is a TF-style string 'gpu:0' (Config.py:62); 'cuda:0' and ints are accepted too."""
+    if isinstance(device, int):
+        return device
+    m = re.fullmatch(r"/?(?:device:)?(gpu|cuda)(?::(\d+))?", str(device).strip().lower())
+    if not m:
+        raise ValueError(f"unsupported device {device!r}: this implementation is GPU-only ('gpu:N')")
+    return int(m.group(2) or 0)
+
+
+class _DevArray:
+    """Exposes a raw device allocation owned by the C library through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, n: int, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class Network:
+    def __init__(self, device, model_name, num_actions, state_dim=STATE_DIM, *, config=None, max_batch=None,
+                 seed=None, data_parallel=None):
+        cfg = config or _DefaultConfig
+        self.config = cfg
+        self.device = device
+        self.model_name = model_name
+        self.num_actions = int(num_actions)
+        self.state_dim = int(np.prod(state_dim)) if not isinstance(state_dim, int) else state_dim
+        if self.state_dim != STATE_DIM:
+            raise ValueError(f"conv NetworkVP expects state_dim = 84*84*4 = {STATE_DIM}, got {self.state_dim}")
+        for knob in ("USE_LOG_SOFTMAX", "DUAL_RMSPROP", "USE_GRAD_CLIP"):
+            if getattr(cfg, knob, False):
+                raise NotImplementedError(f"Config.{knob}=True is not built yet (SURVEY.md 8f F4)")
+
+        self.learning_rate = cfg.LEARNING_RATE_START      # NetworkVP.py:44
+        self.beta = cfg.BETA_START                        # NetworkVP.py:45
+        self.log_epsilon = cfg.LOG_EPSILON                # NetworkVP.py:46
+
+        self._lib = _capi.load()
+        if not torch.cuda.is_available():
+            raise _capi.Ga3cError("no CUDA device visible: ga3c_b200 has no CPU fallback")
+        self._ordinal = _parse_device(device)
+        self._tdev = torch.device("cuda", self._ordinal)
+        self._lock = threading.Lock()
+        self._max_batch = int(max_batch or max(getattr(cfg, "PREDICTION_BATCH_SIZE", 128), 128))
+
+        c = _capi.ga3c_config(device=self._ordinal, num_actions=self.num_actions, max_batch=self._max_batch,
+                              rmsprop_decay=cfg.RMSPROP_DECAY, rmsprop_momentum=cfg.RMSPROP_MOMENTUM,
+                              rmsprop_epsilon=cfg.RMSPROP_EPSILON, log_epsilon=cfg.LOG_EPSILON,
+                              min_policy=cfg.MIN_POLICY)
+        h = C.c_void_p()
+        _capi.check(self._lib.ga3c_create(C.byref(c), C.byref(h)), "ga3c_create")
+        self._h = h
+
+        # name -> (offset, shape) table in TF creation order
+        self._table = {}
+        for i in range(self._lib.ga3c_param_count(self._h)):
+            name, off, nd = C.c_char_p(), C.c_int64(), C.c_int32()
+            shape = (C.c_int64 * 4)()
+            _capi.check(self._lib.ga3c_param_info(self._h, i, C.byref(name), C.byref(off), C.byref(nd), shape),
+                        "ga3c_param_info")
+            self._table[name.value.decode()] = (off.value, tuple(shape[k] for k in range(nd.value)))
+        self._arena_floats = self._lib.ga3c_arena_floats(self._h)
+        ptrs = [C.c_void_p() for _ in range(4)]
+        _capi.check(self._lib.ga3c_arena_ptrs(self._h, *[C.byref(p) for p in ptrs]), "ga3c_arena_ptrs")
+        with torch.cuda.device(self._tdev):
+            self._grad_arena = torch.as_tensor(_DevArray(ptrs[1].value, self._arena_floats, self), device=self._tdev)
+            self._param_arena = torch.as_tensor(_DevArray(ptrs[0].value, self._arena_floats, self), device=self._tdev)
+            self._stream = torch.cuda.Stream(device=self._tdev)
+            self._loss_dev = torch.zeros(4, dtype=torch.float32, device=self._tdev)
+        self._alloc_io(self._max_batch)
+
+        # variable init: U(-d, d), d = 1/sqrt(fan_in)  (NetworkVP.py:214-217, NetworkDNav.py:258-261)
+        rng = np.random.default_rng(seed)
+        fan_in = {"conv11": 8 * 8 * 4, "conv12": 4 * 4 * 16, "dense1": 3872, "logits_v": 256, "logits_p": 256}
+        init = {}
+        for name, (_, shape) in self._table.items():
+            d = 1.0 / np.sqrt(fan_in[name.split("/")[0]])
+            init[name] = rng.uniform(-d, d, size=shape).astype(np.float32)
+        self.set_variables(init)
+
+        # data parallelism: gradients are SUM-allreduced (no averaging: the loss is sum-reduced,
+        # NetworkVP_discrate.py:61,:83-85), then every rank applies the identical RMSProp update
+        import torch.distributed as dist
+        if data_parallel is None:
+            data_parallel = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self._dp = bool(data_parallel)
+        self._dist = dist if self._dp else None
+        self.last_losses = None
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc_io(self, rows: int):
+        with torch.cuda.device(self._tdev):
+            a = self.num_actions
+            self._hx = torch.empty((rows, STATE_DIM), dtype=torch.float32, pin_memory=True)
+            self._hyr = torch.empty((rows,), dtype=torch.float32, pin_memory=True)
+            self._ha = torch.empty((rows, a), dtype=torch.float32, pin_memory=True)
+            self._hp = torch.empty((rows, a), dtype=torch.float32, pin_memory=True)
+            self._hv = torch.empty((rows,), dtype=torch.float32, pin_memory=True)
+            self._dx = torch.empty((rows, STATE_DIM), dtype=torch.float32, device=self._tdev)
+            self._dyr = torch.empty((rows,), dtype=torch.float32, device=self._tdev)
+            self._da = torch.empty((rows, a), dtype=torch.float32, device=self._tdev)
+            self._dp_out = torch.empty((rows, a), dtype=torch.float32, device=self._tdev)
+            self._dv_out = torch.empty((rows,), dtype=torch.float32, device=self._tdev)
+        self._io_rows = rows
+
+    def _ensure(self, rows: int):
+        if rows > self._max_batch:
+            _capi.check(self._lib.ga3c_reserve(self._h, rows), "ga3c_reserve")
+            self._max_batch = rows
+        if rows > self._io_rows:
+            self._alloc_io(rows)
+
+    @staticmethod
+    def _stage(arr: np.ndarray, pinned: torch.Tensor, b: int) -> torch.Tensor:
+        """Host source for the H2D copy: the caller's array itself when it already lives in pinned
+        memory (no extra host pass), otherwise a copy into this Network's pinned staging buffer."""
+        if arr.flags["C_CONTIGUOUS"] and arr.flags["WRITEABLE"]:
+            t = torch.from_numpy(arr)
+            if t.is_pinned():
+                return t
+        pinned[:b].numpy()[...] = arr
+        return pinned[:b]
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.ga3c_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ device-resident API
+    def predict_device(self, x_dev: torch.Tensor, p_out: torch.Tensor = None, v_out: torch.Tensor = None, stream=None):
+        """predict_p_and_v on tensors already in HBM.  Asynchronous on `stream` (default: current)."""
+        b = x_dev.shape[0]
+        self._ensure(b)
+        if p_out is None:
+            p_out = torch.empty((b, self.num_actions), dtype=torch.float32, device=self._tdev)
+        if v_out is None:
+            v_out = torch.empty((b,), dtype=torch.float32, device=self._tdev)
+        st = stream or torch.cuda.current_stream(self._tdev)
+        _capi.check(self._lib.ga3c_predict(self._h, x_dev.data_ptr(), b, p_out.data_ptr(), v_out.data_ptr(),
+                                           st.cuda_stream), "ga3c_predict")
+        return p_out, v_out
+
+    def train_device(self, x_dev, yr_dev, a_dev, *, loss_out: torch.Tensor = None, stream=None):
+        """One A3C step on tensors already in HBM (forward, loss fwd/bwd, backward, [allreduce], RMSProp)."""
+        b = x_dev.shape[0]
+        self._ensure(b)
+        st = stream or torch.cuda.current_stream(self._tdev)
+        loss_ptr = loss_out.data_ptr() if loss_out is not None else None
+        _capi.check(self._lib.ga3c_forward_backward(self._h, x_dev.data_ptr(), yr_dev.data_ptr(), a_dev.data_ptr(), b,
+                                                    float(self.beta), loss_ptr, st.cuda_stream), "ga3c_forward_backward")
+        if self._dp:
+            with torch.cuda.stream(st):
+                self._dist.all_reduce(self._grad_arena, op=self._dist.ReduceOp.SUM)
+        _capi.check(self._lib.ga3c_apply_rmsprop(self._h, float(self.learning_rate), st.cuda_stream), "ga3c_apply_rmsprop")
+
+    # ------------------------------------------------------------------ reference API (host numpy)
+    def predict_p_and_v(self, x):
+        """NetworkVP.py:248-252.  x: float32 [B, state_dim] (a view of the predictor's reused buffer,
+        ThreadPredictor.py:57 -- consumed before returning).  Returns [p [B,A] f32, v [B] f32]."""
+        x = np.asarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.state_dim:
+            raise ValueError(f"x must be [B, {self.state_dim}], got {x.shape}")
+        b = x.shape[0]
+        if b == 0:
+            return [np.zeros((0, self.num_actions), np.float32), np.zeros((0,), np.float32)]
+        with self._lock:
+            self._ensure(b)
+            src = self._stage(x, self._hx, b)
+            with torch.cuda.stream(self._stream):
+                self._dx[:b].copy_(src, non_blocking=True)
+                self.predict_device(self._dx[:b], self._dp_out[:b], self._dv_out[:b], stream=self._stream)
+                self._hp[:b].copy_(self._dp_out[:b], non_blocking=True)
+                self._hv[:b].copy_(self._dv_out[:b], non_blocking=True)
+            self._stream.synchronize()
+            return [self._hp[:b].numpy().copy(), self._hv[:b].numpy().copy()]
+
+    def predict_single(self, x):            # NetworkVP.py:237-238
+        return self.predict_p(x[None, :])[0]
+
+    def predict_v(self, x):                 # NetworkVP.py:240-242
+        return self.predict_p_and_v(x)[1]
+
+    def predict_p(self, x):                 # NetworkVP.py:244-246
+        return self.predict_p_and_v(x)[0]
+
+    def train(self, x, y_r, a, x2=None, done=None, trainer_id=0, *, fetch_losses=False):
+        """NetworkVP.py:254-257.  x2, done, trainer_id are accepted and ignored exactly as the A3C
+        networks of the reference ignore them; y_r may arrive as float64 (ProcessAgent.py:99)."""
+        x = np.asarray(x, dtype=np.float32)
+        b = x.shape[0]
+        if b == 0:
+            return None
+        y_r = np.asarray(y_r, dtype=np.float32).reshape(b)
+        a = np.asarray(a, dtype=np.float32).reshape(b, self.num_actions)
+        with self._lock:
+            self._ensure(b)
+            sx = self._stage(x.reshape(b, self.state_dim), self._hx, b)
+            syr = self._stage(y_r, self._hyr, b)
+            sa = self._stage(a, self._ha, b)
+            with torch.cuda.stream(self._stream):
+                self._dx[:b].copy_(sx, non_blocking=True)
+                self._dyr[:b].copy_(syr, non_blocking=True)
+                self._da[:b].copy_(sa, non_blocking=True)
+                self.train_device(self._dx[:b], self._dyr[:b], self._da[:b],
+                                  loss_out=self._loss_dev if fetch_losses else None, stream=self._stream)
+                losses = self._loss_dev.cpu() if fetch_losses else None
+            self._stream.synchronize()
+        if fetch_losses:
+            c1, c2, cv = (float(v) for v in losses[:3])
+            self.last_losses = dict(cost_p_1=c1, cost_p_2=c2, cost_p=-(c1 + c2), cost_v=cv, cost_all=-(c1 + c2) + cv)
+            return self.last_losses
+        return None
+
+    def losses(self, x, y_r, a):
+        """Forward + loss only (what `log` evaluates, NetworkVP.py:259-265), without touching the weights:
+        runs forward_backward and discards the gradients."""
+        x = np.asarray(x, dtype=np.float32)
+        b = x.shape[0]
+        with self._lock:
+            self._ensure(b)
+            st = self._stream
+            with torch.cuda.stream(st):
+                dx = torch.as_tensor(x.reshape(b, self.state_dim), device=self._tdev)
+                dyr = torch.as_tensor(np.asarray(y_r, dtype=np.float32).reshape(b), device=self._tdev)
+                da = torch.as_tensor(np.asarray(a, dtype=np.float32).reshape(b, self.num_actions), device=self._tdev)
+                _capi.check(self._lib.ga3c_forward_backward(self._h, dx.data_ptr(), dyr.data_ptr(), da.data_ptr(), b,
+                                                            float(self.beta), self._loss_dev.data_ptr(), st.cuda_stream),
+                            "ga3c_forward_backward")
+                l = self._loss_dev.cpu()
+            st.synchronize()
+        c1, c2, cv = (float(v) for v in l[:3])
+        return dict(cost_p_1=c1, cost_p_2=c2, cost_p=-(c1 + c2), cost_v=cv, cost_all=-(c1 + c2) + cv)
+
+    def log(self, x, y_r, a, training_step, feed_dict=None):
+        """NetworkVP.py:259-265 writes TensorBoard summaries from a second forward pass.  Here the same
+        scalars (Pcost_advantage, Pcost_entropy, Pcost, Vcost, LearningRate, Beta) are appended to
+        logs/<model_name>/scalars.csv."""
+        l = self.losses(x, y_r, a)
+        os.makedirs(os.path.join("logs", self.model_name), exist_ok=True)
+        with open(os.path.join("logs", self.model_name, "scalars.csv"), "a") as f:
+            f.write(f"{training_step},{l['cost_p_1']},{l['cost_p_2']},{l['cost_p']},{l['cost_v']},"
+                    f"{self.learning_rate},{self.beta}\n")
+
+    # ------------------------------------------------------------------ variables / checkpoints
+    def get_global_step(self):              # NetworkVP.py:233-235
+        return int(self._lib.ga3c_global_step(self._h))
+
+    def get_variables_names(self):          # NetworkVP.py:284-285 (TF creation order)
+        return list(self._table.keys())
+
+    def _download(self, which: int) -> np.ndarray:
+        out = np.empty(self._arena_floats, dtype=np.float32)
+        with self._lock:
+            _capi.check(self._lib.ga3c_arena_download(self._h, which, out.ctypes.data, out.size), "ga3c_arena_download")
+        return out
+
+    def _upload(self, which: int, arena: np.ndarray):
+        arena = np.ascontiguousarray(arena, dtype=np.float32)
+        with self._lock:
+            _capi.check(self._lib.ga3c_arena_upload(self._h, which, arena.ctypes.data, arena.size), "ga3c_arena_upload")
+
+    def _split(self, arena: np.ndarray):
+        return {k: arena[o:o + int(np.prod(s))].reshape(s).copy() for k, (o, s) in self._table.items()}
+
+    def _join(self, which: int, tensors: dict) -> np.ndarray:
+        arena = self._download(which)
+        for k, v in tensors.items():
+            o, s = self._table[k]
+            v = np.asarray(v, dtype=np.float32)
+            if v.shape != tuple(s):
+                raise ValueError(f"{k}: expected shape {s}, got {v.shape}")
+            arena[o:o + v.size] = v.ravel()
+        return arena
+
+    def get_variable_value(self, name):     # NetworkVP.py:287-288
+        o, s = self._table[name]
+        return self._download(0)[o:o + int(np.prod(s))].reshape(s).copy()
+
+    def get_variables(self):
+        return self._split(self._download(0))
+
+    def set_variables(self, tensors: dict):
+        self._upload(0, self._join(0, tensors))
+
+    def get_gradients(self):
+        """Gradients left by the last forward_backward (after allreduce when data-parallel)."""
+        return self._split(self._download(1))
+
+    def get_slots(self):
+        return self._split(self._download(2)), self._split(self._download(3))
+
+    def set_slots(self, ms: dict = None, mom: dict = None):
+        if ms is not None:
+            self._upload(2, self._join(2, ms))
+        if mom is not None:
+            self._upload(3, self._join(3, mom))
+
+    def _checkpoint_filename(self, episode):    # NetworkVP.py:267-268
+        return 'checkpoints/%s_%08d' % (self.model_name, episode)
+
+    def _get_episode_from_filename(self, filename):     # NetworkVP.py:270-272
+        return int(re.split(r'/|_|\.', filename)[2])
+
+    def save(self, episode):
+        """NetworkVP.py:274-275: all global variables (weights, RMSProp slots, step), keyed by TF name."""
+        fn = self._checkpoint_filename(episode) + ".npz"
+        os.makedirs(os.path.dirname(fn), exist_ok=True)
+        ms, mom = self.get_slots()
+        blob = {k: v for k, v in self.get_variables().items()}
+        blob.update({k.replace(":0", "/RMSProp:0"): v for k, v in ms.items()})
+        blob.update({k.replace(":0", "/RMSProp_1:0"): v for k, v in mom.items()})
+        blob["step:0"] = np.array(self.get_global_step(), dtype=np.int64)
+        np.savez(fn, **blob)
+        return fn
+
+    def load(self):
+        """NetworkVP.py:277-282: latest checkpoint, or Config.LOAD_EPISODE; returns the episode number."""
+        d = os.path.dirname(self._checkpoint_filename(episode=0))
+        if getattr(self.config, "LOAD_EPISODE", 0) > 0:
+            filename = self._checkpoint_filename(self.config.LOAD_EPISODE)
+        else:
+            cands = sorted(f for f in os.listdir(d) if f.startswith(self.model_name + "_") and f.endswith(".npz"))
+            filename = os.path.join(d, cands[-1][:-4])
+        z = np.load(filename + ".npz")
+        names = self.get_variables_names()
+        self.set_variables({k: z[k] for k in names})
+        self.set_slots({k: z[k.replace(":0", "/RMSProp:0")] for k in names},
+                       {k: z[k.replace(":0", "/RMSProp_1:0")] for k in names})
+        self._lib.ga3c_set_global_step(self._h, int(z["step:0"]))
+        return self._get_episode_from_filename(filename)
+
+    # ------------------------------------------------------------------ introspection (tests / profiling)
+    def launch_count(self) -> int:
+        return int(self._lib.ga3c_launch_count(self._h))
+
+    def workspace(self, which: int) -> np.ndarray:
+        """Activation workspace of the last call as float32 numpy (bf16 buffers are widened)."""
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        _capi.check(self._lib.ga3c_workspace_ptr(self._h, which, C.byref(ptr), C.byref(nbytes)), "ga3c_workspace_ptr")
+        torch.cuda.synchronize(self._tdev)
+        if which == 2:
+            t = torch.as_tensor(_DevArray(ptr.value, nbytes.value // 4, self), device=self._tdev)
+            return t.cpu().numpy().copy()
+        iface = {"shape": (nbytes.value // 2,), "typestr": "<i2", "data": (ptr.value, False), "version": 2}
+        holder = type("H", (), {"__cuda_array_interface__": iface})()
+        t = torch.as_tensor(holder, device=self._tdev).view(torch.bfloat16)
+        return t.float().cpu().numpy().copy()

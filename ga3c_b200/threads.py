@@ -1,0 +1,88 @@
+"""Host-side batching threads with the reference's queue contracts.
+
+`ThreadPredictor(server, id, state_dim, prediction_q)` -- ThreadPredictor.py:34-66
+    drains `prediction_q` items `(agent_id, state)` into a batch of at most
+    Config.PREDICTION_BATCH_SIZE rows (block for the first item, then take whatever is already
+    queued, no timeout), calls `server.model.predict_p_and_v`, and answers every agent on its own
+    `wait_q` with `(p_row, v_scalar)`.
+`ThreadTrainer(server, id)` -- ThreadTrainer.py:33-62
+    concatenates `(x, r, a, x2, done)` items from `server.training_q` until the row count exceeds
+    Config.TRAINING_MIN_BATCH_SIZE, then calls `server.train_model(x, r, a, x2, done, id)`.
+
+They only need a `server` exposing `.model`, `.agents`, `.training_q`, `.train_model` (and
+`.network_tester_process` / `.replay_q` when those Config switches are on), as in Server.py:70-150.
+"""
+from __future__ import annotations
+
+from threading import Thread
+
+import numpy as np
+
+from .config import Config as _DefaultConfig
+
+NETWORK_TESTER_ID = 100      # ThreadPredictor.py:64-66
+
+
+class ThreadPredictor(Thread):
+    def __init__(self, server, id, state_dim, prediction_q, config=None):
+        super().__init__(daemon=True)
+        self.server = server
+        self.id = id
+        self.state_dim = state_dim
+        self.prediction_q = prediction_q
+        self.exit_flag = False
+        self.config = config or getattr(server, "config", None) or _DefaultConfig
+        self.batches = 0
+        self.rows = 0
+
+    def run(self):
+        cap = self.config.PREDICTION_BATCH_SIZE
+        ids = np.zeros(cap, dtype=np.uint16)                      # uint16 as in ThreadPredictor.py:46
+        states = np.zeros((cap, self.state_dim), dtype=np.float32)
+        q = self.prediction_q
+        while not self.exit_flag:
+            ids[0], states[0] = q.get()
+            n = 1
+            while n < cap and not q.empty():
+                ids[n], states[n] = q.get()
+                n += 1
+            p, v = self.server.model.predict_p_and_v(states[:n])
+            self.batches += 1
+            self.rows += n
+            agents = self.server.agents
+            for i in range(n):
+                aid = int(ids[i])
+                if aid < len(agents):
+                    agents[aid].wait_q.put((p[i], v[i]))
+                if aid == NETWORK_TESTER_ID and getattr(self.config, "USE_NETWORK_TESTER", False):
+                    self.server.network_tester_process.wait_q.put((p[i], v[i]))
+
+
+class ThreadTrainer(Thread):
+    def __init__(self, server, id, config=None):
+        super().__init__(daemon=True)
+        self.server = server
+        self.id = id
+        self.exit_flag = False
+        self.config = config or getattr(server, "config", None) or _DefaultConfig
+
+    def _next_batch(self):
+        """Accumulate agent batches until the row count EXCEEDS TRAINING_MIN_BATCH_SIZE (the
+        reference loops `while batch_size <= MIN`, ThreadTrainer.py:49)."""
+        parts, rows = [], 0
+        while rows <= self.config.TRAINING_MIN_BATCH_SIZE:
+            item = self.server.training_q.get()
+            parts.append(item)
+            rows += item[0].shape[0]
+        if len(parts) == 1:
+            return parts[0]
+        return tuple(np.concatenate([p[k] for p in parts]) for k in range(5))
+
+    def run(self):
+        while not self.exit_flag:
+            if getattr(self.config, "USE_REPLAY_MEMORY", False):
+                x, a, r, done, x2 = self.server.replay_q.get()     # ThreadTrainer.py:45-46 (DDPG only)
+            else:
+                x, r, a, x2, done = self._next_batch()
+            if self.config.TRAIN_MODELS:
+                self.server.train_model(x, r, a, x2, done, self.id)

@@ -1,0 +1,121 @@
+/* ga3c_b200.h -- C ABI of the B200-native GA3C predict/train hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one
+ * `tf.Session.run` call site of the reference `Network` class (paths into /root/reference/ga3c):
+ *
+ *   ga3c_create / ga3c_destroy      NetworkVP.py:37-64    (graph + session + variable init)
+ *   ga3c_param_*                    NetworkVP.py:284-288  (get_variables_names / get_variable_value)
+ *   ga3c_predict                    NetworkVP.py:248-252  (predict_p_and_v: sess.run([softmax_p, logits_v]))
+ *   ga3c_forward_backward           NetworkVP_discrate.py:60-85,:100 + the autodiff half of opt.minimize (:130)
+ *   ga3c_apply_rmsprop              NetworkVP_discrate.py:101-105 (ApplyRMSProp on every variable) + global_step++
+ *   ga3c_train_step                 NetworkVP.py:254-257  (train: sess.run(train_op))
+ *   ga3c_returns                    ProcessAgent.py:70-84 (_accumulate_rewards), on device, fp64, bit-exact
+ *   ga3c_select_actions             ProcessAgent.py:110-115 (np.random.choice given its uniform draw), bit-exact
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types.  Every function returns 0 on success, non-zero on error;
+ *     ga3c_last_error() returns a thread-local message for the last failure on this thread.
+ *   - pointers named *_dev are DEVICE pointers owned by the caller; `stream` is a cudaStream_t
+ *     passed as void* (NULL = legacy default stream).  Calls are asynchronous on `stream`.
+ *   - the handle owns the parameter / gradient / RMSProp-slot arenas and the activation workspace.
+ *   - there is no CPU fallback: ga3c_create fails if no sm_100 device is present.
+ *   - a handle is NOT re-entrant: the caller serialises predict/train on one handle (the Python
+ *     `Network` holds a lock; the reference gives no ordering guarantee between its predictor and
+ *     trainer threads, Server.py:123-134, so serialising them changes nothing observable).
+ */
+#ifndef GA3C_B200_H
+#define GA3C_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ga3c_net ga3c_net;
+
+/* Config.py knobs the path reads. */
+typedef struct ga3c_config {
+  int32_t device;            /* CUDA ordinal; Config.DEVICE 'gpu:N' -> N                      */
+  int32_t num_actions;       /* A, 1..18                                                      */
+  int32_t max_batch;         /* rows of activation workspace (predict and train)              */
+  float   rmsprop_decay;     /* Config.RMSPROP_DECAY    (0.99)                                */
+  float   rmsprop_momentum;  /* Config.RMSPROP_MOMENTUM (0.0)                                 */
+  float   rmsprop_epsilon;   /* Config.RMSPROP_EPSILON  (0.1)  -- inside the sqrt             */
+  float   log_epsilon;       /* Config.LOG_EPSILON      (1e-6)                                */
+  float   min_policy;        /* Config.MIN_POLICY       (0.0)                                 */
+} ga3c_config;
+
+const char* ga3c_last_error(void);
+int ga3c_abi_version(void);
+
+int ga3c_create(const ga3c_config* cfg, ga3c_net** out);
+int ga3c_destroy(ga3c_net* net);
+/* grow the activation workspace to hold `max_batch` rows (no-op if already large enough).  The
+ * reference's train batch is unbounded (ThreadTrainer.py:48-59 concatenates agent batches). */
+int ga3c_reserve(ga3c_net* net, int32_t max_batch);
+
+/* ---- parameter arena -------------------------------------------------------------------
+ * One flat fp32 arena holds all 10 variables; grads / ms / mom arenas have the same layout.
+ * Tensors are listed in TF creation order (conv11/w:0, conv11/b:0, conv12/w:0, ... logits_p/b:0);
+ * offsets are in floats and are NOT in that order (small tensors are packed first). */
+int     ga3c_param_count(const ga3c_net* net);
+int     ga3c_param_info(const ga3c_net* net, int index, const char** name, int64_t* offset,
+                        int32_t* ndim, int64_t shape[4]);
+int64_t ga3c_arena_floats(const ga3c_net* net);
+/* device base pointers of the four arenas (any may be NULL to skip) */
+int ga3c_arena_ptrs(ga3c_net* net, float** params_dev, float** grads_dev, float** ms_dev, float** mom_dev);
+/* host <-> device copies of a whole arena; which: 0 params, 1 grads, 2 ms, 3 mom.  Synchronous.
+ * Writing params also refreshes the bf16 shadow of dense1/w. */
+int ga3c_arena_upload(ga3c_net* net, int which, const float* host, int64_t n_floats);
+int ga3c_arena_download(ga3c_net* net, int which, float* host, int64_t n_floats);
+int64_t ga3c_global_step(const ga3c_net* net);
+int ga3c_set_global_step(ga3c_net* net, int64_t step);
+
+/* ---- hot path -----------------------------------------------------------------------------
+ * x_dev   fp32 [B, 28224]  NHWC frames flattened (84*84*4), exactly what ThreadPredictor stacks
+ * p_dev   fp32 [B, A]      softmax policy (fp32 so np.random.choice accepts it)
+ * v_dev   fp32 [B]
+ * yr_dev  fp32 [B]         discounted returns; a_dev fp32 [B, A] one-hot actions
+ * loss_dev fp32 [4] or NULL: {cost_p_1_agg, cost_p_2_agg, cost_v, 0} (sums over the batch);
+ *          cost_p = -(loss[0]+loss[1]), cost_all = cost_p + loss[2]  (NetworkVP_discrate.py:83-85,:100)
+ */
+int ga3c_predict(ga3c_net* net, const float* x_dev, int32_t batch, float* p_dev, float* v_dev, void* stream);
+int ga3c_forward_backward(ga3c_net* net, const float* x_dev, const float* yr_dev, const float* a_dev,
+                          int32_t batch, float beta, float* loss_dev, void* stream);
+int ga3c_apply_rmsprop(ga3c_net* net, float learning_rate, void* stream);
+int ga3c_train_step(ga3c_net* net, const float* x_dev, const float* yr_dev, const float* a_dev,
+                    int32_t batch, float learning_rate, float beta, float* loss_dev, void* stream);
+
+/* ---- returns (ProcessAgent.py:70-84) --------------------------------------------------------
+ * Segments (one per agent rollout) are packed back to back; seg_offsets_dev has n_segments+1
+ * entries.  fp64 throughout, same operation order as the reference loop => bit-exact.
+ * flags: bit0 DISCOUNTING, bit1 USE_INTERMEDIATE_REWARD, bit2 REWARD_CLIPPING  (Config.py:73-83)
+ *        bit3 NSTEP: upstream semantics R_t = clip(r_t) + gamma*R_{t+1} seeded with terminal[s]
+ *             (the commented ProcessAgent.py:83,:146); out[n-1] is set to the seed.              */
+#define GA3C_RET_DISCOUNTING 1
+#define GA3C_RET_INTERMEDIATE 2
+#define GA3C_RET_CLIPPING 4
+#define GA3C_RET_NSTEP 8
+int ga3c_returns(const double* rewards_dev, const int64_t* seg_offsets_dev, int32_t n_segments,
+                 const double* terminal_dev, double discount, int32_t flags, double reward_min,
+                 double reward_max, double* out_dev, void* stream);
+
+/* ---- sampling (ProcessAgent.py:110-115) ------------------------------------------------------
+ * action[i] = searchsorted(cumsum(float64(p[i])) / sum, u[i], side='right'): np.random.choice given
+ * the uniform it drew.  Bit-exact.  */
+int ga3c_select_actions(const float* p_dev, const double* u_dev, int32_t batch, int32_t num_actions,
+                        int32_t* action_dev, void* stream);
+
+/* ---- introspection for tests / profiling ---------------------------------------------------- */
+/* device pointers to the activation workspace of the last call (bf16 stored as uint16):
+ * which: 0 n1 [B,441,16] bf16, 1 n2 [B,3872] bf16, 2 d1 [B,256] fp32, 3 dd1 [B,256] bf16,
+ *        4 dn2 [B,3872] bf16, 5 dn1 [B,441,16] bf16 */
+int ga3c_workspace_ptr(ga3c_net* net, int which, void** ptr_dev, int64_t* bytes);
+/* number of kernels this library has launched on this handle since creation */
+int64_t ga3c_launch_count(const ga3c_net* net);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GA3C_B200_H */
