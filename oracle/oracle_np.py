@@ -177,8 +177,9 @@ def losses_from_heads(p, v, y_r, a, beta, log_eps, v_stop=None):
 
 
 def loss_and_grads(params, x, y_r, a, *, beta=0.01, log_eps=1e-6, min_policy=0.0,
-                   dtype=np.float64, quant=None):
-    """A5 minus the optimizer: returns (losses dict, grads dict keyed like params)."""
+                   dtype=np.float64, quant=None, keep=False):
+    """A5 minus the optimizer: returns (losses dict, grads dict keyed like params); with keep=True
+    also the forward cache extended by the backward intermediates dd1 / dn2 / dn1 / dz / dv."""
     f = forward(params, x, dtype=dtype, quant=quant, min_policy=min_policy, keep=True)
     b = x.shape[0]
     y_r = np.asarray(y_r, dtype=dtype)
@@ -218,6 +219,9 @@ def loss_and_grads(params, x, y_r, a, *, beta=0.01, log_eps=1e-6, min_policy=0.0
     grads["conv11/b:0"] = dn1.sum(axis=0)
     for k in grads:
         grads[k] = grads[k].reshape(params[k].shape)
+    if keep:
+        f.update(dd1=dd1, dn2=dn2.reshape(b, FLAT), dn1=dn1.reshape(b, H1 * H1 * C1_OUT), dz=dz, dv=dv)
+        return losses, grads, f
     return losses, grads
 
 
