@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- GA3C hot-path throughput on B200: TPS (training frames/s) and PPS (predictions/s).
+
+    python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the C-ABI)
+    python bench.py --impl reference --gpus N --steps K ...  the reference arm: CPU restatement of the
+                                                             reference TF graph on the host cores
+
+Workload (BASELINE.json configs[2] / configs[1]): conv NetworkVP, 84x84x4 fp32 frames,
+6 actions.  A "step" is one batched A3C train step (forward, fused loss fwd/bwd, backward, gradient
+allreduce when N>1, RMSProp) over B=1024 frames PER GPU (weak scaling).  `value` is the whole-job
+training frames/s with inputs resident in HBM; `e2e` is the same step through Network.train() on
+pinned HOST numpy buffers (H2D of the batch and D2H of the loss inside the timed region).  The `pps`
+object is the ThreadPredictor path (Network.predict_p_and_v) at B=4096, measured the same two ways.
+
+One JSON line on stdout (rank 0).  Everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+STATE_DIM = 84 * 84 * 4
+NUM_ACTIONS = 6
+N_PARAMS = 1005623
+L2_BYTES = 126 * 2 ** 20
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tensor_burst=float(d["bf16_tflops"]),
+                    tensor_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback")
+
+
+def workload_config(args, world):
+    return {"workload": f"NetworkVP 84x84x4 (conv8x8s4/16 -> conv4x4s2/32 -> fc256 -> 6 policy + 1 value), "
+                        f"A3C train step B={args.batch}/GPU (BASELINE configs[2]); pps: predict B={args.predict_batch} "
+                        f"(configs[1])",
+            "train_batch_per_gpu": args.batch, "global_batch": args.batch * world, "predict_batch": args.predict_batch,
+            "num_actions": NUM_ACTIONS, "frame": "84x84x4 fp32", "parallelism": f"dp{world}",
+            "l2": "ring of device input batches > 126 MB L2, rotated every step"}
+
+
+METRIC = "TPS: A3C training frames/s, NetworkVP 84x84x4 (PPS: predictions/s, in 'pps')"
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic work per launch (DESIGN.md "Kernels").  bytes for HBM-bound kernels,
+# flops for the tensor-bound dense1 GEMMs.
+def kernel_work(name, b, train):
+    n1, n2, fc = 441 * 16, 3872, 256
+    x = STATE_DIM * 4
+    if name == "conv_fwd":
+        return "hbm", b * (x + (n1 * 2 if train else 0) + n2 * 2)
+    if name == "conv11_wgrad":
+        return "hbm", b * (x + n1 * 2)
+    if name == "conv12_bwd":
+        return "hbm", b * (n1 * 2 + n2 * 2 + n1 * 2)
+    if name == "heads":
+        return "hbm", b * (fc * 4 + (fc * 2 + 4 + NUM_ACTIONS * 4 if train else (NUM_ACTIONS + 1) * 4))
+    if name == "rmsprop":
+        return "hbm", N_PARAMS * 20 + n2 * fc * 2
+    if name in ("dense_fwd", "dense_wgrad", "dense_dgrad"):
+        return "tensor", 2.0 * b * n2 * fc
+    raise KeyError(name)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons while the timed regions run (NVML, 50 ms period)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._th = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:      # noqa
+            log(f"[bench] NVML unavailable: {e}")
+            self._nv = None
+
+    def _once(self):
+        nv = self._nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20),
+                          ("hw_thermal_slowdown", 0x40), ("hw_power_brake", 0x80)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def start(self):
+        if self._nv is None:
+            return
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self._once()
+                except Exception:   # noqa
+                    pass
+                self._stop.wait(0.05)
+        self._th = threading.Thread(target=loop, daemon=True)
+        self._th.start()
+
+    def stop(self):
+        if self._th is not None:
+            self._stop.set()
+            self._th.join()
+            try:
+                self._once()
+            except Exception:       # noqa
+                pass
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+def synth_batch(rng, b):
+    """Frames exactly as Environment.py:57-61 yields them (uint8 k -> k/128 - 1), returns U(-1,1),
+    one-hot actions."""
+    k = rng.integers(0, 256, size=(b, STATE_DIM), dtype=np.uint8)
+    x = k.astype(np.float32)
+    x *= np.float32(1 / 128.0)
+    x -= np.float32(1.0)
+    y_r = rng.uniform(-1.0, 1.0, size=b).astype(np.float32)
+    a = np.eye(NUM_ACTIONS, dtype=np.float32)[rng.integers(0, NUM_ACTIONS, size=b)]
+    return x, y_r, a
+
+
+def cpu_reference_run(args, steps, warmup, budget_s=150.0):
+    """The reference arm / cpu_baseline leg: torch-CPU fp32 restatement of the reference TF graph
+    (oracle/oracle_torch.py; TensorFlow is not installable here), all host threads."""
+    import torch
+    from oracle import oracle_np as onp
+    from oracle.oracle_torch import TorchNetworkVP
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(12345)
+    net = TorchNetworkVP(onp.init_params(rng, NUM_ACTIONS))
+    x, y_r, a = synth_batch(rng, args.batch)
+    tx, tyr, ta = torch.from_numpy(x), torch.from_numpy(y_r), torch.from_numpy(a)
+    # probe one step on 64 rows to size the bounded sample
+    t0 = time.perf_counter()
+    net.train(tx[:64], tyr[:64], ta[:64], 3e-4, 0.01)
+    probe = time.perf_counter() - t0
+    net.train(tx[:64], tyr[:64], ta[:64], 3e-4, 0.01)
+    t0 = time.perf_counter()
+    net.train(tx[:64], tyr[:64], ta[:64], 3e-4, 0.01)
+    probe = min(probe, time.perf_counter() - t0)
+    rows = args.batch
+    while rows > 64 and probe * (rows / 64) * (steps + warmup) > budget_s:
+        rows //= 2
+    for _ in range(warmup):
+        net.train(tx[:rows], tyr[:rows], ta[:rows], 3e-4, 0.01)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        net.train(tx[:rows], tyr[:rows], ta[:rows], 3e-4, 0.01)
+    dt = time.perf_counter() - t0
+    tps = rows * steps / dt
+    # predict leg
+    prow = min(args.predict_batch, max(64, rows * 2))
+    px = torch.from_numpy(synth_batch(rng, prow)[0])
+    net.predict_p_and_v(px)
+    psteps = max(2, min(steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(psteps):
+        net.predict_p_and_v(px)
+    pdt = time.perf_counter() - t0
+    return dict(tps=tps, ms_per_step=dt / steps * 1e3, rows=rows, steps=steps, cores=cores,
+                pps=prow * psteps / pdt, prow=prow, psteps=psteps)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    r = cpu_reference_run(args, args.steps, args.warmup)
+    sample = (f"{r['steps']} train steps of {r['rows']} frames (of B={args.batch}); "
+              f"{r['psteps']} predict calls of {r['prow']} frames")
+    out = {"impl": "reference", "metric": METRIC, "value": r["tps"], "unit": "frames/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config(args, world),
+           "cpu_baseline": {"value": r["tps"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": sample,
+                            "note": "torch-CPU fp32 restatement of the reference TF graph (TensorFlow not installable)"},
+           "e2e": {"value": r["tps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "pps": {"value": r["pps"], "unit": "predictions/s", "batch": r["prow"]},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import ga3c_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    B, PB = args.batch, args.predict_batch
+    K, W = args.steps, max(args.warmup, 3)
+    net = ga3c_b200.Network(f"gpu:{local_rank}", "bench", NUM_ACTIONS, max_batch=max(B, PB), seed=12345)
+    pk = peaks()
+    stream = torch.cuda.current_stream(dev)
+
+    # ---- synthetic data: pinned host batches (e2e) and a device ring larger than L2 (value) ----
+    rng = np.random.default_rng(12345 + 1000 * rank)
+    n_ring = max(2, -(-int(1.5 * L2_BYTES) // (B * STATE_DIM * 4)) + 1)
+    host = []
+    for _ in range(min(n_ring, 2)):
+        x, y_r, a = synth_batch(rng, B)
+        host.append(tuple(torch.from_numpy(t).pin_memory() for t in (x, y_r, a)))
+    ring = []
+    for i in range(n_ring):
+        hx, hyr, ha = host[i % len(host)]
+        dx = hx.to(dev)
+        if i >= len(host):                  # distinct contents per ring slot without more host RNG time
+            dx = torch.roll(dx, shifts=i, dims=0)
+        ring.append((dx, hyr.to(dev), ha.to(dev)))
+    px_host = torch.from_numpy(synth_batch(rng, PB)[0]).pin_memory()
+    n_pring = max(2, -(-int(1.5 * L2_BYTES) // (PB * STATE_DIM * 4)) + 1)
+    pring = [torch.roll(px_host.to(dev), shifts=i, dims=0) for i in range(n_pring)]
+    p_out = torch.empty((PB, NUM_ACTIONS), dtype=torch.float32, device=dev)
+    v_out = torch.empty((PB,), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """barrier + sync on both sides, CUDA events on the launching stream, max over ranks (ms)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); torch.cuda.synchronize()
+        e0.record(stream)
+        for i in range(steps):
+            fn(i)
+        e1.record(stream)
+        torch.cuda.synchronize(); barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    def train_step(i):
+        dx, dyr, da = ring[i % n_ring]
+        net.train_device(dx, dyr, da, stream=stream)
+
+    def predict_step(i):
+        net.predict_device(pring[i % n_pring], p_out, v_out, stream=stream)
+
+    sampler = ClockSampler(local_rank)
+    for i in range(W):
+        train_step(i)
+    for i in range(W):
+        predict_step(i)
+    torch.cuda.synchronize()
+
+    sampler.start()
+    l0 = net.launch_count()
+    ms_train = timed(train_step, K)
+    launches = net.launch_count() - l0
+    ms_pred = timed(predict_step, K)
+
+    # ---- per-kernel durations, live, with events on the launch stream (roofline leg) ----
+    net.kernel_timing(K * 8)
+    ms_train_ev = timed(train_step, K)
+    kt_train = net.kernel_times()
+    net.kernel_timing(K * 3)
+    ms_pred_ev = timed(predict_step, K)
+    kt_pred = net.kernel_times()
+    net.kernel_timing(0)
+
+    # ---- e2e through the public API on pinned host buffers ----
+    def e2e(fn, steps):
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            fn(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        return max_over_ranks(dt)
+
+    def train_e2e(i):
+        hx, hyr, ha = host[i % len(host)]
+        net.train(hx.numpy(), hyr.numpy(), ha.numpy(), None, None, 0, fetch_losses=True)
+
+    def predict_e2e(i):
+        net.predict_p_and_v(px_host.numpy())
+
+    k_e2e = max(3, min(K, 20))
+    for i in range(2):
+        train_e2e(i); predict_e2e(i)
+    s_train_e2e = e2e(train_e2e, k_e2e)
+    s_pred_e2e = e2e(predict_e2e, k_e2e)
+    sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    def roofline(kt, b, train, total_ms_events):
+        rows = {}
+        for name, (tot, cnt) in kt.items():
+            if cnt == 0:
+                continue
+            bound, work = kernel_work(name, b, train)
+            avg_s = tot / cnt / 1e3
+            if bound == "hbm":
+                ach, peak, unit = work / avg_s / 1e9, pk["hbm"], "GB/s"
+            else:
+                ach, peak, unit = work / avg_s / 1e12, pk["tensor_sustained"], "TFLOP/s"
+            rows[name] = {"bound": bound, "achieved": round(ach, 1), "peak": peak, "unit": unit,
+                          "frac": round(ach / peak, 4), "avg_us": round(avg_s * 1e6, 2),
+                          "share": round(tot / total_ms_events, 4), "launches": int(cnt)}
+        return rows
+
+    rf_train = roofline(kt_train, B, True, ms_train_ev)
+    rf_pred = roofline(kt_pred, PB, False, ms_pred_ev)
+    top = max(rf_train, key=lambda k: rf_train[k]["share"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(top)
+    roof = dict(rf_train[top], kernel=top, traffic=traffic, peak_source=pk["source"],
+                note="achieved = algorithmic bytes (or flops) per launch / CUDA-event duration of that kernel, "
+                     "measured in this run on the launch stream",
+                kernels_train=rf_train, kernels_predict=rf_pred,
+                step_ms_with_events=round(ms_train_ev / K, 4))
+
+    tps = world * B * K / (ms_train / 1e3)
+    pps = world * PB * K / (ms_pred / 1e3)
+    out = {"metric": METRIC, "value": tps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+           "ms_per_step": ms_train / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "bf16", "data": "synthetic", "config": workload_config(args, world),
+           "tps_batches_per_s": tps / B,
+           "roofline": roof,
+           "e2e": {"value": world * B * k_e2e / s_train_e2e, "unit": "frames/s",
+                   "h2d_bytes_per_step": B * (STATE_DIM + 1 + NUM_ACTIONS) * 4, "d2h_bytes_per_step": 16,
+                   "steps": k_e2e, "api": "Network.train(x, y_r, a, x2, done, trainer_id) on pinned host numpy"},
+           "pps": {"value": pps, "unit": "predictions/s", "batch": PB, "ms_per_step": ms_pred / K,
+                   "e2e": {"value": world * PB * k_e2e / s_pred_e2e, "unit": "predictions/s",
+                           "h2d_bytes_per_step": PB * STATE_DIM * 4, "d2h_bytes_per_step": PB * (NUM_ACTIONS + 1) * 4,
+                           "api": "Network.predict_p_and_v(x) on pinned host numpy"}},
+           "gpu_launches": int(launches),
+           "clocks": sampler.summary()}
+
+    if world == 1 and not args.no_cpu_baseline:
+        log("[bench] timing the CPU restatement (bounded sample) ...")
+        r = cpu_reference_run(args, steps=args.cpu_steps, warmup=1, budget_s=25.0)
+        out["cpu_baseline"] = {"value": r["tps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
+                               "sample": f"{r['steps']} train steps of {r['rows']} frames (of B={B})",
+                               "pps": r["pps"],
+                               "note": "torch-CPU fp32 restatement of the reference TF graph (TensorFlow not installable)"}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="train frames per GPU per step")
+    ap.add_argument("--predict-batch", type=int, default=4096)
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

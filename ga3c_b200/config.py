@@ -55,7 +55,7 @@ class Config:
     LOAD_CHECKPOINT = False
     LOAD_EPISODE = 0
     SAVE_MODELS = True
-    TENSORBOARD = False
+    TENSORBOARD = True
     TENSORBOARD_UPDATE_FREQUENCY = 1000
     NETWORK_NAME = 'network'
     USE_REPLAY_MEMORY = False

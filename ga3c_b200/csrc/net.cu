@@ -59,9 +59,31 @@ struct ga3c_net {
   int64_t global_step = 0;
   int64_t launches = 0;
   int last_batch = 0;
+  // per-kernel CUDA-event timing (ga3c_timing_*): record r uses events 2r (before) and 2r+1 (after)
+  std::vector<cudaEvent_t> tev;
+  std::vector<int> tkid;
+  int tcursor = 0;
 
   int64_t off(int i) const { return params[i].offset; }
 };
+
+enum { K_CONV_FWD = 0, K_DENSE_FWD, K_HEADS, K_DENSE_WGRAD, K_DENSE_DGRAD, K_CONV12_BWD, K_CONV11_WGRAD, K_RMSPROP,
+       K_COUNT };
+static const char* const kKernelNames[K_COUNT] = {"conv_fwd", "dense_fwd", "heads", "dense_wgrad", "dense_dgrad",
+                                                  "conv12_bwd", "conv11_wgrad", "rmsprop"};
+
+// launch one kernel of the path; when timing is enabled bracket it with events on the same stream
+#define LAUNCH(net, kid, st, call)                                                        \
+  do {                                                                                    \
+    const bool _t = !(net)->tev.empty() && (size_t)(2 * (net)->tcursor + 1) < (net)->tev.size(); \
+    if (_t) CK(cudaEventRecord((net)->tev[2 * (net)->tcursor], (st)));                    \
+    CKL(call);                                                                            \
+    if (_t) {                                                                             \
+      CK(cudaEventRecord((net)->tev[2 * (net)->tcursor + 1], (st)));                      \
+      (net)->tkid[(net)->tcursor++] = (kid);                                              \
+    }                                                                                     \
+    (net)->launches++;                                                                    \
+  } while (0)
 
 enum { P_C11W = 0, P_C11B, P_C12W, P_C12B, P_D1W, P_D1B, P_VW, P_VB, P_PW, P_PB, P_COUNT };
 
@@ -167,6 +189,7 @@ extern "C" int ga3c_destroy(ga3c_net* n) {
   if (!n) return 0;
   cudaFree(n->w); cudaFree(n->g); cudaFree(n->ms); cudaFree(n->mom); cudaFree(n->w1_shadow);
   free_workspace(n);
+  for (cudaEvent_t e : n->tev) cudaEventDestroy(e);
   delete n;
   return 0;
 }
@@ -250,13 +273,12 @@ extern "C" int ga3c_predict(ga3c_net* n, const float* x, int32_t batch, float* p
   CK(cudaSetDevice(n->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   const float* w = n->w;
-  CKL(launch_conv_fwd(x, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W), w + n->off(P_C12B), nullptr, n->n2,
-                      batch, n->num_sms, st));
-  CKL(launch_dense_fwd(n->n2, n->w1_shadow, w + n->off(P_D1B), n->d1, batch, st));
+  LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
+                                            w + n->off(P_C12B), nullptr, n->n2, batch, n->num_sms, st));
+  LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd(n->n2, n->w1_shadow, w + n->off(P_D1B), n->d1, batch, st));
   HeadsArgs h = heads_args(n, batch);
   h.p_out = p_out; h.v_out = v_out; h.train = 0;
-  CKL(launch_heads(h, n->num_sms, st));
-  n->launches += 3;
+  LAUNCH(n, K_HEADS, st, launch_heads(h, n->num_sms, st));
   n->last_batch = batch;
   return 0;
 }
@@ -272,20 +294,20 @@ extern "C" int ga3c_forward_backward(ga3c_net* n, const float* x, const float* y
   // small-tensor gradients are accumulated with atomics -> zero them; dense1/w is overwritten by its GEMM
   CK(cudaMemsetAsync(g, 0, (size_t)n->small_floats * 4, st));
   if (loss) CK(cudaMemsetAsync(loss, 0, 4 * sizeof(float), st));
-  CKL(launch_conv_fwd(x, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W), w + n->off(P_C12B), n->n1, n->n2,
-                      batch, n->num_sms, st));
-  CKL(launch_dense_fwd(n->n2, n->w1_shadow, w + n->off(P_D1B), n->d1, batch, st));
+  LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
+                                            w + n->off(P_C12B), n->n1, n->n2, batch, n->num_sms, st));
+  LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd(n->n2, n->w1_shadow, w + n->off(P_D1B), n->d1, batch, st));
   HeadsArgs h = heads_args(n, batch);
   h.yr = yr; h.a = a; h.beta = beta; h.train = 1; h.dd1 = n->dd1; h.loss = loss;
   h.g_wp = g + n->off(P_PW); h.g_bp = g + n->off(P_PB); h.g_wv = g + n->off(P_VW); h.g_bv = g + n->off(P_VB);
   h.g_b1 = g + n->off(P_D1B);
-  CKL(launch_heads(h, n->num_sms, st));
-  CKL(launch_dense_wgrad(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
-  CKL(launch_dense_dgrad(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
-  CKL(launch_conv12_bwd(n->n1, n->dn2, w + n->off(P_C12W), n->dn1, g + n->off(P_C12W), g + n->off(P_C12B), batch,
-                        n->num_sms, st));
-  CKL(launch_conv11_wgrad(x, n->dn1, g + n->off(P_C11W), g + n->off(P_C11B), batch, n->num_sms, st));
-  n->launches += 7;
+  LAUNCH(n, K_HEADS, st, launch_heads(h, n->num_sms, st));
+  LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
+  LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
+  LAUNCH(n, K_CONV12_BWD, st, launch_conv12_bwd(n->n1, n->dn2, w + n->off(P_C12W), n->dn1, g + n->off(P_C12W),
+                                                g + n->off(P_C12B), batch, n->num_sms, st));
+  LAUNCH(n, K_CONV11_WGRAD, st, launch_conv11_wgrad(x, n->dn1, g + n->off(P_C11W), g + n->off(P_C11B), batch,
+                                                    n->num_sms, st));
   n->last_batch = batch;
   return 0;
 }
@@ -297,8 +319,7 @@ extern "C" int ga3c_apply_rmsprop(ga3c_net* n, float lr, void* stream) {
   a.w = n->w; a.ms = n->ms; a.mom = n->mom; a.g = n->g; a.w1_shadow = n->w1_shadow;
   a.n_floats = n->arena_floats; a.w1_offset = n->off(P_D1W); a.w1_count = (int64_t)FLAT * FC;
   a.lr = lr; a.decay = n->cfg.rmsprop_decay; a.momentum = n->cfg.rmsprop_momentum; a.eps = n->cfg.rmsprop_epsilon;
-  CKL(launch_rmsprop(a, (cudaStream_t)stream));
-  n->launches += 1;
+  LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop(a, (cudaStream_t)stream));
   n->global_step += 1;   // opt.minimize(..., global_step=self.global_step), NetworkVP_discrate.py:130
   return 0;
 }
@@ -344,3 +365,37 @@ extern "C" int ga3c_workspace_ptr(ga3c_net* n, int which, void** ptr, int64_t* b
 }
 
 extern "C" int64_t ga3c_launch_count(const ga3c_net* n) { return n ? n->launches : 0; }
+
+extern "C" int ga3c_kernel_count(void) { return K_COUNT; }
+extern "C" const char* ga3c_kernel_name(int kid) { return (kid >= 0 && kid < K_COUNT) ? kKernelNames[kid] : nullptr; }
+
+static void timing_free(ga3c_net* n) {
+  for (cudaEvent_t e : n->tev) cudaEventDestroy(e);
+  n->tev.clear(); n->tkid.clear(); n->tcursor = 0;
+}
+
+extern "C" int ga3c_timing_enable(ga3c_net* n, int32_t max_records) {
+  if (!n || max_records < 0) return fail_msg("ga3c_timing_enable: bad argument");
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaDeviceSynchronize());
+  timing_free(n);
+  n->tev.resize((size_t)2 * max_records);
+  n->tkid.assign((size_t)max_records, 0);
+  for (auto& e : n->tev) CK(cudaEventCreate(&e));
+  return 0;
+}
+
+extern "C" int ga3c_timing_collect(ga3c_net* n, double* total_ms, int64_t* counts, int32_t n_kernels) {
+  if (!n || !total_ms || !counts || n_kernels < K_COUNT) return fail_msg("ga3c_timing_collect: bad argument");
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaDeviceSynchronize());
+  for (int k = 0; k < n_kernels; ++k) { total_ms[k] = 0.0; counts[k] = 0; }
+  for (int r = 0; r < n->tcursor; ++r) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, n->tev[2 * r], n->tev[2 * r + 1]));
+    total_ms[n->tkid[r]] += ms;
+    counts[n->tkid[r]] += 1;
+  }
+  n->tcursor = 0;
+  return 0;
+}

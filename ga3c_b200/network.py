@@ -367,6 +367,17 @@ class Network:
     def launch_count(self) -> int:
         return int(self._lib.ga3c_launch_count(self._h))
 
+    def kernel_timing(self, max_records: int):
+        """Bracket every kernel of the path with CUDA events on its launch stream (0 = off)."""
+        _capi.check(self._lib.ga3c_timing_enable(self._h, int(max_records)), "ga3c_timing_enable")
+
+    def kernel_times(self) -> dict:
+        """{kernel name: (total ms, launches)} since the last call; synchronises the device."""
+        n = self._lib.ga3c_kernel_count()
+        tot, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+        _capi.check(self._lib.ga3c_timing_collect(self._h, tot, cnt, n), "ga3c_timing_collect")
+        return {self._lib.ga3c_kernel_name(k).decode(): (tot[k], cnt[k]) for k in range(n)}
+
     def workspace(self, which: int) -> np.ndarray:
         """Activation workspace of the last call as float32 numpy (bf16 buffers are widened)."""
         ptr, nbytes = C.c_void_p(), C.c_int64()

@@ -115,6 +115,18 @@ int ga3c_workspace_ptr(ga3c_net* net, int which, void** ptr_dev, int64_t* bytes)
 /* number of kernels this library has launched on this handle since creation */
 int64_t ga3c_launch_count(const ga3c_net* net);
 
+
+/* ---- per-kernel device timing (bench.py's roofline leg) -------------------------------------
+ * ga3c_timing_enable(net, R) pre-creates events for R kernel records (R = 0 switches timing off).
+ * While enabled, every kernel the hot path launches is bracketed by cudaEventRecord on the launch
+ * stream -- no synchronisation is added.  ga3c_timing_collect synchronises the device, sums the
+ * durations per kernel id (ga3c_kernel_name(id), id < ga3c_kernel_count()) and rewinds the record
+ * cursor; launches beyond R records are simply not timed. */
+int         ga3c_kernel_count(void);
+const char* ga3c_kernel_name(int kernel_id);
+int ga3c_timing_enable(ga3c_net* net, int32_t max_records);
+int ga3c_timing_collect(ga3c_net* net, double* total_ms, int64_t* counts, int32_t n_kernels);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,465 @@
+"""GPU parity tests (`-m gpu`): the CUDA path, called through the C-ABI library, against the oracle.
+
+Tolerances (calibrated on B200 and frozen here).  The CUDA path rounds operands to
+bf16 at fixed points (x, conv weights, n1, n2, w1, dd1, dn2, dn1) and accumulates in fp32; the
+oracle is run in its `quant='bf16'` mode, which rounds at the same points and accumulates in fp64.
+Residual differences are fp32-vs-fp64 accumulation order, which now and then flips a bf16 rounding
+(1 ulp = 2^-8 relative) of a stored activation:
+    p        |d| <= 2e-5          v        |d| <= 2e-4
+    stored bf16 activations      |d| <= 2^-7 * max|ref|  and  <= 1% of elements off by > 1e-5 * max|ref|
+    loss sums                    rel <= 1e-4
+    gradients                    |d| <= 2e-3 * max|ref| per tensor
+    weights after RMSProp        |d| <= 2e-6   (lr 3e-4 scales the gradient error)
+Against the un-quantised fp64 oracle (the irreducible bf16 gap): |dp| <= 1e-2, |dv| <= 2e-2.
+Integer / fp64 work (returns, sampling) is bit-exact.
+"""
+import json
+import os
+import threading
+import queue
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as onp
+from _parity import make_case, layer_report, err
+
+pytestmark = pytest.mark.gpu
+
+TOL_P, TOL_V = 2e-5, 2e-4
+TOL_ACT_REL = 2.0 ** -7
+TOL_LOSS_REL = 1e-4
+TOL_GRAD_REL = 2e-3
+TOL_W_ABS = 2e-6
+
+
+@pytest.fixture(scope="module")
+def ga3c():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; there is no CPU fallback")
+    import ga3c_b200
+    return ga3c_b200
+
+
+def check_report(rep):
+    assert rep["p"][0] <= TOL_P and rep["v"][0] <= TOL_V, rep
+    for k in ("n1", "n2", "dd1", "dn2", "dn1"):
+        assert rep[k][1] <= TOL_ACT_REL, (k, rep[k])
+    assert rep["d1"][1] <= 1e-3, rep["d1"]
+    for k, (d, r) in rep.items():
+        if k.startswith("loss/"):
+            assert r <= TOL_LOSS_REL or d <= 1e-5, (k, d, r)
+        if k.startswith("grad/"):
+            assert r <= TOL_GRAD_REL, (k, d, r)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("batch", [1, 2, 7, 32, 33, 128, 300])
+def test_layers_and_gradients_match_oracle(ga3c, batch):
+    """Every stored activation, all 10 gradients and the 4 loss sums, at ragged and full batch sizes
+    (1, odd, one CTA chunk +1, PREDICTION_BATCH_SIZE, more than 2 x 148 CTAs)."""
+    params, x, y_r, a = make_case(batch)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=max(batch, 16))
+    check_report(layer_report(net, params, x, y_r, a))
+
+
+@pytest.mark.parametrize("num_actions", [1, 2, 18])
+def test_num_actions_range(ga3c, num_actions):
+    params, x, y_r, a = make_case(9, num_actions=num_actions, seed=3)
+    net = ga3c.Network("gpu:0", "t", num_actions, max_batch=16)
+    check_report(layer_report(net, params, x, y_r, a))
+
+
+def test_min_policy_and_active_epsilon_floor(ga3c):
+    """MIN_POLICY mixing and an epsilon floor large enough that both mask branches of A.4 fire."""
+    class Cfg(ga3c.Config):
+        MIN_POLICY = 0.02
+        LOG_EPSILON = 0.12
+    params, x, y_r, a = make_case(24, seed=11)
+    params["logits_p/w:0"] *= 8.0           # spread the policy so some p_ij fall under the floor
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=32, config=Cfg)
+    rep = layer_report(net, params, x, y_r, a, beta=0.05, log_eps=0.12, min_policy=0.02)
+    p, _ = onp.forward(params, x, quant="bf16", min_policy=0.02)
+    assert (p < 0.12).any() and (p >= 0.12).any()
+    check_report(rep)
+
+
+def test_golden_network_b4(ga3c, golden_dir):
+    """The committed B=4 fixture (tests/golden/network_b4.npz, oracle/gen_golden.py)."""
+    g = np.load(os.path.join(golden_dir, "network_b4.npz"))
+    params, x, y_r, a = make_case(4)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=16)
+    net.set_variables(params)
+    p, v = net.predict_p_and_v(x)
+    assert np.abs(p - g["bf16_p"]).max() <= TOL_P and np.abs(v - g["bf16_v"]).max() <= TOL_V
+    assert np.abs(p - g["f64_p"]).max() <= 1e-2 and np.abs(v - g["f64_v"]).max() <= 2e-2     # bf16 gap
+    l = net.losses(x, y_r, a)
+    got = np.array([l[k] for k in ("cost_p_1", "cost_p_2", "cost_p", "cost_v", "cost_all")])
+    assert np.allclose(got, g["bf16_losses"], rtol=TOL_LOSS_REL, atol=1e-5)
+    grads = net.get_gradients()
+    for k in ("conv11/b:0", "conv12/b:0", "dense1/b:0", "logits_p/w:0", "logits_v/w:0", "conv11/w:0"):
+        ref = g["bf16_grad_" + k]
+        assert err(grads[k], ref)[1] <= TOL_GRAD_REL, k
+
+
+def test_prediction_is_fp32_softmax_accepted_by_numpy_choice(ga3c):
+    """np.random.choice rejects p whose sum is off by > ~3.45e-4; ours is fp32 softmax."""
+    params, x, _, _ = make_case(64)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=64)
+    net.set_variables(params)
+    p, v = net.predict_p_and_v(x)
+    assert p.dtype == np.float32 and v.dtype == np.float32 and p.shape == (64, 6) and v.shape == (64,)
+    assert np.abs(p.astype(np.float64).sum(axis=1) - 1).max() < 1e-6
+    rs = np.random.RandomState(0)
+    for i in range(64):
+        rs.choice(6, p=p[i])               # raises ValueError if the row is not a distribution
+
+
+def test_sampling_flip_rate_vs_fp64_oracle(ga3c):
+    """Same uniforms, p from the CUDA bf16 trunk vs p from the fp64 oracle: the sampled action differs
+    only when u lands within |dp| of a CDF edge."""
+    params, x, _, _ = make_case(256, seed=21)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=256)
+    net.set_variables(params)
+    p, _ = net.predict_p_and_v(x)
+    p64, _ = onp.forward(params, x)
+    pq, _ = onp.forward(params, x, quant="bf16")
+    u = np.random.default_rng(5).random(256)
+    assert np.array_equal(onp.select_actions(p, u), onp.select_actions(pq.astype(np.float32), u))
+    flips = int((onp.select_actions(p, u) != onp.select_actions(p64, u)).sum())
+    assert flips <= 6, flips               # expected ~ A * |dp| * B ~ 6 * 2e-3 * 256 = 3
+
+
+# ------------------------------------------------------------------------------------------------
+def test_train_step_weights_and_slots(ga3c):
+    params, x, y_r, a = make_case(48, seed=2)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=64)
+    net.set_variables(params)
+    net.learning_rate, net.beta = 3e-4, 0.01
+    ms, mom = onp.rmsprop_init(params)
+    l_ref, g_ref, p2, ms2, _ = onp.train_step(params, ms, mom, x, y_r.astype(np.float64), a, lr=3e-4, beta=0.01,
+                                              quant="bf16")
+    losses = net.train(x, y_r.astype(np.float64), a, None, None, 0, fetch_losses=True)   # y_r arrives fp64 (A11)
+    assert abs(losses["cost_all"] - l_ref["cost_all"]) <= TOL_LOSS_REL * abs(l_ref["cost_all"])
+    got = net.get_variables()
+    got_ms, got_mom = net.get_slots()
+    for k in got:
+        assert np.abs(got[k] - p2[k]).max() <= TOL_W_ABS, k
+        assert err(got_ms[k] - 0.99, ms2[k] - 0.99)[1] <= 2 * TOL_GRAD_REL, k     # ms = .99 + .01 g^2
+        assert not np.array_equal(got[k], params[k]), k                            # every variable moved
+        assert np.all(got_mom[k] == 0), k                                          # mu = 0: slot untouched
+    assert net.get_global_step() == 1
+
+
+def test_rmsprop_kernel_alone_is_fp32_exact(ga3c):
+    """ga3c_apply_rmsprop on injected gradients vs the fp32 numpy formula (A.5): <= 1 ulp."""
+    import ctypes as C
+    import torch
+    from ga3c_b200 import _capi
+    params, _, _, _ = make_case(1)
+    class Cfg(ga3c.Config):
+        RMSPROP_MOMENTUM = 0.5
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=16, config=Cfg)
+    net.set_variables(params)
+    rng = np.random.default_rng(0)
+    n = net._arena_floats
+    g = (rng.standard_normal(n) * 3).astype(np.float32)
+    ms0 = rng.uniform(0.5, 2, n).astype(np.float32)
+    mom0 = (rng.standard_normal(n) * 1e-3).astype(np.float32)
+    w0 = net._download(0)
+    for which, arr in ((1, g), (2, ms0), (3, mom0)):
+        net._upload(which, arr)
+    _capi.check(net._lib.ga3c_apply_rmsprop(net._h, C.c_float(1e-3), None), "rmsprop")
+    torch.cuda.synchronize()
+    f = np.float32
+    ms1 = f(0.99) * ms0 + (f(1) - f(0.99)) * g * g
+    mom1 = f(0.5) * mom0 + f(1e-3) * g / np.sqrt(ms1 + f(0.1))
+    w1 = w0 - mom1
+    assert np.allclose(net._download(2), ms1, rtol=3e-7, atol=0)
+    assert np.allclose(net._download(3), mom1, rtol=1e-6, atol=1e-12)
+    assert np.allclose(net._download(0), w1, rtol=0, atol=1e-7)
+    # the bf16 shadow of dense1/w follows the update: the next forward uses the new weights
+    off, shape = net._table["dense1/w:0"]
+    x = onp.synth_frames(rng, 4)
+    p, v = net.predict_p_and_v(x)
+    pr, vr = onp.forward(net.get_variables(), x, quant="bf16")
+    assert np.abs(p - pr).max() <= TOL_P and np.abs(v - vr).max() <= TOL_V
+
+
+def test_five_step_trajectory(ga3c):
+    """Five consecutive train steps on fresh batches track the oracle's trajectory."""
+    rng = np.random.default_rng(77)
+    params = onp.init_params(rng, 6)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=32)
+    net.set_variables(params)
+    ms, mom = onp.rmsprop_init(params)
+    ref = params
+    for step in range(5):
+        x = onp.synth_frames(rng, 16)
+        y_r, a = onp.synth_targets(rng, 16)
+        net.train(x, y_r, a, x, np.zeros(16, bool), 0)
+        _, _, ref, ms, mom = onp.train_step(ref, ms, mom, x, y_r, a, lr=net.learning_rate, beta=net.beta, quant="bf16")
+        ref = {k: v.astype(np.float32) for k, v in ref.items()}
+    got = net.get_variables()
+    for k in got:
+        assert np.abs(got[k] - ref[k]).max() <= 5 * TOL_W_ABS, k
+    assert net.get_global_step() == 5
+
+
+def test_learning_rate_and_beta_are_read_per_call(ga3c):
+    """Server.py:174-175 rewrites model.learning_rate / model.beta while training runs."""
+    params, x, y_r, a = make_case(8)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=16)
+    net.set_variables(params)
+    net.learning_rate = 0.0
+    net.train(x, y_r, a, None, None, 0)
+    w = net.get_variables()
+    assert all(np.array_equal(w[k], params[k]) for k in w)          # lr = 0: weights untouched
+    net.beta = 0.5
+    l = net.losses(x, y_r, a)
+    lr_ = onp.loss_and_grads(params, x, y_r, a, beta=0.5, quant="bf16")[0]
+    assert abs(l["cost_p_2"] - lr_["cost_p_2"]) <= TOL_LOSS_REL * abs(lr_["cost_p_2"])
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full sizes
+def test_predict_batch_4096_is_row_independent(ga3c):
+    """Config 2's largest batch: every row of a 4096-batch equals the same frame predicted in a
+    batch of 128 (bit-exact: no cross-row arithmetic), and a sample of rows matches the oracle."""
+    rng = np.random.default_rng(4096)
+    params = onp.init_params(rng, 6)
+    x = onp.synth_frames(rng, 4096)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=4096)
+    net.set_variables(params)
+    p, v = net.predict_p_and_v(x)
+    for lo in (0, 1920, 3968):
+        p2, v2 = net.predict_p_and_v(x[lo:lo + 128])
+        assert np.array_equal(p[lo:lo + 128], p2) and np.array_equal(v[lo:lo + 128], v2)
+    idx = rng.choice(4096, 24, replace=False)
+    pr, vr = onp.forward(params, x[idx], quant="bf16")
+    assert np.abs(p[idx] - pr).max() <= TOL_P and np.abs(v[idx] - vr).max() <= TOL_V
+
+
+def test_gradients_are_additive_over_batch_shards_b1024(ga3c):
+    """Config 3 (B=1024): every loss term is a SUM over the batch (NetworkVP_discrate.py:61,:83-85), so
+    grad(full batch) = sum of grad(shards) -- the identity the data-parallel allreduce relies on."""
+    params, x, y_r, a = make_case(1024, seed=8)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=1024)
+    net.set_variables(params)
+    full_l = net.losses(x, y_r, a)
+    full = net.get_gradients()
+    acc = {k: np.zeros_like(v, dtype=np.float64) for k, v in full.items()}
+    acc_l = 0.0
+    for lo in range(0, 1024, 128):
+        acc_l += net.losses(x[lo:lo + 128], y_r[lo:lo + 128], a[lo:lo + 128])["cost_all"]
+        for k, v in net.get_gradients().items():
+            acc[k] += v
+    assert abs(acc_l - full_l["cost_all"]) <= 1e-5 * abs(full_l["cost_all"])
+    for k in full:
+        assert err(full[k], acc[k])[1] <= 2e-4, k      # fp32 accumulation order only
+    # and a 64-row shard against the oracle
+    _, g_ref = onp.loss_and_grads(params, x[:64], y_r[:64], a[:64], quant="bf16")
+    net.losses(x[:64], y_r[:64], a[:64])
+    got = net.get_gradients()
+    for k in got:
+        assert err(got[k], g_ref[k])[1] <= TOL_GRAD_REL, k
+
+
+def test_workspace_grows_for_unbounded_train_batches(ga3c):
+    """ThreadTrainer concatenates agent batches without bound (ThreadTrainer.py:48-59)."""
+    params, x, y_r, a = make_case(40)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=16)
+    net.set_variables(params)
+    p, v = net.predict_p_and_v(x)
+    pr, vr = onp.forward(params, x, quant="bf16")
+    assert np.abs(p - pr).max() <= TOL_P and np.abs(v - vr).max() <= TOL_V
+    assert net.train(x, y_r, a, None, None, 0) is None
+
+
+# ------------------------------------------------------------------------------------------------
+# returns and sampling: bit-exact against outputs of the REAL reference (tests/golden)
+def test_returns_golden_bit_exact_on_device(ga3c, golden_dir):
+    from ga3c_b200.agent_ops import accumulate_rewards
+    cases = json.load(open(os.path.join(golden_dir, "returns.json")))
+    by_cfg = {}
+    for c in cases:
+        f = c["flags"]
+        by_cfg.setdefault((f["DISCOUNTING"], f["USE_INTERMEDIATE_REWARD"], f["REWARD_CLIPPING"], c["gamma"]), []).append(c)
+    for (disc, inter, clip, gamma), group in by_cfg.items():
+        class Cfg(ga3c.Config):
+            DISCOUNTING, USE_INTERMEDIATE_REWARD, REWARD_CLIPPING = disc, inter, clip
+        outs = accumulate_rewards([c["rewards"] for c in group], gamma, [c["terminal"] for c in group], config=Cfg)
+        for c, o in zip(group, outs):
+            assert [float(r).hex() for r in o] == c["out"]
+
+
+def test_returns_ragged_and_empty_segments(ga3c):
+    from ga3c_b200.agent_ops import accumulate_rewards
+    rng = np.random.default_rng(3)
+    lens = [0, 1, 2, 5, 0, 1000, 6, 1]               # TIME_MAX upstream 5, fork 1000
+    segs = [list(rng.uniform(-2, 2, n)) for n in lens]
+    term = [s[-1] if s else 0.0 for s in segs]
+    outs = accumulate_rewards(segs, 0.99, term)
+    for s, t, o in zip(segs, term, outs):
+        assert list(o) == onp.accumulate_rewards(s, 0.99, t)
+    outs = accumulate_rewards(segs, 0.99, term, nstep=True)
+    for s, t, o in zip(segs, term, outs):
+        assert list(o[:-1]) == onp.nstep_returns(s, 0.99, t) if s else len(o) == 0
+    assert accumulate_rewards([], 0.99, []) == []
+
+
+def test_returns_256_agents_t1000(ga3c):
+    """SURVEY 8d returns-kernel input: 256 agents x T=1000, closed form R_t = gamma^(n-1-t) r_last."""
+    from ga3c_b200.agent_ops import accumulate_rewards
+    rng = np.random.default_rng(9)
+    segs = [list(rng.uniform(-1, 1, 1000)) for _ in range(256)]
+    outs = accumulate_rewards(segs, 0.99, [s[-1] for s in segs])
+    for i in (0, 100, 255):
+        assert list(outs[i]) == onp.accumulate_rewards(segs[i], 0.99, segs[i][-1])
+
+
+def test_sampling_golden_bit_exact_on_device(ga3c, golden_dir):
+    from ga3c_b200.agent_ops import select_actions
+    g = np.load(os.path.join(golden_dir, "sampling.npz"))
+    assert np.array_equal(select_actions(g["p"], g["u"]), g["chosen"])
+    assert select_actions(np.zeros((0, 6), np.float32), np.zeros(0)).shape == (0,)
+    # CDF-edge cases: u exactly on an edge goes right (side='right'); last bin closed by cdf[-1] = 1
+    p = np.array([[0.25, 0.25, 0.5], [0.5, 0.5, 0.0], [1.0, 0.0, 0.0]], dtype=np.float32)
+    u = np.array([0.25, 0.5, 0.999999], dtype=np.float64)
+    assert np.array_equal(select_actions(p, u), onp.select_actions(p, u))
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's thread / queue contracts on top of the CUDA Network
+class _Agent:
+    def __init__(self):
+        self.wait_q = queue.Queue(maxsize=1)
+
+
+class _Server:
+    def __init__(self, model, n_agents):
+        self.model = model
+        self.agents = [_Agent() for _ in range(n_agents)]
+        self.training_q = queue.Queue(maxsize=100)
+        self.trained = []
+
+    def train_model(self, x_, r_, a_, x2_, done_, trainer_id):       # Server.py:141-150
+        self.model.train(x_, r_, a_, x2_, done_, trainer_id)
+        self.trained.append(x_.shape[0])
+
+
+def test_predictor_and_trainer_threads_queue_contract(ga3c):
+    params, x, y_r, a = make_case(40, seed=5)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=128)
+    net.set_variables(params)
+    srv = _Server(net, 40)
+    pq = queue.Queue(maxsize=100)
+    pred = ga3c.ThreadPredictor(srv, 0, onp.STATE_DIM, pq)
+    pred.start()
+    for i in range(40):
+        pq.put((i, x[i]))                                  # ProcessAgent.py:104
+    pr, vr = onp.forward(params, x, quant="bf16")
+    for i in range(40):
+        p_i, v_i = srv.agents[i].wait_q.get(timeout=60)   # ProcessAgent.py:106
+        assert p_i.shape == (6,) and np.abs(p_i - pr[i]).max() <= TOL_P and abs(v_i - vr[i]) <= TOL_V
+    pred.exit_flag = True
+
+    class Cfg(ga3c.Config):
+        TRAINING_MIN_BATCH_SIZE = 20
+    tr = ga3c.ThreadTrainer(srv, 0, config=Cfg)
+    tr.start()
+    for lo in range(0, 40, 8):                             # ProcessAgent.py:175 items (x_, r_, a_, x2_, done_)
+        sl = slice(lo, lo + 8)
+        srv.training_q.put((x[sl], y_r[sl].astype(np.float64), a[sl], x[sl], np.zeros(8, bool)))
+    import time
+    t0 = time.time()
+    while sum(srv.trained) < 24 and time.time() - t0 < 60:
+        time.sleep(0.01)
+    tr.exit_flag = True
+    assert srv.trained[0] == 24                            # 8+8+8 > 20: first batch that EXCEEDS the minimum
+    assert net.get_global_step() >= 1
+
+
+def test_concurrent_predict_and_train_threads(ga3c):
+    """Server.py:123-134: predictors and trainers call into one model concurrently, with no locks."""
+    params, x, y_r, a = make_case(32, seed=6)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=32)
+    net.set_variables(params)
+    net.learning_rate = 0.0                                 # keep weights fixed so predictions are checkable
+    pr, vr = onp.forward(params, x, quant="bf16")
+    errs = []
+
+    def predictor():
+        try:
+            for _ in range(30):
+                p, v = net.predict_p_and_v(x)
+                assert np.abs(p - pr).max() <= TOL_P and np.abs(v - vr).max() <= TOL_V
+        except Exception as e:      # noqa
+            errs.append(e)
+
+    def trainer():
+        try:
+            for _ in range(30):
+                net.train(x, y_r, a, None, None, 0)
+        except Exception as e:      # noqa
+            errs.append(e)
+
+    ts = [threading.Thread(target=f) for f in (predictor, predictor, trainer, trainer)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    assert net.get_global_step() == 60
+
+
+# ------------------------------------------------------------------------------------------------
+def test_checkpoint_round_trip(ga3c, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    params, x, y_r, a = make_case(8)
+    net = ga3c.Network("gpu:0", "ckpt", 6, max_batch=16)
+    net.set_variables(params)
+    net.train(x, y_r, a, None, None, 0)
+    net.save(42)
+    want = net.get_variables()
+    want_ms, _ = net.get_slots()
+    net2 = ga3c.Network("gpu:0", "ckpt", 6, max_batch=16)
+    assert net2.load() == 42
+    got = net2.get_variables()
+    got_ms, _ = net2.get_slots()
+    assert all(np.array_equal(got[k], want[k]) and np.array_equal(got_ms[k], want_ms[k]) for k in want)
+    assert net2.get_global_step() == 1
+    p1, v1 = net.predict_p_and_v(x)
+    p2, v2 = net2.predict_p_and_v(x)
+    assert np.array_equal(p1, p2) and np.array_equal(v1, v2)
+
+
+def test_variable_introspection(ga3c):
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=16, seed=1)
+    assert net.get_variables_names() == list(onp.PARAM_NAMES)          # TF creation order
+    shapes = onp.param_shapes(6)
+    for k in onp.PARAM_NAMES:
+        v = net.get_variable_value(k)
+        assert v.shape == shapes[k] and v.dtype == np.float32
+    w = net.get_variable_value("dense1/w:0")
+    assert np.abs(w).max() <= 1 / np.sqrt(3872) and w.std() > 0         # U(+-1/sqrt(fan_in))
+    assert net.get_global_step() == 0
+
+
+def test_errors_are_raised_not_swallowed(ga3c):
+    from ga3c_b200 import _capi
+    import ctypes as C
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=16)
+    with pytest.raises(ValueError):
+        net.predict_p_and_v(np.zeros((2, 100), np.float32))
+    with pytest.raises(ValueError):
+        ga3c.Network("gpu:0", "t", 6, state_dim=4)
+    with pytest.raises(ValueError):
+        ga3c.Network("cpu:0", "t", 6)
+    with pytest.raises(_capi.Ga3cError):
+        ga3c.Network("gpu:0", "t", 19)                      # num_actions out of range
+    rc = net._lib.ga3c_predict(net._h, None, 4, None, None, None)
+    assert rc != 0 and b"null buffer" in net._lib.ga3c_last_error()
+    rc = net._lib.ga3c_predict(net._h, C.c_void_p(1), 10 ** 6, C.c_void_p(1), C.c_void_p(1), None)
+    assert rc != 0 and b"batch" in net._lib.ga3c_last_error()
+    p, v = net.predict_p_and_v(np.zeros((0, onp.STATE_DIM), np.float32))
+    assert p.shape == (0, 6) and v.shape == (0,)

@@ -1,0 +1,226 @@
+"""CPU tests (`-m "not gpu"`) of the boundary and the host logic: the C-ABI library loads and exports
+every symbol include/ga3c_b200.h declares (no compute calls), the batching threads keep the
+reference's queue contracts, and -- where /root/reference exists -- behave like the reference's
+own ThreadPredictor / ThreadTrainer on the same queue traffic."""
+import ctypes
+import os
+import queue
+import re
+import sys
+import time
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, REFERENCE
+
+
+# ---------------------------------------------------------------- C ABI
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "ga3c_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ga3c_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    from ga3c_b200 import _capi
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/ga3c_b200.h but not exported"
+    assert sorted(_capi.SIGNATURES) == syms               # the ctypes table covers the header exactly
+    assert _capi.load().ga3c_abi_version() >= 1
+
+
+def test_header_compiles_as_plain_c(tmp_path):
+    """The boundary is plain C: no C++ / torch types in the signatures."""
+    import subprocess
+    c = tmp_path / "t.c"
+    c.write_text('#include "ga3c_b200.h"\nint main(void){ga3c_config c; (void)c; return sizeof(ga3c_config)==32?0:1;}\n')
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c), "-c", "-o",
+                    str(exe)], check=True)
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a GPU constructing a Network must fail loudly, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import ga3c_b200
+    from ga3c_b200 import _capi
+    with pytest.raises(_capi.Ga3cError):
+        ga3c_b200.Network("gpu:0", "t", 6)
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "ga3c_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read(), f
+
+
+def test_parse_device():
+    from ga3c_b200.network import _parse_device
+    assert _parse_device("gpu:0") == 0 and _parse_device("/gpu:3") == 3 and _parse_device("cuda:1") == 1
+    assert _parse_device("GPU") == 0 and _parse_device(2) == 2
+    with pytest.raises(ValueError):
+        _parse_device("cpu:0")
+
+
+def test_config_matches_reference_defaults():
+    """Every knob the path reads has the reference's default (Config.py)."""
+    from ga3c_b200 import Config
+    if not os.path.isdir(REFERENCE):
+        pytest.skip("reference not present")
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REFERENCE)
+    try:
+        import Config as RC
+    finally:
+        sys.path.remove(REFERENCE)
+    ref = RC.Config
+    skip = {"PREDICTORS", "TRAINERS", "AGENTS"}            # machine-dependent in the fork
+    for k, v in vars(Config).items():
+        if k.startswith("_") or k in skip or not hasattr(ref, k):
+            continue
+        assert getattr(ref, k) == v, k
+
+
+# ---------------------------------------------------------------- batching threads with a fake model
+class FakeModel:
+    """Deterministic stand-in so the thread logic is testable without a GPU: p row = softmax-free
+    function of the state, v = state mean."""
+    def __init__(self, a=6):
+        self.a = a
+        self.calls = []
+        self.trained = []
+
+    def predict_p_and_v(self, x):
+        self.calls.append(x.shape[0])
+        p = np.tile(np.arange(self.a, dtype=np.float32), (x.shape[0], 1)) + x[:, :1]
+        return [p, x.mean(axis=1)]
+
+    def train(self, x, r, a, x2, done, tid):
+        self.trained.append((x.copy(), np.asarray(r).copy(), a.copy(), tid))
+
+
+class Agent:
+    def __init__(self):
+        self.wait_q = queue.Queue(maxsize=1)
+
+
+class Server:
+    def __init__(self, n):
+        self.model = FakeModel()
+        self.agents = [Agent() for _ in range(n)]
+        self.training_q = queue.Queue(maxsize=100)
+
+    def train_model(self, x_, r_, a_, x2_, done_, trainer_id):
+        self.model.train(x_, r_, a_, x2_, done_, trainer_id)
+
+
+def _drive_predictor(cls, **kw):
+    srv = Server(50)
+    pq = queue.Queue(maxsize=100)
+    rng = np.random.default_rng(0)
+    states = rng.standard_normal((50, 12)).astype(np.float32)
+    for i in range(50):
+        pq.put((i, states[i]))
+    th = cls(srv, 0, 12, pq, **kw) if kw else cls(srv, 0, 12, pq)
+    th.daemon = True
+    th.start()
+    out = [srv.agents[i].wait_q.get(timeout=20) for i in range(50)]
+    th.exit_flag = True
+    return states, out, srv.model.calls
+
+
+def test_thread_predictor_contract():
+    from ga3c_b200 import ThreadPredictor
+    states, out, calls = _drive_predictor(ThreadPredictor)
+    assert sum(calls) == 50 and max(calls) <= 128
+    for i, (p, v) in enumerate(out):
+        assert np.array_equal(p, np.arange(6, dtype=np.float32) + states[i, 0]) and v == states[i].mean()
+
+
+def test_thread_predictor_respects_batch_cap():
+    from ga3c_b200 import ThreadPredictor, Config
+
+    class Cfg(Config):
+        PREDICTION_BATCH_SIZE = 16
+    _, _, calls = _drive_predictor(ThreadPredictor, config=Cfg)
+    assert max(calls) <= 16 and sum(calls) == 50
+
+
+@pytest.mark.reference
+def test_thread_predictor_matches_reference_class():
+    """The reference's own ThreadPredictor (ThreadPredictor.py:34-66), unmodified, on the same traffic."""
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REFERENCE)
+    try:
+        import ThreadPredictor as RTP
+    finally:
+        sys.path.remove(REFERENCE)
+    from ga3c_b200 import ThreadPredictor
+    s1, o1, _ = _drive_predictor(RTP.ThreadPredictor)
+    s2, o2, _ = _drive_predictor(ThreadPredictor)
+    for (p1, v1), (p2, v2) in zip(o1, o2):
+        assert np.array_equal(p1, p2) and v1 == v2
+
+
+def _drive_trainer(cls, min_batch, **kw):
+    srv = Server(1)
+    rng = np.random.default_rng(1)
+    items = []
+    for n in (5, 3, 7, 2, 9, 4):
+        items.append((rng.standard_normal((n, 12)).astype(np.float32), rng.standard_normal(n),
+                      np.eye(6, dtype=np.float32)[rng.integers(0, 6, n)], rng.standard_normal((n, 12)).astype(np.float32),
+                      np.zeros(n, bool)))
+    for it in items:
+        srv.training_q.put(it)
+    th = cls(srv, 3, **kw) if kw else cls(srv, 3)
+    th.daemon = True
+    th.start()
+    t0 = time.time()
+    while not srv.training_q.empty() and time.time() - t0 < 20:
+        time.sleep(0.01)
+    time.sleep(0.2)
+    th.exit_flag = True
+    return items, srv.model.trained
+
+
+def test_thread_trainer_contract_min_batch_zero():
+    from ga3c_b200 import ThreadTrainer
+    items, trained = _drive_trainer(ThreadTrainer, 0)
+    assert [t[0].shape[0] for t in trained] == [5, 3, 7, 2, 9, 4]           # one agent batch per step
+    assert all(t[3] == 3 for t in trained)
+    assert np.array_equal(trained[2][0], items[2][0]) and trained[2][1].dtype == np.float64
+
+
+def test_thread_trainer_concatenates_until_exceeding_min():
+    from ga3c_b200 import ThreadTrainer, Config
+
+    class Cfg(Config):
+        TRAINING_MIN_BATCH_SIZE = 8
+    items, trained = _drive_trainer(ThreadTrainer, 8, config=Cfg)
+    assert [t[0].shape[0] for t in trained] == [15, 11]                     # 5+3+7 > 8 ; 2+9 > 8 ; 4 waits
+    assert np.array_equal(trained[0][0], np.concatenate([items[0][0], items[1][0], items[2][0]]))
+    assert np.array_equal(trained[1][2], np.concatenate([items[3][2], items[4][2]]))
+
+
+@pytest.mark.reference
+def test_thread_trainer_matches_reference_class():
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REFERENCE)
+    try:
+        import ThreadTrainer as RTT
+    finally:
+        sys.path.remove(REFERENCE)
+    from ga3c_b200 import ThreadTrainer
+    _, t1 = _drive_trainer(RTT.ThreadTrainer, 0)
+    _, t2 = _drive_trainer(ThreadTrainer, 0)
+    assert len(t1) == len(t2)
+    for a, b in zip(t1, t2):
+        assert all(np.array_equal(a[k], b[k]) for k in range(3)) and a[3] == b[3]
