@@ -75,13 +75,13 @@ def test_min_policy_and_active_epsilon_floor(ga3c):
     """MIN_POLICY mixing and an epsilon floor large enough that both mask branches of A.4 fire."""
     class Cfg(ga3c.Config):
         MIN_POLICY = 0.02
-        LOG_EPSILON = 0.12
+        LOG_EPSILON = 0.16
     params, x, y_r, a = make_case(24, seed=11)
     params["logits_p/w:0"] *= 8.0           # spread the policy so some p_ij fall under the floor
     net = ga3c.Network("gpu:0", "t", 6, max_batch=32, config=Cfg)
-    rep = layer_report(net, params, x, y_r, a, beta=0.05, log_eps=0.12, min_policy=0.02)
+    rep = layer_report(net, params, x, y_r, a, beta=0.05, log_eps=0.16, min_policy=0.02)
     p, _ = onp.forward(params, x, quant="bf16", min_policy=0.02)
-    assert (p < 0.12).any() and (p >= 0.12).any()
+    assert (p < 0.16).any() and (p >= 0.16).any()
     check_report(rep)
 
 
