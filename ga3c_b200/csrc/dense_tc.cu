@@ -1,0 +1,299 @@
+// dense1 GEMMs on the 5th-generation tensor cores: tcgen05.mma with TMEM accumulators, operands
+// staged in shared memory by TMA (cp.async.bulk.tensor, SWIZZLE_128B), mbarrier pipeline, warp roles.
+//
+// Reference ops: dense1 = relu(flat @ w + b) (NetworkDNav.py:90, dense_layer :256-269) and the two
+// matmul gradients TF autodiff derives from it (opt.minimize, NetworkVP_discrate.py:130).
+//
+//   fwd  : part[s][B,256]  = n2[B,3872]    x w1[3872,256]           (A K-major,  B MN-major)  split-K
+//   dgrad: dn2[B,3872]     = dd1[B,256]    x w1[3872,256]^T  ⊙ n2>0 (A K-major,  B K-major)
+//   wgrad: g_w1[3872,256]  = n2[B,3872]^T  x dd1[B,256]             (A MN-major, B MN-major)
+//
+// One output tile (128 x BN, fp32 in BN TMEM columns) per CTA.  192 threads:
+//   warp 0   TMA producer (one elected lane)
+//   warp 1   TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma.cta_group::1.kind::f16)
+//   warp 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global
+// K is consumed in blocks of 64 (one 128-byte swizzle row); a k-block is 4 MMAs of K = 16.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ga3c {
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192;
+constexpr int TC_A_STAGE = TC_BM * TC_BK * 2;                       // 16 KB
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B (layout type 2), descriptor version 1 (Blackwell).
+//   K-major : rows of 128 B (64 bf16 of K), 8-row atoms of 1024 B -> SBO = 1024, LBO unused (1)
+//   MN-major: atom = 8 k-rows x 128 B (64 bf16 of M/N); SBO = 1024 between k-atoms,
+//             LBO = 8192 between the 64-wide M/N atoms (one TMA box each)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
+  const uint64_t lbo = mn_major ? (8192u >> 4) : 1u;
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// instruction descriptor, kind::f16: D = f32, A = B = bf16, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+// ---- epilogues: one thread owns one output row and 32 consecutive columns ------------------------
+struct EpiPartialF32 {      // raw fp32 tile into part[split][M][N]  (bias + relu are applied by the consumer)
+  float* out; int ldc; int64_t split_stride;
+  __device__ __forceinline__ void operator()(int split, int m, int n, const uint32_t (&r)[32]) const {
+    float4* dst = reinterpret_cast<float4*>(out + split * split_stride + (size_t)m * ldc + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                           __uint_as_float(r[4 * i + 3]));
+  }
+};
+struct EpiReluMaskBf16Tc {  // dn2 = acc where n2 > 0 else 0, bf16
+  uint16_t* out; const uint16_t* act; int ldc;
+  __device__ __forceinline__ void operator()(int, int m, int n, const uint32_t (&r)[32]) const {
+    const uint4* a = reinterpret_cast<const uint4*>(act + (size_t)m * ldc + n);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)m * ldc + n);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 av = a[i];
+      const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // post-ReLU activations are never negative: "> 0" == any magnitude bit set
+        const float lo = (aw[j] & 0x7FFFu) ? __uint_as_float(r[8 * i + 2 * j]) : 0.f;
+        const float hi = (aw[j] & 0x7FFF0000u) ? __uint_as_float(r[8 * i + 2 * j + 1]) : 0.f;
+        o[j] = pack_bf16(lo, hi);
+      }
+      dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int M, int N,
+               int k_blocks, int k_blocks_per_split, Epi epi) {
+  constexpr int B_STAGE = BN * TC_BK * 2;
+  constexpr int STAGE = TC_A_STAGE + B_STAGE;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms need 1024-byte alignment
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = sbase + STAGES * STAGE;            // full[STAGES], empty[STAGES], tmem_full : 8 B each
+  const uint32_t tmem_slot = bars + (2 * STAGES + 1) * 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN, split = blockIdx.z;
+  const int kb0 = split * k_blocks_per_split;
+  const int kb1 = min(kb0 + k_blocks_per_split, k_blocks);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tm_a));
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tm_b));
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bars + s * 8, 1); mbar_init(bars + (STAGES + s) * 8, 1); }
+    mbar_init(bars + 2 * STAGES * 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "n"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int it = kb - kb0, s = it % STAGES;
+        mbar_wait(bars + (STAGES + s) * 8, ((it / STAGES) & 1) ^ 1);          // slot free
+        const uint32_t full = bars + s * 8, sa = sbase + s * STAGE, sb = sa + TC_A_STAGE;
+        mbar_expect_tx(full, STAGE);
+        if (A_MN) {
+          tma_load_2d(sa, &tm_a, m0, kb * TC_BK, full);
+          tma_load_2d(sa + 8192, &tm_a, m0 + 64, kb * TC_BK, full);
+        } else {
+          tma_load_2d(sa, &tm_a, kb * TC_BK, m0, full);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tm_b, n0 + 64 * j, kb * TC_BK, full);
+        } else {
+          tma_load_2d(sb, &tm_b, kb * TC_BK, n0, full);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int it = kb - kb0, s = it % STAGES;
+        mbar_wait(bars + s * 8, (it / STAGES) & 1);                           // TMA bytes landed
+        tc_fence_after();
+        const uint32_t sa = sbase + s * STAGE, sb = sa + TC_A_STAGE;
+        const uint64_t da = make_desc(sa, A_MN), db = make_desc(sb, B_MN);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          // advance K by 16: +32 B inside the 128-B swizzle row (K-major), +2 k-atoms = 2048 B (MN-major)
+          const uint64_t ka = (uint64_t)((A_MN ? 2048u : 32u) * k >> 4), kbv = (uint64_t)((B_MN ? 2048u : 32u) * k >> 4);
+          tc_mma_bf16(tmem_base, da + ka, db + kbv, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(bars + (STAGES + s) * 8);                                    // frees the slot when the MMAs retire
+      }
+      tc_commit(bars + 2 * STAGES * 8);                                        // accumulator complete
+    }
+  } else {
+    mbar_wait(bars + 2 * STAGES * 8, 0);
+    tc_fence_after();
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
+      const int n = n0 + c * 32;
+      if (m < M && n < N) epi(split, m, n, r);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+// 2-D bf16 row-major matrix [rows][cols] (ld elements between rows), box = 64 inner x box_rows, 128-B swizzle,
+// out-of-bounds elements read as zero (ragged M / N / K tails need no special casing in the kernel).
+static int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+template <int BN, int STAGES>
+constexpr int tc_smem() { return STAGES * (TC_A_STAGE + BN * TC_BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024; }
+
+constexpr int FWD_BN = 128, FWD_ST = 4;     // fwd : M = B,    N = 256,  K = 3872  (split-K)
+constexpr int DG_BN = 128, DG_ST = 2;       // dgrad: M = B,   N = 3872, K = 256
+constexpr int WG_BN = 64, WG_ST = 4;        // wgrad: M = 3872, N = 256, K = B
+
+using FwdKernel = decltype(&gemm_tc_kernel<FWD_BN, FWD_ST, false, true, EpiPartialF32>);
+
+int configure_dense_tc() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(gemm_tc_kernel<FWD_BN, FWD_ST, false, true, EpiPartialF32>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem<FWD_BN, FWD_ST>());
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(gemm_tc_kernel<DG_BN, DG_ST, false, false, EpiReluMaskBf16Tc>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem<DG_BN, DG_ST>());
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(gemm_tc_kernel<WG_BN, WG_ST, true, true, EpiPartialF32>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem<WG_BN, WG_ST>());
+  return (int)e;
+}
+
+int dense_fwd_splits(int batch, int num_sms) {
+  const int tiles = ((batch + TC_BM - 1) / TC_BM) * (FC / FWD_BN);
+  const int kblocks = (FLAT + TC_BK - 1) / TC_BK;                 // 61
+  int s = num_sms / tiles;
+  if (s < 1) s = 1;
+  if (s > 16) s = 16;
+  const int per = (kblocks + s - 1) / s;
+  return (kblocks + per - 1) / per;                               // no empty splits
+}
+
+int launch_dense_fwd_tc(const uint16_t* n2, const uint16_t* w1bf, float* d1_part, int batch, int splits, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  if (make_tmap(&ta, n2, batch, FLAT, FLAT, TC_BM)) return (int)cudaErrorInvalidValue;        // A: [B][3872], K inner
+  if (make_tmap(&tb, w1bf, FLAT, FC, FC, 64)) return (int)cudaErrorInvalidValue;              // B: [3872][256], N inner
+  const int kblocks = (FLAT + TC_BK - 1) / TC_BK;
+  const int per = (kblocks + splits - 1) / splits;
+  dim3 grid((batch + TC_BM - 1) / TC_BM, FC / FWD_BN, splits);
+  gemm_tc_kernel<FWD_BN, FWD_ST, false, true, EpiPartialF32><<<grid, TC_THREADS, tc_smem<FWD_BN, FWD_ST>(), stream>>>(
+      ta, tb, batch, FC, kblocks, per, EpiPartialF32{d1_part, FC, (int64_t)batch * FC});
+  return (int)cudaGetLastError();
+}
+
+int launch_dense_dgrad_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint16_t* dn2, int batch,
+                          cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  if (make_tmap(&ta, dd1, batch, FC, FC, TC_BM)) return (int)cudaErrorInvalidValue;           // A: [B][256], K inner
+  if (make_tmap(&tb, w1bf, FLAT, FC, FC, DG_BN)) return (int)cudaErrorInvalidValue;           // B: [3872][256] = [N][K]
+  dim3 grid((batch + TC_BM - 1) / TC_BM, (FLAT + DG_BN - 1) / DG_BN, 1);
+  gemm_tc_kernel<DG_BN, DG_ST, false, false, EpiReluMaskBf16Tc><<<grid, TC_THREADS, tc_smem<DG_BN, DG_ST>(), stream>>>(
+      ta, tb, batch, FLAT, FC / TC_BK, FC / TC_BK, EpiReluMaskBf16Tc{dn2, n2, FLAT});
+  return (int)cudaGetLastError();
+}
+
+int launch_dense_wgrad_tc(const uint16_t* n2, const uint16_t* dd1, float* g_w1, int batch, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  if (make_tmap(&ta, n2, batch, FLAT, FLAT, 64)) return (int)cudaErrorInvalidValue;           // A: [K=B][M=3872], M inner
+  if (make_tmap(&tb, dd1, batch, FC, FC, 64)) return (int)cudaErrorInvalidValue;              // B: [K=B][N=256],  N inner
+  const int kblocks = (batch + TC_BK - 1) / TC_BK;
+  dim3 grid((FLAT + TC_BM - 1) / TC_BM, FC / WG_BN, 1);
+  gemm_tc_kernel<WG_BN, WG_ST, true, true, EpiPartialF32><<<grid, TC_THREADS, tc_smem<WG_BN, WG_ST>(), stream>>>(
+      ta, tb, FLAT, FC, kblocks, kblocks, EpiPartialF32{g_w1, FC, 0});
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ga3c

@@ -4,16 +4,18 @@
 //   v = d1.Wv + bv ; z = d1.Wp + bp ; s = softmax(z) ; p = (s + MIN_POLICY) / (1 + MIN_POLICY*A)
 //   cost_p_1 = log(max(sum(p*a), eps)) * (R - stop_gradient(v)) ; cost_p_2 = -beta * sum(log(max(p, eps)) * p)
 //   cost_v = 0.5 * (R - v)^2 ; every batch reduction is a SUM.
+// The kernel is also the tail of dense1 (NetworkDNav.py:90): it sums the split-K partial tiles the
+// tcgen05 GEMM left in d1_part (fixed order => deterministic), adds the bias and applies the ReLU.
 // Phase 1: one warp per sample, warp-shuffle reductions for the A+1 dot products, then the whole
-//          softmax / loss / dlogits chain in registers; writes p, v, dd1 (bf16) and stages (dz, dv).
-// Phase 2: one thread per dense1 feature j accumulates dWp[j,:], dWv[j], db1[j] over the chunk.
+//          softmax / loss / dlogits chain in registers; writes d1, p, v, dd1 (bf16) and stages (dz, dv).
+// Phase 2: one thread per dense1 feature accumulates dWp[j,:], dWv[j], db1[j] over the chunk.
 // Gradient / loss accumulators live in registers across chunks; one atomicAdd per element per CTA.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace ga3c {
 
-constexpr int HD_THREADS = 256, HD_CHUNK = 16;
+constexpr int HD_THREADS = 256, HD_CHUNK = 8;
 
 template <int A>
 __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
@@ -21,6 +23,8 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
   __shared__ __align__(16) float wt[A1][FC];           // wt[k][j]: k < A -> Wp[j][k]; k == A -> Wv[j]
   __shared__ float dzs[HD_CHUNK][A1];                  // (dz_0..dz_{A-1}, dv) per sample of the chunk
   __shared__ __align__(16) uint16_t dd1s[HD_CHUNK][FC];
+  __shared__ __align__(16) float d1s[HD_CHUNK][FC];    // dense1 output of the chunk (post bias + ReLU)
+  __shared__ __align__(16) float b1s[FC];
   __shared__ float bias_s[A1];
   __shared__ float loss_s[3];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -30,6 +34,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
     wt[k][jx] = (k < A) ? p.wp[jx * A + k] : p.wv[jx];
   }
   if (tid < A1) bias_s[tid] = (tid < A) ? p.bp[tid] : p.bv[0];
+  b1s[tid] = p.b1[tid];
   if (tid < 3) loss_s[tid] = 0.f;
   __syncthreads();
 
@@ -47,8 +52,27 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
       const int sl = warp * (HD_CHUNK / 8) + i;
       const int b = c * HD_CHUNK + sl;
       if (b < p.batch) {
-        const float4 fa = *reinterpret_cast<const float4*>(p.d1 + (size_t)b * FC + 4 * lane);
-        const float4 fb = *reinterpret_cast<const float4*>(p.d1 + (size_t)b * FC + 128 + 4 * lane);
+        // dense1 tail: sum the split-K partials in split order, + bias, ReLU
+        float4 fa = *reinterpret_cast<const float4*>(&b1s[4 * lane]);
+        float4 fb = *reinterpret_cast<const float4*>(&b1s[128 + 4 * lane]);
+        {
+          float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+          for (int sp = 0; sp < p.n_split; ++sp) {
+            const float* src = p.d1_part + ((size_t)sp * p.batch + b) * FC;
+            const float4 qa = *reinterpret_cast<const float4*>(src + 4 * lane);
+            const float4 qb = *reinterpret_cast<const float4*>(src + 128 + 4 * lane);
+            sa.x += qa.x; sa.y += qa.y; sa.z += qa.z; sa.w += qa.w;
+            sb.x += qb.x; sb.y += qb.y; sb.z += qb.z; sb.w += qb.w;
+          }
+          fa.x = fmaxf(fa.x + sa.x, 0.f); fa.y = fmaxf(fa.y + sa.y, 0.f); fa.z = fmaxf(fa.z + sa.z, 0.f); fa.w = fmaxf(fa.w + sa.w, 0.f);
+          fb.x = fmaxf(fb.x + sb.x, 0.f); fb.y = fmaxf(fb.y + sb.y, 0.f); fb.z = fmaxf(fb.z + sb.z, 0.f); fb.w = fmaxf(fb.w + sb.w, 0.f);
+        }
+        *reinterpret_cast<float4*>(p.d1 + (size_t)b * FC + 4 * lane) = fa;
+        *reinterpret_cast<float4*>(p.d1 + (size_t)b * FC + 128 + 4 * lane) = fb;
+        if (p.train) {
+          *reinterpret_cast<float4*>(&d1s[sl][4 * lane]) = fa;
+          *reinterpret_cast<float4*>(&d1s[sl][128 + 4 * lane]) = fb;
+        }
         float z[A1];
 #pragma unroll
         for (int k = 0; k < A1; ++k) {
@@ -142,7 +166,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
 #pragma unroll 4
       for (int s = 0; s < HD_CHUNK; ++s) {
         const int b = c * HD_CHUNK + s;
-        const float dval = (b < p.batch) ? p.d1[(size_t)b * FC + jx] : 0.f;
+        const float dval = (b < p.batch) ? d1s[s][jx] : 0.f;
 #pragma unroll
         for (int k = 0; k < A1; ++k) acc[k] = fmaf(dval, dzs[s][k], acc[k]);
         acc_b1 += __uint_as_float((uint32_t)dd1s[s][jx] << 16);

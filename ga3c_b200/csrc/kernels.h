@@ -9,6 +9,7 @@ namespace ga3c {
 int configure_conv_fwd();
 int configure_conv_bwd();
 int configure_dense();
+int configure_dense_tc();
 
 // conv_fwd.cu -- x fp32 [B,28224] -> n1 bf16 [B,441,16] (optional), n2 bf16 [B,3872]
 int launch_conv_fwd(const float* x, const float* w11, const float* b11, const float* w12, const float* b12,
@@ -23,9 +24,20 @@ int launch_dense_dgrad(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t
                        cudaStream_t stream);
 int launch_dense_wgrad(const uint16_t* n2, const uint16_t* dd1, float* g_w1, int batch, cudaStream_t stream);
 
+// dense_tc.cu -- the same three GEMMs on tcgen05 / TMEM / TMA.  fwd leaves `splits` raw fp32 partial tiles
+// in d1_part[splits][B][256]; the heads kernel sums them, adds the bias and applies the ReLU.
+int dense_fwd_splits(int batch, int num_sms);
+int launch_dense_fwd_tc(const uint16_t* n2, const uint16_t* w1bf, float* d1_part, int batch, int splits, cudaStream_t stream);
+int launch_dense_dgrad_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint16_t* dn2, int batch,
+                          cudaStream_t stream);
+int launch_dense_wgrad_tc(const uint16_t* n2, const uint16_t* dd1, float* g_w1, int batch, cudaStream_t stream);
+
 // heads.cu -- value / policy heads, softmax, A3C loss and its backward (NetworkVP_discrate.py:60-85)
 struct HeadsArgs {
-  const float* d1;      // [B,256]
+  const float* d1_part; // [n_split][B,256] raw split-K partial sums of dense1 (no bias, no ReLU)
+  int n_split;
+  const float* b1;      // dense1 bias
+  float* d1;            // [B,256] out: relu(sum of partials + b1)
   const float *wp, *bp, *wv, *bv;
   const float *yr, *a;  // train only
   int batch, num_actions;

@@ -1,6 +1,7 @@
 // C-ABI host layer: handle, flat arenas, workspace, and the launch sequences of the hot path.
 // See include/ga3c_b200.h for the contract and the reference call sites each entry replaces.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -56,6 +57,8 @@ struct ga3c_net {
   // workspace
   uint16_t *n1 = nullptr, *n2 = nullptr, *dd1 = nullptr, *dn2 = nullptr, *dn1 = nullptr;
   float* d1 = nullptr;
+  float* d1_part = nullptr;        // [splits][B,256] raw split-K partials of dense1 (dense_tc.cu)
+  int legacy_dense_bwd = 0;        // debug: GA3C_DENSE_BWD=mma routes dgrad/wgrad through the mma.sync GEMM
   int64_t global_step = 0;
   int64_t launches = 0;
   int last_batch = 0;
@@ -151,7 +154,8 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
     cudaMemcpy(n->ms, ones.data(), ab, cudaMemcpyHostToDevice);
   }
   int r;
-  if ((r = configure_conv_fwd()) || (r = configure_conv_bwd()) || (r = configure_dense())) {
+  if (const char* e = getenv("GA3C_DENSE_BWD")) n->legacy_dense_bwd = (std::string(e) == "mma");
+  if ((r = configure_conv_fwd()) || (r = configure_conv_bwd()) || (r = configure_dense()) || (r = configure_dense_tc())) {
     ga3c_destroy(n);
     return fail("cudaFuncSetAttribute", (cudaError_t)r);
   }
@@ -163,7 +167,8 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
 
 static void free_workspace(ga3c_net* n) {
   cudaFree(n->n1); cudaFree(n->n2); cudaFree(n->d1); cudaFree(n->dd1); cudaFree(n->dn2); cudaFree(n->dn1);
-  n->n1 = n->n2 = n->dd1 = n->dn2 = n->dn1 = nullptr; n->d1 = nullptr;
+  cudaFree(n->d1_part);
+  n->n1 = n->n2 = n->dd1 = n->dn2 = n->dn1 = nullptr; n->d1 = n->d1_part = nullptr;
 }
 
 static int alloc_workspace(ga3c_net* n, int max_batch) {
@@ -171,6 +176,9 @@ static int alloc_workspace(ga3c_net* n, int max_batch) {
   CK(cudaMalloc((void**)&n->n1, mb * N1_POS * C1_OUT * 2)); CK(cudaMalloc((void**)&n->n2, mb * FLAT * 2));
   CK(cudaMalloc((void**)&n->d1, mb * FC * 4)); CK(cudaMalloc((void**)&n->dd1, mb * FC * 2));
   CK(cudaMalloc((void**)&n->dn2, mb * FLAT * 2)); CK(cudaMalloc((void**)&n->dn1, mb * N1_POS * C1_OUT * 2));
+  // splits * batch <= max(batch, 64 * num_sms) rows for every batch (dense_fwd_splits)
+  const size_t part_rows = mb > (size_t)64 * n->num_sms ? mb : (size_t)64 * n->num_sms;
+  CK(cudaMalloc((void**)&n->d1_part, part_rows * FC * 4));
   n->cfg.max_batch = max_batch;
   return 0;
 }
@@ -257,9 +265,9 @@ static int check_batch(ga3c_net* n, int batch, const char* who) {
   return 0;
 }
 
-static HeadsArgs heads_args(ga3c_net* n, int batch) {
+static HeadsArgs heads_args(ga3c_net* n, int batch, int splits) {
   HeadsArgs h{};
-  h.d1 = n->d1;
+  h.d1 = n->d1; h.d1_part = n->d1_part; h.n_split = splits; h.b1 = n->w + n->off(P_D1B);
   h.wp = n->w + n->off(P_PW); h.bp = n->w + n->off(P_PB);
   h.wv = n->w + n->off(P_VW); h.bv = n->w + n->off(P_VB);
   h.batch = batch; h.num_actions = n->cfg.num_actions;
@@ -275,8 +283,9 @@ extern "C" int ga3c_predict(ga3c_net* n, const float* x, int32_t batch, float* p
   const float* w = n->w;
   LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
                                             w + n->off(P_C12B), nullptr, n->n2, batch, n->num_sms, st));
-  LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd(n->n2, n->w1_shadow, w + n->off(P_D1B), n->d1, batch, st));
-  HeadsArgs h = heads_args(n, batch);
+  const int splits = dense_fwd_splits(batch, n->num_sms);
+  LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
+  HeadsArgs h = heads_args(n, batch, splits);
   h.p_out = p_out; h.v_out = v_out; h.train = 0;
   LAUNCH(n, K_HEADS, st, launch_heads(h, n->num_sms, st));
   n->last_batch = batch;
@@ -296,14 +305,20 @@ extern "C" int ga3c_forward_backward(ga3c_net* n, const float* x, const float* y
   if (loss) CK(cudaMemsetAsync(loss, 0, 4 * sizeof(float), st));
   LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
                                             w + n->off(P_C12B), n->n1, n->n2, batch, n->num_sms, st));
-  LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd(n->n2, n->w1_shadow, w + n->off(P_D1B), n->d1, batch, st));
-  HeadsArgs h = heads_args(n, batch);
+  const int splits = dense_fwd_splits(batch, n->num_sms);
+  LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
+  HeadsArgs h = heads_args(n, batch, splits);
   h.yr = yr; h.a = a; h.beta = beta; h.train = 1; h.dd1 = n->dd1; h.loss = loss;
   h.g_wp = g + n->off(P_PW); h.g_bp = g + n->off(P_PB); h.g_wv = g + n->off(P_VW); h.g_bv = g + n->off(P_VB);
   h.g_b1 = g + n->off(P_D1B);
   LAUNCH(n, K_HEADS, st, launch_heads(h, n->num_sms, st));
-  LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
-  LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
+  if (n->legacy_dense_bwd) {
+    LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
+    LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
+  } else {
+    LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad_tc(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
+    LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
+  }
   LAUNCH(n, K_CONV12_BWD, st, launch_conv12_bwd(n->n1, n->dn2, w + n->off(P_C12W), n->dn1, g + n->off(P_C12W),
                                                 g + n->off(P_C12B), batch, n->num_sms, st));
   LAUNCH(n, K_CONV11_WGRAD, st, launch_conv11_wgrad(x, n->dn1, g + n->off(P_C11W), g + n->off(P_C11B), batch,
