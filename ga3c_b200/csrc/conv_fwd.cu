@@ -1,4 +1,5 @@
-// Fused conv11 (8x8 s4, 16) -> conv12 (4x4 s2, 32) forward for one frame per CTA iteration.
+// Fused conv11 (8x8 s4, 16) -> conv12 (4x4 s2, 32) forward; one persistent CTA per SM, one frame
+// per iteration, the next frame's bytes in flight while the current one is computed.
 //
 // Reference op: tf.nn.conv2d(..., padding='SAME') + b, relu  (NetworkVP.py:224-226), wired as
 // NetworkDNav.py:81-82.  Implicit GEMM on bf16 tensor-core tiles, fp32 accumulate:
@@ -9,33 +10,72 @@
 // materialised in shared memory for a UMMA descriptor.  Warp-level mma.sync reads the *un-duplicated*
 // image straight out of shared memory with conflict-free 8-byte fragment loads, so the frame is
 // converted once, stays on chip, and conv11's output never leaves the SM before conv12 consumes it.
-// The kernel is bound by the HBM read of the fp32 frame (112,896 B / sample); see DESIGN.md.
+//
+// Pipeline per frame (HBM traffic: the fp32 frame, 112,896 B / sample, read exactly once):
+//   TMA engine : cp.async.bulk of frame i+1 (8 chunks) into the fp32 staging buffer, signalled on an mbarrier
+//   all warps  : wait(frame i) -> fp32 staging -> padded bf16 image -> [issue frame i+1] -> conv11 -> conv12 -> stores
+// Measured limits (profiles/): shared-memory wavefronts (74 % of peak) and the legacy HMMA pipe
+// (33 % active; its ceiling is ~44 M frames/s, below the 58 M frames/s HBM roofline).
 #include "common.cuh"
 #include "kernels.h"
 
 namespace ga3c {
 
-constexpr int CF_THREADS = 256;
-constexpr int CF_OFF_XS = 0;
-constexpr int CF_OFF_N1P = CF_OFF_XS + XS_BYTES;          // 61952
-constexpr int CF_OFF_W12F = CF_OFF_N1P + N1P_BYTES;       // 80384
-constexpr int CF_OFF_N2S = CF_OFF_W12F + 16 * 2 * 32 * 16;  // 96768
-constexpr int CF_OFF_BIAS = CF_OFF_N2S + N2_POS * 64;     // 104512
-constexpr int CF_SMEM = CF_OFF_BIAS + (C1_OUT + C2_OUT) * 4;  // 104704
+constexpr int CF_THREADS = 512, CF_WARPS = CF_THREADS / 32;
+constexpr int FRAME_BYTES = STATE_DIM * 4;                  // 112,896
+constexpr int CF_CHUNKS = 8, CF_CHUNK_BYTES = FRAME_BYTES / CF_CHUNKS;   // 14,112 = 16 * 882
+static_assert(CF_CHUNK_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+constexpr int CF_OFF_STG = 0;
+constexpr int CF_OFF_XS = CF_OFF_STG + FRAME_BYTES;         // 112,896
+constexpr int CF_OFF_N1P = CF_OFF_XS + XS_BYTES;            // 174,848
+constexpr int CF_OFF_W12F = CF_OFF_N1P + N1P_BYTES;         // 193,280
+constexpr int CF_OFF_N2S = CF_OFF_W12F + 16 * 2 * 32 * 16;  // 209,664
+constexpr int CF_OFF_BIAS = CF_OFF_N2S + N2_POS * 64;       // 217,408
+constexpr int CF_OFF_BAR = CF_OFF_BIAS + (C1_OUT + C2_OUT) * 4;   // 217,600
+constexpr int CF_SMEM = CF_OFF_BAR + 16;                    // 217,616 <= 232,448
 
-__global__ void __launch_bounds__(CF_THREADS, 2)
+// fp32 staging (dense NHWC frame) -> zero-bordered bf16 image, 8 B per pixel
+template <int NT>
+__device__ __forceinline__ void convert_frame(uint32_t stg, uint32_t xs, int tid) {
+  constexpr int NPIX = IMG * IMG;
+#pragma unroll 2
+  for (int i = tid; i < NPIX; i += NT) {
+    uint32_t r[4];
+    lds128(r, stg + i * 16);
+    const int y = i / IMG, xx = i - y * IMG;
+    sts64(xs + (y + 2) * XS_ROW_BYTES + (xx + 2) * 8,
+          pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1])), pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3])));
+  }
+}
+
+__device__ __forceinline__ void issue_frame(uint32_t stg, const float* src, uint32_t bar) {
+  mbar_expect_tx(bar, FRAME_BYTES);
+#pragma unroll
+  for (int c = 0; c < CF_CHUNKS; ++c)
+    bulk_load(stg + c * CF_CHUNK_BYTES, reinterpret_cast<const uint8_t*>(src) + c * CF_CHUNK_BYTES, CF_CHUNK_BYTES, bar);
+}
+
+__global__ void __launch_bounds__(CF_THREADS, 1)
 conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, const float* __restrict__ b11,
                 const float* __restrict__ w12, const float* __restrict__ b12,
                 uint16_t* __restrict__ n1_out, uint16_t* __restrict__ n2_out, int batch) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t xs = sbase + CF_OFF_XS, n1p = sbase + CF_OFF_N1P, w12f = sbase + CF_OFF_W12F,
-                 n2s = sbase + CF_OFF_N2S;
+  const uint32_t stg = sbase + CF_OFF_STG, xs = sbase + CF_OFF_XS, n1p = sbase + CF_OFF_N1P,
+                 w12f = sbase + CF_OFF_W12F, n2s = sbase + CF_OFF_N2S, bar = sbase + CF_OFF_BAR;
   float* bias_s = reinterpret_cast<float*>(smem + CF_OFF_BIAS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
 
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  int b = blockIdx.x;
+  if (tid == 0 && b < batch) issue_frame(stg, x + (size_t)b * STATE_DIM, bar);   // overlaps the weight setup below
+
   // zero the padded buffers once: the borders are never written again
-  for (int i = tid; i < (XS_BYTES + N1P_BYTES) / 16; i += CF_THREADS) sts128(sbase + i * 16, make_uint4(0, 0, 0, 0));
+  for (int i = tid; i < (XS_BYTES + N1P_BYTES) / 16; i += CF_THREADS) sts128(xs + i * 16, make_uint4(0, 0, 0, 0));
   // conv12 weights in mma B-fragment order: [kstep = tap][n-tile pair][lane] -> {b0,b1 (tile 2np), b0,b1 (tile 2np+1)}
   // K permutation inside a k16 step (one tap, 16 ci): logical cols (2t,2t+1,2t+8,2t+9) <-> ci (4t..4t+3)
   for (int i = tid; i < 16 * 2 * 32; i += CF_THREADS) {
@@ -66,12 +106,19 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
   }
   __syncthreads();
 
-  for (int b = blockIdx.x; b < batch; b += gridDim.x) {
-    stage_frame_bf16<CF_THREADS>(x + (size_t)b * STATE_DIM, xs, tid);
-    __syncthreads();
+  uint32_t phase = 0;
+  for (; b < batch; b += gridDim.x) {
+    mbar_wait(bar, phase);                    // frame b has landed in the staging buffer
+    phase ^= 1;
+    convert_frame<CF_THREADS>(stg, xs, tid);
+    __syncthreads();                          // staging is free again, the bf16 image is complete
+    if (tid == 0 && b + (int)gridDim.x < batch) {
+      fence_proxy_async();                    // order the generic-proxy reads above before the async-proxy refill
+      issue_frame(stg, x + (size_t)(b + gridDim.x) * STATE_DIM, bar);
+    }
 
-    // ---------------- conv11: 28 m16 tiles over 8 warps ----------------
-    for (int tile = warp; tile < 28; tile += 8) {
+    // ---------------- conv11: 28 m16 tiles over 16 warps ----------------
+    for (int tile = warp; tile < 28; tile += CF_WARPS) {
       const int r0 = tile * 16 + g, r1 = r0 + 8;
       const int p0 = min(r0, N1_POS - 1), p1 = min(r1, N1_POS - 1);
       const int oy0 = p0 / H1, ox0 = p0 - oy0 * H1, oy1 = p1 / H1, ox1 = p1 - oy1 * H1;
@@ -111,12 +158,13 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
       }
     }
 
-    // ---------------- conv12: 8 m16 tiles, one per warp ----------------
+    // ---------------- conv12: 8 m16 tiles x 2 n-halves = 16 warp tasks ----------------
     {
-      const int r0 = warp * 16 + g, r1 = r0 + 8;
+      const int mt = warp >> 1, nh = warp & 1;
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
       const int p0 = min(r0, N2_POS - 1), p1 = min(r1, N2_POS - 1);
       const int oy0 = p0 / H2, ox0 = p0 - oy0 * H2, oy1 = p1 / H2, ox1 = p1 - oy1 * H2;
-      float acc[4][4] = {};
+      float acc[2][4] = {};
 #pragma unroll
       for (int kh = 0; kh < 4; ++kh) {
 #pragma unroll
@@ -125,21 +173,19 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
           uint32_t a[4], bw[4];
           lds64(a[0], a[2], n1p + n1p_off(2 * oy0 + kh, 2 * ox0 + kw, t >> 1) + (t & 1) * 8);
           lds64(a[1], a[3], n1p + n1p_off(2 * oy1 + kh, 2 * ox1 + kw, t >> 1) + (t & 1) * 8);
-          lds128(bw, w12f + ((ks * 2 + 0) * 32 + lane) * 16);
+          lds128(bw, w12f + ((ks * 2 + nh) * 32 + lane) * 16);
           mma_bf16_16816(acc[0], a, bw[0], bw[1]);
           mma_bf16_16816(acc[1], a, bw[2], bw[3]);
-          lds128(bw, w12f + ((ks * 2 + 1) * 32 + lane) * 16);
-          mma_bf16_16816(acc[2], a, bw[0], bw[1]);
-          mma_bf16_16816(acc[3], a, bw[2], bw[3]);
         }
       }
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+      for (int q = 0; q < 2; ++q) {
+        const int nt = 2 * nh + q;
         const float bz0 = bias_s[C1_OUT + 8 * nt + 2 * t], bz1 = bias_s[C1_OUT + 8 * nt + 2 * t + 1];
         if (r0 < N2_POS)
-          sts32(n2s + r0 * 64 + (8 * nt + 2 * t) * 2, pack_bf16(fmaxf(acc[nt][0] + bz0, 0.f), fmaxf(acc[nt][1] + bz1, 0.f)));
+          sts32(n2s + r0 * 64 + (8 * nt + 2 * t) * 2, pack_bf16(fmaxf(acc[q][0] + bz0, 0.f), fmaxf(acc[q][1] + bz1, 0.f)));
         if (r1 < N2_POS)
-          sts32(n2s + r1 * 64 + (8 * nt + 2 * t) * 2, pack_bf16(fmaxf(acc[nt][2] + bz0, 0.f), fmaxf(acc[nt][3] + bz1, 0.f)));
+          sts32(n2s + r1 * 64 + (8 * nt + 2 * t) * 2, pack_bf16(fmaxf(acc[q][2] + bz0, 0.f), fmaxf(acc[q][3] + bz1, 0.f)));
       }
     }
     __syncthreads();
@@ -151,8 +197,9 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
         dst[i] = make_uint4(r[0], r[1], r[2], r[3]);
       }
     }
-    // no barrier needed here: the next iteration's staging only writes xs (last read before two
-    // barriers ago) and its conv11 writes n1p only after the barrier that follows staging.
+    // no barrier needed here: the next iteration's convert only writes xs (last read two barriers ago),
+    // its conv11 writes n1p only after the barrier that follows the convert, and n2s is rewritten only
+    // after two more barriers.
   }
 }
 
@@ -162,7 +209,7 @@ int configure_conv_fwd() {
 
 int launch_conv_fwd(const float* x, const float* w11, const float* b11, const float* w12, const float* b12,
                     uint16_t* n1_out, uint16_t* n2_out, int batch, int num_sms, cudaStream_t stream) {
-  const int grid = min(batch, 2 * num_sms);
+  const int grid = min(batch, num_sms);
   conv_fwd_kernel<<<grid, CF_THREADS, CF_SMEM, stream>>>(x, w11, b11, w12, b12, n1_out, n2_out, batch);
   return (int)cudaGetLastError();
 }
