@@ -14,53 +14,48 @@
 
 namespace ga3c {
 
-constexpr int CB_THREADS = 256;
-
-// padded dn2 in smem: 12x12 positions (index (oy+1, ox+1); row/col 0 are zero), 64 B per position,
-// 16-B chunk c stored at c ^ f(pp) so that 8 consecutive positions x one chunk are conflict-free
-constexpr int DN2P_W = 12, DN2P_BYTES = DN2P_W * DN2P_W * 64;     // 9216
-__device__ __forceinline__ int dn2p_off(int pp, int chunk) {
-  const int f = (((pp >> 1) & 1) << 1) | ((pp >> 2) & 1);
-  return (pp << 6) + ((chunk ^ f) << 4);
-}
-
 // ------------------------------------------------------------------------------------------------
-// inputs are double-buffered: frame i+1 streams in (cp.async) while frame i is computed
-constexpr int C12_IN_BYTES = N1P_BYTES + DN2P_BYTES;              // 27648 per buffer
-constexpr int C12_OFF_IN = 0;
-constexpr int C12_OFF_WDF = C12_OFF_IN + 2 * C12_IN_BYTES;        // 55296
-constexpr int C12_OFF_DN1S = C12_OFF_WDF + 4 * 8 * 32 * 16;       // 71680
-constexpr int C12_OFF_RED = C12_OFF_DN1S + N1_POS * 32;           // 85792
-constexpr int C12_SMEM = C12_OFF_RED + CB_THREADS * 4;            // 86816  (2 CTAs / SM)
+// conv12 backward.  One persistent CTA per SM, 16 warps, inputs double-buffered with cp.async.
+// Every shared-memory layout is AFFINE (padding instead of XOR swizzles) so that tap / k-step offsets
+// fold into instruction immediates, and everything that depends only on the thread (tile -> pixel
+// maps, staging destinations) is computed once per CTA: the frame loop is loads + HMMA.
+//   n1pl  conv11 output, SAME-padded (1 before, 2 after) 24x24 pixels, split by x parity into two planes
+//         of 24 x 12 pixels, 48 B per pixel (32 B data + 16 B pad): the stride-2 pixel walks of conv12 become
+//         unit-stride walks at 48 B, conflict-free for ldmatrix and for the 4-byte mask reads
+//   dn2a  dn2 on a zero-bordered 12x12 grid (index (oy+1, ox+1)), 96 B per position: dgrad A fragments (8-byte loads)
+//   dn2b  dn2 as 128 plain positions (121 + zero rows), 80 B per position: wgrad B fragments (ldmatrix.trans)
+constexpr int B12_THREADS = 512, B12_WARPS = B12_THREADS / 32;
+constexpr int N1PL_PITCH = 48, N1PL_PLANE = 24 * 12 * N1PL_PITCH, N1PL_BYTES = 2 * N1PL_PLANE;   // 13,824 / 27,648
+constexpr int DN2A_W = 12, DN2A_PITCH = 96, DN2A_BYTES = DN2A_W * DN2A_W * DN2A_PITCH;             // 13,824
+constexpr int DN2B_PITCH = 80, DN2B_BYTES = 128 * DN2B_PITCH;                                      // 10,240
+constexpr int B12_IN_BYTES = N1PL_BYTES + DN2A_BYTES + DN2B_BYTES;                                 // 51,712
+constexpr int B12_TILES = 29;                                       // dgrad m16 tiles: 7 + 7 + 7 + 8 over the 4 parity classes
+constexpr int B12_OFF_IN = 0;
+constexpr int B12_OFF_WDF = B12_OFF_IN + 2 * B12_IN_BYTES;          // 103,424
+constexpr int B12_OFF_DN1S = B12_OFF_WDF + 4 * 8 * 32 * 16;         // 119,808
+constexpr int B12_OFF_LUT = B12_OFF_DN1S + N1_POS * 32;             // 133,920
+constexpr int B12_OFF_RED = B12_OFF_LUT + B12_TILES * 16 * 8;       // 137,632
+constexpr int B12_SMEM = B12_OFF_RED + B12_THREADS * 4;             // 139,680
 
-__device__ __forceinline__ void c12_prefetch(const uint16_t* __restrict__ n1, const uint16_t* __restrict__ dn2, int b,
-                                             uint32_t n1p, uint32_t dn2p, int tid) {
-  const uint4* s1 = reinterpret_cast<const uint4*>(n1 + (size_t)b * N1_POS * C1_OUT);
-  for (int i = tid; i < N1_POS * 2; i += CB_THREADS) {
-    const int pos = i >> 1, oy = pos / H1, ox = pos - oy * H1;
-    cp_async16(n1p + n1p_off(oy + 1, ox + 1, i & 1), s1 + i, 16);
-  }
-  const uint4* s2 = reinterpret_cast<const uint4*>(dn2 + (size_t)b * FLAT);
-  for (int i = tid; i < N2_POS * 4; i += CB_THREADS) {
-    const int pos = i >> 2, oy = pos / H2, ox = pos - oy * H2;
-    cp_async16(dn2p + dn2p_off((oy + 1) * DN2P_W + ox + 1, i & 3), s2 + i, 16);
-  }
+__device__ __forceinline__ int n1pl_off(int Y, int X) {              // padded pixel (Y, X) in [0,24)^2
+  return (X & 1) * N1PL_PLANE + (Y * 12 + (X >> 1)) * N1PL_PITCH;
 }
 
-__global__ void __launch_bounds__(CB_THREADS, 2)
+__global__ void __launch_bounds__(B12_THREADS, 1)
 conv12_bwd_kernel(const uint16_t* __restrict__ n1, const uint16_t* __restrict__ dn2, const float* __restrict__ w12,
                   uint16_t* __restrict__ dn1, float* __restrict__ g_w12, float* __restrict__ g_b12, int batch) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t wdf = sbase + C12_OFF_WDF, dn1s = sbase + C12_OFF_DN1S;
-  float* red = reinterpret_cast<float*>(smem + C12_OFF_RED);
+  const uint32_t wdf = sbase + B12_OFF_WDF, dn1s = sbase + B12_OFF_DN1S, lut = sbase + B12_OFF_LUT;
+  float* red = reinterpret_cast<float*>(smem + B12_OFF_RED);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int j = lane >> 3, rr = lane & 7;
+  const int stride = gridDim.x;
 
-  for (int i = tid; i < 2 * C12_IN_BYTES / 16; i += CB_THREADS) sts128(sbase + i * 16, make_uint4(0, 0, 0, 0));
+  for (int i = tid; i < 2 * B12_IN_BYTES / 16; i += B12_THREADS) sts128(sbase + i * 16, make_uint4(0, 0, 0, 0));
   // data-gradient weights in B-fragment order: [class = par_y*2+par_x][kstep = (a*2+b)*2+half][lane]
   //   K = (a, b, co): taps kh = par_y + 2a, kw = par_x + 2b ; N = ci
-  for (int i = tid; i < 4 * 8 * 32; i += CB_THREADS) {
+  for (int i = tid; i < 4 * 8 * 32; i += B12_THREADS) {
     const int cls = i >> 8, ks = (i >> 5) & 7, ln = i & 31, gg = ln >> 2, tt = ln & 3;
     const int kh = (cls >> 1) + 2 * (ks >> 2), kw = (cls & 1) + 2 * ((ks >> 1) & 1), half = ks & 1;
     uint32_t r[4];
@@ -73,133 +68,157 @@ conv12_bwd_kernel(const uint16_t* __restrict__ n1, const uint16_t* __restrict__ 
     }
     sts128(wdf + i * 16, make_uint4(r[0], r[1], r[2], r[3]));
   }
+  // dgrad row table: entry (tile, row) = { dn2a byte offset of its (untapped) position, dn1 staging offset or 0xFFFF,
+  //                                        n1pl offset of its pixel (relu mask), 0 }
+  //   class (pary, parx): pixel y = 2*iy + 1 - pary ; q = i + 2 - par ; tap a reaches dn2 row q - a on the padded grid
+  for (int e = tid; e < B12_TILES * 16; e += B12_THREADS) {
+    const int tile = e >> 4, r = e & 15;
+    const int cls = tile < 7 ? 0 : tile < 14 ? 1 : tile < 21 ? 2 : 3;
+    const int pary = cls >> 1, parx = cls & 1, nx = 10 + parx, cnt = (10 + pary) * nx;
+    const int rix = (tile - cls * 7) * 16 + r, c = min(rix, cnt - 1);
+    const int iy = c / nx, ix = c - iy * nx;
+    const int y = 2 * iy + 1 - pary, xx = 2 * ix + 1 - parx;
+    const uint32_t a_off = ((iy + 2 - pary) * DN2A_W + (ix + 2 - parx)) * DN2A_PITCH;
+    const uint32_t o_off = rix < cnt ? (uint32_t)(y * H1 + xx) * 32 : 0xFFFFu;
+    const uint32_t m_off = n1pl_off(y + 1, xx + 1);
+    sts64(lut + e * 8, a_off | (o_off << 16), m_off);
+  }
+  // staging destinations of this thread's 16-B chunks (frame-invariant)
+  uint32_t dst_n1[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int i = min(tid + k * B12_THREADS, N1_POS * 2 - 1), pos = i >> 1, y = pos / H1, xx = pos - y * H1;
+    dst_n1[k] = n1pl_off(y + 1, xx + 1) + (i & 1) * 16;
+  }
+  uint32_t dst_a, dst_b;
+  {
+    const int i = min(tid, N2_POS * 4 - 1), pos = i >> 2, oy = pos / H2, ox = pos - oy * H2;
+    dst_a = N1PL_BYTES + ((oy + 1) * DN2A_W + ox + 1) * DN2A_PITCH + (i & 3) * 16;
+    dst_b = N1PL_BYTES + DN2A_BYTES + pos * DN2B_PITCH + (i & 3) * 16;
+  }
+  // wgrad A bases: row (ks, j>>1, rr) -> pixel (2*oy, 2*ox) of the tap-(0,0) window, 16-B chunk j&1
+  uint32_t wa_base[8];
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const int pos = min(ks * 16 + (j >> 1) * 8 + rr, N2_POS - 1), oy = pos / H2, ox = pos - oy * H2;   // rows >= 121 meet zero dn2b rows
+    wa_base[ks] = (2 * oy * 12 + ox) * N1PL_PITCH + (j & 1) * 16;
+  }
+  const int kh = warp >> 2, kw = warp & 3;                            // wgrad: one tap per warp
+  const uint32_t tap_off = (kw & 1) * N1PL_PLANE + (kh * 12 + (kw >> 1)) * N1PL_PITCH;
   __syncthreads();
 
-  float wacc[2][4][4] = {};   // wgrad: taps 2*warp, 2*warp+1 ; 4 n-tiles
+  auto prefetch = [&](int b, uint32_t in) {
+    const uint4* s1 = reinterpret_cast<const uint4*>(n1 + (size_t)b * N1_POS * C1_OUT);
+    cp_async16(in + dst_n1[0], s1 + tid, 16);
+    if (tid + B12_THREADS < N1_POS * 2) cp_async16(in + dst_n1[1], s1 + tid + B12_THREADS, 16);
+    if (tid < N2_POS * 4) {
+      const uint4* s2 = reinterpret_cast<const uint4*>(dn2 + (size_t)b * FLAT) + tid;
+      cp_async16(in + dst_a, s2, 16);
+      cp_async16(in + dst_b, s2, 16);
+    }
+  };
+
+  float wacc[4][4] = {};      // wgrad: tap = warp, 16 ci x 32 co
   float bacc = 0.f;           // db2 partial: co = tid & 31, part = tid >> 5
 
-  // the zero fill above must land before the first cp.async overwrites the interiors (same threads do
-  // not own the same bytes), so the prefetch of the first frame follows the setup barrier
-  if ((int)blockIdx.x < batch) c12_prefetch(n1, dn2, blockIdx.x, sbase + C12_OFF_IN, sbase + C12_OFF_IN + N1P_BYTES, tid);
+  int b = blockIdx.x, buf = 0;
+  if (b < batch) prefetch(b, sbase + B12_OFF_IN);
   cp_async_commit();
-  int buf = 0;
-  for (int b = blockIdx.x; b < batch; b += gridDim.x, buf ^= 1) {
-    const uint32_t n1p = sbase + C12_OFF_IN + buf * C12_IN_BYTES, dn2p = n1p + N1P_BYTES;
+  for (; b < batch; b += stride, buf ^= 1) {
+    const uint32_t in = sbase + B12_OFF_IN + buf * B12_IN_BYTES;
+    const uint32_t n1pl = in, dn2a = in + N1PL_BYTES, dn2b = dn2a + DN2A_BYTES;
     cp_async_wait<0>();
-    __syncthreads();          // frame b is visible to every warp; the other buffer and dn1s are free (barrier at loop end)
-    if (b + (int)gridDim.x < batch)
-      c12_prefetch(n1, dn2, b + gridDim.x, sbase + C12_OFF_IN + (buf ^ 1) * C12_IN_BYTES,
-                   sbase + C12_OFF_IN + (buf ^ 1) * C12_IN_BYTES + N1P_BYTES, tid);
+    __syncthreads();          // frame b visible to every warp; the other buffer and dn1s are free (barrier at loop end)
+    if (b + stride < batch) prefetch(b + stride, sbase + B12_OFF_IN + (buf ^ 1) * B12_IN_BYTES);
     cp_async_commit();
 
     // ---------------- data gradient: 29 m16 tiles over 4 parity classes ----------------
-    for (int tile = warp; tile < 29; tile += 8) {
+    for (int tile = warp; tile < B12_TILES; tile += B12_WARPS) {
       const int cls = tile < 7 ? 0 : tile < 14 ? 1 : tile < 21 ? 2 : 3;
-      const int lt = tile - cls * 7;
-      const int pary = cls >> 1, parx = cls & 1;
-      const int ny = 10 + pary, nx = 10 + parx, cnt = ny * nx;
-      const int r0 = lt * 16 + g, r1 = r0 + 8;
-      const int c0 = min(r0, cnt - 1), c1 = min(r1, cnt - 1);
-      const int iy0 = c0 / nx, ix0 = c0 - iy0 * nx, iy1 = c1 / nx, ix1 = c1 - iy1 * nx;
-      // pixel y = 2*i + 1 - par ; q = i + 1 - par ; tap a -> oy = q - a ; padded row = oy + 1
-      const int qy0 = iy0 + 2 - pary, qx0 = ix0 + 2 - parx, qy1 = iy1 + 2 - pary, qx1 = ix1 + 2 - parx;
+      uint32_t e0a, e0m, e1a, e1m;
+      lds64(e0a, e0m, lut + (tile * 16 + g) * 8);
+      lds64(e1a, e1m, lut + (tile * 16 + g + 8) * 8);
+      const uint32_t a0 = dn2a + (e0a & 0xFFFFu) + (t >> 1) * 16 + (t & 1) * 8;
+      const uint32_t a1 = dn2a + (e1a & 0xFFFFu) + (t >> 1) * 16 + (t & 1) * 8;
+      const uint32_t bsrc = wdf + cls * 4096 + lane * 16;
       float acc[2][4] = {};
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
-        const int a_ = ks >> 2, b_ = (ks >> 1) & 1, half = ks & 1;
-        const int pp0 = (qy0 - a_) * DN2P_W + (qx0 - b_), pp1 = (qy1 - a_) * DN2P_W + (qx1 - b_);
+        const int off = -((ks >> 2) * DN2A_W + ((ks >> 1) & 1)) * DN2A_PITCH + (ks & 1) * 32;
         uint32_t a[4], bw[4];
-        lds64(a[0], a[2], dn2p + dn2p_off(pp0, 2 * half + (t >> 1)) + (t & 1) * 8);
-        lds64(a[1], a[3], dn2p + dn2p_off(pp1, 2 * half + (t >> 1)) + (t & 1) * 8);
-        lds128(bw, wdf + ((cls * 8 + ks) * 32 + lane) * 16);
+        lds64(a[0], a[2], a0 + off);
+        lds64(a[1], a[3], a1 + off);
+        lds128(bw, bsrc + ks * 512);
         mma_bf16_16816(acc[0], a, bw[0], bw[1]);
         mma_bf16_16816(acc[1], a, bw[2], bw[3]);
       }
-      const int y0 = 2 * iy0 + 1 - pary, x0 = 2 * ix0 + 1 - parx, y1 = 2 * iy1 + 1 - pary, x1 = 2 * ix1 + 1 - parx;
+      const uint32_t o0 = e0a >> 16, o1 = e1a >> 16;
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
-        if (r0 < cnt) {
+        if (o0 != 0xFFFFu) {
           uint32_t m;
-          asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(m) : "r"(n1p + n1p_off(y0 + 1, x0 + 1, nt) + 4 * t));
-          sts32(dn1s + (y0 * H1 + x0) * 32 + nt * 16 + 4 * t,
-                pack_bf16((m & 0x7FFFu) ? acc[nt][0] : 0.f, (m & 0x7FFF0000u) ? acc[nt][1] : 0.f));
+          asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(m) : "r"(n1pl + e0m + nt * 16 + 4 * t));
+          sts32(dn1s + o0 + nt * 16 + 4 * t, pack_bf16((m & 0x7FFFu) ? acc[nt][0] : 0.f, (m & 0x7FFF0000u) ? acc[nt][1] : 0.f));
         }
-        if (r1 < cnt) {
+        if (o1 != 0xFFFFu) {
           uint32_t m;
-          asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(m) : "r"(n1p + n1p_off(y1 + 1, x1 + 1, nt) + 4 * t));
-          sts32(dn1s + (y1 * H1 + x1) * 32 + nt * 16 + 4 * t,
-                pack_bf16((m & 0x7FFFu) ? acc[nt][2] : 0.f, (m & 0x7FFF0000u) ? acc[nt][3] : 0.f));
+          asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(m) : "r"(n1pl + e1m + nt * 16 + 4 * t));
+          sts32(dn1s + o1 + nt * 16 + 4 * t, pack_bf16((m & 0x7FFFu) ? acc[nt][2] : 0.f, (m & 0x7FFF0000u) ? acc[nt][3] : 0.f));
         }
       }
     }
 
-    // ---------------- weight gradient: M = 256 (tap, ci), N = 32, K = 121 positions ----------------
-#pragma unroll 2
-    for (int ks = 0; ks < 8; ++ks) {
-      uint32_t bf[2][4];
-      {
-        const int pos = ks * 16 + (j & 1) * 8 + rr;
-        int pp = 0;
-        if (pos < N2_POS) { const int oy = pos / H2, ox = pos - oy * H2; pp = (oy + 1) * DN2P_W + ox + 1; }
-        ldsm_x4_t(bf[0], dn2p + dn2p_off(pp, (j >> 1)));
-        ldsm_x4_t(bf[1], dn2p + dn2p_off(pp, 2 + (j >> 1)));
-      }
-      const int pos = ks * 16 + (j >> 1) * 8 + rr;
-      int oy = 0, ox = 0;
-      const bool ok = pos < N2_POS;
-      if (ok) { oy = pos / H2; ox = pos - oy * H2; }
+    // ---------------- weight gradient: M = 16 ci of this warp's tap, N = 32 co, K = 121 positions ----------------
+    {
+      const uint32_t brow = dn2b + ((j & 1) * 8 + rr) * DN2B_PITCH + (j >> 1) * 16;
+      const uint32_t asrc = n1pl + tap_off;
 #pragma unroll
-      for (int ti = 0; ti < 2; ++ti) {
-        const int tap = 2 * warp + ti, kh = tap >> 2, kw = tap & 3;
-        uint32_t af[4];
-        const int py = ok ? 2 * oy + kh : N1P_W - 1, px = ok ? 2 * ox + kw : N1P_W - 1;
-        ldsm_x4_t(af, n1p + n1p_off(py, px, j & 1));
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-          mma_bf16_16816(wacc[ti][nt], af, bf[nt >> 1][(nt & 1) * 2], bf[nt >> 1][(nt & 1) * 2 + 1]);
+      for (int ks = 0; ks < 8; ++ks) {
+        uint32_t bf0[4], bf1[4], af[4];
+        ldsm_x4_t(bf0, brow + ks * 16 * DN2B_PITCH);
+        ldsm_x4_t(bf1, brow + ks * 16 * DN2B_PITCH + 32);
+        ldsm_x4_t(af, asrc + wa_base[ks]);
+        mma_bf16_16816(wacc[0], af, bf0[0], bf0[1]);
+        mma_bf16_16816(wacc[1], af, bf0[2], bf0[3]);
+        mma_bf16_16816(wacc[2], af, bf1[0], bf1[1]);
+        mma_bf16_16816(wacc[3], af, bf1[2], bf1[3]);
       }
     }
     // bias gradient partials
     {
-      const int co = tid & 31;
-      for (int pos = tid >> 5; pos < N2_POS; pos += 8) {
-        const int oy = pos / H2, ox = pos - oy * H2;
+      const uint32_t src = dn2b + (tid & 31) * 2;
+      for (int pos = tid >> 5; pos < N2_POS; pos += B12_WARPS) {
         uint16_t v;
-        asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v)
-                     : "r"(dn2p + dn2p_off((oy + 1) * DN2P_W + ox + 1, co >> 3) + (co & 7) * 2));
+        asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(src + pos * DN2B_PITCH));
         bacc += __uint_as_float((uint32_t)v << 16);
       }
     }
     __syncthreads();
     {
       uint4* dst = reinterpret_cast<uint4*>(dn1 + (size_t)b * N1_POS * C1_OUT);
-      for (int i = tid; i < N1_POS * 2; i += CB_THREADS) {
+      for (int i = tid; i < N1_POS * 2; i += B12_THREADS) {
         uint32_t r[4];
         lds128(r, dn1s + i * 16);
         dst[i] = make_uint4(r[0], r[1], r[2], r[3]);
       }
     }
-    __syncthreads();   // dn1s / n1p / dn2p are rewritten by the next iteration
+    __syncthreads();   // dn1s and this input buffer are rewritten by the following iterations
   }
 
 #pragma unroll
-  for (int ti = 0; ti < 2; ++ti) {
-    const int tap = 2 * warp + ti;
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      float* o = g_w12 + (tap * C1_OUT) * C2_OUT + 8 * nt + 2 * t;
-      atomicAdd(o + g * C2_OUT, wacc[ti][nt][0]);
-      atomicAdd(o + g * C2_OUT + 1, wacc[ti][nt][1]);
-      atomicAdd(o + (g + 8) * C2_OUT, wacc[ti][nt][2]);
-      atomicAdd(o + (g + 8) * C2_OUT + 1, wacc[ti][nt][3]);
-    }
+  for (int nt = 0; nt < 4; ++nt) {
+    float* o = g_w12 + (warp * C1_OUT) * C2_OUT + 8 * nt + 2 * t;
+    atomicAdd(o + g * C2_OUT, wacc[nt][0]);
+    atomicAdd(o + g * C2_OUT + 1, wacc[nt][1]);
+    atomicAdd(o + (g + 8) * C2_OUT, wacc[nt][2]);
+    atomicAdd(o + (g + 8) * C2_OUT + 1, wacc[nt][3]);
   }
   red[tid] = bacc;
   __syncthreads();
   if (tid < C2_OUT) {
     float s = 0.f;
 #pragma unroll
-    for (int p = 0; p < 8; ++p) s += red[p * 32 + tid];
+    for (int p = 0; p < B12_WARPS; ++p) s += red[p * 32 + tid];
     atomicAdd(g_b12 + tid, s);
   }
 }
@@ -353,7 +372,7 @@ conv11_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dn
 }
 
 int configure_conv_bwd() {
-  cudaError_t e = cudaFuncSetAttribute(conv12_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C12_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(conv12_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B12_SMEM);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(conv11_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C11_SMEM);
   return (int)e;
@@ -361,8 +380,8 @@ int configure_conv_bwd() {
 
 int launch_conv12_bwd(const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1, float* g_w12,
                       float* g_b12, int batch, int num_sms, cudaStream_t stream) {
-  const int grid = min(batch, 2 * num_sms);
-  conv12_bwd_kernel<<<grid, CB_THREADS, C12_SMEM, stream>>>(n1, dn2, w12, dn1, g_w12, g_b12, batch);
+  const int grid = min(batch, num_sms);
+  conv12_bwd_kernel<<<grid, B12_THREADS, B12_SMEM, stream>>>(n1, dn2, w12, dn1, g_w12, g_b12, batch);
   return (int)cudaGetLastError();
 }
 
