@@ -33,6 +33,8 @@ SIGNATURES = {
     "ga3c_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ga3c_forward_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
                                         C.c_void_p, C.c_void_p]),
+    "ga3c_fb_head": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
+    "ga3c_fb_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "ga3c_apply_rmsprop": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p]),
     "ga3c_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,
                                   C.c_void_p, C.c_void_p]),

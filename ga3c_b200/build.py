@@ -65,7 +65,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         list(ex.map(compile_one, jobs))
     objs = [os.path.join(OBJDIR, s[:-3] + ".o") for s in sources]
     if jobs or force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcuda"]
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -202,7 +202,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 // ---- host side ----------------------------------------------------------------------------------
 // 2-D bf16 row-major matrix [rows][cols] (ld elements between rows), box = 64 inner x box_rows, 128-B swizzle,
 // out-of-bounds elements read as zero (ragged M / N / K tails need no special casing in the kernel).
+// cuTensorMapEncodeTiled is resolved through the runtime (cudaGetDriverEntryPoint) so the library has no
+// link-time dependency on libcuda.so.1 and still loads on a box without a driver (symbol-export test).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
 static int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn cuTensorMapEncodeTiled = encode_tiled_fn();
+  if (!cuTensorMapEncodeTiled) return (int)cudaErrorNotSupported;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * 2};
   cuuint32_t box[2] = {64, box_rows};

@@ -292,10 +292,13 @@ extern "C" int ga3c_predict(ga3c_net* n, const float* x, int32_t batch, float* p
   return 0;
 }
 
-extern "C" int ga3c_forward_backward(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch,
-                                     float beta, float* loss, void* stream) {
-  if (int r = check_batch(n, batch, "ga3c_forward_backward")) return r;
-  if (!x || !yr || !a) return fail_msg("ga3c_forward_backward: null buffer");
+// forward, fused loss forward/backward, and the dense1 weight gradient: on return (in stream order) the
+// gradients of dense1/w, dense1/b, logits_v/*, logits_p/* are final, so their allreduce can start while
+// ga3c_fb_tail computes the conv gradients.
+extern "C" int ga3c_fb_head(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch, float beta,
+                            float* loss, void* stream) {
+  if (int r = check_batch(n, batch, "ga3c_fb_head")) return r;
+  if (!x || !yr || !a) return fail_msg("ga3c_fb_head: null buffer");
   CK(cudaSetDevice(n->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   const float* w = n->w;
@@ -312,19 +315,34 @@ extern "C" int ga3c_forward_backward(ga3c_net* n, const float* x, const float* y
   h.g_wp = g + n->off(P_PW); h.g_bp = g + n->off(P_PB); h.g_wv = g + n->off(P_VW); h.g_bv = g + n->off(P_VB);
   h.g_b1 = g + n->off(P_D1B);
   LAUNCH(n, K_HEADS, st, launch_heads(h, n->num_sms, st));
-  if (n->legacy_dense_bwd) {
-    LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
-    LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
-  } else {
-    LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad_tc(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
-    LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
-  }
+  if (n->legacy_dense_bwd) LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
+  else LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad_tc(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
+  n->last_batch = batch;
+  return 0;
+}
+
+// dense1 data gradient and the two conv backward kernels: completes conv11/* and conv12/* gradients.
+extern "C" int ga3c_fb_tail(ga3c_net* n, const float* x, int32_t batch, void* stream) {
+  if (int r = check_batch(n, batch, "ga3c_fb_tail")) return r;
+  if (!x) return fail_msg("ga3c_fb_tail: null buffer");
+  if (batch != n->last_batch) return fail_msg("ga3c_fb_tail: batch differs from the preceding ga3c_fb_head");
+  CK(cudaSetDevice(n->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const float* w = n->w;
+  float* g = n->g;
+  if (n->legacy_dense_bwd) LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
+  else LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
   LAUNCH(n, K_CONV12_BWD, st, launch_conv12_bwd(n->n1, n->dn2, w + n->off(P_C12W), n->dn1, g + n->off(P_C12W),
                                                 g + n->off(P_C12B), batch, n->num_sms, st));
   LAUNCH(n, K_CONV11_WGRAD, st, launch_conv11_wgrad(x, n->dn1, g + n->off(P_C11W), g + n->off(P_C11B), batch,
                                                     n->num_sms, st));
-  n->last_batch = batch;
   return 0;
+}
+
+extern "C" int ga3c_forward_backward(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch,
+                                     float beta, float* loss, void* stream) {
+  if (int r = ga3c_fb_head(n, x, yr, a, batch, beta, loss, stream)) return r;
+  return ga3c_fb_tail(n, x, batch, stream);
 }
 
 extern "C" int ga3c_apply_rmsprop(ga3c_net* n, float lr, void* stream) {

@@ -83,6 +83,13 @@ int ga3c_set_global_step(ga3c_net* net, int64_t step);
 int ga3c_predict(ga3c_net* net, const float* x_dev, int32_t batch, float* p_dev, float* v_dev, void* stream);
 int ga3c_forward_backward(ga3c_net* net, const float* x_dev, const float* yr_dev, const float* a_dev,
                           int32_t batch, float beta, float* loss_dev, void* stream);
+/* ga3c_forward_backward in two halves, so that a data-parallel host can overlap the gradient allreduce with
+ * the conv backward: after ga3c_fb_head (in stream order) the gradients of dense1/w (98.8 % of the arena, the
+ * last tensor: floats [offset(dense1/w:0), arena_floats)), dense1/b and both heads are final; ga3c_fb_tail
+ * (same batch, same x) then completes the conv11 and conv12 gradients. */
+int ga3c_fb_head(ga3c_net* net, const float* x_dev, const float* yr_dev, const float* a_dev, int32_t batch, float beta,
+                 float* loss_dev, void* stream);
+int ga3c_fb_tail(ga3c_net* net, const float* x_dev, int32_t batch, void* stream);
 int ga3c_apply_rmsprop(ga3c_net* net, float learning_rate, void* stream);
 int ga3c_train_step(ga3c_net* net, const float* x_dev, const float* yr_dev, const float* a_dev,
                     int32_t batch, float learning_rate, float beta, float* loss_dev, void* stream);

@@ -1,0 +1,87 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: the batch is sharded by
+rows, per-rank gradients are SUM-allreduced in two segments (no averaging -- every loss term is a
+reduce_sum, NetworkVP_discrate.py:61,:83-85) and every rank then applies the identical RMSProp update.
+The per-rank arithmetic here is the oracle's (the CUDA kernels need a GPU); what is under test is
+ga3c_b200.dataparallel and the identity grad(full batch) == sum of grad(shards)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle_np as onp
+from ga3c_b200.dataparallel import GradientAllReduce, shard_rows
+
+
+def test_shard_rows_partition():
+    for n in (0, 1, 7, 8, 1024, 1025):
+        for w in (1, 2, 3, 8):
+            cuts = [shard_rows(n, r, w) for r in range(w)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _flatten(tensors, order):
+    return np.concatenate([np.asarray(tensors[k], dtype=np.float64).ravel() for k in order])
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(12345)
+        params = onp.init_params(rng, 6)
+        x = onp.synth_frames(rng, 6)
+        y_r, a = onp.synth_targets(rng, 6)
+        lo, hi = shard_rows(6, rank, world)
+        _, grads = onp.loss_and_grads(params, x[lo:hi], y_r[lo:hi], a[lo:hi])
+        # arena order mirrors the C library: small tensors first, dense1/w last
+        order = [k for k in onp.PARAM_NAMES if k != "dense1/w:0"] + ["dense1/w:0"]
+        arena = torch.from_numpy(_flatten(grads, order))
+        split = arena.numel() - grads["dense1/w:0"].size
+        ar = GradientAllReduce(arena, split)
+        assert ar.enabled
+        ar.start_big()
+        ar.finish()
+        # identical RMSProp update on every rank (fp64 oracle arithmetic)
+        flat_p = _flatten(params, order)
+        ms = 0.99 * np.ones_like(flat_p) + 0.01 * arena.numpy() ** 2
+        new_p = flat_p - 3e-4 * arena.numpy() / np.sqrt(ms + 0.1)
+        gathered = [torch.zeros_like(arena) for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(new_p))
+        assert all(torch.equal(gathered[0], g) for g in gathered)          # replicas stay bit-identical
+        if rank == 0:
+            np.save(os.path.join(out_dir, "reduced.npy"), arena.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sum_allreduce_equals_full_batch_gradient(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    reduced = np.load(tmp_path / "reduced.npy")
+    rng = np.random.default_rng(12345)
+    params = onp.init_params(rng, 6)
+    x = onp.synth_frames(rng, 6)
+    y_r, a = onp.synth_targets(rng, 6)
+    _, full = onp.loss_and_grads(params, x, y_r, a)
+    order = [k for k in onp.PARAM_NAMES if k != "dense1/w:0"] + ["dense1/w:0"]
+    ref = _flatten(full, order)
+    assert np.abs(reduced - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
+def test_allreduce_is_a_no_op_without_a_process_group():
+    arena = torch.arange(10, dtype=torch.float32)
+    ar = GradientAllReduce(arena, 4)
+    assert not ar.enabled
+    ar.start_big(); ar.finish()
+    assert torch.equal(arena, torch.arange(10, dtype=torch.float32))
+    with pytest.raises(ValueError):
+        GradientAllReduce(arena, 11)

@@ -467,3 +467,17 @@ def test_errors_are_raised_not_swallowed(ga3c):
     assert rc != 0 and b"batch" in net._lib.ga3c_last_error()
     p, v = net.predict_p_and_v(np.zeros((0, onp.STATE_DIM), np.float32))
     assert p.shape == (0, 6) and v.shape == (0,)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_data_parallel_two_gpus_matches_concatenated_batch(ga3c):
+    """two ranks (one per GPU, NCCL) on row shards of one global batch == the oracle's single
+    step on the concatenated batch, and the replicas stay bit-identical.  Needs >= 2 visible GPUs."""
+    import subprocess, sys, torch
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (covered on CPU by tests/test_dataparallel.py with gloo)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tools", "dp_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DP_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
