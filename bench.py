@@ -33,6 +33,7 @@ STATE_DIM = 84 * 84 * 4
 NUM_ACTIONS = 6
 N_PARAMS = 1005623
 L2_BYTES = 126 * 2 ** 20
+_REAL_STDOUT = sys.stdout
 
 
 def log(*a):
@@ -209,7 +210,7 @@ def run_reference(args, rank, world):
            "e2e": {"value": r["tps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "pps": {"value": r["pps"], "unit": "predictions/s", "batch": r["prow"]},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_REAL_STDOUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -386,9 +387,18 @@ def run_ours(args, rank, local_rank, world):
                                "sample": f"{r['steps']} train steps of {r['rows']} frames (of B={B})",
                                "pps": r["pps"],
                                "note": "torch-CPU fp32 restatement of the reference TF graph (TensorFlow not installable)"}
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _claim_stdout():
+    """Library chatter (NCCL prints its version on stdout) must not pollute the one-JSON-line contract:
+    point fd 1 at stderr for the whole run and keep the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -405,6 +415,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    global _REAL_STDOUT
+    _REAL_STDOUT = _claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
