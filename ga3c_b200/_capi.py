@@ -36,6 +36,10 @@ SIGNATURES = {
     "ga3c_fb_head": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     "ga3c_fb_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "ga3c_apply_rmsprop": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p]),
+    "ga3c_dp_handle_bytes": (C.c_int, []),
+    "ga3c_dp_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ga3c_dp_attach": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "ga3c_dp_detach": (C.c_int, [C.c_void_p]),
     "ga3c_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,
                                   C.c_void_p, C.c_void_p]),
     "ga3c_returns": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_int32, C.c_double,

@@ -43,6 +43,99 @@ int launch_rmsprop(const RmsPropArgs& a, cudaStream_t stream) {
   return (int)cudaGetLastError();
 }
 
+// ---- data-parallel RMSProp over peer memory ---------------------------------------------------------
+// reduce-scatter(gradients) -> RMSProp on the owned slice -> all-gather(weights), fused in one kernel:
+// the gradient slice is read from every rank's slab with plain loads through NVLink (P2P mappings), the
+// updated fp32 weights and the bf16 shadow of dense1/w are stored into every rank's slab.  Cross-rank
+// ordering uses two monotonically increasing step flags per rank in its own slab:
+//   ready = s  "my gradients of step s are final"       (written when my kernel starts: it is stream-ordered
+//                                                          after my backward)
+//   done  = s  "my slice of step s is stored everywhere" (written by the one-block kernel that follows)
+// No block waits on another block of its own grid, so residency is not required for progress.
+__device__ __forceinline__ uint64_t ld_flag(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_flag(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+
+template <bool HAS_MOM>
+__global__ void __launch_bounds__(512) rmsprop_dp_kernel(RmsPropDpArgs d) {
+  const RmsPropArgs& a = d.base;
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    st_flag(reinterpret_cast<uint64_t*>(d.peer[d.rank] + d.comm_offset), d.step);        // my gradients are final
+  if ((int)threadIdx.x < d.world) {
+    const uint64_t* f = reinterpret_cast<const uint64_t*>(d.peer[threadIdx.x] + d.comm_offset);
+    while (ld_flag(f) < d.step) __nanosleep(64);
+    __threadfence_system();
+  }
+  __syncthreads();
+
+  const int64_t n4 = a.n_floats >> 2;
+  const int64_t per = (n4 + d.world - 1) / d.world;
+  const int64_t lo = per * d.rank, hi = lo + per < n4 ? lo + per : n4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float one_m_rho = 1.f - a.decay;
+  const int64_t g_off = d.arena_bytes, shadow_off = 4 * d.arena_bytes;
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < DP_MAX_WORLD; ++r) {
+      if (r < d.world) {
+        const float4 q = reinterpret_cast<const float4*>(d.peer[r] + g_off)[i];
+        g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+      }
+    }
+    float4 w = reinterpret_cast<float4*>(a.w)[i];
+    float4 ms = reinterpret_cast<float4*>(a.ms)[i];
+    float4 mo = HAS_MOM ? reinterpret_cast<float4*>(a.mom)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#define GA3C_RMS(c)                                                          \
+  ms.c = a.decay * ms.c + one_m_rho * g.c * g.c;                             \
+  mo.c = a.momentum * mo.c + a.lr * g.c / sqrtf(ms.c + a.eps);              \
+  w.c -= mo.c;
+    GA3C_RMS(x) GA3C_RMS(y) GA3C_RMS(z) GA3C_RMS(w)
+#undef GA3C_RMS
+    reinterpret_cast<float4*>(a.ms)[i] = ms;
+    if (HAS_MOM) reinterpret_cast<float4*>(a.mom)[i] = mo;
+    reinterpret_cast<float4*>(const_cast<float*>(a.g))[i] = g;       // the reduced gradient of the owned slice (introspection)
+    const int64_t e = i << 2;
+    const bool in_w1 = e >= a.w1_offset && e < a.w1_offset + a.w1_count;
+    const uint2 sh = make_uint2(pack_bf16(w.x, w.y), pack_bf16(w.z, w.w));
+#pragma unroll
+    for (int r = 0; r < DP_MAX_WORLD; ++r) {
+      if (r < d.world) {
+        reinterpret_cast<float4*>(d.peer[r])[i] = w;
+        if (in_w1) reinterpret_cast<uint2*>(d.peer[r] + shadow_off)[(e - a.w1_offset) >> 2] = sh;
+      }
+    }
+  }
+  __threadfence_system();
+}
+
+__global__ void __launch_bounds__(32) dp_done_kernel(RmsPropDpArgs d) {
+  // stream-ordered after rmsprop_dp_kernel: every store of my slice has been issued and fenced
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    st_flag(reinterpret_cast<uint64_t*>(d.peer[d.rank] + d.comm_offset + 64), d.step);
+  }
+  if ((int)threadIdx.x < d.world) {
+    const uint64_t* f = reinterpret_cast<const uint64_t*>(d.peer[threadIdx.x] + d.comm_offset + 64);
+    while (ld_flag(f) < d.step) __nanosleep(64);
+    __threadfence_system();
+  }
+}
+
+int launch_rmsprop_dp(const RmsPropDpArgs& d, int num_sms, cudaStream_t stream) {
+  if (d.base.momentum != 0.f) rmsprop_dp_kernel<true><<<num_sms, 512, 0, stream>>>(d);
+  else rmsprop_dp_kernel<false><<<num_sms, 512, 0, stream>>>(d);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  dp_done_kernel<<<1, 32, 0, stream>>>(d);
+  return (int)cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int64_t n4) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {

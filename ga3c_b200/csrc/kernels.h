@@ -68,6 +68,17 @@ struct RmsPropArgs {
   float lr, decay, momentum, eps;
 };
 int launch_rmsprop(const RmsPropArgs& a, cudaStream_t stream);
+// data-parallel RMSProp over peer memory: rank r owns arena slice r; it sums that slice of every rank's gradient
+// arena (fixed rank order), applies RMSProp, and stores the new weights (+ bf16 shadow) into every rank's slab.
+constexpr int DP_MAX_WORLD = 8;
+struct RmsPropDpArgs {
+  RmsPropArgs base;                 // this rank's own arenas
+  uint8_t* peer[DP_MAX_WORLD];      // slab bases: [params | grads | ms | mom | shadow | comm]
+  int rank, world;
+  uint64_t step;                    // 1, 2, ... : value the ready / done flags reach in this step
+  int64_t arena_bytes, comm_offset;
+};
+int launch_rmsprop_dp(const RmsPropDpArgs& a, int num_sms, cudaStream_t stream);
 int launch_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cudaStream_t stream);
 int launch_returns(const double* rewards, const int64_t* seg_offsets, int n_segments, const double* terminal,
                    double discount, int flags, double rmin, double rmax, double* out, cudaStream_t stream);

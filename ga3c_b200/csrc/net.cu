@@ -52,8 +52,16 @@ struct ga3c_net {
   std::vector<ParamDesc> params;   // TF creation order
   int64_t arena_floats = 0;
   int64_t small_floats = 0;        // prefix holding every tensor except dense1/w (grads zeroed per step)
+  // one slab holds [params | grads | ms | mom | bf16 shadow of dense1/w | comm flags]: a single CUDA IPC handle
+  // exposes everything a data-parallel peer needs (ga3c_dp_*)
+  uint8_t* slab = nullptr;
+  size_t slab_bytes = 0;
   float *w = nullptr, *g = nullptr, *ms = nullptr, *mom = nullptr;
   uint16_t* w1_shadow = nullptr;   // bf16 [3872,256]
+  // data parallel over peer memory (single node, <= 8 ranks)
+  int dp_rank = 0, dp_world = 1;
+  uint8_t* dp_peer[DP_MAX_WORLD] = {};   // slab base of every rank as mapped in this process (own slab at dp_rank)
+  uint64_t dp_step = 0;
   // workspace
   uint16_t *n1 = nullptr, *n2 = nullptr, *dd1 = nullptr, *dn2 = nullptr, *dn1 = nullptr;
   float* d1 = nullptr;
@@ -69,6 +77,8 @@ struct ga3c_net {
 
   int64_t off(int i) const { return params[i].offset; }
 };
+
+constexpr int DP_COMM_BYTES = 256;    // [0] ready step, [8] done step (uint64 at 64-byte spacing)
 
 enum { K_CONV_FWD = 0, K_DENSE_FWD, K_HEADS, K_DENSE_WGRAD, K_DENSE_DGRAD, K_CONV12_BWD, K_CONV11_WGRAD, K_RMSPROP,
        K_COUNT };
@@ -143,9 +153,16 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
     cudaError_t _e = cudaMalloc((void**)&(ptr), (bytes));                        \
     if (_e != cudaSuccess) { ga3c_destroy(n); return fail("cudaMalloc", _e); }   \
   } while (0)
-  GA3C_ALLOC(n->w, ab); GA3C_ALLOC(n->g, ab); GA3C_ALLOC(n->ms, ab); GA3C_ALLOC(n->mom, ab);
-  GA3C_ALLOC(n->w1_shadow, (size_t)FLAT * FC * 2);
+  const size_t shadow_bytes = (size_t)FLAT * FC * 2;
+  n->slab_bytes = 4 * ab + shadow_bytes + DP_COMM_BYTES;
+  GA3C_ALLOC(n->slab, n->slab_bytes);
 #undef GA3C_ALLOC
+  n->w = reinterpret_cast<float*>(n->slab);
+  n->g = reinterpret_cast<float*>(n->slab + ab);
+  n->ms = reinterpret_cast<float*>(n->slab + 2 * ab);
+  n->mom = reinterpret_cast<float*>(n->slab + 3 * ab);
+  n->w1_shadow = reinterpret_cast<uint16_t*>(n->slab + 4 * ab);
+  cudaMemset(n->slab + 4 * ab + shadow_bytes, 0, DP_COMM_BYTES);
   if (int r = alloc_workspace(n, cfg->max_batch)) { ga3c_destroy(n); return r; }
   cudaMemset(n->w, 0, ab); cudaMemset(n->g, 0, ab); cudaMemset(n->mom, 0, ab);
   cudaMemset(n->w1_shadow, 0, (size_t)FLAT * FC * 2);
@@ -195,7 +212,8 @@ extern "C" int ga3c_reserve(ga3c_net* n, int32_t max_batch) {
 
 extern "C" int ga3c_destroy(ga3c_net* n) {
   if (!n) return 0;
-  cudaFree(n->w); cudaFree(n->g); cudaFree(n->ms); cudaFree(n->mom); cudaFree(n->w1_shadow);
+  ga3c_dp_detach(n);
+  cudaFree(n->slab);
   free_workspace(n);
   for (cudaEvent_t e : n->tev) cudaEventDestroy(e);
   delete n;
@@ -352,8 +370,63 @@ extern "C" int ga3c_apply_rmsprop(ga3c_net* n, float lr, void* stream) {
   a.w = n->w; a.ms = n->ms; a.mom = n->mom; a.g = n->g; a.w1_shadow = n->w1_shadow;
   a.n_floats = n->arena_floats; a.w1_offset = n->off(P_D1W); a.w1_count = (int64_t)FLAT * FC;
   a.lr = lr; a.decay = n->cfg.rmsprop_decay; a.momentum = n->cfg.rmsprop_momentum; a.eps = n->cfg.rmsprop_epsilon;
-  LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop(a, (cudaStream_t)stream));
+  if (n->dp_world > 1) {
+    // fused reduce-scatter(grads) -> RMSProp on this rank's slice -> all-gather(weights) over peer memory
+    RmsPropDpArgs d{};
+    d.base = a;
+    for (int r = 0; r < n->dp_world; ++r) d.peer[r] = n->dp_peer[r];
+    d.rank = n->dp_rank; d.world = n->dp_world; d.step = ++n->dp_step;
+    d.arena_bytes = (int64_t)n->arena_floats * 4;
+    d.comm_offset = 4 * d.arena_bytes + (int64_t)FLAT * FC * 2;
+    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_dp(d, n->num_sms, (cudaStream_t)stream));
+  } else {
+    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop(a, (cudaStream_t)stream));
+  }
   n->global_step += 1;   // opt.minimize(..., global_step=self.global_step), NetworkVP_discrate.py:130
+  return 0;
+}
+
+// ---- data parallel over CUDA IPC peer memory ---------------------------------------------------------
+extern "C" int ga3c_dp_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+extern "C" int ga3c_dp_export(ga3c_net* n, void* handle_out) {
+  if (!n || !handle_out) return fail_msg("ga3c_dp_export: null argument");
+  CK(cudaSetDevice(n->cfg.device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, n->slab));
+  memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+
+extern "C" int ga3c_dp_detach(ga3c_net* n) {
+  if (!n) return 0;
+  for (int r = 0; r < DP_MAX_WORLD; ++r)
+    if (n->dp_peer[r] && n->dp_peer[r] != n->slab) cudaIpcCloseMemHandle(n->dp_peer[r]);
+  for (int r = 0; r < DP_MAX_WORLD; ++r) n->dp_peer[r] = nullptr;
+  n->dp_world = 1; n->dp_rank = 0;
+  return 0;
+}
+
+extern "C" int ga3c_dp_attach(ga3c_net* n, int32_t rank, int32_t world, const void* handles) {
+  if (!n || !handles) return fail_msg("ga3c_dp_attach: null argument");
+  if (world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world)
+    return fail_msg("ga3c_dp_attach: world must be 1.." + std::to_string(DP_MAX_WORLD) + " and 0 <= rank < world");
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaDeviceSynchronize());
+  ga3c_dp_detach(n);
+  const cudaIpcMemHandle_t* hs = static_cast<const cudaIpcMemHandle_t*>(handles);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { n->dp_peer[r] = n->slab; continue; }
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, hs[r], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      ga3c_dp_detach(n);
+      return fail("cudaIpcOpenMemHandle (peer-to-peer access between the ranks' GPUs is required)", e);
+    }
+    n->dp_peer[r] = static_cast<uint8_t*>(p);
+  }
+  n->dp_rank = rank; n->dp_world = world; n->dp_step = 0;
+  CK(cudaMemset(n->slab + n->slab_bytes - DP_COMM_BYTES, 0, DP_COMM_BYTES));
   return 0;
 }
 

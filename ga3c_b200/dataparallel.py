@@ -65,3 +65,13 @@ class GradientAllReduce:
         with torch.cuda.stream(stream):
             dist.all_reduce(self.small, op=dist.ReduceOp.SUM, group=self.group)
         stream.wait_event(self._ev_done)
+
+
+def exchange_ipc_handles(mine: bytes, device: torch.device, group=None) -> bytes:
+    """all_gather of one fixed-size opaque handle per rank (CUDA IPC handle of the rank's state slab);
+    returns the handles concatenated in rank order."""
+    world = dist.get_world_size(group)
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    return b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)

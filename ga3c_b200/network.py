@@ -49,7 +49,7 @@ class _DevArray:
 
 class Network:
     def __init__(self, device, model_name, num_actions, state_dim=STATE_DIM, *, config=None, max_batch=None,
-                 seed=None, data_parallel=None):
+                 seed=None, data_parallel=None, dp_mode=None):
         cfg = config or _DefaultConfig
         self.config = cfg
         self.device = device
@@ -111,11 +111,28 @@ class Network:
 
         # data parallelism: gradients are SUM-allreduced (no averaging: the loss is sum-reduced,
         # NetworkVP_discrate.py:61,:83-85), then every rank applies the identical RMSProp update
-        from .dataparallel import GradientAllReduce
+        #   dp_mode "fused" (default): reduce-scatter + RMSProp + all-gather in ONE kernel over CUDA-IPC peer
+        #                             memory (ga3c_dp_attach); no collective library call on the step's critical path
+        #   dp_mode "nccl"          : two-segment NCCL allreduce overlapping the conv backward, then local RMSProp
+        from .dataparallel import GradientAllReduce, exchange_ipc_handles
         self._allreduce = GradientAllReduce(self._grad_arena, self._table["dense1/w:0"][0])
         if data_parallel is False:
             self._allreduce.enabled = False
-        self._dp = self._allreduce.enabled
+        self.dp_mode = None
+        if self._allreduce.enabled:
+            self.dp_mode = dp_mode or os.environ.get("GA3C_DP", "fused")
+            if self.dp_mode not in ("fused", "nccl"):
+                raise ValueError(f"dp_mode must be 'fused' or 'nccl', got {self.dp_mode!r}")
+        if self.dp_mode == "fused":
+            import torch.distributed as dist
+            n = self._lib.ga3c_dp_handle_bytes()
+            mine = C.create_string_buffer(n)
+            _capi.check(self._lib.ga3c_dp_export(self._h, mine), "ga3c_dp_export")
+            handles = exchange_ipc_handles(mine.raw, self._tdev)
+            _capi.check(self._lib.ga3c_dp_attach(self._h, dist.get_rank(), dist.get_world_size(), handles),
+                        "ga3c_dp_attach")
+            dist.barrier(device_ids=[self._ordinal])      # every rank has mapped every slab before the first step
+        self._dp = self.dp_mode == "nccl"
         self.last_losses = None
 
     # ------------------------------------------------------------------ buffers
@@ -155,6 +172,7 @@ class Network:
     def __del__(self):
         try:
             if getattr(self, "_h", None):
+                self._lib.ga3c_dp_detach(self._h)
                 self._lib.ga3c_destroy(self._h)
                 self._h = None
         except Exception:

@@ -94,6 +94,20 @@ int ga3c_apply_rmsprop(ga3c_net* net, float learning_rate, void* stream);
 int ga3c_train_step(ga3c_net* net, const float* x_dev, const float* yr_dev, const float* a_dev,
                     int32_t batch, float learning_rate, float beta, float* loss_dev, void* stream);
 
+/* ---- data parallel over peer memory (one process per GPU, one node, <= 8 ranks) ---------------------
+ * Every rank exports a CUDA IPC handle of its state slab (ga3c_dp_export), the host exchanges the handles
+ * (torch.distributed all_gather in ga3c_b200.Network) and attaches them in rank order (ga3c_dp_attach).  From
+ * then on ga3c_apply_rmsprop is ONE fused kernel per rank: wait until every rank's gradients of this step are
+ * final, sum this rank's slice of all gradient arenas over NVLink (fixed rank order => replicas bit-identical),
+ * apply RMSProp to the slice, store the new weights into every rank's slab -- followed by a one-block kernel
+ * that publishes "done" and waits for the other ranks, so the next forward sees all slices.  SUM, no averaging:
+ * every loss term is a reduce_sum (NetworkVP_discrate.py:61,:83-85).  All ranks must call train the same number
+ * of times. */
+int ga3c_dp_handle_bytes(void);
+int ga3c_dp_export(ga3c_net* net, void* handle_out);
+int ga3c_dp_attach(ga3c_net* net, int32_t rank, int32_t world, const void* handles);
+int ga3c_dp_detach(ga3c_net* net);
+
 /* ---- returns (ProcessAgent.py:70-84) --------------------------------------------------------
  * Segments (one per agent rollout) are packed back to back; seg_offsets_dev has n_segments+1
  * entries.  fp64 throughout, same operation order as the reference loop => bit-exact.

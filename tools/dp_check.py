@@ -20,7 +20,8 @@ rng = np.random.default_rng(12345)
 params = onp.init_params(rng, 6)
 net = ga3c_b200.Network(f"gpu:{local}", "dp", 6, max_batch=64)
 net.set_variables(params)
-assert net._dp
+assert net.dp_mode in ("fused", "nccl")
+print(f"rank {rank}: dp_mode={net.dp_mode}", flush=True)
 ms, mom = onp.rmsprop_init(params)
 ref = params
 for step in range(3):
