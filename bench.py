@@ -77,6 +77,8 @@ def kernel_work(name, b, train):
         return "hbm", b * (fc * 4 + (fc * 2 + 4 + NUM_ACTIONS * 4 if train else (NUM_ACTIONS + 1) * 4))
     if name == "rmsprop":
         return "hbm", N_PARAMS * 20 + n2 * fc * 2
+    if name == "dp_done":
+        return "hbm", 128
     if name in ("dense_fwd", "dense_wgrad", "dense_dgrad"):
         return "tensor", 2.0 * b * n2 * fc
     raise KeyError(name)
@@ -296,13 +298,14 @@ def run_ours(args, rank, local_rank, world):
     ms_pred = timed(predict_step, K)
 
     # ---- per-kernel durations, live, with events on the launch stream (roofline leg) ----
-    net.kernel_timing(K * 8)
+    net.kernel_timing(K * 10)
     ms_train_ev = timed(train_step, K)
     kt_train = net.kernel_times()
     net.kernel_timing(K * 3)
     ms_pred_ev = timed(predict_step, K)
     kt_pred = net.kernel_times()
     net.kernel_timing(0)
+    log(f"[bench] rank {rank} train kernels (us): " + ", ".join(f"{k} {t / max(c, 1) * 1e3:.1f}" for k, (t, c) in kt_train.items() if c))
 
     # ---- e2e through the public API on pinned host buffers ----
     def e2e(fn, steps):

@@ -44,14 +44,17 @@ int launch_rmsprop(const RmsPropArgs& a, cudaStream_t stream) {
 }
 
 // ---- data-parallel RMSProp over peer memory ---------------------------------------------------------
-// reduce-scatter(gradients) -> RMSProp on the owned slice -> all-gather(weights), fused in one kernel:
+// reduce-scatter(gradients) -> RMSProp on the owned slice -> all-gather(weights), fused in ONE kernel:
 // the gradient slice is read from every rank's slab with plain loads through NVLink (P2P mappings), the
 // updated fp32 weights and the bf16 shadow of dense1/w are stored into every rank's slab.  Cross-rank
-// ordering uses two monotonically increasing step flags per rank in its own slab:
-//   ready = s  "my gradients of step s are final"       (written when my kernel starts: it is stream-ordered
-//                                                          after my backward)
-//   done  = s  "my slice of step s is stored everywhere" (written by the one-block kernel that follows)
-// No block waits on another block of its own grid, so residency is not required for progress.
+// ordering uses two monotonically increasing step flags per rank, kept in its own slab:
+//   ready = s  "my gradients of step s are final"        written when my kernel starts (it is stream-ordered
+//                                                          after my backward); every block waits for all ranks
+//   done  = s  "my slice of step s is stored everywhere"  written by the LAST block of my grid to finish, which
+//                                                          then waits for every rank's done before the kernel ends,
+//                                                          so the next forward (stream-ordered) sees all slices
+// No block waits on another block of its own grid, so progress does not depend on co-residency.
+// comm block layout (bytes): [0] ready u64, [64] done u64, [128] finished-block counter u32
 __device__ __forceinline__ uint64_t ld_flag(const uint64_t* p) {
   uint64_t v;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
@@ -64,11 +67,11 @@ __device__ __forceinline__ void st_flag(uint64_t* p, uint64_t v) {
 template <bool HAS_MOM>
 __global__ void __launch_bounds__(512) rmsprop_dp_kernel(RmsPropDpArgs d) {
   const RmsPropArgs& a = d.base;
-  if (blockIdx.x == 0 && threadIdx.x == 0)
-    st_flag(reinterpret_cast<uint64_t*>(d.peer[d.rank] + d.comm_offset), d.step);        // my gradients are final
+  uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
+  if (blockIdx.x == 0 && threadIdx.x == 0) st_flag(reinterpret_cast<uint64_t*>(my_comm), d.step);   // my gradients are final
   if ((int)threadIdx.x < d.world) {
     const uint64_t* f = reinterpret_cast<const uint64_t*>(d.peer[threadIdx.x] + d.comm_offset);
-    while (ld_flag(f) < d.step) __nanosleep(64);
+    while (ld_flag(f) < d.step) __nanosleep(32);
     __threadfence_system();
   }
   __syncthreads();
@@ -111,18 +114,24 @@ __global__ void __launch_bounds__(512) rmsprop_dp_kernel(RmsPropDpArgs d) {
       }
     }
   }
-  __threadfence_system();
-}
 
-__global__ void __launch_bounds__(32) dp_done_kernel(RmsPropDpArgs d) {
-  // stream-ordered after rmsprop_dp_kernel: every store of my slice has been issued and fenced
+  // publish "done" once the whole grid has stored its part, then hold the kernel open until every rank is done
+  __shared__ int last;
+  __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
-    st_flag(reinterpret_cast<uint64_t*>(d.peer[d.rank] + d.comm_offset + 64), d.step);
+    __threadfence_system();            // cumulative: orders the block's peer stores (observed through the barrier)
+    unsigned int* ctr = reinterpret_cast<unsigned int*>(my_comm + 128);
+    last = atomicAdd(ctr, 1u) == gridDim.x - 1;
+    if (last) {
+      *ctr = 0;
+      __threadfence_system();
+      st_flag(reinterpret_cast<uint64_t*>(my_comm + 64), d.step);
+    }
   }
-  if ((int)threadIdx.x < d.world) {
+  __syncthreads();
+  if (last && (int)threadIdx.x < d.world) {
     const uint64_t* f = reinterpret_cast<const uint64_t*>(d.peer[threadIdx.x] + d.comm_offset + 64);
-    while (ld_flag(f) < d.step) __nanosleep(64);
+    while (ld_flag(f) < d.step) __nanosleep(32);
     __threadfence_system();
   }
 }
@@ -130,9 +139,6 @@ __global__ void __launch_bounds__(32) dp_done_kernel(RmsPropDpArgs d) {
 int launch_rmsprop_dp(const RmsPropDpArgs& d, int num_sms, cudaStream_t stream) {
   if (d.base.momentum != 0.f) rmsprop_dp_kernel<true><<<num_sms, 512, 0, stream>>>(d);
   else rmsprop_dp_kernel<false><<<num_sms, 512, 0, stream>>>(d);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return (int)e;
-  dp_done_kernel<<<1, 32, 0, stream>>>(d);
   return (int)cudaGetLastError();
 }
 

@@ -99,8 +99,8 @@ int ga3c_train_step(ga3c_net* net, const float* x_dev, const float* yr_dev, cons
  * (torch.distributed all_gather in ga3c_b200.Network) and attaches them in rank order (ga3c_dp_attach).  From
  * then on ga3c_apply_rmsprop is ONE fused kernel per rank: wait until every rank's gradients of this step are
  * final, sum this rank's slice of all gradient arenas over NVLink (fixed rank order => replicas bit-identical),
- * apply RMSProp to the slice, store the new weights into every rank's slab -- followed by a one-block kernel
- * that publishes "done" and waits for the other ranks, so the next forward sees all slices.  SUM, no averaging:
+ * apply RMSProp to the slice, store the new weights into every rank's slab; the last block to finish publishes
+ * "done" and holds the kernel open until every rank is done, so the next forward sees all slices.  SUM, no averaging:
  * every loss term is a reduce_sum (NetworkVP_discrate.py:61,:83-85).  All ranks must call train the same number
  * of times. */
 int ga3c_dp_handle_bytes(void);
