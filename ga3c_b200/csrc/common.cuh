@@ -107,6 +107,19 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 
+// ---- fp32 frame staging ring (conv_fwd, conv11_wgrad) ---------------------------------------------
+// A frame (112,896 B, dense NHWC fp32) is streamed by the TMA engine into a shared-memory staging buffer in
+// STG_CHUNKS chunks, each signalled on its own mbarrier.  The consumer converts chunk c, and as soon as every
+// thread is done with it re-arms that chunk with the NEXT frame's bytes -- so about one full frame is always
+// in flight per SM, which is what a 1/148 share of HBM bandwidth needs (112,896 B at ~44 GB/s = 2.6 us).
+constexpr int FRAME_BYTES = STATE_DIM * 4;                         // 112,896
+constexpr int STG_CHUNKS = 4, STG_CHUNK_BYTES = FRAME_BYTES / STG_CHUNKS, STG_CHUNK_PIX = IMG * IMG / STG_CHUNKS;   // 28,224 B, 1,764 px
+static_assert(STG_CHUNK_BYTES % 16 == 0 && STG_CHUNK_PIX * STG_CHUNKS == IMG * IMG, "chunking must be exact");
+__device__ __forceinline__ void stg_issue_chunk(uint32_t stg, const float* frame, int c, uint32_t bars) {
+  mbar_expect_tx(bars + 8 * c, STG_CHUNK_BYTES);
+  bulk_load(stg + c * STG_CHUNK_BYTES, reinterpret_cast<const uint8_t*>(frame) + c * STG_CHUNK_BYTES, STG_CHUNK_BYTES, bars + 8 * c);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -229,16 +229,14 @@ conv12_bwd_kernel(const uint16_t* __restrict__ n1, const uint16_t* __restrict__ 
 //   all warps  : wait -> fp32 staging -> padded bf16 image -> [issue frame i+1] -> wgrad MMAs
 // warp = (kh, part): M tile pair (kh, half 0/1) x N 16, K = the 14 k16 position steps of its part.
 constexpr int W11_THREADS = 512;
-constexpr int W11_FRAME_BYTES = STATE_DIM * 4;                    // 112,896
-constexpr int W11_CHUNKS = 8, W11_CHUNK_BYTES = W11_FRAME_BYTES / W11_CHUNKS;
 constexpr int DN1S_ROWS = 448;                                    // 441 padded to 28 k16 steps
 constexpr int DN1S_BYTES = DN1S_ROWS * 32;                        // 14,336
 constexpr int C11_OFF_STG = 0;
-constexpr int C11_OFF_XS = C11_OFF_STG + W11_FRAME_BYTES;         // 112,896
+constexpr int C11_OFF_XS = C11_OFF_STG + FRAME_BYTES;         // 112,896
 constexpr int C11_OFF_DN1S = C11_OFF_XS + XS_BYTES;               // 174,848 (two buffers)
 constexpr int C11_OFF_RED = C11_OFF_DN1S + 2 * DN1S_BYTES;        // 203,520
 constexpr int C11_OFF_BAR = C11_OFF_RED + W11_THREADS * 4;        // 205,568
-constexpr int C11_SMEM = C11_OFF_BAR + 16;                        // 205,584
+constexpr int C11_SMEM = C11_OFF_BAR + 8 * STG_CHUNKS;            // 205,600
 
 // 16-B chunk h (pixels 2h, 2h+1) of pixel quad q sits at h ^ ((q >> 2) & 1): the transposed ldmatrix
 // reads of 8 consecutive positions (32 B apart) then touch all 32 banks once
@@ -255,13 +253,6 @@ __device__ __forceinline__ void w11_prefetch_dn1(const uint16_t* __restrict__ dn
   }
 }
 
-__device__ __forceinline__ void w11_issue_frame(uint32_t stg, const float* src, uint32_t bar) {
-  mbar_expect_tx(bar, W11_FRAME_BYTES);
-#pragma unroll
-  for (int c = 0; c < W11_CHUNKS; ++c)
-    bulk_load(stg + c * W11_CHUNK_BYTES, reinterpret_cast<const uint8_t*>(src) + c * W11_CHUNK_BYTES, W11_CHUNK_BYTES, bar);
-}
-
 __global__ void __launch_bounds__(W11_THREADS, 1)
 conv11_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dn1, float* __restrict__ g_w11,
                     float* __restrict__ g_b11, int batch) {
@@ -275,14 +266,15 @@ conv11_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dn
   const int stride = gridDim.x;
 
   if (tid == 0) {
-    mbar_init(bar, 1);
+    for (int c = 0; c < STG_CHUNKS; ++c) mbar_init(bar + 8 * c, 1);
     fence_mbar_init();
   }
   for (int i = tid; i < (XS_BYTES + 2 * DN1S_BYTES) / 16; i += W11_THREADS) sts128(xs + i * 16, make_uint4(0, 0, 0, 0));
   __syncthreads();
   int b = blockIdx.x;
   if (b < batch) {
-    if (tid == 0) w11_issue_frame(stg, x + (size_t)b * STATE_DIM, bar);
+    if (tid == 0)
+      for (int c = 0; c < STG_CHUNKS; ++c) stg_issue_chunk(stg, x + (size_t)b * STATE_DIM, c, bar);
     w11_prefetch_dn1(dn1, b, sbase + C11_OFF_DN1S, tid);
   }
   cp_async_commit();
@@ -294,28 +286,28 @@ conv11_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dn
   int buf = 0;
   for (; b < batch; b += stride, buf ^= 1) {
     const uint32_t dn1s = sbase + C11_OFF_DN1S + buf * DN1S_BYTES;
-    mbar_wait(bar, phase);                    // frame b has landed in the staging buffer
-    phase ^= 1;
-    {                                         // fp32 staging -> zero-bordered, chunk-swizzled bf16 image
-      constexpr int NPIX = IMG * IMG;
+    const bool more = b + stride < batch;
+    cp_async_wait<0>();                       // dn1(b): visible to all after the first barrier below
+#pragma unroll 1
+    for (int c = 0; c < STG_CHUNKS; ++c) {    // fp32 staging -> zero-bordered, chunk-swizzled bf16 image
+      mbar_wait(bar + 8 * c, phase);
 #pragma unroll 2
-      for (int i = tid; i < NPIX; i += W11_THREADS) {
+      for (int k = tid; k < STG_CHUNK_PIX; k += W11_THREADS) {
+        const int i = c * STG_CHUNK_PIX + k;
         uint32_t r[4];
         lds128(r, stg + i * 16);
         const int y = i / IMG, px = i - y * IMG + 2;
         sts64(xs + (y + 2) * XS_ROW_BYTES + xs_chunk_off(px & ~1) + (px & 1) * 8,
               pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1])), pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3])));
       }
-    }
-    cp_async_wait<0>();                       // dn1(b)
-    __syncthreads();                          // staging and the other dn1 buffer are free; image + dn1(b) complete
-    if (b + stride < batch) {
-      if (tid == 0) {
+      __syncthreads();                        // chunk c is free (after the last one: image + dn1(b) complete)
+      if (tid == 0 && more) {
         fence_proxy_async();
-        w11_issue_frame(stg, x + (size_t)(b + stride) * STATE_DIM, bar);
+        stg_issue_chunk(stg, x + (size_t)(b + stride) * STATE_DIM, c, bar);
       }
-      w11_prefetch_dn1(dn1, b + stride, sbase + C11_OFF_DN1S + (buf ^ 1) * DN1S_BYTES, tid);
     }
+    phase ^= 1;
+    if (more) w11_prefetch_dn1(dn1, b + stride, sbase + C11_OFF_DN1S + (buf ^ 1) * DN1S_BYTES, tid);
     cp_async_commit();
 
 #pragma unroll 2

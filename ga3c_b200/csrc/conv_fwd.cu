@@ -12,7 +12,7 @@
 // converted once, stays on chip, and conv11's output never leaves the SM before conv12 consumes it.
 //
 // Pipeline per frame (HBM traffic: the fp32 frame, 112,896 B / sample, read exactly once):
-//   TMA engine : cp.async.bulk of frame i+1 (8 chunks) into the fp32 staging buffer, signalled on an mbarrier
+//   TMA engine : cp.async.bulk of frame i+1 into the fp32 staging buffer, 4 chunks, each re-armed as soon as it is consumed
 //   all warps  : wait(frame i) -> fp32 staging -> padded bf16 image -> [issue frame i+1] -> conv11 -> conv12 -> stores
 // Measured limits (profiles/): shared-memory wavefronts (74 % of peak) and the legacy HMMA pipe
 // (33 % active; its ceiling is ~44 M frames/s, below the 58 M frames/s HBM roofline).
@@ -22,9 +22,6 @@
 namespace ga3c {
 
 constexpr int CF_THREADS = 512, CF_WARPS = CF_THREADS / 32;
-constexpr int FRAME_BYTES = STATE_DIM * 4;                  // 112,896
-constexpr int CF_CHUNKS = 8, CF_CHUNK_BYTES = FRAME_BYTES / CF_CHUNKS;   // 14,112 = 16 * 882
-static_assert(CF_CHUNK_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
 constexpr int CF_OFF_STG = 0;
 constexpr int CF_OFF_XS = CF_OFF_STG + FRAME_BYTES;         // 112,896
 constexpr int CF_OFF_N1P = CF_OFF_XS + XS_BYTES;            // 174,848
@@ -32,27 +29,20 @@ constexpr int CF_OFF_W12F = CF_OFF_N1P + N1P_BYTES;         // 193,280
 constexpr int CF_OFF_N2S = CF_OFF_W12F + 16 * 2 * 32 * 16;  // 209,664
 constexpr int CF_OFF_BIAS = CF_OFF_N2S + N2_POS * 64;       // 217,408
 constexpr int CF_OFF_BAR = CF_OFF_BIAS + (C1_OUT + C2_OUT) * 4;   // 217,600
-constexpr int CF_SMEM = CF_OFF_BAR + 16;                    // 217,616 <= 232,448
+constexpr int CF_SMEM = CF_OFF_BAR + 8 * STG_CHUNKS;        // 217,632 <= 232,448
 
-// fp32 staging (dense NHWC frame) -> zero-bordered bf16 image, 8 B per pixel
+// one chunk of the fp32 staging buffer (dense NHWC) -> zero-bordered bf16 image, 8 B per pixel
 template <int NT>
-__device__ __forceinline__ void convert_frame(uint32_t stg, uint32_t xs, int tid) {
-  constexpr int NPIX = IMG * IMG;
+__device__ __forceinline__ void convert_chunk(uint32_t stg, uint32_t xs, int c, int tid) {
 #pragma unroll 2
-  for (int i = tid; i < NPIX; i += NT) {
+  for (int k = tid; k < STG_CHUNK_PIX; k += NT) {
+    const int i = c * STG_CHUNK_PIX + k;
     uint32_t r[4];
     lds128(r, stg + i * 16);
     const int y = i / IMG, xx = i - y * IMG;
     sts64(xs + (y + 2) * XS_ROW_BYTES + (xx + 2) * 8,
           pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1])), pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3])));
   }
-}
-
-__device__ __forceinline__ void issue_frame(uint32_t stg, const float* src, uint32_t bar) {
-  mbar_expect_tx(bar, FRAME_BYTES);
-#pragma unroll
-  for (int c = 0; c < CF_CHUNKS; ++c)
-    bulk_load(stg + c * CF_CHUNK_BYTES, reinterpret_cast<const uint8_t*>(src) + c * CF_CHUNK_BYTES, CF_CHUNK_BYTES, bar);
 }
 
 __global__ void __launch_bounds__(CF_THREADS, 1)
@@ -67,12 +57,13 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
 
   if (tid == 0) {
-    mbar_init(bar, 1);
+    for (int c = 0; c < STG_CHUNKS; ++c) mbar_init(bar + 8 * c, 1);
     fence_mbar_init();
   }
   __syncthreads();
   int b = blockIdx.x;
-  if (tid == 0 && b < batch) issue_frame(stg, x + (size_t)b * STATE_DIM, bar);   // overlaps the weight setup below
+  if (tid == 0 && b < batch)                                      // overlaps the weight setup below
+    for (int c = 0; c < STG_CHUNKS; ++c) stg_issue_chunk(stg, x + (size_t)b * STATE_DIM, c, bar);
 
   // zero the padded buffers once: the borders are never written again
   for (int i = tid; i < (XS_BYTES + N1P_BYTES) / 16; i += CF_THREADS) sts128(xs + i * 16, make_uint4(0, 0, 0, 0));
@@ -108,14 +99,18 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
 
   uint32_t phase = 0;
   for (; b < batch; b += gridDim.x) {
-    mbar_wait(bar, phase);                    // frame b has landed in the staging buffer
-    phase ^= 1;
-    convert_frame<CF_THREADS>(stg, xs, tid);
-    __syncthreads();                          // staging is free again, the bf16 image is complete
-    if (tid == 0 && b + (int)gridDim.x < batch) {
-      fence_proxy_async();                    // order the generic-proxy reads above before the async-proxy refill
-      issue_frame(stg, x + (size_t)(b + gridDim.x) * STATE_DIM, bar);
+    const bool more = b + (int)gridDim.x < batch;
+#pragma unroll 1
+    for (int c = 0; c < STG_CHUNKS; ++c) {
+      mbar_wait(bar + 8 * c, phase);          // chunk c of frame b has landed in the staging buffer
+      convert_chunk<CF_THREADS>(stg, xs, c, tid);
+      __syncthreads();                        // every thread is done with chunk c (after the last one: image complete)
+      if (tid == 0 && more) {
+        fence_proxy_async();                  // order the generic-proxy reads above before the async-proxy refill
+        stg_issue_chunk(stg, x + (size_t)(b + gridDim.x) * STATE_DIM, c, bar);
+      }
     }
+    phase ^= 1;
 
     // ---------------- conv11: 28 m16 tiles over 16 warps ----------------
     for (int tile = warp; tile < 28; tile += CF_WARPS) {

@@ -74,7 +74,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
 // ---- epilogues: one thread owns one output row and 32 consecutive columns ------------------------
 struct EpiPartialF32 {      // raw fp32 tile into part[split][M][N]  (bias + relu are applied by the consumer)
   float* out; int ldc; int64_t split_stride;
-  __device__ __forceinline__ void operator()(int split, int m, int n, const uint32_t (&r)[32]) const {
+  struct Pre {};
+  __device__ __forceinline__ void prefetch(Pre&, int, int, bool) const {}
+  __device__ __forceinline__ void operator()(const Pre&, int split, int m, int n, const uint32_t (&r)[32]) const {
     float4* dst = reinterpret_cast<float4*>(out + split * split_stride + (size_t)m * ldc + n);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -84,12 +86,17 @@ struct EpiPartialF32 {      // raw fp32 tile into part[split][M][N]  (bias + rel
 };
 struct EpiReluMaskBf16Tc {  // dn2 = acc where n2 > 0 else 0, bf16
   uint16_t* out; const uint16_t* act; int ldc;
-  __device__ __forceinline__ void operator()(int, int m, int n, const uint32_t (&r)[32]) const {
+  struct Pre { uint4 a[4]; };     // this thread's 32 activations: fetched while the MMAs are still running
+  __device__ __forceinline__ void prefetch(Pre& p, int m, int n, bool ok) const {
     const uint4* a = reinterpret_cast<const uint4*>(act + (size_t)m * ldc + n);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p.a[i] = ok ? a[i] : make_uint4(0, 0, 0, 0);
+  }
+  __device__ __forceinline__ void operator()(const Pre& p, int, int m, int n, const uint32_t (&r)[32]) const {
     uint4* dst = reinterpret_cast<uint4*>(out + (size_t)m * ldc + n);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const uint4 av = a[i];
+      const uint4 av = p.a[i];
       const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
       uint32_t o[4];
 #pragma unroll
@@ -178,16 +185,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       tc_commit(bars + 2 * STAGES * 8);                                        // accumulator complete
     }
   } else {
-    mbar_wait(bars + 2 * STAGES * 8, 0);
-    tc_fence_after();
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int m = m0 + q * 32 + lane;
-#pragma unroll 1
+    typename Epi::Pre pre[BN / 32];               // epilogue inputs from global memory, loaded under the MMAs
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) epi.prefetch(pre[c], m, n0 + c * 32, m < M && n0 + c * 32 < N);
+    mbar_wait(bars + 2 * STAGES * 8, 0);
+    tc_fence_after();
+#pragma unroll
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
       tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
       const int n = n0 + c * 32;
-      if (m < M && n < N) epi(split, m, n, r);
+      if (m < M && n < N) epi(pre[c], split, m, n, r);
     }
   }
   tc_fence_before();

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
         float4 fb = *reinterpret_cast<const float4*>(&b1s[128 + 4 * lane]);
         {
           float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+#pragma unroll 4
           for (int sp = 0; sp < p.n_split; ++sp) {
             const float* src = p.d1_part + ((size_t)sp * p.batch + b) * FC;
             const float4 qa = *reinterpret_cast<const float4*>(src + 4 * lane);
