@@ -109,15 +109,40 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 
 // ---- fp32 frame staging ring (conv_fwd, conv11_wgrad) ---------------------------------------------
 // A frame (112,896 B, dense NHWC fp32) is streamed by the TMA engine into a shared-memory staging buffer in
-// STG_CHUNKS chunks, each signalled on its own mbarrier.  The consumer converts chunk c, and as soon as every
-// thread is done with it re-arms that chunk with the NEXT frame's bytes -- so about one full frame is always
-// in flight per SM, which is what a 1/148 share of HBM bandwidth needs (112,896 B at ~44 GB/s = 2.6 us).
+// NCH chunks, each signalled on its own mbarrier.  The consumer converts chunk c and, as soon as every thread
+// is done with it, re-arms that chunk with the NEXT frame's bytes: with NCH > 1 close to a full frame is always
+// in flight per SM (a 1/148 share of HBM bandwidth moves 112,896 B in ~2.6 us), at the price of NCH - 1 extra
+// block barriers per frame.  conv_fwd (compute-bound per frame) uses 1 chunk, conv11_wgrad 2.
 constexpr int FRAME_BYTES = STATE_DIM * 4;                         // 112,896
-constexpr int STG_CHUNKS = 4, STG_CHUNK_BYTES = FRAME_BYTES / STG_CHUNKS, STG_CHUNK_PIX = IMG * IMG / STG_CHUNKS;   // 28,224 B, 1,764 px
-static_assert(STG_CHUNK_BYTES % 16 == 0 && STG_CHUNK_PIX * STG_CHUNKS == IMG * IMG, "chunking must be exact");
+template <int NCH>
 __device__ __forceinline__ void stg_issue_chunk(uint32_t stg, const float* frame, int c, uint32_t bars) {
-  mbar_expect_tx(bars + 8 * c, STG_CHUNK_BYTES);
-  bulk_load(stg + c * STG_CHUNK_BYTES, reinterpret_cast<const uint8_t*>(frame) + c * STG_CHUNK_BYTES, STG_CHUNK_BYTES, bars + 8 * c);
+  constexpr int CB = FRAME_BYTES / NCH, PARTS = 4 / NCH > 0 ? 4 / NCH : 1, PB = CB / PARTS;   // <= 28,224 B per bulk copy
+  static_assert(CB * NCH == FRAME_BYTES && PB * PARTS == CB && PB % 16 == 0, "chunking must be exact and 16-B granular");
+  mbar_expect_tx(bars + 8 * c, CB);
+#pragma unroll
+  for (int k = 0; k < PARTS; ++k)
+    bulk_load(stg + c * CB + k * PB, reinterpret_cast<const uint8_t*>(frame) + c * CB + k * PB, PB, bars + 8 * c);
+}
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// Every kernel of the step is launched with programmatic stream serialization: it may start (and run its
+// prologue: shared-memory setup, TMEM allocation, barrier init, weight fragments, input prefetch) while its
+// predecessor in the stream is still draining.  griddep_wait() blocks until the predecessor grid has
+// completed and its memory is visible; EVERY kernel calls it, which makes the ordering transitive.
+// griddep_launch() lets the successor begin launching; kernels call it once all their CTAs hold the
+// resources they need (so an early successor can never starve a not-yet-started CTA of this grid).
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

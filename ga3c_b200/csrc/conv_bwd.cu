@@ -105,7 +105,9 @@ conv12_bwd_kernel(const uint16_t* __restrict__ n1, const uint16_t* __restrict__ 
   }
   const int kh = warp >> 2, kw = warp & 3;                            // wgrad: one tap per warp
   const uint32_t tap_off = (kw & 1) * N1PL_PLANE + (kh * 12 + (kw >> 1)) * N1PL_PITCH;
+  griddep_launch();
   __syncthreads();
+  griddep_wait();               // dn2 comes from the dense1 data-gradient GEMM that precedes this kernel
 
   auto prefetch = [&](int b, uint32_t in) {
     const uint4* s1 = reinterpret_cast<const uint4*>(n1 + (size_t)b * N1_POS * C1_OUT);
@@ -229,6 +231,7 @@ conv12_bwd_kernel(const uint16_t* __restrict__ n1, const uint16_t* __restrict__ 
 //   all warps  : wait -> fp32 staging -> padded bf16 image -> [issue frame i+1] -> wgrad MMAs
 // warp = (kh, part): M tile pair (kh, half 0/1) x N 16, K = the 14 k16 position steps of its part.
 constexpr int W11_THREADS = 512;
+constexpr int W11_NCH = 2, W11_CHUNK_PIX = IMG * IMG / W11_NCH;   // staging chunks per frame
 constexpr int DN1S_ROWS = 448;                                    // 441 padded to 28 k16 steps
 constexpr int DN1S_BYTES = DN1S_ROWS * 32;                        // 14,336
 constexpr int C11_OFF_STG = 0;
@@ -236,7 +239,7 @@ constexpr int C11_OFF_XS = C11_OFF_STG + FRAME_BYTES;         // 112,896
 constexpr int C11_OFF_DN1S = C11_OFF_XS + XS_BYTES;               // 174,848 (two buffers)
 constexpr int C11_OFF_RED = C11_OFF_DN1S + 2 * DN1S_BYTES;        // 203,520
 constexpr int C11_OFF_BAR = C11_OFF_RED + W11_THREADS * 4;        // 205,568
-constexpr int C11_SMEM = C11_OFF_BAR + 8 * STG_CHUNKS;            // 205,600
+constexpr int C11_SMEM = C11_OFF_BAR + 8 * W11_NCH;            // 205,600
 
 // 16-B chunk h (pixels 2h, 2h+1) of pixel quad q sits at h ^ ((q >> 2) & 1): the transposed ldmatrix
 // reads of 8 consecutive positions (32 B apart) then touch all 32 banks once
@@ -266,17 +269,19 @@ conv11_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dn
   const int stride = gridDim.x;
 
   if (tid == 0) {
-    for (int c = 0; c < STG_CHUNKS; ++c) mbar_init(bar + 8 * c, 1);
+    for (int c = 0; c < W11_NCH; ++c) mbar_init(bar + 8 * c, 1);
     fence_mbar_init();
   }
   for (int i = tid; i < (XS_BYTES + 2 * DN1S_BYTES) / 16; i += W11_THREADS) sts128(xs + i * 16, make_uint4(0, 0, 0, 0));
   __syncthreads();
   int b = blockIdx.x;
   if (b < batch) {
-    if (tid == 0)
-      for (int c = 0; c < STG_CHUNKS; ++c) stg_issue_chunk(stg, x + (size_t)b * STATE_DIM, c, bar);
-    w11_prefetch_dn1(dn1, b, sbase + C11_OFF_DN1S, tid);
+    if (tid == 0)                                 // x is an input of the step: stream it before the dependency wait
+      for (int c = 0; c < W11_NCH; ++c) stg_issue_chunk<W11_NCH>(stg, x + (size_t)b * STATE_DIM, c, bar);
   }
+  griddep_launch();
+  griddep_wait();               // dn1 comes from conv12_bwd, which precedes this kernel
+  if (b < batch) w11_prefetch_dn1(dn1, b, sbase + C11_OFF_DN1S, tid);
   cp_async_commit();
 
   float wacc[2][2][4] = {};   // m-tiles (kh, half = 0/1) x 2 n-tiles
@@ -289,11 +294,11 @@ conv11_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dn
     const bool more = b + stride < batch;
     cp_async_wait<0>();                       // dn1(b): visible to all after the first barrier below
 #pragma unroll 1
-    for (int c = 0; c < STG_CHUNKS; ++c) {    // fp32 staging -> zero-bordered, chunk-swizzled bf16 image
+    for (int c = 0; c < W11_NCH; ++c) {    // fp32 staging -> zero-bordered, chunk-swizzled bf16 image
       mbar_wait(bar + 8 * c, phase);
 #pragma unroll 2
-      for (int k = tid; k < STG_CHUNK_PIX; k += W11_THREADS) {
-        const int i = c * STG_CHUNK_PIX + k;
+      for (int k = tid; k < W11_CHUNK_PIX; k += W11_THREADS) {
+        const int i = c * W11_CHUNK_PIX + k;
         uint32_t r[4];
         lds128(r, stg + i * 16);
         const int y = i / IMG, px = i - y * IMG + 2;
@@ -303,7 +308,7 @@ conv11_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dn
       __syncthreads();                        // chunk c is free (after the last one: image + dn1(b) complete)
       if (tid == 0 && more) {
         fence_proxy_async();
-        stg_issue_chunk(stg, x + (size_t)(b + stride) * STATE_DIM, c, bar);
+        stg_issue_chunk<W11_NCH>(stg, x + (size_t)(b + stride) * STATE_DIM, c, bar);
       }
     }
     phase ^= 1;
@@ -373,15 +378,13 @@ int configure_conv_bwd() {
 int launch_conv12_bwd(const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1, float* g_w12,
                       float* g_b12, int batch, int num_sms, cudaStream_t stream) {
   const int grid = min(batch, num_sms);
-  conv12_bwd_kernel<<<grid, B12_THREADS, B12_SMEM, stream>>>(n1, dn2, w12, dn1, g_w12, g_b12, batch);
-  return (int)cudaGetLastError();
+  return launch_pdl(conv12_bwd_kernel, dim3(grid), dim3(B12_THREADS), B12_SMEM, stream, n1, dn2, w12, dn1, g_w12, g_b12, batch);
 }
 
 int launch_conv11_wgrad(const float* x, const uint16_t* dn1, float* g_w11, float* g_b11, int batch, int num_sms,
                         cudaStream_t stream) {
   const int grid = min(batch, num_sms);
-  conv11_wgrad_kernel<<<grid, W11_THREADS, C11_SMEM, stream>>>(x, dn1, g_w11, g_b11, batch);
-  return (int)cudaGetLastError();
+  return launch_pdl(conv11_wgrad_kernel, dim3(grid), dim3(W11_THREADS), C11_SMEM, stream, x, dn1, g_w11, g_b11, batch);
 }
 
 }  // namespace ga3c

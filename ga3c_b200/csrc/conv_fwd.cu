@@ -22,6 +22,7 @@
 namespace ga3c {
 
 constexpr int CF_THREADS = 512, CF_WARPS = CF_THREADS / 32;
+constexpr int CF_NCH = 1, CF_CHUNK_PIX = IMG * IMG / CF_NCH;     // staging chunks per frame
 constexpr int CF_OFF_STG = 0;
 constexpr int CF_OFF_XS = CF_OFF_STG + FRAME_BYTES;         // 112,896
 constexpr int CF_OFF_N1P = CF_OFF_XS + XS_BYTES;            // 174,848
@@ -29,14 +30,14 @@ constexpr int CF_OFF_W12F = CF_OFF_N1P + N1P_BYTES;         // 193,280
 constexpr int CF_OFF_N2S = CF_OFF_W12F + 16 * 2 * 32 * 16;  // 209,664
 constexpr int CF_OFF_BIAS = CF_OFF_N2S + N2_POS * 64;       // 217,408
 constexpr int CF_OFF_BAR = CF_OFF_BIAS + (C1_OUT + C2_OUT) * 4;   // 217,600
-constexpr int CF_SMEM = CF_OFF_BAR + 8 * STG_CHUNKS;        // 217,632 <= 232,448
+constexpr int CF_SMEM = CF_OFF_BAR + 8 * CF_NCH;        // 217,632 <= 232,448
 
 // one chunk of the fp32 staging buffer (dense NHWC) -> zero-bordered bf16 image, 8 B per pixel
 template <int NT>
 __device__ __forceinline__ void convert_chunk(uint32_t stg, uint32_t xs, int c, int tid) {
 #pragma unroll 2
-  for (int k = tid; k < STG_CHUNK_PIX; k += NT) {
-    const int i = c * STG_CHUNK_PIX + k;
+  for (int k = tid; k < CF_CHUNK_PIX; k += NT) {
+    const int i = c * CF_CHUNK_PIX + k;
     uint32_t r[4];
     lds128(r, stg + i * 16);
     const int y = i / IMG, xx = i - y * IMG;
@@ -57,16 +58,18 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
 
   if (tid == 0) {
-    for (int c = 0; c < STG_CHUNKS; ++c) mbar_init(bar + 8 * c, 1);
+    for (int c = 0; c < CF_NCH; ++c) mbar_init(bar + 8 * c, 1);
     fence_mbar_init();
   }
   __syncthreads();
   int b = blockIdx.x;
   if (tid == 0 && b < batch)                                      // overlaps the weight setup below
-    for (int c = 0; c < STG_CHUNKS; ++c) stg_issue_chunk(stg, x + (size_t)b * STATE_DIM, c, bar);
+    for (int c = 0; c < CF_NCH; ++c) stg_issue_chunk<CF_NCH>(stg, x + (size_t)b * STATE_DIM, c, bar);
 
   // zero the padded buffers once: the borders are never written again
   for (int i = tid; i < (XS_BYTES + N1P_BYTES) / 16; i += CF_THREADS) sts128(xs + i * 16, make_uint4(0, 0, 0, 0));
+  griddep_launch();
+  griddep_wait();               // the weights below come from the optimizer kernel that precedes this one in the stream
   // conv12 weights in mma B-fragment order: [kstep = tap][n-tile pair][lane] -> {b0,b1 (tile 2np), b0,b1 (tile 2np+1)}
   // K permutation inside a k16 step (one tap, 16 ci): logical cols (2t,2t+1,2t+8,2t+9) <-> ci (4t..4t+3)
   for (int i = tid; i < 16 * 2 * 32; i += CF_THREADS) {
@@ -101,13 +104,13 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
   for (; b < batch; b += gridDim.x) {
     const bool more = b + (int)gridDim.x < batch;
 #pragma unroll 1
-    for (int c = 0; c < STG_CHUNKS; ++c) {
+    for (int c = 0; c < CF_NCH; ++c) {
       mbar_wait(bar + 8 * c, phase);          // chunk c of frame b has landed in the staging buffer
       convert_chunk<CF_THREADS>(stg, xs, c, tid);
       __syncthreads();                        // every thread is done with chunk c (after the last one: image complete)
       if (tid == 0 && more) {
         fence_proxy_async();                  // order the generic-proxy reads above before the async-proxy refill
-        stg_issue_chunk(stg, x + (size_t)(b + gridDim.x) * STATE_DIM, c, bar);
+        stg_issue_chunk<CF_NCH>(stg, x + (size_t)(b + gridDim.x) * STATE_DIM, c, bar);
       }
     }
     phase ^= 1;
@@ -205,8 +208,7 @@ int configure_conv_fwd() {
 int launch_conv_fwd(const float* x, const float* w11, const float* b11, const float* w12, const float* b12,
                     uint16_t* n1_out, uint16_t* n2_out, int batch, int num_sms, cudaStream_t stream) {
   const int grid = min(batch, num_sms);
-  conv_fwd_kernel<<<grid, CF_THREADS, CF_SMEM, stream>>>(x, w11, b11, w12, b12, n1_out, n2_out, batch);
-  return (int)cudaGetLastError();
+  return launch_pdl(conv_fwd_kernel, dim3(grid), dim3(CF_THREADS), CF_SMEM, stream, x, w11, b11, w12, b12, n1_out, n2_out, batch);
 }
 
 }  // namespace ga3c

@@ -141,6 +141,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_launch();             // every CTA of this grid holds its TMEM columns and shared memory
+  griddep_wait();               // operands are produced by the preceding kernels
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -281,9 +283,9 @@ int launch_dense_fwd_tc(const uint16_t* n2, const uint16_t* w1bf, float* d1_part
   const int kblocks = (FLAT + TC_BK - 1) / TC_BK;
   const int per = (kblocks + splits - 1) / splits;
   dim3 grid((batch + TC_BM - 1) / TC_BM, FC / FWD_BN, splits);
-  gemm_tc_kernel<FWD_BN, FWD_ST, false, true, EpiPartialF32><<<grid, TC_THREADS, tc_smem<FWD_BN, FWD_ST>(), stream>>>(
-      ta, tb, batch, FC, kblocks, per, EpiPartialF32{d1_part, FC, (int64_t)batch * FC});
-  return (int)cudaGetLastError();
+  return launch_pdl(gemm_tc_kernel<FWD_BN, FWD_ST, false, true, EpiPartialF32>, grid, dim3(TC_THREADS),
+                    tc_smem<FWD_BN, FWD_ST>(), stream, ta, tb, batch, (int)FC, kblocks, per,
+                    EpiPartialF32{d1_part, FC, (int64_t)batch * FC});
 }
 
 int launch_dense_dgrad_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint16_t* dn2, int batch,
@@ -292,9 +294,9 @@ int launch_dense_dgrad_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint1
   if (make_tmap(&ta, dd1, batch, FC, FC, TC_BM)) return (int)cudaErrorInvalidValue;           // A: [B][256], K inner
   if (make_tmap(&tb, w1bf, FLAT, FC, FC, DG_BN)) return (int)cudaErrorInvalidValue;           // B: [3872][256] = [N][K]
   dim3 grid((batch + TC_BM - 1) / TC_BM, (FLAT + DG_BN - 1) / DG_BN, 1);
-  gemm_tc_kernel<DG_BN, DG_ST, false, false, EpiReluMaskBf16Tc><<<grid, TC_THREADS, tc_smem<DG_BN, DG_ST>(), stream>>>(
-      ta, tb, batch, FLAT, FC / TC_BK, FC / TC_BK, EpiReluMaskBf16Tc{dn2, n2, FLAT});
-  return (int)cudaGetLastError();
+  return launch_pdl(gemm_tc_kernel<DG_BN, DG_ST, false, false, EpiReluMaskBf16Tc>, grid, dim3(TC_THREADS),
+                    tc_smem<DG_BN, DG_ST>(), stream, ta, tb, batch, (int)FLAT, FC / TC_BK, FC / TC_BK,
+                    EpiReluMaskBf16Tc{dn2, n2, FLAT});
 }
 
 int launch_dense_wgrad_tc(const uint16_t* n2, const uint16_t* dd1, float* g_w1, int batch, cudaStream_t stream) {
@@ -303,9 +305,9 @@ int launch_dense_wgrad_tc(const uint16_t* n2, const uint16_t* dd1, float* g_w1, 
   if (make_tmap(&tb, dd1, batch, FC, FC, 64)) return (int)cudaErrorInvalidValue;              // B: [K=B][N=256],  N inner
   const int kblocks = (batch + TC_BK - 1) / TC_BK;
   dim3 grid((FLAT + TC_BM - 1) / TC_BM, FC / WG_BN, 1);
-  gemm_tc_kernel<WG_BN, WG_ST, true, true, EpiPartialF32><<<grid, TC_THREADS, tc_smem<WG_BN, WG_ST>(), stream>>>(
-      ta, tb, FLAT, FC, kblocks, kblocks, EpiPartialF32{g_w1, FC, 0});
-  return (int)cudaGetLastError();
+  return launch_pdl(gemm_tc_kernel<WG_BN, WG_ST, true, true, EpiPartialF32>, grid, dim3(TC_THREADS),
+                    tc_smem<WG_BN, WG_ST>(), stream, ta, tb, (int)FLAT, (int)FC, kblocks, kblocks,
+                    EpiPartialF32{g_w1, FC, 0});
 }
 
 }  // namespace ga3c

@@ -12,6 +12,8 @@ namespace ga3c {
 // 20 B/param of traffic (read w,g,ms; write w,ms) + 2 B/param for the bf16 shadow of dense1/w.
 template <bool HAS_MOM>
 __global__ void __launch_bounds__(256) rmsprop_kernel(RmsPropArgs a) {
+  griddep_launch();
+  griddep_wait();               // the gradients come from the backward kernels that precede this one
   const int64_t n4 = a.n_floats >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const float one_m_rho = 1.f - a.decay;
@@ -38,9 +40,8 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(RmsPropArgs a) {
 int launch_rmsprop(const RmsPropArgs& a, cudaStream_t stream) {
   const int64_t n4 = a.n_floats >> 2;
   const int grid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
-  if (a.momentum != 0.f) rmsprop_kernel<true><<<grid, 256, 0, stream>>>(a);
-  else rmsprop_kernel<false><<<grid, 256, 0, stream>>>(a);
-  return (int)cudaGetLastError();
+  if (a.momentum != 0.f) return launch_pdl(rmsprop_kernel<true>, dim3(grid), dim3(256), 0, stream, a);
+  return launch_pdl(rmsprop_kernel<false>, dim3(grid), dim3(256), 0, stream, a);
 }
 
 // ---- data-parallel RMSProp over peer memory ---------------------------------------------------------
@@ -67,6 +68,8 @@ __device__ __forceinline__ void st_flag(uint64_t* p, uint64_t v) {
 template <bool HAS_MOM>
 __global__ void __launch_bounds__(512) rmsprop_dp_kernel(RmsPropDpArgs d) {
   const RmsPropArgs& a = d.base;
+  griddep_launch();
+  griddep_wait();               // the gradients come from the backward kernels that precede this one
   uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
   if (blockIdx.x == 0 && threadIdx.x == 0) st_flag(reinterpret_cast<uint64_t*>(my_comm), d.step);   // my gradients are final
   if ((int)threadIdx.x < d.world) {
@@ -137,9 +140,8 @@ __global__ void __launch_bounds__(512) rmsprop_dp_kernel(RmsPropDpArgs d) {
 }
 
 int launch_rmsprop_dp(const RmsPropDpArgs& d, int num_sms, cudaStream_t stream) {
-  if (d.base.momentum != 0.f) rmsprop_dp_kernel<true><<<num_sms, 512, 0, stream>>>(d);
-  else rmsprop_dp_kernel<false><<<num_sms, 512, 0, stream>>>(d);
-  return (int)cudaGetLastError();
+  if (d.base.momentum != 0.f) return launch_pdl(rmsprop_dp_kernel<true>, dim3(num_sms), dim3(512), 0, stream, d);
+  return launch_pdl(rmsprop_dp_kernel<false>, dim3(num_sms), dim3(512), 0, stream, d);
 }
 
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int64_t n4) {

@@ -36,7 +36,9 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
   if (tid < A1) bias_s[tid] = (tid < A) ? p.bp[tid] : p.bv[0];
   b1s[tid] = p.b1[tid];
   if (tid < 3) loss_s[tid] = 0.f;
+  griddep_launch();
   __syncthreads();
+  griddep_wait();               // d1_part comes from the dense1 GEMM that precedes this kernel
 
   float acc[A1] = {};      // thread j: dWp[j][0..A-1], dWv[j]
   float acc_b1 = 0.f;      // thread j: db1[j]
@@ -199,8 +201,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
 
 template <int A>
 static int launch_heads_t(const HeadsArgs& args, int grid, cudaStream_t stream) {
-  heads_kernel<A><<<grid, HD_THREADS, 0, stream>>>(args);
-  return (int)cudaGetLastError();
+  return launch_pdl(heads_kernel<A>, dim3(grid), dim3(HD_THREADS), 0, stream, args);
 }
 
 int launch_heads(const HeadsArgs& args, int num_sms, cudaStream_t stream) {

@@ -8,23 +8,13 @@ namespace ga3c {
 // one-time per-process function-attribute setup (dynamic smem opt-in); returns cudaError_t as int
 int configure_conv_fwd();
 int configure_conv_bwd();
-int configure_dense();
 int configure_dense_tc();
 
 // conv_fwd.cu -- x fp32 [B,28224] -> n1 bf16 [B,441,16] (optional), n2 bf16 [B,3872]
 int launch_conv_fwd(const float* x, const float* w11, const float* b11, const float* w12, const float* b12,
                     uint16_t* n1_out, uint16_t* n2_out, int batch, int num_sms, cudaStream_t stream);
 
-// dense.cu -- the three dense1 GEMMs (NetworkDNav.py:90 and its autodiff)
-//   fwd  : d1[B,256]      = relu(n2[B,3872] @ w1bf[3872,256] + b1)                 fp32 out
-//   dgrad: dn2[B,3872]    = (dd1[B,256] @ w1bf^T) masked by n2 > 0                  bf16 out
-//   wgrad: g_w1[3872,256] = n2^T @ dd1                                              fp32 out (overwrites)
-int launch_dense_fwd(const uint16_t* n2, const uint16_t* w1bf, const float* b1, float* d1, int batch, cudaStream_t stream);
-int launch_dense_dgrad(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint16_t* dn2, int batch,
-                       cudaStream_t stream);
-int launch_dense_wgrad(const uint16_t* n2, const uint16_t* dd1, float* g_w1, int batch, cudaStream_t stream);
-
-// dense_tc.cu -- the same three GEMMs on tcgen05 / TMEM / TMA.  fwd leaves `splits` raw fp32 partial tiles
+// dense_tc.cu -- the three dense1 GEMMs (NetworkDNav.py:90 and its autodiff) on tcgen05 / TMEM / TMA.  fwd leaves `splits` raw fp32 partial tiles
 // in d1_part[splits][B][256]; the heads kernel sums them, adds the bias and applies the ReLU.
 int dense_fwd_splits(int batch, int num_sms);
 int launch_dense_fwd_tc(const uint16_t* n2, const uint16_t* w1bf, float* d1_part, int batch, int splits, cudaStream_t stream);

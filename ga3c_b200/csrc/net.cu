@@ -66,7 +66,6 @@ struct ga3c_net {
   uint16_t *n1 = nullptr, *n2 = nullptr, *dd1 = nullptr, *dn2 = nullptr, *dn1 = nullptr;
   float* d1 = nullptr;
   float* d1_part = nullptr;        // [splits][B,256] raw split-K partials of dense1 (dense_tc.cu)
-  int legacy_dense_bwd = 0;        // debug: GA3C_DENSE_BWD=mma routes dgrad/wgrad through the mma.sync GEMM
   int64_t global_step = 0;
   int64_t launches = 0;
   int last_batch = 0;
@@ -171,8 +170,7 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
     cudaMemcpy(n->ms, ones.data(), ab, cudaMemcpyHostToDevice);
   }
   int r;
-  if (const char* e = getenv("GA3C_DENSE_BWD")) n->legacy_dense_bwd = (std::string(e) == "mma");
-  if ((r = configure_conv_fwd()) || (r = configure_conv_bwd()) || (r = configure_dense()) || (r = configure_dense_tc())) {
+  if ((r = configure_conv_fwd()) || (r = configure_conv_bwd()) || (r = configure_dense_tc())) {
     ga3c_destroy(n);
     return fail("cudaFuncSetAttribute", (cudaError_t)r);
   }
@@ -333,8 +331,7 @@ extern "C" int ga3c_fb_head(ga3c_net* n, const float* x, const float* yr, const 
   h.g_wp = g + n->off(P_PW); h.g_bp = g + n->off(P_PB); h.g_wv = g + n->off(P_VW); h.g_bv = g + n->off(P_VB);
   h.g_b1 = g + n->off(P_D1B);
   LAUNCH(n, K_HEADS, st, launch_heads(h, n->num_sms, st));
-  if (n->legacy_dense_bwd) LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
-  else LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad_tc(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
+  LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad_tc(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
   n->last_batch = batch;
   return 0;
 }
@@ -348,8 +345,7 @@ extern "C" int ga3c_fb_tail(ga3c_net* n, const float* x, int32_t batch, void* st
   cudaStream_t st = (cudaStream_t)stream;
   const float* w = n->w;
   float* g = n->g;
-  if (n->legacy_dense_bwd) LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
-  else LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
+  LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
   LAUNCH(n, K_CONV12_BWD, st, launch_conv12_bwd(n->n1, n->dn2, w + n->off(P_C12W), n->dn1, g + n->off(P_C12W),
                                                 g + n->off(P_C12B), batch, n->num_sms, st));
   LAUNCH(n, K_CONV11_WGRAD, st, launch_conv11_wgrad(x, n->dn1, g + n->off(P_C11W), g + n->off(P_C11B), batch,
