@@ -1,57 +1,87 @@
-// Fused conv11 (8x8 s4, 16) -> conv12 (4x4 s2, 32) forward: one persistent, warp-specialised CTA per SM.
+// Fused conv11 (8x8 s4, 16) -> conv12 (4x4 s2, 32) forward: one persistent, warp-specialised CTA per SM,
+// BOTH convolutions on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
 //
 // Reference op: tf.nn.conv2d(..., padding='SAME') + b, relu  (NetworkVP.py:224-226), wired as
 // NetworkDNav.py:81-82.  bf16 operands, fp32 accumulate.
 //
-//   conv11  M = 441 positions, N = 16, K = 256 = (kh, kw, c): warp-level mma.sync whose A fragments are read straight
-//           from the un-duplicated, zero-bordered bf16 image in shared memory (8-byte conflict-free loads).  N = 16
-//           is too narrow for tcgen05: a UMMA re-reads the whole A tile from shared memory for every MMA and cannot
-//           reuse fragments across the 4x-overlapping windows, so it would be bound by shared-memory reads.
-//   conv12  M = 121 (one 128-row UMMA tile), N = 32, K = 256 = (kh, kw, ci): tcgen05.mma with a TMEM accumulator.
-//           The conv11 epilogue scatters every output pixel into the (up to four) im2col slots it feeds, directly in the
-//           canonical K-major SWIZZLE_128B operand layout, so conv12 costs 16 asynchronous UMMAs per frame instead
-//           of 512 HMMAs + 2,048 shared-memory wavefronts (profiles/: the mma.sync version was bound by both).
+// conv11 as 4 shifted GEMMs (space-to-depth).  The zero-padded 88x88x4 image is cut into 22x22 blocks of 4x4 pixels;
+//   a block is one row (K = 64 = (dy, dx, c)) of the "block matrix" Blk[484, 64].  An 8x8 stride-4 window is exactly 2x2
+//   blocks, so   out[oy, ox, :] = sum_{a,b in {0,1}} Blk[(oy+a)*22 + (ox+b), :] . W_ab        (W_ab = w11[4a.., 4b.., :, :])
+//   With output rows indexed m = oy*22 + ox (column 21 is a dead column) quadrant (a,b) reads Blk rows m + 22a + b: the same
+//   matrix at a ROW-SHIFTED start address.  Blk is kept in the no-swizzle K-major UMMA layout with all rows contiguous
+//   (16-byte k-chunk j of row r at j*LBO + r*16), so any row shift is a legal descriptor start address and nothing is
+//   duplicated.  The a-shift (+22 rows) is done by the tensor core (two accumulating UMMAs per k-step); the b-shift (+1 row)
+//   is folded into N: D[m, b*16 + c] = sum_a Blk[m + 22a] . W_ab[:, c]  (N = 32), and the epilogue adds
+//   out[m] = D[m, 0:16] + D[m+1, 16:32] with one warp shuffle.  M tiles start every 127 rows (row 127 of a tile only feeds
+//   row 126): 4 tiles x 2 shifts x 4 k16 steps = 32 UMMAs (M=128, N=32) per frame -- the UMMA time is set by the A-operand
+//   shared-memory reads, so halving the instruction count halves it.
+// conv12 as one im2col GEMM.  M = 121 (one 128-row tile), N = 32, K = 256 = (kh, kw, ci): the conv11 epilogue scatters every
+//   output pixel into the (up to four) im2col slots it feeds, directly in the K-major SWIZZLE_128B operand layout:
+//   16 UMMAs per frame.
+// The mma.sync predecessors of this kernel (experiments/) were bound by instruction issue: ~17k warp instructions per
+// frame; here the SM only converts fp32 -> bf16 and runs the two epilogues.
 //
-// Streaming pipeline (per frame: 112,896 B of fp32 input read from HBM exactly once; nothing else leaves the SM but n2
-// [+ n1 when training]):
+// Streaming pipeline per frame (112,896 B of fp32 input read from HBM exactly once; only n2 [+ n1 when training] leave):
 //   TMA engine        cp.async.bulk of 12-row chunks (16,128 B) of the fp32 frame into a 4-slot ring (mbarrier per slot)
-//   warps 0-5  (aux)  chunk -> bf16 -> the band buffers (3 bands of 7 output rows, 32 padded image rows each); re-arm the slot
-//                     with the chunk 4 ahead (next frames included); warps 0-3: TMEM -> +bias, ReLU -> n2 of the previous frame
-//   warps 6-15        conv11 on a band as soon as it is complete (one m16 tile per warp, HMMA), epilogue -> +bias, ReLU -> im2col scatter
-//                     (+ n1 to HBM when training); after the last band one thread issues the 16 UMMAs of conv12
-// Cross-role ordering is all mbarriers: band full/empty, MMA done (= im2col buffer free), TMEM drained.
+//   warps 0-5  (aux)  chunk -> bf16 -> Blk, re-arm the slot with the chunk 4 ahead (next frames included)
+//   warp  6           one thread issues the UMMAs: conv11 tile i as soon as its Blk rows are converted, conv12 after the
+//                     conv11 epilogues; tcgen05.commit signals TMEM-full / operand-free mbarriers
+//   warps 8-11        epilogues (one TMEM lane quarter each): conv11 tile -> +bias, ReLU -> im2col scatter (+ n1 to HBM when
+//                     training); conv12 tile -> +bias, ReLU -> n2 to HBM
 #include "common.cuh"
 #include "kernels.h"
 #include "tcgen05.cuh"
 
 namespace ga3c {
 
-constexpr int CF_THREADS = 512, CF_AUX_WARPS = 6, CF_C11_WARPS = 10;
-constexpr int CF_AUX_THREADS = 32 * CF_AUX_WARPS, CF_C11_THREADS = 32 * CF_C11_WARPS;
-constexpr int CH_ROWS = 12, CF_NCHUNK = IMG / CH_ROWS, CH_PIX = CH_ROWS * IMG, CH_BYTES = CH_PIX * 16;   // 7 chunks of 16,128 B
+constexpr int CF_THREADS = 384, CF_AUX_WARPS = 6, CF_AUX_THREADS = 32 * CF_AUX_WARPS, CF_ISSUE_WARP = 6, CF_EPI_WARP0 = 8;
+static_assert(CF_EPI_WARP0 % 4 == 0, "epilogue warp e must own TMEM lane quarter e");
+constexpr int CH_ROWS = 12, CF_NCHUNK = IMG / CH_ROWS, CH_BYTES = CH_ROWS * IMG * 16;     // 7 chunks of 16,128 B
 constexpr int CF_NSLOT = 4;
-static_assert(CF_NCHUNK * CH_ROWS == IMG && CH_BYTES % 16 == 0, "chunks must tile the frame");
-// the image is processed in 3 bands of 7 output rows (147 positions = 10 m16 tiles = one tile per conv11 warp); band j
-// needs padded image rows [28 j, 28 j + 32) and has its own buffer, so converting band j of frame k+1 overlaps the
-// conv11 of the two other bands
-constexpr int CF_BANDS = 3, BAND_OROWS = 7, BAND_POS = BAND_OROWS * H1, BAND_ROW0 = 4 * BAND_OROWS;     // 147 positions, 28 rows
-constexpr int HB_ROWS = 32, HB_BYTES = HB_ROWS * XS_ROW_BYTES;                                          // 22,528 B each
-static_assert(CF_BANDS * BAND_OROWS == H1 && (BAND_POS + 15) / 16 == CF_C11_WARPS, "one m16 tile per conv11 warp and band");
+static_assert(CF_NCHUNK * CH_ROWS == IMG && CH_BYTES % 16 == 0 && CH_ROWS % CF_AUX_WARPS == 0, "chunks must tile the frame");
+// block matrix: 22 x 22 blocks (+ slack rows read by the dead part of the last M tile); chunk arrays padded so that
+// neighbouring k-chunks start 16 banks apart
+constexpr int BLK_W = 22, BLK_ROWS = 548, BLK_LBO = BLK_ROWS * 16, BLK_BYTES = 8 * BLK_LBO;              // 8,768 / 70,144
+constexpr int C11_TILES = 4;                     // 462 output rows (21 x 22, column 21 dead) in 4 x 128
+constexpr int C11_TSTRIDE = 127;                                     // output rows per tile (tile row 127 only feeds row 126)
+static_assert((C11_TILES - 1) * C11_TSTRIDE + 128 + BLK_W <= BLK_ROWS && C11_TILES * C11_TSTRIDE >= H1 * BLK_W, "tiles must cover the outputs and stay inside the buffer");
 
-constexpr int CF_OFF_A = 0;                                      // conv12 A operand: 4 k-blocks (kh) x [128 rows x 128 B], SW128
-constexpr int CF_OFF_B = CF_OFF_A + 4 * 128 * 128;               // 65,536: conv12 B operand: 4 k-blocks x [32 rows x 128 B]
-constexpr int CF_OFF_RING = CF_OFF_B + 4 * 32 * 128;             // 81,920
-constexpr int CF_OFF_H = CF_OFF_RING + CF_NSLOT * CH_BYTES;      // 146,432
-constexpr int CF_OFF_LUT = CF_OFF_H + CF_BANDS * HB_BYTES;       // 214,016
-constexpr int CF_OFF_BIAS = CF_OFF_LUT + 3584;                   // 217,600 (441 x 8 B rounded up)
-constexpr int CF_OFF_BAR = CF_OFF_BIAS + (C1_OUT + C2_OUT) * 4;  // 217,792
-// barriers (8 B each): ring full[4] | band full[3] | band empty[3] | mma done | tmem drained ; then the TMEM slot
-constexpr int BAR_RING = 0, BAR_HFULL = 4, BAR_HEMPTY = 7, BAR_MMA = 10, BAR_TMEM = 11, CF_NBAR = 12;
-constexpr int CF_OFF_TSLOT = CF_OFF_BAR + CF_NBAR * 8;           // 217,872
-constexpr int CF_SMEM = CF_OFF_TSLOT + 16 + 1024;                // + slack to align the base to 1024 B (swizzle atoms)
+constexpr int CF_OFF_A2 = 0;                                         // conv12 A: 4 k-blocks (kh) x [128 rows x 128 B], SW128
+constexpr int CF_OFF_B2 = CF_OFF_A2 + 4 * 128 * 128;                 //  65,536: conv12 B: 4 k-blocks x [32 rows x 128 B], SW128
+constexpr int CF_OFF_BLK = CF_OFF_B2 + 4 * 32 * 128;                 //  81,920
+constexpr int CF_OFF_RING = CF_OFF_BLK + BLK_BYTES;                  // 152,064
+constexpr int CF_OFF_WQ = CF_OFF_RING + CF_NSLOT * CH_BYTES;         // 216,576: conv11 B: 2 row shifts a x [8 k-chunks][32 rows (b, cout) x 16 B]
+constexpr int CF_OFF_LUT = CF_OFF_WQ + 4 * 2048;                     // 224,768
+constexpr int CF_OFF_BIAS = CF_OFF_LUT + 3584;                       // 228,352 (441 x 8 B rounded up)
+constexpr int CF_OFF_BAR = CF_OFF_BIAS + (C1_OUT + C2_OUT) * 4;      // 228,544
+// mbarriers (8 B each)
+constexpr int BAR_RING = 0;          // [4]  TMA chunk landed
+constexpr int BAR_BLKRDY = 4;        // [4]  Blk rows of conv11 tile i converted            (aux -> issuer)
+constexpr int BAR_C11 = 8;           // [4]  conv11 tile i accumulated (tcgen05.commit)     (-> epilogue; -> aux: its Blk rows are free)
+constexpr int BAR_T1FREE = 12;       // [4]  conv11 TMEM tile i drained, 4 arrivals         (epilogue -> issuer)
+constexpr int BAR_A2RDY = 16;        //      im2col operand of the frame complete, 4 arrivals (epilogue -> issuer)
+constexpr int BAR_MMA2 = 17;         //      conv12 accumulated (tcgen05.commit)            (-> epilogue; im2col operand free)
+constexpr int BAR_T2FREE = 18;       //      conv12 TMEM tile drained, 4 arrivals           (epilogue -> issuer)
+constexpr int CF_NBAR = 19;
+constexpr int CF_OFF_TSLOT = CF_OFF_BAR + CF_NBAR * 8;               // 228,696
+constexpr int CF_OFF_XCH = CF_OFF_TSLOT + 16;                        // 228,712: [2][4 warps][16 floats] b-shift exchange across warps
+constexpr int CF_SMEM = CF_OFF_XCH + 512 + 1024;                     // 230,248 incl. slack to align the base to 1024 B
+constexpr int CF_TMEM_COLS = 256, TMEM_C12 = 128;                    // conv11 tiles at columns 0,32,64,96; conv12 at 128..159
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+// no-swizzle K-major operand: 16-byte k-chunk j of row r at start + j*LBO + (r/8)*SBO + (r%8)*16
+__device__ __forceinline__ uint64_t make_desc_ns(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
 __global__ void __launch_bounds__(CF_THREADS, 1)
@@ -61,39 +91,42 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const smem = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t sa = sbase + CF_OFF_A, sb = sbase + CF_OFF_B, ring = sbase + CF_OFF_RING, hb = sbase + CF_OFF_H,
-                 lut = sbase + CF_OFF_LUT, bars = sbase + CF_OFF_BAR, tslot = sbase + CF_OFF_TSLOT;
+  const uint32_t sa2 = sbase + CF_OFF_A2, sb2 = sbase + CF_OFF_B2, blk = sbase + CF_OFF_BLK, ring = sbase + CF_OFF_RING,
+                 wq = sbase + CF_OFF_WQ, lut = sbase + CF_OFF_LUT, bars = sbase + CF_OFF_BAR, tslot = sbase + CF_OFF_TSLOT;
   float* bias_s = reinterpret_cast<float*>(smem + CF_OFF_BIAS);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int stride = gridDim.x;
   const int n_frames = ((int)blockIdx.x < batch) ? (batch - 1 - (int)blockIdx.x) / stride + 1 : 0;
-  const int n_chunks = n_frames * CF_NCHUNK;                       // chunk stream of this CTA: q = k * 7 + c
+  const int n_chunks = n_frames * CF_NCHUNK;                         // chunk stream of this CTA: q = k * 7 + c
   auto frame_of = [&](int k) { return (size_t)(blockIdx.x + k * stride); };
-  auto issue_chunk = [&](int q) {                                  // one thread
+  auto bar = [&](int i) { return bars + i * 8; };
+  auto issue_chunk = [&](int q) {                                    // one thread
     const int k = q / CF_NCHUNK, c = q - k * CF_NCHUNK, slot = q % CF_NSLOT;
-    const uint32_t bar = bars + (BAR_RING + slot) * 8;
-    mbar_expect_tx(bar, CH_BYTES);
-    bulk_load(ring + slot * CH_BYTES, reinterpret_cast<const uint8_t*>(x + frame_of(k) * STATE_DIM) + c * CH_BYTES, CH_BYTES, bar);
+    mbar_expect_tx(bar(BAR_RING + slot), CH_BYTES);
+    bulk_load(ring + slot * CH_BYTES, reinterpret_cast<const uint8_t*>(x + frame_of(k) * STATE_DIM) + c * CH_BYTES, CH_BYTES,
+              bar(BAR_RING + slot));
   };
 
   // ---------------- prologue ----------------
   if (tid == 0) {
-    for (int i = 0; i < CF_NSLOT; ++i) mbar_init(bars + (BAR_RING + i) * 8, 1);
-    for (int h = 0; h < CF_BANDS; ++h) {
-      mbar_init(bars + (BAR_HFULL + h) * 8, 1);
-      mbar_init(bars + (BAR_HEMPTY + h) * 8, CF_C11_WARPS);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar(BAR_RING + i), 1);
+      mbar_init(bar(BAR_BLKRDY + i), 1);
+      mbar_init(bar(BAR_C11 + i), 1);
+      mbar_init(bar(BAR_T1FREE + i), 4);
     }
-    mbar_init(bars + BAR_MMA * 8, 1);
-    mbar_init(bars + BAR_TMEM * 8, 1);
+    mbar_init(bar(BAR_A2RDY), 4);
+    mbar_init(bar(BAR_MMA2), 1);
+    mbar_init(bar(BAR_T2FREE), 4);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc<32>(tslot);
+  if (warp == CF_EPI_WARP0) tmem_alloc<CF_TMEM_COLS>(tslot);
   __syncthreads();
-  if (tid == 0)                                                    // x is an input of the step: stream it before the dependency wait
+  if (tid == 0)                                                      // x is an input of the step: stream it before the dependency wait
     for (int q = 0; q < CF_NSLOT && q < n_chunks; ++q) issue_chunk(q);
-  // zero the im2col operand (padding taps, rows 121..127) and the half images (borders): never written again
-  for (int i = tid; i < (4 * 128 * 128) / 16; i += CF_THREADS) sts128(sa + i * 16, make_uint4(0, 0, 0, 0));
-  for (int i = tid; i < (CF_BANDS * HB_BYTES) / 16; i += CF_THREADS) sts128(hb + i * 16, make_uint4(0, 0, 0, 0));
+  // zero the operands once: image borders / slack rows of Blk, padding taps and rows 121..127 of the im2col operand
+  for (int i = tid; i < (CF_OFF_RING - CF_OFF_A2) / 16; i += CF_THREADS)
+    if (i < CF_OFF_B2 / 16 || i >= CF_OFF_BLK / 16) sts128(sbase + i * 16, make_uint4(0, 0, 0, 0));
   // scatter table: conv11 output pixel p = (y, x) feeds conv12 position (oy, ox) through tap (kh, kw) when
   // y + 1 = 2 oy + kh and x + 1 = 2 ox + kw (SAME padding 1 before / 2 after).  Up to 4 (kh, kw) per pixel:
   // kh = ((y+1)&1) + 2 ia, kw = ((x+1)&1) + 2 ib.  Entry = offset, in 16-byte units, of the pixel's channels 0..7 in the
@@ -114,17 +147,30 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
   }
   griddep_launch();
   griddep_wait();               // the weights below come from the optimizer kernel that precedes this one in the stream
+  // conv11 weights for row shift a: B operand [32 rows n2 = b*16 + cout][K = 64], no-swizzle K-major: k-chunk j = dy*2 + (dx>>1)
+  // holds (dx&1, c) -> 8 elements; chunk j of row n2 at a*4096 + j*512 + n2*16
+  for (int i = tid; i < 2 * 8 * 32; i += CF_THREADS) {
+    const int a = i >> 8, j = (i >> 5) & 7, n2 = i & 31, b = n2 >> 4, n = n2 & 15, dy = j >> 1;
+    uint32_t v[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {                                    // element pair (2h, 2h+1): dx = (j&1)*2 + (h>>1), c = (2h)&3
+      const int dx = (j & 1) * 2 + (h >> 1), c = (2 * h) & 3;
+      const float* w = w11 + (((4 * a + dy) * 8 + 4 * b + dx) * 4 + c) * C1_OUT + n;
+      v[h] = pack_bf16(w[0], w[C1_OUT]);
+    }
+    sts128(wq + a * 4096 + j * 512 + n2 * 16, make_uint4(v[0], v[1], v[2], v[3]));
+  }
   // conv12 weights as the UMMA B operand: k-block kh, row n (cout), 128 B = (kw, ci) K-major, 16-B chunks XOR (n & 7)
   for (int i = tid; i < 4 * 32 * 8; i += CF_THREADS) {
     const int kh = i >> 8, n = (i >> 3) & 31, c = i & 7, kw = c >> 1, ci0 = (c & 1) * 8;
     const float* w = w12 + ((kh * 4 + kw) * C1_OUT + ci0) * C2_OUT + n;
-    sts128(sb + kh * 4096 + n * 128 + ((c ^ (n & 7)) << 4),
+    sts128(sb2 + kh * 4096 + n * 128 + ((c ^ (n & 7)) << 4),
            make_uint4(pack_bf16(w[0], w[C2_OUT]), pack_bf16(w[2 * C2_OUT], w[3 * C2_OUT]),
                       pack_bf16(w[4 * C2_OUT], w[5 * C2_OUT]), pack_bf16(w[6 * C2_OUT], w[7 * C2_OUT])));
   }
   if (tid < C1_OUT) bias_s[tid] = b11[tid];
   if (tid < C2_OUT) bias_s[C1_OUT + tid] = b12[tid];
-  fence_proxy_async();          // the B operand (generic-proxy stores) is read by the tensor core (async proxy)
+  fence_proxy_async();          // operands written with generic-proxy stores are read by the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -132,18 +178,98 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tslot));
 
   if (warp < CF_AUX_WARPS) {
-    // =========================== aux group: convert, slot re-arm, conv12 epilogue ===========================
-    const int atid = tid;                                          // 0..127
-    auto epilogue = [&](int k) {                                   // TMEM (frame k) -> +bias, ReLU, bf16 -> n2[frame k]
-      if (warp >= 4) return;                                       // one warp per TMEM lane quarter
-      mbar_wait(bars + BAR_MMA * 8, k & 1);
+    // =========================== aux: fp32 chunk -> bf16 block matrix, slot re-arm ===========================
+    constexpr int RPW = CH_ROWS / CF_AUX_WARPS;                      // image rows per warp and chunk
+    // per-lane part of the destination: padded pixel px = x + 2 -> block column X = px >> 2, dx = px & 3
+    uint32_t lane_off[3];
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+      const int px = lane + 32 * it + 2;
+      lane_off[it] = ((px >> 1) & 1) * BLK_LBO + (px >> 2) * 16 + (px & 1) * 8;
+    }
+    for (int k = 0; k < n_frames; ++k) {
+#pragma unroll 1
+      for (int c = 0; c < CF_NCHUNK; ++c) {
+        const int q = k * CF_NCHUNK + c, slot = q % CF_NSLOT;
+        // block rows 3c..3c+3 are rewritten: the last conv11 tile of frame k-1 that reads them must have completed
+        if (k > 0) mbar_wait(bar(BAR_C11 + (c + 1) / 2), (k - 1) & 1);
+        mbar_wait(bar(BAR_RING + slot), (q / CF_NSLOT) & 1);         // chunk q has landed
+        const uint32_t src = ring + slot * CH_BYTES;
+        uint32_t px4[RPW][3][4];                                     // all six 16-byte loads first: their latencies overlap
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr)
+#pragma unroll
+          for (int it = 0; it < 3; ++it)
+            if (lane + 32 * it < IMG) lds128(px4[rr][it], src + ((warp + rr * CF_AUX_WARPS) * IMG + lane + 32 * it) * 16);
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) {
+          const int py = c * CH_ROWS + warp + rr * CF_AUX_WARPS + 2; // padded row -> block row Y = py >> 2, dy = py & 3
+          const uint32_t row_off = blk + (py & 3) * (2 * BLK_LBO) + (py >> 2) * (BLK_W * 16);
+#pragma unroll
+          for (int it = 0; it < 3; ++it) {
+            if (lane + 32 * it < IMG) {
+              const uint32_t* r = px4[rr][it];
+              sts64(row_off + lane_off[it], pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1])),
+                    pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3])));
+            }
+          }
+        }
+        fence_proxy_async();                                         // Blk is read by the tensor core; the slot is refilled by the TMA
+        named_bar_sync(1, CF_AUX_THREADS);                           // the slot has been consumed, the rows are written
+        if (tid == 0) {
+          if (q + CF_NSLOT < n_chunks) issue_chunk(q + CF_NSLOT);
+          // conv11 tile i reads block rows up to (128 i + 150) / 22: complete after chunk 2 / 4 / 6 / 6
+          if (c == 2) mbar_arrive(bar(BAR_BLKRDY + 0));
+          if (c == 4) mbar_arrive(bar(BAR_BLKRDY + 1));
+          if (c == 6) { mbar_arrive(bar(BAR_BLKRDY + 2)); mbar_arrive(bar(BAR_BLKRDY + 3)); }
+        }
+      }
+    }
+  } else if (warp == CF_ISSUE_WARP) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc11 = make_idesc(2 * C1_OUT, false, false), idesc12 = make_idesc(C2_OUT, false, false);
+      for (int k = 0; k < n_frames; ++k) {
+        for (int i = 0; i < C11_TILES; ++i) {
+          mbar_wait(bar(BAR_BLKRDY + i), k & 1);                     // the Blk rows this tile reads hold frame k
+          if (k > 0) mbar_wait(bar(BAR_T1FREE + i), (k - 1) & 1);    // its accumulator of frame k-1 has been drained
+          tc_fence_after();
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const uint32_t arow = blk + (C11_TSTRIDE * i + BLK_W * a) * 16;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              tc_mma_bf16(tmem_base + 32 * i, make_desc_ns(arow + 2 * kk * BLK_LBO, BLK_LBO, 128),
+                          make_desc_ns(wq + a * 4096 + 2 * kk * 512, 512, 128), idesc11, (a | kk) ? 1u : 0u);
+          }
+          tc_commit(bar(BAR_C11 + i));
+        }
+        mbar_wait(bar(BAR_A2RDY), k & 1);                            // every conv11 output of frame k sits in the im2col operand
+        if (k > 0) mbar_wait(bar(BAR_T2FREE), (k - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint64_t da = make_desc(sa2 + kb * 16384, false), db = make_desc(sb2 + kb * 4096, false);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            tc_mma_bf16(tmem_base + TMEM_C12, da + (uint64_t)(kk * 32 >> 4), db + (uint64_t)(kk * 32 >> 4), idesc12, (kb | kk) ? 1u : 0u);
+        }
+        tc_commit(bar(BAR_MMA2));
+      }
+    }
+  } else if (warp >= CF_EPI_WARP0) {
+    // =========================== epilogues ===========================
+    const int ew = warp - CF_EPI_WARP0;                              // TMEM lane quarter
+    const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16);
+    auto conv12_epilogue = [&](int k) {                              // TMEM -> +bias, ReLU, bf16 -> n2[frame k]
+      mbar_wait(bar(BAR_MMA2), k & 1);
       tc_fence_after();
       uint32_t r[32];
-      tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), r);
+      tc_ld32(tlane + TMEM_C12, r);
       tc_fence_before();
-      named_bar_sync(3, 128);                                      // all four lane quarters have left TMEM
-      if (atid == 0) mbar_arrive(bars + BAR_TMEM * 8);
-      const int pos = warp * 32 + lane;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(BAR_T2FREE));
+      const int pos = ew * 32 + lane;
       if (pos < N2_POS) {
         uint4* dst = reinterpret_cast<uint4*>(n2_out + frame_of(k) * FLAT + pos * C2_OUT);
 #pragma unroll
@@ -160,145 +286,69 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
       }
     };
     for (int k = 0; k < n_frames; ++k) {
-#pragma unroll 1
-      for (int c = 0; c < CF_NCHUNK; ++c) {
-        const int q = k * CF_NCHUNK + c, slot = q % CF_NSLOT;
-        if ((c & 1) == 0 && c < 2 * CF_BANDS)                      // chunks 0 / 2 / 4 are the first to write band 0 / 1 / 2
-          mbar_wait(bars + (BAR_HEMPTY + (c >> 1)) * 8, (k & 1) ^ 1);
-        mbar_wait(bars + (BAR_RING + slot) * 8, (q / CF_NSLOT) & 1);           // chunk q has landed
-        const uint32_t src = ring + slot * CH_BYTES;
-        // each warp converts 2 of the chunk's 12 image rows (84 pixels = 3 lane passes each); all six 16-byte loads are
-        // issued before the first conversion so their latencies overlap
-        constexpr int RPW = CH_ROWS / CF_AUX_WARPS;
-        static_assert(RPW * CF_AUX_WARPS == CH_ROWS, "rows must split evenly over the aux warps");
-        uint32_t px4[RPW][3][4];
-#pragma unroll
-        for (int rr = 0; rr < RPW; ++rr)
-#pragma unroll
-          for (int it = 0; it < 3; ++it)
-            if (lane + 32 * it < IMG) lds128(px4[rr][it], src + ((warp + rr * CF_AUX_WARPS) * IMG + lane + 32 * it) * 16);
-#pragma unroll
-        for (int rr = 0; rr < RPW; ++rr) {
-          const int pr = c * CH_ROWS + warp + rr * CF_AUX_WARPS + 2;   // padded row: band pr / 28 and, for the 4 halo rows, band - 1
-          const int bj = min(pr / BAND_ROW0, CF_BANDS - 1), rj = pr - bj * BAND_ROW0;
-          const uint32_t d0 = hb + bj * HB_BYTES + rj * XS_ROW_BYTES + 16;
-          const bool halo = bj > 0 && rj < HB_ROWS - BAND_ROW0;   // rows 28 j .. 28 j + 3 also close band j - 1
-          const uint32_t d1 = d0 - HB_BYTES + BAND_ROW0 * XS_ROW_BYTES;
-#pragma unroll
-          for (int it = 0; it < 3; ++it) {
-            const int px = lane + 32 * it;
-            if (px < IMG) {
-              const uint32_t* r = px4[rr][it];
-              const uint32_t lo = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1])),
-                             hi = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
-              sts64(d0 + px * 8, lo, hi);
-              if (halo) sts64(d1 + px * 8, lo, hi);
-            }
-          }
-        }
-        named_bar_sync(1, CF_AUX_THREADS);                         // the slot has been consumed, the rows are written
-        if (atid == 0) {
-          if (q + CF_NSLOT < n_chunks) {
-            fence_proxy_async();                                   // generic-proxy reads of the slot before its async-proxy refill
-            issue_chunk(q + CF_NSLOT);
-          }
-          if (c == 2) mbar_arrive(bars + (BAR_HFULL + 0) * 8);     // image rows 0..35 written: band 0 (padded rows 0..31) complete
-          if (c == 4) mbar_arrive(bars + (BAR_HFULL + 1) * 8);     // image rows ..59: band 1 (padded rows 28..59) complete
-          if (c == CF_NCHUNK - 1) mbar_arrive(bars + (BAR_HFULL + 2) * 8);
-        }
-      }
-      if (k > 0) epilogue(k - 1);
-    }
-    if (n_frames > 0) epilogue(n_frames - 1);
-  } else {
-    // =========================== conv11 group: HMMA, im2col scatter, UMMA issue ===========================
-    const int cw = warp - CF_AUX_WARPS;                            // 0..11
-    // conv11 weights as register-resident B fragments: k16 step = (kh, half): pixels kw = 4*half + t, 4 channels
-    uint32_t wb[16][2][2];
-#pragma unroll
-    for (int ks = 0; ks < 16; ++ks) {
-      const int kh = ks >> 1, kw = 4 * (ks & 1) + t;
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const float* w = w11 + ((kh * 8 + kw) * 4) * C1_OUT + 8 * nt + g;
-        wb[ks][nt][0] = pack_bf16(w[0], w[C1_OUT]);
-        wb[ks][nt][1] = pack_bf16(w[2 * C1_OUT], w[3 * C1_OUT]);
-      }
-    }
-    constexpr uint32_t idesc = make_idesc(C2_OUT, false, false);
-    const float bz[2][2] = {{bias_s[2 * t], bias_s[2 * t + 1]}, {bias_s[8 + 2 * t], bias_s[8 + 2 * t + 1]}};
-    const uint32_t sa4t = sa + 4 * t;
-    for (int k = 0; k < n_frames; ++k) {
-      bool a_free = (k == 0);                                      // frame k-1's UMMAs have finished reading the im2col buffer
+      if (k > 0) conv12_epilogue(k - 1);                             // also: the im2col operand of frame k-1 is no longer read
       uint16_t* n1_dst = n1_out ? n1_out + frame_of(k) * (N1_POS * C1_OUT) : nullptr;
 #pragma unroll 1
-      for (int h = 0; h < CF_BANDS; ++h) {                         // this warp's tile of band h
-        const int pbase = h * BAND_POS + cw * 16, pend = (h + 1) * BAND_POS;
-        mbar_wait(bars + (BAR_HFULL + h) * 8, k & 1);              // band h of frame k is complete
-        const int r0 = pbase + g, r1 = r0 + 8;
-        const int p0 = min(r0, pend - 1), p1 = min(r1, pend - 1);
-        const int oy0 = p0 / H1, ox0 = p0 - oy0 * H1, oy1 = p1 / H1, ox1 = p1 - oy1 * H1;
-        const uint32_t hbase = hb + h * HB_BYTES - h * BAND_ROW0 * XS_ROW_BYTES;
-        const uint32_t a0 = hbase + (4 * oy0) * XS_ROW_BYTES + (4 * ox0 + t) * 8;
-        const uint32_t a1 = hbase + (4 * oy1) * XS_ROW_BYTES + (4 * ox1 + t) * 8;
-        float acc[2][4] = {};
+      for (int i = 0; i < C11_TILES; ++i) {
+        mbar_wait(bar(BAR_C11 + i), k & 1);
+        tc_fence_after();
+        uint32_t r[32];                                              // [0,16): b = 0 part of row m ; [16,32): b = 1 part, owed to row m-1
+        tc_ld32(tlane + 32 * i, r);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BAR_T1FREE + i));
+        // out[m] = D[m, 0:16] + D[m+1, 16:32]: the neighbour row is the next lane; lane 31 takes it from the next warp's lane 0
+        float* xch = reinterpret_cast<float*>(smem + CF_OFF_XCH) + (i & 1) * 64;
+        if (lane == 0) {
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks) {
-          const int off = (ks >> 1) * XS_ROW_BYTES + (ks & 1) * 32;
-          uint32_t a[4];
-          lds64(a[0], a[2], a0 + off);
-          lds64(a[1], a[3], a1 + off);
-          mma_bf16_16816(acc[0], a, wb[ks][0][0], wb[ks][0][1]);
-          mma_bf16_16816(acc[1], a, wb[ks][1][0], wb[ks][1][1]);
+          for (int c = 0; c < 16; ++c) xch[ew * 16 + c] = __uint_as_float(r[16 + c]);
         }
-        __syncwarp();                                              // this warp no longer reads band h of frame k
-        if (lane == 0) mbar_arrive(bars + (BAR_HEMPTY + h) * 8);
-        if (!a_free) {
-          mbar_wait(bars + BAR_MMA * 8, (k - 1) & 1);
-          a_free = true;
+        named_bar_sync(2, 128);
+        float up[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) up[c] = __shfl_down_sync(0xffffffffu, __uint_as_float(r[16 + c]), 1);
+        if (lane == 31 && ew < 3) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) up[c] = xch[(ew + 1) * 16 + c];
         }
-        // epilogue: +bias, ReLU, bf16 -> the im2col slots this pixel feeds (+ n1 to HBM when training)
+        const int mt = ew * 32 + lane, m = C11_TSTRIDE * i + mt, oy = m / BLK_W, ox = m - oy * BLK_W;
+        if (mt < C11_TSTRIDE && oy < H1 && ox < H1) {
+          uint32_t o[8];
 #pragma unroll
-        for (int rsel = 0; rsel < 2; ++rsel) {
-          const int r = rsel ? r1 : r0;
-          if (r < pend) {
-            uint32_t e01, e23;
-            lds64(e01, e23, lut + r * 8);
-            const uint32_t e[4] = {e01 & 0xFFFFu, e01 >> 16, e23 & 0xFFFFu, e23 >> 16};
+          for (int jj = 0; jj < 8; ++jj)
+            o[jj] = pack_bf16(fmaxf(__uint_as_float(r[2 * jj]) + up[2 * jj] + bias_s[2 * jj], 0.f),
+                              fmaxf(__uint_as_float(r[2 * jj + 1]) + up[2 * jj + 1] + bias_s[2 * jj + 1], 0.f));
+          const uint4 lo = make_uint4(o[0], o[1], o[2], o[3]), hi = make_uint4(o[4], o[5], o[6], o[7]);
+          const int p = oy * H1 + ox;
+          uint32_t e01, e23;
+          lds64(e01, e23, lut + p * 8);
+          const uint32_t e[4] = {e01 & 0xFFFFu, e01 >> 16, e23 & 0xFFFFu, e23 >> 16};
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-              const uint32_t v = pack_bf16(fmaxf(acc[nt][2 * rsel] + bz[nt][0], 0.f), fmaxf(acc[nt][2 * rsel + 1] + bz[nt][1], 0.f));
-#pragma unroll
-              for (int idx = 0; idx < 4; ++idx)
-                if (e[idx] != 0xFFFFu) sts32(sa4t + ((e[idx] ^ nt) << 4), v);
-              if (n1_dst) *reinterpret_cast<uint32_t*>(n1_dst + r * C1_OUT + 8 * nt + 2 * t) = v;
+          for (int idx = 0; idx < 4; ++idx) {
+            if (e[idx] != 0xFFFFu) {
+              sts128(sa2 + (e[idx] << 4), lo);
+              sts128(sa2 + ((e[idx] ^ 1u) << 4), hi);
             }
+          }
+          if (n1_dst) {
+            uint4* d = reinterpret_cast<uint4*>(n1_dst + p * C1_OUT);
+            d[0] = lo;
+            d[1] = hi;
           }
         }
       }
-      // every scatter of frame k is done: hand the im2col buffer to the tensor core
-      fence_proxy_async();
-      named_bar_sync(2, CF_C11_THREADS);
-      if (cw == 0 && lane == 0) {
-        if (k > 0) mbar_wait(bars + BAR_TMEM * 8, (k - 1) & 1);    // the accumulator of frame k-1 has been drained
-        tc_fence_after();
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-          const uint64_t da = make_desc(sa + kb * 16384, false), db = make_desc(sb + kb * 4096, false);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            tc_mma_bf16(tmem_base, da + (uint64_t)(kk * 32 >> 4), db + (uint64_t)(kk * 32 >> 4), idesc, (kb | kk) ? 1u : 0u);
-        }
-        tc_commit(bars + BAR_MMA * 8);
-      }
+      fence_proxy_async();                                           // the scatter is read by the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(BAR_A2RDY));
     }
+    if (n_frames > 0) conv12_epilogue(n_frames - 1);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == CF_EPI_WARP0) {
     tc_fence_after();
-    tmem_dealloc<32>(tmem_base);
+    tmem_dealloc<CF_TMEM_COLS>(tmem_base);
   }
 }
 
