@@ -11,6 +11,8 @@
 // atomicAdd per element per CTA.
 #include "common.cuh"
 #include "kernels.h"
+#include "tcgen05.cuh"
+#include "conv_blk.cuh"
 
 namespace ga3c {
 
@@ -226,145 +228,197 @@ conv12_bwd_kernel(const uint16_t* __restrict__ n1, const uint16_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv11 weight gradient.  One persistent CTA per SM, 16 warps; per frame
-//   TMA engine : cp.async.bulk of frame i+1 into the fp32 staging buffer (mbarrier), cp.async of dn1(i+1)
-//   all warps  : wait -> fp32 staging -> padded bf16 image -> [issue frame i+1] -> wgrad MMAs
-// warp = (kh, part): M tile pair (kh, half 0/1) x N 16, K = the 14 k16 position steps of its part.
-constexpr int W11_THREADS = 512;
-constexpr int W11_NCH = 2, W11_CHUNK_PIX = IMG * IMG / W11_NCH;   // staging chunks per frame
-constexpr int DN1S_ROWS = 448;                                    // 441 padded to 28 k16 steps
-constexpr int DN1S_BYTES = DN1S_ROWS * 32;                        // 14,336
-constexpr int C11_OFF_STG = 0;
-constexpr int C11_OFF_XS = C11_OFF_STG + FRAME_BYTES;         // 112,896
-constexpr int C11_OFF_DN1S = C11_OFF_XS + XS_BYTES;               // 174,848 (two buffers)
-constexpr int C11_OFF_RED = C11_OFF_DN1S + 2 * DN1S_BYTES;        // 203,520
-constexpr int C11_OFF_BAR = C11_OFF_RED + W11_THREADS * 4;        // 205,568
-constexpr int C11_SMEM = C11_OFF_BAR + 8 * W11_NCH;            // 205,600
-
-// 16-B chunk h (pixels 2h, 2h+1) of pixel quad q sits at h ^ ((q >> 2) & 1): the transposed ldmatrix
-// reads of 8 consecutive positions (32 B apart) then touch all 32 banks once
-__device__ __forceinline__ uint32_t xs_chunk_off(int px) {        // byte offset of the 16-B chunk holding padded pixel px (even)
-  const int q = px >> 2, h = (px >> 1) & 1;
-  return q * 32 + ((h ^ ((q >> 2) & 1)) << 4);
-}
-
-__device__ __forceinline__ void w11_prefetch_dn1(const uint16_t* __restrict__ dn1, int b, uint32_t dn1s, int tid) {
-  const uint4* s1 = reinterpret_cast<const uint4*>(dn1 + (size_t)b * N1_POS * C1_OUT);
-  for (int i = tid; i < N1_POS * 2; i += W11_THREADS) {
-    const int pos = i >> 1;
-    cp_async16(dn1s + pos * 32 + ((((i & 1) ^ (pos >> 2)) & 1) << 4), s1 + i, 16);
-  }
-}
+// conv11 weight gradient on tcgen05.  With the space-to-depth block matrix Blk (conv_blk.cuh) the gradient of
+// quadrant (a, b) of the 8x8 kernel is one long-K GEMM over output positions m = oy*22 + ox:
+//     dW_ab[64 (dy, dx, c), 16 cout] = sum_m Blk[m + 22a + b, :]^T . dn1[m, :]
+// A = Blk read MN-major (transposed) at a row-shifted start address, B = dn1 staged MN-major (two 8-channel planes,
+// dead column and tail rows zero), M = 64, N = 16, K = 464 positions = 29 UMMAs per quadrant and frame.  The four
+// accumulators live in TMEM for the whole kernel (all frames of the CTA) and are flushed once with atomics.
+//   warps 0-5   fp32 chunk (TMA ring) -> bf16 -> Blk (as in conv_fwd)
+//   warp  6     one thread issues the UMMAs group by group as the Blk rows land
+//   warps 8-11  dn1 frame -> shared memory (cp.async, double buffered), bias gradient; final TMEM flush
+constexpr int W11_THREADS = 384, W11_AUX_WARPS = 6, W11_AUX_THREADS = 32 * W11_AUX_WARPS, W11_ISSUE_WARP = 6, W11_EPI_WARP0 = 8;
+constexpr int W11_KSTEPS = 29;                                   // 464 >= 462 positions (21 rows x 22, column 21 dead)
+constexpr int DN1_PLANE = 512 * 16, DN1_BUF = 2 * DN1_PLANE;     // 8 channels x 512 rows per plane, 2 planes per frame
+constexpr int W11_OFF_BLK = 0;
+constexpr int W11_OFF_RING = W11_OFF_BLK + BLK_BYTES;            //  70,144
+constexpr int W11_OFF_DN1 = W11_OFF_RING + CF_NSLOT * CH_BYTES;  // 134,656 (two buffers)
+constexpr int W11_OFF_RED = W11_OFF_DN1 + 2 * DN1_BUF;           // 167,424
+constexpr int W11_OFF_BAR = W11_OFF_RED + 128 * 4;               // 167,936
+constexpr int WB_RING = 0;        // [4] TMA chunk landed
+constexpr int WB_BLKRDY = 4;      // [4] Blk rows of position group i converted          (aux -> issuer)
+constexpr int WB_GRP = 8;         // [4] UMMAs of group i retired (tcgen05.commit)       (-> aux: Blk rows free)
+constexpr int WB_DN1RDY = 12;     // [2] dn1 buffer staged                                (stager -> issuer)
+constexpr int WB_DN1FREE = 14;    // [2] every UMMA reading the dn1 buffer retired        (-> stager)
+constexpr int WB_DONE = 16;       //     every UMMA of the kernel retired                   (-> final flush)
+constexpr int W11_NBAR = 17;
+constexpr int W11_OFF_TSLOT = W11_OFF_BAR + W11_NBAR * 8;
+constexpr int C11_SMEM = W11_OFF_TSLOT + 16 + 128;
 
 __global__ void __launch_bounds__(W11_THREADS, 1)
 conv11_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dn1, float* __restrict__ g_w11,
                     float* __restrict__ g_b11, int batch) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t sbase = smem_u32(smem);
-  const uint32_t stg = sbase + C11_OFF_STG, xs = sbase + C11_OFF_XS, bar = sbase + C11_OFF_BAR;
-  float* red = reinterpret_cast<float*>(smem + C11_OFF_RED);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int j = lane >> 3, rr = lane & 7;
-  const int kh = warp & 7, part = warp >> 3;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* const smem = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t blk = sbase + W11_OFF_BLK, ring = sbase + W11_OFF_RING, dn1s = sbase + W11_OFF_DN1, bars = sbase + W11_OFF_BAR,
+                 tslot = sbase + W11_OFF_TSLOT;
+  float* red = reinterpret_cast<float*>(smem + W11_OFF_RED);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int stride = gridDim.x;
+  const int n_frames = ((int)blockIdx.x < batch) ? (batch - 1 - (int)blockIdx.x) / stride + 1 : 0;
+  const int n_chunks = n_frames * CF_NCHUNK;
+  auto frame_of = [&](int k) { return (size_t)(blockIdx.x + k * stride); };
+  auto bar = [&](int i) { return bars + i * 8; };
+  auto issue_chunk = [&](int q) {                                  // one thread
+    const int k = q / CF_NCHUNK, c = q - k * CF_NCHUNK, slot = q % CF_NSLOT;
+    mbar_expect_tx(bar(WB_RING + slot), CH_BYTES);
+    bulk_load(ring + slot * CH_BYTES, reinterpret_cast<const uint8_t*>(x + frame_of(k) * STATE_DIM) + c * CH_BYTES, CH_BYTES,
+              bar(WB_RING + slot));
+  };
 
   if (tid == 0) {
-    for (int c = 0; c < W11_NCH; ++c) mbar_init(bar + 8 * c, 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar(WB_RING + i), 1);
+      mbar_init(bar(WB_BLKRDY + i), 1);
+      mbar_init(bar(WB_GRP + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(WB_DN1RDY + i), 1);
+      mbar_init(bar(WB_DN1FREE + i), 1);
+    }
+    mbar_init(bar(WB_DONE), 1);
     fence_mbar_init();
   }
-  for (int i = tid; i < (XS_BYTES + 2 * DN1S_BYTES) / 16; i += W11_THREADS) sts128(xs + i * 16, make_uint4(0, 0, 0, 0));
+  if (warp == W11_EPI_WARP0) tmem_alloc<64>(tslot);
   __syncthreads();
-  int b = blockIdx.x;
-  if (b < batch) {
-    if (tid == 0)                                 // x is an input of the step: stream it before the dependency wait
-      for (int c = 0; c < W11_NCH; ++c) stg_issue_chunk<W11_NCH>(stg, x + (size_t)b * STATE_DIM, c, bar);
-  }
+  if (tid == 0)                                                    // x is an input of the step: stream it before the dependency wait
+    for (int q = 0; q < CF_NSLOT && q < n_chunks; ++q) issue_chunk(q);
+  // zero once: image borders / slack rows of Blk; dead-column and tail rows of both dn1 buffers
+  for (int i = tid; i < BLK_BYTES / 16; i += W11_THREADS) sts128(blk + i * 16, make_uint4(0, 0, 0, 0));
+  for (int i = tid; i < 2 * DN1_BUF / 16; i += W11_THREADS) sts128(dn1s + i * 16, make_uint4(0, 0, 0, 0));
   griddep_launch();
   griddep_wait();               // dn1 comes from conv12_bwd, which precedes this kernel
-  if (b < batch) w11_prefetch_dn1(dn1, b, sbase + C11_OFF_DN1S, tid);
-  cp_async_commit();
-
-  float wacc[2][2][4] = {};   // m-tiles (kh, half = 0/1) x 2 n-tiles
-  float bacc = 0.f;           // db11 partial: co = tid & 15, part = tid >> 4
-
-  uint32_t phase = 0;
-  int buf = 0;
-  for (; b < batch; b += stride, buf ^= 1) {
-    const uint32_t dn1s = sbase + C11_OFF_DN1S + buf * DN1S_BYTES;
-    const bool more = b + stride < batch;
-    cp_async_wait<0>();                       // dn1(b): visible to all after the first barrier below
-#pragma unroll 1
-    for (int c = 0; c < W11_NCH; ++c) {    // fp32 staging -> zero-bordered, chunk-swizzled bf16 image
-      mbar_wait(bar + 8 * c, phase);
-#pragma unroll 2
-      for (int k = tid; k < W11_CHUNK_PIX; k += W11_THREADS) {
-        const int i = c * W11_CHUNK_PIX + k;
-        uint32_t r[4];
-        lds128(r, stg + i * 16);
-        const int y = i / IMG, px = i - y * IMG + 2;
-        sts64(xs + (y + 2) * XS_ROW_BYTES + xs_chunk_off(px & ~1) + (px & 1) * 8,
-              pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1])), pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3])));
-      }
-      __syncthreads();                        // chunk c is free (after the last one: image + dn1(b) complete)
-      if (tid == 0 && more) {
-        fence_proxy_async();
-        stg_issue_chunk<W11_NCH>(stg, x + (size_t)(b + stride) * STATE_DIM, c, bar);
-      }
-    }
-    phase ^= 1;
-    if (more) w11_prefetch_dn1(dn1, b + stride, sbase + C11_OFF_DN1S + (buf ^ 1) * DN1S_BYTES, tid);
-    cp_async_commit();
-
-#pragma unroll 2
-    for (int kk = 0; kk < 14; ++kk) {
-      const int ks = part * 14 + kk;
-      uint32_t bf[4];
-      {
-        const int pos = ks * 16 + (j & 1) * 8 + rr;                 // rows 441..447 are zero
-        ldsm_x4_t(bf, dn1s + pos * 32 + ((((j >> 1) ^ (pos >> 2)) & 1) << 4));
-      }
-      const int pos = min(ks * 16 + (j >> 1) * 8 + rr, N1_POS - 1);
-      const int oy = pos / H1, ox = pos - oy * H1;
-      const uint32_t arow = xs + (4 * oy + kh) * XS_ROW_BYTES;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t af[4];
-        ldsm_x4_t(af, arow + xs_chunk_off(4 * ox + 4 * half + 2 * (j & 1)));
-        mma_bf16_16816(wacc[half][0], af, bf[0], bf[1]);
-        mma_bf16_16816(wacc[half][1], af, bf[2], bf[3]);
-      }
-    }
-    {
-      const int co = tid & 15;
-      for (int pos = tid >> 4; pos < N1_POS; pos += W11_THREADS / 16) {
-        uint16_t v;
-        asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v)
-                     : "r"(dn1s + pos * 32 + ((((co >> 3) ^ (pos >> 2)) & 1) << 4) + (co & 7) * 2));
-        bacc += __uint_as_float((uint32_t)v << 16);
-      }
-    }
-    __syncthreads();                          // the image is rewritten by the next iteration's convert
-  }
-
-  // m_local = kw_local*4 + c within tile (kh, kw = 4*half + kw_local); the two parts of a kh add up in global
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-      float* o = g_w11 + ((kh * 8 + 4 * half) * 4) * C1_OUT + 8 * nt + 2 * t;
-      atomicAdd(o + g * C1_OUT, wacc[half][nt][0]);
-      atomicAdd(o + g * C1_OUT + 1, wacc[half][nt][1]);
-      atomicAdd(o + (g + 8) * C1_OUT, wacc[half][nt][2]);
-      atomicAdd(o + (g + 8) * C1_OUT + 1, wacc[half][nt][3]);
-    }
-  }
-  red[tid] = bacc;
+  fence_proxy_async();
+  tc_fence_before();
   __syncthreads();
-  if (tid < C1_OUT) {
-    float s = 0.f;
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tslot));
+
+  if (warp < W11_AUX_WARPS) {
+    // =========================== aux: fp32 chunk -> bf16 block matrix, slot re-arm ===========================
+    uint32_t lane_off[3];
+    blk_lane_offsets(lane, lane_off);
+    for (int k = 0; k < n_frames; ++k) {
+#pragma unroll 1
+      for (int c = 0; c < CF_NCHUNK; ++c) {
+        const int q = k * CF_NCHUNK + c, slot = q % CF_NSLOT;
+        // block rows 3c..3c+3 are rewritten: the last position group of frame k-1 that reads them must have retired
+        if (k > 0) mbar_wait(bar(WB_GRP + (c + 1) / 2), (k - 1) & 1);
+        mbar_wait(bar(WB_RING + slot), (q / CF_NSLOT) & 1);
+        blk_convert_chunk<W11_AUX_WARPS>(ring + slot * CH_BYTES, blk, c, warp, lane, lane_off);
+        fence_proxy_async();
+        named_bar_sync(1, W11_AUX_THREADS);
+        if (tid == 0) {
+          if (q + CF_NSLOT < n_chunks) issue_chunk(q + CF_NSLOT);
+          // position group i (m in [128 i, 128 i + 128)) reads block rows up to (128 i + 150) / 22
+          if (c == 2) mbar_arrive(bar(WB_BLKRDY + 0));
+          if (c == 4) mbar_arrive(bar(WB_BLKRDY + 1));
+          if (c == 6) { mbar_arrive(bar(WB_BLKRDY + 2)); mbar_arrive(bar(WB_BLKRDY + 3)); }
+        }
+      }
+    }
+  } else if (warp == W11_ISSUE_WARP) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_m(64, C1_OUT, true, true);
+      for (int k = 0; k < n_frames; ++k) {
+        const uint32_t dbuf = dn1s + (k & 1) * DN1_BUF;
+        mbar_wait(bar(WB_DN1RDY + (k & 1)), (k >> 1) & 1);
+        for (int gi = 0; gi < 4; ++gi) {
+          mbar_wait(bar(WB_BLKRDY + gi), k & 1);
+          tc_fence_after();
+          const int s1 = gi == 3 ? W11_KSTEPS : 8 * gi + 8;
+          for (int s = 8 * gi; s < s1; ++s) {
+            // B: dn1 rows [16 s, 16 s + 16): MN-major, 8-channel planes at SBO = DN1_PLANE, 8-row k groups at LBO = 128
+            const uint64_t db = make_desc_ns(dbuf + s * 256, 128, DN1_PLANE);
 #pragma unroll
-    for (int p = 0; p < W11_THREADS / 16; ++p) s += red[p * 16 + tid];
-    atomicAdd(g_b11 + tid, s);
+            for (int q = 0; q < 4; ++q)
+              // A: Blk rows 16 s + 22 a + b ..: MN-major, k-chunks (8 of the 64 block elements) at SBO = BLK_LBO
+              tc_mma_bf16(tmem_base + 16 * q, make_desc_ns(blk + (16 * s + BLK_W * (q >> 1) + (q & 1)) * 16, 128, BLK_LBO), db,
+                          idesc, (k | s) ? 1u : 0u);
+          }
+          tc_commit(bar(WB_GRP + gi));
+        }
+        tc_commit(bar(WB_DN1FREE + (k & 1)));
+      }
+      tc_commit(bar(WB_DONE));
+    }
+  } else if (warp >= W11_EPI_WARP0) {
+    // =========================== dn1 staging + bias gradient; final flush ===========================
+    const int etid = tid - 32 * W11_EPI_WARP0, ew = warp - W11_EPI_WARP0;
+    float bacc = 0.f;                                              // db11 partial: channel etid & 15, row phase etid >> 4
+    for (int k = 0; k < n_frames; ++k) {
+      const uint32_t dbuf = dn1s + (k & 1) * DN1_BUF;
+      if (k >= 2) mbar_wait(bar(WB_DN1FREE + (k & 1)), ((k >> 1) - 1) & 1);   // frame k-2 (same buffer) has been consumed
+      const uint4* src = reinterpret_cast<const uint4*>(dn1 + frame_of(k) * (N1_POS * C1_OUT));
+      for (int i = etid; i < N1_POS * 2; i += 128) {
+        const int p = i >> 1, oy = p / H1, ox = p - oy * H1;
+        cp_async16(dbuf + (i & 1) * DN1_PLANE + (oy * BLK_W + ox) * 16, src + i, 16);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      fence_proxy_async();
+      named_bar_sync(2, 128);
+      if (etid == 0) mbar_arrive(bar(WB_DN1RDY + (k & 1)));
+      {
+        const int co = etid & 15;
+        for (int m = etid >> 4; m < H1 * BLK_W; m += 8) {          // dead-column rows are zero
+          uint16_t v;
+          asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(dbuf + (co >> 3) * DN1_PLANE + m * 16 + (co & 7) * 2));
+          bacc += __uint_as_float((uint32_t)v << 16);
+        }
+      }
+    }
+    red[etid] = bacc;
+    named_bar_sync(2, 128);
+    if (etid < C1_OUT) {
+      float sum = 0.f;
+#pragma unroll
+      for (int ph = 0; ph < 8; ++ph) sum += red[ph * 16 + etid];
+      if (n_frames > 0) atomicAdd(g_b11 + etid, sum);
+    }
+    // flush the four accumulators: M = 64 rows sit on TMEM lanes 32 w + (0..15) (rows 16 w ..), 16 columns per quadrant
+    if (n_frames > 0) {
+      mbar_wait(bar(WB_DONE), 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(tmem_base + ((uint32_t)(ew * 32) << 16) + 16 * q));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (lane < 16) {
+          // row = block element j*8 + e: j = dy*2 + (dx>>1), e = (dx&1)*4 + c
+          const int row = 16 * ew + lane, j = row >> 3, e = row & 7;
+          const int kh = 4 * (q >> 1) + (j >> 1), kw = 4 * (q & 1) + (j & 1) * 2 + (e >> 2), c = e & 3;
+          float* o = g_w11 + ((kh * 8 + kw) * 4 + c) * C1_OUT;
+#pragma unroll
+          for (int n = 0; n < C1_OUT; ++n) atomicAdd(o + n, __uint_as_float(r[n]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W11_EPI_WARP0) {
+    tc_fence_after();
+    tmem_dealloc<64>(tmem_base);
   }
 }
 

@@ -31,17 +31,13 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tcgen05.cuh"
+#include "conv_blk.cuh"
 
 namespace ga3c {
 
 constexpr int CF_THREADS = 384, CF_AUX_WARPS = 6, CF_AUX_THREADS = 32 * CF_AUX_WARPS, CF_ISSUE_WARP = 6, CF_EPI_WARP0 = 8;
 static_assert(CF_EPI_WARP0 % 4 == 0, "epilogue warp e must own TMEM lane quarter e");
-constexpr int CH_ROWS = 12, CF_NCHUNK = IMG / CH_ROWS, CH_BYTES = CH_ROWS * IMG * 16;     // 7 chunks of 16,128 B
-constexpr int CF_NSLOT = 4;
-static_assert(CF_NCHUNK * CH_ROWS == IMG && CH_BYTES % 16 == 0 && CH_ROWS % CF_AUX_WARPS == 0, "chunks must tile the frame");
-// block matrix: 22 x 22 blocks (+ slack rows read by the dead part of the last M tile); chunk arrays padded so that
-// neighbouring k-chunks start 16 banks apart
-constexpr int BLK_W = 22, BLK_ROWS = 548, BLK_LBO = BLK_ROWS * 16, BLK_BYTES = 8 * BLK_LBO;              // 8,768 / 70,144
+static_assert(CH_ROWS % CF_AUX_WARPS == 0, "image rows of a chunk split evenly over the aux warps");
 constexpr int C11_TILES = 4;                     // 462 output rows (21 x 22, column 21 dead) in 4 x 128
 constexpr int C11_TSTRIDE = 127;                                     // output rows per tile (tile row 127 only feeds row 126)
 static_assert((C11_TILES - 1) * C11_TSTRIDE + 128 + BLK_W <= BLK_ROWS && C11_TILES * C11_TSTRIDE >= H1 * BLK_W, "tiles must cover the outputs and stay inside the buffer");
@@ -67,22 +63,6 @@ constexpr int CF_OFF_TSLOT = CF_OFF_BAR + CF_NBAR * 8;               // 228,696
 constexpr int CF_OFF_XCH = CF_OFF_TSLOT + 16;                        // 228,712: [2][4 warps][16 floats] b-shift exchange across warps
 constexpr int CF_SMEM = CF_OFF_XCH + 512 + 1024;                     // 230,248 incl. slack to align the base to 1024 B
 constexpr int CF_TMEM_COLS = 256, TMEM_C12 = 128;                    // conv11 tiles at columns 0,32,64,96; conv12 at 128..159
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
-}
-// no-swizzle K-major operand: 16-byte k-chunk j of row r at start + j*LBO + (r/8)*SBO + (r%8)*16
-__device__ __forceinline__ uint64_t make_desc_ns(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-}
 
 __global__ void __launch_bounds__(CF_THREADS, 1)
 conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, const float* __restrict__ b11,
@@ -179,14 +159,8 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
 
   if (warp < CF_AUX_WARPS) {
     // =========================== aux: fp32 chunk -> bf16 block matrix, slot re-arm ===========================
-    constexpr int RPW = CH_ROWS / CF_AUX_WARPS;                      // image rows per warp and chunk
-    // per-lane part of the destination: padded pixel px = x + 2 -> block column X = px >> 2, dx = px & 3
     uint32_t lane_off[3];
-#pragma unroll
-    for (int it = 0; it < 3; ++it) {
-      const int px = lane + 32 * it + 2;
-      lane_off[it] = ((px >> 1) & 1) * BLK_LBO + (px >> 2) * 16 + (px & 1) * 8;
-    }
+    blk_lane_offsets(lane, lane_off);
     for (int k = 0; k < n_frames; ++k) {
 #pragma unroll 1
       for (int c = 0; c < CF_NCHUNK; ++c) {
@@ -194,26 +168,7 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
         // block rows 3c..3c+3 are rewritten: the last conv11 tile of frame k-1 that reads them must have completed
         if (k > 0) mbar_wait(bar(BAR_C11 + (c + 1) / 2), (k - 1) & 1);
         mbar_wait(bar(BAR_RING + slot), (q / CF_NSLOT) & 1);         // chunk q has landed
-        const uint32_t src = ring + slot * CH_BYTES;
-        uint32_t px4[RPW][3][4];                                     // all six 16-byte loads first: their latencies overlap
-#pragma unroll
-        for (int rr = 0; rr < RPW; ++rr)
-#pragma unroll
-          for (int it = 0; it < 3; ++it)
-            if (lane + 32 * it < IMG) lds128(px4[rr][it], src + ((warp + rr * CF_AUX_WARPS) * IMG + lane + 32 * it) * 16);
-#pragma unroll
-        for (int rr = 0; rr < RPW; ++rr) {
-          const int py = c * CH_ROWS + warp + rr * CF_AUX_WARPS + 2; // padded row -> block row Y = py >> 2, dy = py & 3
-          const uint32_t row_off = blk + (py & 3) * (2 * BLK_LBO) + (py >> 2) * (BLK_W * 16);
-#pragma unroll
-          for (int it = 0; it < 3; ++it) {
-            if (lane + 32 * it < IMG) {
-              const uint32_t* r = px4[rr][it];
-              sts64(row_off + lane_off[it], pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1])),
-                    pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3])));
-            }
-          }
-        }
+        blk_convert_chunk<CF_AUX_WARPS>(ring + slot * CH_BYTES, blk, c, warp, lane, lane_off);
         fence_proxy_async();                                         // Blk is read by the tensor core; the slot is refilled by the TMA
         named_bar_sync(1, CF_AUX_THREADS);                           // the slot has been consumed, the rows are written
         if (tid == 0) {

@@ -50,11 +50,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-// instruction descriptor, kind::f16: D = f32, A = B = bf16, M = 128
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+// instruction descriptor, kind::f16: D = f32, A = B = bf16; a_mn / b_mn: operand is MN-major (transposed)
+__host__ __device__ constexpr uint32_t make_idesc_m(int m, int n, bool a_mn, bool b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) { return make_idesc_m(TC_BM, n, a_mn, b_mn); }
 
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
