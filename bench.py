@@ -79,6 +79,8 @@ def kernel_work(name, b, train):
         return "hbm", N_PARAMS * 20 + n2 * fc * 2
     if name == "dp_done":
         return "hbm", 128
+    if name == "grad_reduce":     # L2-resident slabs: one slab per SM read, the small-tensor gradients written
+        return "hbm", (148 + 1) * 14_500 * 4
     if name in ("dense_fwd", "dense_wgrad", "dense_dgrad"):
         return "tensor", 2.0 * b * n2 * fc
     raise KeyError(name)

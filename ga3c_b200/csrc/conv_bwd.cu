@@ -6,9 +6,10 @@
 //   conv11_wgrad_kernel per frame: g_w11 += patches(x)^T dn1, g_b11 += colsum(dn1)
 //                      (conv11 has no data-gradient: x is the input)
 //
-// bf16 operands / fp32 accumulate on mma.sync tiles fed from shared memory; weight-gradient
-// accumulators stay in registers across all frames a CTA processes and are flushed with one
-// atomicAdd per element per CTA.
+// bf16 operands / fp32 accumulate (conv12: mma.sync tiles fed from shared memory, conv11: tcgen05 with TMEM
+// accumulators); weight-gradient accumulators stay on chip across all frames a CTA processes and are stored once,
+// into the CTA's own slab of the gradient-partial workspace.  grad_reduce (elementwise.cu) adds the slabs in a
+// fixed order: contended atomics cost more than the whole frame loop (measured), and the sums become reproducible.
 #include "common.cuh"
 #include "kernels.h"
 #include "tcgen05.cuh"
@@ -45,7 +46,8 @@ __device__ __forceinline__ int n1pl_off(int Y, int X) {              // padded p
 
 __global__ void __launch_bounds__(B12_THREADS, 1)
 conv12_bwd_kernel(const uint16_t* __restrict__ n1, const uint16_t* __restrict__ dn2, const float* __restrict__ w12,
-                  uint16_t* __restrict__ dn1, float* __restrict__ g_w12, float* __restrict__ g_b12, int batch) {
+                  uint16_t* __restrict__ dn1, float* __restrict__ g_w12, float* __restrict__ g_b12, int64_t gp_stride,
+                  int batch) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t wdf = sbase + B12_OFF_WDF, dn1s = sbase + B12_OFF_DN1S, lut = sbase + B12_OFF_LUT;
@@ -209,13 +211,14 @@ conv12_bwd_kernel(const uint16_t* __restrict__ n1, const uint16_t* __restrict__ 
     __syncthreads();   // dn1s and this input buffer are rewritten by the following iterations
   }
 
+  // this CTA's partial sums -> its slab (summed over CTAs by grad_reduce)
+  g_w12 += (int64_t)blockIdx.x * gp_stride;
+  g_b12 += (int64_t)blockIdx.x * gp_stride;
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
     float* o = g_w12 + (warp * C1_OUT) * C2_OUT + 8 * nt + 2 * t;
-    atomicAdd(o + g * C2_OUT, wacc[nt][0]);
-    atomicAdd(o + g * C2_OUT + 1, wacc[nt][1]);
-    atomicAdd(o + (g + 8) * C2_OUT, wacc[nt][2]);
-    atomicAdd(o + (g + 8) * C2_OUT + 1, wacc[nt][3]);
+    *reinterpret_cast<float2*>(o + g * C2_OUT) = make_float2(wacc[nt][0], wacc[nt][1]);
+    *reinterpret_cast<float2*>(o + (g + 8) * C2_OUT) = make_float2(wacc[nt][2], wacc[nt][3]);
   }
   red[tid] = bacc;
   __syncthreads();
@@ -223,7 +226,7 @@ conv12_bwd_kernel(const uint16_t* __restrict__ n1, const uint16_t* __restrict__ 
     float s = 0.f;
 #pragma unroll
     for (int p = 0; p < B12_WARPS; ++p) s += red[p * 32 + tid];
-    atomicAdd(g_b12 + tid, s);
+    g_b12[tid] = s;
   }
 }
 
@@ -257,7 +260,7 @@ constexpr int C11_SMEM = W11_OFF_TSLOT + 16 + 128;
 
 __global__ void __launch_bounds__(W11_THREADS, 1)
 conv11_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dn1, float* __restrict__ g_w11,
-                    float* __restrict__ g_b11, int batch) {
+                    float* __restrict__ g_b11, int64_t gp_stride, int batch) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* const smem = smem_raw + (sbase - smem_u32(smem_raw));
@@ -387,12 +390,13 @@ conv11_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dn
       float sum = 0.f;
 #pragma unroll
       for (int ph = 0; ph < 8; ++ph) sum += red[ph * 16 + etid];
-      if (n_frames > 0) atomicAdd(g_b11 + etid, sum);
+      g_b11[(int64_t)blockIdx.x * gp_stride + etid] = sum;
     }
     // flush the four accumulators: M = 64 rows sit on TMEM lanes 32 w + (0..15) (rows 16 w ..), 16 columns per quadrant
     if (n_frames > 0) {
       mbar_wait(bar(WB_DONE), 0);
       tc_fence_after();
+      float* const slab = g_w11 + (int64_t)blockIdx.x * gp_stride;  // this CTA's partial sums (summed by grad_reduce)
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         uint32_t r[16];
@@ -406,9 +410,11 @@ conv11_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dn
           // row = block element j*8 + e: j = dy*2 + (dx>>1), e = (dx&1)*4 + c
           const int row = 16 * ew + lane, j = row >> 3, e = row & 7;
           const int kh = 4 * (q >> 1) + (j >> 1), kw = 4 * (q & 1) + (j & 1) * 2 + (e >> 2), c = e & 3;
-          float* o = g_w11 + ((kh * 8 + kw) * 4 + c) * C1_OUT;
+          float4* o = reinterpret_cast<float4*>(slab + ((kh * 8 + kw) * 4 + c) * C1_OUT);
 #pragma unroll
-          for (int n = 0; n < C1_OUT; ++n) atomicAdd(o + n, __uint_as_float(r[n]));
+          for (int n = 0; n < C1_OUT / 4; ++n)
+            o[n] = make_float4(__uint_as_float(r[4 * n]), __uint_as_float(r[4 * n + 1]), __uint_as_float(r[4 * n + 2]),
+                               __uint_as_float(r[4 * n + 3]));
         }
       }
     }
@@ -429,16 +435,18 @@ int configure_conv_bwd() {
   return (int)e;
 }
 
+int conv_bwd_grid(int batch, int num_sms) { return min(batch, num_sms); }
+
 int launch_conv12_bwd(const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1, float* g_w12,
-                      float* g_b12, int batch, int num_sms, cudaStream_t stream) {
-  const int grid = min(batch, num_sms);
-  return launch_pdl(conv12_bwd_kernel, dim3(grid), dim3(B12_THREADS), B12_SMEM, stream, n1, dn2, w12, dn1, g_w12, g_b12, batch);
+                      float* g_b12, int64_t gp_stride, int batch, int num_sms, cudaStream_t stream) {
+  return launch_pdl(conv12_bwd_kernel, dim3(conv_bwd_grid(batch, num_sms)), dim3(B12_THREADS), B12_SMEM, stream, n1, dn2,
+                    w12, dn1, g_w12, g_b12, gp_stride, batch);
 }
 
-int launch_conv11_wgrad(const float* x, const uint16_t* dn1, float* g_w11, float* g_b11, int batch, int num_sms,
-                        cudaStream_t stream) {
-  const int grid = min(batch, num_sms);
-  return launch_pdl(conv11_wgrad_kernel, dim3(grid), dim3(W11_THREADS), C11_SMEM, stream, x, dn1, g_w11, g_b11, batch);
+int launch_conv11_wgrad(const float* x, const uint16_t* dn1, float* g_w11, float* g_b11, int64_t gp_stride, int batch,
+                        int num_sms, cudaStream_t stream) {
+  return launch_pdl(conv11_wgrad_kernel, dim3(conv_bwd_grid(batch, num_sms)), dim3(W11_THREADS), C11_SMEM, stream, x, dn1,
+                    g_w11, g_b11, gp_stride, batch);
 }
 
 }  // namespace ga3c

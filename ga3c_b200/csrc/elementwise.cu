@@ -5,6 +5,57 @@
 
 namespace ga3c {
 
+// ---- gradient-partial reduction ---------------------------------------------------------------------
+// The heads / conv12_bwd / conv11_wgrad kernels leave one slab of partial sums per CTA (a mirror of the small-tensor
+// prefix of the gradient arena + the loss sums).  512 threads = 16 slab lanes x 32 float4 columns: lane l adds slabs
+// l, l + 16, ... (independent 16-byte loads of L2-resident data), then the 16 lane sums are added in lane order.
+// The order is a function of the launch geometry only, so the gradients are bit-reproducible.
+constexpr int GR_LANES = 16, GR_COLS = 32, GR_UNROLL = 10;     // 160 slabs (one per SM) in a single batch of loads
+__global__ void __launch_bounds__(GR_LANES * GR_COLS) grad_reduce_kernel(GradReduceArgs a) {
+  __shared__ float4 part[GR_LANES][GR_COLS];
+  const int col = threadIdx.x & (GR_COLS - 1), sl = threadIdx.x / GR_COLS;
+  const int j = (blockIdx.x * GR_COLS + col) * 4;
+  int count = 0;
+  if (j < a.n_floats) {
+#pragma unroll
+    for (int s = GR_MAX_SEG - 1; s >= 0; --s)
+      if (j < a.seg_end[s]) count = a.seg_count[s];
+  }
+  griddep_launch();
+  griddep_wait();               // the slabs come from the kernels that precede this one
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* src = a.part + j;
+  for (int i0 = sl; i0 < count; i0 += GR_UNROLL * GR_LANES) {
+    float4 q[GR_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GR_UNROLL; ++u) {
+      const int i = i0 + u * GR_LANES;
+      q[u] = i < count ? __ldcg(reinterpret_cast<const float4*>(src + (int64_t)i * a.stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < GR_UNROLL; ++u) { acc.x += q[u].x; acc.y += q[u].y; acc.z += q[u].z; acc.w += q[u].w; }
+  }
+  part[sl][col] = acc;
+  __syncthreads();
+  if (sl == 0 && j < a.n_floats) {
+#pragma unroll
+    for (int l = 1; l < GR_LANES; ++l) {
+      const float4 q = part[l][col];
+      acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+    }
+    if (j < a.out_floats) *reinterpret_cast<float4*>(a.out + j) = acc;
+    else if (a.out_tail != nullptr) {          // caller's buffer: no alignment assumed
+      float* t = a.out_tail + (j - a.out_floats);
+      t[0] = acc.x; t[1] = acc.y; t[2] = acc.z; t[3] = acc.w;
+    }
+  }
+}
+
+int launch_grad_reduce(const GradReduceArgs& a, cudaStream_t stream) {
+  const int grid = (a.n_floats / 4 + GR_COLS - 1) / GR_COLS;
+  return launch_pdl(grad_reduce_kernel, dim3(grid), dim3(GR_LANES * GR_COLS), 0, stream, a);
+}
+
 // ---- RMSProp, TensorFlow semantics (tf.train.RMSPropOptimizer, NetworkVP_discrate.py:101-105) ----
 //   ms  <- rho*ms + (1-rho)*g^2 ; mom <- mu*mom + lr*g/sqrt(ms + eps) ; w <- w - mom       [TF-SEMANTICS]
 // One float4 per thread per iteration over the whole arena (all 10 variables in one launch instead

@@ -9,7 +9,8 @@
 // Phase 1: one warp per sample, warp-shuffle reductions for the A+1 dot products, then the whole
 //          softmax / loss / dlogits chain in registers; writes d1, p, v, dd1 (bf16) and stages (dz, dv).
 // Phase 2: one thread per dense1 feature accumulates dWp[j,:], dWv[j], db1[j] over the chunk.
-// Gradient / loss accumulators live in registers across chunks; one atomicAdd per element per CTA.
+// Gradient / loss accumulators live in registers across chunks; each CTA stores its partial sums into its own slab
+// of the gradient-partial workspace (summed in a fixed order by grad_reduce: no atomics, bit-reproducible).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -26,7 +27,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
   __shared__ __align__(16) float d1s[HD_CHUNK][FC];    // dense1 output of the chunk (post bias + ReLU)
   __shared__ __align__(16) float b1s[FC];
   __shared__ float bias_s[A1];
-  __shared__ float loss_s[3];
+  __shared__ float loss_s[HD_THREADS / 32][3];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   for (int i = tid; i < A1 * FC; i += HD_THREADS) {
@@ -35,7 +36,6 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
   }
   if (tid < A1) bias_s[tid] = (tid < A) ? p.bp[tid] : p.bv[0];
   b1s[tid] = p.b1[tid];
-  if (tid < 3) loss_s[tid] = 0.f;
   griddep_launch();
   __syncthreads();
   griddep_wait();               // d1_part comes from the dense1 GEMM that precedes this kernel
@@ -183,19 +183,24 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
   }
 
   if (!p.train) return;
+  const int64_t slab = (int64_t)blockIdx.x * p.gp_stride;
   {
     const int jx = tid;
 #pragma unroll
-    for (int k = 0; k < A; ++k) atomicAdd(p.g_wp + jx * A + k, acc[k]);
-    atomicAdd(p.g_wv + jx, acc[A]);
-    atomicAdd(p.g_b1 + jx, acc_b1);
-    if (tid < A) atomicAdd(p.g_bp + tid, acc_bh);
-    if (tid == A) atomicAdd(p.g_bv, acc_bh);
+    for (int k = 0; k < A; ++k) p.g_wp[slab + jx * A + k] = acc[k];
+    p.g_wv[slab + jx] = acc[A];
+    p.g_b1[slab + jx] = acc_b1;
+    if (tid < A) p.g_bp[slab + tid] = acc_bh;
+    if (tid == A) p.g_bv[slab] = acc_bh;
   }
-  if (p.loss != nullptr) {
-    if (lane == 0) { atomicAdd(&loss_s[0], l1); atomicAdd(&loss_s[1], l2); atomicAdd(&loss_s[2], lv); }
-    __syncthreads();
-    if (tid < 3) atomicAdd(p.loss + tid, loss_s[tid]);
+  if (lane == 0) { loss_s[warp][0] = l1; loss_s[warp][1] = l2; loss_s[warp][2] = lv; }
+  __syncthreads();
+  if (tid < 4) {
+    float s = 0.f;
+    if (tid < 3)
+#pragma unroll
+      for (int w = 0; w < HD_THREADS / 32; ++w) s += loss_s[w][tid];
+    p.loss[slab + tid] = s;
   }
 }
 
@@ -204,9 +209,10 @@ static int launch_heads_t(const HeadsArgs& args, int grid, cudaStream_t stream) 
   return launch_pdl(heads_kernel<A>, dim3(grid), dim3(HD_THREADS), 0, stream, args);
 }
 
+int heads_grid(int batch, int num_sms) { return min((batch + HD_CHUNK - 1) / HD_CHUNK, 2 * num_sms); }
+
 int launch_heads(const HeadsArgs& args, int num_sms, cudaStream_t stream) {
-  const int n_chunks = (args.batch + HD_CHUNK - 1) / HD_CHUNK;
-  const int grid = min(n_chunks, 2 * num_sms);
+  const int grid = heads_grid(args.batch, num_sms);
   switch (args.num_actions) {
 #define GA3C_CASE(N) case N: return launch_heads_t<N>(args, grid, stream);
     GA3C_CASE(1) GA3C_CASE(2) GA3C_CASE(3) GA3C_CASE(4) GA3C_CASE(5) GA3C_CASE(6) GA3C_CASE(7) GA3C_CASE(8)

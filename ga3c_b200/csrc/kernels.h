@@ -34,21 +34,42 @@ struct HeadsArgs {
   float beta, log_eps, min_policy;
   float *p_out, *v_out;        // may be null in train mode
   uint16_t* dd1;               // [B,256] bf16, train only
-  float *g_wp, *g_bp, *g_wv, *g_bv, *g_b1;   // accumulated with atomics, train only
-  float* loss;                 // [4] accumulated with atomics, may be null
+  // train only: this CTA's partial sums go to slab blockIdx.x of the gradient-partial workspace (pointers are
+  // into slab 0, consecutive slabs gp_stride floats apart); launch_grad_reduce sums the slabs
+  float *g_wp, *g_bp, *g_wv, *g_bv, *g_b1;
+  float* loss;                 // [4] (cost_p_1, cost_p_2, cost_v, 0) partial sums, same slab scheme
+  int64_t gp_stride;
   int train;
 };
+int heads_grid(int batch, int num_sms);          // CTAs (= slabs written) of a training launch
 int launch_heads(const HeadsArgs& args, int num_sms, cudaStream_t stream);
 
 // conv_bwd.cu
-//   conv12 backward: dn1 = dgrad(dn2, w12) masked by n1 > 0 (bf16 out); g_w12 += wgrad; g_b12 += colsum(dn2)
+// Weight / bias gradients are per-CTA partial sums: CTA i stores into slab i (g_* point into slab 0, slabs are
+// gp_stride floats apart) and launch_grad_reduce adds the slabs in a fixed order.  No contended atomics, and the
+// step is bit-reproducible.
+int conv_bwd_grid(int batch, int num_sms);       // CTAs (= slabs written) of both kernels
+//   conv12 backward: dn1 = dgrad(dn2, w12) masked by n1 > 0 (bf16 out); g_w12 = wgrad; g_b12 = colsum(dn2)
 int launch_conv12_bwd(const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1, float* g_w12,
-                      float* g_b12, int batch, int num_sms, cudaStream_t stream);
-//   conv11 wgrad: g_w11 += patches(x)^T dn1 ; g_b11 += colsum(dn1)
-int launch_conv11_wgrad(const float* x, const uint16_t* dn1, float* g_w11, float* g_b11, int batch, int num_sms,
-                        cudaStream_t stream);
+                      float* g_b12, int64_t gp_stride, int batch, int num_sms, cudaStream_t stream);
+//   conv11 wgrad: g_w11 = patches(x)^T dn1 ; g_b11 = colsum(dn1)
+int launch_conv11_wgrad(const float* x, const uint16_t* dn1, float* g_w11, float* g_b11, int64_t gp_stride, int batch,
+                        int num_sms, cudaStream_t stream);
 
 // elementwise.cu
+// out[j] = sum over slabs i < count(j) of part[i * stride + j], j in [0, n_floats): the per-CTA gradient partials of
+// the heads / conv12_bwd / conv11_wgrad kernels -> the small-tensor prefix of the gradient arena (+ the loss sums).
+constexpr int GR_MAX_SEG = 4;
+struct GradReduceArgs {
+  const float* part;
+  int64_t stride;
+  float* out;                       // floats [0, out_floats) go here ...
+  float* out_tail;                  // ... and floats [out_floats, n_floats) here (the loss sums; may be null)
+  int out_floats, n_floats;         // multiples of 4
+  int seg_end[GR_MAX_SEG];          // segment s covers [seg_end[s-1], seg_end[s]) and sums seg_count[s] slabs
+  int seg_count[GR_MAX_SEG];
+};
+int launch_grad_reduce(const GradReduceArgs& a, cudaStream_t stream);
 struct RmsPropArgs {
   float *w, *ms, *mom;
   const float* g;

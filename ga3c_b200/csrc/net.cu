@@ -66,6 +66,12 @@ struct ga3c_net {
   uint16_t *n1 = nullptr, *n2 = nullptr, *dd1 = nullptr, *dn2 = nullptr, *dn1 = nullptr;
   float* d1 = nullptr;
   float* d1_part = nullptr;        // [splits][B,256] raw split-K partials of dense1 (dense_tc.cu)
+  // gradient partials: one slab per CTA of the heads / conv backward kernels, laid out like the small-tensor prefix
+  // of the gradient arena followed by the 4 loss sums; summed by grad_reduce at the end of ga3c_fb_tail
+  float* gpart = nullptr;
+  int64_t gp_stride = 0;
+  int gp_heads_grid = 0;           // slabs the heads kernel of the current step wrote
+  float* loss_out = nullptr;       // caller's loss buffer of the current step (may be null)
   int64_t global_step = 0;
   int64_t launches = 0;
   int last_batch = 0;
@@ -80,9 +86,9 @@ struct ga3c_net {
 constexpr int DP_COMM_BYTES = 256;    // [0] ready step, [8] done step (uint64 at 64-byte spacing)
 
 enum { K_CONV_FWD = 0, K_DENSE_FWD, K_HEADS, K_DENSE_WGRAD, K_DENSE_DGRAD, K_CONV12_BWD, K_CONV11_WGRAD, K_RMSPROP,
-       K_COUNT };
+       K_GRAD_REDUCE, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {"conv_fwd", "dense_fwd", "heads", "dense_wgrad", "dense_dgrad",
-                                                  "conv12_bwd", "conv11_wgrad", "rmsprop"};
+                                                  "conv12_bwd", "conv11_wgrad", "rmsprop", "grad_reduce"};
 
 // launch one kernel of the path; when timing is enabled bracket it with events on the same stream
 #define LAUNCH(net, kid, st, call)                                                        \
@@ -162,6 +168,10 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
   n->mom = reinterpret_cast<float*>(n->slab + 3 * ab);
   n->w1_shadow = reinterpret_cast<uint16_t*>(n->slab + 4 * ab);
   cudaMemset(n->slab + 4 * ab + shadow_bytes, 0, DP_COMM_BYTES);
+  n->gp_stride = n->small_floats + 64;
+  e = cudaMalloc((void**)&n->gpart, (size_t)2 * n->num_sms * n->gp_stride * sizeof(float));
+  if (e != cudaSuccess) { ga3c_destroy(n); return fail("cudaMalloc", e); }
+  cudaMemset(n->gpart, 0, (size_t)2 * n->num_sms * n->gp_stride * sizeof(float));
   if (int r = alloc_workspace(n, cfg->max_batch)) { ga3c_destroy(n); return r; }
   cudaMemset(n->w, 0, ab); cudaMemset(n->g, 0, ab); cudaMemset(n->mom, 0, ab);
   cudaMemset(n->w1_shadow, 0, (size_t)FLAT * FC * 2);
@@ -212,6 +222,7 @@ extern "C" int ga3c_destroy(ga3c_net* n) {
   if (!n) return 0;
   ga3c_dp_detach(n);
   cudaFree(n->slab);
+  cudaFree(n->gpart);
   free_workspace(n);
   for (cudaEvent_t e : n->tev) cudaEventDestroy(e);
   delete n;
@@ -319,17 +330,17 @@ extern "C" int ga3c_fb_head(ga3c_net* n, const float* x, const float* yr, const 
   cudaStream_t st = (cudaStream_t)stream;
   const float* w = n->w;
   float* g = n->g;
-  // small-tensor gradients are accumulated with atomics -> zero them; dense1/w is overwritten by its GEMM
-  CK(cudaMemsetAsync(g, 0, (size_t)n->small_floats * 4, st));
-  if (loss) CK(cudaMemsetAsync(loss, 0, 4 * sizeof(float), st));
+  float* gp = n->gpart;       // small-tensor gradients: per-CTA partial slabs, summed at the end of ga3c_fb_tail
   LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
                                             w + n->off(P_C12B), n->n1, n->n2, batch, n->num_sms, st));
   const int splits = dense_fwd_splits(batch, n->num_sms);
   LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
   HeadsArgs h = heads_args(n, batch, splits);
-  h.yr = yr; h.a = a; h.beta = beta; h.train = 1; h.dd1 = n->dd1; h.loss = loss;
-  h.g_wp = g + n->off(P_PW); h.g_bp = g + n->off(P_PB); h.g_wv = g + n->off(P_VW); h.g_bv = g + n->off(P_VB);
-  h.g_b1 = g + n->off(P_D1B);
+  h.yr = yr; h.a = a; h.beta = beta; h.train = 1; h.dd1 = n->dd1;
+  h.g_wp = gp + n->off(P_PW); h.g_bp = gp + n->off(P_PB); h.g_wv = gp + n->off(P_VW); h.g_bv = gp + n->off(P_VB);
+  h.g_b1 = gp + n->off(P_D1B); h.loss = gp + n->small_floats; h.gp_stride = n->gp_stride;
+  n->gp_heads_grid = heads_grid(batch, n->num_sms);
+  n->loss_out = loss;
   LAUNCH(n, K_HEADS, st, launch_heads(h, n->num_sms, st));
   LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad_tc(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
   n->last_batch = batch;
@@ -344,12 +355,21 @@ extern "C" int ga3c_fb_tail(ga3c_net* n, const float* x, int32_t batch, void* st
   CK(cudaSetDevice(n->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   const float* w = n->w;
-  float* g = n->g;
+  float* gp = n->gpart;
   LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
-  LAUNCH(n, K_CONV12_BWD, st, launch_conv12_bwd(n->n1, n->dn2, w + n->off(P_C12W), n->dn1, g + n->off(P_C12W),
-                                                g + n->off(P_C12B), batch, n->num_sms, st));
-  LAUNCH(n, K_CONV11_WGRAD, st, launch_conv11_wgrad(x, n->dn1, g + n->off(P_C11W), g + n->off(P_C11B), batch,
-                                                    n->num_sms, st));
+  LAUNCH(n, K_CONV12_BWD, st, launch_conv12_bwd(n->n1, n->dn2, w + n->off(P_C12W), n->dn1, gp + n->off(P_C12W),
+                                                gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, st));
+  LAUNCH(n, K_CONV11_WGRAD, st, launch_conv11_wgrad(x, n->dn1, gp + n->off(P_C11W), gp + n->off(P_C11B), n->gp_stride,
+                                                    batch, n->num_sms, st));
+  // sum the per-CTA slabs: conv tensors (the first four of the arena) over the conv grids, head tensors and the
+  // loss sums over the heads grid
+  GradReduceArgs r{};
+  r.part = gp; r.stride = n->gp_stride; r.out = n->g; r.out_tail = n->loss_out;
+  r.out_floats = (int)n->small_floats; r.n_floats = (int)n->small_floats + 4;
+  const int conv_end = (int)n->off(P_D1B);
+  for (int s = 0; s < GR_MAX_SEG; ++s) { r.seg_end[s] = r.n_floats; r.seg_count[s] = n->gp_heads_grid; }
+  r.seg_end[0] = conv_end; r.seg_count[0] = conv_bwd_grid(batch, n->num_sms);
+  LAUNCH(n, K_GRAD_REDUCE, st, launch_grad_reduce(r, st));
   return 0;
 }
 

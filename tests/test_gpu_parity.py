@@ -270,6 +270,23 @@ def test_gradients_are_additive_over_batch_shards_b1024(ga3c):
         assert err(got[k], g_ref[k])[1] <= TOL_GRAD_REL, k
 
 
+def test_train_step_is_bit_reproducible_b1024(ga3c):
+    """Weight / bias gradients are per-CTA partial sums added in a fixed order (grad_reduce), the dense1 split-K
+    partials likewise: the same batch twice gives identical gradient and loss BITS, also with a different batch
+    (other slab contents, other grids) in between."""
+    params, x, y_r, a = make_case(1024, seed=21)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=1024)
+    net.set_variables(params)
+    l0 = net.losses(x, y_r, a)
+    g0 = net.get_gradients()
+    net.losses(x[:37], y_r[:37], a[:37])
+    l1 = net.losses(x, y_r, a)
+    g1 = net.get_gradients()
+    assert l0 == l1
+    for k in g0:
+        assert np.array_equal(g0[k], g1[k]), k
+
+
 def test_workspace_grows_for_unbounded_train_batches(ga3c):
     """ThreadTrainer concatenates agent batches without bound (ThreadTrainer.py:48-59)."""
     params, x, y_r, a = make_case(40)
