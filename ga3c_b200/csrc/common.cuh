@@ -132,7 +132,35 @@ __device__ __forceinline__ void stg_issue_chunk(uint32_t stg, const float* frame
 // griddep_launch() lets the successor begin launching; kernels call it once all their CTAs hold the
 // resources they need (so an early successor can never starve a not-yet-started CTA of this grid).
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
+// ---- step timeline trace (ga3c_trace_*) ---------------------------------------------------------------
+// When a trace buffer is attached, thread 0 of every CTA stamps %globaltimer (ns) at three points of its kernel:
+// launched (reached the dependency wait), started (dependency satisfied), ended.  Per kernel id the buffer keeps
+// {min, max} of each: 6 uint64.  This is the only way to see the pipelined step as it runs (per-kernel events
+// serialise the PDL chain, ncu serialises and flushes the caches).  One pointer per translation unit, set by
+// trace_attach_<file>(); detached (the default) it costs one predicated load per CTA.
+enum KernelId { K_CONV_FWD = 0, K_DENSE_FWD, K_HEADS, K_DENSE_WGRAD, K_DENSE_DGRAD, K_CONV12_BWD, K_CONV11_WGRAD, K_RMSPROP,
+                K_GRAD_REDUCE, K_COUNT };
+constexpr int TRACE_SLOTS = 6;
+static __device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ void trace_mark(int kid, int what) {      // what: 0 launched, 1 started, 2 ended
+  if (threadIdx.x == 0) {
+    unsigned long long* t = g_trace;
+    if (t != nullptr) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(now));
+      atomicMin(t + kid * TRACE_SLOTS + 2 * what, now);
+      atomicMax(t + kid * TRACE_SLOTS + 2 * what + 1, now);
+    }
+  }
+}
+__device__ __forceinline__ void griddep_wait(int kid) {
+  trace_mark(kid, 0);
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  trace_mark(kid, 1);
+}
+#define GA3C_TRACE_ATTACH(fn)                                                                   \
+  int fn(unsigned long long* buf) { return (int)cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)); }
 
 template <class... KArgs, class... Args>
 inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {

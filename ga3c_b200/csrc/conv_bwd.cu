@@ -111,7 +111,7 @@ conv12_bwd_kernel(const uint16_t* __restrict__ n1, const uint16_t* __restrict__ 
   const uint32_t tap_off = (kw & 1) * N1PL_PLANE + (kh * 12 + (kw >> 1)) * N1PL_PITCH;
   griddep_launch();
   __syncthreads();
-  griddep_wait();               // dn2 comes from the dense1 data-gradient GEMM that precedes this kernel
+  griddep_wait(K_CONV12_BWD); // dn2 comes from the dense1 data-gradient GEMM that precedes this kernel
 
   auto prefetch = [&](int b, uint32_t in) {
     const uint4* s1 = reinterpret_cast<const uint4*>(n1 + (size_t)b * N1_POS * C1_OUT);
@@ -228,6 +228,7 @@ conv12_bwd_kernel(const uint16_t* __restrict__ n1, const uint16_t* __restrict__ 
     for (int p = 0; p < B12_WARPS; ++p) s += red[p * 32 + tid];
     g_b12[tid] = s;
   }
+  trace_mark(K_CONV12_BWD, 2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -301,7 +302,7 @@ conv11_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dn
   for (int i = tid; i < BLK_BYTES / 16; i += W11_THREADS) sts128(blk + i * 16, make_uint4(0, 0, 0, 0));
   for (int i = tid; i < 2 * DN1_BUF / 16; i += W11_THREADS) sts128(dn1s + i * 16, make_uint4(0, 0, 0, 0));
   griddep_launch();
-  griddep_wait();               // dn1 comes from conv12_bwd, which precedes this kernel
+  griddep_wait(K_CONV11_WGRAD); // dn1 comes from conv12_bwd, which precedes this kernel
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -422,11 +423,14 @@ conv11_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ dn
 
   tc_fence_before();
   __syncthreads();
+  trace_mark(K_CONV11_WGRAD, 2);
   if (warp == W11_EPI_WARP0) {
     tc_fence_after();
     tmem_dealloc<64>(tmem_base);
   }
 }
+
+GA3C_TRACE_ATTACH(trace_attach_conv_bwd)
 
 int configure_conv_bwd() {
   cudaError_t e = cudaFuncSetAttribute(conv12_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B12_SMEM);

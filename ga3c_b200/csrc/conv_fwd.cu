@@ -126,7 +126,7 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
     sts64(lut + p * 8, e[0] | (e[1] << 16), e[2] | (e[3] << 16));
   }
   griddep_launch();
-  griddep_wait();               // the weights below come from the optimizer kernel that precedes this one in the stream
+  griddep_wait(K_CONV_FWD);               // the weights below come from the optimizer kernel that precedes this one in the stream
   // conv11 weights for row shift a: B operand [32 rows n2 = b*16 + cout][K = 64], no-swizzle K-major: k-chunk j = dy*2 + (dx>>1)
   // holds (dx&1, c) -> 8 elements; chunk j of row n2 at a*4096 + j*512 + n2*16
   for (int i = tid; i < 2 * 8 * 32; i += CF_THREADS) {
@@ -301,11 +301,14 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
 
   tc_fence_before();
   __syncthreads();
+  trace_mark(K_CONV_FWD, 2);
   if (warp == CF_EPI_WARP0) {
     tc_fence_after();
     tmem_dealloc<CF_TMEM_COLS>(tmem_base);
   }
 }
+
+GA3C_TRACE_ATTACH(trace_attach_conv_fwd)
 
 int configure_conv_fwd() {
   return (int)cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM);

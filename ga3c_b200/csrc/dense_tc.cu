@@ -94,7 +94,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   griddep_launch();             // every CTA of this grid holds its TMEM columns and shared memory
-  griddep_wait();               // operands are produced by the preceding kernels
+  constexpr int kid = A_MN ? K_DENSE_WGRAD : (B_MN ? K_DENSE_FWD : K_DENSE_DGRAD);
+  griddep_wait(kid);            // operands are produced by the preceding kernels
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -156,12 +157,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  trace_mark(kid, 2);
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(BN) : "memory");
   }
 }
+
+GA3C_TRACE_ATTACH(trace_attach_dense_tc)
 
 // ---- host side ----------------------------------------------------------------------------------
 // 2-D bf16 row-major matrix [rows][cols] (ld elements between rows), box = 64 inner x box_rows, 128-B swizzle,

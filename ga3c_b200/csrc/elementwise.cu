@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) grad_reduce_kernel(GradRed
       if (j < a.seg_end[s]) count = a.seg_count[s];
   }
   griddep_launch();
-  griddep_wait();               // the slabs come from the kernels that precede this one
+  griddep_wait(K_GRAD_REDUCE);  // the slabs come from the kernels that precede this one
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* src = a.part + j;
   for (int i0 = sl; i0 < count; i0 += GR_UNROLL * GR_LANES) {
@@ -49,7 +49,10 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) grad_reduce_kernel(GradRed
       t[0] = acc.x; t[1] = acc.y; t[2] = acc.z; t[3] = acc.w;
     }
   }
+  trace_mark(K_GRAD_REDUCE, 2);
 }
+
+GA3C_TRACE_ATTACH(trace_attach_elementwise)
 
 int launch_grad_reduce(const GradReduceArgs& a, cudaStream_t stream) {
   const int grid = (a.n_floats / 4 + GR_COLS - 1) / GR_COLS;
@@ -64,7 +67,7 @@ int launch_grad_reduce(const GradReduceArgs& a, cudaStream_t stream) {
 template <bool HAS_MOM>
 __global__ void __launch_bounds__(256) rmsprop_kernel(RmsPropArgs a) {
   griddep_launch();
-  griddep_wait();               // the gradients come from the backward kernels that precede this one
+  griddep_wait(K_RMSPROP);      // the gradients come from the backward kernels that precede this one
   const int64_t n4 = a.n_floats >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const float one_m_rho = 1.f - a.decay;
@@ -86,6 +89,7 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(RmsPropArgs a) {
     if (e >= a.w1_offset && e < a.w1_offset + a.w1_count)
       reinterpret_cast<uint2*>(a.w1_shadow)[(e - a.w1_offset) >> 2] = make_uint2(pack_bf16(w.x, w.y), pack_bf16(w.z, w.w));
   }
+  trace_mark(K_RMSPROP, 2);
 }
 
 int launch_rmsprop(const RmsPropArgs& a, cudaStream_t stream) {
@@ -120,7 +124,7 @@ template <bool HAS_MOM>
 __global__ void __launch_bounds__(512) rmsprop_dp_kernel(RmsPropDpArgs d) {
   const RmsPropArgs& a = d.base;
   griddep_launch();
-  griddep_wait();               // the gradients come from the backward kernels that precede this one
+  griddep_wait(K_RMSPROP);      // the gradients come from the backward kernels that precede this one
   uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
   if (blockIdx.x == 0 && threadIdx.x == 0) st_flag(reinterpret_cast<uint64_t*>(my_comm), d.step);   // my gradients are final
   if ((int)threadIdx.x < d.world) {

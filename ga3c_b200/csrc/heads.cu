@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
   b1s[tid] = p.b1[tid];
   griddep_launch();
   __syncthreads();
-  griddep_wait();               // d1_part comes from the dense1 GEMM that precedes this kernel
+  griddep_wait(K_HEADS);               // d1_part comes from the dense1 GEMM that precedes this kernel
 
   float acc[A1] = {};      // thread j: dWp[j][0..A-1], dWv[j]
   float acc_b1 = 0.f;      // thread j: db1[j]
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
     __syncthreads();
   }
 
-  if (!p.train) return;
+  if (!p.train) { trace_mark(K_HEADS, 2); return; }
   const int64_t slab = (int64_t)blockIdx.x * p.gp_stride;
   {
     const int jx = tid;
@@ -202,7 +202,10 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
       for (int w = 0; w < HD_THREADS / 32; ++w) s += loss_s[w][tid];
     p.loss[slab + tid] = s;
   }
+  trace_mark(K_HEADS, 2);
 }
+
+GA3C_TRACE_ATTACH(trace_attach_heads)
 
 template <int A>
 static int launch_heads_t(const HeadsArgs& args, int grid, cudaStream_t stream) {

@@ -5,6 +5,13 @@
 
 namespace ga3c {
 
+// step timeline trace: attach (or detach with nullptr) the [K_COUNT][TRACE_SLOTS] uint64 buffer, one call per kernel file
+int trace_attach_conv_fwd(unsigned long long* buf);
+int trace_attach_conv_bwd(unsigned long long* buf);
+int trace_attach_dense_tc(unsigned long long* buf);
+int trace_attach_heads(unsigned long long* buf);
+int trace_attach_elementwise(unsigned long long* buf);
+
 // one-time per-process function-attribute setup (dynamic smem opt-in); returns cudaError_t as int
 int configure_conv_fwd();
 int configure_conv_bwd();

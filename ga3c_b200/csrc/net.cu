@@ -76,6 +76,7 @@ struct ga3c_net {
   int64_t launches = 0;
   int last_batch = 0;
   // per-kernel CUDA-event timing (ga3c_timing_*): record r uses events 2r (before) and 2r+1 (after)
+  unsigned long long* trace = nullptr;     // [K_COUNT][TRACE_SLOTS] globaltimer stamps (ga3c_trace_*), device memory
   std::vector<cudaEvent_t> tev;
   std::vector<int> tkid;
   int tcursor = 0;
@@ -85,8 +86,6 @@ struct ga3c_net {
 
 constexpr int DP_COMM_BYTES = 256;    // [0] ready step, [8] done step (uint64 at 64-byte spacing)
 
-enum { K_CONV_FWD = 0, K_DENSE_FWD, K_HEADS, K_DENSE_WGRAD, K_DENSE_DGRAD, K_CONV12_BWD, K_CONV11_WGRAD, K_RMSPROP,
-       K_GRAD_REDUCE, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {"conv_fwd", "dense_fwd", "heads", "dense_wgrad", "dense_dgrad",
                                                   "conv12_bwd", "conv11_wgrad", "rmsprop", "grad_reduce"};
 
@@ -106,6 +105,7 @@ static const char* const kKernelNames[K_COUNT] = {"conv_fwd", "dense_fwd", "head
 enum { P_C11W = 0, P_C11B, P_C12W, P_C12B, P_D1W, P_D1B, P_VW, P_VB, P_PW, P_PB, P_COUNT };
 
 static int alloc_workspace(ga3c_net* n, int max_batch);
+static int trace_attach_all(unsigned long long* buf);
 
 extern "C" const char* ga3c_last_error(void) { return g_err.c_str(); }
 extern "C" int ga3c_abi_version(void) { return 1; }
@@ -223,6 +223,7 @@ extern "C" int ga3c_destroy(ga3c_net* n) {
   ga3c_dp_detach(n);
   cudaFree(n->slab);
   cudaFree(n->gpart);
+  if (n->trace) { trace_attach_all(nullptr); cudaFree(n->trace); }
   free_workspace(n);
   for (cudaEvent_t e : n->tev) cudaEventDestroy(e);
   delete n;
@@ -494,6 +495,38 @@ extern "C" const char* ga3c_kernel_name(int kid) { return (kid >= 0 && kid < K_C
 static void timing_free(ga3c_net* n) {
   for (cudaEvent_t e : n->tev) cudaEventDestroy(e);
   n->tev.clear(); n->tkid.clear(); n->tcursor = 0;
+}
+
+// ---- step timeline trace --------------------------------------------------------------------------
+static int trace_attach_all(unsigned long long* buf) {
+  int r;
+  if ((r = trace_attach_conv_fwd(buf)) || (r = trace_attach_conv_bwd(buf)) || (r = trace_attach_dense_tc(buf)) ||
+      (r = trace_attach_heads(buf)) || (r = trace_attach_elementwise(buf)))
+    return r;
+  return 0;
+}
+
+extern "C" int ga3c_trace_begin(ga3c_net* n, void* stream) {
+  if (!n) return fail_msg("ga3c_trace_begin: null handle");
+  CK(cudaSetDevice(n->cfg.device));
+  const size_t words = (size_t)K_COUNT * TRACE_SLOTS;
+  if (!n->trace) CK(cudaMalloc((void**)&n->trace, words * 8));
+  std::vector<unsigned long long> init(words);
+  for (size_t i = 0; i < words; ++i) init[i] = (i & 1) ? 0ull : ~0ull;      // even slots take a min, odd slots a max
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  CK(cudaMemcpy(n->trace, init.data(), words * 8, cudaMemcpyHostToDevice));
+  CKL(trace_attach_all(n->trace));
+  return 0;
+}
+
+extern "C" int ga3c_trace_end(ga3c_net* n, uint64_t* stamps, int32_t n_kernels) {
+  if (!n || !stamps || n_kernels < K_COUNT) return fail_msg("ga3c_trace_end: bad argument");
+  if (!n->trace) return fail_msg("ga3c_trace_end: no trace in progress");
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaDeviceSynchronize());
+  CKL(trace_attach_all(nullptr));
+  CK(cudaMemcpy(stamps, n->trace, (size_t)K_COUNT * TRACE_SLOTS * 8, cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 extern "C" int ga3c_timing_enable(ga3c_net* n, int32_t max_records) {

@@ -401,6 +401,22 @@ class Network:
         _capi.check(self._lib.ga3c_timing_collect(self._h, tot, cnt, n), "ga3c_timing_collect")
         return {self._lib.ga3c_kernel_name(k).decode(): (tot[k], cnt[k]) for k in range(n)}
 
+    def trace_begin(self, stream=None):
+        """Start a step timeline trace (ga3c_trace_begin): kernels stamp %globaltimer at launch / start / end."""
+        st = stream if stream is not None else torch.cuda.current_stream(self._tdev)
+        _capi.check(self._lib.ga3c_trace_begin(self._h, st.cuda_stream), "ga3c_trace_begin")
+
+    def trace_end(self) -> dict:
+        """{kernel name: (first launched, last launched, first started, last started, first ended, last ended)} in
+        microseconds relative to the earliest stamp; kernels that did not run are omitted.  Synchronises."""
+        n = self._lib.ga3c_kernel_count()
+        buf = (C.c_uint64 * (6 * n))()
+        _capi.check(self._lib.ga3c_trace_end(self._h, buf, n), "ga3c_trace_end")
+        rows = {self._lib.ga3c_kernel_name(k).decode(): [buf[6 * k + i] for i in range(6)] for k in range(n)}
+        rows = {k: v for k, v in rows.items() if v[1] != 0}
+        t0 = min(v[0] for v in rows.values()) if rows else 0
+        return {k: tuple((t - t0) / 1e3 for t in v) for k, v in rows.items()}
+
     def workspace(self, which: int) -> np.ndarray:
         """Activation workspace of the last call as float32 numpy (bf16 buffers are widened)."""
         ptr, nbytes = C.c_void_p(), C.c_int64()

@@ -148,6 +148,17 @@ const char* ga3c_kernel_name(int kernel_id);
 int ga3c_timing_enable(ga3c_net* net, int32_t max_records);
 int ga3c_timing_collect(ga3c_net* net, double* total_ms, int64_t* counts, int32_t n_kernels);
 
+/* ---- step timeline trace (profiles/: where the pipelined step spends its time) ----------------
+ * Between ga3c_trace_begin and ga3c_trace_end thread 0 of every CTA of every hot-path kernel stamps
+ * %globaltimer (ns) when it is launched (reaches its dependency wait), started (dependency satisfied)
+ * and ended.  stamps[k*6 + {0,1}] = first/last CTA launched, {2,3} = first/last started, {4,5} =
+ * first/last ended, for kernel id k < ga3c_kernel_count(); kernels that did not run keep
+ * {UINT64_MAX, 0}.  The trace is process-wide (one handle at a time).  Unlike the event timing above it
+ * does not serialise the programmatic-dependent-launch chain.  ga3c_trace_begin synchronises `stream`;
+ * ga3c_trace_end synchronises the device. */
+int ga3c_trace_begin(ga3c_net* net, void* stream);
+int ga3c_trace_end(ga3c_net* net, uint64_t* stamps, int32_t n_kernels);
+
 #ifdef __cplusplus
 }
 #endif
