@@ -83,6 +83,8 @@ def kernel_work(name, b, train):
         return "hbm", (148 + 1) * 14_500 * 4
     if name in ("dense_fwd", "dense_wgrad", "dense_dgrad"):
         return "tensor", 2.0 * b * n2 * fc
+    if name == "dense_bwd":       # dgrad + wgrad tiles in one grid (dgrad alone in dp_mode='nccl')
+        return "tensor", 4.0 * b * n2 * fc
     raise KeyError(name)
 
 

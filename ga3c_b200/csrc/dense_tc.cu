@@ -13,6 +13,9 @@
 //   warp 1   TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma.cta_group::1.kind::f16)
 //   warp 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global
 // K is consumed in blocks of 64 (one 128-byte swizzle row); a k-block is 4 MMAs of K = 16.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tcgen05.cuh"
@@ -64,9 +67,8 @@ struct EpiReluMaskBf16Tc {  // dn2 = acc where n2 > 0 else 0, bf16
 };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int M, int N,
-               int k_blocks, int k_blocks_per_split, Epi epi) {
+__device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tm_a, const CUtensorMap& tm_b, int M, int N, int k_blocks,
+                                             int k_blocks_per_split, const Epi& epi, int bx, int by, int bz) {
   constexpr int B_STAGE = BN * TC_BK * 2;
   constexpr int STAGE = TC_A_STAGE + B_STAGE;
   extern __shared__ uint8_t smem_raw[];
@@ -75,7 +77,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const uint32_t bars = sbase + STAGES * STAGE;            // full[STAGES], empty[STAGES], tmem_full : 8 B each
   const uint32_t tmem_slot = bars + (2 * STAGES + 1) * 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN, split = blockIdx.z;
+  const int m0 = bx * TC_BM, n0 = by * BN, split = bz;
   const int kb0 = split * k_blocks_per_split;
   const int kb1 = min(kb0 + k_blocks_per_split, k_blocks);
 
@@ -165,6 +167,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   }
 }
 
+template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int M, int N,
+               int k_blocks, int k_blocks_per_split, Epi epi) {
+  gemm_tc_body<BN, STAGES, A_MN, B_MN, Epi>(tm_a, tm_b, M, N, k_blocks, k_blocks_per_split, epi, blockIdx.x, blockIdx.y,
+                                            blockIdx.z);
+}
+
+// dense1 backward in ONE launch: both GEMMs only need dd1, so their tiles share a grid.  Blocks [0, n_dg) are the
+// data-gradient tiles (first: conv12_bwd waits for dn2), the rest the weight-gradient tiles (needed at the step's end).
+constexpr int DG_BN = 128, DG_ST = 2;       // dgrad: M = B,   N = 3872, K = 256
+constexpr int WG_BN = 64, WG_ST = 4;        // wgrad: M = 3872, N = 256, K = B
+constexpr int WGM_ST = 3;                   // wgrad inside the merged launch: 3 stages -> 3 CTAs per SM, one wave
+struct DenseBwdArgs {
+  int batch, dg_mtiles, n_dg, wg_mtiles, wg_kblocks;
+  EpiReluMaskBf16Tc epi_dg;
+  EpiPartialF32 epi_wg;
+};
+__global__ void __launch_bounds__(TC_THREADS, 3)     // <= 96 registers: 18 warps fit the four 16K register files
+dense_bwd_kernel(const __grid_constant__ CUtensorMap dg_a, const __grid_constant__ CUtensorMap dg_b,
+                 const __grid_constant__ CUtensorMap wg_a, const __grid_constant__ CUtensorMap wg_b, const DenseBwdArgs p) {
+  const int b = blockIdx.x;
+  if (b < p.n_dg) {
+    gemm_tc_body<DG_BN, DG_ST, false, false, EpiReluMaskBf16Tc>(dg_a, dg_b, p.batch, (int)FLAT, FC / TC_BK, FC / TC_BK,
+                                                                p.epi_dg, b % p.dg_mtiles, b / p.dg_mtiles, 0);
+  } else {
+    const int t = b - p.n_dg;
+    gemm_tc_body<WG_BN, WGM_ST, true, true, EpiPartialF32>(wg_a, wg_b, (int)FLAT, (int)FC, p.wg_kblocks, p.wg_kblocks,
+                                                           p.epi_wg, t % p.wg_mtiles, t / p.wg_mtiles, 0);
+  }
+}
+
 GA3C_TRACE_ATTACH(trace_attach_dense_tc)
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -204,8 +238,7 @@ template <int BN, int STAGES>
 constexpr int tc_smem() { return STAGES * (TC_A_STAGE + BN * TC_BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024; }
 
 constexpr int FWD_BN = 128, FWD_ST = 4;     // fwd : M = B,    N = 256,  K = 3872  (split-K)
-constexpr int DG_BN = 128, DG_ST = 2;       // dgrad: M = B,   N = 3872, K = 256
-constexpr int WG_BN = 64, WG_ST = 4;        // wgrad: M = 3872, N = 256, K = B
+constexpr int DBW_SMEM = tc_smem<DG_BN, DG_ST>() > tc_smem<WG_BN, WGM_ST>() ? tc_smem<DG_BN, DG_ST>() : tc_smem<WG_BN, WGM_ST>();
 
 using FwdKernel = decltype(&gemm_tc_kernel<FWD_BN, FWD_ST, false, true, EpiPartialF32>);
 
@@ -219,6 +252,29 @@ int configure_dense_tc() {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(gemm_tc_kernel<WG_BN, WG_ST, true, true, EpiPartialF32>,
                            cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem<WG_BN, WG_ST>());
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DBW_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  // 3 CTAs per SM (all dgrad + wgrad tiles in one wave) need the full shared-memory carveout
+  e = cudaFuncSetAttribute(dense_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return (int)e;
+  if (getenv("GA3C_DEBUG_OCC")) {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dense_bwd_kernel, TC_THREADS, DBW_SMEM);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, dense_bwd_kernel);
+    int smem_sm = 0, regs_sm = 0, dev = 0, resv = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&resv, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+    fprintf(stderr, "[ga3c] dense_bwd_kernel: %d CTAs/SM at %d B dynamic smem; regs %d static smem %zu maxdyn %d carveout %d; SM smem %d regs %d reserved/block %d\n",
+            nb, DBW_SMEM, fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.preferredShmemCarveout, smem_sm, regs_sm, resv);
+    for (int sm = 16384; sm <= 114688; sm += 16384) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dense_bwd_kernel, TC_THREADS, sm);
+      fprintf(stderr, "[ga3c]   dyn smem %d -> %d CTAs/SM\n", sm, nb);
+    }
+  }
   return (int)e;
 }
 
@@ -264,6 +320,25 @@ int launch_dense_wgrad_tc(const uint16_t* n2, const uint16_t* dd1, float* g_w1, 
   return launch_pdl(gemm_tc_kernel<WG_BN, WG_ST, true, true, EpiPartialF32>, grid, dim3(TC_THREADS),
                     tc_smem<WG_BN, WG_ST>(), stream, ta, tb, (int)FLAT, (int)FC, kblocks, kblocks,
                     EpiPartialF32{g_w1, FC, 0});
+}
+
+int launch_dense_bwd_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint16_t* dn2, float* g_w1, int batch,
+                        cudaStream_t stream) {
+  CUtensorMap da, db, wa, wb;
+  if (make_tmap(&da, dd1, batch, FC, FC, TC_BM)) return (int)cudaErrorInvalidValue;           // dgrad A: [B][256], K inner
+  if (make_tmap(&db, w1bf, FLAT, FC, FC, DG_BN)) return (int)cudaErrorInvalidValue;           // dgrad B: [3872][256] = [N][K]
+  if (make_tmap(&wa, n2, batch, FLAT, FLAT, 64)) return (int)cudaErrorInvalidValue;           // wgrad A: [K=B][M=3872], M inner
+  if (make_tmap(&wb, dd1, batch, FC, FC, 64)) return (int)cudaErrorInvalidValue;              // wgrad B: [K=B][N=256],  N inner
+  DenseBwdArgs p{};
+  p.batch = batch;
+  p.dg_mtiles = (batch + TC_BM - 1) / TC_BM;
+  p.n_dg = p.dg_mtiles * ((FLAT + DG_BN - 1) / DG_BN);
+  p.wg_mtiles = (FLAT + TC_BM - 1) / TC_BM;
+  p.wg_kblocks = (batch + TC_BK - 1) / TC_BK;
+  p.epi_dg = EpiReluMaskBf16Tc{dn2, n2, FLAT};
+  p.epi_wg = EpiPartialF32{g_w1, FC, 0};
+  const int grid = p.n_dg + p.wg_mtiles * (FC / WG_BN);
+  return launch_pdl(dense_bwd_kernel, dim3(grid), dim3(TC_THREADS), DBW_SMEM, stream, da, db, wa, wb, p);
 }
 
 }  // namespace ga3c

@@ -65,23 +65,28 @@ int launch_grad_reduce(const GradReduceArgs& a, cudaStream_t stream) {
 // of TF's 10 ApplyRMSProp launches).  With mu == 0 (Config.RMSPROP_MOMENTUM) the mom slot is dead:
 // 20 B/param of traffic (read w,g,ms; write w,ms) + 2 B/param for the bf16 shadow of dense1/w.
 template <bool HAS_MOM>
+__device__ __forceinline__ void rms_update(const RmsPropArgs& a, const float4& g, float4& w, float4& ms, float4& mo) {
+  const float one_m_rho = 1.f - a.decay;
+#define GA3C_RMS(c)                                                          \
+  ms.c = a.decay * ms.c + one_m_rho * g.c * g.c;                             \
+  mo.c = a.momentum * mo.c + a.lr * g.c / sqrtf(ms.c + a.eps);              \
+  w.c -= mo.c;
+  GA3C_RMS(x) GA3C_RMS(y) GA3C_RMS(z) GA3C_RMS(w)
+#undef GA3C_RMS
+}
+
+template <bool HAS_MOM>
 __global__ void __launch_bounds__(256) rmsprop_kernel(RmsPropArgs a) {
   griddep_launch();
   griddep_wait(K_RMSPROP);      // the gradients come from the backward kernels that precede this one
   const int64_t n4 = a.n_floats >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const float one_m_rho = 1.f - a.decay;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 g = reinterpret_cast<const float4*>(a.g)[i];
     float4 w = reinterpret_cast<float4*>(a.w)[i];
     float4 ms = reinterpret_cast<float4*>(a.ms)[i];
     float4 mo = HAS_MOM ? reinterpret_cast<float4*>(a.mom)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-#define GA3C_RMS(c)                                                          \
-  ms.c = a.decay * ms.c + one_m_rho * g.c * g.c;                             \
-  mo.c = a.momentum * mo.c + a.lr * g.c / sqrtf(ms.c + a.eps);              \
-  w.c -= mo.c;
-    GA3C_RMS(x) GA3C_RMS(y) GA3C_RMS(z) GA3C_RMS(w)
-#undef GA3C_RMS
+    rms_update<HAS_MOM>(a, g, w, ms, mo);
     reinterpret_cast<float4*>(a.w)[i] = w;
     reinterpret_cast<float4*>(a.ms)[i] = ms;
     if (HAS_MOM) reinterpret_cast<float4*>(a.mom)[i] = mo;
@@ -97,6 +102,113 @@ int launch_rmsprop(const RmsPropArgs& a, cudaStream_t stream) {
   const int grid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
   if (a.momentum != 0.f) return launch_pdl(rmsprop_kernel<true>, dim3(grid), dim3(256), 0, stream, a);
   return launch_pdl(rmsprop_kernel<false>, dim3(grid), dim3(256), 0, stream, a);
+}
+
+// ---- single-GPU step tail: grad_reduce + RMSProp in one launch -------------------------------------------
+// Blocks [0, n_red) sum the gradient-partial slabs of 32 float4 columns exactly like grad_reduce_kernel (same order,
+// same bits), store the reduced gradient and apply RMSProp to those columns; the remaining blocks update dense1/w,
+// one float4 per thread.  w / ms (and mom) do not depend on the preceding kernels, so they are loaded BEFORE the
+// dependency wait and their latency hides under the tail of the backward.
+template <bool HAS_MOM>
+__global__ void __launch_bounds__(GR_LANES * GR_COLS) rmsprop_reduce_kernel(RmsPropArgs a, GradReduceArgs r, int n_red) {
+  __shared__ float4 part[GR_LANES][GR_COLS];
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  if ((int)blockIdx.x < n_red) {
+    const int col = threadIdx.x & (GR_COLS - 1), sl = threadIdx.x / GR_COLS;
+    const int j = (blockIdx.x * GR_COLS + col) * 4;
+    int count = 0;
+    if (j < r.n_floats) {
+#pragma unroll
+      for (int s = GR_MAX_SEG - 1; s >= 0; --s)
+        if (j < r.seg_end[s]) count = r.seg_count[s];
+    }
+    const bool owner = sl == 0 && j < r.out_floats;
+    float4 w = zero, ms = zero, mo = zero;
+    if (owner) {
+      w = *reinterpret_cast<const float4*>(a.w + j);
+      ms = *reinterpret_cast<const float4*>(a.ms + j);
+      if (HAS_MOM) mo = *reinterpret_cast<const float4*>(a.mom + j);
+    }
+    griddep_launch();
+    griddep_wait(K_RMSPROP);      // the slabs come from the kernels that precede this one
+    float4 acc = zero;
+    const float* src = r.part + j;
+    for (int i0 = sl; i0 < count; i0 += GR_UNROLL * GR_LANES) {
+      float4 q[GR_UNROLL];
+#pragma unroll
+      for (int u = 0; u < GR_UNROLL; ++u) {
+        const int i = i0 + u * GR_LANES;
+        q[u] = i < count ? __ldcg(reinterpret_cast<const float4*>(src + (int64_t)i * r.stride)) : zero;
+      }
+#pragma unroll
+      for (int u = 0; u < GR_UNROLL; ++u) { acc.x += q[u].x; acc.y += q[u].y; acc.z += q[u].z; acc.w += q[u].w; }
+    }
+    part[sl][col] = acc;
+    __syncthreads();
+    if (sl == 0 && j < r.n_floats) {
+#pragma unroll
+      for (int l = 1; l < GR_LANES; ++l) {
+        const float4 q = part[l][col];
+        acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+      }
+      if (owner) {
+        *reinterpret_cast<float4*>(r.out + j) = acc;                 // the reduced gradient (introspection, checkpoints)
+        rms_update<HAS_MOM>(a, acc, w, ms, mo);
+        *reinterpret_cast<float4*>(a.w + j) = w;
+        *reinterpret_cast<float4*>(a.ms + j) = ms;
+        if (HAS_MOM) *reinterpret_cast<float4*>(a.mom + j) = mo;
+      } else if (r.out_tail != nullptr) {
+        float* t = r.out_tail + (j - r.out_floats);
+        t[0] = acc.x; t[1] = acc.y; t[2] = acc.z; t[3] = acc.w;
+      }
+    }
+  } else {
+    // two float4 per thread, a block apart (coalesced): the whole grid is resident in one wave
+    const int64_t i0 = (r.out_floats >> 2) + (int64_t)(blockIdx.x - n_red) * (2 * blockDim.x) + threadIdx.x;
+    const int64_t n4 = a.n_floats >> 2;
+    float4 w[2], ms[2], mo[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * blockDim.x;
+      w[u] = ms[u] = mo[u] = zero;
+      if (i < n4) {
+        w[u] = reinterpret_cast<const float4*>(a.w)[i];
+        ms[u] = reinterpret_cast<const float4*>(a.ms)[i];
+        if (HAS_MOM) mo[u] = reinterpret_cast<const float4*>(a.mom)[i];
+      }
+    }
+    griddep_launch();
+    griddep_wait(K_RMSPROP);      // dense1/w's gradient comes from the wgrad GEMM
+    float4 g[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * blockDim.x;
+      g[u] = i < n4 ? reinterpret_cast<const float4*>(a.g)[i] : zero;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * blockDim.x;
+      if (i < n4) {
+        rms_update<HAS_MOM>(a, g[u], w[u], ms[u], mo[u]);
+        reinterpret_cast<float4*>(a.w)[i] = w[u];
+        reinterpret_cast<float4*>(a.ms)[i] = ms[u];
+        if (HAS_MOM) reinterpret_cast<float4*>(a.mom)[i] = mo[u];
+        const int64_t e = i << 2;
+        if (e >= a.w1_offset && e < a.w1_offset + a.w1_count)
+          reinterpret_cast<uint2*>(a.w1_shadow)[(e - a.w1_offset) >> 2] = make_uint2(pack_bf16(w[u].x, w[u].y), pack_bf16(w[u].z, w[u].w));
+      }
+    }
+  }
+  trace_mark(K_RMSPROP, 2);
+}
+
+int launch_rmsprop_reduce(const RmsPropArgs& a, const GradReduceArgs& r, cudaStream_t stream) {
+  constexpr int T = GR_LANES * GR_COLS;
+  const int n_red = (r.n_floats / 4 + GR_COLS - 1) / GR_COLS;
+  const int64_t rest4 = (a.n_floats - r.out_floats) >> 2;
+  const int grid = n_red + (int)((rest4 + 2 * T - 1) / (2 * T));
+  if (a.momentum != 0.f) return launch_pdl(rmsprop_reduce_kernel<true>, dim3(grid), dim3(T), 0, stream, a, r, n_red);
+  return launch_pdl(rmsprop_reduce_kernel<false>, dim3(grid), dim3(T), 0, stream, a, r, n_red);
 }
 
 // ---- data-parallel RMSProp over peer memory ---------------------------------------------------------

@@ -28,6 +28,9 @@ int launch_dense_fwd_tc(const uint16_t* n2, const uint16_t* w1bf, float* d1_part
 int launch_dense_dgrad_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint16_t* dn2, int batch,
                           cudaStream_t stream);
 int launch_dense_wgrad_tc(const uint16_t* n2, const uint16_t* dd1, float* g_w1, int batch, cudaStream_t stream);
+// dgrad + wgrad tiles in one grid (both only need dd1): the single-GPU / fused-DP step uses this one
+int launch_dense_bwd_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint16_t* dn2, float* g_w1, int batch,
+                        cudaStream_t stream);
 
 // heads.cu -- value / policy heads, softmax, A3C loss and its backward (NetworkVP_discrate.py:60-85)
 struct HeadsArgs {
@@ -86,6 +89,8 @@ struct RmsPropArgs {
   float lr, decay, momentum, eps;
 };
 int launch_rmsprop(const RmsPropArgs& a, cudaStream_t stream);
+// grad_reduce + RMSProp in one launch (single-GPU step; r.out must be a.g, r.out_floats the small-tensor prefix)
+int launch_rmsprop_reduce(const RmsPropArgs& a, const GradReduceArgs& r, cudaStream_t stream);
 // data-parallel RMSProp over peer memory: rank r owns arena slice r; it sums that slice of every rank's gradient
 // arena (fixed rank order), applies RMSProp, and stores the new weights (+ bf16 shadow) into every rank's slab.
 constexpr int DP_MAX_WORLD = 8;

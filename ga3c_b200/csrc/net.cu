@@ -86,7 +86,7 @@ struct ga3c_net {
 
 constexpr int DP_COMM_BYTES = 256;    // [0] ready step, [8] done step (uint64 at 64-byte spacing)
 
-static const char* const kKernelNames[K_COUNT] = {"conv_fwd", "dense_fwd", "heads", "dense_wgrad", "dense_dgrad",
+static const char* const kKernelNames[K_COUNT] = {"conv_fwd", "dense_fwd", "heads", "dense_wgrad", "dense_bwd",
                                                   "conv12_bwd", "conv11_wgrad", "rmsprop", "grad_reduce"};
 
 // launch one kernel of the path; when timing is enabled bracket it with events on the same stream
@@ -323,8 +323,8 @@ extern "C" int ga3c_predict(ga3c_net* n, const float* x, int32_t batch, float* p
 // forward, fused loss forward/backward, and the dense1 weight gradient: on return (in stream order) the
 // gradients of dense1/w, dense1/b, logits_v/*, logits_p/* are final, so their allreduce can start while
 // ga3c_fb_tail computes the conv gradients.
-extern "C" int ga3c_fb_head(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch, float beta,
-                            float* loss, void* stream) {
+static int fb_head_impl(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch, float beta,
+                        float* loss, void* stream, bool with_wgrad) {
   if (int r = check_batch(n, batch, "ga3c_fb_head")) return r;
   if (!x || !yr || !a) return fail_msg("ga3c_fb_head: null buffer");
   CK(cudaSetDevice(n->cfg.device));
@@ -343,13 +343,30 @@ extern "C" int ga3c_fb_head(ga3c_net* n, const float* x, const float* yr, const 
   n->gp_heads_grid = heads_grid(batch, n->num_sms);
   n->loss_out = loss;
   LAUNCH(n, K_HEADS, st, launch_heads(h, n->num_sms, st));
-  LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad_tc(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
+  if (with_wgrad) LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad_tc(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
   n->last_batch = batch;
   return 0;
 }
 
-// dense1 data gradient and the two conv backward kernels: completes conv11/* and conv12/* gradients.
-extern "C" int ga3c_fb_tail(ga3c_net* n, const float* x, int32_t batch, void* stream) {
+extern "C" int ga3c_fb_head(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch, float beta,
+                            float* loss, void* stream) {
+  return fb_head_impl(n, x, yr, a, batch, beta, loss, stream, true);
+}
+
+// sum of the per-CTA slabs: conv tensors (the first four of the arena) over the conv grids, head tensors and the loss
+// sums over the heads grid
+static GradReduceArgs reduce_args(ga3c_net* n, int batch) {
+  GradReduceArgs r{};
+  r.part = n->gpart; r.stride = n->gp_stride; r.out = n->g; r.out_tail = n->loss_out;
+  r.out_floats = (int)n->small_floats; r.n_floats = (int)n->small_floats + 4;
+  for (int s = 0; s < GR_MAX_SEG; ++s) { r.seg_end[s] = r.n_floats; r.seg_count[s] = n->gp_heads_grid; }
+  r.seg_end[0] = (int)n->off(P_D1B); r.seg_count[0] = conv_bwd_grid(batch, n->num_sms);
+  return r;
+}
+
+// dense1 data gradient and the two conv backward kernels; with `reduce` the slabs are summed into the gradient arena
+// (conv11/*, conv12/*, dense1/b, heads, loss sums), otherwise the caller does it (fused with RMSProp).
+static int fb_tail_impl(ga3c_net* n, const float* x, int32_t batch, void* stream, bool with_wgrad, bool reduce) {
   if (int r = check_batch(n, batch, "ga3c_fb_tail")) return r;
   if (!x) return fail_msg("ga3c_fb_tail: null buffer");
   if (batch != n->last_batch) return fail_msg("ga3c_fb_tail: batch differs from the preceding ga3c_fb_head");
@@ -357,36 +374,40 @@ extern "C" int ga3c_fb_tail(ga3c_net* n, const float* x, int32_t batch, void* st
   cudaStream_t st = (cudaStream_t)stream;
   const float* w = n->w;
   float* gp = n->gpart;
-  LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
+  if (with_wgrad)   // dgrad + wgrad tiles of dense1 in one grid
+    LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_bwd_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, n->g + n->off(P_D1W), batch, st));
+  else
+    LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
   LAUNCH(n, K_CONV12_BWD, st, launch_conv12_bwd(n->n1, n->dn2, w + n->off(P_C12W), n->dn1, gp + n->off(P_C12W),
                                                 gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, st));
   LAUNCH(n, K_CONV11_WGRAD, st, launch_conv11_wgrad(x, n->dn1, gp + n->off(P_C11W), gp + n->off(P_C11B), n->gp_stride,
                                                     batch, n->num_sms, st));
-  // sum the per-CTA slabs: conv tensors (the first four of the arena) over the conv grids, head tensors and the
-  // loss sums over the heads grid
-  GradReduceArgs r{};
-  r.part = gp; r.stride = n->gp_stride; r.out = n->g; r.out_tail = n->loss_out;
-  r.out_floats = (int)n->small_floats; r.n_floats = (int)n->small_floats + 4;
-  const int conv_end = (int)n->off(P_D1B);
-  for (int s = 0; s < GR_MAX_SEG; ++s) { r.seg_end[s] = r.n_floats; r.seg_count[s] = n->gp_heads_grid; }
-  r.seg_end[0] = conv_end; r.seg_count[0] = conv_bwd_grid(batch, n->num_sms);
-  LAUNCH(n, K_GRAD_REDUCE, st, launch_grad_reduce(r, st));
+  if (reduce) LAUNCH(n, K_GRAD_REDUCE, st, launch_grad_reduce(reduce_args(n, batch), st));
   return 0;
+}
+
+extern "C" int ga3c_fb_tail(ga3c_net* n, const float* x, int32_t batch, void* stream) {
+  return fb_tail_impl(n, x, batch, stream, false, true);
 }
 
 extern "C" int ga3c_forward_backward(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch,
                                      float beta, float* loss, void* stream) {
-  if (int r = ga3c_fb_head(n, x, yr, a, batch, beta, loss, stream)) return r;
-  return ga3c_fb_tail(n, x, batch, stream);
+  if (int r = fb_head_impl(n, x, yr, a, batch, beta, loss, stream, false)) return r;
+  return fb_tail_impl(n, x, batch, stream, true, true);
+}
+
+static RmsPropArgs rmsprop_args(ga3c_net* n, float lr) {
+  RmsPropArgs a{};
+  a.w = n->w; a.ms = n->ms; a.mom = n->mom; a.g = n->g; a.w1_shadow = n->w1_shadow;
+  a.n_floats = n->arena_floats; a.w1_offset = n->off(P_D1W); a.w1_count = (int64_t)FLAT * FC;
+  a.lr = lr; a.decay = n->cfg.rmsprop_decay; a.momentum = n->cfg.rmsprop_momentum; a.eps = n->cfg.rmsprop_epsilon;
+  return a;
 }
 
 extern "C" int ga3c_apply_rmsprop(ga3c_net* n, float lr, void* stream) {
   if (!n) return fail_msg("ga3c_apply_rmsprop: null handle");
   CK(cudaSetDevice(n->cfg.device));
-  RmsPropArgs a{};
-  a.w = n->w; a.ms = n->ms; a.mom = n->mom; a.g = n->g; a.w1_shadow = n->w1_shadow;
-  a.n_floats = n->arena_floats; a.w1_offset = n->off(P_D1W); a.w1_count = (int64_t)FLAT * FC;
-  a.lr = lr; a.decay = n->cfg.rmsprop_decay; a.momentum = n->cfg.rmsprop_momentum; a.eps = n->cfg.rmsprop_epsilon;
+  RmsPropArgs a = rmsprop_args(n, lr);
   if (n->dp_world > 1) {
     // fused reduce-scatter(grads) -> RMSProp on this rank's slice -> all-gather(weights) over peer memory
     RmsPropDpArgs d{};
@@ -449,8 +470,16 @@ extern "C" int ga3c_dp_attach(ga3c_net* n, int32_t rank, int32_t world, const vo
 
 extern "C" int ga3c_train_step(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch, float lr,
                                float beta, float* loss, void* stream) {
-  if (int r = ga3c_forward_backward(n, x, yr, a, batch, beta, loss, stream)) return r;
-  return ga3c_apply_rmsprop(n, lr, stream);
+  if (n && n->dp_world > 1) {     // peers read this rank's gradient arena: it must hold the reduced gradients
+    if (int r = ga3c_forward_backward(n, x, yr, a, batch, beta, loss, stream)) return r;
+    return ga3c_apply_rmsprop(n, lr, stream);
+  }
+  // single GPU: the slab reduction rides in the optimizer launch
+  if (int r = fb_head_impl(n, x, yr, a, batch, beta, loss, stream, false)) return r;
+  if (int r = fb_tail_impl(n, x, batch, stream, true, false)) return r;
+  LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_reduce(rmsprop_args(n, lr), reduce_args(n, batch), (cudaStream_t)stream));
+  n->global_step += 1;   // opt.minimize(..., global_step=self.global_step), NetworkVP_discrate.py:130
+  return 0;
 }
 
 extern "C" int ga3c_returns(const double* rewards, const int64_t* seg, int32_t n_segments, const double* terminal,

@@ -199,8 +199,11 @@ class Network:
         st = stream or torch.cuda.current_stream(self._tdev)
         loss_ptr = loss_out.data_ptr() if loss_out is not None else None
         if not self._dp:
-            _capi.check(self._lib.ga3c_forward_backward(self._h, x_dev.data_ptr(), yr_dev.data_ptr(), a_dev.data_ptr(), b,
-                                                        float(self.beta), loss_ptr, st.cuda_stream), "ga3c_forward_backward")
+            # single GPU: one call; the gradient-slab reduction is fused into the RMSProp launch
+            _capi.check(self._lib.ga3c_train_step(self._h, x_dev.data_ptr(), yr_dev.data_ptr(), a_dev.data_ptr(), b,
+                                                  float(self.learning_rate), float(self.beta), loss_ptr, st.cuda_stream),
+                        "ga3c_train_step")
+            return
         else:
             # dense1/w (98.8 % of the arena) is final after the head: its allreduce overlaps the conv backward
             _capi.check(self._lib.ga3c_fb_head(self._h, x_dev.data_ptr(), yr_dev.data_ptr(), a_dev.data_ptr(), b,
