@@ -71,8 +71,10 @@ def kernel_work(name, b, train):
         return "hbm", b * (x + (n1 * 2 if train else 0) + n2 * 2)
     if name == "conv11_wgrad":
         return "hbm", b * (x + n1 * 2)
-    if name == "conv12_bwd":
+    if name == "conv12_bwd":      # split predecessor (GA3C_SPLIT_CONV_BWD)
         return "hbm", b * (n1 * 2 + n2 * 2 + n1 * 2)
+    if name == "conv_bwd":        # fused conv12 dgrad + conv12 wgrad + conv11 wgrad: x, n1, dn2 read once, dn1 stays on chip
+        return "hbm", b * (x + n1 * 2 + n2 * 2)
     if name == "heads":
         return "hbm", b * (fc * 4 + (fc * 2 + 4 + NUM_ACTIONS * 4 if train else (NUM_ACTIONS + 1) * 4))
     if name == "rmsprop":

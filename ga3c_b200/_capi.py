@@ -46,6 +46,7 @@ SIGNATURES = {
                                C.c_double, C.c_void_p, C.c_void_p]),
     "ga3c_select_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ga3c_workspace_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "ga3c_keep_dn1": (C.c_int, [C.c_void_p, C.c_int32]),
     "ga3c_launch_count": (C.c_int64, [C.c_void_p]),
     "ga3c_kernel_count": (C.c_int, []),
     "ga3c_kernel_name": (C.c_char_p, [C.c_int]),

@@ -15,7 +15,8 @@ constexpr int CH_ROWS = 12, CF_NCHUNK = IMG / CH_ROWS, CH_BYTES = CH_ROWS * IMG 
 constexpr int CF_NSLOT = 4;
 static_assert(CF_NCHUNK * CH_ROWS == IMG && CH_BYTES % 16 == 0, "chunks must tile the frame");
 // block matrix: 22 x 22 blocks (+ slack rows read by the dead part of the last M tile); chunk arrays padded so that
-// neighbouring k-chunks start 16 banks apart
+// neighbouring k-chunks start 16 banks apart.  548 rows cover conv_fwd's four 128-row tiles; kernels that read fewer rows
+// pass their own plane stride (LBO) to the helpers below.
 constexpr int BLK_W = 22, BLK_ROWS = 548, BLK_LBO = BLK_ROWS * 16, BLK_BYTES = 8 * BLK_LBO;              // 8,768 / 70,144
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -27,17 +28,18 @@ __device__ __forceinline__ uint64_t make_desc_ns(uint32_t saddr, uint32_t lbo, u
 }
 
 // per-lane part of a pixel's destination in Blk: padded pixel px = x + 2 -> block column X = px >> 2, dx = px & 3
+template <int LBO = BLK_LBO>
 __device__ __forceinline__ void blk_lane_offsets(int lane, uint32_t (&lane_off)[3]) {
 #pragma unroll
   for (int it = 0; it < 3; ++it) {
     const int px = lane + 32 * it + 2;
-    lane_off[it] = ((px >> 1) & 1) * BLK_LBO + (px >> 2) * 16 + (px & 1) * 8;
+    lane_off[it] = ((px >> 1) & 1) * LBO + (px >> 2) * 16 + (px & 1) * 8;
   }
 }
 
 // one 12-row fp32 chunk (staging slot `src`) -> bf16 -> Blk; warp w of AUX_WARPS converts rows w, w + AUX_WARPS, ...
 // All 16-byte loads are issued before the first conversion so their latencies overlap.
-template <int AUX_WARPS>
+template <int AUX_WARPS, int LBO = BLK_LBO>
 __device__ __forceinline__ void blk_convert_chunk(uint32_t src, uint32_t blk, int c, int warp, int lane,
                                                   const uint32_t (&lane_off)[3]) {
   constexpr int RPW = CH_ROWS / AUX_WARPS;
@@ -51,7 +53,7 @@ __device__ __forceinline__ void blk_convert_chunk(uint32_t src, uint32_t blk, in
 #pragma unroll
   for (int rr = 0; rr < RPW; ++rr) {
     const int py = c * CH_ROWS + warp + rr * AUX_WARPS + 2;        // padded row -> block row Y = py >> 2, dy = py & 3
-    const uint32_t row_off = blk + (py & 3) * (2 * BLK_LBO) + (py >> 2) * (BLK_W * 16);
+    const uint32_t row_off = blk + (py & 3) * (2 * LBO) + (py >> 2) * (BLK_W * 16);
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
       if (lane + 32 * it < IMG) {

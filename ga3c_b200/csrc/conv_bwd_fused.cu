@@ -1,0 +1,413 @@
+// Backward of both convolutions in ONE persistent, warp-specialised kernel on the 5th-generation tensor cores
+// (the autodiff half of opt.minimize, NetworkVP_discrate.py:130, for the layers at NetworkVP.py:212-228 wired as
+// NetworkDNav.py:81-82):
+//     dn1  = conv12 data-gradient of dn2, masked by relu'(n1)          (never leaves the SM)
+//     g_w12 = patches(n1)^T dn2 , g_b12 = colsum(dn2)
+//     g_w11 = patches(x)^T dn1  , g_b11 = colsum(dn1)                  (conv11 has no data-gradient: x is the input)
+// bf16 operands, fp32 accumulation in TMEM.  Per frame the kernel reads x (112,896 B fp32), n1 (14,112 B) and dn2
+// (7,744 B) from HBM exactly once and writes nothing; the weight-gradient accumulators stay in TMEM for all frames of
+// the CTA and are stored once into the CTA's slab of the gradient-partial workspace (grad_reduce / rmsprop_reduce add
+// the slabs in a fixed order).
+//
+// All three products are GEMMs over space-to-depth "block matrices" kept in the no-swizzle UMMA layout with every row
+// contiguous (16-byte chunk j of row r at j*LBO + r*16), so that a spatial shift is a different descriptor start address:
+//   G    dn2 on a zero-bordered 13x13 grid, row (oy+1)*13 + (ox+1), K = 32 co in 4 chunk planes
+//   Blk2 n1, SAME-padded (1 before, 2 after) to 24x24 and cut into 12x12 blocks of 2x2 pixels, row Yb*13 + Xb (column 12
+//        dead), 64 elements (dy, dx, ci) in 8 chunk planes
+//   Blk  x, zero-padded to 88x88 and cut into 22x22 blocks of 4x4 pixels (conv_blk.cuh)
+// conv12 data gradient.  Output pixel (2Yh+py, 2Xh+px) of the padded image gets taps kh = py + 2a, kw = px + 2b from
+//   dn2[Yh - a, Xh - b].  With m = Yh*13 + Xh:   D[m, (py, px, ci)] = sum_{a,b} G[m + 14 - 13a - b, :] . Wd_ab
+//   where Wd_ab[co, (py, px, ci)] = w12[py + 2a, px + 2b, ci, co]: four row-shifted GEMMs, M = 156 (two 128-row tiles, the
+//   second one starting at row 28), N = 64, K = 32 each -> 16 UMMAs.  Row m of D is the whole 2x2 block (Yh, Xh) of dn1.
+// conv12 weight gradient.  kh = 2a + dy, kw = 2b + dx: quadrant (a, b) is  dW_ab[(dy, dx, ci), co] = sum_m Blk2[m + 13a + b]^T
+//   G[m + 14]  over positions m = oy*13 + ox (dead columns hit the zero border of G): A = Blk2 read MN-major, B = G read
+//   MN-major, M = 64, N = 32, K = 144 -> 4 x 9 UMMAs.
+// conv11 weight gradient.  As before (4 quadrants, M = 64, N = 16, K = 464 positions m = oy*22 + ox): A = Blk read MN-major
+//   at row m + 22a + b, B = dn1 staged MN-major -- now written by the data-gradient epilogue instead of loaded from HBM.
+//
+//   warps 0-5    fp32 chunk of x (TMA ring) -> bf16 -> Blk
+//   warp  6      one thread issues every UMMA: conv12 of frame k+1 between the conv11 position groups of frame k
+//   warp  7      one thread streams n1 / dn2 of the next frame into a raw staging buffer (cp.async.bulk)
+//   warps 8-11   data-gradient epilogue: TMEM -> relu' mask (n1 from Blk2) -> bf16 -> dn1 operand, bias gradient of conv11;
+//                final store of the TMEM weight-gradient accumulators
+//   warps 12-15  raw staging -> G / Blk2 layouts, bias gradient of conv12
+#include "common.cuh"
+#include "kernels.h"
+#include "tcgen05.cuh"
+#include "conv_blk.cuh"
+
+namespace ga3c {
+
+constexpr int FB_THREADS = 512, FB_AUX_WARPS = 6, FB_AUX_THREADS = 32 * FB_AUX_WARPS, FB_ISSUE_WARP = 6, FB_TMA_WARP = 7,
+              FB_EPI_WARP0 = 8, FB_RE_WARP0 = 12;
+static_assert(FB_EPI_WARP0 % 4 == 0, "epilogue warp e must own TMEM lane quarter e");
+constexpr int FBLK_ROWS = 492, FBLK_LBO = FBLK_ROWS * 16, FBLK_BYTES = 8 * FBLK_LBO;     // rows read: <= 16*28 + 23 + 15 = 486
+constexpr int W11_KSTEPS = 29;                                   // 464 >= 462 positions (21 rows x 22, column 21 dead)
+constexpr int DN1_ROWS = 16 * W11_KSTEPS, DN1_PLANE = DN1_ROWS * 16, DN1_BUF = 2 * DN1_PLANE;   // 2 planes of 8 channels
+constexpr int G_W = 13, G_ROWS = 176, G_LBO = G_ROWS * 16, G_BYTES = 4 * G_LBO;          // rows read: <= 28 + 127 + 14 = 169
+constexpr int B2_ROWS = 160, B2_LBO = B2_ROWS * 16, B2_BYTES = 8 * B2_LBO;               // rows read: <= 143 + 14 = 157
+constexpr int DG_TILE1 = 28;                                     // first row of the second data-gradient tile
+constexpr int DG_ROWS = 12 * G_W;                                // 156 rows of D (12 x 12 blocks + dead column)
+constexpr int W12_KSTEPS = 9;                                    // 144 >= 11 rows x 13 positions
+constexpr int RAW_DN2 = N2_POS * C2_OUT * 2, RAW_N1 = N1_POS * C1_OUT * 2, RAW_BYTES = RAW_DN2 + RAW_N1;   // 7,744 + 14,112
+constexpr int W12D_BYTES = 4 * 4 * 64 * 16;                      // 4 taps x [4 k-chunks (8 co)][64 rows (py, px, ci)][16 B]
+
+constexpr int FB_OFF_BLK = 0;
+constexpr int FB_OFF_RING = FB_OFF_BLK + FBLK_BYTES;             //  62,976
+constexpr int FB_OFF_DN1 = FB_OFF_RING + CF_NSLOT * CH_BYTES;    // 127,488 (two buffers)
+constexpr int FB_OFF_G = FB_OFF_DN1 + 2 * DN1_BUF;               // 157,184
+constexpr int FB_OFF_B2 = FB_OFF_G + G_BYTES;                    // 168,448
+constexpr int FB_OFF_W12D = FB_OFF_B2 + B2_BYTES;                // 188,928
+constexpr int FB_OFF_RAW = FB_OFF_W12D + W12D_BYTES;             // 205,312
+constexpr int FB_OFF_RED = FB_OFF_RAW + RAW_BYTES;               // 227,168: [4][16] conv11 + [4][32] conv12 bias partials
+constexpr int FB_OFF_BAR = FB_OFF_RED + (4 * C1_OUT + 4 * C2_OUT) * 4;
+constexpr int FB_RING = 0;        // [4] TMA chunk of x landed
+constexpr int FB_BLKRDY = 4;      // [4] Blk rows of conv11 position group i converted              (aux -> issuer)
+constexpr int FB_GRP = 8;         // [4] conv11 UMMAs of group i retired (tcgen05.commit)           (-> aux: Blk rows free)
+constexpr int FB_DN1RDY = 12;     // [2] dn1 operand buffer written, 4 arrivals                     (epilogue -> issuer)
+constexpr int FB_DN1FREE = 14;    // [2] every conv11 UMMA reading the buffer retired               (-> epilogue)
+constexpr int FB_RAWFULL = 16;    //     n1 / dn2 of a frame landed in the raw buffer               (TMA -> re-layout)
+constexpr int FB_RAWFREE = 17;    //     raw buffer consumed                                        (re-layout -> TMA thread)
+constexpr int FB_C12RDY = 18;     //     G / Blk2 hold the frame                                    (re-layout -> issuer)
+constexpr int FB_MMA12 = 19;      //     conv12 UMMAs of the frame retired (tcgen05.commit)         (-> epilogue)
+constexpr int FB_EPI12 = 20;      //     D drained and Blk2 mask reads done, 4 arrivals             (epilogue -> issuer, re-layout)
+constexpr int FB_DONE = 21;       //     every UMMA of the kernel retired                           (-> final store)
+constexpr int FB_NBAR = 22;
+constexpr int FB_OFF_TSLOT = FB_OFF_BAR + FB_NBAR * 8;
+constexpr int FB_SMEM = FB_OFF_TSLOT + 16 + 128;                 // incl. slack to align the base to 128 B
+static_assert(FB_SMEM <= 232448, "shared memory budget of one CTA per SM");
+constexpr int FB_TMEM_COLS = 512, TM_W11 = 0, TM_W12 = 64, TM_D12 = 192;   // 4x16 | 4x32 | 2x64 columns
+
+__global__ void __launch_bounds__(FB_THREADS, 1)
+conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, const uint16_t* __restrict__ dn2,
+                const float* __restrict__ w12, uint16_t* __restrict__ dn1_out, float* __restrict__ g_w11,
+                float* __restrict__ g_b11, float* __restrict__ g_w12, float* __restrict__ g_b12, int64_t gp_stride, int batch) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* const smem = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t blk = sbase + FB_OFF_BLK, ring = sbase + FB_OFF_RING, dn1s = sbase + FB_OFF_DN1, gg = sbase + FB_OFF_G,
+                 b2 = sbase + FB_OFF_B2, w12d = sbase + FB_OFF_W12D, raw = sbase + FB_OFF_RAW, bars = sbase + FB_OFF_BAR,
+                 tslot = sbase + FB_OFF_TSLOT;
+  float* red = reinterpret_cast<float*>(smem + FB_OFF_RED);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stride = gridDim.x;
+  const int n_frames = ((int)blockIdx.x < batch) ? (batch - 1 - (int)blockIdx.x) / stride + 1 : 0;
+  const int n_chunks = n_frames * CF_NCHUNK;
+  auto frame_of = [&](int k) { return (size_t)(blockIdx.x + k * stride); };
+  auto bar = [&](int i) { return bars + i * 8; };
+  auto issue_chunk = [&](int q) {                                  // one thread
+    const int k = q / CF_NCHUNK, c = q - k * CF_NCHUNK, slot = q % CF_NSLOT;
+    mbar_expect_tx(bar(FB_RING + slot), CH_BYTES);
+    bulk_load(ring + slot * CH_BYTES, reinterpret_cast<const uint8_t*>(x + frame_of(k) * STATE_DIM) + c * CH_BYTES, CH_BYTES,
+              bar(FB_RING + slot));
+  };
+
+  // ---------------- prologue ----------------
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar(FB_RING + i), 1);
+      mbar_init(bar(FB_BLKRDY + i), 1);
+      mbar_init(bar(FB_GRP + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(FB_DN1RDY + i), 4);
+      mbar_init(bar(FB_DN1FREE + i), 1);
+    }
+    mbar_init(bar(FB_RAWFULL), 1);
+    mbar_init(bar(FB_RAWFREE), 1);
+    mbar_init(bar(FB_C12RDY), 1);
+    mbar_init(bar(FB_MMA12), 1);
+    mbar_init(bar(FB_EPI12), 4);
+    mbar_init(bar(FB_DONE), 1);
+    fence_mbar_init();
+  }
+  if (warp == FB_EPI_WARP0) tmem_alloc<FB_TMEM_COLS>(tslot);
+  __syncthreads();
+  if (tid == 0)                                                    // x is an input of the step: stream it before the dependency wait
+    for (int q = 0; q < CF_NSLOT && q < n_chunks; ++q) issue_chunk(q);
+  // zero once: image borders / slack rows of Blk, dead rows of both dn1 buffers, borders of G and Blk2
+  for (int i = tid; i < FBLK_BYTES / 16; i += FB_THREADS) sts128(blk + i * 16, make_uint4(0, 0, 0, 0));
+  for (int i = tid; i < (FB_OFF_W12D - FB_OFF_DN1) / 16; i += FB_THREADS) sts128(dn1s + i * 16, make_uint4(0, 0, 0, 0));
+  griddep_launch();
+  griddep_wait(K_CONV12_BWD);   // dn2 comes from the dense1 data-gradient GEMM that precedes this kernel
+  // data-gradient weights as the UMMA B operand (K-major, no swizzle): tap (a, b), k-chunk j (8 co), row n = (py, px, ci)
+  for (int i = tid; i < 4 * 4 * 64; i += FB_THREADS) {
+    const int tap = i >> 8, j = (i >> 6) & 3, n = i & 63, a = tap >> 1, b = tap & 1, py = n >> 5, px = (n >> 4) & 1, ci = n & 15;
+    const float* w = w12 + (((py + 2 * a) * 4 + px + 2 * b) * C1_OUT + ci) * C2_OUT + 8 * j;
+    sts128(w12d + tap * 4096 + j * 1024 + n * 16,
+           make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7])));
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tslot));
+
+  if (warp < FB_AUX_WARPS) {
+    // =========================== aux: fp32 chunk -> bf16 block matrix, slot re-arm ===========================
+    uint32_t lane_off[3];
+    blk_lane_offsets<FBLK_LBO>(lane, lane_off);
+    for (int k = 0; k < n_frames; ++k) {
+#pragma unroll 1
+      for (int c = 0; c < CF_NCHUNK; ++c) {
+        const int q = k * CF_NCHUNK + c, slot = q % CF_NSLOT;
+        // block rows 3c..3c+3 are rewritten: the last position group of frame k-1 that reads them must have retired
+        if (k > 0) mbar_wait(bar(FB_GRP + (c + 1) / 2), (k - 1) & 1);
+        mbar_wait(bar(FB_RING + slot), (q / CF_NSLOT) & 1);
+        blk_convert_chunk<FB_AUX_WARPS, FBLK_LBO>(ring + slot * CH_BYTES, blk, c, warp, lane, lane_off);
+        fence_proxy_async();
+        named_bar_sync(1, FB_AUX_THREADS);
+        if (tid == 0) {
+          if (q + CF_NSLOT < n_chunks) issue_chunk(q + CF_NSLOT);
+          // position group i (m in [128 i, 128 i + 128)) reads block rows up to (128 i + 150) / 22
+          if (c == 2) mbar_arrive(bar(FB_BLKRDY + 0));
+          if (c == 4) mbar_arrive(bar(FB_BLKRDY + 1));
+          if (c == 6) { mbar_arrive(bar(FB_BLKRDY + 2)); mbar_arrive(bar(FB_BLKRDY + 3)); }
+        }
+      }
+    }
+  } else if (warp == FB_ISSUE_WARP) {
+    // =========================== MMA issuer ===========================
+    // warp-uniform: all 32 lanes run the loops and wait on the barriers, elect_one() issues
+    constexpr uint32_t idesc_dg = make_idesc_m(128, 64, false, false), idesc_w12 = make_idesc_m(64, C2_OUT, true, true),
+                       idesc_w11 = make_idesc_m(64, C1_OUT, true, true);
+    // descriptor low words of row 0 / k-chunk 0 of every operand; a shift of r rows is + r, a k-chunk plane is + LBO/16
+    const uint32_t g_k = desc_ns_lo(gg, G_LBO), wd_k = desc_ns_lo(w12d, 1024);                 // K-major: LBO = plane, SBO = 128
+    const uint32_t g_mn = desc_ns_lo(gg, 128), b2_mn = desc_ns_lo(b2, 128), blk_mn = desc_ns_lo(blk, 128),
+                   dn1_mn = desc_ns_lo(dn1s, 128);                                             // MN-major: LBO = 128, SBO = plane
+    constexpr uint32_t hi_k = desc_ns_hi(128), hi_g = desc_ns_hi(G_LBO), hi_b2 = desc_ns_hi(B2_LBO), hi_blk = desc_ns_hi(FBLK_LBO),
+                       hi_dn1 = desc_ns_hi(DN1_PLANE);
+    auto conv12_mmas = [&](int k) {
+      mbar_wait(bar(FB_C12RDY), k & 1);                            // G / Blk2 hold frame k
+      if (k > 0) mbar_wait(bar(FB_EPI12), (k - 1) & 1);            // D of frame k-1 has been drained
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int tap = 0; tap < 4; ++tap)
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+              tc_mma_bf16_w(tmem_base + TM_D12 + 64 * t,
+                            g_k + ((t ? DG_TILE1 : 0) + G_W + 1 - G_W * (tap >> 1) - (tap & 1)) + 2 * kk * (G_LBO / 16), hi_k,
+                            wd_k + (tap * 4096 + 2 * kk * 1024) / 16, hi_k, idesc_dg, (tap | kk) ? 1u : 0u);
+        const uint32_t acc = k ? 1u : 0u;
+#pragma unroll
+        for (int s = 0; s < W12_KSTEPS; ++s)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            // A: Blk2 rows 16 s + 13 a + b .., B: G rows 16 s + 14 ..; both MN-major
+            tc_mma_bf16_w(tmem_base + TM_W12 + 32 * q, b2_mn + 16 * s + G_W * (q >> 1) + (q & 1), hi_b2, g_mn + 16 * s + G_W + 1, hi_g,
+                          idesc_w12, s ? 1u : acc);
+        tc_commit(bar(FB_MMA12));
+      }
+      __syncwarp();
+    };
+    if (n_frames > 0) conv12_mmas(0);
+    for (int k = 0; k < n_frames; ++k) {
+      const uint32_t dbuf = dn1_mn + (k & 1) * (DN1_BUF / 16);
+      mbar_wait(bar(FB_DN1RDY + (k & 1)), (k >> 1) & 1);
+#pragma unroll
+      for (int gi = 0; gi < 4; ++gi) {
+        if (gi == 1 && k + 1 < n_frames) conv12_mmas(k + 1);       // one frame ahead of the conv11 gradient
+        mbar_wait(bar(FB_BLKRDY + gi), k & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t acc = k ? 1u : 0u;
+#pragma unroll
+          for (int s = 8 * gi; s < (gi == 3 ? W11_KSTEPS : 8 * gi + 8); ++s)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              // A: Blk rows 16 s + 22 a + b .., B: dn1 rows 16 s ..; both MN-major
+              tc_mma_bf16_w(tmem_base + TM_W11 + 16 * q, blk_mn + 16 * s + BLK_W * (q >> 1) + (q & 1), hi_blk, dbuf + 16 * s, hi_dn1,
+                            idesc_w11, s ? 1u : acc);
+          tc_commit(bar(FB_GRP + gi));
+          if (gi == 3) tc_commit(bar(FB_DN1FREE + (k & 1)));
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) tc_commit(bar(FB_DONE));
+    __syncwarp();
+  } else if (warp == FB_TMA_WARP) {
+    // =========================== n1 / dn2 of the next frame -> raw staging buffer ===========================
+    if (lane == 0) {
+      for (int k = 0; k < n_frames; ++k) {
+        if (k > 0) mbar_wait(bar(FB_RAWFREE), (k - 1) & 1);
+        mbar_expect_tx(bar(FB_RAWFULL), RAW_BYTES);
+        bulk_load(raw, dn2 + frame_of(k) * FLAT, RAW_DN2, bar(FB_RAWFULL));
+        bulk_load(raw + RAW_DN2, n1 + frame_of(k) * (N1_POS * C1_OUT), RAW_N1, bar(FB_RAWFULL));
+      }
+    }
+  } else if (warp >= FB_RE_WARP0) {
+    // =========================== raw -> G / Blk2, conv12 bias gradient ===========================
+    const int rtid = tid - 32 * FB_RE_WARP0;
+    float bacc = 0.f;                                              // db12 partial: channel rtid & 31, position phase rtid >> 5
+    for (int k = 0; k < n_frames; ++k) {
+      mbar_wait(bar(FB_RAWFULL), k & 1);
+      if (k > 0) mbar_wait(bar(FB_EPI12), (k - 1) & 1);            // conv12 UMMAs and mask reads of frame k-1 are done
+      for (int i = rtid; i < N2_POS * 4; i += 128) {               // dn2: 4 chunks of 8 co per position
+        const int pos = i >> 2, j = i & 3, oy = pos / H2, ox = pos - oy * H2;
+        uint32_t r[4];
+        lds128(r, raw + i * 16);
+        sts128(gg + j * G_LBO + ((oy + 1) * G_W + ox + 1) * 16, make_uint4(r[0], r[1], r[2], r[3]));
+      }
+      for (int i = rtid; i < N1_POS * 2; i += 128) {               // n1: 2 chunks of 8 ci per pixel
+        const int p = i >> 1, h = i & 1, y = p / H1, Y = y + 1, X = p - y * H1 + 1;
+        uint32_t r[4];
+        lds128(r, raw + RAW_DN2 + i * 16);
+        sts128(b2 + ((((Y & 1) * 2 + (X & 1)) * 2 + h) * B2_LBO) + ((Y >> 1) * G_W + (X >> 1)) * 16, make_uint4(r[0], r[1], r[2], r[3]));
+      }
+      {
+        const int co = rtid & 31;
+        for (int pos = rtid >> 5; pos < N2_POS; pos += 4) {
+          uint16_t v;
+          asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(raw + pos * 64 + co * 2));
+          bacc += __uint_as_float((uint32_t)v << 16);
+        }
+      }
+      fence_proxy_async();
+      named_bar_sync(3, 128);
+      if (rtid == 0) {
+        mbar_arrive(bar(FB_C12RDY));
+        mbar_arrive(bar(FB_RAWFREE));
+      }
+    }
+    red[4 * C1_OUT + rtid] = bacc;
+    named_bar_sync(3, 128);
+    if (rtid < C2_OUT)
+      g_b12[(int64_t)blockIdx.x * gp_stride + rtid] =
+          red[4 * C1_OUT + rtid] + red[4 * C1_OUT + 32 + rtid] + red[4 * C1_OUT + 64 + rtid] + red[4 * C1_OUT + 96 + rtid];
+  } else {
+    // =========================== data-gradient epilogue; final store ===========================
+    const int ew = warp - FB_EPI_WARP0;                            // TMEM lane quarter
+    const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16);
+    float bacc[C1_OUT];                                            // db11 partials of this thread's pixels
+#pragma unroll
+    for (int c = 0; c < C1_OUT; ++c) bacc[c] = 0.f;
+    for (int k = 0; k < n_frames; ++k) {
+      mbar_wait(bar(FB_MMA12), k & 1);
+      if (k >= 2) mbar_wait(bar(FB_DN1FREE + (k & 1)), ((k >> 1) - 1) & 1);   // conv11 UMMAs of frame k-2 (same buffer) retired
+      tc_fence_after();
+      const uint32_t dbuf = dn1s + (k & 1) * DN1_BUF;
+      uint16_t* dn1_dst = dn1_out ? dn1_out + frame_of(k) * (N1_POS * C1_OUT) : nullptr;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        if (t == 1 && ew != 3) break;                              // rows 128..155 are lanes 100..127 of the second tile
+        const int m = (t ? DG_TILE1 : 0) + 32 * ew + lane;
+        const int Yh = m / G_W, Xh = m - Yh * G_W;
+        const bool row_ok = (t == 0 || m >= 128) && m < DG_ROWS && Xh < 12;
+#pragma unroll
+        for (int cls = 0; cls < 4; ++cls) {
+          uint32_t r[16];
+          tc_ld16(tlane + TM_D12 + 64 * t + 16 * cls, r);
+          const int y = 2 * Yh + (cls >> 1) - 1, xx = 2 * Xh + (cls & 1) - 1;
+          if (row_ok && y >= 0 && y < H1 && xx >= 0 && xx < H1) {
+            uint32_t mk[8];                                        // n1 of this pixel: relu'(n1) = (n1 > 0); post-ReLU values are >= 0
+            lds128(*reinterpret_cast<uint32_t(*)[4]>(&mk[0]), b2 + (2 * cls) * B2_LBO + m * 16);
+            lds128(*reinterpret_cast<uint32_t(*)[4]>(&mk[4]), b2 + (2 * cls + 1) * B2_LBO + m * 16);
+            uint32_t o[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const float lo = (mk[jj] & 0x7FFFu) ? __uint_as_float(r[2 * jj]) : 0.f;
+              const float hi = (mk[jj] & 0x7FFF0000u) ? __uint_as_float(r[2 * jj + 1]) : 0.f;
+              o[jj] = pack_bf16(lo, hi);
+              bacc[2 * jj] += bf16_lo(o[jj]);
+              bacc[2 * jj + 1] += bf16_hi(o[jj]);
+            }
+            const uint4 lo4 = make_uint4(o[0], o[1], o[2], o[3]), hi4 = make_uint4(o[4], o[5], o[6], o[7]);
+            const int p22 = y * BLK_W + xx;
+            sts128(dbuf + p22 * 16, lo4);
+            sts128(dbuf + DN1_PLANE + p22 * 16, hi4);
+            if (dn1_dst) {
+              uint4* d = reinterpret_cast<uint4*>(dn1_dst + (y * H1 + xx) * C1_OUT);
+              d[0] = lo4;
+              d[1] = hi4;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();                                         // the dn1 operand is read by the tensor core
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(FB_EPI12));
+        mbar_arrive(bar(FB_DN1RDY + (k & 1)));
+      }
+    }
+    // conv11 bias gradient: warp-reduce the 16 channel sums, then add the four warps in order
+#pragma unroll
+    for (int c = 0; c < C1_OUT; ++c) {
+      float v = bacc[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[ew * C1_OUT + c] = v;
+    }
+    named_bar_sync(2, 128);
+    const int etid = tid - 32 * FB_EPI_WARP0;
+    if (etid < C1_OUT)
+      g_b11[(int64_t)blockIdx.x * gp_stride + etid] = red[etid] + red[C1_OUT + etid] + red[2 * C1_OUT + etid] + red[3 * C1_OUT + etid];
+    // weight-gradient accumulators: M = 64 rows sit on TMEM lanes 32 w + (0..15) (rows 16 w ..); row = chunk plane * 8 + e
+    if (n_frames > 0) {
+      mbar_wait(bar(FB_DONE), 0);
+      tc_fence_after();
+      float* const s11 = g_w11 + (int64_t)blockIdx.x * gp_stride;
+      float* const s12 = g_w12 + (int64_t)blockIdx.x * gp_stride;
+      const int row = 16 * ew + lane, j = row >> 3, e = row & 7;
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        uint32_t r[16];
+        tc_ld16(tlane + TM_W11 + 16 * q, r);
+        if (lane < 16) {
+          // conv11 block element: j = dy*2 + (dx>>1), e = (dx&1)*4 + c
+          const int kh = 4 * (q >> 1) + (j >> 1), kw = 4 * (q & 1) + (j & 1) * 2 + (e >> 2), c = e & 3;
+          float4* o = reinterpret_cast<float4*>(s11 + ((kh * 8 + kw) * 4 + c) * C1_OUT);
+#pragma unroll
+          for (int n = 0; n < C1_OUT / 4; ++n)
+            o[n] = make_float4(__uint_as_float(r[4 * n]), __uint_as_float(r[4 * n + 1]), __uint_as_float(r[4 * n + 2]),
+                               __uint_as_float(r[4 * n + 3]));
+        }
+      }
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q)
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t r[16];
+          tc_ld16(tlane + TM_W12 + 32 * q + 16 * hh, r);
+          if (lane < 16) {
+            // conv12 block element: j = (dy*2 + dx)*2 + (ci>>3), e = ci & 7
+            const int kh = 2 * (q >> 1) + (j >> 2), kw = 2 * (q & 1) + ((j >> 1) & 1), ci = (j & 1) * 8 + e;
+            float4* o = reinterpret_cast<float4*>(s12 + ((kh * 4 + kw) * C1_OUT + ci) * C2_OUT + 16 * hh);
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+              o[n] = make_float4(__uint_as_float(r[4 * n]), __uint_as_float(r[4 * n + 1]), __uint_as_float(r[4 * n + 2]),
+                                 __uint_as_float(r[4 * n + 3]));
+          }
+        }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  trace_mark(K_CONV12_BWD, 2);
+  if (warp == FB_EPI_WARP0) {
+    tc_fence_after();
+    tmem_dealloc<FB_TMEM_COLS>(tmem_base);
+  }
+}
+
+GA3C_TRACE_ATTACH(trace_attach_conv_bwd_fused)
+
+int configure_conv_bwd_fused() {
+  return (int)cudaFuncSetAttribute(conv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+}
+
+int launch_conv_bwd(const float* x, const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1_out,
+                    float* g_w11, float* g_b11, float* g_w12, float* g_b12, int64_t gp_stride, int batch, int num_sms,
+                    cudaStream_t stream) {
+  return launch_pdl(conv_bwd_kernel, dim3(conv_bwd_grid(batch, num_sms)), dim3(FB_THREADS), FB_SMEM, stream, x, n1, dn2, w12,
+                    dn1_out, g_w11, g_b11, g_w12, g_b12, gp_stride, batch);
+}
+
+}  // namespace ga3c

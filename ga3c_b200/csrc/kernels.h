@@ -8,6 +8,7 @@ namespace ga3c {
 // step timeline trace: attach (or detach with nullptr) the [K_COUNT][TRACE_SLOTS] uint64 buffer, one call per kernel file
 int trace_attach_conv_fwd(unsigned long long* buf);
 int trace_attach_conv_bwd(unsigned long long* buf);
+int trace_attach_conv_bwd_fused(unsigned long long* buf);
 int trace_attach_dense_tc(unsigned long long* buf);
 int trace_attach_heads(unsigned long long* buf);
 int trace_attach_elementwise(unsigned long long* buf);
@@ -15,6 +16,7 @@ int trace_attach_elementwise(unsigned long long* buf);
 // one-time per-process function-attribute setup (dynamic smem opt-in); returns cudaError_t as int
 int configure_conv_fwd();
 int configure_conv_bwd();
+int configure_conv_bwd_fused();
 int configure_dense_tc();
 
 // conv_fwd.cu -- x fp32 [B,28224] -> n1 bf16 [B,441,16] (optional), n2 bf16 [B,3872]
@@ -65,6 +67,11 @@ int launch_conv12_bwd(const uint16_t* n1, const uint16_t* dn2, const float* w12,
 //   conv11 wgrad: g_w11 = patches(x)^T dn1 ; g_b11 = colsum(dn1)
 int launch_conv11_wgrad(const float* x, const uint16_t* dn1, float* g_w11, float* g_b11, int64_t gp_stride, int batch,
                         int num_sms, cudaStream_t stream);
+
+// conv_bwd_fused.cu -- both of the above in one kernel on tcgen05; dn1 stays on chip (dn1_out: optional copy for tests)
+int launch_conv_bwd(const float* x, const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1_out,
+                    float* g_w11, float* g_b11, float* g_w12, float* g_b12, int64_t gp_stride, int batch, int num_sms,
+                    cudaStream_t stream);
 
 // elementwise.cu
 // out[j] = sum over slabs i < count(j) of part[i * stride + j], j in [0, n_floats): the per-CTA gradient partials of

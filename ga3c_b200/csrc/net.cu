@@ -72,6 +72,7 @@ struct ga3c_net {
   int64_t gp_stride = 0;
   int gp_heads_grid = 0;           // slabs the heads kernel of the current step wrote
   float* loss_out = nullptr;       // caller's loss buffer of the current step (may be null)
+  bool keep_dn1 = false;           // tests: also store dn1 (which otherwise never leaves the SM) to the workspace
   int64_t global_step = 0;
   int64_t launches = 0;
   int last_batch = 0;
@@ -87,7 +88,7 @@ struct ga3c_net {
 constexpr int DP_COMM_BYTES = 256;    // [0] ready step, [8] done step (uint64 at 64-byte spacing)
 
 static const char* const kKernelNames[K_COUNT] = {"conv_fwd", "dense_fwd", "heads", "dense_wgrad", "dense_bwd",
-                                                  "conv12_bwd", "conv11_wgrad", "rmsprop", "grad_reduce"};
+                                                  "conv_bwd", "conv11_wgrad", "rmsprop", "grad_reduce"};
 
 // launch one kernel of the path; when timing is enabled bracket it with events on the same stream
 #define LAUNCH(net, kid, st, call)                                                        \
@@ -180,7 +181,7 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
     cudaMemcpy(n->ms, ones.data(), ab, cudaMemcpyHostToDevice);
   }
   int r;
-  if ((r = configure_conv_fwd()) || (r = configure_conv_bwd()) || (r = configure_dense_tc())) {
+  if ((r = configure_conv_fwd()) || (r = configure_conv_bwd()) || (r = configure_conv_bwd_fused()) || (r = configure_dense_tc())) {
     ga3c_destroy(n);
     return fail("cudaFuncSetAttribute", (cudaError_t)r);
   }
@@ -378,10 +379,16 @@ static int fb_tail_impl(ga3c_net* n, const float* x, int32_t batch, void* stream
     LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_bwd_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, n->g + n->off(P_D1W), batch, st));
   else
     LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
-  LAUNCH(n, K_CONV12_BWD, st, launch_conv12_bwd(n->n1, n->dn2, w + n->off(P_C12W), n->dn1, gp + n->off(P_C12W),
+  if (getenv("GA3C_SPLIT_CONV_BWD")) {      // the two-kernel predecessor (mma.sync conv12, dn1 through HBM), kept for A/B runs
+    LAUNCH(n, K_CONV12_BWD, st, launch_conv12_bwd(n->n1, n->dn2, w + n->off(P_C12W), n->dn1, gp + n->off(P_C12W),
+                                                  gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, st));
+    LAUNCH(n, K_CONV11_WGRAD, st, launch_conv11_wgrad(x, n->dn1, gp + n->off(P_C11W), gp + n->off(P_C11B), n->gp_stride,
+                                                      batch, n->num_sms, st));
+  } else {
+    LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(x, n->n1, n->dn2, w + n->off(P_C12W), n->keep_dn1 ? n->dn1 : nullptr,
+                                                gp + n->off(P_C11W), gp + n->off(P_C11B), gp + n->off(P_C12W),
                                                 gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, st));
-  LAUNCH(n, K_CONV11_WGRAD, st, launch_conv11_wgrad(x, n->dn1, gp + n->off(P_C11W), gp + n->off(P_C11B), n->gp_stride,
-                                                    batch, n->num_sms, st));
+  }
   if (reduce) LAUNCH(n, K_GRAD_REDUCE, st, launch_grad_reduce(reduce_args(n, batch), st));
   return 0;
 }
@@ -516,6 +523,12 @@ extern "C" int ga3c_workspace_ptr(ga3c_net* n, int which, void** ptr, int64_t* b
   return 0;
 }
 
+extern "C" int ga3c_keep_dn1(ga3c_net* n, int32_t on) {
+  if (!n) return fail_msg("ga3c_keep_dn1: null handle");
+  n->keep_dn1 = on != 0;
+  return 0;
+}
+
 extern "C" int64_t ga3c_launch_count(const ga3c_net* n) { return n ? n->launches : 0; }
 
 extern "C" int ga3c_kernel_count(void) { return K_COUNT; }
@@ -529,7 +542,7 @@ static void timing_free(ga3c_net* n) {
 // ---- step timeline trace --------------------------------------------------------------------------
 static int trace_attach_all(unsigned long long* buf) {
   int r;
-  if ((r = trace_attach_conv_fwd(buf)) || (r = trace_attach_conv_bwd(buf)) || (r = trace_attach_dense_tc(buf)) ||
+  if ((r = trace_attach_conv_fwd(buf)) || (r = trace_attach_conv_bwd(buf)) || (r = trace_attach_conv_bwd_fused(buf)) || (r = trace_attach_dense_tc(buf)) ||
       (r = trace_attach_heads(buf)) || (r = trace_attach_elementwise(buf)))
     return r;
   return 0;

@@ -420,6 +420,10 @@ class Network:
         t0 = min(v[0] for v in rows.values()) if rows else 0
         return {k: tuple((t - t0) / 1e3 for t in v) for k, v in rows.items()}
 
+    def keep_dn1(self, on: bool):
+        """Tests: make the fused conv backward also store dn1 (normally shared-memory only) to the workspace."""
+        _capi.check(self._lib.ga3c_keep_dn1(self._h, int(bool(on))), "ga3c_keep_dn1")
+
     def workspace(self, which: int) -> np.ndarray:
         """Activation workspace of the last call as float32 numpy (bf16 buffers are widened)."""
         ptr, nbytes = C.c_void_p(), C.c_int64()

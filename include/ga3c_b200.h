@@ -133,6 +133,9 @@ int ga3c_select_actions(const float* p_dev, const double* u_dev, int32_t batch, 
  * which: 0 n1 [B,441,16] bf16, 1 n2 [B,3872] bf16, 2 d1 [B,256] fp32, 3 dd1 [B,256] bf16,
  *        4 dn2 [B,3872] bf16, 5 dn1 [B,441,16] bf16 */
 int ga3c_workspace_ptr(ga3c_net* net, int which, void** ptr_dev, int64_t* bytes);
+/* dn1 (the conv12 data gradient) normally never leaves the SM: the fused conv backward kernel consumes it from shared
+ * memory.  on != 0 makes that kernel also store it to the workspace (id 5 above) so that tests can compare it. */
+int ga3c_keep_dn1(ga3c_net* net, int32_t on);
 /* number of kernels this library has launched on this handle since creation */
 int64_t ga3c_launch_count(const ga3c_net* net);
 

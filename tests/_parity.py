@@ -36,7 +36,9 @@ def layer_report(net, params, x, y_r, a, *, beta=0.01, log_eps=1e-6, min_policy=
                                                   min_policy=min_policy, quant="bf16", keep=True)
     rep["p"] = err(p, f["p"])
     rep["v"] = err(v, f["v"])
+    net.keep_dn1(True)          # dn1 is consumed on chip by the fused conv backward; ask for a copy
     losses = net.losses(x, y_r, a)
+    net.keep_dn1(False)
     b = x.shape[0]
     rep["n1"] = err(net.workspace(0), f["n1"].reshape(b, -1))
     rep["n2"] = err(net.workspace(1), f["n2"].reshape(b, -1))
