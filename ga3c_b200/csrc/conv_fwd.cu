@@ -182,26 +182,31 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
     }
   } else if (warp == CF_ISSUE_WARP) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc11 = make_idesc(2 * C1_OUT, false, false), idesc12 = make_idesc(C2_OUT, false, false);
-      for (int k = 0; k < n_frames; ++k) {
-        for (int i = 0; i < C11_TILES; ++i) {
-          mbar_wait(bar(BAR_BLKRDY + i), k & 1);                     // the Blk rows this tile reads hold frame k
-          if (k > 0) mbar_wait(bar(BAR_T1FREE + i), (k - 1) & 1);    // its accumulator of frame k-1 has been drained
-          tc_fence_after();
+    // warp-uniform: all 32 lanes run the loops and wait on the barriers, elect_one() issues (tcgen05.cuh)
+    constexpr uint32_t idesc11 = make_idesc(2 * C1_OUT, false, false), idesc12 = make_idesc(C2_OUT, false, false);
+    const uint32_t blk_k = desc_ns_lo(blk, BLK_LBO), wq_k = desc_ns_lo(wq, 512);     // K-major, no swizzle: LBO = k-chunk plane, SBO = 128
+    constexpr uint32_t hi_k = desc_ns_hi(128);
+    for (int k = 0; k < n_frames; ++k) {
 #pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            const uint32_t arow = blk + (C11_TSTRIDE * i + BLK_W * a) * 16;
+      for (int i = 0; i < C11_TILES; ++i) {
+        mbar_wait(bar(BAR_BLKRDY + i), k & 1);                       // the Blk rows this tile reads hold frame k
+        if (k > 0) mbar_wait(bar(BAR_T1FREE + i), (k - 1) & 1);      // its accumulator of frame k-1 has been drained
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              tc_mma_bf16(tmem_base + 32 * i, make_desc_ns(arow + 2 * kk * BLK_LBO, BLK_LBO, 128),
-                          make_desc_ns(wq + a * 4096 + 2 * kk * 512, 512, 128), idesc11, (a | kk) ? 1u : 0u);
-          }
+              tc_mma_bf16_w(tmem_base + 32 * i, blk_k + C11_TSTRIDE * i + BLK_W * a + 2 * kk * (BLK_LBO / 16), hi_k,
+                            wq_k + (a * 4096 + 2 * kk * 512) / 16, hi_k, idesc11, (a | kk) ? 1u : 0u);
           tc_commit(bar(BAR_C11 + i));
         }
-        mbar_wait(bar(BAR_A2RDY), k & 1);                            // every conv11 output of frame k sits in the im2col operand
-        if (k > 0) mbar_wait(bar(BAR_T2FREE), (k - 1) & 1);
-        tc_fence_after();
+        __syncwarp();
+      }
+      mbar_wait(bar(BAR_A2RDY), k & 1);                              // every conv11 output of frame k sits in the im2col operand
+      if (k > 0) mbar_wait(bar(BAR_T2FREE), (k - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           const uint64_t da = make_desc(sa2 + kb * 16384, false), db = make_desc(sb2 + kb * 4096, false);
@@ -211,6 +216,7 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
         }
         tc_commit(bar(BAR_MMA2));
       }
+      __syncwarp();
     }
   } else if (warp >= CF_EPI_WARP0) {
     // =========================== epilogues ===========================

@@ -101,11 +101,13 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tm_a, const CUte
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // producer and issuer run warp-uniform (all lanes loop and wait, elect_one() issues): descriptors and TMA coordinates
+  // stay in uniform registers instead of going through R2UR inside an ELECT retry loop
   if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = kb0; kb < kb1; ++kb) {
-        const int it = kb - kb0, s = it % STAGES;
-        mbar_wait(bars + (STAGES + s) * 8, ((it / STAGES) & 1) ^ 1);          // slot free
+    for (int kb = kb0; kb < kb1; ++kb) {
+      const int it = kb - kb0, s = it % STAGES;
+      mbar_wait(bars + (STAGES + s) * 8, ((it / STAGES) & 1) ^ 1);          // slot free
+      if (elect_one()) {
         const uint32_t full = bars + s * 8, sa = sbase + s * STAGE, sb = sa + TC_A_STAGE;
         mbar_expect_tx(full, STAGE);
         if (A_MN) {
@@ -121,14 +123,15 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tm_a, const CUte
           tma_load_2d(sb, &tm_b, kb * TC_BK, n0, full);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
-      for (int kb = kb0; kb < kb1; ++kb) {
-        const int it = kb - kb0, s = it % STAGES;
-        mbar_wait(bars + s * 8, (it / STAGES) & 1);                           // TMA bytes landed
-        tc_fence_after();
+    constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+    for (int kb = kb0; kb < kb1; ++kb) {
+      const int it = kb - kb0, s = it % STAGES;
+      mbar_wait(bars + s * 8, (it / STAGES) & 1);                           // TMA bytes landed
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t sa = sbase + s * STAGE, sb = sa + TC_A_STAGE;
         const uint64_t da = make_desc(sa, A_MN), db = make_desc(sb, B_MN);
 #pragma unroll
@@ -137,10 +140,12 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tm_a, const CUte
           const uint64_t ka = (uint64_t)((A_MN ? 2048u : 32u) * k >> 4), kbv = (uint64_t)((B_MN ? 2048u : 32u) * k >> 4);
           tc_mma_bf16(tmem_base, da + ka, db + kbv, idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
-        tc_commit(bars + (STAGES + s) * 8);                                    // frees the slot when the MMAs retire
+        tc_commit(bars + (STAGES + s) * 8);                                  // frees the slot when the MMAs retire
       }
-      tc_commit(bars + 2 * STAGES * 8);                                        // accumulator complete
+      __syncwarp();
     }
+    if (elect_one()) tc_commit(bars + 2 * STAGES * 8);                       // accumulator complete
+    __syncwarp();
   } else {
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int m = m0 + q * 32 + lane;
