@@ -1,5 +1,5 @@
 // Shared by the kernels that stream fp32 frames into the space-to-depth "block matrix" operand
-// (conv_fwd.cu, conv_bwd.cu: conv11 forward and conv11 weight gradient on tcgen05).
+// (conv_fwd.cu, conv_bwd_fused.cu: conv11 forward and conv11 weight gradient on tcgen05).
 //
 // The zero-padded 88x88x4 bf16 image is cut into 22x22 blocks of 4x4 pixels; block (Y, X) is row Y*22 + X of
 // Blk[484, K = 64 = (dy, dx, c)].  Storage is the no-swizzle UMMA layout with ALL rows contiguous: 16-byte k-chunk
@@ -11,9 +11,6 @@
 
 namespace ga3c {
 
-constexpr int CH_ROWS = 12, CF_NCHUNK = IMG / CH_ROWS, CH_BYTES = CH_ROWS * IMG * 16;     // 7 chunks of 16,128 B
-constexpr int CF_NSLOT = 4;
-static_assert(CF_NCHUNK * CH_ROWS == IMG && CH_BYTES % 16 == 0, "chunks must tile the frame");
 // block matrix: 22 x 22 blocks (+ slack rows read by the dead part of the last M tile); chunk arrays padded so that
 // neighbouring k-chunks start 16 banks apart.  548 rows cover conv_fwd's four 128-row tiles; kernels that read fewer rows
 // pass their own plane stride (LBO) to the helpers below.
@@ -37,29 +34,43 @@ __device__ __forceinline__ void blk_lane_offsets(int lane, uint32_t (&lane_off)[
   }
 }
 
-// one 12-row fp32 chunk (staging slot `src`) -> bf16 -> Blk; warp w of AUX_WARPS converts rows w, w + AUX_WARPS, ...
-// All 16-byte loads are issued before the first conversion so their latencies overlap.
-template <int AUX_WARPS, int LBO = BLK_LBO>
-__device__ __forceinline__ void blk_convert_chunk(uint32_t src, uint32_t blk, int c, int warp, int lane,
-                                                  const uint32_t (&lane_off)[3]) {
-  constexpr int RPW = CH_ROWS / AUX_WARPS;
-  static_assert(RPW * AUX_WARPS == CH_ROWS, "image rows of a chunk split evenly over the aux warps");
-  uint32_t px4[RPW][3][4];
+// ---- per-warp streaming pipeline --------------------------------------------------------------------------------
+// Every aux warp runs its OWN chunk pipeline: chunk = 4 image rows (5,376 B fp32, one cp.async.bulk), two ring slots per
+// warp, no barrier between the warps.  (With all aux warps converting one 12-row chunk in lockstep -- wait, load, convert,
+// fence, block barrier, re-arm -- the per-chunk latency chain, not HBM, set the frame rate.)  Chunk c (image rows 4c..4c+3)
+// is padded rows 4c+2..4c+5, i.e. (block row c, dy = 2, 3) and (block row c+1, dy = 0, 1); block row Y is complete after
+// chunks Y-1 and Y.  Consumers are four position groups i (conv11 tiles forward, k-step groups in the weight gradient),
+// each reading Blk rows [~128 i, 128 i + 150]: block rows floor(128 i / 22) .. min((128 i + 150) / 22, 21).
+constexpr int PW_ROWS = 4, PW_NCHUNK = IMG / PW_ROWS, PW_BYTES = PW_ROWS * IMG * 16, PW_SLOTS = 2;       // 21 chunks of 5,376 B
+static_assert(PW_NCHUNK * PW_ROWS == IMG && PW_BYTES % 16 == 0, "chunks must tile the frame");
+// first group that needs chunk c (the group's "rows ready" barrier counts its own chunks: 7, 6, 6, 2) ...
+__device__ __forceinline__ int pw_first_consumer(int c) { return c <= 6 ? 0 : c <= 12 ? 1 : c <= 18 ? 2 : 3; }
+__host__ __device__ constexpr int pw_group_chunks(int i) { return i == 0 ? 7 : i == 3 ? 2 : 6; }
+// ... and last group of the PREVIOUS frame that still reads block rows c, c+1 (they are about to be rewritten)
+__device__ __forceinline__ int pw_last_consumer(int c) { return c >= 16 ? 3 : c >= 10 ? 2 : c >= 4 ? 1 : 0; }
+
+// one warp: 4-row fp32 chunk (staging slot `src`) -> bf16 -> Blk, two rows at a time (24 registers of loads in flight)
+template <int LBO>
+__device__ __forceinline__ void blk_convert_rows4(uint32_t src, uint32_t blk, int c, int lane, const uint32_t (&lane_off)[3]) {
 #pragma unroll
-  for (int rr = 0; rr < RPW; ++rr)
+  for (int half = 0; half < 2; ++half) {
+    uint32_t px4[2][3][4];
 #pragma unroll
-    for (int it = 0; it < 3; ++it)
-      if (lane + 32 * it < IMG) lds128(px4[rr][it], src + ((warp + rr * AUX_WARPS) * IMG + lane + 32 * it) * 16);
+    for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-  for (int rr = 0; rr < RPW; ++rr) {
-    const int py = c * CH_ROWS + warp + rr * AUX_WARPS + 2;        // padded row -> block row Y = py >> 2, dy = py & 3
-    const uint32_t row_off = blk + (py & 3) * (2 * LBO) + (py >> 2) * (BLK_W * 16);
+      for (int it = 0; it < 3; ++it)
+        if (lane + 32 * it < IMG) lds128(px4[rr][it], src + ((2 * half + rr) * IMG + lane + 32 * it) * 16);
 #pragma unroll
-    for (int it = 0; it < 3; ++it) {
-      if (lane + 32 * it < IMG) {
-        const uint32_t* r = px4[rr][it];
-        sts64(row_off + lane_off[it], pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1])),
-              pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3])));
+    for (int rr = 0; rr < 2; ++rr) {
+      const int py = c * PW_ROWS + 2 * half + rr + 2;              // padded row -> block row Y = py >> 2, dy = py & 3
+      const uint32_t row_off = blk + (py & 3) * (2 * LBO) + (py >> 2) * (BLK_W * 16);
+#pragma unroll
+      for (int it = 0; it < 3; ++it) {
+        if (lane + 32 * it < IMG) {
+          const uint32_t* r = px4[rr][it];
+          sts64(row_off + lane_off[it], pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1])),
+                pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3])));
+        }
       }
     }
   }

@@ -25,7 +25,7 @@
 // conv11 weight gradient.  As before (4 quadrants, M = 64, N = 16, K = 464 positions m = oy*22 + ox): A = Blk read MN-major
 //   at row m + 22a + b, B = dn1 staged MN-major -- now written by the data-gradient epilogue instead of loaded from HBM.
 //
-//   warps 0-5    fp32 chunk of x (TMA ring) -> bf16 -> Blk
+//   warps 0-5    fp32 chunks of x (TMA ring, one independent pipeline per warp) -> bf16 -> Blk
 //   warp  6      one thread issues every UMMA: conv12 of frame k+1 between the conv11 position groups of frame k
 //   warp  7      one thread streams n1 / dn2 of the next frame into a raw staging buffer (cp.async.bulk)
 //   warps 8-11   data-gradient epilogue: TMEM -> relu' mask (n1 from Blk2) -> bf16 -> dn1 operand, bias gradient of conv11;
@@ -38,7 +38,7 @@
 
 namespace ga3c {
 
-constexpr int FB_THREADS = 512, FB_AUX_WARPS = 6, FB_AUX_THREADS = 32 * FB_AUX_WARPS, FB_ISSUE_WARP = 6, FB_TMA_WARP = 7,
+constexpr int FB_THREADS = 512, FB_AUX_WARPS = 6, FB_ISSUE_WARP = 6, FB_TMA_WARP = 7,
               FB_EPI_WARP0 = 8, FB_RE_WARP0 = 12;
 static_assert(FB_EPI_WARP0 % 4 == 0, "epilogue warp e must own TMEM lane quarter e");
 constexpr int FBLK_ROWS = 492, FBLK_LBO = FBLK_ROWS * 16, FBLK_BYTES = 8 * FBLK_LBO;     // rows read: <= 16*28 + 23 + 15 = 486
@@ -54,25 +54,26 @@ constexpr int W12D_BYTES = 4 * 4 * 64 * 16;                      // 4 taps x [4 
 
 constexpr int FB_OFF_BLK = 0;
 constexpr int FB_OFF_RING = FB_OFF_BLK + FBLK_BYTES;             //  62,976
-constexpr int FB_OFF_DN1 = FB_OFF_RING + CF_NSLOT * CH_BYTES;    // 127,488 (two buffers)
+constexpr int FB_RING_BYTES = FB_AUX_WARPS * PW_SLOTS * PW_BYTES; //  64,512: two 4-row slots per aux warp
+constexpr int FB_OFF_DN1 = FB_OFF_RING + FB_RING_BYTES;          // 127,488 (two buffers)
 constexpr int FB_OFF_G = FB_OFF_DN1 + 2 * DN1_BUF;               // 157,184
 constexpr int FB_OFF_B2 = FB_OFF_G + G_BYTES;                    // 168,448
 constexpr int FB_OFF_W12D = FB_OFF_B2 + B2_BYTES;                // 188,928
 constexpr int FB_OFF_RAW = FB_OFF_W12D + W12D_BYTES;             // 205,312
 constexpr int FB_OFF_RED = FB_OFF_RAW + RAW_BYTES;               // 227,168: [4][16] conv11 + [4][32] conv12 bias partials
 constexpr int FB_OFF_BAR = FB_OFF_RED + (4 * C1_OUT + 4 * C2_OUT) * 4;
-constexpr int FB_RING = 0;        // [4] TMA chunk of x landed
-constexpr int FB_BLKRDY = 4;      // [4] Blk rows of conv11 position group i converted              (aux -> issuer)
-constexpr int FB_GRP = 8;         // [4] conv11 UMMAs of group i retired (tcgen05.commit)           (-> aux: Blk rows free)
-constexpr int FB_DN1RDY = 12;     // [2] dn1 operand buffer written, 4 arrivals                     (epilogue -> issuer)
-constexpr int FB_DN1FREE = 14;    // [2] every conv11 UMMA reading the buffer retired               (-> epilogue)
-constexpr int FB_RAWFULL = 16;    //     n1 / dn2 of a frame landed in the raw buffer               (TMA -> re-layout)
-constexpr int FB_RAWFREE = 17;    //     raw buffer consumed                                        (re-layout -> TMA thread)
-constexpr int FB_C12RDY = 18;     //     G / Blk2 hold the frame                                    (re-layout -> issuer)
-constexpr int FB_MMA12 = 19;      //     conv12 UMMAs of the frame retired (tcgen05.commit)         (-> epilogue)
-constexpr int FB_EPI12 = 20;      //     D drained and Blk2 mask reads done, 4 arrivals             (epilogue -> issuer, re-layout)
-constexpr int FB_DONE = 21;       //     every UMMA of the kernel retired                           (-> final store)
-constexpr int FB_NBAR = 22;
+constexpr int FB_RING = 0;        // [12] TMA chunk of x landed (slot = aux warp * 2 + parity)
+constexpr int FB_BLKRDY = 12;     // [4] Blk rows of conv11 position group i converted, one arrival per chunk (aux -> issuer)
+constexpr int FB_GRP = 16;        // [4] conv11 UMMAs of group i retired (tcgen05.commit)           (-> aux: Blk rows free)
+constexpr int FB_DN1RDY = 20;     // [2] dn1 operand buffer written, 4 arrivals                     (epilogue -> issuer)
+constexpr int FB_DN1FREE = 22;    // [2] every conv11 UMMA reading the buffer retired               (-> epilogue)
+constexpr int FB_RAWFULL = 24;    //     n1 / dn2 of a frame landed in the raw buffer               (TMA -> re-layout)
+constexpr int FB_RAWFREE = 25;    //     raw buffer consumed                                        (re-layout -> TMA thread)
+constexpr int FB_C12RDY = 26;     //     G / Blk2 hold the frame                                    (re-layout -> issuer)
+constexpr int FB_MMA12 = 27;      //     conv12 UMMAs of the frame retired (tcgen05.commit)         (-> epilogue)
+constexpr int FB_EPI12 = 28;      //     D drained and Blk2 mask reads done, 4 arrivals             (epilogue -> issuer, re-layout)
+constexpr int FB_DONE = 29;       //     every UMMA of the kernel retired                           (-> final store)
+constexpr int FB_NBAR = 30;
 constexpr int FB_OFF_TSLOT = FB_OFF_BAR + FB_NBAR * 8;
 constexpr int FB_SMEM = FB_OFF_TSLOT + 16 + 128;                 // incl. slack to align the base to 128 B
 static_assert(FB_SMEM <= 232448, "shared memory budget of one CTA per SM");
@@ -92,21 +93,21 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int stride = gridDim.x;
   const int n_frames = ((int)blockIdx.x < batch) ? (batch - 1 - (int)blockIdx.x) / stride + 1 : 0;
-  const int n_chunks = n_frames * CF_NCHUNK;
+  const int n_chunks = n_frames * PW_NCHUNK;                       // chunk stream of this CTA: q = k * 21 + c, warp q % 6
   auto frame_of = [&](int k) { return (size_t)(blockIdx.x + k * stride); };
   auto bar = [&](int i) { return bars + i * 8; };
-  auto issue_chunk = [&](int q) {                                  // one thread
-    const int k = q / CF_NCHUNK, c = q - k * CF_NCHUNK, slot = q % CF_NSLOT;
-    mbar_expect_tx(bar(FB_RING + slot), CH_BYTES);
-    bulk_load(ring + slot * CH_BYTES, reinterpret_cast<const uint8_t*>(x + frame_of(k) * STATE_DIM) + c * CH_BYTES, CH_BYTES,
+  auto issue_chunk = [&](int q, int slot) {                        // one thread
+    const int k = q / PW_NCHUNK, c = q - k * PW_NCHUNK;
+    mbar_expect_tx(bar(FB_RING + slot), PW_BYTES);
+    bulk_load(ring + slot * PW_BYTES, reinterpret_cast<const uint8_t*>(x + frame_of(k) * STATE_DIM) + c * PW_BYTES, PW_BYTES,
               bar(FB_RING + slot));
   };
 
   // ---------------- prologue ----------------
   if (tid == 0) {
+    for (int i = 0; i < FB_AUX_WARPS * PW_SLOTS; ++i) mbar_init(bar(FB_RING + i), 1);
     for (int i = 0; i < 4; ++i) {
-      mbar_init(bar(FB_RING + i), 1);
-      mbar_init(bar(FB_BLKRDY + i), 1);
+      mbar_init(bar(FB_BLKRDY + i), pw_group_chunks(i));
       mbar_init(bar(FB_GRP + i), 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -123,8 +124,9 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
   }
   if (warp == FB_EPI_WARP0) tmem_alloc<FB_TMEM_COLS>(tslot);
   __syncthreads();
-  if (tid == 0)                                                    // x is an input of the step: stream it before the dependency wait
-    for (int q = 0; q < CF_NSLOT && q < n_chunks; ++q) issue_chunk(q);
+  if (warp < FB_AUX_WARPS && lane == 0)                            // x is an input of the step: stream it before the dependency wait
+    for (int j = 0; j < PW_SLOTS; ++j)
+      if (warp + j * FB_AUX_WARPS < n_chunks) issue_chunk(warp + j * FB_AUX_WARPS, warp * PW_SLOTS + j);
   // zero once: image borders / slack rows of Blk, dead rows of both dn1 buffers, borders of G and Blk2
   for (int i = tid; i < FBLK_BYTES / 16; i += FB_THREADS) sts128(blk + i * 16, make_uint4(0, 0, 0, 0));
   for (int i = tid; i < (FB_OFF_W12D - FB_OFF_DN1) / 16; i += FB_THREADS) sts128(dn1s + i * 16, make_uint4(0, 0, 0, 0));
@@ -145,26 +147,22 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tslot));
 
   if (warp < FB_AUX_WARPS) {
-    // =========================== aux: fp32 chunk -> bf16 block matrix, slot re-arm ===========================
+    // =========================== aux: one chunk pipeline per warp (conv_blk.cuh) ===========================
     uint32_t lane_off[3];
     blk_lane_offsets<FBLK_LBO>(lane, lane_off);
-    for (int k = 0; k < n_frames; ++k) {
+    int j = 0;
 #pragma unroll 1
-      for (int c = 0; c < CF_NCHUNK; ++c) {
-        const int q = k * CF_NCHUNK + c, slot = q % CF_NSLOT;
-        // block rows 3c..3c+3 are rewritten: the last position group of frame k-1 that reads them must have retired
-        if (k > 0) mbar_wait(bar(FB_GRP + (c + 1) / 2), (k - 1) & 1);
-        mbar_wait(bar(FB_RING + slot), (q / CF_NSLOT) & 1);
-        blk_convert_chunk<FB_AUX_WARPS, FBLK_LBO>(ring + slot * CH_BYTES, blk, c, warp, lane, lane_off);
-        fence_proxy_async();
-        named_bar_sync(1, FB_AUX_THREADS);
-        if (tid == 0) {
-          if (q + CF_NSLOT < n_chunks) issue_chunk(q + CF_NSLOT);
-          // position group i (m in [128 i, 128 i + 128)) reads block rows up to (128 i + 150) / 22
-          if (c == 2) mbar_arrive(bar(FB_BLKRDY + 0));
-          if (c == 4) mbar_arrive(bar(FB_BLKRDY + 1));
-          if (c == 6) { mbar_arrive(bar(FB_BLKRDY + 2)); mbar_arrive(bar(FB_BLKRDY + 3)); }
-        }
+    for (int q = warp; q < n_chunks; q += FB_AUX_WARPS, ++j) {
+      const int k = q / PW_NCHUNK, c = q - k * PW_NCHUNK, slot = warp * PW_SLOTS + (j & 1);
+      // block rows c, c+1 are rewritten: the last position group of frame k-1 that reads them must have retired
+      if (k > 0) mbar_wait(bar(FB_GRP + pw_last_consumer(c)), (k - 1) & 1);
+      mbar_wait(bar(FB_RING + slot), (j >> 1) & 1);
+      blk_convert_rows4<FBLK_LBO>(ring + slot * PW_BYTES, blk, c, lane, lane_off);
+      fence_proxy_async();                                         // Blk is read by the tensor core; the slot is refilled by the TMA
+      __syncwarp();
+      if (lane == 0) {
+        if (q + PW_SLOTS * FB_AUX_WARPS < n_chunks) issue_chunk(q + PW_SLOTS * FB_AUX_WARPS, slot);
+        mbar_arrive(bar(FB_BLKRDY + pw_first_consumer(c)));
       }
     }
   } else if (warp == FB_ISSUE_WARP) {
@@ -398,6 +396,8 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
 }
 
 GA3C_TRACE_ATTACH(trace_attach_conv_bwd_fused)
+
+int conv_bwd_grid(int batch, int num_sms) { return min(batch, num_sms); }
 
 int configure_conv_bwd_fused() {
   return (int)cudaFuncSetAttribute(conv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);

@@ -22,8 +22,8 @@
 // frame; here the SM only converts fp32 -> bf16 and runs the two epilogues.
 //
 // Streaming pipeline per frame (112,896 B of fp32 input read from HBM exactly once; only n2 [+ n1 when training] leave):
-//   TMA engine        cp.async.bulk of 12-row chunks (16,128 B) of the fp32 frame into a 4-slot ring (mbarrier per slot)
-//   warps 0-5  (aux)  chunk -> bf16 -> Blk, re-arm the slot with the chunk 4 ahead (next frames included)
+//   TMA engine        cp.async.bulk of 4-row chunks (5,376 B) of the fp32 frame, two ring slots per aux warp (mbarrier per slot)
+//   warps 0-5  (aux)  one independent pipeline per warp: chunk -> bf16 -> Blk, re-arm the slot with the warp's chunk after next
 //   warp  6           one thread issues the UMMAs: conv11 tile i as soon as its Blk rows are converted, conv12 after the
 //                     conv11 epilogues; tcgen05.commit signals TMEM-full / operand-free mbarriers
 //   warps 8-11        epilogues (one TMEM lane quarter each): conv11 tile -> +bias, ReLU -> im2col scatter (+ n1 to HBM when
@@ -35,9 +35,8 @@
 
 namespace ga3c {
 
-constexpr int CF_THREADS = 384, CF_AUX_WARPS = 6, CF_AUX_THREADS = 32 * CF_AUX_WARPS, CF_ISSUE_WARP = 6, CF_EPI_WARP0 = 8;
+constexpr int CF_THREADS = 384, CF_AUX_WARPS = 6, CF_ISSUE_WARP = 6, CF_EPI_WARP0 = 8;
 static_assert(CF_EPI_WARP0 % 4 == 0, "epilogue warp e must own TMEM lane quarter e");
-static_assert(CH_ROWS % CF_AUX_WARPS == 0, "image rows of a chunk split evenly over the aux warps");
 constexpr int C11_TILES = 4;                     // 462 output rows (21 x 22, column 21 dead) in 4 x 128
 constexpr int C11_TSTRIDE = 127;                                     // output rows per tile (tile row 127 only feeds row 126)
 static_assert((C11_TILES - 1) * C11_TSTRIDE + 128 + BLK_W <= BLK_ROWS && C11_TILES * C11_TSTRIDE >= H1 * BLK_W, "tiles must cover the outputs and stay inside the buffer");
@@ -46,19 +45,19 @@ constexpr int CF_OFF_A2 = 0;                                         // conv12 A
 constexpr int CF_OFF_B2 = CF_OFF_A2 + 4 * 128 * 128;                 //  65,536: conv12 B: 4 k-blocks x [32 rows x 128 B], SW128
 constexpr int CF_OFF_BLK = CF_OFF_B2 + 4 * 32 * 128;                 //  81,920
 constexpr int CF_OFF_RING = CF_OFF_BLK + BLK_BYTES;                  // 152,064
-constexpr int CF_OFF_WQ = CF_OFF_RING + CF_NSLOT * CH_BYTES;         // 216,576: conv11 B: 2 row shifts a x [8 k-chunks][32 rows (b, cout) x 16 B]
+constexpr int CF_OFF_WQ = CF_OFF_RING + CF_AUX_WARPS * PW_SLOTS * PW_BYTES;   // 216,576 (ring: two 4-row slots per aux warp): conv11 B: 2 row shifts a x [8 k-chunks][32 rows (b, cout) x 16 B]
 constexpr int CF_OFF_LUT = CF_OFF_WQ + 4 * 2048;                     // 224,768
 constexpr int CF_OFF_BIAS = CF_OFF_LUT + 3584;                       // 228,352 (441 x 8 B rounded up)
 constexpr int CF_OFF_BAR = CF_OFF_BIAS + (C1_OUT + C2_OUT) * 4;      // 228,544
 // mbarriers (8 B each)
-constexpr int BAR_RING = 0;          // [4]  TMA chunk landed
-constexpr int BAR_BLKRDY = 4;        // [4]  Blk rows of conv11 tile i converted            (aux -> issuer)
-constexpr int BAR_C11 = 8;           // [4]  conv11 tile i accumulated (tcgen05.commit)     (-> epilogue; -> aux: its Blk rows are free)
-constexpr int BAR_T1FREE = 12;       // [4]  conv11 TMEM tile i drained, 4 arrivals         (epilogue -> issuer)
-constexpr int BAR_A2RDY = 16;        //      im2col operand of the frame complete, 4 arrivals (epilogue -> issuer)
-constexpr int BAR_MMA2 = 17;         //      conv12 accumulated (tcgen05.commit)            (-> epilogue; im2col operand free)
-constexpr int BAR_T2FREE = 18;       //      conv12 TMEM tile drained, 4 arrivals           (epilogue -> issuer)
-constexpr int CF_NBAR = 19;
+constexpr int BAR_RING = 0;          // [12] TMA chunk landed (slot = aux warp * 2 + parity)
+constexpr int BAR_BLKRDY = 12;       // [4]  Blk rows of conv11 tile i converted, one arrival per chunk (aux -> issuer)
+constexpr int BAR_C11 = 16;          // [4]  conv11 tile i accumulated (tcgen05.commit)     (-> epilogue; -> aux: its Blk rows are free)
+constexpr int BAR_T1FREE = 20;       // [4]  conv11 TMEM tile i drained, 4 arrivals         (epilogue -> issuer)
+constexpr int BAR_A2RDY = 24;        //      im2col operand of the frame complete, 4 arrivals (epilogue -> issuer)
+constexpr int BAR_MMA2 = 25;         //      conv12 accumulated (tcgen05.commit)            (-> epilogue; im2col operand free)
+constexpr int BAR_T2FREE = 26;       //      conv12 TMEM tile drained, 4 arrivals           (epilogue -> issuer)
+constexpr int CF_NBAR = 27;
 constexpr int CF_OFF_TSLOT = CF_OFF_BAR + CF_NBAR * 8;               // 228,696
 constexpr int CF_OFF_XCH = CF_OFF_TSLOT + 16;                        // 228,712: [2][4 warps][16 floats] b-shift exchange across warps
 constexpr int CF_SMEM = CF_OFF_XCH + 512 + 1024;                     // 230,248 incl. slack to align the base to 1024 B
@@ -77,21 +76,21 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int stride = gridDim.x;
   const int n_frames = ((int)blockIdx.x < batch) ? (batch - 1 - (int)blockIdx.x) / stride + 1 : 0;
-  const int n_chunks = n_frames * CF_NCHUNK;                         // chunk stream of this CTA: q = k * 7 + c
+  const int n_chunks = n_frames * PW_NCHUNK;                         // chunk stream of this CTA: q = k * 21 + c, warp q % 6
   auto frame_of = [&](int k) { return (size_t)(blockIdx.x + k * stride); };
   auto bar = [&](int i) { return bars + i * 8; };
-  auto issue_chunk = [&](int q) {                                    // one thread
-    const int k = q / CF_NCHUNK, c = q - k * CF_NCHUNK, slot = q % CF_NSLOT;
-    mbar_expect_tx(bar(BAR_RING + slot), CH_BYTES);
-    bulk_load(ring + slot * CH_BYTES, reinterpret_cast<const uint8_t*>(x + frame_of(k) * STATE_DIM) + c * CH_BYTES, CH_BYTES,
+  auto issue_chunk = [&](int q, int slot) {                          // one thread
+    const int k = q / PW_NCHUNK, c = q - k * PW_NCHUNK;
+    mbar_expect_tx(bar(BAR_RING + slot), PW_BYTES);
+    bulk_load(ring + slot * PW_BYTES, reinterpret_cast<const uint8_t*>(x + frame_of(k) * STATE_DIM) + c * PW_BYTES, PW_BYTES,
               bar(BAR_RING + slot));
   };
 
   // ---------------- prologue ----------------
   if (tid == 0) {
+    for (int i = 0; i < CF_AUX_WARPS * PW_SLOTS; ++i) mbar_init(bar(BAR_RING + i), 1);
     for (int i = 0; i < 4; ++i) {
-      mbar_init(bar(BAR_RING + i), 1);
-      mbar_init(bar(BAR_BLKRDY + i), 1);
+      mbar_init(bar(BAR_BLKRDY + i), pw_group_chunks(i));
       mbar_init(bar(BAR_C11 + i), 1);
       mbar_init(bar(BAR_T1FREE + i), 4);
     }
@@ -102,8 +101,9 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
   }
   if (warp == CF_EPI_WARP0) tmem_alloc<CF_TMEM_COLS>(tslot);
   __syncthreads();
-  if (tid == 0)                                                      // x is an input of the step: stream it before the dependency wait
-    for (int q = 0; q < CF_NSLOT && q < n_chunks; ++q) issue_chunk(q);
+  if (warp < CF_AUX_WARPS && lane == 0)                              // x is an input of the step: stream it before the dependency wait
+    for (int j = 0; j < PW_SLOTS; ++j)
+      if (warp + j * CF_AUX_WARPS < n_chunks) issue_chunk(warp + j * CF_AUX_WARPS, warp * PW_SLOTS + j);
   // zero the operands once: image borders / slack rows of Blk, padding taps and rows 121..127 of the im2col operand
   for (int i = tid; i < (CF_OFF_RING - CF_OFF_A2) / 16; i += CF_THREADS)
     if (i < CF_OFF_B2 / 16 || i >= CF_OFF_BLK / 16) sts128(sbase + i * 16, make_uint4(0, 0, 0, 0));
@@ -158,26 +158,22 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tslot));
 
   if (warp < CF_AUX_WARPS) {
-    // =========================== aux: fp32 chunk -> bf16 block matrix, slot re-arm ===========================
+    // =========================== aux: one chunk pipeline per warp (conv_blk.cuh) ===========================
     uint32_t lane_off[3];
     blk_lane_offsets(lane, lane_off);
-    for (int k = 0; k < n_frames; ++k) {
+    int j = 0;
 #pragma unroll 1
-      for (int c = 0; c < CF_NCHUNK; ++c) {
-        const int q = k * CF_NCHUNK + c, slot = q % CF_NSLOT;
-        // block rows 3c..3c+3 are rewritten: the last conv11 tile of frame k-1 that reads them must have completed
-        if (k > 0) mbar_wait(bar(BAR_C11 + (c + 1) / 2), (k - 1) & 1);
-        mbar_wait(bar(BAR_RING + slot), (q / CF_NSLOT) & 1);         // chunk q has landed
-        blk_convert_chunk<CF_AUX_WARPS>(ring + slot * CH_BYTES, blk, c, warp, lane, lane_off);
-        fence_proxy_async();                                         // Blk is read by the tensor core; the slot is refilled by the TMA
-        named_bar_sync(1, CF_AUX_THREADS);                           // the slot has been consumed, the rows are written
-        if (tid == 0) {
-          if (q + CF_NSLOT < n_chunks) issue_chunk(q + CF_NSLOT);
-          // conv11 tile i reads block rows up to (128 i + 150) / 22: complete after chunk 2 / 4 / 6 / 6
-          if (c == 2) mbar_arrive(bar(BAR_BLKRDY + 0));
-          if (c == 4) mbar_arrive(bar(BAR_BLKRDY + 1));
-          if (c == 6) { mbar_arrive(bar(BAR_BLKRDY + 2)); mbar_arrive(bar(BAR_BLKRDY + 3)); }
-        }
+    for (int q = warp; q < n_chunks; q += CF_AUX_WARPS, ++j) {
+      const int k = q / PW_NCHUNK, c = q - k * PW_NCHUNK, slot = warp * PW_SLOTS + (j & 1);
+      // block rows c, c+1 are rewritten: the last conv11 tile of frame k-1 that reads them must have completed
+      if (k > 0) mbar_wait(bar(BAR_C11 + pw_last_consumer(c)), (k - 1) & 1);
+      mbar_wait(bar(BAR_RING + slot), (j >> 1) & 1);                 // the chunk has landed
+      blk_convert_rows4<BLK_LBO>(ring + slot * PW_BYTES, blk, c, lane, lane_off);
+      fence_proxy_async();                                           // Blk is read by the tensor core; the slot is refilled by the TMA
+      __syncwarp();
+      if (lane == 0) {
+        if (q + PW_SLOTS * CF_AUX_WARPS < n_chunks) issue_chunk(q + PW_SLOTS * CF_AUX_WARPS, slot);
+        mbar_arrive(bar(BAR_BLKRDY + pw_first_consumer(c)));
       }
     }
   } else if (warp == CF_ISSUE_WARP) {

@@ -7,7 +7,6 @@ namespace ga3c {
 
 // step timeline trace: attach (or detach with nullptr) the [K_COUNT][TRACE_SLOTS] uint64 buffer, one call per kernel file
 int trace_attach_conv_fwd(unsigned long long* buf);
-int trace_attach_conv_bwd(unsigned long long* buf);
 int trace_attach_conv_bwd_fused(unsigned long long* buf);
 int trace_attach_dense_tc(unsigned long long* buf);
 int trace_attach_heads(unsigned long long* buf);
@@ -15,7 +14,6 @@ int trace_attach_elementwise(unsigned long long* buf);
 
 // one-time per-process function-attribute setup (dynamic smem opt-in); returns cudaError_t as int
 int configure_conv_fwd();
-int configure_conv_bwd();
 int configure_conv_bwd_fused();
 int configure_dense_tc();
 
@@ -56,19 +54,13 @@ struct HeadsArgs {
 int heads_grid(int batch, int num_sms);          // CTAs (= slabs written) of a training launch
 int launch_heads(const HeadsArgs& args, int num_sms, cudaStream_t stream);
 
-// conv_bwd.cu
+// conv_bwd_fused.cu
 // Weight / bias gradients are per-CTA partial sums: CTA i stores into slab i (g_* point into slab 0, slabs are
 // gp_stride floats apart) and launch_grad_reduce adds the slabs in a fixed order.  No contended atomics, and the
 // step is bit-reproducible.
 int conv_bwd_grid(int batch, int num_sms);       // CTAs (= slabs written) of both kernels
-//   conv12 backward: dn1 = dgrad(dn2, w12) masked by n1 > 0 (bf16 out); g_w12 = wgrad; g_b12 = colsum(dn2)
-int launch_conv12_bwd(const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1, float* g_w12,
-                      float* g_b12, int64_t gp_stride, int batch, int num_sms, cudaStream_t stream);
-//   conv11 wgrad: g_w11 = patches(x)^T dn1 ; g_b11 = colsum(dn1)
-int launch_conv11_wgrad(const float* x, const uint16_t* dn1, float* g_w11, float* g_b11, int64_t gp_stride, int batch,
-                        int num_sms, cudaStream_t stream);
-
-// conv_bwd_fused.cu -- both of the above in one kernel on tcgen05; dn1 stays on chip (dn1_out: optional copy for tests)
+// conv_bwd_fused.cu -- conv12 data gradient (dn1, kept on chip; dn1_out: optional copy for tests), conv12 and conv11
+// weight / bias gradients in one kernel on tcgen05
 int launch_conv_bwd(const float* x, const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1_out,
                     float* g_w11, float* g_b11, float* g_w12, float* g_b12, int64_t gp_stride, int batch, int num_sms,
                     cudaStream_t stream);

@@ -181,7 +181,7 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
     cudaMemcpy(n->ms, ones.data(), ab, cudaMemcpyHostToDevice);
   }
   int r;
-  if ((r = configure_conv_fwd()) || (r = configure_conv_bwd()) || (r = configure_conv_bwd_fused()) || (r = configure_dense_tc())) {
+  if ((r = configure_conv_fwd()) || (r = configure_conv_bwd_fused()) || (r = configure_dense_tc())) {
     ga3c_destroy(n);
     return fail("cudaFuncSetAttribute", (cudaError_t)r);
   }
@@ -379,16 +379,9 @@ static int fb_tail_impl(ga3c_net* n, const float* x, int32_t batch, void* stream
     LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_bwd_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, n->g + n->off(P_D1W), batch, st));
   else
     LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
-  if (getenv("GA3C_SPLIT_CONV_BWD")) {      // the two-kernel predecessor (mma.sync conv12, dn1 through HBM), kept for A/B runs
-    LAUNCH(n, K_CONV12_BWD, st, launch_conv12_bwd(n->n1, n->dn2, w + n->off(P_C12W), n->dn1, gp + n->off(P_C12W),
-                                                  gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, st));
-    LAUNCH(n, K_CONV11_WGRAD, st, launch_conv11_wgrad(x, n->dn1, gp + n->off(P_C11W), gp + n->off(P_C11B), n->gp_stride,
-                                                      batch, n->num_sms, st));
-  } else {
-    LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(x, n->n1, n->dn2, w + n->off(P_C12W), n->keep_dn1 ? n->dn1 : nullptr,
-                                                gp + n->off(P_C11W), gp + n->off(P_C11B), gp + n->off(P_C12W),
-                                                gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, st));
-  }
+  LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(x, n->n1, n->dn2, w + n->off(P_C12W), n->keep_dn1 ? n->dn1 : nullptr,
+                                              gp + n->off(P_C11W), gp + n->off(P_C11B), gp + n->off(P_C12W),
+                                              gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, st));
   if (reduce) LAUNCH(n, K_GRAD_REDUCE, st, launch_grad_reduce(reduce_args(n, batch), st));
   return 0;
 }
@@ -542,7 +535,7 @@ static void timing_free(ga3c_net* n) {
 // ---- step timeline trace --------------------------------------------------------------------------
 static int trace_attach_all(unsigned long long* buf) {
   int r;
-  if ((r = trace_attach_conv_fwd(buf)) || (r = trace_attach_conv_bwd(buf)) || (r = trace_attach_conv_bwd_fused(buf)) || (r = trace_attach_dense_tc(buf)) ||
+  if ((r = trace_attach_conv_fwd(buf)) || (r = trace_attach_conv_bwd_fused(buf)) || (r = trace_attach_dense_tc(buf)) ||
       (r = trace_attach_heads(buf)) || (r = trace_attach_elementwise(buf)))
     return r;
   return 0;
