@@ -52,6 +52,8 @@ SIGNATURES = {
     "ga3c_kernel_name": (C.c_char_p, [C.c_int]),
     "ga3c_timing_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "ga3c_timing_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
+    "ga3c_evt_begin": (C.c_int, [C.c_void_p]),
+    "ga3c_evt_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32, C.POINTER(C.c_int32)]),
     "ga3c_trace_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ga3c_trace_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32]),
 }

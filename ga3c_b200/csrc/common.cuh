@@ -159,6 +159,24 @@ __device__ __forceinline__ void griddep_wait(int kid) {
   asm volatile("griddepcontrol.wait;\n" ::: "memory");
   trace_mark(kid, 1);
 }
+// fine-grained event log of CTA 0 (debug view of a kernel's pipeline): lane 0 of every warp appends {globaltimer, id, arg}
+// to the warp's own region of the buffer with plain stores (index in a register: no atomics, nothing to wait for)
+static __device__ unsigned long long* g_evt = nullptr;
+constexpr unsigned int EVT_PER_WARP = 1024, EVT_WARPS = 16;
+__device__ __forceinline__ void evt_mark(unsigned int& i, int id, int arg) {
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+    unsigned long long* e = g_evt;
+    if (e != nullptr && i < EVT_PER_WARP) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(now));
+      const unsigned int slot = (threadIdx.x >> 5) * EVT_PER_WARP + i++;
+      e[2 * slot] = now;
+      e[2 * slot + 1] = ((unsigned long long)(threadIdx.x >> 5) << 32) | ((unsigned long long)id << 16) | (unsigned long long)(arg & 0xFFFF);
+    }
+  }
+}
+#define GA3C_EVT_ATTACH(fn) \
+  int fn(unsigned long long* buf) { return (int)cudaMemcpyToSymbol(g_evt, &buf, sizeof(buf)); }
 #define GA3C_TRACE_ATTACH(fn)                                                                   \
   int fn(unsigned long long* buf) { return (int)cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)); }
 

@@ -91,6 +91,7 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
                  tslot = sbase + FB_OFF_TSLOT;
   float* red = reinterpret_cast<float*>(smem + FB_OFF_RED);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned int evt_i = 0;                                          // event-log cursor (ga3c_evt_*; dead code unless attached)
   const int stride = gridDim.x;
   const int n_frames = ((int)blockIdx.x < batch) ? (batch - 1 - (int)blockIdx.x) / stride + 1 : 0;
   const int n_chunks = n_frames * PW_NCHUNK;                       // chunk stream of this CTA: q = k * 21 + c, warp q % 6
@@ -131,6 +132,7 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
   for (int i = tid; i < FBLK_BYTES / 16; i += FB_THREADS) sts128(blk + i * 16, make_uint4(0, 0, 0, 0));
   for (int i = tid; i < (FB_OFF_W12D - FB_OFF_DN1) / 16; i += FB_THREADS) sts128(dn1s + i * 16, make_uint4(0, 0, 0, 0));
   griddep_launch();
+  evt_mark(evt_i, 50, 0);
   griddep_wait(K_CONV12_BWD);   // dn2 comes from the dense1 data-gradient GEMM that precedes this kernel
   // data-gradient weights as the UMMA B operand (K-major, no swizzle): tap (a, b), k-chunk j (8 co), row n = (py, px, ci)
   for (int i = tid; i < 4 * 4 * 64; i += FB_THREADS) {
@@ -145,6 +147,7 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tslot));
+  evt_mark(evt_i, 51, 0);
 
   if (warp < FB_AUX_WARPS) {
     // =========================== aux: one chunk pipeline per warp (conv_blk.cuh) ===========================
@@ -155,8 +158,11 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
     for (int q = warp; q < n_chunks; q += FB_AUX_WARPS, ++j) {
       const int k = q / PW_NCHUNK, c = q - k * PW_NCHUNK, slot = warp * PW_SLOTS + (j & 1);
       // block rows c, c+1 are rewritten: the last position group of frame k-1 that reads them must have retired
+      evt_mark(evt_i, 1, q);
       if (k > 0) mbar_wait(bar(FB_GRP + pw_last_consumer(c)), (k - 1) & 1);
+      evt_mark(evt_i, 2, q);
       mbar_wait(bar(FB_RING + slot), (j >> 1) & 1);
+      evt_mark(evt_i, 3, q);
       blk_convert_rows4<FBLK_LBO>(ring + slot * PW_BYTES, blk, c, lane, lane_off);
       fence_proxy_async();                                         // Blk is read by the tensor core; the slot is refilled by the TMA
       __syncwarp();
@@ -164,6 +170,7 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
         if (q + PW_SLOTS * FB_AUX_WARPS < n_chunks) issue_chunk(q + PW_SLOTS * FB_AUX_WARPS, slot);
         mbar_arrive(bar(FB_BLKRDY + pw_first_consumer(c)));
       }
+      evt_mark(evt_i, 4, q);
     }
   } else if (warp == FB_ISSUE_WARP) {
     // =========================== MMA issuer ===========================
@@ -177,7 +184,9 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
     constexpr uint32_t hi_k = desc_ns_hi(128), hi_g = desc_ns_hi(G_LBO), hi_b2 = desc_ns_hi(B2_LBO), hi_blk = desc_ns_hi(FBLK_LBO),
                        hi_dn1 = desc_ns_hi(DN1_PLANE);
     auto conv12_mmas = [&](int k) {
+      evt_mark(evt_i, 10, k);
       mbar_wait(bar(FB_C12RDY), k & 1);                            // G / Blk2 hold frame k
+      evt_mark(evt_i, 11, k);
       if (k > 0) mbar_wait(bar(FB_EPI12), (k - 1) & 1);            // D of frame k-1 has been drained
       tc_fence_after();
       if (elect_one()) {
@@ -201,15 +210,19 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
         tc_commit(bar(FB_MMA12));
       }
       __syncwarp();
+      evt_mark(evt_i, 12, k);
     };
     if (n_frames > 0) conv12_mmas(0);
     for (int k = 0; k < n_frames; ++k) {
       const uint32_t dbuf = dn1_mn + (k & 1) * (DN1_BUF / 16);
+      evt_mark(evt_i, 13, k);
       mbar_wait(bar(FB_DN1RDY + (k & 1)), (k >> 1) & 1);
+      evt_mark(evt_i, 14, k);
 #pragma unroll
       for (int gi = 0; gi < 4; ++gi) {
         if (gi == 1 && k + 1 < n_frames) conv12_mmas(k + 1);       // one frame ahead of the conv11 gradient
         mbar_wait(bar(FB_BLKRDY + gi), k & 1);
+        evt_mark(evt_i, 15, k * 4 + gi);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t acc = k ? 1u : 0u;
@@ -224,6 +237,7 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
           if (gi == 3) tc_commit(bar(FB_DN1FREE + (k & 1)));
         }
         __syncwarp();
+        evt_mark(evt_i, 16, k * 4 + gi);
       }
     }
     if (elect_one()) tc_commit(bar(FB_DONE));
@@ -233,6 +247,7 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
     if (lane == 0) {
       for (int k = 0; k < n_frames; ++k) {
         if (k > 0) mbar_wait(bar(FB_RAWFREE), (k - 1) & 1);
+        evt_mark(evt_i, 20, k);
         mbar_expect_tx(bar(FB_RAWFULL), RAW_BYTES);
         bulk_load(raw, dn2 + frame_of(k) * FLAT, RAW_DN2, bar(FB_RAWFULL));
         bulk_load(raw + RAW_DN2, n1 + frame_of(k) * (N1_POS * C1_OUT), RAW_N1, bar(FB_RAWFULL));
@@ -244,7 +259,9 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
     float bacc = 0.f;                                              // db12 partial: channel rtid & 31, position phase rtid >> 5
     for (int k = 0; k < n_frames; ++k) {
       mbar_wait(bar(FB_RAWFULL), k & 1);
+      evt_mark(evt_i, 30, k);
       if (k > 0) mbar_wait(bar(FB_EPI12), (k - 1) & 1);            // conv12 UMMAs and mask reads of frame k-1 are done
+      evt_mark(evt_i, 31, k);
       for (int i = rtid; i < N2_POS * 4; i += 128) {               // dn2: 4 chunks of 8 co per position
         const int pos = i >> 2, j = i & 3, oy = pos / H2, ox = pos - oy * H2;
         uint32_t r[4];
@@ -271,6 +288,7 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
         mbar_arrive(bar(FB_C12RDY));
         mbar_arrive(bar(FB_RAWFREE));
       }
+      evt_mark(evt_i, 32, k);
     }
     red[4 * C1_OUT + rtid] = bacc;
     named_bar_sync(3, 128);
@@ -286,7 +304,9 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
     for (int c = 0; c < C1_OUT; ++c) bacc[c] = 0.f;
     for (int k = 0; k < n_frames; ++k) {
       mbar_wait(bar(FB_MMA12), k & 1);
+      evt_mark(evt_i, 40, k);
       if (k >= 2) mbar_wait(bar(FB_DN1FREE + (k & 1)), ((k >> 1) - 1) & 1);   // conv11 UMMAs of frame k-2 (same buffer) retired
+      evt_mark(evt_i, 41, k);
       tc_fence_after();
       const uint32_t dbuf = dn1s + (k & 1) * DN1_BUF;
       uint16_t* dn1_dst = dn1_out ? dn1_out + frame_of(k) * (N1_POS * C1_OUT) : nullptr;
@@ -333,6 +353,7 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
         mbar_arrive(bar(FB_EPI12));
         mbar_arrive(bar(FB_DN1RDY + (k & 1)));
       }
+      evt_mark(evt_i, 42, k);
     }
     // conv11 bias gradient: warp-reduce the 16 channel sums, then add the four warps in order
 #pragma unroll
@@ -386,6 +407,7 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
     }
   }
 
+  evt_mark(evt_i, 52, 0);
   tc_fence_before();
   __syncthreads();
   trace_mark(K_CONV12_BWD, 2);
@@ -396,6 +418,7 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
 }
 
 GA3C_TRACE_ATTACH(trace_attach_conv_bwd_fused)
+GA3C_EVT_ATTACH(evt_attach_conv_bwd)
 
 int conv_bwd_grid(int batch, int num_sms) { return min(batch, num_sms); }
 

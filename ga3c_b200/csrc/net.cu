@@ -77,6 +77,7 @@ struct ga3c_net {
   int64_t launches = 0;
   int last_batch = 0;
   // per-kernel CUDA-event timing (ga3c_timing_*): record r uses events 2r (before) and 2r+1 (after)
+  unsigned long long* evt = nullptr;       // pipeline event log of CTA 0 (ga3c_evt_*), device memory
   unsigned long long* trace = nullptr;     // [K_COUNT][TRACE_SLOTS] globaltimer stamps (ga3c_trace_*), device memory
   std::vector<cudaEvent_t> tev;
   std::vector<int> tkid;
@@ -561,6 +562,31 @@ extern "C" int ga3c_trace_end(ga3c_net* n, uint64_t* stamps, int32_t n_kernels) 
   CK(cudaDeviceSynchronize());
   CKL(trace_attach_all(nullptr));
   CK(cudaMemcpy(stamps, n->trace, (size_t)K_COUNT * TRACE_SLOTS * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---- pipeline event log (debug) ----------------------------------------------------------------------
+extern "C" int ga3c_evt_begin(ga3c_net* n) {
+  if (!n) return fail_msg("ga3c_evt_begin: null handle");
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaDeviceSynchronize());
+  if (!n->evt) CK(cudaMalloc((void**)&n->evt, (size_t)2 * 16384 * 8));
+  CK(cudaMemset(n->evt, 0, (size_t)2 * 16384 * 8));
+  CKL(evt_attach_conv_bwd(n->evt));
+  return 0;
+}
+
+extern "C" int ga3c_evt_end(ga3c_net* n, uint64_t* records, int32_t cap, int32_t* count) {
+  if (!n || !records || !count || !n->evt || cap < 16384) return fail_msg("ga3c_evt_end: bad argument");
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaDeviceSynchronize());
+  CKL(evt_attach_conv_bwd(nullptr));
+  std::vector<uint64_t> all((size_t)2 * 16384);
+  CK(cudaMemcpy(all.data(), n->evt, all.size() * 8, cudaMemcpyDeviceToHost));
+  int32_t c = 0;
+  for (int i = 0; i < 16384; ++i)
+    if (all[2 * i] != 0) { records[2 * c] = all[2 * i]; records[2 * c + 1] = all[2 * i + 1]; ++c; }
+  *count = c;
   return 0;
 }
 

@@ -162,6 +162,12 @@ int ga3c_timing_collect(ga3c_net* net, double* total_ms, int64_t* counts, int32_
 int ga3c_trace_begin(ga3c_net* net, void* stream);
 int ga3c_trace_end(ga3c_net* net, uint64_t* stamps, int32_t n_kernels);
 
+/* ---- pipeline event log (debug) ----------------------------------------------------------------
+ * CTA 0 of the conv backward kernel appends {globaltimer ns, warp << 32 | event id << 16 | arg} records (two uint64
+ * each, at most 16384) between ga3c_evt_begin and ga3c_evt_end; tools/evt_timeline.py prints them per warp role. */
+int ga3c_evt_begin(ga3c_net* net);
+int ga3c_evt_end(ga3c_net* net, uint64_t* records, int32_t cap, int32_t* count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,33 @@
+"""Event log of CTA 0 of the conv backward kernel for one train step (ga3c_evt_*): per-role timeline in us.
+usage: python tools/evt_timeline.py [TB]"""
+import os, sys, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import ga3c_b200
+from ga3c_b200 import _capi
+
+NAMES = {1: "aux: next chunk", 2: "aux: WAR wait done", 3: "aux: chunk landed", 4: "aux: converted+armed",
+         10: "iss: conv12 begin", 11: "iss: C12RDY passed", 12: "iss: conv12 issued", 13: "iss: frame begin", 14: "iss: DN1RDY passed",
+         15: "iss: BLKRDY passed", 16: "iss: group issued", 20: "tma: raw issue", 30: "re: RAWFULL passed", 31: "re: EPI12 passed",
+         32: "re: done", 40: "epi: MMA12 passed", 41: "epi: DN1FREE passed", 42: "epi: done", 50: "prologue: at griddep_wait",
+         51: "prologue: done", 52: "role done"}
+tb = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+net = ga3c_b200.Network("gpu:0", "evt", 6, max_batch=tb, seed=1)
+dev = torch.device("cuda:0")
+xs = [(torch.randint(0, 256, (tb, 84 * 84 * 4), device=dev, dtype=torch.int32).float() / 128 - 1).contiguous() for _ in range(3)]
+yr = torch.rand(tb, device=dev) * 2 - 1
+a = torch.nn.functional.one_hot(torch.randint(0, 6, (tb,), device=dev), 6).float().contiguous()
+for i in range(10):
+    net.train_device(xs[i % 3], yr, a)
+torch.cuda.synchronize()
+lib = _capi.load()
+_capi.check(lib.ga3c_evt_begin(net._h), "evt_begin")
+net.train_device(xs[0], yr, a)
+buf = (C.c_uint64 * (2 * 16384))(); cnt = C.c_int32()
+_capi.check(lib.ga3c_evt_end(net._h, buf, 16384, C.byref(cnt)), "evt_end")
+recs = sorted((buf[2 * i], buf[2 * i + 1] >> 32, (buf[2 * i + 1] >> 16) & 0xFFFF, buf[2 * i + 1] & 0xFFFF) for i in range(cnt.value))
+t0 = recs[0][0]
+only = set(int(v) for v in os.environ.get("WARPS", "").split(",") if v)
+for t, w, e, arg in recs:
+    if only and w not in only: continue
+    print(f"{(t - t0) / 1e3:8.2f} us  warp {w:2d}  {NAMES.get(e, e):28s} {arg}")
