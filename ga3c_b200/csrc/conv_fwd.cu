@@ -26,8 +26,8 @@
 //   warps 0-5  (aux)  one independent pipeline per warp: chunk -> bf16 -> Blk, re-arm the slot with the warp's chunk after next
 //   warp  6           one thread issues the UMMAs: conv11 tile i as soon as its Blk rows are converted, conv12 after the
 //                     conv11 epilogues; tcgen05.commit signals TMEM-full / operand-free mbarriers
-//   warps 8-11        epilogues (one TMEM lane quarter each): conv11 tile -> +bias, ReLU -> im2col scatter (+ n1 to HBM when
-//                     training); conv12 tile -> +bias, ReLU -> n2 to HBM
+//   warps 8-15        epilogues, two sets of four warps (one TMEM lane quarter each): conv11 tile -> +bias, ReLU -> im2col
+//                     scatter (+ n1 to HBM when training); conv12 tile -> +bias, ReLU -> n2 to HBM
 #include "common.cuh"
 #include "kernels.h"
 #include "tcgen05.cuh"
@@ -35,7 +35,7 @@
 
 namespace ga3c {
 
-constexpr int CF_THREADS = 384, CF_AUX_WARPS = 6, CF_ISSUE_WARP = 6, CF_EPI_WARP0 = 8;
+constexpr int CF_THREADS = 512, CF_AUX_WARPS = 6, CF_ISSUE_WARP = 6, CF_EPI_WARP0 = 8;     // two epilogue sets: warps 8-11, 12-15
 static_assert(CF_EPI_WARP0 % 4 == 0, "epilogue warp e must own TMEM lane quarter e");
 constexpr int C11_TILES = 4;                     // 462 output rows (21 x 22, column 21 dead) in 4 x 128
 constexpr int C11_TSTRIDE = 127;                                     // output rows per tile (tile row 127 only feeds row 126)
@@ -59,8 +59,9 @@ constexpr int BAR_MMA2 = 25;         //      conv12 accumulated (tcgen05.commit)
 constexpr int BAR_T2FREE = 26;       //      conv12 TMEM tile drained, 4 arrivals           (epilogue -> issuer)
 constexpr int CF_NBAR = 27;
 constexpr int CF_OFF_TSLOT = CF_OFF_BAR + CF_NBAR * 8;               // 228,696
-constexpr int CF_OFF_XCH = CF_OFF_TSLOT + 16;                        // 228,712: [2][4 warps][16 floats] b-shift exchange across warps
-constexpr int CF_SMEM = CF_OFF_XCH + 512 + 1024;                     // 230,248 incl. slack to align the base to 1024 B
+constexpr int CF_OFF_XCH = CF_OFF_TSLOT + 16;                        // [2 sets][2][4 warps][16 floats] b-shift exchange across warps
+constexpr int CF_SMEM = CF_OFF_XCH + 1024 + 1024;                    // incl. slack to align the base to 1024 B
+static_assert(CF_SMEM <= 232448, "shared memory budget of one CTA per SM");
 constexpr int CF_TMEM_COLS = 256, TMEM_C12 = 128;                    // conv11 tiles at columns 0,32,64,96; conv12 at 128..159
 
 __global__ void __launch_bounds__(CF_THREADS, 1)
@@ -94,7 +95,7 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
       mbar_init(bar(BAR_C11 + i), 1);
       mbar_init(bar(BAR_T1FREE + i), 4);
     }
-    mbar_init(bar(BAR_A2RDY), 4);
+    mbar_init(bar(BAR_A2RDY), 8);
     mbar_init(bar(BAR_MMA2), 1);
     mbar_init(bar(BAR_T2FREE), 4);
     fence_mbar_init();
@@ -216,7 +217,9 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
     }
   } else if (warp >= CF_EPI_WARP0) {
     // =========================== epilogues ===========================
-    const int ew = warp - CF_EPI_WARP0;                              // TMEM lane quarter
+    // Two sets of four warps (one TMEM lane quarter each): set 0 drains conv11 tiles 0 and 2, set 1 the conv12 tile of the
+    // previous frame and conv11 tiles 1 and 3.  One set alone is the longest serial chain of the frame loop.
+    const int ew = warp & 3, eset = (warp - CF_EPI_WARP0) >> 2;      // TMEM lane quarter, epilogue set
     const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16);
     auto conv12_epilogue = [&](int k) {                              // TMEM -> +bias, ReLU, bf16 -> n2[frame k]
       mbar_wait(bar(BAR_MMA2), k & 1);
@@ -243,10 +246,13 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
       }
     };
     for (int k = 0; k < n_frames; ++k) {
-      if (k > 0) conv12_epilogue(k - 1);                             // also: the im2col operand of frame k-1 is no longer read
+      if (k > 0) {                                                   // the im2col operand of frame k-1 is no longer read
+        if (eset == 1) conv12_epilogue(k - 1);
+        else mbar_wait(bar(BAR_MMA2), (k - 1) & 1);
+      }
       uint16_t* n1_dst = n1_out ? n1_out + frame_of(k) * (N1_POS * C1_OUT) : nullptr;
 #pragma unroll 1
-      for (int i = 0; i < C11_TILES; ++i) {
+      for (int i = eset; i < C11_TILES; i += 2) {
         mbar_wait(bar(BAR_C11 + i), k & 1);
         tc_fence_after();
         uint32_t r[32];                                              // [0,16): b = 0 part of row m ; [16,32): b = 1 part, owed to row m-1
@@ -255,12 +261,12 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(BAR_T1FREE + i));
         // out[m] = D[m, 0:16] + D[m+1, 16:32]: the neighbour row is the next lane; lane 31 takes it from the next warp's lane 0
-        float* xch = reinterpret_cast<float*>(smem + CF_OFF_XCH) + (i & 1) * 64;
+        float* xch = reinterpret_cast<float*>(smem + CF_OFF_XCH) + eset * 128 + ((i >> 1) & 1) * 64;
         if (lane == 0) {
 #pragma unroll
           for (int c = 0; c < 16; ++c) xch[ew * 16 + c] = __uint_as_float(r[16 + c]);
         }
-        named_bar_sync(2, 128);
+        named_bar_sync(2 + eset, 128);
         float up[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) up[c] = __shfl_down_sync(0xffffffffu, __uint_as_float(r[16 + c]), 1);
@@ -298,7 +304,7 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(BAR_A2RDY));
     }
-    if (n_frames > 0) conv12_epilogue(n_frames - 1);
+    if (n_frames > 0 && eset == 1) conv12_epilogue(n_frames - 1);
   }
 
   tc_fence_before();
