@@ -164,7 +164,7 @@ __device__ __forceinline__ void griddep_wait(int kid) {
 static __device__ unsigned long long* g_evt = nullptr;
 constexpr unsigned int EVT_PER_WARP = 1024, EVT_WARPS = 16;
 __device__ __forceinline__ void evt_mark(unsigned int& i, int id, int arg) {
-  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+  if ((blockIdx.x == 0 || id == 65) && (threadIdx.x & 31) == 0) {
     unsigned long long* e = g_evt;
     if (e != nullptr && i < EVT_PER_WARP) {
       unsigned long long now;

@@ -235,16 +235,76 @@ __device__ __forceinline__ void st_flag(uint64_t* p, uint64_t v) {
 template <bool HAS_MOM>
 __global__ void __launch_bounds__(512) rmsprop_dp_kernel(RmsPropDpArgs d) {
   const RmsPropArgs& a = d.base;
+  unsigned int evt_i = 0;
   griddep_launch();
+  evt_mark(evt_i, 60, 0);
   griddep_wait(K_RMSPROP);      // the gradients come from the backward kernels that precede this one
+  evt_mark(evt_i, 61, 0);
   uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
-  if (blockIdx.x == 0 && threadIdx.x == 0) st_flag(reinterpret_cast<uint64_t*>(my_comm), d.step);   // my gradients are final
+  if (d.has_red) {
+    // phase 0: this rank's slabs -> its gradient arena (same order and bits as grad_reduce_kernel); the block that
+    // finishes last publishes "ready"
+    __shared__ float4 part[GR_LANES][GR_COLS];
+    __shared__ int last_red;
+    const GradReduceArgs& r = d.red;
+    const int col = threadIdx.x & (GR_COLS - 1), sl = threadIdx.x / GR_COLS;
+    const int n_cb = (r.n_floats / 4 + GR_COLS - 1) / GR_COLS;
+    for (int cb = blockIdx.x; cb < n_cb; cb += gridDim.x) {
+      const int j = (cb * GR_COLS + col) * 4;
+      int count = 0;
+      if (j < r.n_floats) {
+#pragma unroll
+        for (int s = GR_MAX_SEG - 1; s >= 0; --s)
+          if (j < r.seg_end[s]) count = r.seg_count[s];
+      }
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* src = r.part + j;
+      for (int i0 = sl; i0 < count; i0 += GR_UNROLL * GR_LANES) {
+        float4 q[GR_UNROLL];
+#pragma unroll
+        for (int u = 0; u < GR_UNROLL; ++u) {
+          const int i = i0 + u * GR_LANES;
+          q[u] = i < count ? __ldcg(reinterpret_cast<const float4*>(src + (int64_t)i * r.stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < GR_UNROLL; ++u) { acc.x += q[u].x; acc.y += q[u].y; acc.z += q[u].z; acc.w += q[u].w; }
+      }
+      part[sl][col] = acc;
+      __syncthreads();
+      if (sl == 0 && j < r.n_floats) {
+#pragma unroll
+        for (int l = 1; l < GR_LANES; ++l) {
+          const float4 q = part[l][col];
+          acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+        }
+        if (j < r.out_floats) *reinterpret_cast<float4*>(r.out + j) = acc;
+        else if (r.out_tail != nullptr) {
+          float* t = r.out_tail + (j - r.out_floats);
+          t[0] = acc.x; t[1] = acc.y; t[2] = acc.z; t[3] = acc.w;
+        }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      __threadfence_system();          // the reduced gradients are read by the peers
+      unsigned int* ctr = reinterpret_cast<unsigned int*>(my_comm + 132);
+      last_red = atomicAdd(ctr, 1u) == gridDim.x - 1;
+      if (last_red) {
+        *ctr = 0;
+        __threadfence_system();
+        st_flag(reinterpret_cast<uint64_t*>(my_comm), d.step);     // my gradients are final
+      }
+    }
+  } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st_flag(reinterpret_cast<uint64_t*>(my_comm), d.step);         // my gradients are final
+  }
   if ((int)threadIdx.x < d.world) {
     const uint64_t* f = reinterpret_cast<const uint64_t*>(d.peer[threadIdx.x] + d.comm_offset);
     while (ld_flag(f) < d.step) __nanosleep(32);
     __threadfence_system();
   }
   __syncthreads();
+  evt_mark(evt_i, 62, 0);
 
   const int64_t n4 = a.n_floats >> 2;
   const int64_t per = (n4 + d.world - 1) / d.world;
@@ -287,9 +347,11 @@ __global__ void __launch_bounds__(512) rmsprop_dp_kernel(RmsPropDpArgs d) {
 
   // publish "done" once the whole grid has stored its part, then hold the kernel open until every rank is done
   __shared__ int last;
+  evt_mark(evt_i, 63, 0);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();            // cumulative: orders the block's peer stores (observed through the barrier)
+    evt_mark(evt_i, 64, 0);
     unsigned int* ctr = reinterpret_cast<unsigned int*>(my_comm + 128);
     last = atomicAdd(ctr, 1u) == gridDim.x - 1;
     if (last) {
@@ -304,7 +366,11 @@ __global__ void __launch_bounds__(512) rmsprop_dp_kernel(RmsPropDpArgs d) {
     while (ld_flag(f) < d.step) __nanosleep(32);
     __threadfence_system();
   }
+  if (last) evt_mark(evt_i, 65, blockIdx.x);
+  trace_mark(K_RMSPROP, 2);
 }
+
+GA3C_EVT_ATTACH(evt_attach_elementwise)
 
 int launch_rmsprop_dp(const RmsPropDpArgs& d, int num_sms, cudaStream_t stream) {
   if (d.base.momentum != 0.f) return launch_pdl(rmsprop_dp_kernel<true>, dim3(num_sms), dim3(512), 0, stream, d);

@@ -14,6 +14,7 @@ int trace_attach_elementwise(unsigned long long* buf);
 
 // pipeline event log of CTA 0 (debug): attach a zeroed [16 warps][1024][2] uint64 buffer (or nullptr)
 int evt_attach_conv_bwd(unsigned long long* buf);
+int evt_attach_elementwise(unsigned long long* buf);
 
 // one-time per-process function-attribute setup (dynamic smem opt-in); returns cudaError_t as int
 int configure_conv_fwd();
@@ -102,6 +103,8 @@ struct RmsPropDpArgs {
   int rank, world;
   uint64_t step;                    // 1, 2, ... : value the ready / done flags reach in this step
   int64_t arena_bytes, comm_offset;
+  GradReduceArgs red;               // has_red: first sum this rank's gradient-partial slabs into its gradient arena
+  int has_red;                      // (saves the separate grad_reduce launch in front of the exchange)
 };
 int launch_rmsprop_dp(const RmsPropDpArgs& a, int num_sms, cudaStream_t stream);
 int launch_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cudaStream_t stream);

@@ -405,7 +405,7 @@ static RmsPropArgs rmsprop_args(ga3c_net* n, float lr) {
   return a;
 }
 
-extern "C" int ga3c_apply_rmsprop(ga3c_net* n, float lr, void* stream) {
+static int apply_rmsprop_impl(ga3c_net* n, float lr, void* stream, const GradReduceArgs* red) {
   if (!n) return fail_msg("ga3c_apply_rmsprop: null handle");
   CK(cudaSetDevice(n->cfg.device));
   RmsPropArgs a = rmsprop_args(n, lr);
@@ -417,6 +417,8 @@ extern "C" int ga3c_apply_rmsprop(ga3c_net* n, float lr, void* stream) {
     d.rank = n->dp_rank; d.world = n->dp_world; d.step = ++n->dp_step;
     d.arena_bytes = (int64_t)n->arena_floats * 4;
     d.comm_offset = 4 * d.arena_bytes + (int64_t)FLAT * FC * 2;
+    d.has_red = red != nullptr;
+    if (red) d.red = *red;
     LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_dp(d, n->num_sms, (cudaStream_t)stream));
   } else {
     LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop(a, (cudaStream_t)stream));
@@ -424,6 +426,8 @@ extern "C" int ga3c_apply_rmsprop(ga3c_net* n, float lr, void* stream) {
   n->global_step += 1;   // opt.minimize(..., global_step=self.global_step), NetworkVP_discrate.py:130
   return 0;
 }
+
+extern "C" int ga3c_apply_rmsprop(ga3c_net* n, float lr, void* stream) { return apply_rmsprop_impl(n, lr, stream, nullptr); }
 
 // ---- data parallel over CUDA IPC peer memory ---------------------------------------------------------
 extern "C" int ga3c_dp_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
@@ -471,9 +475,11 @@ extern "C" int ga3c_dp_attach(ga3c_net* n, int32_t rank, int32_t world, const vo
 
 extern "C" int ga3c_train_step(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch, float lr,
                                float beta, float* loss, void* stream) {
-  if (n && n->dp_world > 1) {     // peers read this rank's gradient arena: it must hold the reduced gradients
-    if (int r = ga3c_forward_backward(n, x, yr, a, batch, beta, loss, stream)) return r;
-    return ga3c_apply_rmsprop(n, lr, stream);
+  if (n && n->dp_world > 1) {     // peers read this rank's gradient arena: the exchange kernel first sums the slabs into it
+    if (int r = fb_head_impl(n, x, yr, a, batch, beta, loss, stream, false)) return r;
+    if (int r = fb_tail_impl(n, x, batch, stream, true, false)) return r;
+    const GradReduceArgs red = reduce_args(n, batch);
+    return apply_rmsprop_impl(n, lr, stream, &red);
   }
   // single GPU: the slab reduction rides in the optimizer launch
   if (int r = fb_head_impl(n, x, yr, a, batch, beta, loss, stream, false)) return r;
@@ -573,6 +579,7 @@ extern "C" int ga3c_evt_begin(ga3c_net* n) {
   if (!n->evt) CK(cudaMalloc((void**)&n->evt, (size_t)2 * 16384 * 8));
   CK(cudaMemset(n->evt, 0, (size_t)2 * 16384 * 8));
   CKL(evt_attach_conv_bwd(n->evt));
+  CKL(evt_attach_elementwise(n->evt));
   return 0;
 }
 
@@ -581,6 +588,7 @@ extern "C" int ga3c_evt_end(ga3c_net* n, uint64_t* records, int32_t cap, int32_t
   CK(cudaSetDevice(n->cfg.device));
   CK(cudaDeviceSynchronize());
   CKL(evt_attach_conv_bwd(nullptr));
+  CKL(evt_attach_elementwise(nullptr));
   std::vector<uint64_t> all((size_t)2 * 16384);
   CK(cudaMemcpy(all.data(), n->evt, all.size() * 8, cudaMemcpyDeviceToHost));
   int32_t c = 0;
