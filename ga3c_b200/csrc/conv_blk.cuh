@@ -76,4 +76,37 @@ __device__ __forceinline__ void blk_convert_rows4(uint32_t src, uint32_t blk, in
   }
 }
 
+// uint8 frames (F2 ingestion: the reference's `image.astype(np.float32) / 128.0 - 1.0`, Environment.py:60, done here): a
+// 4-row chunk is 1,344 B, one 32-bit load per pixel; x = k / 128 - 1 is exact in fp32 and in bf16.
+constexpr int PW_BYTES_U8 = PW_ROWS * IMG * 4;
+__device__ __forceinline__ void u8x4_to_bf16x4(uint32_t k4, uint32_t& lo, uint32_t& hi) {
+  // byte -> float through the 2^23 trick (0x4B000000 | k = 8388608 + k), then (k - 128) / 128
+  const float f0 = __uint_as_float(0x4B000000u | (k4 & 0xFFu)) - 8388608.f, f1 = __uint_as_float(0x4B000000u | ((k4 >> 8) & 0xFFu)) - 8388608.f,
+              f2 = __uint_as_float(0x4B000000u | ((k4 >> 16) & 0xFFu)) - 8388608.f, f3 = __uint_as_float(0x4B000000u | (k4 >> 24)) - 8388608.f;
+  lo = pack_bf16(fmaf(f0, 0.0078125f, -1.f), fmaf(f1, 0.0078125f, -1.f));
+  hi = pack_bf16(fmaf(f2, 0.0078125f, -1.f), fmaf(f3, 0.0078125f, -1.f));
+}
+template <int LBO>
+__device__ __forceinline__ void blk_convert_rows4_u8(uint32_t src, uint32_t blk, int c, int lane, const uint32_t (&lane_off)[3]) {
+  uint32_t k4[PW_ROWS][3];
+#pragma unroll
+  for (int rr = 0; rr < PW_ROWS; ++rr)
+#pragma unroll
+    for (int it = 0; it < 3; ++it)
+      if (lane + 32 * it < IMG) asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(k4[rr][it]) : "r"(src + (rr * IMG + lane + 32 * it) * 4));
+#pragma unroll
+  for (int rr = 0; rr < PW_ROWS; ++rr) {
+    const int py = c * PW_ROWS + rr + 2;
+    const uint32_t row_off = blk + (py & 3) * (2 * LBO) + (py >> 2) * (BLK_W * 16);
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+      if (lane + 32 * it < IMG) {
+        uint32_t lo, hi;
+        u8x4_to_bf16x4(k4[rr][it], lo, hi);
+        sts64(row_off + lane_off[it], lo, hi);
+      }
+    }
+  }
+}
+
 }  // namespace ga3c

@@ -79,8 +79,9 @@ constexpr int FB_SMEM = FB_OFF_TSLOT + 16 + 128;                 // incl. slack 
 static_assert(FB_SMEM <= 232448, "shared memory budget of one CTA per SM");
 constexpr int FB_TMEM_COLS = 512, TM_W11 = 0, TM_W12 = 64, TM_D12 = 192;   // 4x16 | 4x32 | 2x64 columns
 
+template <bool U8>       // U8: frames are uint8 [B,28224] (x = k/128 - 1 applied on the fly), else fp32
 __global__ void __launch_bounds__(FB_THREADS, 1)
-conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, const uint16_t* __restrict__ dn2,
+conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, const uint16_t* __restrict__ dn2,
                 const float* __restrict__ w12, uint16_t* __restrict__ dn1_out, float* __restrict__ g_w11,
                 float* __restrict__ g_b11, float* __restrict__ g_w12, float* __restrict__ g_b12, int64_t gp_stride, int batch) {
   extern __shared__ uint8_t smem_raw[];
@@ -99,9 +100,9 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
   auto bar = [&](int i) { return bars + i * 8; };
   auto issue_chunk = [&](int q, int slot) {                        // one thread
     const int k = q / PW_NCHUNK, c = q - k * PW_NCHUNK;
-    mbar_expect_tx(bar(FB_RING + slot), PW_BYTES);
-    bulk_load(ring + slot * PW_BYTES, reinterpret_cast<const uint8_t*>(x + frame_of(k) * STATE_DIM) + c * PW_BYTES, PW_BYTES,
-              bar(FB_RING + slot));
+    constexpr uint32_t bytes = U8 ? PW_BYTES_U8 : PW_BYTES;
+    mbar_expect_tx(bar(FB_RING + slot), bytes);
+    bulk_load(ring + slot * PW_BYTES, static_cast<const uint8_t*>(x) + (frame_of(k) * PW_NCHUNK + c) * bytes, bytes, bar(FB_RING + slot));
   };
 
   // ---------------- prologue ----------------
@@ -163,7 +164,8 @@ conv_bwd_kernel(const float* __restrict__ x, const uint16_t* __restrict__ n1, co
       evt_mark(evt_i, 2, q);
       mbar_wait(bar(FB_RING + slot), (j >> 1) & 1);
       evt_mark(evt_i, 3, q);
-      blk_convert_rows4<FBLK_LBO>(ring + slot * PW_BYTES, blk, c, lane, lane_off);
+      if (U8) blk_convert_rows4_u8<FBLK_LBO>(ring + slot * PW_BYTES, blk, c, lane, lane_off);
+      else blk_convert_rows4<FBLK_LBO>(ring + slot * PW_BYTES, blk, c, lane, lane_off);
       fence_proxy_async();                                         // Blk is read by the tensor core; the slot is refilled by the TMA
       __syncwarp();
       if (lane == 0) {
@@ -423,14 +425,19 @@ GA3C_EVT_ATTACH(evt_attach_conv_bwd)
 int conv_bwd_grid(int batch, int num_sms) { return min(batch, num_sms); }
 
 int configure_conv_bwd_fused() {
-  return (int)cudaFuncSetAttribute(conv_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(conv_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaFuncSetAttribute(conv_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
 }
 
-int launch_conv_bwd(const float* x, const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1_out,
+int launch_conv_bwd(const void* x, bool x_u8, const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1_out,
                     float* g_w11, float* g_b11, float* g_w12, float* g_b12, int64_t gp_stride, int batch, int num_sms,
                     cudaStream_t stream) {
-  return launch_pdl(conv_bwd_kernel, dim3(conv_bwd_grid(batch, num_sms)), dim3(FB_THREADS), FB_SMEM, stream, x, n1, dn2, w12,
-                    dn1_out, g_w11, g_b11, g_w12, g_b12, gp_stride, batch);
+  if (x_u8)
+    return launch_pdl(conv_bwd_kernel<true>, dim3(conv_bwd_grid(batch, num_sms)), dim3(FB_THREADS), FB_SMEM, stream, x, n1, dn2,
+                      w12, dn1_out, g_w11, g_b11, g_w12, g_b12, gp_stride, batch);
+  return launch_pdl(conv_bwd_kernel<false>, dim3(conv_bwd_grid(batch, num_sms)), dim3(FB_THREADS), FB_SMEM, stream, x, n1, dn2,
+                    w12, dn1_out, g_w11, g_b11, g_w12, g_b12, gp_stride, batch);
 }
 
 }  // namespace ga3c

@@ -64,8 +64,9 @@ constexpr int CF_SMEM = CF_OFF_XCH + 1024 + 1024;                    // incl. sl
 static_assert(CF_SMEM <= 232448, "shared memory budget of one CTA per SM");
 constexpr int CF_TMEM_COLS = 256, TMEM_C12 = 128;                    // conv11 tiles at columns 0,32,64,96; conv12 at 128..159
 
+template <bool U8>       // U8: frames are uint8 [B,28224] (x = k/128 - 1 applied on the fly), else fp32
 __global__ void __launch_bounds__(CF_THREADS, 1)
-conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, const float* __restrict__ b11,
+conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const float* __restrict__ b11,
                 const float* __restrict__ w12, const float* __restrict__ b12,
                 uint16_t* __restrict__ n1_out, uint16_t* __restrict__ n2_out, int batch) {
   extern __shared__ uint8_t smem_raw[];
@@ -82,9 +83,9 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
   auto bar = [&](int i) { return bars + i * 8; };
   auto issue_chunk = [&](int q, int slot) {                          // one thread
     const int k = q / PW_NCHUNK, c = q - k * PW_NCHUNK;
-    mbar_expect_tx(bar(BAR_RING + slot), PW_BYTES);
-    bulk_load(ring + slot * PW_BYTES, reinterpret_cast<const uint8_t*>(x + frame_of(k) * STATE_DIM) + c * PW_BYTES, PW_BYTES,
-              bar(BAR_RING + slot));
+    constexpr uint32_t bytes = U8 ? PW_BYTES_U8 : PW_BYTES;
+    mbar_expect_tx(bar(BAR_RING + slot), bytes);
+    bulk_load(ring + slot * PW_BYTES, static_cast<const uint8_t*>(x) + (frame_of(k) * PW_NCHUNK + c) * bytes, bytes, bar(BAR_RING + slot));
   };
 
   // ---------------- prologue ----------------
@@ -169,7 +170,8 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
       // block rows c, c+1 are rewritten: the last conv11 tile of frame k-1 that reads them must have completed
       if (k > 0) mbar_wait(bar(BAR_C11 + pw_last_consumer(c)), (k - 1) & 1);
       mbar_wait(bar(BAR_RING + slot), (j >> 1) & 1);                 // the chunk has landed
-      blk_convert_rows4<BLK_LBO>(ring + slot * PW_BYTES, blk, c, lane, lane_off);
+      if (U8) blk_convert_rows4_u8<BLK_LBO>(ring + slot * PW_BYTES, blk, c, lane, lane_off);
+      else blk_convert_rows4<BLK_LBO>(ring + slot * PW_BYTES, blk, c, lane, lane_off);
       fence_proxy_async();                                           // Blk is read by the tensor core; the slot is refilled by the TMA
       __syncwarp();
       if (lane == 0) {
@@ -319,13 +321,17 @@ conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w11, cons
 GA3C_TRACE_ATTACH(trace_attach_conv_fwd)
 
 int configure_conv_fwd() {
-  return (int)cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaFuncSetAttribute(conv_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM);
 }
 
-int launch_conv_fwd(const float* x, const float* w11, const float* b11, const float* w12, const float* b12,
+int launch_conv_fwd(const void* x, bool x_u8, const float* w11, const float* b11, const float* w12, const float* b12,
                     uint16_t* n1_out, uint16_t* n2_out, int batch, int num_sms, cudaStream_t stream) {
   const int grid = min(batch, num_sms);
-  return launch_pdl(conv_fwd_kernel, dim3(grid), dim3(CF_THREADS), CF_SMEM, stream, x, w11, b11, w12, b12, n1_out, n2_out, batch);
+  if (x_u8)
+    return launch_pdl(conv_fwd_kernel<true>, dim3(grid), dim3(CF_THREADS), CF_SMEM, stream, x, w11, b11, w12, b12, n1_out, n2_out, batch);
+  return launch_pdl(conv_fwd_kernel<false>, dim3(grid), dim3(CF_THREADS), CF_SMEM, stream, x, w11, b11, w12, b12, n1_out, n2_out, batch);
 }
 
 }  // namespace ga3c

@@ -21,8 +21,8 @@ int configure_conv_fwd();
 int configure_conv_bwd_fused();
 int configure_dense_tc();
 
-// conv_fwd.cu -- x fp32 [B,28224] -> n1 bf16 [B,441,16] (optional), n2 bf16 [B,3872]
-int launch_conv_fwd(const float* x, const float* w11, const float* b11, const float* w12, const float* b12,
+// conv_fwd.cu -- x fp32 (or uint8, x_u8: k/128 - 1 applied on the fly) [B,28224] -> n1 bf16 [B,441,16] (optional), n2 bf16 [B,3872]
+int launch_conv_fwd(const void* x, bool x_u8, const float* w11, const float* b11, const float* w12, const float* b12,
                     uint16_t* n1_out, uint16_t* n2_out, int batch, int num_sms, cudaStream_t stream);
 
 // dense_tc.cu -- the three dense1 GEMMs (NetworkDNav.py:90 and its autodiff) on tcgen05 / TMEM / TMA.  fwd leaves `splits` raw fp32 partial tiles
@@ -65,7 +65,7 @@ int launch_heads(const HeadsArgs& args, int num_sms, cudaStream_t stream);
 int conv_bwd_grid(int batch, int num_sms);       // CTAs (= slabs written) of both kernels
 // conv_bwd_fused.cu -- conv12 data gradient (dn1, kept on chip; dn1_out: optional copy for tests), conv12 and conv11
 // weight / bias gradients in one kernel on tcgen05
-int launch_conv_bwd(const float* x, const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1_out,
+int launch_conv_bwd(const void* x, bool x_u8, const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1_out,
                     float* g_w11, float* g_b11, float* g_w12, float* g_b12, int64_t gp_stride, int batch, int num_sms,
                     cudaStream_t stream);
 

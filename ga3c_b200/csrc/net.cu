@@ -305,13 +305,13 @@ static HeadsArgs heads_args(ga3c_net* n, int batch, int splits) {
   return h;
 }
 
-extern "C" int ga3c_predict(ga3c_net* n, const float* x, int32_t batch, float* p_out, float* v_out, void* stream) {
+static int predict_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, float* p_out, float* v_out, void* stream) {
   if (int r = check_batch(n, batch, "ga3c_predict")) return r;
   if (!x || !p_out || !v_out) return fail_msg("ga3c_predict: null buffer");
   CK(cudaSetDevice(n->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   const float* w = n->w;
-  LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
+  LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, x_u8, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
                                             w + n->off(P_C12B), nullptr, n->n2, batch, n->num_sms, st));
   const int splits = dense_fwd_splits(batch, n->num_sms);
   LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
@@ -322,10 +322,17 @@ extern "C" int ga3c_predict(ga3c_net* n, const float* x, int32_t batch, float* p
   return 0;
 }
 
+extern "C" int ga3c_predict(ga3c_net* n, const float* x, int32_t batch, float* p_out, float* v_out, void* stream) {
+  return predict_impl(n, x, false, batch, p_out, v_out, stream);
+}
+extern "C" int ga3c_predict_u8(ga3c_net* n, const uint8_t* x, int32_t batch, float* p_out, float* v_out, void* stream) {
+  return predict_impl(n, x, true, batch, p_out, v_out, stream);
+}
+
 // forward, fused loss forward/backward, and the dense1 weight gradient: on return (in stream order) the
 // gradients of dense1/w, dense1/b, logits_v/*, logits_p/* are final, so their allreduce can start while
 // ga3c_fb_tail computes the conv gradients.
-static int fb_head_impl(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch, float beta,
+static int fb_head_impl(ga3c_net* n, const void* x, bool x_u8, const float* yr, const float* a, int32_t batch, float beta,
                         float* loss, void* stream, bool with_wgrad) {
   if (int r = check_batch(n, batch, "ga3c_fb_head")) return r;
   if (!x || !yr || !a) return fail_msg("ga3c_fb_head: null buffer");
@@ -334,7 +341,7 @@ static int fb_head_impl(ga3c_net* n, const float* x, const float* yr, const floa
   const float* w = n->w;
   float* g = n->g;
   float* gp = n->gpart;       // small-tensor gradients: per-CTA partial slabs, summed at the end of ga3c_fb_tail
-  LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
+  LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, x_u8, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
                                             w + n->off(P_C12B), n->n1, n->n2, batch, n->num_sms, st));
   const int splits = dense_fwd_splits(batch, n->num_sms);
   LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
@@ -352,7 +359,7 @@ static int fb_head_impl(ga3c_net* n, const float* x, const float* yr, const floa
 
 extern "C" int ga3c_fb_head(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch, float beta,
                             float* loss, void* stream) {
-  return fb_head_impl(n, x, yr, a, batch, beta, loss, stream, true);
+  return fb_head_impl(n, x, false, yr, a, batch, beta, loss, stream, true);
 }
 
 // sum of the per-CTA slabs: conv tensors (the first four of the arena) over the conv grids, head tensors and the loss
@@ -368,7 +375,7 @@ static GradReduceArgs reduce_args(ga3c_net* n, int batch) {
 
 // dense1 data gradient and the two conv backward kernels; with `reduce` the slabs are summed into the gradient arena
 // (conv11/*, conv12/*, dense1/b, heads, loss sums), otherwise the caller does it (fused with RMSProp).
-static int fb_tail_impl(ga3c_net* n, const float* x, int32_t batch, void* stream, bool with_wgrad, bool reduce) {
+static int fb_tail_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, void* stream, bool with_wgrad, bool reduce) {
   if (int r = check_batch(n, batch, "ga3c_fb_tail")) return r;
   if (!x) return fail_msg("ga3c_fb_tail: null buffer");
   if (batch != n->last_batch) return fail_msg("ga3c_fb_tail: batch differs from the preceding ga3c_fb_head");
@@ -380,7 +387,7 @@ static int fb_tail_impl(ga3c_net* n, const float* x, int32_t batch, void* stream
     LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_bwd_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, n->g + n->off(P_D1W), batch, st));
   else
     LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
-  LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(x, n->n1, n->dn2, w + n->off(P_C12W), n->keep_dn1 ? n->dn1 : nullptr,
+  LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(x, x_u8, n->n1, n->dn2, w + n->off(P_C12W), n->keep_dn1 ? n->dn1 : nullptr,
                                               gp + n->off(P_C11W), gp + n->off(P_C11B), gp + n->off(P_C12W),
                                               gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, st));
   if (reduce) LAUNCH(n, K_GRAD_REDUCE, st, launch_grad_reduce(reduce_args(n, batch), st));
@@ -388,13 +395,28 @@ static int fb_tail_impl(ga3c_net* n, const float* x, int32_t batch, void* stream
 }
 
 extern "C" int ga3c_fb_tail(ga3c_net* n, const float* x, int32_t batch, void* stream) {
-  return fb_tail_impl(n, x, batch, stream, false, true);
+  return fb_tail_impl(n, x, false, batch, stream, false, true);
 }
 
+static int forward_backward_impl(ga3c_net* n, const void* x, bool x_u8, const float* yr, const float* a, int32_t batch,
+                                 float beta, float* loss, void* stream) {
+  if (int r = fb_head_impl(n, x, x_u8, yr, a, batch, beta, loss, stream, false)) return r;
+  return fb_tail_impl(n, x, x_u8, batch, stream, true, true);
+}
 extern "C" int ga3c_forward_backward(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch,
                                      float beta, float* loss, void* stream) {
-  if (int r = fb_head_impl(n, x, yr, a, batch, beta, loss, stream, false)) return r;
-  return fb_tail_impl(n, x, batch, stream, true, true);
+  return forward_backward_impl(n, x, false, yr, a, batch, beta, loss, stream);
+}
+extern "C" int ga3c_forward_backward_u8(ga3c_net* n, const uint8_t* x, const float* yr, const float* a, int32_t batch,
+                                        float beta, float* loss, void* stream) {
+  return forward_backward_impl(n, x, true, yr, a, batch, beta, loss, stream);
+}
+extern "C" int ga3c_fb_head_u8(ga3c_net* n, const uint8_t* x, const float* yr, const float* a, int32_t batch, float beta,
+                               float* loss, void* stream) {
+  return fb_head_impl(n, x, true, yr, a, batch, beta, loss, stream, true);
+}
+extern "C" int ga3c_fb_tail_u8(ga3c_net* n, const uint8_t* x, int32_t batch, void* stream) {
+  return fb_tail_impl(n, x, true, batch, stream, false, true);
 }
 
 static RmsPropArgs rmsprop_args(ga3c_net* n, float lr) {
@@ -473,20 +495,25 @@ extern "C" int ga3c_dp_attach(ga3c_net* n, int32_t rank, int32_t world, const vo
   return 0;
 }
 
-extern "C" int ga3c_train_step(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch, float lr,
-                               float beta, float* loss, void* stream) {
-  if (n && n->dp_world > 1) {     // peers read this rank's gradient arena: the exchange kernel first sums the slabs into it
-    if (int r = fb_head_impl(n, x, yr, a, batch, beta, loss, stream, false)) return r;
-    if (int r = fb_tail_impl(n, x, batch, stream, true, false)) return r;
-    const GradReduceArgs red = reduce_args(n, batch);
+static int train_step_impl(ga3c_net* n, const void* x, bool x_u8, const float* yr, const float* a, int32_t batch, float lr,
+                           float beta, float* loss, void* stream) {
+  if (int r = fb_head_impl(n, x, x_u8, yr, a, batch, beta, loss, stream, false)) return r;
+  if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, false)) return r;
+  const GradReduceArgs red = reduce_args(n, batch);
+  if (n->dp_world > 1)            // peers read this rank's gradient arena: the exchange kernel first sums the slabs into it
     return apply_rmsprop_impl(n, lr, stream, &red);
-  }
   // single GPU: the slab reduction rides in the optimizer launch
-  if (int r = fb_head_impl(n, x, yr, a, batch, beta, loss, stream, false)) return r;
-  if (int r = fb_tail_impl(n, x, batch, stream, true, false)) return r;
-  LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_reduce(rmsprop_args(n, lr), reduce_args(n, batch), (cudaStream_t)stream));
+  LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_reduce(rmsprop_args(n, lr), red, (cudaStream_t)stream));
   n->global_step += 1;   // opt.minimize(..., global_step=self.global_step), NetworkVP_discrate.py:130
   return 0;
+}
+extern "C" int ga3c_train_step(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch, float lr,
+                               float beta, float* loss, void* stream) {
+  return train_step_impl(n, x, false, yr, a, batch, lr, beta, loss, stream);
+}
+extern "C" int ga3c_train_step_u8(ga3c_net* n, const uint8_t* x, const float* yr, const float* a, int32_t batch, float lr,
+                                  float beta, float* loss, void* stream) {
+  return train_step_impl(n, x, true, yr, a, batch, lr, beta, loss, stream);
 }
 
 extern "C" int ga3c_returns(const double* rewards, const int64_t* seg, int32_t n_segments, const double* terminal,

@@ -150,6 +150,27 @@ class Network:
             self._dp_out = torch.empty((rows, a), dtype=torch.float32, device=self._tdev)
             self._dv_out = torch.empty((rows,), dtype=torch.float32, device=self._tdev)
         self._io_rows = rows
+        self._hx8 = self._dx8 = None          # uint8 frame staging, allocated on first use (F2 ingestion)
+
+    def _io_u8(self):
+        if self._hx8 is None or self._hx8.shape[0] < self._io_rows:
+            with torch.cuda.device(self._tdev):
+                self._hx8 = torch.empty((self._io_rows, STATE_DIM), dtype=torch.uint8, pin_memory=True)
+                self._dx8 = torch.empty((self._io_rows, STATE_DIM), dtype=torch.uint8, device=self._tdev)
+        return self._hx8, self._dx8
+
+    @staticmethod
+    def _frames(x, state_dim):
+        """Frames as handed over: float32 [B, state_dim] (the reference contract), or uint8 [B, state_dim] raw pixels
+        (F2 ingestion: x = k/128 - 1, Environment.py:60, is applied on the GPU; outputs are bit-identical)."""
+        x = np.asarray(x)
+        if x.dtype != np.uint8:
+            x = np.asarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != state_dim:
+            x = x.reshape(x.shape[0], -1)
+            if x.shape[1] != state_dim:
+                raise ValueError(f"x must be [B, {state_dim}], got {x.shape}")
+        return x
 
     def _ensure(self, rows: int):
         if rows > self._max_batch:
@@ -188,8 +209,8 @@ class Network:
         if v_out is None:
             v_out = torch.empty((b,), dtype=torch.float32, device=self._tdev)
         st = stream or torch.cuda.current_stream(self._tdev)
-        _capi.check(self._lib.ga3c_predict(self._h, x_dev.data_ptr(), b, p_out.data_ptr(), v_out.data_ptr(),
-                                           st.cuda_stream), "ga3c_predict")
+        fn = self._lib.ga3c_predict_u8 if x_dev.dtype == torch.uint8 else self._lib.ga3c_predict
+        _capi.check(fn(self._h, x_dev.data_ptr(), b, p_out.data_ptr(), v_out.data_ptr(), st.cuda_stream), "ga3c_predict")
         return p_out, v_out
 
     def train_device(self, x_dev, yr_dev, a_dev, *, loss_out: torch.Tensor = None, stream=None):
@@ -198,18 +219,21 @@ class Network:
         self._ensure(b)
         st = stream or torch.cuda.current_stream(self._tdev)
         loss_ptr = loss_out.data_ptr() if loss_out is not None else None
+        u8 = x_dev.dtype == torch.uint8
         if not self._dp:
-            # single GPU: one call; the gradient-slab reduction is fused into the RMSProp launch
-            _capi.check(self._lib.ga3c_train_step(self._h, x_dev.data_ptr(), yr_dev.data_ptr(), a_dev.data_ptr(), b,
-                                                  float(self.learning_rate), float(self.beta), loss_ptr, st.cuda_stream),
-                        "ga3c_train_step")
+            # single GPU / fused data parallel: one call; the gradient-slab reduction rides in the optimizer launch
+            fn = self._lib.ga3c_train_step_u8 if u8 else self._lib.ga3c_train_step
+            _capi.check(fn(self._h, x_dev.data_ptr(), yr_dev.data_ptr(), a_dev.data_ptr(), b, float(self.learning_rate),
+                           float(self.beta), loss_ptr, st.cuda_stream), "ga3c_train_step")
             return
         else:
             # dense1/w (98.8 % of the arena) is final after the head: its allreduce overlaps the conv backward
-            _capi.check(self._lib.ga3c_fb_head(self._h, x_dev.data_ptr(), yr_dev.data_ptr(), a_dev.data_ptr(), b,
-                                               float(self.beta), loss_ptr, st.cuda_stream), "ga3c_fb_head")
+            head = self._lib.ga3c_fb_head_u8 if u8 else self._lib.ga3c_fb_head
+            tail = self._lib.ga3c_fb_tail_u8 if u8 else self._lib.ga3c_fb_tail
+            _capi.check(head(self._h, x_dev.data_ptr(), yr_dev.data_ptr(), a_dev.data_ptr(), b,
+                             float(self.beta), loss_ptr, st.cuda_stream), "ga3c_fb_head")
             self._allreduce.start_big(st)
-            _capi.check(self._lib.ga3c_fb_tail(self._h, x_dev.data_ptr(), b, st.cuda_stream), "ga3c_fb_tail")
+            _capi.check(tail(self._h, x_dev.data_ptr(), b, st.cuda_stream), "ga3c_fb_tail")
             self._allreduce.finish(st)
         _capi.check(self._lib.ga3c_apply_rmsprop(self._h, float(self.learning_rate), st.cuda_stream), "ga3c_apply_rmsprop")
 
@@ -217,18 +241,20 @@ class Network:
     def predict_p_and_v(self, x):
         """NetworkVP.py:248-252.  x: float32 [B, state_dim] (a view of the predictor's reused buffer,
         ThreadPredictor.py:57 -- consumed before returning).  Returns [p [B,A] f32, v [B] f32]."""
-        x = np.asarray(x, dtype=np.float32)
+        x = np.asarray(x)
         if x.ndim != 2 or x.shape[1] != self.state_dim:
             raise ValueError(f"x must be [B, {self.state_dim}], got {x.shape}")
+        x = self._frames(x, self.state_dim)
         b = x.shape[0]
         if b == 0:
             return [np.zeros((0, self.num_actions), np.float32), np.zeros((0,), np.float32)]
         with self._lock:
             self._ensure(b)
-            src = self._stage(x, self._hx, b)
+            hx, dx = self._io_u8() if x.dtype == np.uint8 else (self._hx, self._dx)
+            src = self._stage(x, hx, b)
             with torch.cuda.stream(self._stream):
-                self._dx[:b].copy_(src, non_blocking=True)
-                self.predict_device(self._dx[:b], self._dp_out[:b], self._dv_out[:b], stream=self._stream)
+                dx[:b].copy_(src, non_blocking=True)
+                self.predict_device(dx[:b], self._dp_out[:b], self._dv_out[:b], stream=self._stream)
                 self._hp[:b].copy_(self._dp_out[:b], non_blocking=True)
                 self._hv[:b].copy_(self._dv_out[:b], non_blocking=True)
             self._stream.synchronize()
@@ -246,22 +272,24 @@ class Network:
     def train(self, x, y_r, a, x2=None, done=None, trainer_id=0, *, fetch_losses=False):
         """NetworkVP.py:254-257.  x2, done, trainer_id are accepted and ignored exactly as the A3C
         networks of the reference ignore them; y_r may arrive as float64 (ProcessAgent.py:99)."""
-        x = np.asarray(x, dtype=np.float32)
+        x = np.asarray(x)
         b = x.shape[0]
         if b == 0:
             return None
+        x = self._frames(x, self.state_dim)
         y_r = np.asarray(y_r, dtype=np.float32).reshape(b)
         a = np.asarray(a, dtype=np.float32).reshape(b, self.num_actions)
         with self._lock:
             self._ensure(b)
-            sx = self._stage(x.reshape(b, self.state_dim), self._hx, b)
+            hx, dx = self._io_u8() if x.dtype == np.uint8 else (self._hx, self._dx)
+            sx = self._stage(x, hx, b)
             syr = self._stage(y_r, self._hyr, b)
             sa = self._stage(a, self._ha, b)
             with torch.cuda.stream(self._stream):
-                self._dx[:b].copy_(sx, non_blocking=True)
+                dx[:b].copy_(sx, non_blocking=True)
                 self._dyr[:b].copy_(syr, non_blocking=True)
                 self._da[:b].copy_(sa, non_blocking=True)
-                self.train_device(self._dx[:b], self._dyr[:b], self._da[:b],
+                self.train_device(dx[:b], self._dyr[:b], self._da[:b],
                                   loss_out=self._loss_dev if fetch_losses else None, stream=self._stream)
                 losses = self._loss_dev.cpu() if fetch_losses else None
             self._stream.synchronize()
@@ -274,18 +302,18 @@ class Network:
     def losses(self, x, y_r, a):
         """Forward + loss only (what `log` evaluates, NetworkVP.py:259-265), without touching the weights:
         runs forward_backward and discards the gradients."""
-        x = np.asarray(x, dtype=np.float32)
+        x = self._frames(x, self.state_dim)
         b = x.shape[0]
         with self._lock:
             self._ensure(b)
             st = self._stream
             with torch.cuda.stream(st):
-                dx = torch.as_tensor(x.reshape(b, self.state_dim), device=self._tdev)
+                dx = torch.as_tensor(x, device=self._tdev)
                 dyr = torch.as_tensor(np.asarray(y_r, dtype=np.float32).reshape(b), device=self._tdev)
                 da = torch.as_tensor(np.asarray(a, dtype=np.float32).reshape(b, self.num_actions), device=self._tdev)
-                _capi.check(self._lib.ga3c_forward_backward(self._h, dx.data_ptr(), dyr.data_ptr(), da.data_ptr(), b,
-                                                            float(self.beta), self._loss_dev.data_ptr(), st.cuda_stream),
-                            "ga3c_forward_backward")
+                fn = self._lib.ga3c_forward_backward_u8 if x.dtype == np.uint8 else self._lib.ga3c_forward_backward
+                _capi.check(fn(self._h, dx.data_ptr(), dyr.data_ptr(), da.data_ptr(), b, float(self.beta),
+                               self._loss_dev.data_ptr(), st.cuda_stream), "ga3c_forward_backward")
                 l = self._loss_dev.cpu()
             st.synchronize()
         c1, c2, cv = (float(v) for v in l[:3])

@@ -94,6 +94,20 @@ int ga3c_apply_rmsprop(ga3c_net* net, float learning_rate, void* stream);
 int ga3c_train_step(ga3c_net* net, const float* x_dev, const float* yr_dev, const float* a_dev,
                     int32_t batch, float learning_rate, float beta, float* loss_dev, void* stream);
 
+/* ---- uint8 frame ingestion ---------------------------------------------------------
+ * Same calls with x8_dev = uint8 [B, 28224]: the raw 0..255 pixels BEFORE the reference's
+ * `image.astype(np.float32) / 128.0 - 1.0` (Environment.py:60).  The kernels apply x = k/128 - 1 while converting to
+ * bf16 (exact), so every output is bit-identical to the fp32 call on the normalised frames, with 4x fewer host->device
+ * and HBM input bytes.  An extension of the reference contract (its queues carry float32 states): see INTEGRATION.md. */
+int ga3c_predict_u8(ga3c_net* net, const uint8_t* x8_dev, int32_t batch, float* p_dev, float* v_dev, void* stream);
+int ga3c_forward_backward_u8(ga3c_net* net, const uint8_t* x8_dev, const float* yr_dev, const float* a_dev,
+                             int32_t batch, float beta, float* loss_dev, void* stream);
+int ga3c_fb_head_u8(ga3c_net* net, const uint8_t* x8_dev, const float* yr_dev, const float* a_dev, int32_t batch, float beta,
+                    float* loss_dev, void* stream);
+int ga3c_fb_tail_u8(ga3c_net* net, const uint8_t* x8_dev, int32_t batch, void* stream);
+int ga3c_train_step_u8(ga3c_net* net, const uint8_t* x8_dev, const float* yr_dev, const float* a_dev,
+                       int32_t batch, float learning_rate, float beta, float* loss_dev, void* stream);
+
 /* ---- data parallel over peer memory (one process per GPU, one node, <= 8 ranks) ---------------------
  * Every rank exports a CUDA IPC handle of its state slab (ga3c_dp_export), the host exchanges the handles
  * (torch.distributed all_gather in ga3c_b200.Network) and attaches them in rank order (ga3c_dp_attach).  From

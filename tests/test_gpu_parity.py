@@ -287,6 +287,34 @@ def test_train_step_is_bit_reproducible_b1024(ga3c):
         assert np.array_equal(g0[k], g1[k]), k
 
 
+def test_uint8_frames_match_normalised_fp32_bit_for_bit(ga3c):
+    """F2 ingestion: uint8 pixels k handed over as they are, x = k/128 - 1 (Environment.py:60) applied in the
+    kernels' fp32 -> bf16 conversion.  The normalisation is exact, so predictions, losses, gradients and the updated
+    weights equal the fp32 path on the normalised frames bit for bit (and therefore match the oracle as it does)."""
+    rng = np.random.default_rng(77)
+    params = onp.init_params(rng, 6)
+    b = 37
+    k = rng.integers(0, 256, size=(b, 84 * 84 * 4), dtype=np.uint8)
+    x = k.astype(np.float32) / 128.0 - 1.0
+    y_r, a = onp.synth_targets(rng, b)
+    nets = []
+    for frames in (x, k):
+        net = ga3c.Network("gpu:0", "t", 6, max_batch=64)
+        net.set_variables(params)
+        p, v = net.predict_p_and_v(frames)
+        l = net.losses(frames, y_r, a)
+        g = net.get_gradients()
+        net.train(frames, y_r, a, None, None, 0)
+        nets.append((p, v, l, g, net.get_variables()))
+    (p0, v0, l0, g0, w0), (p1, v1, l1, g1, w1) = nets
+    assert np.array_equal(p0, p1) and np.array_equal(v0, v1) and l0 == l1
+    for name in g0:
+        assert np.array_equal(g0[name], g1[name]), name
+        assert np.array_equal(w0[name], w1[name]), name
+    pr, vr = onp.forward(params, x, quant="bf16")
+    assert np.abs(p1 - pr).max() <= TOL_P and np.abs(v1 - vr).max() <= TOL_V
+
+
 def test_workspace_grows_for_unbounded_train_batches(ga3c):
     """ThreadTrainer concatenates agent batches without bound (ThreadTrainer.py:48-59)."""
     params, x, y_r, a = make_case(40)
