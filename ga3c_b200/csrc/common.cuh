@@ -163,16 +163,23 @@ __device__ __forceinline__ void griddep_wait(int kid) {
 // to the warp's own region of the buffer with plain stores (index in a register: no atomics, nothing to wait for)
 static __device__ unsigned long long* g_evt = nullptr;
 constexpr unsigned int EVT_PER_WARP = 1024, EVT_WARPS = 16;
-__device__ __forceinline__ void evt_mark(unsigned int& i, int id, int arg) {
-  if ((blockIdx.x == 0 || id == 65) && (threadIdx.x & 31) == 0) {
-    unsigned long long* e = g_evt;
-    if (e != nullptr && i < EVT_PER_WARP) {
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(now));
-      const unsigned int slot = (threadIdx.x >> 5) * EVT_PER_WARP + i++;
-      e[2 * slot] = now;
-      e[2 * slot + 1] = ((unsigned long long)(threadIdx.x >> 5) << 32) | ((unsigned long long)id << 16) | (unsigned long long)(arg & 0xFFFF);
-    }
+struct EvtLog {                      // per-thread cursor; `base` is read ONCE (a load per mark would sit on CTA 0's critical path)
+  unsigned long long* base;
+  unsigned int i;
+};
+__device__ __forceinline__ EvtLog evt_open() {
+  EvtLog l;
+  l.base = (blockIdx.x == 0 && (threadIdx.x & 31) == 0) ? g_evt : nullptr;
+  l.i = 0;
+  return l;
+}
+__device__ __forceinline__ void evt_mark(EvtLog& l, int id, int arg) {
+  if (l.base != nullptr && l.i < EVT_PER_WARP) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(now));
+    const unsigned int slot = (threadIdx.x >> 5) * EVT_PER_WARP + l.i++;
+    l.base[2 * slot] = now;
+    l.base[2 * slot + 1] = ((unsigned long long)(threadIdx.x >> 5) << 32) | ((unsigned long long)id << 16) | (unsigned long long)(arg & 0xFFFF);
   }
 }
 #define GA3C_EVT_ATTACH(fn) \

@@ -49,33 +49,6 @@ __host__ __device__ constexpr int pw_group_chunks(int i) { return i == 0 ? 7 : i
 // ... and last group of the PREVIOUS frame that still reads block rows c, c+1 (they are about to be rewritten)
 __device__ __forceinline__ int pw_last_consumer(int c) { return c >= 16 ? 3 : c >= 10 ? 2 : c >= 4 ? 1 : 0; }
 
-// one warp: 4-row fp32 chunk (staging slot `src`) -> bf16 -> Blk, two rows at a time (24 registers of loads in flight)
-template <int LBO>
-__device__ __forceinline__ void blk_convert_rows4(uint32_t src, uint32_t blk, int c, int lane, const uint32_t (&lane_off)[3]) {
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t px4[2][3][4];
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-      for (int it = 0; it < 3; ++it)
-        if (lane + 32 * it < IMG) lds128(px4[rr][it], src + ((2 * half + rr) * IMG + lane + 32 * it) * 16);
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int py = c * PW_ROWS + 2 * half + rr + 2;              // padded row -> block row Y = py >> 2, dy = py & 3
-      const uint32_t row_off = blk + (py & 3) * (2 * LBO) + (py >> 2) * (BLK_W * 16);
-#pragma unroll
-      for (int it = 0; it < 3; ++it) {
-        if (lane + 32 * it < IMG) {
-          const uint32_t* r = px4[rr][it];
-          sts64(row_off + lane_off[it], pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1])),
-                pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3])));
-        }
-      }
-    }
-  }
-}
-
 // uint8 frames (F2 ingestion: the reference's `image.astype(np.float32) / 128.0 - 1.0`, Environment.py:60, done here): a
 // 4-row chunk is 1,344 B, one 32-bit load per pixel; x = k / 128 - 1 is exact in fp32 and in bf16.
 constexpr int PW_BYTES_U8 = PW_ROWS * IMG * 4;
@@ -86,26 +59,54 @@ __device__ __forceinline__ void u8x4_to_bf16x4(uint32_t k4, uint32_t& lo, uint32
   lo = pack_bf16(fmaf(f0, 0.0078125f, -1.f), fmaf(f1, 0.0078125f, -1.f));
   hi = pack_bf16(fmaf(f2, 0.0078125f, -1.f), fmaf(f3, 0.0078125f, -1.f));
 }
+
+// One warp, one 4-row chunk, in two phases so that the ring slot can be re-armed (and the Blk rows' previous readers
+// awaited) BETWEEN them: load + convert into 24 registers of packed bf16 (the slot is free afterwards), then store into Blk.
+template <bool U8>
+__device__ __forceinline__ void blk_load_rows4(uint32_t src, int lane, uint32_t (&pk)[PW_ROWS][3][2]) {
+  if (U8) {
+    uint32_t k4[PW_ROWS][3];
+#pragma unroll
+    for (int rr = 0; rr < PW_ROWS; ++rr)
+#pragma unroll
+      for (int it = 0; it < 3; ++it)
+        if (lane + 32 * it < IMG) asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(k4[rr][it]) : "r"(src + (rr * IMG + lane + 32 * it) * 4));
+#pragma unroll
+    for (int rr = 0; rr < PW_ROWS; ++rr)
+#pragma unroll
+      for (int it = 0; it < 3; ++it)
+        if (lane + 32 * it < IMG) u8x4_to_bf16x4(k4[rr][it], pk[rr][it][0], pk[rr][it][1]);
+  } else {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {                          // two rows at a time: 24 registers of loads in flight
+      uint32_t px4[2][3][4];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int it = 0; it < 3; ++it)
+          if (lane + 32 * it < IMG) lds128(px4[rr][it], src + ((2 * half + rr) * IMG + lane + 32 * it) * 16);
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int it = 0; it < 3; ++it)
+          if (lane + 32 * it < IMG) {
+            const uint32_t* r = px4[rr][it];
+            pk[2 * half + rr][it][0] = pack_bf16(__uint_as_float(r[0]), __uint_as_float(r[1]));
+            pk[2 * half + rr][it][1] = pack_bf16(__uint_as_float(r[2]), __uint_as_float(r[3]));
+          }
+    }
+  }
+}
 template <int LBO>
-__device__ __forceinline__ void blk_convert_rows4_u8(uint32_t src, uint32_t blk, int c, int lane, const uint32_t (&lane_off)[3]) {
-  uint32_t k4[PW_ROWS][3];
-#pragma unroll
-  for (int rr = 0; rr < PW_ROWS; ++rr)
-#pragma unroll
-    for (int it = 0; it < 3; ++it)
-      if (lane + 32 * it < IMG) asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(k4[rr][it]) : "r"(src + (rr * IMG + lane + 32 * it) * 4));
+__device__ __forceinline__ void blk_store_rows4(uint32_t blk, int c, int lane, const uint32_t (&lane_off)[3],
+                                                const uint32_t (&pk)[PW_ROWS][3][2]) {
 #pragma unroll
   for (int rr = 0; rr < PW_ROWS; ++rr) {
-    const int py = c * PW_ROWS + rr + 2;
+    const int py = c * PW_ROWS + rr + 2;                           // padded row -> block row Y = py >> 2, dy = py & 3
     const uint32_t row_off = blk + (py & 3) * (2 * LBO) + (py >> 2) * (BLK_W * 16);
 #pragma unroll
-    for (int it = 0; it < 3; ++it) {
-      if (lane + 32 * it < IMG) {
-        uint32_t lo, hi;
-        u8x4_to_bf16x4(k4[rr][it], lo, hi);
-        sts64(row_off + lane_off[it], lo, hi);
-      }
-    }
+    for (int it = 0; it < 3; ++it)
+      if (lane + 32 * it < IMG) sts64(row_off + lane_off[it], pk[rr][it][0], pk[rr][it][1]);
   }
 }
 

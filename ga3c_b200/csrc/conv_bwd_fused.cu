@@ -92,7 +92,7 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
                  tslot = sbase + FB_OFF_TSLOT;
   float* red = reinterpret_cast<float*>(smem + FB_OFF_RED);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  unsigned int evt_i = 0;                                          // event-log cursor (ga3c_evt_*; dead code unless attached)
+  EvtLog evt_i = evt_open();                                      // pipeline event log of CTA 0 (ga3c_evt_*), off unless attached
   const int stride = gridDim.x;
   const int n_frames = ((int)blockIdx.x < batch) ? (batch - 1 - (int)blockIdx.x) / stride + 1 : 0;
   const int n_chunks = n_frames * PW_NCHUNK;                       // chunk stream of this CTA: q = k * 21 + c, warp q % 6
@@ -158,21 +158,17 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
 #pragma unroll 1
     for (int q = warp; q < n_chunks; q += FB_AUX_WARPS, ++j) {
       const int k = q / PW_NCHUNK, c = q - k * PW_NCHUNK, slot = warp * PW_SLOTS + (j & 1);
-      // block rows c, c+1 are rewritten: the last position group of frame k-1 that reads them must have retired
-      evt_mark(evt_i, 1, q);
+      uint32_t pk[PW_ROWS][3][2];
+      mbar_wait(bar(FB_RING + slot), (j >> 1) & 1);                 // the chunk has landed
+      blk_load_rows4<U8>(ring + slot * PW_BYTES, lane, pk);
+      __syncwarp();                                                  // every lane has read its part: the slot is free
+      if (lane == 0 && q + PW_SLOTS * FB_AUX_WARPS < n_chunks) issue_chunk(q + PW_SLOTS * FB_AUX_WARPS, slot);
+      // block rows c, c+1 are rewritten: the last consumer group of frame k-1 that reads them must have retired
       if (k > 0) mbar_wait(bar(FB_GRP + pw_last_consumer(c)), (k - 1) & 1);
-      evt_mark(evt_i, 2, q);
-      mbar_wait(bar(FB_RING + slot), (j >> 1) & 1);
-      evt_mark(evt_i, 3, q);
-      if (U8) blk_convert_rows4_u8<FBLK_LBO>(ring + slot * PW_BYTES, blk, c, lane, lane_off);
-      else blk_convert_rows4<FBLK_LBO>(ring + slot * PW_BYTES, blk, c, lane, lane_off);
-      fence_proxy_async();                                         // Blk is read by the tensor core; the slot is refilled by the TMA
+      blk_store_rows4<FBLK_LBO>(blk, c, lane, lane_off, pk);
+      fence_proxy_async();                                           // Blk is read by the tensor core
       __syncwarp();
-      if (lane == 0) {
-        if (q + PW_SLOTS * FB_AUX_WARPS < n_chunks) issue_chunk(q + PW_SLOTS * FB_AUX_WARPS, slot);
-        mbar_arrive(bar(FB_BLKRDY + pw_first_consumer(c)));
-      }
-      evt_mark(evt_i, 4, q);
+      if (lane == 0) mbar_arrive(bar(FB_BLKRDY + pw_first_consumer(c)));
     }
   } else if (warp == FB_ISSUE_WARP) {
     // =========================== MMA issuer ===========================

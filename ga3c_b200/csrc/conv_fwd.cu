@@ -76,6 +76,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
                  wq = sbase + CF_OFF_WQ, lut = sbase + CF_OFF_LUT, bars = sbase + CF_OFF_BAR, tslot = sbase + CF_OFF_TSLOT;
   float* bias_s = reinterpret_cast<float*>(smem + CF_OFF_BIAS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  EvtLog evt_i = evt_open();                                      // pipeline event log of CTA 0 (ga3c_evt_*), off unless attached
   const int stride = gridDim.x;
   const int n_frames = ((int)blockIdx.x < batch) ? (batch - 1 - (int)blockIdx.x) / stride + 1 : 0;
   const int n_chunks = n_frames * PW_NCHUNK;                         // chunk stream of this CTA: q = k * 21 + c, warp q % 6
@@ -167,17 +168,17 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
 #pragma unroll 1
     for (int q = warp; q < n_chunks; q += CF_AUX_WARPS, ++j) {
       const int k = q / PW_NCHUNK, c = q - k * PW_NCHUNK, slot = warp * PW_SLOTS + (j & 1);
-      // block rows c, c+1 are rewritten: the last conv11 tile of frame k-1 that reads them must have completed
-      if (k > 0) mbar_wait(bar(BAR_C11 + pw_last_consumer(c)), (k - 1) & 1);
+      uint32_t pk[PW_ROWS][3][2];
       mbar_wait(bar(BAR_RING + slot), (j >> 1) & 1);                 // the chunk has landed
-      if (U8) blk_convert_rows4_u8<BLK_LBO>(ring + slot * PW_BYTES, blk, c, lane, lane_off);
-      else blk_convert_rows4<BLK_LBO>(ring + slot * PW_BYTES, blk, c, lane, lane_off);
-      fence_proxy_async();                                           // Blk is read by the tensor core; the slot is refilled by the TMA
+      blk_load_rows4<U8>(ring + slot * PW_BYTES, lane, pk);
+      __syncwarp();                                                  // every lane has read its part: the slot is free
+      if (lane == 0 && q + PW_SLOTS * CF_AUX_WARPS < n_chunks) issue_chunk(q + PW_SLOTS * CF_AUX_WARPS, slot);
+      // block rows c, c+1 are rewritten: the last consumer group of frame k-1 that reads them must have retired
+      if (k > 0) mbar_wait(bar(BAR_C11 + pw_last_consumer(c)), (k - 1) & 1);
+      blk_store_rows4<BLK_LBO>(blk, c, lane, lane_off, pk);
+      fence_proxy_async();                                           // Blk is read by the tensor core
       __syncwarp();
-      if (lane == 0) {
-        if (q + PW_SLOTS * CF_AUX_WARPS < n_chunks) issue_chunk(q + PW_SLOTS * CF_AUX_WARPS, slot);
-        mbar_arrive(bar(BAR_BLKRDY + pw_first_consumer(c)));
-      }
+      if (lane == 0) mbar_arrive(bar(BAR_BLKRDY + pw_first_consumer(c)));
     }
   } else if (warp == CF_ISSUE_WARP) {
     // =========================== MMA issuer ===========================
@@ -189,6 +190,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
 #pragma unroll
       for (int i = 0; i < C11_TILES; ++i) {
         mbar_wait(bar(BAR_BLKRDY + i), k & 1);                       // the Blk rows this tile reads hold frame k
+        evt_mark(evt_i, 15, k * 4 + i);
         if (k > 0) mbar_wait(bar(BAR_T1FREE + i), (k - 1) & 1);      // its accumulator of frame k-1 has been drained
         tc_fence_after();
         if (elect_one()) {
@@ -201,8 +203,10 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
           tc_commit(bar(BAR_C11 + i));
         }
         __syncwarp();
+        evt_mark(evt_i, 16, k * 4 + i);
       }
       mbar_wait(bar(BAR_A2RDY), k & 1);                              // every conv11 output of frame k sits in the im2col operand
+      evt_mark(evt_i, 17, k);
       if (k > 0) mbar_wait(bar(BAR_T2FREE), (k - 1) & 1);
       tc_fence_after();
       if (elect_one()) {
@@ -216,6 +220,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
         tc_commit(bar(BAR_MMA2));
       }
       __syncwarp();
+      evt_mark(evt_i, 18, k);
     }
   } else if (warp >= CF_EPI_WARP0) {
     // =========================== epilogues ===========================
@@ -225,6 +230,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
     const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16);
     auto conv12_epilogue = [&](int k) {                              // TMEM -> +bias, ReLU, bf16 -> n2[frame k]
       mbar_wait(bar(BAR_MMA2), k & 1);
+      evt_mark(evt_i, 43, k);
       tc_fence_after();
       uint32_t r[32];
       tc_ld32(tlane + TMEM_C12, r);
@@ -252,10 +258,12 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
         if (eset == 1) conv12_epilogue(k - 1);
         else mbar_wait(bar(BAR_MMA2), (k - 1) & 1);
       }
+      evt_mark(evt_i, 44, k);
       uint16_t* n1_dst = n1_out ? n1_out + frame_of(k) * (N1_POS * C1_OUT) : nullptr;
 #pragma unroll 1
       for (int i = eset; i < C11_TILES; i += 2) {
         mbar_wait(bar(BAR_C11 + i), k & 1);
+        evt_mark(evt_i, 40, k * 4 + i);
         tc_fence_after();
         uint32_t r[32];                                              // [0,16): b = 0 part of row m ; [16,32): b = 1 part, owed to row m-1
         tc_ld32(tlane + 32 * i, r);
@@ -305,6 +313,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
       fence_proxy_async();                                           // the scatter is read by the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(BAR_A2RDY));
+      evt_mark(evt_i, 42, k);
     }
     if (n_frames > 0 && eset == 1) conv12_epilogue(n_frames - 1);
   }
@@ -319,6 +328,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
 }
 
 GA3C_TRACE_ATTACH(trace_attach_conv_fwd)
+GA3C_EVT_ATTACH(evt_attach_conv_fwd)
 
 int configure_conv_fwd() {
   cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM);

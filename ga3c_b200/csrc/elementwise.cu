@@ -235,7 +235,7 @@ __device__ __forceinline__ void st_flag(uint64_t* p, uint64_t v) {
 template <bool HAS_MOM>
 __global__ void __launch_bounds__(512) rmsprop_dp_kernel(RmsPropDpArgs d) {
   const RmsPropArgs& a = d.base;
-  unsigned int evt_i = 0;
+  EvtLog evt_i = evt_open();                                      // pipeline event log of CTA 0 (ga3c_evt_*), off unless attached
   griddep_launch();
   evt_mark(evt_i, 60, 0);
   griddep_wait(K_RMSPROP);      // the gradients come from the backward kernels that precede this one

@@ -13,6 +13,7 @@ int trace_attach_heads(unsigned long long* buf);
 int trace_attach_elementwise(unsigned long long* buf);
 
 // pipeline event log of CTA 0 (debug): attach a zeroed [16 warps][1024][2] uint64 buffer (or nullptr)
+int evt_attach_conv_fwd(unsigned long long* buf);
 int evt_attach_conv_bwd(unsigned long long* buf);
 int evt_attach_elementwise(unsigned long long* buf);
 

@@ -605,6 +605,7 @@ extern "C" int ga3c_evt_begin(ga3c_net* n) {
   CK(cudaDeviceSynchronize());
   if (!n->evt) CK(cudaMalloc((void**)&n->evt, (size_t)2 * 16384 * 8));
   CK(cudaMemset(n->evt, 0, (size_t)2 * 16384 * 8));
+  CKL(evt_attach_conv_fwd(n->evt));
   CKL(evt_attach_conv_bwd(n->evt));
   CKL(evt_attach_elementwise(n->evt));
   return 0;
@@ -614,6 +615,7 @@ extern "C" int ga3c_evt_end(ga3c_net* n, uint64_t* records, int32_t cap, int32_t
   if (!n || !records || !count || !n->evt || cap < 16384) return fail_msg("ga3c_evt_end: bad argument");
   CK(cudaSetDevice(n->cfg.device));
   CK(cudaDeviceSynchronize());
+  CKL(evt_attach_conv_fwd(nullptr));
   CKL(evt_attach_conv_bwd(nullptr));
   CKL(evt_attach_elementwise(nullptr));
   std::vector<uint64_t> all((size_t)2 * 16384);

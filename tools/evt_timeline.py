@@ -6,9 +6,10 @@ import torch
 import ga3c_b200
 from ga3c_b200 import _capi
 
-NAMES = {1: "aux: next chunk", 2: "aux: WAR wait done", 3: "aux: chunk landed", 4: "aux: converted+armed",
+NAMES = {1: "aux: next chunk", 2: "aux: WAR wait done", 3: "aux: chunk landed", 4: "aux: converted+armed", 5: "aux: converted", 6: "aux: fenced",
          10: "iss: conv12 begin", 11: "iss: C12RDY passed", 12: "iss: conv12 issued", 13: "iss: frame begin", 14: "iss: DN1RDY passed",
-         15: "iss: BLKRDY passed", 16: "iss: group issued", 20: "tma: raw issue", 30: "re: RAWFULL passed", 31: "re: EPI12 passed",
+         15: "iss: BLKRDY passed", 16: "iss: group issued", 17: "iss: A2RDY passed", 18: "iss: conv12 issued", 43: "epi: MMA2 passed",
+         44: "epi: frame begin", 20: "tma: raw issue", 30: "re: RAWFULL passed", 31: "re: EPI12 passed",
          32: "re: done", 40: "epi: MMA12 passed", 41: "epi: DN1FREE passed", 42: "epi: done", 50: "prologue: at griddep_wait",
          51: "prologue: done", 52: "role done"}
 tb = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
@@ -22,7 +23,10 @@ for i in range(10):
 torch.cuda.synchronize()
 lib = _capi.load()
 _capi.check(lib.ga3c_evt_begin(net._h), "evt_begin")
-net.train_device(xs[0], yr, a)
+if os.environ.get("PREDICT"):
+    net.predict_device(xs[0])
+else:
+    net.train_device(xs[0], yr, a)
 buf = (C.c_uint64 * (2 * 16384))(); cnt = C.c_int32()
 _capi.check(lib.ga3c_evt_end(net._h, buf, 16384, C.byref(cnt)), "evt_end")
 recs = sorted((buf[2 * i], buf[2 * i + 1] >> 32, (buf[2 * i + 1] >> 16) & 0xFFFF, buf[2 * i + 1] & 0xFFFF) for i in range(cnt.value))
