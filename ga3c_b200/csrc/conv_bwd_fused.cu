@@ -22,8 +22,11 @@
 // conv12 weight gradient.  kh = 2a + dy, kw = 2b + dx: quadrant (a, b) is  dW_ab[(dy, dx, ci), co] = sum_m Blk2[m + 13a + b]^T
 //   G[m + 14]  over positions m = oy*13 + ox (dead columns hit the zero border of G): A = Blk2 read MN-major, B = G read
 //   MN-major, M = 64, N = 32, K = 144 -> 4 x 9 UMMAs.
-// conv11 weight gradient.  As before (4 quadrants, M = 64, N = 16, K = 464 positions m = oy*22 + ox): A = Blk read MN-major
-//   at row m + 22a + b, B = dn1 staged MN-major -- now written by the data-gradient epilogue instead of loaded from HBM.
+// conv11 weight gradient.  Quadrant (a, b) is dW_ab = sum_m Blk[m + 22a + b]^T dn1[m] over positions m = oy*22 + ox.  A = Blk
+//   read MN-major at row m' + 22a; the b-shift moves to the B side (m' = m + b): dn1 is written twice by the data-gradient
+//   epilogue, planes (0, half) at row m and planes (1, half) at row m + 1, so ONE UMMA per (a, k-step) with N = 32 = (b, cout)
+//   covers both b: 2 x 29 UMMAs (M = 64, N = 32) per frame instead of 4 x 29 -- the frame loop is bound by UMMA count and
+//   operand bytes (every small UMMA costs ~40-80 cycles, microbenchmark in profiles/), not by HBM.
 //
 //   warps 0-5    fp32 chunks of x (TMA ring, one independent pipeline per warp) -> bf16 -> Blk
 //   warp  6      one thread issues every UMMA: conv12 of frame k+1 between the conv11 position groups of frame k
@@ -43,7 +46,9 @@ constexpr int FB_THREADS = 512, FB_AUX_WARPS = 6, FB_ISSUE_WARP = 6, FB_TMA_WARP
 static_assert(FB_EPI_WARP0 % 4 == 0, "epilogue warp e must own TMEM lane quarter e");
 constexpr int FBLK_ROWS = 492, FBLK_LBO = FBLK_ROWS * 16, FBLK_BYTES = 8 * FBLK_LBO;     // rows read: <= 16*28 + 23 + 15 = 486
 constexpr int W11_KSTEPS = 29;                                   // 464 >= 462 positions (21 rows x 22, column 21 dead)
-constexpr int DN1_ROWS = 16 * W11_KSTEPS, DN1_PLANE = DN1_ROWS * 16, DN1_BUF = 2 * DN1_PLANE;   // 2 planes of 8 channels
+// dn1 operand: 4 planes (b, half) of 8 channels; planes (1, .) hold the SAME rows shifted down by one, so that one UMMA
+// with N = 32 computes both column quadrants b = 0, 1 of the conv11 weight gradient (A = Blk is read once for two)
+constexpr int DN1_ROWS = 16 * W11_KSTEPS, DN1_PLANE = DN1_ROWS * 16, DN1_BUF = 4 * DN1_PLANE;
 constexpr int G_W = 13, G_ROWS = 176, G_LBO = G_ROWS * 16, G_BYTES = 4 * G_LBO;          // rows read: <= 28 + 127 + 14 = 169
 constexpr int B2_ROWS = 160, B2_LBO = B2_ROWS * 16, B2_BYTES = 8 * B2_LBO;               // rows read: <= 143 + 14 = 157
 constexpr int DG_TILE1 = 28;                                     // first row of the second data-gradient tile
@@ -55,29 +60,30 @@ constexpr int W12D_BYTES = 4 * 4 * 64 * 16;                      // 4 taps x [4 
 constexpr int FB_OFF_BLK = 0;
 constexpr int FB_OFF_RING = FB_OFF_BLK + FBLK_BYTES;             //  62,976
 constexpr int FB_RING_BYTES = FB_AUX_WARPS * PW_SLOTS * PW_BYTES; //  64,512: two 4-row slots per aux warp
-constexpr int FB_OFF_DN1 = FB_OFF_RING + FB_RING_BYTES;          // 127,488 (two buffers)
-constexpr int FB_OFF_G = FB_OFF_DN1 + 2 * DN1_BUF;               // 157,184
+constexpr int FB_OFF_DN1 = FB_OFF_RING + FB_RING_BYTES;          // 127,488 (one buffer of four planes)
+constexpr int FB_OFF_G = FB_OFF_DN1 + DN1_BUF;                   // 157,184
 constexpr int FB_OFF_B2 = FB_OFF_G + G_BYTES;                    // 168,448
 constexpr int FB_OFF_W12D = FB_OFF_B2 + B2_BYTES;                // 188,928
 constexpr int FB_OFF_RAW = FB_OFF_W12D + W12D_BYTES;             // 205,312
-constexpr int FB_OFF_RED = FB_OFF_RAW + RAW_BYTES;               // 227,168: [4][16] conv11 + [4][32] conv12 bias partials
-constexpr int FB_OFF_BAR = FB_OFF_RED + (4 * C1_OUT + 4 * C2_OUT) * 4;
+constexpr int FB_OFF_RED = FB_OFF_RAW + RAW_BYTES;               // 227,168: [5][16] conv11 + [4][32] conv12 bias partials
+constexpr int RED_B12 = 5 * C1_OUT;
+constexpr int FB_OFF_BAR = FB_OFF_RED + (RED_B12 + 4 * C2_OUT) * 4;
 constexpr int FB_RING = 0;        // [12] TMA chunk of x landed (slot = aux warp * 2 + parity)
 constexpr int FB_BLKRDY = 12;     // [4] Blk rows of conv11 position group i converted, one arrival per chunk (aux -> issuer)
 constexpr int FB_GRP = 16;        // [4] conv11 UMMAs of group i retired (tcgen05.commit)           (-> aux: Blk rows free)
-constexpr int FB_DN1RDY = 20;     // [2] dn1 operand buffer written, 4 arrivals                     (epilogue -> issuer)
-constexpr int FB_DN1FREE = 22;    // [2] every conv11 UMMA reading the buffer retired               (-> epilogue)
+constexpr int FB_DN1RDY = 20;     //     dn1 operand written, 5 arrivals                            (epilogue -> issuer)
+constexpr int FB_DN1FREE = 22;    //     every conv11 UMMA of the frame retired                     (-> epilogue: operand free)
 constexpr int FB_RAWFULL = 24;    //     n1 / dn2 of a frame landed in the raw buffer               (TMA -> re-layout)
 constexpr int FB_RAWFREE = 25;    //     raw buffer consumed                                        (re-layout -> TMA thread)
 constexpr int FB_C12RDY = 26;     //     G / Blk2 hold the frame                                    (re-layout -> issuer)
 constexpr int FB_MMA12 = 27;      //     conv12 UMMAs of the frame retired (tcgen05.commit)         (-> epilogue)
-constexpr int FB_EPI12 = 28;      //     D drained and Blk2 mask reads done, 4 arrivals             (epilogue -> issuer, re-layout)
+constexpr int FB_EPI12 = 28;      //     D drained and Blk2 mask reads done, 5 arrivals             (epilogue -> issuer, re-layout)
 constexpr int FB_DONE = 29;       //     every UMMA of the kernel retired                           (-> final store)
 constexpr int FB_NBAR = 30;
 constexpr int FB_OFF_TSLOT = FB_OFF_BAR + FB_NBAR * 8;
 constexpr int FB_SMEM = FB_OFF_TSLOT + 16 + 128;                 // incl. slack to align the base to 128 B
 static_assert(FB_SMEM <= 232448, "shared memory budget of one CTA per SM");
-constexpr int FB_TMEM_COLS = 512, TM_W11 = 0, TM_W12 = 64, TM_D12 = 192;   // 4x16 | 4x32 | 2x64 columns
+constexpr int FB_TMEM_COLS = 512, TM_W11 = 0, TM_W12 = 64, TM_D12 = 192;   // 2x32 | 4x32 | 2x64 columns
 
 template <bool U8>       // U8: frames are uint8 [B,28224] (x = k/128 - 1 applied on the fly), else fp32
 __global__ void __launch_bounds__(FB_THREADS, 1)
@@ -112,15 +118,13 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
       mbar_init(bar(FB_BLKRDY + i), pw_group_chunks(i));
       mbar_init(bar(FB_GRP + i), 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar(FB_DN1RDY + i), 4);
-      mbar_init(bar(FB_DN1FREE + i), 1);
-    }
+    mbar_init(bar(FB_DN1RDY), 5);
+    mbar_init(bar(FB_DN1FREE), 1);
     mbar_init(bar(FB_RAWFULL), 1);
     mbar_init(bar(FB_RAWFREE), 1);
     mbar_init(bar(FB_C12RDY), 1);
     mbar_init(bar(FB_MMA12), 1);
-    mbar_init(bar(FB_EPI12), 4);
+    mbar_init(bar(FB_EPI12), 5);
     mbar_init(bar(FB_DONE), 1);
     fence_mbar_init();
   }
@@ -150,6 +154,80 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tslot));
   evt_mark(evt_i, 51, 0);
 
+  // Data-gradient epilogue of one 128-row tile for TMEM lane quarter `qt`: rows of the first tile go to warps 8-11, the 28
+  // live rows of the second tile (lanes 100..127) to warp 15, which shares lane quarter 3 with warp 11 and is otherwise idle
+  // once the frame's operands are laid out.
+  auto dgrad_epilogue = [&](int k, int t, int qt, float (&bacc)[C1_OUT]) {
+    const uint32_t tlane = tmem_base + ((uint32_t)(qt * 32) << 16);
+    mbar_wait(bar(FB_MMA12), k & 1);
+    evt_mark(evt_i, 40, k);
+    tc_fence_after();
+    uint16_t* dn1_dst = dn1_out ? dn1_out + frame_of(k) * (N1_POS * C1_OUT) : nullptr;
+    // Phase 1: TMEM -> relu' mask -> packed bf16 in registers (one 2x2 block of dn1 per row).  Nothing is written yet: the
+    // conv11 UMMAs of frame k-1 may still be reading the dn1 operand.
+    uint32_t o[4][8];
+    int p22[4];
+    const int m = (t ? DG_TILE1 : 0) + 32 * qt + lane;
+    const int Yh = m / G_W, Xh = m - Yh * G_W;
+    const bool row_ok = (t == 0 || m >= 128) && m < DG_ROWS && Xh < 12;
+#pragma unroll
+    for (int cls = 0; cls < 4; ++cls) {
+      uint32_t r[16];
+      tc_ld16(tlane + TM_D12 + 64 * t + 16 * cls, r);
+      const int y = 2 * Yh + (cls >> 1) - 1, xx = 2 * Xh + (cls & 1) - 1;
+      p22[cls] = -1;
+      if (row_ok && y >= 0 && y < H1 && xx >= 0 && xx < H1) {
+        uint32_t mk[8];                                            // n1 of this pixel: relu'(n1) = (n1 > 0); post-ReLU values are >= 0
+        lds128(*reinterpret_cast<uint32_t(*)[4]>(&mk[0]), b2 + (2 * cls) * B2_LBO + m * 16);
+        lds128(*reinterpret_cast<uint32_t(*)[4]>(&mk[4]), b2 + (2 * cls + 1) * B2_LBO + m * 16);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const float lo = (mk[jj] & 0x7FFFu) ? __uint_as_float(r[2 * jj]) : 0.f;
+          const float hi = (mk[jj] & 0x7FFF0000u) ? __uint_as_float(r[2 * jj + 1]) : 0.f;
+          o[cls][jj] = pack_bf16(lo, hi);
+          bacc[2 * jj] += bf16_lo(o[cls][jj]);
+          bacc[2 * jj + 1] += bf16_hi(o[cls][jj]);
+        }
+        p22[cls] = y * BLK_W + xx;
+        if (dn1_dst) {
+          uint4* d = reinterpret_cast<uint4*>(dn1_dst + (y * H1 + xx) * C1_OUT);
+          d[0] = make_uint4(o[cls][0], o[cls][1], o[cls][2], o[cls][3]);
+          d[1] = make_uint4(o[cls][4], o[cls][5], o[cls][6], o[cls][7]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar(FB_EPI12));                     // D is drained and Blk2 has been read: conv12 of the next frame may start
+    // Phase 2: the operand buffer is free once every conv11 UMMA of frame k-1 has retired
+    if (k > 0) mbar_wait(bar(FB_DN1FREE), (k - 1) & 1);
+    evt_mark(evt_i, 41, k);
+#pragma unroll
+    for (int cls = 0; cls < 4; ++cls) {
+      if (p22[cls] >= 0) {
+        const uint4 lo4 = make_uint4(o[cls][0], o[cls][1], o[cls][2], o[cls][3]), hi4 = make_uint4(o[cls][4], o[cls][5], o[cls][6], o[cls][7]);
+        const uint32_t dst = dn1s + p22[cls] * 16;
+        sts128(dst, lo4);                                          // planes (b = 0, half): row p
+        sts128(dst + DN1_PLANE, hi4);
+        sts128(dst + 2 * DN1_PLANE + 16, lo4);                     // planes (b = 1, half): row p + 1
+        sts128(dst + 3 * DN1_PLANE + 16, hi4);
+      }
+    }
+    fence_proxy_async();                                           // the dn1 operand is read by the tensor core
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar(FB_DN1RDY));
+    evt_mark(evt_i, 42, k);
+  };
+  auto b11_partial = [&](int slot, const float (&bacc)[C1_OUT]) {   // warp-reduce the 16 channel sums of this warp
+#pragma unroll
+    for (int c = 0; c < C1_OUT; ++c) {
+      float v = bacc[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[slot * C1_OUT + c] = v;
+    }
+  };
+
   if (warp < FB_AUX_WARPS) {
     // =========================== aux: one chunk pipeline per warp (conv_blk.cuh) ===========================
     uint32_t lane_off[3];
@@ -159,22 +237,27 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
     for (int q = warp; q < n_chunks; q += FB_AUX_WARPS, ++j) {
       const int k = q / PW_NCHUNK, c = q - k * PW_NCHUNK, slot = warp * PW_SLOTS + (j & 1);
       uint32_t pk[PW_ROWS][3][2];
+      evt_mark(evt_i, 1, q);
       mbar_wait(bar(FB_RING + slot), (j >> 1) & 1);                 // the chunk has landed
+      evt_mark(evt_i, 3, q);
       blk_load_rows4<U8>(ring + slot * PW_BYTES, lane, pk);
       __syncwarp();                                                  // every lane has read its part: the slot is free
       if (lane == 0 && q + PW_SLOTS * FB_AUX_WARPS < n_chunks) issue_chunk(q + PW_SLOTS * FB_AUX_WARPS, slot);
       // block rows c, c+1 are rewritten: the last consumer group of frame k-1 that reads them must have retired
+      evt_mark(evt_i, 5, q);
       if (k > 0) mbar_wait(bar(FB_GRP + pw_last_consumer(c)), (k - 1) & 1);
+      evt_mark(evt_i, 2, q);
       blk_store_rows4<FBLK_LBO>(blk, c, lane, lane_off, pk);
       fence_proxy_async();                                           // Blk is read by the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(FB_BLKRDY + pw_first_consumer(c)));
+      evt_mark(evt_i, 4, q);
     }
   } else if (warp == FB_ISSUE_WARP) {
     // =========================== MMA issuer ===========================
     // warp-uniform: all 32 lanes run the loops and wait on the barriers, elect_one() issues
     constexpr uint32_t idesc_dg = make_idesc_m(128, 64, false, false), idesc_w12 = make_idesc_m(64, C2_OUT, true, true),
-                       idesc_w11 = make_idesc_m(64, C1_OUT, true, true);
+                       idesc_w11 = make_idesc_m(64, 2 * C1_OUT, true, true);
     // descriptor low words of row 0 / k-chunk 0 of every operand; a shift of r rows is + r, a k-chunk plane is + LBO/16
     const uint32_t g_k = desc_ns_lo(gg, G_LBO), wd_k = desc_ns_lo(w12d, 1024);                 // K-major: LBO = plane, SBO = 128
     const uint32_t g_mn = desc_ns_lo(gg, 128), b2_mn = desc_ns_lo(b2, 128), blk_mn = desc_ns_lo(blk, 128),
@@ -212,9 +295,8 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
     };
     if (n_frames > 0) conv12_mmas(0);
     for (int k = 0; k < n_frames; ++k) {
-      const uint32_t dbuf = dn1_mn + (k & 1) * (DN1_BUF / 16);
       evt_mark(evt_i, 13, k);
-      mbar_wait(bar(FB_DN1RDY + (k & 1)), (k >> 1) & 1);
+      mbar_wait(bar(FB_DN1RDY), k & 1);
       evt_mark(evt_i, 14, k);
 #pragma unroll
       for (int gi = 0; gi < 4; ++gi) {
@@ -227,12 +309,12 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
 #pragma unroll
           for (int s = 8 * gi; s < (gi == 3 ? W11_KSTEPS : 8 * gi + 8); ++s)
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              // A: Blk rows 16 s + 22 a + b .., B: dn1 rows 16 s ..; both MN-major
-              tc_mma_bf16_w(tmem_base + TM_W11 + 16 * q, blk_mn + 16 * s + BLK_W * (q >> 1) + (q & 1), hi_blk, dbuf + 16 * s, hi_dn1,
-                            idesc_w11, s ? 1u : acc);
+            for (int a = 0; a < 2; ++a)
+              // A: Blk rows 16 s + 22 a .., B: dn1 rows 16 s .. in the four (b, half) planes; both MN-major
+              tc_mma_bf16_w(tmem_base + TM_W11 + 32 * a, blk_mn + 16 * s + BLK_W * a, hi_blk, dn1_mn + 16 * s, hi_dn1, idesc_w11,
+                            s ? 1u : acc);
           tc_commit(bar(FB_GRP + gi));
-          if (gi == 3) tc_commit(bar(FB_DN1FREE + (k & 1)));
+          if (gi == 3) tc_commit(bar(FB_DN1FREE));
         }
         __syncwarp();
         evt_mark(evt_i, 16, k * 4 + gi);
@@ -255,6 +337,9 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
     // =========================== raw -> G / Blk2, conv12 bias gradient ===========================
     const int rtid = tid - 32 * FB_RE_WARP0;
     float bacc = 0.f;                                              // db12 partial: channel rtid & 31, position phase rtid >> 5
+    float bacc11[C1_OUT];                                          // warp 15: db11 partials of the second data-gradient tile
+#pragma unroll
+    for (int c = 0; c < C1_OUT; ++c) bacc11[c] = 0.f;
     for (int k = 0; k < n_frames; ++k) {
       mbar_wait(bar(FB_RAWFULL), k & 1);
       evt_mark(evt_i, 30, k);
@@ -272,6 +357,10 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
         lds128(r, raw + RAW_DN2 + i * 16);
         sts128(b2 + ((((Y & 1) * 2 + (X & 1)) * 2 + h) * B2_LBO) + ((Y >> 1) * G_W + (X >> 1)) * 16, make_uint4(r[0], r[1], r[2], r[3]));
       }
+      fence_proxy_async();
+      named_bar_sync(3, 128);
+      if (rtid == 0) mbar_arrive(bar(FB_C12RDY));                  // the UMMAs can go; the bias sums below only read raw
+      evt_mark(evt_i, 32, k);
       {
         const int co = rtid & 31;
         for (int pos = rtid >> 5; pos < N2_POS; pos += 4) {
@@ -280,19 +369,16 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
           bacc += __uint_as_float((uint32_t)v << 16);
         }
       }
-      fence_proxy_async();
       named_bar_sync(3, 128);
-      if (rtid == 0) {
-        mbar_arrive(bar(FB_C12RDY));
-        mbar_arrive(bar(FB_RAWFREE));
-      }
-      evt_mark(evt_i, 32, k);
+      if (rtid == 0) mbar_arrive(bar(FB_RAWFREE));
+      if (warp == FB_RE_WARP0 + 3) dgrad_epilogue(k, 1, 3, bacc11);
     }
-    red[4 * C1_OUT + rtid] = bacc;
+    red[RED_B12 + rtid] = bacc;
+    if (warp == FB_RE_WARP0 + 3) b11_partial(4, bacc11);
     named_bar_sync(3, 128);
     if (rtid < C2_OUT)
       g_b12[(int64_t)blockIdx.x * gp_stride + rtid] =
-          red[4 * C1_OUT + rtid] + red[4 * C1_OUT + 32 + rtid] + red[4 * C1_OUT + 64 + rtid] + red[4 * C1_OUT + 96 + rtid];
+          red[RED_B12 + rtid] + red[RED_B12 + 32 + rtid] + red[RED_B12 + 64 + rtid] + red[RED_B12 + 96 + rtid];
   } else {
     // =========================== data-gradient epilogue; final store ===========================
     const int ew = warp - FB_EPI_WARP0;                            // TMEM lane quarter
@@ -300,71 +386,8 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
     float bacc[C1_OUT];                                            // db11 partials of this thread's pixels
 #pragma unroll
     for (int c = 0; c < C1_OUT; ++c) bacc[c] = 0.f;
-    for (int k = 0; k < n_frames; ++k) {
-      mbar_wait(bar(FB_MMA12), k & 1);
-      evt_mark(evt_i, 40, k);
-      if (k >= 2) mbar_wait(bar(FB_DN1FREE + (k & 1)), ((k >> 1) - 1) & 1);   // conv11 UMMAs of frame k-2 (same buffer) retired
-      evt_mark(evt_i, 41, k);
-      tc_fence_after();
-      const uint32_t dbuf = dn1s + (k & 1) * DN1_BUF;
-      uint16_t* dn1_dst = dn1_out ? dn1_out + frame_of(k) * (N1_POS * C1_OUT) : nullptr;
-#pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
-        if (t == 1 && ew != 3) break;                              // rows 128..155 are lanes 100..127 of the second tile
-        const int m = (t ? DG_TILE1 : 0) + 32 * ew + lane;
-        const int Yh = m / G_W, Xh = m - Yh * G_W;
-        const bool row_ok = (t == 0 || m >= 128) && m < DG_ROWS && Xh < 12;
-#pragma unroll
-        for (int cls = 0; cls < 4; ++cls) {
-          uint32_t r[16];
-          tc_ld16(tlane + TM_D12 + 64 * t + 16 * cls, r);
-          const int y = 2 * Yh + (cls >> 1) - 1, xx = 2 * Xh + (cls & 1) - 1;
-          if (row_ok && y >= 0 && y < H1 && xx >= 0 && xx < H1) {
-            uint32_t mk[8];                                        // n1 of this pixel: relu'(n1) = (n1 > 0); post-ReLU values are >= 0
-            lds128(*reinterpret_cast<uint32_t(*)[4]>(&mk[0]), b2 + (2 * cls) * B2_LBO + m * 16);
-            lds128(*reinterpret_cast<uint32_t(*)[4]>(&mk[4]), b2 + (2 * cls + 1) * B2_LBO + m * 16);
-            uint32_t o[8];
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              const float lo = (mk[jj] & 0x7FFFu) ? __uint_as_float(r[2 * jj]) : 0.f;
-              const float hi = (mk[jj] & 0x7FFF0000u) ? __uint_as_float(r[2 * jj + 1]) : 0.f;
-              o[jj] = pack_bf16(lo, hi);
-              bacc[2 * jj] += bf16_lo(o[jj]);
-              bacc[2 * jj + 1] += bf16_hi(o[jj]);
-            }
-            const uint4 lo4 = make_uint4(o[0], o[1], o[2], o[3]), hi4 = make_uint4(o[4], o[5], o[6], o[7]);
-            const int p22 = y * BLK_W + xx;
-            sts128(dbuf + p22 * 16, lo4);
-            sts128(dbuf + DN1_PLANE + p22 * 16, hi4);
-            if (dn1_dst) {
-              uint4* d = reinterpret_cast<uint4*>(dn1_dst + (y * H1 + xx) * C1_OUT);
-              d[0] = lo4;
-              d[1] = hi4;
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      fence_proxy_async();                                         // the dn1 operand is read by the tensor core
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar(FB_EPI12));
-        mbar_arrive(bar(FB_DN1RDY + (k & 1)));
-      }
-      evt_mark(evt_i, 42, k);
-    }
-    // conv11 bias gradient: warp-reduce the 16 channel sums, then add the four warps in order
-#pragma unroll
-    for (int c = 0; c < C1_OUT; ++c) {
-      float v = bacc[c];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) red[ew * C1_OUT + c] = v;
-    }
-    named_bar_sync(2, 128);
-    const int etid = tid - 32 * FB_EPI_WARP0;
-    if (etid < C1_OUT)
-      g_b11[(int64_t)blockIdx.x * gp_stride + etid] = red[etid] + red[C1_OUT + etid] + red[2 * C1_OUT + etid] + red[3 * C1_OUT + etid];
+    for (int k = 0; k < n_frames; ++k) dgrad_epilogue(k, 0, ew, bacc);
+    b11_partial(ew, bacc);                                         // summed with warp 15's after the final block barrier
     // weight-gradient accumulators: M = 64 rows sit on TMEM lanes 32 w + (0..15) (rows 16 w ..); row = chunk plane * 8 + e
     if (n_frames > 0) {
       mbar_wait(bar(FB_DONE), 0);
@@ -373,9 +396,9 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
       float* const s12 = g_w12 + (int64_t)blockIdx.x * gp_stride;
       const int row = 16 * ew + lane, j = row >> 3, e = row & 7;
 #pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 4; ++q) {                                // q = a*2 + b: accumulator a, columns 16 b ..
         uint32_t r[16];
-        tc_ld16(tlane + TM_W11 + 16 * q, r);
+        tc_ld16(tlane + TM_W11 + 32 * (q >> 1) + 16 * (q & 1), r);
         if (lane < 16) {
           // conv11 block element: j = dy*2 + (dx>>1), e = (dx&1)*4 + c
           const int kh = 4 * (q >> 1) + (j >> 1), kw = 4 * (q & 1) + (j & 1) * 2 + (e >> 2), c = e & 3;
@@ -408,6 +431,9 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
   evt_mark(evt_i, 52, 0);
   tc_fence_before();
   __syncthreads();
+  if (tid < C1_OUT)                                                // conv11 bias gradient: the five warp partials in a fixed order
+    g_b11[(int64_t)blockIdx.x * gp_stride + tid] =
+        red[tid] + red[C1_OUT + tid] + red[2 * C1_OUT + tid] + red[3 * C1_OUT + tid] + red[4 * C1_OUT + tid];
   trace_mark(K_CONV12_BWD, 2);
   if (warp == FB_EPI_WARP0) {
     tc_fence_after();

@@ -6,7 +6,7 @@ import torch
 import ga3c_b200
 from ga3c_b200 import _capi
 
-NAMES = {1: "aux: next chunk", 2: "aux: WAR wait done", 3: "aux: chunk landed", 4: "aux: converted+armed", 5: "aux: converted", 6: "aux: fenced",
+NAMES = {1: "aux: next chunk", 2: "aux: WAR wait done", 3: "aux: chunk landed", 4: "aux: converted+armed", 5: "aux: loaded+rearmed", 6: "aux: fenced",
          10: "iss: conv12 begin", 11: "iss: C12RDY passed", 12: "iss: conv12 issued", 13: "iss: frame begin", 14: "iss: DN1RDY passed",
          15: "iss: BLKRDY passed", 16: "iss: group issued", 17: "iss: A2RDY passed", 18: "iss: conv12 issued", 43: "epi: MMA2 passed",
          44: "epi: frame begin", 20: "tma: raw issue", 30: "re: RAWFULL passed", 31: "re: EPI12 passed",
