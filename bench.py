@@ -311,6 +311,15 @@ def run_ours(args, rank, local_rank, world):
     ms_pred_ev = timed(predict_step, K)
     kt_pred = net.kernel_times()
     net.kernel_timing(0)
+    # the same step seen WITHOUT serialising the programmatic-dependent-launch chain: globaltimer stamps per kernel
+    # (first CTA past its dependency wait -> last CTA ended), one traced step each
+    torch.cuda.synchronize()
+    net.trace_begin(stream)
+    train_step(0)
+    tr_train = {k: round(v[5] - v[2], 2) for k, v in net.trace_end().items()}
+    net.trace_begin(stream)
+    predict_step(0)
+    tr_pred = {k: round(v[5] - v[2], 2) for k, v in net.trace_end().items()}
     log(f"[bench] rank {rank} train kernels (us): " + ", ".join(f"{k} {t / max(c, 1) * 1e3:.1f}" for k, (t, c) in kt_train.items() if c))
 
     # ---- e2e through the public API on pinned host buffers ----
@@ -403,7 +412,10 @@ def run_ours(args, rank, local_rank, world):
                 note="achieved = algorithmic bytes (or flops) per launch / CUDA-event duration of that kernel, "
                      "measured in this run on the launch stream",
                 kernels_train=rf_train, kernels_predict=rf_pred,
-                step_ms_with_events=round(ms_train_ev / K, 4))
+                step_ms_with_events=round(ms_train_ev / K, 4),
+                in_step_us={"note": "per-kernel busy time inside the pipelined step (ga3c_trace_*: first CTA started -> last CTA "
+                                    "ended, one traced step); event brackets above serialise the launch chain and read 3-8 us longer",
+                            "train": tr_train, "predict": tr_pred})
 
     tps = world * B * K / (ms_train / 1e3)
     pps = world * PB * K / (ms_pred / 1e3)
