@@ -1,0 +1,97 @@
+"""Pins for the config-4 MLP oracle (oracle/oracle_mlp.py): finite differences in fp64 and torch autograd as an
+independent second opinion (the reference's TensorFlow is not installable: parity unpinned)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_mlp as om
+
+CASES = [("fork_vp", 3, 1), ("fork_vp", 4, 2), ("discrate", 4, 2)]
+
+
+def _case(kind, s, a, b=9, seed=5):
+    rng = np.random.default_rng(seed)
+    params = om.init_params(rng, kind, s, a)
+    x = rng.uniform(-1, 1, size=(b, s)).astype(np.float32)
+    y_r = rng.uniform(-1, 1, size=b).astype(np.float32)
+    if kind == "fork_vp":
+        act = rng.uniform(-1, 1, size=(b, a)).astype(np.float32)          # continuous action (ProcessAgent.py:92-93)
+    else:
+        act = np.eye(a, dtype=np.float32)[rng.integers(0, a, size=b)]
+    return params, x, y_r, act
+
+
+@pytest.mark.parametrize("kind,s,a", CASES)
+def test_analytic_gradients_match_finite_differences(kind, s, a):
+    params, x, y_r, act = _case(kind, s, a)
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    _, grads = om.loss_and_grads(p64, x, y_r, act, kind)
+    assert set(grads) == set(params) - set(om.dead_params(kind))
+    rng = np.random.default_rng(1)
+    for name, g in grads.items():
+        for _ in range(4):
+            idx = tuple(rng.integers(0, d) for d in g.shape)
+            h = 1e-6
+            pp = {k: v.copy() for k, v in p64.items()}; pp[name][idx] += h
+            pm = {k: v.copy() for k, v in p64.items()}; pm[name][idx] -= h
+            # cost_p_1 uses stop_gradient(v): differentiate with the advantage frozen at the unperturbed v
+            fd = (_frozen_cost(pp, p64, x, y_r, act, kind) - _frozen_cost(pm, p64, x, y_r, act, kind)) / (2 * h)
+            assert abs(fd - g[idx]) <= 1e-5 * max(1.0, abs(fd)), (name, idx, fd, g[idx])
+
+
+def _frozen_cost(p, p_ref, x, y_r, act, kind, beta=0.01, log_eps=1e-6):
+    pr, v = om.forward(p, x, kind)
+    _, v0 = om.forward(p_ref, x, kind)
+    adv = y_r - v0
+    cost_v = 0.5 * np.sum((y_r - v) ** 2)
+    if kind == "fork_vp":
+        c1 = np.sum(np.sum(pr * act, axis=1) * adv)
+        c2 = np.sum(-beta * np.sum(pr * pr, axis=1))
+    else:
+        c1 = np.sum(np.log(np.maximum(np.sum(pr * act, axis=1), log_eps)) * adv)
+        c2 = np.sum(-beta * np.sum(np.log(np.maximum(pr, log_eps)) * pr, axis=1))
+    return -(c1 + c2) + cost_v
+
+
+@pytest.mark.parametrize("kind,s,a", CASES)
+def test_torch_autograd_second_opinion(kind, s, a):
+    params, x, y_r, act = _case(kind, s, a, b=17, seed=9)
+    losses, grads = om.loss_and_grads(params, x, y_r, act, kind)
+    P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in params.items()}
+    h = torch.tensor(x, dtype=torch.float64)
+    for name, _, fn in om.layers_of(kind):
+        h = h @ P[f"{name}/w:0"] + P[f"{name}/b:0"]
+        if fn == "sigmoid":
+            h = torch.sigmoid(h)
+    v = (h @ P["logits_v/w:0"] + P["logits_v/b:0"])[:, 0]
+    R, A = torch.tensor(y_r, dtype=torch.float64), torch.tensor(act, dtype=torch.float64)
+    adv = R - v.detach()
+    if kind == "fork_vp":
+        ox = torch.sigmoid(h @ P["logits_p/out_x/w:0"] + P["logits_p/out_x/b:0"])
+        oy = torch.sigmoid(h @ P["logits_p/out_y/w:0"] + P["logits_p/out_y/b:0"])
+        p = torch.atan2(oy - 0.5, ox - 0.5) / np.pi
+        c1 = ((p * A).sum(1) * adv).sum()
+        c2 = (-0.01 * (p * p).sum(1)).sum()
+    else:
+        p = torch.softmax(h @ P["logits_p/w:0"] + P["logits_p/b:0"], dim=1)
+        c1 = (torch.log(torch.clamp((p * A).sum(1), min=1e-6)) * adv).sum()
+        c2 = (-0.01 * (torch.log(torch.clamp(p, min=1e-6)) * p).sum(1)).sum()
+    cost_v = 0.5 * ((R - v) ** 2).sum()
+    cost_all = -(c1 + c2) + cost_v
+    cost_all.backward()
+    assert abs(float(cost_all) - losses["cost_all"]) <= 1e-9 * max(1.0, abs(losses["cost_all"]))
+    for name, g in grads.items():
+        tg = P[name].grad.numpy()
+        assert np.abs(tg - g).max() <= 1e-9 * max(1.0, np.abs(g).max()), name
+    for name in om.dead_params(kind):
+        assert P[name].grad is None
+
+
+def test_discrate_dead_layers_keep_their_values():
+    params, x, y_r, act = _case("discrate", 4, 2)
+    from oracle import oracle_np as onp
+    ms, mom = onp.rmsprop_init(params)
+    _, _, p2, ms2, _ = om.train_step(params, ms, mom, x, y_r, act, "discrate", lr=3e-4)
+    for name in om.dead_params("discrate"):
+        assert np.array_equal(p2[name], params[name]) and np.array_equal(ms2[name], ms[name])
+    assert not np.array_equal(p2["dense1_4_p/w:0"], params["dense1_4_p/w:0"])
