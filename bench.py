@@ -222,6 +222,85 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+def mlp_flops(kind, s, a, train):
+    """Algorithmic flops per sample of the config-4 MLPs: 2 per MAC; training = forward + weight gradients of every layer +
+    data gradients of every layer but the first."""
+    widths = [s, 4, 256, 256, 100, 64] if kind == "fork_vp" else [s, 10]
+    n_out = 1 + 2 * a if kind == "fork_vp" else 1 + a
+    macs = [widths[i] * widths[i + 1] for i in range(len(widths) - 1)] + [widths[-1] * n_out]
+    fwd = 2.0 * sum(macs)
+    return fwd * 3 - 2.0 * macs[0] if train else fwd
+
+
+def run_mlp_section(args, dev, stream, pk, clocks):
+    """BASELINE configs[3]: the fork's low-dimensional networks (fork NetworkVP S=3 A=1, NetworkVP_discrate S=4 A=2) at
+    B = 1024 and 65,536, device-resident and end to end through the plugin API; fp32 SIMT kernels (ga3c_mlp_*)."""
+    import torch
+    from ga3c_b200 import mlp_network
+    from oracle import oracle_mlp as om
+    out = {"note": "BASELINE configs[3] (SURVEY 8a A6/A7): fp32 throughout; mlp_fused keeps a 64-row tile's activations in shared "
+                   "memory through forward, heads, loss and the data-gradient chain; bound = fp32 FMA issue, not HBM"}
+    sm_mhz = clocks.get("sm_max_mhz") or 1965
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12          # TFLOP/s: 128 FMA lanes per SM per clock
+    for kind, s, a, cls in (("fork_vp", 3, 1, mlp_network.NetworkVP), ("discrate", 4, 2, mlp_network.NetworkVP_discrate)):
+        for b in (1024, 65536):
+            rng = np.random.default_rng(12345)
+            net = cls(f"gpu:{dev.index}", "bench_" + kind, a, s, max_batch=b, seed=12345)
+            x = rng.uniform(-1, 1, size=(b, s)).astype(np.float32)
+            y_r = rng.uniform(-1, 1, size=b).astype(np.float32)
+            act = (rng.uniform(-1, 1, size=(b, a)).astype(np.float32) if kind == "fork_vp"
+                   else np.eye(a, dtype=np.float32)[rng.integers(0, a, size=b)])
+            dx, dyr, da = (torch.from_numpy(t).to(dev) for t in (x, y_r, act))
+            p_out = torch.empty((b, a), dtype=torch.float32, device=dev)
+            v_out = torch.empty((b,), dtype=torch.float32, device=dev)
+            steps = 20 if b > 4096 else 100
+
+            def timed(fn):
+                for _ in range(3):
+                    fn()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record(stream)
+                for _ in range(steps):
+                    fn()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / steps
+
+            ms_t = timed(lambda: net.train_device(dx, dyr, da, stream=stream))
+            ms_p = timed(lambda: net.predict_device(dx, p_out, v_out, stream=stream))
+            net.kernel_timing(steps * 4)
+            timed(lambda: net.train_device(dx, dyr, da, stream=stream))
+            kt = {k: round(t / c * 1e3, 2) for k, (t, c) in net.kernel_times().items()}
+            net.kernel_timing(0)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                net.train(x, y_r, act, None, None, 0, fetch_losses=True)
+            s_e2e_t = (time.perf_counter() - t0) / 5
+            t0 = time.perf_counter()
+            for _ in range(5):
+                net.predict_p_and_v(x)
+            s_e2e_p = (time.perf_counter() - t0) / 5
+            row = {"train_samples_per_s": b / (ms_t / 1e3), "train_ms": round(ms_t, 4),
+                   "predictions_per_s": b / (ms_p / 1e3), "predict_ms": round(ms_p, 4),
+                   "e2e_train_samples_per_s": b / s_e2e_t, "e2e_predictions_per_s": b / s_e2e_p,
+                   "kernel_us": kt,
+                   "fp32_tflops_train": round(mlp_flops(kind, s, a, True) * b / (ms_t / 1e3) / 1e12, 3),
+                   "fp32_tflops_predict": round(mlp_flops(kind, s, a, False) * b / (ms_p / 1e3) / 1e12, 3),
+                   "fp32_simt_peak_tflops": round(fp32_peak, 1)}
+            if b == 65536:          # CPU port of the same step (numpy fp32 restatement, bounded sample)
+                params = om.init_params(np.random.default_rng(1), kind, s, a)
+                rows = 8192
+                t0 = time.perf_counter()
+                om.loss_and_grads(params, x[:rows], y_r[:rows], act[:rows], kind, dtype=np.float32)
+                row["cpu_port_train_samples_per_s"] = rows / (time.perf_counter() - t0)
+                row["cpu_port_sample"] = f"1 forward+backward of {rows} rows, numpy fp32 (oracle/oracle_mlp.py), {os.cpu_count()} cores visible"
+            out[f"{kind}_S{s}_A{a}_B{b}"] = row
+            del net
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -442,6 +521,8 @@ def run_ours(args, rank, local_rank, world):
            "gpu_launches": int(launches),
            "clocks": sampler.summary()}
 
+    if world == 1 and not args.no_mlp:
+        out["mlp"] = run_mlp_section(args, dev, stream, pk, out["clocks"])
     if world == 1 and not args.no_cpu_baseline:
         log("[bench] timing the CPU restatement (bounded sample) ...")
         r = cpu_reference_run(args, steps=args.cpu_steps, warmup=1, budget_s=25.0)
@@ -473,6 +554,7 @@ def main():
     ap.add_argument("--predict-batch", type=int, default=4096)
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mlp", action="store_true", help="skip the configs[3] low-dimensional MLP section")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -14,6 +14,15 @@ class ga3c_config(C.Structure):
                 ("log_epsilon", C.c_float), ("min_policy", C.c_float)]
 
 
+class ga3c_mlp_config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("kind", C.c_int32), ("state_dim", C.c_int32), ("num_actions", C.c_int32),
+                ("max_batch", C.c_int32), ("n_dense", C.c_int32), ("dense_width", C.c_int32 * 8),
+                ("rmsprop_decay", C.c_float), ("rmsprop_momentum", C.c_float), ("rmsprop_epsilon", C.c_float),
+                ("log_epsilon", C.c_float), ("min_policy", C.c_float)]
+
+
+MLP_FORK_VP, MLP_DISCRATE = 0, 1
+
 # name -> (restype, argtypes); the single source the symbol-export test checks against the header
 SIGNATURES = {
     "ga3c_last_error": (C.c_char_p, []),
@@ -63,6 +72,26 @@ SIGNATURES = {
     "ga3c_evt_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32, C.POINTER(C.c_int32)]),
     "ga3c_trace_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ga3c_trace_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32]),
+    "ga3c_mlp_create": (C.c_int, [C.POINTER(ga3c_mlp_config), C.POINTER(C.c_void_p)]),
+    "ga3c_mlp_destroy": (C.c_int, [C.c_void_p]),
+    "ga3c_mlp_reserve": (C.c_int, [C.c_void_p, C.c_int32]),
+    "ga3c_mlp_param_count": (C.c_int, [C.c_void_p]),
+    "ga3c_mlp_param_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "ga3c_mlp_arena_floats": (C.c_int64, [C.c_void_p]),
+    "ga3c_mlp_arena_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+    "ga3c_mlp_arena_download": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+    "ga3c_mlp_global_step": (C.c_int64, [C.c_void_p]),
+    "ga3c_mlp_set_global_step": (C.c_int, [C.c_void_p, C.c_int64]),
+    "ga3c_mlp_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ga3c_mlp_forward_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                                            C.c_void_p, C.c_void_p]),
+    "ga3c_mlp_apply_rmsprop": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p]),
+    "ga3c_mlp_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,
+                                      C.c_void_p, C.c_void_p]),
+    "ga3c_mlp_launch_count": (C.c_int64, [C.c_void_p]),
+    "ga3c_mlp_timing_enable": (C.c_int, [C.c_void_p, C.c_int32]),
+    "ga3c_mlp_timing_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
 }
 
 RET_DISCOUNTING, RET_INTERMEDIATE, RET_CLIPPING, RET_NSTEP = 1, 2, 4, 8

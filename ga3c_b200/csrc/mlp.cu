@@ -1,0 +1,538 @@
+// Low-dimensional MLP policy/value networks of the fork (BASELINE config 4), fp32 throughout:
+//   fork NetworkVP          NetworkVP.py:79-105, :175-210   x -> 4 -> 256 -> 256 (linear) -> 100 -> 64 (sigmoid); atan2 angle head
+//   NetworkVP_discrate      NetworkVP_discrate.py:52-85     x -> last DENSE_LAYERS entry (sigmoid); softmax head, A3C loss
+//
+// Three kernels per training step (one per prediction):
+//   mlp_fused   one persistent CTA per SM walks 64-row batch tiles.  A tile's activations stay in shared memory through
+//               all layers, the heads, the loss and the whole data-gradient chain; HBM sees x once, p / v, and (training
+//               only) the layer outputs and pre-activation gradients that the weight-gradient pass needs.
+//   mlp_wgrad   every dW = in^T dz and db = sum dz of the step as 64x64 output tiles, the batch split over CTAs; split s
+//               writes its own partial arena -- no atomics, fixed summation order, bit-reproducible.
+//   mlp_reduce  sums the partial arenas into the gradient arena and the per-tile loss sums into loss[4].
+// RMSProp is the arena kernel of elementwise.cu.  The weights (0.4 MB) stay L2-resident; they are staged through shared
+// memory in 16-row chunks, transposed on the fly for the data gradients (no transposed shadow copy to keep in sync).
+#include "common.cuh"
+#include "kernels.h"
+#include "mlp.cuh"
+
+namespace ga3c {
+
+namespace {
+
+constexpr int LD = 260;              // row pitch (floats) of the activation tiles and of the weight chunk: 16-B aligned rows
+constexpr int RC = 16;               // reduction chunk
+constexpr int HLD = 45;              // row pitch of the head matrix / logits tile (odd: conflict-free column walks)
+constexpr int NT = 256;
+constexpr float PI_F = 3.14159265358979323846f;
+
+constexpr size_t FUSED_SMEM =
+    (size_t)(2 * MLP_TM * LD + RC * LD + MLP_MAX_HID * HLD + MLP_TM * HLD + 48 + 32) * sizeof(float);
+
+__device__ __forceinline__ int round_up16(int v) { return (v + 15) & ~15; }
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + expf(-z)); }
+
+// element (k, j) of the head matrix [hid][n_out]: column 0 = logits_v, then logits_p (discrate) or out_x | out_y (fork_vp)
+__device__ __forceinline__ int head_w_index(const MlpNet& net, int k, int j) {
+  const int A = net.num_actions;
+  if (j == 0) return net.wv_off + k;
+  if (j <= A) return net.wp_off + k * A + (j - 1);
+  return net.wy_off + k * A + (j - 1 - A);
+}
+__device__ __forceinline__ int head_b_index(const MlpNet& net, int j) {
+  const int A = net.num_actions;
+  if (j == 0) return net.bv_off;
+  if (j <= A) return net.bp_off + (j - 1);
+  return net.by_off + (j - 1 - A);
+}
+
+// One 64-row x (128 * JH)-column product through the CTA:  out[r][c] = sum_q in_s[r][q] * Wq[q][c], q < kred, with
+//   TRANS = false:  Wq[q][c] = Wg[q * ldw + c]        (forward:        W is [k][n], q = k, c = n)
+//   TRANS = true :  Wq[q][c] = Wg[c * ldw + q]        (data gradient:  W is [k][n], q = n, c = k)
+// Thread (ty = warp, tx = lane) owns rows ty*8 .. ty*8+7 and columns tx*4 .. tx*4+3 (+128 with JH = 2).  The weight
+// chunk [16][<= 256] of step q0+16 is fetched into registers while chunk q0 is being consumed from shared memory.
+// epi(r, c0, v[4]) receives the finished sums of 4 consecutive columns, turns them into what the next pass reads and
+// stores whatever goes to HBM; the result lands in out_s.  in_s must be zero (finite) up to round_up16(kred).
+template <bool TRANS, int JH, class Epi>
+__device__ __forceinline__ void tile_pass(const float* in_s, float* out_s, float* Wc, int kred, const float* __restrict__ Wg,
+                                          int ldw, int nout, Epi epi) {
+  const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
+  float acc[8][4 * JH];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4 * JH; ++j) acc[i][j] = 0.f;
+
+  float pre[RC];
+  auto fetch = [&](int q0) {
+    if (!TRANS) {
+      const int c = tid;
+#pragma unroll
+      for (int rr = 0; rr < RC; ++rr)
+        pre[rr] = (q0 + rr < kred && c < nout) ? __ldg(Wg + (size_t)(q0 + rr) * ldw + c) : 0.f;
+    } else {
+      const int rr = tid & 15, cb = tid >> 4;
+#pragma unroll
+      for (int i = 0; i < RC; ++i) {
+        const int c = cb + 16 * i;
+        pre[i] = (q0 + rr < kred && c < nout) ? __ldg(Wg + (size_t)c * ldw + q0 + rr) : 0.f;
+      }
+    }
+  };
+  auto stash = [&]() {
+    if (!TRANS) {
+#pragma unroll
+      for (int rr = 0; rr < RC; ++rr) Wc[rr * LD + tid] = pre[rr];
+    } else {
+      const int rr = tid & 15, cb = tid >> 4;
+#pragma unroll
+      for (int i = 0; i < RC; ++i) Wc[rr * LD + cb + 16 * i] = pre[i];
+    }
+  };
+
+  fetch(0);
+  for (int q0 = 0; q0 < kred; q0 += RC) {
+    __syncthreads();                 // the previous chunk is consumed (first trip: in_s is complete)
+    stash();
+    __syncthreads();
+    if (q0 + RC < kred) fetch(q0 + RC);
+#pragma unroll
+    for (int q4 = 0; q4 < RC / 4; ++q4) {
+      float4 a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(in_s + (ty * 8 + i) * LD + q0 + q4 * 4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float4 w[JH];
+#pragma unroll
+        for (int h = 0; h < JH; ++h) w[h] = *reinterpret_cast<const float4*>(Wc + (q4 * 4 + e) * LD + tx * 4 + 128 * h);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float av = e == 0 ? a[i].x : e == 1 ? a[i].y : e == 2 ? a[i].z : a[i].w;
+#pragma unroll
+          for (int h = 0; h < JH; ++h) {
+            acc[i][4 * h + 0] = fmaf(av, w[h].x, acc[i][4 * h + 0]);
+            acc[i][4 * h + 1] = fmaf(av, w[h].y, acc[i][4 * h + 1]);
+            acc[i][4 * h + 2] = fmaf(av, w[h].z, acc[i][4 * h + 2]);
+            acc[i][4 * h + 3] = fmaf(av, w[h].w, acc[i][4 * h + 3]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int h = 0; h < JH; ++h) {
+      float v[4] = {acc[i][4 * h], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]};
+      const int r = ty * 8 + i, c0 = tx * 4 + 128 * h;
+      epi(r, c0, v);
+      *reinterpret_cast<float4*>(out_s + r * LD + c0) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// store 4 consecutive columns c0.. of row `row` of a [B][n] matrix (n need not be a multiple of 4)
+__device__ __forceinline__ void store_row4(float* base, int64_t row, int n, int c0, const float (&v)[4]) {
+  float* dst = base + row * n + c0;
+  if ((n & 3) == 0) {
+    if (c0 < n) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (c0 + e < n) dst[e] = v[e];
+  }
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(NT, 1) mlp_fused_kernel(const MlpNet net, const MlpStepArgs s) {
+  extern __shared__ __align__(16) float smem[];
+  float* buf0 = smem;
+  float* buf1 = buf0 + MLP_TM * LD;
+  float* Wc = buf1 + MLP_TM * LD;
+  float* Wh = Wc + RC * LD;                // [hid][HLD] head matrix, columns >= n_out zero
+  float* lg = Wh + MLP_MAX_HID * HLD;      // [64][HLD] logits, then dlogits
+  float* hb = lg + MLP_TM * HLD;           // [48] head biases
+  float* red = hb + 48;                    // [8 warps][4] loss sums
+  const int tid = threadIdx.x;
+  const int B = s.batch, S = net.state_dim, A = net.num_actions, NL = net.n_layers, hid = net.hid, n_out = net.n_out;
+
+  griddep_launch();
+  griddep_wait(K_MLP_FUSED);               // the weights come from the optimizer launch of the previous step
+
+  for (int idx = tid; idx < hid * 44; idx += NT) {
+    const int k = idx / 44, j = idx - k * 44;
+    Wh[k * HLD + j] = j < n_out ? __ldg(s.w + head_w_index(net, k, j)) : 0.f;
+  }
+  if (tid < 48) hb[tid] = tid < n_out ? __ldg(s.w + head_b_index(net, tid)) : 0.f;
+
+  const int ntiles = (B + MLP_TM - 1) / MLP_TM;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * MLP_TM;
+    __syncthreads();                       // the previous tile is fully consumed (and Wh / hb are staged)
+    {
+      const int Sp = round_up16(S);
+      for (int idx = tid; idx < MLP_TM * Sp; idx += NT) {
+        const int r = idx / Sp, c = idx - r * Sp;
+        buf0[r * LD + c] = (row0 + r < B && c < S) ? s.x[(size_t)(row0 + r) * S + c] : 0.f;
+      }
+    }
+    float* cur = buf0;
+    float* nxt = buf1;
+
+    // ---- forward: out_l = act(in_l W_l + b_l)  (NetworkVP.py:194-210) ----
+    for (int l = 0; l < NL; ++l) {
+      const MlpLayerDesc L = net.L[l];
+      const float* bias = s.w + L.b_off;
+      float* out_g = TRAIN ? s.act[l] : nullptr;
+      auto epi = [&](int r, int c0, float (&v)[4]) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = c0 + e;
+          float z = 0.f;
+          if (c < L.n) {
+            z = v[e] + __ldg(bias + c);
+            if (L.act == MLP_ACT_SIGMOID) z = sigmoidf_(z);
+          }
+          v[e] = z;
+        }
+        if (TRAIN && row0 + r < B) store_row4(out_g, row0 + r, L.n, c0, v);
+      };
+      if (L.n > 128) tile_pass<false, 2>(cur, nxt, Wc, L.k, s.w + L.w_off, L.n, L.n, epi);
+      else tile_pass<false, 1>(cur, nxt, Wc, L.k, s.w + L.w_off, L.n, L.n, epi);
+      float* t = cur; cur = nxt; nxt = t;
+    }
+    __syncthreads();                       // h = cur[64][hid] is complete
+
+    // ---- head logits: thread (row, jq) sums columns jq, jq + 4, ... of h Wh ----
+    {
+      const int row = tid >> 2, jq = tid & 3;
+      float z[11];
+#pragma unroll
+      for (int jj = 0; jj < 11; ++jj) z[jj] = 0.f;
+      for (int k = 0; k < hid; ++k) {
+        const float h = cur[row * LD + k];
+#pragma unroll
+        for (int jj = 0; jj < 11; ++jj) z[jj] = fmaf(h, Wh[k * HLD + jq + 4 * jj], z[jj]);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 11; ++jj) {
+        const int j = jq + 4 * jj;
+        if (j < n_out) lg[row * HLD + j] = z[jj] + hb[j];
+      }
+    }
+    __syncthreads();
+
+    // ---- per row: p, v, loss terms, dlogits ----
+    float l1 = 0.f, l2 = 0.f, lv = 0.f;
+    if (tid < MLP_TM) {
+      const int r = tid;
+      const bool valid = row0 + r < B;
+      float* z = lg + r * HLD;
+      const float v = z[0];
+      float yr = 0.f, adv = 0.f, dv = 0.f;
+      if (TRAIN && valid) {
+        yr = s.yr[row0 + r];
+        adv = yr - v;                     // stop_gradient(v) inside cost_p_1
+        dv = v - yr;
+        lv = 0.5f * (yr - v) * (yr - v);
+      }
+      if (valid && s.v_out != nullptr) s.v_out[row0 + r] = v;
+      if (net.kind == MLP_KIND_FORK_VP) {
+        // p = atan2(sigmoid(out_y) - 0.5, sigmoid(out_x) - 0.5) / pi; softmax_p = log_softmax_p = p  (NetworkVP.py:175-192, :95-101)
+        float sel = 0.f, sq = 0.f;
+        for (int j = 0; j < A; ++j) {
+          const float ox = sigmoidf_(z[1 + j]), oy = sigmoidf_(z[1 + A + j]);
+          const float X = ox - 0.5f, Y = oy - 0.5f;
+          const float p = atan2f(Y, X) / PI_F;
+          if (valid && s.p_out != nullptr) s.p_out[(size_t)(row0 + r) * A + j] = p;
+          if (TRAIN) {
+            float dzx = 0.f, dzy = 0.f;
+            if (valid) {
+              const float av = s.a[(size_t)(row0 + r) * A + j];
+              sel = fmaf(p, av, sel);
+              sq = fmaf(p, p, sq);
+              const float dp = -av * adv + 2.f * s.beta * p;
+              const float inv = 1.f / (PI_F * (X * X + Y * Y));
+              dzx = dp * (-Y * inv) * ox * (1.f - ox);
+              dzy = dp * (X * inv) * oy * (1.f - oy);
+            }
+            z[1 + j] = dzx;
+            z[1 + A + j] = dzy;
+          }
+        }
+        if (TRAIN && valid) { l1 = sel * adv; l2 = -s.beta * sq; }
+      } else {
+        // softmax (+ MIN_POLICY mix), log(max(., eps)) loss terms and their backward  (NetworkVP_discrate.py:66-85)
+        const float inv_mix = 1.f / (1.f + net.min_policy * (float)A);
+        float mx = z[1];
+        for (int j = 1; j < A; ++j) mx = fmaxf(mx, z[1 + j]);
+        float den = 0.f;
+        for (int j = 0; j < A; ++j) den += expf(z[1 + j] - mx);
+        const float inv_den = 1.f / den;
+        float sel = 0.f, ent = 0.f, sh = 0.f;
+        for (int j = 0; j < A; ++j) {
+          const float sm = expf(z[1 + j] - mx) * inv_den;
+          const float p = (sm + net.min_policy) * inv_mix;
+          if (valid && s.p_out != nullptr) s.p_out[(size_t)(row0 + r) * A + j] = p;
+          if (TRAIN && valid) sel = fmaf(p, s.a[(size_t)(row0 + r) * A + j], sel);
+        }
+        if (TRAIN) {
+          const float coef = (valid && sel >= net.log_eps) ? adv / sel : 0.f;
+          // two sweeps: sh = sum_j sm_j h_j first, then dz_j = sm_j (h_j - sh)
+          for (int j = 0; j < A; ++j) {
+            const float sm = expf(z[1 + j] - mx) * inv_den;
+            const float p = (sm + net.min_policy) * inv_mix;
+            const float lgp = logf(fmaxf(p, net.log_eps));
+            const float av = valid ? s.a[(size_t)(row0 + r) * A + j] : 0.f;
+            const float gk = -av * coef + s.beta * (lgp + (p >= net.log_eps ? 1.f : 0.f));
+            ent = fmaf(lgp, p, ent);
+            sh = fmaf(sm, gk * inv_mix, sh);
+          }
+          float dzj[MLP_MAX_OUT];
+          for (int j = 0; j < A; ++j) {
+            const float sm = expf(z[1 + j] - mx) * inv_den;
+            const float p = (sm + net.min_policy) * inv_mix;
+            const float lgp = logf(fmaxf(p, net.log_eps));
+            const float av = valid ? s.a[(size_t)(row0 + r) * A + j] : 0.f;
+            const float gk = -av * coef + s.beta * (lgp + (p >= net.log_eps ? 1.f : 0.f));
+            dzj[j] = valid ? sm * (gk * inv_mix - sh) : 0.f;
+          }
+          for (int j = 0; j < A; ++j) z[1 + j] = dzj[j];
+          if (valid) { l1 = logf(fmaxf(sel, net.log_eps)) * adv; l2 = -s.beta * ent; }
+        }
+      }
+      if (TRAIN) {
+        z[0] = dv;
+        if (valid) {
+          float* dl = s.dlogits + (size_t)(row0 + r) * net.n_out_ld;
+          for (int j = 0; j < n_out; ++j) dl[j] = z[j];
+        }
+      }
+    }
+    if (!TRAIN) continue;
+
+    // loss sums of the tile, fixed order: warp tree, then warp 0 + warp 1
+    if (tid < MLP_TM) {
+      l1 = warp_sum(l1); l2 = warp_sum(l2); lv = warp_sum(lv);
+      if ((tid & 31) == 0) { red[(tid >> 5) * 4 + 0] = l1; red[(tid >> 5) * 4 + 1] = l2; red[(tid >> 5) * 4 + 2] = lv; }
+    }
+    __syncthreads();                       // dlogits tile + loss partials visible
+    if (tid < 4) s.loss_part[(size_t)tile * 4 + tid] = tid < 3 ? red[tid] + red[4 + tid] : 0.f;
+
+    // ---- gradient w.r.t. the last hidden pre-activation: dz = (dlogits Wh^T) * act'(h) ----
+    {
+      const MlpLayerDesc L = net.L[NL - 1];
+      const int row = tid >> 2, kq = tid & 3;
+      const int hp = round_up16(hid);
+      float* dz_g = s.dz[NL - 1];
+      for (int k = kq; k < hp; k += 4) {
+        float d = 0.f;
+        if (k < hid) {
+          for (int j = 0; j < n_out; ++j) d = fmaf(lg[row * HLD + j], Wh[k * HLD + j], d);
+          if (L.act == MLP_ACT_SIGMOID) { const float h = cur[row * LD + k]; d *= h * (1.f - h); }
+          if (row0 + row < B) dz_g[(size_t)(row0 + row) * hid + k] = d;
+        }
+        nxt[row * LD + k] = d;
+      }
+    }
+    { float* t = cur; cur = nxt; nxt = t; }
+
+    // ---- data-gradient chain: dz_{l-1} = (dz_l W_l^T) * act'(out_{l-1}) ----
+    for (int l = NL - 1; l >= 1; --l) {
+      const MlpLayerDesc L = net.L[l];
+      const MlpLayerDesc Lp = net.L[l - 1];
+      const float* out_prev = s.act[l - 1];
+      float* dz_g = s.dz[l - 1];
+      auto epi = [&](int r, int c0, float (&v)[4]) {
+        const bool valid = row0 + r < B;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = c0 + e;
+          float d = 0.f;
+          if (c < Lp.n && valid) {
+            d = v[e];
+            if (Lp.act == MLP_ACT_SIGMOID) { const float o = out_prev[(size_t)(row0 + r) * Lp.n + c]; d *= o * (1.f - o); }
+          }
+          v[e] = d;
+        }
+        if (valid) store_row4(dz_g, row0 + r, Lp.n, c0, v);
+      };
+      if (Lp.n > 128) tile_pass<true, 2>(cur, nxt, Wc, L.n, s.w + L.w_off, L.n, Lp.n, epi);
+      else tile_pass<true, 1>(cur, nxt, Wc, L.n, s.w + L.w_off, L.n, Lp.n, epi);
+      float* t = cur; cur = nxt; nxt = t;
+    }
+  }
+  trace_mark(K_MLP_FUSED, 2);
+}
+
+// ---- weight gradients ---------------------------------------------------------------------------------------
+// blockIdx.x walks the 64x64 output tiles of every dW (hidden layers in order, then the head matrix), blockIdx.y the
+// batch splits.  256 threads = 16 (k quads) x 16 (n quads), 4x4 sums each, rows staged 16 at a time.
+constexpr int WT = 64, WLD = 68;
+__global__ void __launch_bounds__(NT) mlp_wgrad_kernel(const MlpNet net, const MlpStepArgs s, float* part, int64_t part_stride,
+                                                       int rows_per_split) {
+  __shared__ __align__(16) float inC[RC][WLD];
+  __shared__ __align__(16) float dzC[RC][WLD];
+  const int tid = threadIdx.x, NL = net.n_layers;
+  // which tile
+  int t = blockIdx.x, l = 0, K = 0, N = 0, tn = 1;
+  for (; l <= NL; ++l) {
+    K = l < NL ? net.L[l].k : net.hid;
+    N = l < NL ? net.L[l].n : net.n_out;
+    const int tk = (K + WT - 1) / WT;
+    tn = (N + WT - 1) / WT;
+    if (t < tk * tn) break;
+    t -= tk * tn;
+  }
+  if (l > NL) return;
+  const int k0 = (t / tn) * WT, n0 = (t % tn) * WT;
+  const float* in = l == 0 ? s.x : s.act[l - 1];
+  const int ld_in = K;
+  const float* dz = l < NL ? s.dz[l] : s.dlogits;
+  const int ld_dz = l < NL ? N : net.n_out_ld;
+  const int r_begin = blockIdx.y * rows_per_split;
+  const int r_end = min(s.batch, r_begin + rows_per_split);
+
+  griddep_launch();
+  griddep_wait(K_MLP_WGRAD);
+
+  const int cc = tid & 63, rq = tid >> 6;           // staging: column cc, rows rq, rq + 4, rq + 8, rq + 12
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4], bs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float pa[4], pb[4];
+  auto fetch = [&](int r0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + rq + 4 * i;
+      pa[i] = (r < r_end && k0 + cc < K) ? in[(size_t)r * ld_in + k0 + cc] : 0.f;
+      pb[i] = (r < r_end && n0 + cc < N) ? dz[(size_t)r * ld_dz + n0 + cc] : 0.f;
+    }
+  };
+  if (r_begin < r_end) fetch(r_begin);
+  for (int r0 = r_begin; r0 < r_end; r0 += RC) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { inC[rq + 4 * i][cc] = pa[i]; dzC[rq + 4 * i][cc] = pb[i]; }
+    __syncthreads();
+    if (r0 + RC < r_end) fetch(r0 + RC);
+#pragma unroll
+    for (int rr = 0; rr < RC; ++rr) {
+      const float4 a = *reinterpret_cast<const float4*>(&inC[rr][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&dzC[rr][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bs[j] += bv[j];
+    }
+  }
+  float* out = part + (size_t)blockIdx.y * part_stride;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + tx * 4 + j;
+    if (n >= N) continue;
+    // column n of this layer's dz -> (tensor, column) of the arena
+    int w_off, b_off, width, col;
+    if (l < NL) { w_off = net.L[l].w_off; b_off = net.L[l].b_off; width = N; col = n; }
+    else {
+      const int A = net.num_actions;
+      if (n == 0) { w_off = net.wv_off; b_off = net.bv_off; width = 1; col = 0; }
+      else if (n <= A) { w_off = net.wp_off; b_off = net.bp_off; width = A; col = n - 1; }
+      else { w_off = net.wy_off; b_off = net.by_off; width = A; col = n - 1 - A; }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + ty * 4 + i;
+      if (k < K) out[w_off + (size_t)k * width + col] = acc[i][j];
+    }
+    if (k0 == 0 && ty == 0) out[b_off + col] = bs[j];
+  }
+  trace_mark(K_MLP_WGRAD, 2);
+}
+
+// ---- partial arenas -> gradient arena; per-tile loss sums -> loss[4] -----------------------------------------
+__global__ void __launch_bounds__(NT) mlp_reduce_kernel(const float* part, int64_t part_stride, int splits, float* g, int n4,
+                                                        const float* loss_part, int tiles, float* loss_out) {
+  griddep_launch();
+  griddep_wait(K_MLP_REDUCE);
+  const int i = blockIdx.x * NT + threadIdx.x;
+  if (i < n4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sp = 0; sp < splits; ++sp) {
+      const float4 q = __ldcg(reinterpret_cast<const float4*>(part + (size_t)sp * part_stride) + i);
+      acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+    }
+    reinterpret_cast<float4*>(g)[i] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 128 && loss_out != nullptr) {
+    // warp c sums component c: lane adds tiles lane, lane + 32, ... in order, then the fixed shuffle tree
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float v = 0.f;
+    for (int t = lane; t < tiles; t += 32) v += __ldcg(loss_part + (size_t)t * 4 + c);
+    v = warp_sum(v);
+    if (lane == 0) loss_out[c] = v;
+  }
+  trace_mark(K_MLP_REDUCE, 2);
+}
+
+int total_wgrad_tiles(const MlpNet& net) {
+  int t = 0;
+  for (int l = 0; l <= net.n_layers; ++l) {
+    const int K = l < net.n_layers ? net.L[l].k : net.hid, N = l < net.n_layers ? net.L[l].n : net.n_out;
+    t += ((K + WT - 1) / WT) * ((N + WT - 1) / WT);
+  }
+  return t;
+}
+
+}  // namespace
+
+GA3C_TRACE_ATTACH(trace_attach_mlp)
+
+int configure_mlp() {
+  int r = (int)cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM);
+  if (r) return r;
+  return (int)cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM);
+}
+
+int mlp_fused_grid(int batch, int num_sms) {
+  const int tiles = (batch + MLP_TM - 1) / MLP_TM;
+  return tiles < num_sms ? tiles : num_sms;
+}
+
+int launch_mlp_fused(const MlpNet& net, const MlpStepArgs& args, int num_sms, cudaStream_t stream) {
+  const dim3 grid(mlp_fused_grid(args.batch, num_sms));
+  if (args.train) return launch_pdl(mlp_fused_kernel<true>, grid, dim3(NT), FUSED_SMEM, stream, net, args);
+  return launch_pdl(mlp_fused_kernel<false>, grid, dim3(NT), FUSED_SMEM, stream, net, args);
+}
+
+int mlp_wgrad_splits(const MlpNet& net, int batch, int num_sms) {
+  const int tiles = total_wgrad_tiles(net);
+  int splits = (4 * num_sms + tiles - 1) / tiles;
+  const int by_rows = (batch + 127) / 128;            // at least 128 rows per split
+  if (splits > by_rows) splits = by_rows;
+  if (splits > MLP_MAX_SPLITS) splits = MLP_MAX_SPLITS;
+  return splits < 1 ? 1 : splits;
+}
+
+int launch_mlp_wgrad(const MlpNet& net, const MlpStepArgs& args, float* part, int64_t part_stride, int splits,
+                     cudaStream_t stream) {
+  int rows = (args.batch + splits - 1) / splits;
+  rows = (rows + RC - 1) / RC * RC;
+  const dim3 grid(total_wgrad_tiles(net), splits);
+  return launch_pdl(mlp_wgrad_kernel, grid, dim3(NT), 0, stream, net, args, part, part_stride, rows);
+}
+
+int launch_mlp_reduce(const float* part, int64_t part_stride, int splits, float* g, int live_floats, const float* loss_part,
+                      int tiles, float* loss_out, cudaStream_t stream) {
+  const int n4 = live_floats / 4;
+  const int grid = (n4 + NT - 1) / NT;
+  return launch_pdl(mlp_reduce_kernel, dim3(grid < 1 ? 1 : grid), dim3(NT), 0, stream, part, part_stride, splits, g, n4,
+                    loss_part, tiles, loss_out);
+}
+
+}  // namespace ga3c

@@ -1,0 +1,64 @@
+// Launch interface of the low-dimensional MLP networks (BASELINE config 4).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ga3c {
+
+constexpr int MLP_MAX_LAYERS = 8;     // live hidden layers
+constexpr int MLP_MAX_WIDTH = 256;    // of any layer and of the state
+constexpr int MLP_MAX_HID = 128;      // width of the last hidden layer (the one the heads read)
+constexpr int MLP_MAX_OUT = 1 + 2 * 18;
+constexpr int MLP_TM = 64;            // batch rows per tile
+constexpr int MLP_MAX_SPLITS = 32;    // batch splits of the weight-gradient pass (partial arenas)
+constexpr int MLP_ACT_LINEAR = 0, MLP_ACT_SIGMOID = 1;
+constexpr int MLP_KIND_FORK_VP = 0, MLP_KIND_DISCRATE = 1;
+
+struct MlpLayerDesc {
+  int k, n, act;        // fan-in, width, activation
+  int w_off, b_off;     // float offsets into the parameter arena ([k][n] row-major, [n])
+};
+
+// everything the kernels need to know about the network; built once by ga3c_mlp_create
+struct MlpNet {
+  int n_layers;
+  MlpLayerDesc L[MLP_MAX_LAYERS];
+  int kind, state_dim, num_actions;
+  int hid;              // L[n_layers - 1].n
+  int n_out;            // columns of the head matrix: v | p (discrate)  or  v | out_x | out_y (fork_vp)
+  int n_out_ld;         // row pitch of dlogits in HBM (n_out rounded up to 4)
+  int wv_off, bv_off;   // logits_v
+  int wp_off, bp_off;   // logits_p   (fork_vp: logits_p/out_x)
+  int wy_off, by_off;   // fork_vp: logits_p/out_y
+  float log_eps, min_policy;
+};
+
+struct MlpStepArgs {
+  const float* w;                       // parameter arena
+  const float* x;                       // [B, state_dim]
+  const float *yr, *a;                  // train: [B], [B, A]
+  int batch, train;
+  float beta;
+  float *p_out, *v_out;                 // may be null in train mode
+  float* act[MLP_MAX_LAYERS];           // train: layer outputs [B, n_l]
+  float* dz[MLP_MAX_LAYERS];            // train: gradients w.r.t. the pre-activations [B, n_l]
+  float* dlogits;                       // train: [B, n_out_ld]
+  float* loss_part;                     // train: [tiles][4] (cost_p_1, cost_p_2, cost_v, 0) per 64-row tile
+};
+
+int configure_mlp();
+int mlp_fused_grid(int batch, int num_sms);
+// forward (+ heads, loss, and the whole data-gradient chain when args.train) in one persistent kernel
+int launch_mlp_fused(const MlpNet& net, const MlpStepArgs& args, int num_sms, cudaStream_t stream);
+
+// all weight / bias gradients in one grid: split s of tile t writes part[s][arena layout]
+int mlp_wgrad_splits(const MlpNet& net, int batch, int num_sms);
+int launch_mlp_wgrad(const MlpNet& net, const MlpStepArgs& args, float* part, int64_t part_stride, int splits,
+                     cudaStream_t stream);
+// g[i] = sum_s part[s][i] (fixed order) over the live prefix; loss[0..3] = sum over tiles (fixed order)
+int launch_mlp_reduce(const float* part, int64_t part_stride, int splits, float* g, int live_floats, const float* loss_part,
+                      int tiles, float* loss_out, cudaStream_t stream);
+
+int trace_attach_mlp(unsigned long long* buf);
+
+}  // namespace ga3c

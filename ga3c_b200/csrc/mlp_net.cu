@@ -1,0 +1,352 @@
+// C-ABI host layer of the low-dimensional MLP networks (ga3c_mlp_*, include/ga3c_b200.h): handle, arenas, workspace and
+// the launch sequences.  Kernels: mlp.cu (+ the arena RMSProp of elementwise.cu).
+#include <string>
+#include <vector>
+
+#include "../../include/ga3c_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "mlp.cuh"
+
+namespace ga3c {
+int set_error(const std::string& m);   // net.cu (thread-local message behind ga3c_last_error)
+}
+using namespace ga3c;
+
+namespace {
+
+int fail(const char* where, cudaError_t e) {
+  set_error(std::string(where) + ": " + cudaGetErrorString(e));
+  return (int)e ? (int)e : -1;
+}
+#define CK(call)                                            \
+  do {                                                      \
+    cudaError_t _e = (call);                                \
+    if (_e != cudaSuccess) return fail(#call, _e);          \
+  } while (0)
+#define CKL(call)                                           \
+  do {                                                      \
+    int _r = (call);                                        \
+    if (_r != 0) return fail(#call, (cudaError_t)_r);       \
+  } while (0)
+
+struct MlpParam {
+  std::string name;
+  int64_t offset, count;
+  int32_t ndim;
+  int64_t shape[4];
+  int32_t live;
+};
+
+constexpr int64_t ALIGN_FLOATS = 64;
+int64_t align_up(int64_t v) { return (v + ALIGN_FLOATS - 1) / ALIGN_FLOATS * ALIGN_FLOATS; }
+
+}  // namespace
+
+struct ga3c_mlp {
+  ga3c_mlp_config cfg;
+  int num_sms = 148;
+  MlpNet net{};
+  std::vector<MlpParam> params;          // TF creation order
+  int64_t arena_floats = 0, live_floats = 0;   // live tensors are packed first; [live_floats, arena_floats) is never updated
+  float *w = nullptr, *g = nullptr, *ms = nullptr, *mom = nullptr;
+  float* part = nullptr;                 // [MLP_MAX_SPLITS][live_floats] weight-gradient partial arenas
+  // workspace for max_batch rows
+  float* act[MLP_MAX_LAYERS] = {};
+  float* dz[MLP_MAX_LAYERS] = {};
+  float* dlogits = nullptr;
+  float* loss_part = nullptr;
+  int64_t global_step = 0, launches = 0;
+  std::vector<cudaEvent_t> tev;
+  std::vector<int> tkid;
+  int tcursor = 0;
+};
+
+#define LAUNCH(net, kid, st, call)                                                        \
+  do {                                                                                    \
+    const bool _t = !(net)->tev.empty() && (size_t)(2 * (net)->tcursor + 1) < (net)->tev.size(); \
+    if (_t) CK(cudaEventRecord((net)->tev[2 * (net)->tcursor], (st)));                    \
+    CKL(call);                                                                            \
+    if (_t) {                                                                             \
+      CK(cudaEventRecord((net)->tev[2 * (net)->tcursor + 1], (st)));                      \
+      (net)->tkid[(net)->tcursor++] = (kid);                                              \
+    }                                                                                     \
+    (net)->launches++;                                                                    \
+  } while (0)
+
+static void free_workspace(ga3c_mlp* n) {
+  for (int l = 0; l < MLP_MAX_LAYERS; ++l) { cudaFree(n->act[l]); cudaFree(n->dz[l]); n->act[l] = n->dz[l] = nullptr; }
+  cudaFree(n->dlogits); cudaFree(n->loss_part);
+  n->dlogits = n->loss_part = nullptr;
+}
+
+static int alloc_workspace(ga3c_mlp* n, int max_batch) {
+  const size_t mb = (size_t)max_batch;
+  for (int l = 0; l < n->net.n_layers; ++l) {
+    CK(cudaMalloc((void**)&n->act[l], mb * n->net.L[l].n * 4));
+    CK(cudaMalloc((void**)&n->dz[l], mb * n->net.L[l].n * 4));
+  }
+  CK(cudaMalloc((void**)&n->dlogits, mb * n->net.n_out_ld * 4));
+  CK(cudaMalloc((void**)&n->loss_part, ((mb + MLP_TM - 1) / MLP_TM) * 4 * 4));
+  n->cfg.max_batch = max_batch;
+  return 0;
+}
+
+extern "C" int ga3c_mlp_destroy(ga3c_mlp* n) {
+  if (!n) return 0;
+  cudaFree(n->w); cudaFree(n->g); cudaFree(n->ms); cudaFree(n->mom); cudaFree(n->part);
+  free_workspace(n);
+  for (cudaEvent_t e : n->tev) cudaEventDestroy(e);
+  delete n;
+  return 0;
+}
+
+extern "C" int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out) {
+  if (!cfg || !out) return set_error("ga3c_mlp_create: null argument");
+  *out = nullptr;
+  if (cfg->kind != GA3C_MLP_FORK_VP && cfg->kind != GA3C_MLP_DISCRATE) return set_error("ga3c_mlp_create: unknown kind");
+  if (cfg->num_actions < 1 || cfg->num_actions > MAX_ACTIONS) return set_error("ga3c_mlp_create: num_actions must be 1..18");
+  if (cfg->state_dim < 1 || cfg->state_dim > MLP_MAX_WIDTH) return set_error("ga3c_mlp_create: state_dim must be 1..256");
+  if (cfg->max_batch < 1) return set_error("ga3c_mlp_create: max_batch must be >= 1");
+  if (cfg->kind == GA3C_MLP_DISCRATE) {
+    if (cfg->n_dense < 1 || cfg->n_dense > MLP_MAX_LAYERS) return set_error("ga3c_mlp_create: n_dense must be 1..8");
+    for (int i = 0; i < cfg->n_dense; ++i)
+      if (cfg->dense_width[i] < 1 || cfg->dense_width[i] > MLP_MAX_WIDTH)
+        return set_error("ga3c_mlp_create: dense widths must be 1..256");
+    if (cfg->dense_width[cfg->n_dense - 1] > MLP_MAX_HID) return set_error("ga3c_mlp_create: the last dense width must be <= 128");
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return set_error("ga3c_mlp_create: no CUDA device (there is no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return set_error("ga3c_mlp_create: device ordinal out of range");
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return set_error("ga3c_mlp_create: kernels are built for sm_100a only");
+
+  ga3c_mlp* n = new ga3c_mlp();
+  n->cfg = *cfg;
+  n->num_sms = prop.multiProcessorCount;
+  const int S = cfg->state_dim, A = cfg->num_actions;
+  MlpNet& net = n->net;
+  net.kind = cfg->kind; net.state_dim = S; net.num_actions = A;
+  net.log_eps = cfg->log_epsilon; net.min_policy = cfg->min_policy;
+
+  auto add = [&](const std::string& scope, int k, int width, int live) {    // dense_layer: 'w' [k, width] then 'b' [width]
+    MlpParam w{scope + "/w:0", 0, (int64_t)k * width, 2, {k, width, 0, 0}, live};
+    MlpParam b{scope + "/b:0", 0, (int64_t)width, 1, {width, 0, 0, 0}, live};
+    n->params.push_back(w); n->params.push_back(b);
+    return (int)n->params.size() - 2;
+  };
+  std::vector<int> layer_param;          // index of each live hidden layer's 'w' in params
+  if (cfg->kind == GA3C_MLP_FORK_VP) {   // NetworkVP.py:79-85
+    const char* names[5] = {"dense11_p", "dense12_p", "dense13_p", "dense14_p", "dense1"};
+    const int widths[5] = {4, 256, 256, 100, 64};
+    const int acts[5] = {MLP_ACT_LINEAR, MLP_ACT_LINEAR, MLP_ACT_LINEAR, MLP_ACT_SIGMOID, MLP_ACT_SIGMOID};
+    int fan = S;
+    net.n_layers = 5;
+    for (int l = 0; l < 5; ++l) {
+      layer_param.push_back(add(names[l], fan, widths[l], 1));
+      net.L[l].k = fan; net.L[l].n = widths[l]; net.L[l].act = acts[l];
+      fan = widths[l];
+    }
+  } else {                               // NetworkVP_discrate.py:52-56: every layer reads x; the last one is self.denselayer
+    for (int i = 0; i < cfg->n_dense; ++i) {
+      const int live = i == cfg->n_dense - 1;
+      const int idx = add("dense1_" + std::to_string(i + 1) + "_p", S, cfg->dense_width[i], live);
+      if (live) layer_param.push_back(idx);
+    }
+    net.n_layers = 1;
+    net.L[0].k = S; net.L[0].n = cfg->dense_width[cfg->n_dense - 1]; net.L[0].act = MLP_ACT_SIGMOID;
+  }
+  net.hid = net.L[net.n_layers - 1].n;
+  const int pv = add("logits_v", net.hid, 1, 1);
+  int px, py = -1;
+  if (cfg->kind == GA3C_MLP_FORK_VP) {
+    px = add("logits_p/out_x", net.hid, A, 1);
+    py = add("logits_p/out_y", net.hid, A, 1);
+    net.n_out = 1 + 2 * A;
+  } else {
+    px = add("logits_p", net.hid, A, 1);
+    net.n_out = 1 + A;
+  }
+  net.n_out_ld = (net.n_out + 3) & ~3;
+  int64_t cur = 0;
+  for (int pass = 1; pass >= 0; --pass) {          // live tensors first, then the gradient-less ones
+    for (MlpParam& p : n->params)
+      if (p.live == pass) { p.offset = cur; cur = align_up(cur + p.count); }
+    if (pass == 1) n->live_floats = cur;
+  }
+  n->arena_floats = cur;
+  for (int l = 0; l < net.n_layers; ++l) {
+    net.L[l].w_off = (int)n->params[layer_param[l]].offset;
+    net.L[l].b_off = (int)n->params[layer_param[l] + 1].offset;
+  }
+  net.wv_off = (int)n->params[pv].offset; net.bv_off = (int)n->params[pv + 1].offset;
+  net.wp_off = (int)n->params[px].offset; net.bp_off = (int)n->params[px + 1].offset;
+  if (py >= 0) { net.wy_off = (int)n->params[py].offset; net.by_off = (int)n->params[py + 1].offset; }
+
+  const size_t ab = (size_t)n->arena_floats * 4;
+  float** arenas[4] = {&n->w, &n->g, &n->ms, &n->mom};
+  for (float** a : arenas) {
+    e = cudaMalloc((void**)a, ab);
+    if (e != cudaSuccess) { ga3c_mlp_destroy(n); return fail("cudaMalloc", e); }
+    cudaMemset(*a, 0, ab);
+  }
+  {  // ms slot starts at 1.0 [TF-SEMANTICS]
+    std::vector<float> ones((size_t)n->arena_floats, 1.0f);
+    cudaMemcpy(n->ms, ones.data(), ab, cudaMemcpyHostToDevice);
+  }
+  e = cudaMalloc((void**)&n->part, (size_t)MLP_MAX_SPLITS * n->live_floats * 4);
+  if (e != cudaSuccess) { ga3c_mlp_destroy(n); return fail("cudaMalloc", e); }
+  cudaMemset(n->part, 0, (size_t)MLP_MAX_SPLITS * n->live_floats * 4);
+  if (int r = alloc_workspace(n, cfg->max_batch)) { ga3c_mlp_destroy(n); return r; }
+  if (int r = configure_mlp()) { ga3c_mlp_destroy(n); return fail("cudaFuncSetAttribute", (cudaError_t)r); }
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { ga3c_mlp_destroy(n); return fail("ga3c_mlp_create sync", e); }
+  *out = n;
+  return 0;
+}
+
+extern "C" int ga3c_mlp_reserve(ga3c_mlp* n, int32_t max_batch) {
+  if (!n) return set_error("ga3c_mlp_reserve: null handle");
+  if (max_batch <= n->cfg.max_batch) return 0;
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaDeviceSynchronize());
+  free_workspace(n);
+  if (int r = alloc_workspace(n, max_batch)) { n->cfg.max_batch = 0; return r; }
+  return 0;
+}
+
+extern "C" int ga3c_mlp_param_count(const ga3c_mlp* n) { return n ? (int)n->params.size() : 0; }
+
+extern "C" int ga3c_mlp_param_info(const ga3c_mlp* n, int i, const char** name, int64_t* offset, int32_t* ndim,
+                                   int64_t shape[4], int32_t* live) {
+  if (!n || i < 0 || i >= (int)n->params.size()) return set_error("ga3c_mlp_param_info: bad index");
+  const MlpParam& d = n->params[i];
+  if (name) *name = d.name.c_str();
+  if (offset) *offset = d.offset;
+  if (ndim) *ndim = d.ndim;
+  if (shape) for (int k = 0; k < 4; ++k) shape[k] = d.shape[k];
+  if (live) *live = d.live;
+  return 0;
+}
+
+extern "C" int64_t ga3c_mlp_arena_floats(const ga3c_mlp* n) { return n ? n->arena_floats : 0; }
+
+static float* arena_of(ga3c_mlp* n, int which) {
+  switch (which) { case 0: return n->w; case 1: return n->g; case 2: return n->ms; case 3: return n->mom; }
+  return nullptr;
+}
+
+extern "C" int ga3c_mlp_arena_upload(ga3c_mlp* n, int which, const float* host, int64_t nf) {
+  if (!n || !host) return set_error("ga3c_mlp_arena_upload: null argument");
+  float* dst = arena_of(n, which);
+  if (!dst || nf != n->arena_floats) return set_error("ga3c_mlp_arena_upload: bad arena id or size");
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(dst, host, (size_t)nf * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int ga3c_mlp_arena_download(ga3c_mlp* n, int which, float* host, int64_t nf) {
+  if (!n || !host) return set_error("ga3c_mlp_arena_download: null argument");
+  float* src = arena_of(n, which);
+  if (!src || nf != n->arena_floats) return set_error("ga3c_mlp_arena_download: bad arena id or size");
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(host, src, (size_t)nf * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int64_t ga3c_mlp_global_step(const ga3c_mlp* n) { return n ? n->global_step : -1; }
+extern "C" int ga3c_mlp_set_global_step(ga3c_mlp* n, int64_t s) { if (!n) return -1; n->global_step = s; return 0; }
+extern "C" int64_t ga3c_mlp_launch_count(const ga3c_mlp* n) { return n ? n->launches : 0; }
+
+static int check_batch(ga3c_mlp* n, int batch, const char* who) {
+  if (!n) return set_error(std::string(who) + ": null handle");
+  if (batch < 1 || batch > n->cfg.max_batch)
+    return set_error(std::string(who) + ": batch " + std::to_string(batch) + " outside 1.." + std::to_string(n->cfg.max_batch));
+  return 0;
+}
+
+static MlpStepArgs step_args(ga3c_mlp* n, const float* x, int batch) {
+  MlpStepArgs s{};
+  s.w = n->w; s.x = x; s.batch = batch;
+  for (int l = 0; l < n->net.n_layers; ++l) { s.act[l] = n->act[l]; s.dz[l] = n->dz[l]; }
+  s.dlogits = n->dlogits; s.loss_part = n->loss_part;
+  return s;
+}
+
+extern "C" int ga3c_mlp_predict(ga3c_mlp* n, const float* x, int32_t batch, float* p_out, float* v_out, void* stream) {
+  if (int r = check_batch(n, batch, "ga3c_mlp_predict")) return r;
+  if (!x || !p_out || !v_out) return set_error("ga3c_mlp_predict: null buffer");
+  CK(cudaSetDevice(n->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  MlpStepArgs s = step_args(n, x, batch);
+  s.p_out = p_out; s.v_out = v_out; s.train = 0;
+  LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(n->net, s, n->num_sms, st));
+  return 0;
+}
+
+extern "C" int ga3c_mlp_forward_backward(ga3c_mlp* n, const float* x, const float* yr, const float* a, int32_t batch,
+                                         float beta, float* loss, void* stream) {
+  if (int r = check_batch(n, batch, "ga3c_mlp_forward_backward")) return r;
+  if (!x || !yr || !a) return set_error("ga3c_mlp_forward_backward: null buffer");
+  CK(cudaSetDevice(n->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  MlpStepArgs s = step_args(n, x, batch);
+  s.yr = yr; s.a = a; s.beta = beta; s.train = 1;
+  LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(n->net, s, n->num_sms, st));
+  const int splits = mlp_wgrad_splits(n->net, batch, n->num_sms);
+  LAUNCH(n, K_MLP_WGRAD, st, launch_mlp_wgrad(n->net, s, n->part, n->live_floats, splits, st));
+  LAUNCH(n, K_MLP_REDUCE, st, launch_mlp_reduce(n->part, n->live_floats, splits, n->g, (int)n->live_floats, n->loss_part,
+                                                (batch + MLP_TM - 1) / MLP_TM, loss, st));
+  return 0;
+}
+
+extern "C" int ga3c_mlp_apply_rmsprop(ga3c_mlp* n, float lr, void* stream) {
+  if (!n) return set_error("ga3c_mlp_apply_rmsprop: null handle");
+  CK(cudaSetDevice(n->cfg.device));
+  RmsPropArgs a{};
+  a.w = n->w; a.ms = n->ms; a.mom = n->mom; a.g = n->g; a.w1_shadow = nullptr;
+  a.n_floats = n->live_floats;           // the gradient-less variables behind the live prefix are never touched
+  a.w1_offset = n->live_floats; a.w1_count = 0;
+  a.lr = lr; a.decay = n->cfg.rmsprop_decay; a.momentum = n->cfg.rmsprop_momentum; a.eps = n->cfg.rmsprop_epsilon;
+  LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop(a, (cudaStream_t)stream));
+  n->global_step += 1;                   // opt.minimize(..., global_step=self.global_step)
+  return 0;
+}
+
+extern "C" int ga3c_mlp_train_step(ga3c_mlp* n, const float* x, const float* yr, const float* a, int32_t batch, float lr,
+                                   float beta, float* loss, void* stream) {
+  if (int r = ga3c_mlp_forward_backward(n, x, yr, a, batch, beta, loss, stream)) return r;
+  return ga3c_mlp_apply_rmsprop(n, lr, stream);
+}
+
+extern "C" int ga3c_mlp_timing_enable(ga3c_mlp* n, int32_t max_records) {
+  if (!n || max_records < 0) return set_error("ga3c_mlp_timing_enable: bad argument");
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaDeviceSynchronize());
+  for (cudaEvent_t e : n->tev) cudaEventDestroy(e);
+  n->tev.clear(); n->tkid.clear(); n->tcursor = 0;
+  n->tev.resize((size_t)2 * max_records);
+  n->tkid.assign((size_t)max_records, 0);
+  for (auto& e : n->tev) CK(cudaEventCreate(&e));
+  return 0;
+}
+
+extern "C" int ga3c_mlp_timing_collect(ga3c_mlp* n, double* total_ms, int64_t* counts, int32_t n_kernels) {
+  if (!n || !total_ms || !counts || n_kernels < K_COUNT) return set_error("ga3c_mlp_timing_collect: bad argument");
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaDeviceSynchronize());
+  for (int k = 0; k < n_kernels; ++k) { total_ms[k] = 0.0; counts[k] = 0; }
+  for (int r = 0; r < n->tcursor; ++r) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, n->tev[2 * r], n->tev[2 * r + 1]));
+    total_ms[n->tkid[r]] += ms;
+    counts[n->tkid[r]] += 1;
+  }
+  n->tcursor = 0;
+  return 0;
+}

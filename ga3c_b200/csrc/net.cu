@@ -9,6 +9,7 @@
 #include "../../include/ga3c_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "mlp.cuh"
 
 using namespace ga3c;
 
@@ -89,7 +90,8 @@ struct ga3c_net {
 constexpr int DP_COMM_BYTES = 256;    // [0] ready step, [8] done step (uint64 at 64-byte spacing)
 
 static const char* const kKernelNames[K_COUNT] = {"conv_fwd", "dense_fwd", "heads", "dense_wgrad", "dense_bwd",
-                                                  "conv_bwd", "conv11_wgrad", "rmsprop", "grad_reduce"};
+                                                  "conv_bwd", "conv11_wgrad", "rmsprop", "grad_reduce",
+                                                  "mlp_fused", "mlp_wgrad", "mlp_reduce"};
 
 // launch one kernel of the path; when timing is enabled bracket it with events on the same stream
 #define LAUNCH(net, kid, st, call)                                                        \
@@ -109,6 +111,10 @@ enum { P_C11W = 0, P_C11B, P_C12W, P_C12B, P_D1W, P_D1B, P_VW, P_VB, P_PW, P_PB,
 static int alloc_workspace(ga3c_net* n, int max_batch);
 static int trace_attach_all(unsigned long long* buf);
 
+namespace ga3c {
+int set_error(const std::string& m) { g_err = m; return -1; }     // for the other host files (mlp_net.cu)
+const char* kernel_name(int kid) { return (kid >= 0 && kid < K_COUNT) ? kKernelNames[kid] : nullptr; }
+}
 extern "C" const char* ga3c_last_error(void) { return g_err.c_str(); }
 extern "C" int ga3c_abi_version(void) { return 1; }
 
@@ -570,7 +576,7 @@ static void timing_free(ga3c_net* n) {
 static int trace_attach_all(unsigned long long* buf) {
   int r;
   if ((r = trace_attach_conv_fwd(buf)) || (r = trace_attach_conv_bwd_fused(buf)) || (r = trace_attach_dense_tc(buf)) ||
-      (r = trace_attach_heads(buf)) || (r = trace_attach_elementwise(buf)))
+      (r = trace_attach_heads(buf)) || (r = trace_attach_elementwise(buf)) || (r = trace_attach_mlp(buf)))
     return r;
   return 0;
 }

@@ -142,6 +142,57 @@ int ga3c_returns(const double* rewards_dev, const int64_t* seg_offsets_dev, int3
 int ga3c_select_actions(const float* p_dev, const double* u_dev, int32_t batch, int32_t num_actions,
                         int32_t* action_dev, void* stream);
 
+/* ---- low-dimensional MLP networks (BASELINE config 4) --------------------------
+ * The fork's two non-conv `Network` plugins behind the same call shapes, fp32 throughout:
+ *   GA3C_MLP_FORK_VP   NetworkVP.py:79-105 (+ :175-210): x[S] -> dense 4 -> 256 -> 256 (all linear) -> 100 (sigmoid) ->
+ *                      'dense1' 64 (sigmoid); v = dense 1; p = atan2(sigmoid(out_y) - 0.5, sigmoid(out_x) - 0.5) / pi;
+ *                      softmax_p = log_softmax_p = p (:95-96); cost_p_1 = sum_a(p a) (R - sg(v)); cost_p_2 = -beta sum p^2.
+ *                      `a` is whatever ProcessAgent hands over ([B, A] float32; the continuous action for Pendulum).
+ *   GA3C_MLP_DISCRATE  NetworkVP_discrate.py:52-85 AS WRITTEN: every Config.DENSE_LAYERS entry is built from x (:55), so
+ *                      only the LAST one (sigmoid, the default func of dense_layer, NetworkVP.py:194) feeds the heads; the
+ *                      earlier ones are variables without a gradient: listed by ga3c_mlp_param_info with live = 0, never
+ *                      touched by the optimizer (tf's minimize skips variables whose gradient is None).  Heads / loss as
+ *                      the conv net: softmax + MIN_POLICY mix, log(max(., eps)) terms (:66-85).
+ * All variables start U(-0.3, 0.3) in the reference (NetworkVP.py:199-202): the host uploads them (ga3c_mlp_arena_upload).
+ * ga3c_mlp_predict       replaces sess.run([softmax_p, logits_v])  (NetworkVP.py:248-252)
+ * ga3c_mlp_train_step    replaces sess.run(train_op)               (NetworkVP.py:254-257)
+ * loss_dev as for the conv net: {cost_p_1_agg, cost_p_2_agg, cost_v, 0}.                                             */
+typedef struct ga3c_mlp ga3c_mlp;
+#define GA3C_MLP_FORK_VP 0
+#define GA3C_MLP_DISCRATE 1
+typedef struct ga3c_mlp_config {
+  int32_t device;
+  int32_t kind;              /* GA3C_MLP_*                                                             */
+  int32_t state_dim;         /* S, 1..256                                                              */
+  int32_t num_actions;       /* A, 1..18                                                               */
+  int32_t max_batch;
+  int32_t n_dense;           /* DISCRATE: len(Config.DENSE_LAYERS), 1..8; FORK_VP: ignored             */
+  int32_t dense_width[8];    /* DISCRATE: Config.DENSE_LAYERS (each 1..256, the last <= 128)           */
+  float   rmsprop_decay, rmsprop_momentum, rmsprop_epsilon, log_epsilon, min_policy;
+} ga3c_mlp_config;
+int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out);
+int ga3c_mlp_destroy(ga3c_mlp* net);
+int ga3c_mlp_reserve(ga3c_mlp* net, int32_t max_batch);
+/* variables in TF creation order; live = 0 for the gradient-less variables of DISCRATE */
+int     ga3c_mlp_param_count(const ga3c_mlp* net);
+int     ga3c_mlp_param_info(const ga3c_mlp* net, int index, const char** name, int64_t* offset, int32_t* ndim,
+                            int64_t shape[4], int32_t* live);
+int64_t ga3c_mlp_arena_floats(const ga3c_mlp* net);
+int ga3c_mlp_arena_upload(ga3c_mlp* net, int which, const float* host, int64_t n_floats);   /* which: 0 params, 1 grads, 2 ms, 3 mom */
+int ga3c_mlp_arena_download(ga3c_mlp* net, int which, float* host, int64_t n_floats);
+int64_t ga3c_mlp_global_step(const ga3c_mlp* net);
+int ga3c_mlp_set_global_step(ga3c_mlp* net, int64_t step);
+int ga3c_mlp_predict(ga3c_mlp* net, const float* x_dev, int32_t batch, float* p_dev, float* v_dev, void* stream);
+int ga3c_mlp_forward_backward(ga3c_mlp* net, const float* x_dev, const float* yr_dev, const float* a_dev, int32_t batch,
+                              float beta, float* loss_dev, void* stream);
+int ga3c_mlp_apply_rmsprop(ga3c_mlp* net, float learning_rate, void* stream);
+int ga3c_mlp_train_step(ga3c_mlp* net, const float* x_dev, const float* yr_dev, const float* a_dev, int32_t batch,
+                        float learning_rate, float beta, float* loss_dev, void* stream);
+int64_t ga3c_mlp_launch_count(const ga3c_mlp* net);
+/* per-kernel event timing, as ga3c_timing_* (kernel ids are shared: ga3c_kernel_name) */
+int ga3c_mlp_timing_enable(ga3c_mlp* net, int32_t max_records);
+int ga3c_mlp_timing_collect(ga3c_mlp* net, double* total_ms, int64_t* counts, int32_t n_kernels);
+
 /* ---- introspection for tests / profiling ---------------------------------------------------- */
 /* device pointers to the activation workspace of the last call (bf16 stored as uint16):
  * which: 0 n1 [B,441,16] bf16, 1 n2 [B,3872] bf16, 2 d1 [B,256] fp32, 3 dd1 [B,256] bf16,
