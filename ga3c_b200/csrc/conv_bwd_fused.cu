@@ -38,6 +38,7 @@
 #include "kernels.h"
 #include "tcgen05.cuh"
 #include "conv_blk.cuh"
+#include "dp_exchange.cuh"
 
 namespace ga3c {
 
@@ -89,7 +90,17 @@ template <bool U8>       // U8: frames are uint8 [B,28224] (x = k/128 - 1 applie
 __global__ void __launch_bounds__(FB_THREADS, 1)
 conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, const uint16_t* __restrict__ dn2,
                 const float* __restrict__ w12, uint16_t* __restrict__ dn1_out, float* __restrict__ g_w11,
-                float* __restrict__ g_b11, float* __restrict__ g_w12, float* __restrict__ g_b12, int64_t gp_stride, int batch) {
+                float* __restrict__ g_b11, float* __restrict__ g_w12, float* __restrict__ g_b12, int64_t gp_stride, int batch,
+                int n_conv, const DpBigArgs dp) {
+  // data parallel: CTAs [n_conv, gridDim.x) are exchange CTAs -- they move dense1/w (final since dense_bwd, the launch
+  // this one depends on) between the ranks while CTAs [0, n_conv) compute the conv gradients (dp_exchange.cuh)
+  if ((int)blockIdx.x >= n_conv) {
+    griddep_launch();
+    griddep_wait(K_DP_BIG);
+    dp_big_exchange(dp, (int)blockIdx.x - n_conv, (int)gridDim.x - n_conv);
+    trace_mark(K_DP_BIG, 2);
+    return;
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* const smem = smem_raw + (sbase - smem_u32(smem_raw));
@@ -99,7 +110,7 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
   float* red = reinterpret_cast<float*>(smem + FB_OFF_RED);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   EvtLog evt_i = evt_open();                                      // pipeline event log of CTA 0 (ga3c_evt_*), off unless attached
-  const int stride = gridDim.x;
+  const int stride = n_conv;
   const int n_frames = ((int)blockIdx.x < batch) ? (batch - 1 - (int)blockIdx.x) / stride + 1 : 0;
   const int n_chunks = n_frames * PW_NCHUNK;                       // chunk stream of this CTA: q = k * 21 + c, warp q % 6
   auto frame_of = [&](int k) { return (size_t)(blockIdx.x + k * stride); };
@@ -444,7 +455,7 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
 GA3C_TRACE_ATTACH(trace_attach_conv_bwd_fused)
 GA3C_EVT_ATTACH(evt_attach_conv_bwd)
 
-int conv_bwd_grid(int batch, int num_sms) { return min(batch, num_sms); }
+int conv_bwd_grid(int batch, int num_sms, int n_exch) { return min(batch, num_sms - n_exch); }
 
 int configure_conv_bwd_fused() {
   cudaError_t e = cudaFuncSetAttribute(conv_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
@@ -454,12 +465,16 @@ int configure_conv_bwd_fused() {
 
 int launch_conv_bwd(const void* x, bool x_u8, const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1_out,
                     float* g_w11, float* g_b11, float* g_w12, float* g_b12, int64_t gp_stride, int batch, int num_sms,
-                    cudaStream_t stream) {
+                    const DpBigArgs* dp, cudaStream_t stream) {
+  DpBigArgs d{};
+  if (dp != nullptr) d = *dp;
+  const int n_conv = conv_bwd_grid(batch, num_sms, d.n_exch);
+  const dim3 grid(n_conv + d.n_exch);
   if (x_u8)
-    return launch_pdl(conv_bwd_kernel<true>, dim3(conv_bwd_grid(batch, num_sms)), dim3(FB_THREADS), FB_SMEM, stream, x, n1, dn2,
-                      w12, dn1_out, g_w11, g_b11, g_w12, g_b12, gp_stride, batch);
-  return launch_pdl(conv_bwd_kernel<false>, dim3(conv_bwd_grid(batch, num_sms)), dim3(FB_THREADS), FB_SMEM, stream, x, n1, dn2,
-                    w12, dn1_out, g_w11, g_b11, g_w12, g_b12, gp_stride, batch);
+    return launch_pdl(conv_bwd_kernel<true>, grid, dim3(FB_THREADS), FB_SMEM, stream, x, n1, dn2,
+                      w12, dn1_out, g_w11, g_b11, g_w12, g_b12, gp_stride, batch, n_conv, d);
+  return launch_pdl(conv_bwd_kernel<false>, grid, dim3(FB_THREADS), FB_SMEM, stream, x, n1, dn2,
+                    w12, dn1_out, g_w11, g_b11, g_w12, g_b12, gp_stride, batch, n_conv, d);
 }
 
 }  // namespace ga3c

@@ -2,6 +2,7 @@
 // returns, action sampling.
 #include "common.cuh"
 #include "kernels.h"
+#include "dp_exchange.cuh"
 
 namespace ga3c {
 
@@ -215,14 +216,16 @@ int launch_rmsprop_reduce(const RmsPropArgs& a, const GradReduceArgs& r, cudaStr
 // reduce-scatter(gradients) -> RMSProp on the owned slice -> all-gather(weights), fused in ONE kernel:
 // the gradient slice is read from every rank's slab with plain loads through NVLink (P2P mappings), the
 // updated fp32 weights and the bf16 shadow of dense1/w are stored into every rank's slab.  Cross-rank
-// ordering uses two monotonically increasing step flags per rank, kept in its own slab:
-//   ready = s  "my gradients of step s are final"        written when my kernel starts (it is stream-ordered
-//                                                          after my backward); every block waits for all ranks
-//   done  = s  "my slice of step s is stored everywhere"  written by the LAST block of my grid to finish, which
-//                                                          then waits for every rank's done before the kernel ends,
-//                                                          so the next forward (stream-ordered) sees all slices
+// ordering uses two monotonically increasing step flags per rank, PUSHED into every rank's slab (a waiter polls its own
+// HBM; polling a peer's slab costs an NVLink round trip per probe):
+//   ready[r] = s  "rank r's gradients of step s are final"        stored when r's kernel starts (it is stream-ordered
+//                                                                   after r's backward); every block waits for all ranks
+//   done[r]  = s  "rank r's slice of step s is stored everywhere"  stored by the LAST block of r's grid to finish, which
+//                                                                   then waits for every rank's done before the kernel ends,
+//                                                                   so the next forward (stream-ordered) sees all slices
 // No block waits on another block of its own grid, so progress does not depend on co-residency.
-// comm block layout (bytes): [0] ready u64, [64] done u64, [128] finished-block counter u32
+// comm block layout (bytes): [64 r] ready[r] u64, [512 + 64 r] done[r] u64, [1024] finished-block counter u32, [1028] the
+// slab-reduction phase's counter
 __device__ __forceinline__ uint64_t ld_flag(const uint64_t* p) {
   uint64_t v;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
@@ -287,20 +290,21 @@ __global__ void __launch_bounds__(512) rmsprop_dp_kernel(RmsPropDpArgs d) {
     }
     if (threadIdx.x == 0) {
       __threadfence_system();          // the reduced gradients are read by the peers
-      unsigned int* ctr = reinterpret_cast<unsigned int*>(my_comm + 132);
+      unsigned int* ctr = reinterpret_cast<unsigned int*>(my_comm + DPC_CTR_RED);
       last_red = atomicAdd(ctr, 1u) == gridDim.x - 1;
       if (last_red) {
         *ctr = 0;
         __threadfence_system();
-        st_flag(reinterpret_cast<uint64_t*>(my_comm), d.step);     // my gradients are final
+        for (int r = 0; r < d.world; ++r)                            // my gradients are final
+          st_flag(reinterpret_cast<uint64_t*>(d.peer[r] + d.comm_offset + 64 * d.rank), d.step);
       }
     }
-  } else if (blockIdx.x == 0 && threadIdx.x == 0) {
-    st_flag(reinterpret_cast<uint64_t*>(my_comm), d.step);         // my gradients are final
+  } else if (blockIdx.x == 0 && (int)threadIdx.x < d.world) {
+    st_flag(reinterpret_cast<uint64_t*>(d.peer[threadIdx.x] + d.comm_offset + 64 * d.rank), d.step);   // my gradients are final
   }
   if ((int)threadIdx.x < d.world) {
-    const uint64_t* f = reinterpret_cast<const uint64_t*>(d.peer[threadIdx.x] + d.comm_offset);
-    while (ld_flag(f) < d.step) __nanosleep(32);
+    const uint64_t* f = reinterpret_cast<const uint64_t*>(my_comm + 64 * threadIdx.x);
+    while (ld_flag(f) < d.step) { }
     __threadfence_system();
   }
   __syncthreads();
@@ -352,18 +356,19 @@ __global__ void __launch_bounds__(512) rmsprop_dp_kernel(RmsPropDpArgs d) {
   if (threadIdx.x == 0) {
     __threadfence_system();            // cumulative: orders the block's peer stores (observed through the barrier)
     evt_mark(evt_i, 64, 0);
-    unsigned int* ctr = reinterpret_cast<unsigned int*>(my_comm + 128);
+    unsigned int* ctr = reinterpret_cast<unsigned int*>(my_comm + DPC_CTR_DONE);
     last = atomicAdd(ctr, 1u) == gridDim.x - 1;
     if (last) {
       *ctr = 0;
       __threadfence_system();
-      st_flag(reinterpret_cast<uint64_t*>(my_comm + 64), d.step);
+      for (int r = 0; r < d.world; ++r)
+        st_flag(reinterpret_cast<uint64_t*>(d.peer[r] + d.comm_offset + DPC_DONE + 64 * d.rank), d.step);
     }
   }
   __syncthreads();
   if (last && (int)threadIdx.x < d.world) {
-    const uint64_t* f = reinterpret_cast<const uint64_t*>(d.peer[threadIdx.x] + d.comm_offset + 64);
-    while (ld_flag(f) < d.step) __nanosleep(32);
+    const uint64_t* f = reinterpret_cast<const uint64_t*>(my_comm + DPC_DONE + 64 * threadIdx.x);
+    while (ld_flag(f) < d.step) { }
     __threadfence_system();
   }
   if (last) evt_mark(evt_i, 65, blockIdx.x);
@@ -371,6 +376,111 @@ __global__ void __launch_bounds__(512) rmsprop_dp_kernel(RmsPropDpArgs d) {
 }
 
 GA3C_EVT_ATTACH(evt_attach_elementwise)
+
+// ---- overlapped data-parallel exchange, second instalment (dp_exchange.cuh) ---------------------------------
+// One block per 32-float4 column block of the small-tensor prefix (+ the loss sums).  Block cb sums this rank's per-CTA
+// slabs for its columns (same order and bits as grad_reduce_kernel); its 32 owner threads push the sums into every peer's
+// receive buffer in the LL wire format, collect the peers' contributions from this rank's own receive buffer, add them in
+// rank order (every rank computes the identical sum) and apply RMSProp to the local copy.  Receive buffers alternate with
+// the step parity: a peer pushes step s + 2 only after it has seen this rank's step s + 1, i.e. after this rank's step-s
+// launch has ended.  Block 0 keeps the launch open until every rank's dense1/w slice (exchange CTAs of the conv backward
+// launch) has landed.
+template <bool HAS_MOM>
+__global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_small_kernel(RmsPropDpArgs d, int64_t recv_offset) {
+  __shared__ float4 part[GR_LANES][GR_COLS];
+  const RmsPropArgs& a = d.base;
+  const GradReduceArgs& r = d.red;
+  EvtLog evt_i = evt_open();
+  const int col = threadIdx.x & (GR_COLS - 1), sl = threadIdx.x / GR_COLS;
+  const int cb = blockIdx.x;
+  const int j = (cb * GR_COLS + col) * 4;
+  const bool owner = sl == 0 && j < r.out_floats;
+  uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
+  int count = 0;
+  if (j < r.n_floats) {
+#pragma unroll
+    for (int s = GR_MAX_SEG - 1; s >= 0; --s)
+      if (j < r.seg_end[s]) count = r.seg_count[s];
+  }
+  // w / ms of the small prefix were last written by this kernel one step ago: fetch them before the dependency wait
+  float4 w = make_float4(0.f, 0.f, 0.f, 0.f), ms = w, mo = w;
+  if (owner) {
+    w = *reinterpret_cast<const float4*>(a.w + j);
+    ms = *reinterpret_cast<const float4*>(a.ms + j);
+    if (HAS_MOM) mo = *reinterpret_cast<const float4*>(a.mom + j);
+  }
+  griddep_launch();
+  evt_mark(evt_i, 60, 0);
+  griddep_wait(K_RMSPROP);            // the slabs come from the conv backward launch that precedes this one
+  evt_mark(evt_i, 61, 0);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* src = r.part + j;
+  for (int i0 = sl; i0 < count; i0 += GR_UNROLL * GR_LANES) {
+    float4 q[GR_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GR_UNROLL; ++u) {
+      const int i = i0 + u * GR_LANES;
+      q[u] = i < count ? __ldcg(reinterpret_cast<const float4*>(src + (int64_t)i * r.stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < GR_UNROLL; ++u) { acc.x += q[u].x; acc.y += q[u].y; acc.z += q[u].z; acc.w += q[u].w; }
+  }
+  part[sl][col] = acc;
+  __syncthreads();
+  if (sl == 0 && j < r.n_floats) {
+#pragma unroll
+    for (int l = 1; l < GR_LANES; ++l) {
+      const float4 q = part[l][col];
+      acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+    }
+    if (j >= r.out_floats && r.out_tail != nullptr) {
+      float* t = r.out_tail + (j - r.out_floats);
+      t[0] = acc.x; t[1] = acc.y; t[2] = acc.z; t[3] = acc.w;
+    }
+  }
+  evt_mark(evt_i, 62, 0);
+  if (owner) {
+    // receive buffers: [parity][source rank][small prefix in LL format: 8 bytes per float]
+    const uint32_t flag = (uint32_t)d.step;
+    const int64_t slot = recv_offset + ((int64_t)(d.step & 1) * DP_WORLD_MAX + d.rank) * r.out_floats * 8 + (int64_t)j * 8;
+#pragma unroll
+    for (int q = 0; q < DP_WORLD_MAX; ++q)
+      if (q < d.world && q != d.rank) dp_ll_store(d.peer[q] + slot, acc, flag);
+    *reinterpret_cast<float4*>(r.out + j) = acc;                     // this rank's own gradient (introspection)
+    evt_mark(evt_i, 66, 0);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < DP_WORLD_MAX; ++q)
+      if (q < d.world) {
+        const float4 v = q == d.rank ? acc
+                                     : dp_ll_load(d.peer[d.rank] + recv_offset +
+                                                      ((int64_t)(d.step & 1) * DP_WORLD_MAX + q) * r.out_floats * 8 + (int64_t)j * 8,
+                                                  flag);
+        g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+      }
+    evt_mark(evt_i, 63, 0);
+    rms_update<HAS_MOM>(a, g, w, ms, mo);
+    *reinterpret_cast<float4*>(a.w + j) = w;
+    *reinterpret_cast<float4*>(a.ms + j) = ms;
+    if (HAS_MOM) *reinterpret_cast<float4*>(a.mom + j) = mo;
+  }
+  evt_mark(evt_i, 64, 0);
+  if (cb == 0 && (int)threadIdx.x < d.world) {
+    while (dp_ld_flag(my_comm + DPC_BIGDONE + 64 * threadIdx.x) < d.step) { }
+    __threadfence_system();
+  }
+  evt_mark(evt_i, 65, 0);
+  trace_mark(K_RMSPROP, 2);
+}
+
+int launch_dp_small(const RmsPropDpArgs& d, int64_t recv_offset, cudaStream_t stream) {
+  const int n_cb = (d.red.n_floats / 4 + GR_COLS - 1) / GR_COLS;
+  if (n_cb > DP_MAX_CB || !d.has_red) return (int)cudaErrorInvalidValue;
+  if (d.base.momentum != 0.f)
+    return launch_pdl(dp_small_kernel<true>, dim3(n_cb), dim3(GR_LANES * GR_COLS), 0, stream, d, recv_offset);
+  return launch_pdl(dp_small_kernel<false>, dim3(n_cb), dim3(GR_LANES * GR_COLS), 0, stream, d, recv_offset);
+}
+
 
 int launch_rmsprop_dp(const RmsPropDpArgs& d, int num_sms, cudaStream_t stream) {
   if (d.base.momentum != 0.f) return launch_pdl(rmsprop_dp_kernel<true>, dim3(num_sms), dim3(512), 0, stream, d);

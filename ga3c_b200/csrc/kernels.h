@@ -63,12 +63,13 @@ int launch_heads(const HeadsArgs& args, int num_sms, cudaStream_t stream);
 // Weight / bias gradients are per-CTA partial sums: CTA i stores into slab i (g_* point into slab 0, slabs are
 // gp_stride floats apart) and launch_grad_reduce adds the slabs in a fixed order.  No contended atomics, and the
 // step is bit-reproducible.
-int conv_bwd_grid(int batch, int num_sms);       // CTAs (= slabs written) of both kernels
+struct DpBigArgs;                                // dp_exchange.cuh
+int conv_bwd_grid(int batch, int num_sms, int n_exch = 0);   // conv CTAs (= slabs written); n_exch SMs are left to the exchange CTAs
 // conv_bwd_fused.cu -- conv12 data gradient (dn1, kept on chip; dn1_out: optional copy for tests), conv12 and conv11
 // weight / bias gradients in one kernel on tcgen05
 int launch_conv_bwd(const void* x, bool x_u8, const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1_out,
                     float* g_w11, float* g_b11, float* g_w12, float* g_b12, int64_t gp_stride, int batch, int num_sms,
-                    cudaStream_t stream);
+                    const DpBigArgs* dp, cudaStream_t stream);   // dp != null: append dp->n_exch exchange CTAs (dense1/w exchange)
 
 // elementwise.cu
 // out[j] = sum over slabs i < count(j) of part[i * stride + j], j in [0, n_floats): the per-CTA gradient partials of
@@ -108,6 +109,10 @@ struct RmsPropDpArgs {
   int has_red;                      // (saves the separate grad_reduce launch in front of the exchange)
 };
 int launch_rmsprop_dp(const RmsPropDpArgs& a, int num_sms, cudaStream_t stream);
+// second instalment of the overlapped exchange (dp_exchange.cuh): slab reduction of the small tensors, LL push into every
+// rank's receive buffer, identical RMSProp on every rank; returns only when every rank's dense1/w slice has landed.
+// a.red is required; recv_offset: byte offset in the slab of the receive buffers [2][DP_MAX_WORLD][small prefix * 8 B].
+int launch_dp_small(const RmsPropDpArgs& a, int64_t recv_offset, cudaStream_t stream);
 int launch_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cudaStream_t stream);
 int launch_returns(const double* rewards, const int64_t* seg_offsets, int n_segments, const double* terminal,
                    double discount, int flags, double rmin, double rmax, double* out, cudaStream_t stream);

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "mlp.cuh"
+#include "dp_exchange.cuh"
 
 using namespace ga3c;
 
@@ -53,7 +54,7 @@ struct ga3c_net {
   std::vector<ParamDesc> params;   // TF creation order
   int64_t arena_floats = 0;
   int64_t small_floats = 0;        // prefix holding every tensor except dense1/w (grads zeroed per step)
-  // one slab holds [params | grads | ms | mom | bf16 shadow of dense1/w | comm flags]: a single CUDA IPC handle
+  // one slab holds [params | grads | ms | mom | bf16 shadow of dense1/w | LL receive buffers | comm flags]: a single CUDA IPC handle
   // exposes everything a data-parallel peer needs (ga3c_dp_*)
   uint8_t* slab = nullptr;
   size_t slab_bytes = 0;
@@ -63,6 +64,9 @@ struct ga3c_net {
   int dp_rank = 0, dp_world = 1;
   uint8_t* dp_peer[DP_MAX_WORLD] = {};   // slab base of every rank as mapped in this process (own slab at dp_rank)
   uint64_t dp_step = 0;
+  int dp_exch = 20;                // exchange CTAs appended to the conv backward launch (GA3C_DP_EXCH_CTAS)
+  int cur_exch = 0;                // ... of the step being enqueued (0 outside the overlapped data-parallel step)
+  int64_t xbuf_off = 0, comm_off = 0;    // byte offsets in the slab: LL receive buffers [2][8][small prefix * 8 B], comm block
   // workspace
   uint16_t *n1 = nullptr, *n2 = nullptr, *dd1 = nullptr, *dn2 = nullptr, *dn1 = nullptr;
   float* d1 = nullptr;
@@ -87,11 +91,10 @@ struct ga3c_net {
   int64_t off(int i) const { return params[i].offset; }
 };
 
-constexpr int DP_COMM_BYTES = 256;    // [0] ready step, [8] done step (uint64 at 64-byte spacing)
 
 static const char* const kKernelNames[K_COUNT] = {"conv_fwd", "dense_fwd", "heads", "dense_wgrad", "dense_bwd",
                                                   "conv_bwd", "conv11_wgrad", "rmsprop", "grad_reduce",
-                                                  "mlp_fused", "mlp_wgrad", "mlp_reduce"};
+                                                  "mlp_fused", "mlp_wgrad", "mlp_reduce", "dp_big"};
 
 // launch one kernel of the path; when timing is enabled bracket it with events on the same stream
 #define LAUNCH(net, kid, st, call)                                                        \
@@ -167,7 +170,9 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
     if (_e != cudaSuccess) { ga3c_destroy(n); return fail("cudaMalloc", _e); }   \
   } while (0)
   const size_t shadow_bytes = (size_t)FLAT * FC * 2;
-  n->slab_bytes = 4 * ab + shadow_bytes + DP_COMM_BYTES;
+  n->xbuf_off = (int64_t)(4 * ab + shadow_bytes);
+  n->comm_off = n->xbuf_off + 2 * (int64_t)DP_MAX_WORLD * n->small_floats * 8;
+  n->slab_bytes = (size_t)n->comm_off + DP_COMM_BYTES;
   GA3C_ALLOC(n->slab, n->slab_bytes);
 #undef GA3C_ALLOC
   n->w = reinterpret_cast<float*>(n->slab);
@@ -175,7 +180,7 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
   n->ms = reinterpret_cast<float*>(n->slab + 2 * ab);
   n->mom = reinterpret_cast<float*>(n->slab + 3 * ab);
   n->w1_shadow = reinterpret_cast<uint16_t*>(n->slab + 4 * ab);
-  cudaMemset(n->slab + 4 * ab + shadow_bytes, 0, DP_COMM_BYTES);
+  cudaMemset(n->slab + n->xbuf_off, 0, n->slab_bytes - (size_t)n->xbuf_off);
   n->gp_stride = n->small_floats + 64;
   e = cudaMalloc((void**)&n->gpart, (size_t)2 * n->num_sms * n->gp_stride * sizeof(float));
   if (e != cudaSuccess) { ga3c_destroy(n); return fail("cudaMalloc", e); }
@@ -288,6 +293,19 @@ extern "C" int ga3c_arena_download(ga3c_net* n, int which, float* host, int64_t 
   CK(cudaSetDevice(n->cfg.device));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(host, src, (size_t)nf * 4, cudaMemcpyDeviceToHost));
+  if (n->dp_world > 1 && (which == 0 || which == 2 || which == 3)) {
+    // overlapped exchange: the fp32 master copy and the RMSProp slots of a dense1/w slice live on its owner (only the bf16
+    // shadow travels).  A peer's slice is stable here: it changes only inside a step this rank takes part in.
+    const int64_t n4 = (int64_t)FLAT * FC / 4, per = (n4 + n->dp_world - 1) / n->dp_world;
+    for (int q = 0; q < n->dp_world; ++q) {
+      if (q == n->dp_rank) continue;
+      const int64_t lo = per * q, hi = lo + per < n4 ? lo + per : n4;
+      if (hi <= lo) continue;
+      const int64_t off = n->off(P_D1W) + lo * 4;
+      CK(cudaMemcpy(host + off, n->dp_peer[q] + (size_t)which * nf * 4 + (size_t)off * 4, (size_t)(hi - lo) * 16,
+                    cudaMemcpyDeviceToHost));
+    }
+  }
   return 0;
 }
 
@@ -375,13 +393,14 @@ static GradReduceArgs reduce_args(ga3c_net* n, int batch) {
   r.part = n->gpart; r.stride = n->gp_stride; r.out = n->g; r.out_tail = n->loss_out;
   r.out_floats = (int)n->small_floats; r.n_floats = (int)n->small_floats + 4;
   for (int s = 0; s < GR_MAX_SEG; ++s) { r.seg_end[s] = r.n_floats; r.seg_count[s] = n->gp_heads_grid; }
-  r.seg_end[0] = (int)n->off(P_D1B); r.seg_count[0] = conv_bwd_grid(batch, n->num_sms);
+  r.seg_end[0] = (int)n->off(P_D1B); r.seg_count[0] = conv_bwd_grid(batch, n->num_sms, n->cur_exch);
   return r;
 }
 
 // dense1 data gradient and the two conv backward kernels; with `reduce` the slabs are summed into the gradient arena
 // (conv11/*, conv12/*, dense1/b, heads, loss sums), otherwise the caller does it (fused with RMSProp).
-static int fb_tail_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, void* stream, bool with_wgrad, bool reduce) {
+static int fb_tail_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, void* stream, bool with_wgrad, bool reduce,
+                        const DpBigArgs* dp = nullptr) {
   if (int r = check_batch(n, batch, "ga3c_fb_tail")) return r;
   if (!x) return fail_msg("ga3c_fb_tail: null buffer");
   if (batch != n->last_batch) return fail_msg("ga3c_fb_tail: batch differs from the preceding ga3c_fb_head");
@@ -395,7 +414,7 @@ static int fb_tail_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, vo
     LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
   LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(x, x_u8, n->n1, n->dn2, w + n->off(P_C12W), n->keep_dn1 ? n->dn1 : nullptr,
                                               gp + n->off(P_C11W), gp + n->off(P_C11B), gp + n->off(P_C12W),
-                                              gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, st));
+                                              gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, dp, st));
   if (reduce) LAUNCH(n, K_GRAD_REDUCE, st, launch_grad_reduce(reduce_args(n, batch), st));
   return 0;
 }
@@ -444,7 +463,7 @@ static int apply_rmsprop_impl(ga3c_net* n, float lr, void* stream, const GradRed
     for (int r = 0; r < n->dp_world; ++r) d.peer[r] = n->dp_peer[r];
     d.rank = n->dp_rank; d.world = n->dp_world; d.step = ++n->dp_step;
     d.arena_bytes = (int64_t)n->arena_floats * 4;
-    d.comm_offset = 4 * d.arena_bytes + (int64_t)FLAT * FC * 2;
+    d.comm_offset = n->comm_off;
     d.has_red = red != nullptr;
     if (red) d.red = *red;
     LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_dp(d, n->num_sms, (cudaStream_t)stream));
@@ -497,13 +516,38 @@ extern "C" int ga3c_dp_attach(ga3c_net* n, int32_t rank, int32_t world, const vo
     n->dp_peer[r] = static_cast<uint8_t*>(p);
   }
   n->dp_rank = rank; n->dp_world = world; n->dp_step = 0;
-  CK(cudaMemset(n->slab + n->slab_bytes - DP_COMM_BYTES, 0, DP_COMM_BYTES));
+  if (const char* e = getenv("GA3C_DP_EXCH_CTAS")) n->dp_exch = atoi(e);     // 0: single exchange kernel at the end of the step
+  if (n->dp_exch < 0 || n->dp_exch > n->num_sms / 2) n->dp_exch = 0;
+  CK(cudaMemset(n->slab + n->xbuf_off, 0, n->slab_bytes - (size_t)n->xbuf_off));
   return 0;
 }
 
 static int train_step_impl(ga3c_net* n, const void* x, bool x_u8, const float* yr, const float* a, int32_t batch, float lr,
                            float beta, float* loss, void* stream) {
   if (int r = fb_head_impl(n, x, x_u8, yr, a, batch, beta, loss, stream, false)) return r;
+  if (n->dp_world > 1 && n->dp_exch > 0) {
+    // overlapped exchange (dp_exchange.cuh): dense1/w moves between the ranks on exchange CTAs of the conv backward
+    // launch; the small tensors follow in dp_small, which also holds the step open until every slice has landed
+    DpBigArgs b{};
+    for (int r = 0; r < n->dp_world; ++r) b.peer[r] = n->dp_peer[r];
+    b.rank = n->dp_rank; b.world = n->dp_world; b.n_exch = n->dp_exch; b.step = ++n->dp_step;
+    b.arena_bytes = (int64_t)n->arena_floats * 4; b.shadow_off = 4 * b.arena_bytes; b.comm_offset = n->comm_off;
+    b.w1_offset = n->off(P_D1W); b.w1_count = (int64_t)FLAT * FC;
+    b.lr = lr; b.decay = n->cfg.rmsprop_decay; b.momentum = n->cfg.rmsprop_momentum; b.eps = n->cfg.rmsprop_epsilon;
+    n->cur_exch = b.n_exch;
+    int r = fb_tail_impl(n, x, x_u8, batch, stream, true, false, &b);
+    RmsPropDpArgs d{};
+    d.base = rmsprop_args(n, lr);
+    for (int q = 0; q < n->dp_world; ++q) d.peer[q] = n->dp_peer[q];
+    d.rank = n->dp_rank; d.world = n->dp_world; d.step = b.step;
+    d.arena_bytes = b.arena_bytes; d.comm_offset = n->comm_off;
+    d.has_red = 1; d.red = reduce_args(n, batch);
+    n->cur_exch = 0;
+    if (r) return r;
+    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_dp_small(d, n->xbuf_off, (cudaStream_t)stream));
+    n->global_step += 1;
+    return 0;
+  }
   if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, false)) return r;
   const GradReduceArgs red = reduce_args(n, batch);
   if (n->dp_world > 1)            // peers read this rank's gradient arena: the exchange kernel first sums the slabs into it
