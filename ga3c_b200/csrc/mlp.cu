@@ -3,7 +3,7 @@
 //   NetworkVP_discrate      NetworkVP_discrate.py:52-85     x -> last DENSE_LAYERS entry (sigmoid); softmax head, A3C loss
 //
 // Three kernels per training step (one per prediction):
-//   mlp_fused   one persistent CTA per SM walks 64-row batch tiles.  A tile's activations stay in shared memory through
+//   mlp_fused   one persistent CTA (16 warps) per SM walks 64-row batch tiles.  A tile's activations stay in shared memory through
 //               all layers, the heads, the loss and the whole data-gradient chain; HBM sees x once, p / v, and (training
 //               only) the layer outputs and pre-activation gradients that the weight-gradient pass needs.
 //   mlp_wgrad   every dW = in^T dz and db = sum dz of the step as 64x64 output tiles, the batch split over CTAs; split s
@@ -21,8 +21,11 @@ namespace {
 
 constexpr int LD = 260;              // row pitch (floats) of the activation tiles and of the weight chunk: 16-B aligned rows
 constexpr int RC = 16;               // reduction chunk
-constexpr int HLD = 45;              // row pitch of the head matrix / logits tile (odd: conflict-free column walks)
-constexpr int NT = 256;
+constexpr int HLD = 49;              // row pitch of the head matrix / logits tile (odd: conflict-free column walks)
+constexpr int NT = 256;              // threads of the weight-gradient / reduce kernels
+constexpr int FT = 512;              // threads of the fused kernel: 16 warps x 4 rows = one 64-row tile
+constexpr int RT = MLP_TM / (FT / 32);   // rows per thread (4)
+constexpr int HW = 48;               // head matrix columns held in shared memory (>= MLP_MAX_OUT, zero padded)
 constexpr float PI_F = 3.14159265358979323846f;
 
 constexpr size_t FUSED_SMEM =
@@ -48,44 +51,49 @@ __device__ __forceinline__ int head_b_index(const MlpNet& net, int j) {
 // One 64-row x (128 * JH)-column product through the CTA:  out[r][c] = sum_q in_s[r][q] * Wq[q][c], q < kred, with
 //   TRANS = false:  Wq[q][c] = Wg[q * ldw + c]        (forward:        W is [k][n], q = k, c = n)
 //   TRANS = true :  Wq[q][c] = Wg[c * ldw + q]        (data gradient:  W is [k][n], q = n, c = k)
-// Thread (ty = warp, tx = lane) owns rows ty*8 .. ty*8+7 and columns tx*4 .. tx*4+3 (+128 with JH = 2).  The weight
-// chunk [16][<= 256] of step q0+16 is fetched into registers while chunk q0 is being consumed from shared memory.
+// Thread (ty = warp, tx = lane) owns rows ty*4 .. ty*4+3 and columns tx*4 .. tx*4+3 (+128 with JH = 2): 16 warps, four per
+// scheduler (two 8-row warps per scheduler left the FMA pipe idle 45 % of the time: nothing to switch to on a shared-memory
+// wait).  The weight chunk [16][<= 256] of step q0+16 is fetched into registers while chunk q0 is being consumed.
 // epi(r, c0, v[4]) receives the finished sums of 4 consecutive columns, turns them into what the next pass reads and
 // stores whatever goes to HBM; the result lands in out_s.  in_s must be zero (finite) up to round_up16(kred).
 template <bool TRANS, int JH, class Epi>
 __device__ __forceinline__ void tile_pass(const float* in_s, float* out_s, float* Wc, int kred, const float* __restrict__ Wg,
                                           int ldw, int nout, Epi epi) {
   const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
-  float acc[8][4 * JH];
+  float acc[RT][4 * JH];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < RT; ++i)
 #pragma unroll
     for (int j = 0; j < 4 * JH; ++j) acc[i][j] = 0.f;
 
-  float pre[RC];
+  constexpr int PF = RC * 256 / FT;      // weight-chunk elements fetched per thread (8)
+  float pre[PF];
   auto fetch = [&](int q0) {
     if (!TRANS) {
-      const int c = tid;
+      const int c = tid & 255, rh = tid >> 8;            // column c, chunk rows rh, rh + 2, ...
 #pragma unroll
-      for (int rr = 0; rr < RC; ++rr)
-        pre[rr] = (q0 + rr < kred && c < nout) ? __ldg(Wg + (size_t)(q0 + rr) * ldw + c) : 0.f;
+      for (int i = 0; i < PF; ++i) {
+        const int rr = rh + 2 * i;
+        pre[i] = (q0 + rr < kred && c < nout) ? __ldg(Wg + (size_t)(q0 + rr) * ldw + c) : 0.f;
+      }
     } else {
-      const int rr = tid & 15, cb = tid >> 4;
+      const int rr = tid & 15, cb = tid >> 4;            // 16 consecutive n of W row c: 64-byte segments
 #pragma unroll
-      for (int i = 0; i < RC; ++i) {
-        const int c = cb + 16 * i;
+      for (int i = 0; i < PF; ++i) {
+        const int c = cb + 32 * i;
         pre[i] = (q0 + rr < kred && c < nout) ? __ldg(Wg + (size_t)c * ldw + q0 + rr) : 0.f;
       }
     }
   };
   auto stash = [&]() {
     if (!TRANS) {
+      const int c = tid & 255, rh = tid >> 8;
 #pragma unroll
-      for (int rr = 0; rr < RC; ++rr) Wc[rr * LD + tid] = pre[rr];
+      for (int i = 0; i < PF; ++i) Wc[(rh + 2 * i) * LD + c] = pre[i];
     } else {
       const int rr = tid & 15, cb = tid >> 4;
 #pragma unroll
-      for (int i = 0; i < RC; ++i) Wc[rr * LD + cb + 16 * i] = pre[i];
+      for (int i = 0; i < PF; ++i) Wc[rr * LD + cb + 32 * i] = pre[i];
     }
   };
 
@@ -97,16 +105,16 @@ __device__ __forceinline__ void tile_pass(const float* in_s, float* out_s, float
     if (q0 + RC < kred) fetch(q0 + RC);
 #pragma unroll
     for (int q4 = 0; q4 < RC / 4; ++q4) {
-      float4 a[8];
+      float4 a[RT];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(in_s + (ty * 8 + i) * LD + q0 + q4 * 4);
+      for (int i = 0; i < RT; ++i) a[i] = *reinterpret_cast<const float4*>(in_s + (ty * RT + i) * LD + q0 + q4 * 4);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float4 w[JH];
 #pragma unroll
         for (int h = 0; h < JH; ++h) w[h] = *reinterpret_cast<const float4*>(Wc + (q4 * 4 + e) * LD + tx * 4 + 128 * h);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < RT; ++i) {
           const float av = e == 0 ? a[i].x : e == 1 ? a[i].y : e == 2 ? a[i].z : a[i].w;
 #pragma unroll
           for (int h = 0; h < JH; ++h) {
@@ -120,11 +128,11 @@ __device__ __forceinline__ void tile_pass(const float* in_s, float* out_s, float
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < RT; ++i)
 #pragma unroll
     for (int h = 0; h < JH; ++h) {
       float v[4] = {acc[i][4 * h], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]};
-      const int r = ty * 8 + i, c0 = tx * 4 + 128 * h;
+      const int r = ty * RT + i, c0 = tx * 4 + 128 * h;
       epi(r, c0, v);
       *reinterpret_cast<float4*>(out_s + r * LD + c0) = make_float4(v[0], v[1], v[2], v[3]);
     }
@@ -143,7 +151,7 @@ __device__ __forceinline__ void store_row4(float* base, int64_t row, int n, int 
 }
 
 template <bool TRAIN>
-__global__ void __launch_bounds__(NT, 1) mlp_fused_kernel(const MlpNet net, const MlpStepArgs s) {
+__global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, const MlpStepArgs s) {
   extern __shared__ __align__(16) float smem[];
   float* buf0 = smem;
   float* buf1 = buf0 + MLP_TM * LD;
@@ -158,8 +166,8 @@ __global__ void __launch_bounds__(NT, 1) mlp_fused_kernel(const MlpNet net, cons
   griddep_launch();
   griddep_wait(K_MLP_FUSED);               // the weights come from the optimizer launch of the previous step
 
-  for (int idx = tid; idx < hid * 44; idx += NT) {
-    const int k = idx / 44, j = idx - k * 44;
+  for (int idx = tid; idx < hid * HW; idx += FT) {
+    const int k = idx / HW, j = idx - k * HW;
     Wh[k * HLD + j] = j < n_out ? __ldg(s.w + head_w_index(net, k, j)) : 0.f;
   }
   if (tid < 48) hb[tid] = tid < n_out ? __ldg(s.w + head_b_index(net, tid)) : 0.f;
@@ -170,7 +178,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_fused_kernel(const MlpNet net, cons
     __syncthreads();                       // the previous tile is fully consumed (and Wh / hb are staged)
     {
       const int Sp = round_up16(S);
-      for (int idx = tid; idx < MLP_TM * Sp; idx += NT) {
+      for (int idx = tid; idx < MLP_TM * Sp; idx += FT) {
         const int r = idx / Sp, c = idx - r * Sp;
         buf0[r * LD + c] = (row0 + r < B && c < S) ? s.x[(size_t)(row0 + r) * S + c] : 0.f;
       }
@@ -202,20 +210,20 @@ __global__ void __launch_bounds__(NT, 1) mlp_fused_kernel(const MlpNet net, cons
     }
     __syncthreads();                       // h = cur[64][hid] is complete
 
-    // ---- head logits: thread (row, jq) sums columns jq, jq + 4, ... of h Wh ----
+    // ---- head logits: thread (row, jq) sums columns jq, jq + 8, ... of h Wh ----
     {
-      const int row = tid >> 2, jq = tid & 3;
-      float z[11];
+      const int row = tid >> 3, jq = tid & 7;
+      float z[HW / 8];
 #pragma unroll
-      for (int jj = 0; jj < 11; ++jj) z[jj] = 0.f;
+      for (int jj = 0; jj < HW / 8; ++jj) z[jj] = 0.f;
       for (int k = 0; k < hid; ++k) {
         const float h = cur[row * LD + k];
 #pragma unroll
-        for (int jj = 0; jj < 11; ++jj) z[jj] = fmaf(h, Wh[k * HLD + jq + 4 * jj], z[jj]);
+        for (int jj = 0; jj < HW / 8; ++jj) z[jj] = fmaf(h, Wh[k * HLD + jq + 8 * jj], z[jj]);
       }
 #pragma unroll
-      for (int jj = 0; jj < 11; ++jj) {
-        const int j = jq + 4 * jj;
+      for (int jj = 0; jj < HW / 8; ++jj) {
+        const int j = jq + 8 * jj;
         if (j < n_out) lg[row * HLD + j] = z[jj] + hb[j];
       }
     }
@@ -321,10 +329,10 @@ __global__ void __launch_bounds__(NT, 1) mlp_fused_kernel(const MlpNet net, cons
     // ---- gradient w.r.t. the last hidden pre-activation: dz = (dlogits Wh^T) * act'(h) ----
     {
       const MlpLayerDesc L = net.L[NL - 1];
-      const int row = tid >> 2, kq = tid & 3;
+      const int row = tid >> 3, kq = tid & 7;
       const int hp = round_up16(hid);
       float* dz_g = s.dz[NL - 1];
-      for (int k = kq; k < hp; k += 4) {
+      for (int k = kq; k < hp; k += 8) {
         float d = 0.f;
         if (k < hid) {
           for (int j = 0; j < n_out; ++j) d = fmaf(lg[row * HLD + j], Wh[k * HLD + j], d);
@@ -506,8 +514,8 @@ int mlp_fused_grid(int batch, int num_sms) {
 
 int launch_mlp_fused(const MlpNet& net, const MlpStepArgs& args, int num_sms, cudaStream_t stream) {
   const dim3 grid(mlp_fused_grid(args.batch, num_sms));
-  if (args.train) return launch_pdl(mlp_fused_kernel<true>, grid, dim3(NT), FUSED_SMEM, stream, net, args);
-  return launch_pdl(mlp_fused_kernel<false>, grid, dim3(NT), FUSED_SMEM, stream, net, args);
+  if (args.train) return launch_pdl(mlp_fused_kernel<true>, grid, dim3(FT), FUSED_SMEM, stream, net, args);
+  return launch_pdl(mlp_fused_kernel<false>, grid, dim3(FT), FUSED_SMEM, stream, net, args);
 }
 
 int mlp_wgrad_splits(const MlpNet& net, int batch, int num_sms) {
