@@ -35,8 +35,30 @@ class ThreadPredictor(Thread):
         self.batches = 0
         self.rows = 0
 
+    def _run_slab(self, q, cap):
+        """Batch calls of ga3c_b200.transport.SlabPredictionQueue: one gather into a pinned buffer (which Network copies
+        to the device without another host pass) and one reply scatter per batch."""
+        dtype = q._states.array.dtype
+        try:
+            import torch
+            tdt = torch.uint8 if dtype == np.uint8 else torch.float32
+            states = torch.empty((cap, self.state_dim), dtype=tdt, pin_memory=torch.cuda.is_available()).numpy()
+        except Exception:
+            states = np.zeros((cap, self.state_dim), dtype=dtype)
+        while not self.exit_flag:
+            ids = q.get_batch(cap, states, timeout=0.05)
+            if ids is None:
+                continue
+            n = ids.size
+            p, v = self.server.model.predict_p_and_v(states[:n])
+            self.batches += 1
+            self.rows += n
+            q.reply_batch(ids, p, v)
+
     def run(self):
         cap = self.config.PREDICTION_BATCH_SIZE
+        if hasattr(self.prediction_q, "get_batch"):
+            return self._run_slab(self.prediction_q, cap)
         ids = np.zeros(cap, dtype=np.uint16)                      # uint16 as in ThreadPredictor.py:46
         states = np.zeros((cap, self.state_dim), dtype=np.float32)
         q = self.prediction_q

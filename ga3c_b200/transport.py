@@ -1,0 +1,298 @@
+"""Shared-memory transport under the predictor / trainer queue contracts.
+
+The reference moves every state through `multiprocessing.Queue`s: one pickle + pipe write + unpickle per item
+(`ProcessAgent.py:102-107`, `ThreadPredictor.py:46-66`, `Server.py:73-75`), which caps the loop at a few thousand
+predictions per second whatever the network costs.  These classes keep the contracts -- items `(id, state)` in,
+`(p_row, v)` back on the agent's own one-slot `wait_q`, items `(x_, r_, a_, x2_, done_)` to the trainer, `put` / `get` /
+`empty` / bounded capacity -- but the payload never leaves shared memory:
+
+    SlabPredictionQueue   one state row per agent + a `pending` byte per agent.  `put((id, state))` copies the state into
+                          row `id` and raises the byte; the consumer scans the bytes.  One outstanding request per agent
+                          (that is what wait_q's maxsize = 1 enforces in the reference, ProcessAgent.py:64), so every byte
+                          has one writer per transition and no lock or atomic is needed across processes.
+    SlabReplySlot         `wait_q` of one agent: `put((p, v))` writes the agent's reply row and wakes it.
+    SlabTrainingQueue     each agent owns a small ring of experience blocks; `put` copies the arrays into the next free
+                          block (blocking while the ring is full = Queue(maxsize) back-pressure) and posts it.
+
+The reference's own `ThreadPredictor` / `ThreadTrainer` / `ProcessAgent` run unmodified over these objects (duck-typed
+queues; tests/test_transport.py does exactly that where /root/reference is present).  `ga3c_b200.ThreadPredictor` also uses
+the batch calls (`get_batch`, `reply_batch`): one gather into a pinned buffer and one reply scatter per batch instead of
+128 queue operations.  Blocking uses OS semaphores (no busy-waiting: 256 agents share the host's cores).
+
+Memory ordering: a producer writes the payload, then the flag byte; x86-64 keeps stores in order and numpy's copies are
+plain stores, so a consumer that sees the flag sees the payload.
+"""
+from __future__ import annotations
+
+import mmap
+import multiprocessing as mp
+import threading
+from multiprocessing import shared_memory
+
+import numpy as np
+
+
+class _Shm:
+    """A shared block viewed as one numpy array.  Default: an anonymous MAP_SHARED mapping, inherited by forked children
+    (how the reference starts its agents on Linux) and not subject to the size of /dev/shm (64 MB in a default container,
+    far less than a training slab of fp32 frames).  named=True uses multiprocessing.shared_memory instead, which
+    re-attaches by name when the object is pickled into a spawned process."""
+
+    def __init__(self, shape, dtype, named=False):
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        nbytes = max(1, int(np.prod(self.shape)) * self.dtype.itemsize)
+        self._named = bool(named)
+        if named:
+            self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            buf = self._shm.buf
+        else:
+            self._shm = mmap.mmap(-1, nbytes)               # MAP_SHARED | MAP_ANONYMOUS, zero-filled
+            buf = self._shm
+        self._owner = True
+        self.array = np.ndarray(self.shape, dtype=self.dtype, buffer=buf)
+
+    def __getstate__(self):
+        if not self._named:
+            raise TypeError("anonymous shared mapping: pass the transport objects to forked children (or build them with "
+                            "named=True to pickle them into spawned processes)")
+        return {"name": self._shm.name, "shape": self.shape, "dtype": self.dtype.str}
+
+    def __setstate__(self, st):
+        self.shape, self.dtype = st["shape"], np.dtype(st["dtype"])
+        self._named = True
+        self._shm = shared_memory.SharedMemory(name=st["name"])
+        self._owner = False
+        self.array = np.ndarray(self.shape, dtype=self.dtype, buffer=self._shm.buf)
+
+    def close(self):
+        self.array = None
+        try:
+            self._shm.close()
+            if self._named and self._owner:
+                self._shm.unlink()
+        except Exception:
+            pass
+
+
+class SlabPredictionQueue:
+    """`prediction_q` (Server.py:74): items `(agent_id, state)`; ids 0 .. num_agents-1."""
+
+    def __init__(self, num_agents, state_dim, num_actions, dtype=np.float32, ctx=None, named=False):
+        ctx = ctx or mp.get_context()
+        self.num_agents, self.state_dim, self.num_actions = int(num_agents), int(state_dim), int(num_actions)
+        self._states = _Shm((num_agents, state_dim), dtype, named)
+        self._pending = _Shm((num_agents,), np.uint8, named)
+        self._reply_p = _Shm((num_agents, num_actions), np.float32, named)
+        self._reply_v = _Shm((num_agents,), np.float32, named)
+        self._work = ctx.Semaphore(0)                       # one release per posted request
+        self._wake = [ctx.Semaphore(0) for _ in range(num_agents)]
+        self._lock = threading.Lock()                       # consumers are threads of one process
+        self._cursor = 0
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d["_lock"] = None
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._lock = threading.Lock()
+
+    # ---- producer side (agent processes) ----
+    def put(self, item, block=True, timeout=None):
+        aid, state = item
+        self._states.array[aid] = np.asarray(state).reshape(-1)
+        self._pending.array[aid] = 1
+        self._work.release()
+
+    def state_row(self, aid):
+        """The agent's own row, for environments that render straight into shared memory (then call `post`)."""
+        return self._states.array[aid]
+
+    def post(self, aid):
+        self._pending.array[aid] = 1
+        self._work.release()
+
+    def wait_q(self, aid):
+        return SlabReplySlot(self, aid)
+
+    # ---- consumer side (predictor threads) ----
+    def empty(self):
+        return not self._pending.array.any()
+
+    def qsize(self):
+        return int(self._pending.array.sum())
+
+    def _take(self, max_n):
+        """Indices of up to max_n pending requests, oldest-cursor-first; caller holds the lock."""
+        idx = np.flatnonzero(self._pending.array.copy())    # snapshot: producers keep raising bytes while we look
+        if idx.size == 0:
+            return idx
+        if idx.size > max_n:
+            k = int(np.searchsorted(idx, self._cursor))
+            idx = np.concatenate((idx[k:], idx[:k]))[:max_n]
+        self._cursor = (int(idx[-1]) + 1) % self.num_agents
+        return idx
+
+    def get(self, block=True, timeout=None):
+        """-> (agent_id, state copy).  Blocks like Queue.get()."""
+        while True:
+            if not self._work.acquire(block, timeout):
+                import queue
+                raise queue.Empty
+            with self._lock:
+                idx = self._take(1)
+                if idx.size:
+                    aid = int(idx[0])
+                    state = self._states.array[aid].copy()
+                    self._pending.array[aid] = 0
+                    return aid, state
+            # a request seen (and served) by get_batch before its semaphore post arrived: spurious wake-up
+
+    def get_batch(self, max_n, out_states, timeout=None):
+        """Blocks for the first request, then takes whatever is pending (at most max_n, ThreadPredictor.py:50-55): gathers
+        the rows into out_states[:n] and returns the agent ids (int array of length n >= 1), or None on timeout."""
+        while True:
+            if not self._work.acquire(True, timeout):
+                return None
+            with self._lock:
+                idx = self._take(max_n)
+                if idx.size == 0:
+                    continue
+                np.take(self._states.array, idx, axis=0, out=out_states[:idx.size])
+                self._pending.array[idx] = 0
+            for _ in range(idx.size - 1):               # keep the semaphore in step with the bytes (best effort)
+                self._work.acquire(False)
+            return idx
+
+    def reply_batch(self, ids, p, v):
+        """(p[i], v[i]) to agent ids[i]'s wait_q, for a whole batch."""
+        self._reply_p.array[ids] = p
+        self._reply_v.array[ids] = v
+        wake = self._wake
+        for aid in ids:
+            wake[int(aid)].release()
+
+    def close(self):
+        for s in (self._states, self._pending, self._reply_p, self._reply_v):
+            s.close()
+
+
+class SlabReplySlot:
+    """`agent.wait_q` (ProcessAgent.py:64, Queue(maxsize=1)): the predictor `put`s `(p_row, v)`, the agent `get`s it."""
+
+    def __init__(self, q: SlabPredictionQueue, aid: int):
+        self._q, self._aid = q, int(aid)
+
+    def put(self, item, block=True, timeout=None):
+        p, v = item
+        self._q._reply_p.array[self._aid] = p
+        self._q._reply_v.array[self._aid] = v
+        self._q._wake[self._aid].release()
+
+    def get(self, block=True, timeout=None):
+        if not self._q._wake[self._aid].acquire(block, timeout):
+            import queue
+            raise queue.Empty
+        return self._q._reply_p.array[self._aid].copy(), self._q._reply_v.array[self._aid].copy()[()]
+
+
+class SlabTrainingQueue:
+    """`training_q` (Server.py:73): items `(x_, r_, a_, x2_, done_)` from ProcessAgent.run (ProcessAgent.py:175).
+
+    Every producer (agent id) owns `blocks_per_agent` blocks of `max_rows` rows.  `put` needs the producer's id: bind it once
+    with `for_agent(id)` (what an agent process holds as its `training_q`).  x2_ is shipped only with ship_next_state=True
+    (the A3C networks ignore it, NetworkVP.py:254-257); otherwise the consumer gets a zero-width array, which the
+    reference ThreadTrainer concatenates without complaint."""
+
+    def __init__(self, num_agents, max_rows, state_dim, num_actions, blocks_per_agent=2, dtype=np.float32,
+                 ship_next_state=False, ctx=None, named=False):
+        ctx = ctx or mp.get_context()
+        self.num_agents, self.max_rows, self.state_dim, self.num_actions = num_agents, max_rows, state_dim, num_actions
+        self.blocks = int(blocks_per_agent)
+        nb = num_agents * self.blocks
+        self._x = _Shm((nb, max_rows, state_dim), dtype, named)
+        self._x2 = _Shm((nb, max_rows, state_dim if ship_next_state else 0), dtype, named)
+        self._r = _Shm((nb, max_rows), np.float64, named)   # r_ arrives as float64 (ProcessAgent.py:99)
+        self._a = _Shm((nb, max_rows, num_actions), np.float32, named)
+        self._done = _Shm((nb, max_rows), np.bool_, named)
+        self._rows = _Shm((nb,), np.int32, named)
+        self._posted = _Shm((nb,), np.uint8, named)
+        self._work = ctx.Semaphore(0)
+        self._free = [ctx.Semaphore(self.blocks) for _ in range(num_agents)]
+        self._next = [0] * num_agents                       # per-producer cursor (each producer only touches its own)
+        self._lock = threading.Lock()
+        self._cursor = 0
+        self.ship_next_state = bool(ship_next_state)
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d["_lock"] = None
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._lock = threading.Lock()
+
+    def for_agent(self, aid):
+        return _AgentTrainingQueue(self, aid)
+
+    def put_from(self, aid, item, block=True, timeout=None):
+        x, r, a, x2, done = item
+        n = int(np.asarray(x).shape[0])
+        if n > self.max_rows:
+            raise ValueError(f"training item of {n} rows exceeds max_rows={self.max_rows} (Config.TIME_MAX + 1)")
+        if not self._free[aid].acquire(block, timeout):     # ring full: Queue(maxsize) back-pressure
+            import queue
+            raise queue.Full
+        b = aid * self.blocks + self._next[aid]
+        self._next[aid] = (self._next[aid] + 1) % self.blocks
+        self._x.array[b, :n] = np.asarray(x).reshape(n, -1)
+        if self.ship_next_state:
+            self._x2.array[b, :n] = np.asarray(x2).reshape(n, -1)
+        self._r.array[b, :n] = r
+        self._a.array[b, :n] = np.asarray(a).reshape(n, -1)
+        self._done.array[b, :n] = done
+        self._rows.array[b] = n
+        self._posted.array[b] = 1
+        self._work.release()
+
+    def empty(self):
+        return not self._posted.array.any()
+
+    def qsize(self):
+        return int(self._posted.array.sum())
+
+    def get(self, block=True, timeout=None):
+        """-> (x_, r_, a_, x2_, done_) copies, like Queue.get()."""
+        while True:
+            if not self._work.acquire(block, timeout):
+                import queue
+                raise queue.Empty
+            with self._lock:
+                idx = np.flatnonzero(self._posted.array.copy())     # snapshot (see SlabPredictionQueue._take)
+                if idx.size == 0:
+                    continue
+                k = int(np.searchsorted(idx, self._cursor)) % idx.size
+                b = int(idx[k])
+                self._cursor = (b + 1) % self._posted.array.size
+                n = int(self._rows.array[b])
+                item = (self._x.array[b, :n].copy(), self._r.array[b, :n].copy(), self._a.array[b, :n].copy(),
+                        self._x2.array[b, :n].copy(), self._done.array[b, :n].copy())
+                self._posted.array[b] = 0
+            self._free[b // self.blocks].release()
+            return item
+
+    def close(self):
+        for s in (self._x, self._x2, self._r, self._a, self._done, self._rows, self._posted):
+            s.close()
+
+
+class _AgentTrainingQueue:
+    """What one agent holds as `training_q`: `put(item)` with the agent's id bound."""
+
+    def __init__(self, q: SlabTrainingQueue, aid: int):
+        self._q, self._aid = q, int(aid)
+
+    def put(self, item, block=True, timeout=None):
+        self._q.put_from(self._aid, item, block, timeout)

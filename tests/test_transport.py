@@ -1,0 +1,202 @@
+"""Shared-memory transport: the queue contracts of ProcessAgent / ThreadPredictor / ThreadTrainer kept over
+shared memory.  CPU only; multi-process cases fork real agent processes."""
+import multiprocessing as mp
+import os
+import queue
+import sys
+import threading
+import time
+
+import numpy as np
+import pytest
+
+from ga3c_b200.transport import SlabPredictionQueue, SlabTrainingQueue
+from ga3c_b200 import ThreadPredictor, ThreadTrainer
+from conftest import REFERENCE
+
+S, A = 24, 3
+CTX = mp.get_context("fork")
+
+
+class FakeModel:
+    """p depends on the state so that a reply delivered to the wrong agent is caught."""
+    def __init__(self):
+        self.batches = []
+
+    def predict_p_and_v(self, x):
+        x = np.asarray(x, dtype=np.float32)
+        self.batches.append(x.shape[0])
+        s = x.sum(axis=1)
+        return np.stack([s, s + 1, s + 2], axis=1).astype(np.float32), (2 * s).astype(np.float32)
+
+
+class FakeServer:
+    def __init__(self, training_q=None):
+        self.model = FakeModel()
+        self.agents = []
+        self.training_q = training_q
+        self.trained = []
+
+    def train_model(self, x, r, a, x2, done, tid):
+        self.trained.append((x.copy(), np.asarray(r).copy(), a.copy(), x2.shape, done.copy()))
+
+
+def test_prediction_queue_contract_single_process():
+    q = SlabPredictionQueue(8, S, A, ctx=CTX)
+    try:
+        assert q.empty() and q.qsize() == 0
+        with pytest.raises(queue.Empty):
+            q.get(block=False)
+        st = {i: np.full(S, i + 0.5, np.float32) for i in (5, 2, 7)}
+        for i, s in st.items():
+            q.put((i, s))
+        assert not q.empty() and q.qsize() == 3
+        got = dict(q.get() for _ in range(3))
+        assert set(got) == {5, 2, 7} and all(np.array_equal(got[i], st[i]) for i in st)
+        assert q.empty()
+        # batch path + replies
+        for i, s in st.items():
+            q.put((i, s))
+        buf = np.zeros((4, S), np.float32)
+        ids = q.get_batch(4, buf)
+        assert sorted(ids.tolist()) == [2, 5, 7] and all(np.array_equal(buf[k], st[int(i)]) for k, i in enumerate(ids))
+        q.reply_batch(ids, np.arange(9, dtype=np.float32).reshape(3, 3), np.array([10, 11, 12], np.float32))
+        for k, i in enumerate(ids):
+            p, v = q.wait_q(int(i)).get(timeout=1)
+            assert np.array_equal(p, np.arange(3 * k, 3 * k + 3)) and v == 10 + k
+        assert q.get_batch(4, buf, timeout=0.01) is None
+        # cap smaller than what is pending: the rest stays queued, nobody is starved
+        for i in range(8):
+            q.put((i, np.full(S, i, np.float32)))
+        a = q.get_batch(3, buf); b = q.get_batch(3, buf); c = q.get_batch(3, buf)
+        assert sorted(a.tolist() + b.tolist() + c.tolist()) == list(range(8))
+    finally:
+        q.close()
+
+
+def test_training_queue_contract_and_backpressure():
+    tq = SlabTrainingQueue(2, max_rows=6, state_dim=S, num_actions=A, blocks_per_agent=2, ctx=CTX)
+    try:
+        mine = tq.for_agent(1)
+        items = []
+        for k in range(2):
+            n = 3 + k
+            item = (np.random.rand(n, S).astype(np.float32), np.random.rand(n), np.eye(A, dtype=np.float32)[np.arange(n) % A],
+                    np.random.rand(n, S).astype(np.float32), np.arange(n) % 2 == 0)
+            items.append(item)
+            mine.put(item)
+        with pytest.raises(queue.Full):                       # ring of 2 blocks is full: Queue(maxsize) behaviour
+            mine.put(items[0], timeout=0.05)
+        with pytest.raises(ValueError):
+            tq.for_agent(0).put((np.zeros((7, S), np.float32), np.zeros(7), np.zeros((7, A), np.float32), None, np.zeros(7, bool)))
+        for item in items:
+            x, r, a, x2, done = tq.get(timeout=1)
+            assert np.array_equal(x, item[0]) and np.array_equal(r, item[1]) and r.dtype == np.float64
+            assert np.array_equal(a, item[2]) and np.array_equal(done, item[4]) and x2.shape == (x.shape[0], 0)
+        assert tq.empty()
+        mine.put(items[0])                                    # blocks were released
+        assert tq.qsize() == 1
+    finally:
+        tq.close()
+
+
+def _agent_proc(aid, pq, tq, n_steps, t_max, out):
+    """A ProcessAgent-shaped loop (ProcessAgent.py:102-107, :117-176): predict every step, ship experiences every t_max."""
+    rng = np.random.default_rng(aid)
+    wait_q = pq.wait_q(aid)
+    train_q = tq.for_agent(aid)
+    bad = 0
+    xs = []
+    for t in range(n_steps):
+        state = rng.random(S, dtype=np.float32)
+        pq.put((aid, state))
+        p, v = wait_q.get()
+        s = np.float32(state.sum())
+        if not (np.allclose(p, [s, s + 1, s + 2], rtol=1e-6) and np.isclose(v, 2 * s, rtol=1e-6)):
+            bad += 1
+        xs.append(state)
+        if len(xs) == t_max:
+            x = np.array(xs)
+            train_q.put((x, np.full(t_max, aid, np.float64), np.eye(A, dtype=np.float32)[np.arange(t_max) % A], x, np.zeros(t_max, bool)))
+            xs = []
+    out.put((aid, bad))
+
+
+def test_agents_in_processes_through_predictor_and_trainer_threads():
+    n_agents, n_steps, t_max = 6, 40, 5
+    pq = SlabPredictionQueue(n_agents, S, A, ctx=CTX)
+    tq = SlabTrainingQueue(n_agents, max_rows=t_max, state_dim=S, num_actions=A, ctx=CTX)
+    server = FakeServer(tq)
+    out = CTX.Queue()
+    pred = ThreadPredictor(server, 0, S, pq)
+    trainer = ThreadTrainer(server, 0)
+    pred.start(); trainer.start()
+    procs = [CTX.Process(target=_agent_proc, args=(i, pq, tq, n_steps, t_max, out)) for i in range(n_agents)]
+    try:
+        for p in procs:
+            p.start()
+        res = dict(out.get(timeout=60) for _ in procs)
+        for p in procs:
+            p.join(timeout=10)
+        assert res == {i: 0 for i in range(n_agents)}                    # every reply reached the agent that asked
+        assert pred.rows == n_agents * n_steps and max(server.model.batches) > 1
+        deadline = time.time() + 10
+        while len(server.trained) < n_agents * n_steps // t_max and time.time() < deadline:
+            time.sleep(0.01)
+        assert len(server.trained) == n_agents * n_steps // t_max
+        assert sorted(int(t[1][0]) for t in server.trained) == sorted(list(range(n_agents)) * (n_steps // t_max))
+        assert all(t[0].shape == (t_max, S) and t[3] == (t_max, 0) for t in server.trained)
+    finally:
+        pred.exit_flag = True; trainer.exit_flag = True
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+        time.sleep(0.1)
+        pq.close(); tq.close()
+
+
+@pytest.mark.reference
+def test_reference_threads_run_unmodified_over_the_slab_queues():
+    """The reference's own ThreadPredictor / ThreadTrainer (imported from /root/reference) over the slab objects."""
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REFERENCE)
+    try:
+        from ThreadPredictor import ThreadPredictor as RefPredictor
+        from ThreadTrainer import ThreadTrainer as RefTrainer
+        from Config import Config as RefConfig
+    finally:
+        sys.path.remove(REFERENCE)
+    n_agents = 5
+    pq = SlabPredictionQueue(n_agents, S, A, ctx=CTX)
+    tq = SlabTrainingQueue(n_agents, max_rows=4, state_dim=S, num_actions=A, ctx=CTX)
+    server = FakeServer(tq)
+
+    class Agent:
+        def __init__(self, i):
+            self.wait_q = pq.wait_q(i)
+    server.agents = [Agent(i) for i in range(n_agents)]
+    old = (RefConfig.USE_REPLAY_MEMORY, RefConfig.TRAIN_MODELS, RefConfig.TRAINING_MIN_BATCH_SIZE, getattr(RefConfig, "USE_NETWORK_TESTER", False))
+    RefConfig.USE_REPLAY_MEMORY, RefConfig.TRAIN_MODELS, RefConfig.TRAINING_MIN_BATCH_SIZE, RefConfig.USE_NETWORK_TESTER = False, True, 0, False
+    pred, trainer = RefPredictor(server, 0, S, pq), RefTrainer(server, 0)
+    pred.daemon = trainer.daemon = True
+    try:
+        pred.start(); trainer.start()
+        states = {i: np.full(S, 0.25 * (i + 1), np.float32) for i in range(n_agents)}
+        for i, s in states.items():
+            pq.put((i, s))
+        for i, s in states.items():
+            p, v = server.agents[i].wait_q.get(timeout=5)
+            assert np.allclose(p, [s.sum(), s.sum() + 1, s.sum() + 2]) and np.isclose(v, 2 * s.sum())
+        x = np.random.rand(4, S).astype(np.float32)
+        tq.for_agent(3).put((x, np.ones(4), np.eye(A, dtype=np.float32)[[0, 1, 2, 0]], x, np.zeros(4, bool)))
+        deadline = time.time() + 5
+        while not server.trained and time.time() < deadline:
+            time.sleep(0.01)
+        assert len(server.trained) == 1 and np.array_equal(server.trained[0][0], x)
+    finally:
+        pred.exit_flag = True; trainer.exit_flag = True
+        RefConfig.USE_REPLAY_MEMORY, RefConfig.TRAIN_MODELS, RefConfig.TRAINING_MIN_BATCH_SIZE, RefConfig.USE_NETWORK_TESTER = old
+        pq.put((0, states[0]))           # unblock the reference predictor so its loop sees exit_flag
+        tq.for_agent(0).put((x, np.ones(4), np.eye(A, dtype=np.float32)[[0, 1, 2, 0]], x, np.zeros(4, bool)))
+        time.sleep(0.2)
+        pq.close(); tq.close()
