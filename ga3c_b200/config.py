@@ -61,3 +61,16 @@ class Config:
     USE_REPLAY_MEMORY = False
     USE_NETWORK_TESTER = False
     RANDOM_SEED = 12345
+
+    # annealing -- Config.py:196-197 (episodes over which lr / beta move from START to END)
+    EPISODES = 40000
+    ANNEALING_EPISODE_COUNT = 40000
+
+
+def annealed(cfg, episode_count):
+    """(learning_rate, beta) as Server.main sets them on the model every 10 ms (Server.py:168-175): linear in the episode
+    count, clamped at ANNEALING_EPISODE_COUNT - 1.  `model.learning_rate, model.beta = annealed(Config, episodes)`."""
+    lr_mult = (cfg.LEARNING_RATE_END - cfg.LEARNING_RATE_START) / cfg.ANNEALING_EPISODE_COUNT
+    beta_mult = (cfg.BETA_END - cfg.BETA_START) / cfg.ANNEALING_EPISODE_COUNT
+    step = min(episode_count, cfg.ANNEALING_EPISODE_COUNT - 1)
+    return cfg.LEARNING_RATE_START + lr_mult * step, cfg.BETA_START + beta_mult * step

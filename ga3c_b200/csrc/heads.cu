@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
         const float inv_den = 1.f / den;
         float pr[A];
 #pragma unroll
-        for (int k = 0; k < A; ++k) { sm[k] *= inv_den; pr[k] = (sm[k] + p.min_policy) * inv_mix; }
+        for (int k = 0; k < A; ++k) { sm[k] *= inv_den; pr[k] = p.log_softmax ? sm[k] : (sm[k] + p.min_policy) * inv_mix; }
         if (p.p_out != nullptr) {
 #pragma unroll
           for (int k = 0; k < A; ++k) if (lane == k) p.p_out[(size_t)b * A + k] = pr[k];
@@ -108,21 +108,39 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
 #pragma unroll
           for (int k = 0; k < A; ++k) { av[k] = p.a[(size_t)b * A + k]; sel = fmaf(pr[k], av[k], sel); }
           const float adv = yr - v, dv = v - yr;
-          const float coef = (sel >= p.log_eps) ? adv / sel : 0.f;
-          float h[A], sh = 0.f, ent = 0.f;
+          float dz[A], ent = 0.f, c1;
+          if (p.log_softmax) {
+            // Config.USE_LOG_SOFTMAX (NetworkVP_discrate.py:64-71): lsm = z - max - log(den); cost_p_1 = sum(lsm a) adv,
+            // cost_p_2 = -beta sum(lsm s);  dz_k = -adv (a_k - s_k sum(a)) + beta s_k (lsm_k - sum(lsm s))
+            const float lden = logf(den);
+            float lsm[A], sa = 0.f, sla = 0.f;
 #pragma unroll
-          for (int k = 0; k < A; ++k) {
-            const float lg = logf(fmaxf(pr[k], p.log_eps));
-            ent = fmaf(lg, pr[k], ent);
-            const float gk = -av[k] * coef + p.beta * (lg + (pr[k] >= p.log_eps ? 1.f : 0.f));
-            h[k] = gk * inv_mix;
-            sh = fmaf(sm[k], h[k], sh);
+            for (int k = 0; k < A; ++k) {
+              lsm[k] = (z[k] - mx) - lden;
+              ent = fmaf(lsm[k], sm[k], ent);
+              sa += av[k];
+              sla = fmaf(lsm[k], av[k], sla);
+            }
+#pragma unroll
+            for (int k = 0; k < A; ++k) dz[k] = -adv * (av[k] - sm[k] * sa) + p.beta * sm[k] * (lsm[k] - ent);
+            c1 = sla * adv;
+          } else {
+            const float coef = (sel >= p.log_eps) ? adv / sel : 0.f;
+            float h[A], sh = 0.f;
+#pragma unroll
+            for (int k = 0; k < A; ++k) {
+              const float lg = logf(fmaxf(pr[k], p.log_eps));
+              ent = fmaf(lg, pr[k], ent);
+              const float gk = -av[k] * coef + p.beta * (lg + (pr[k] >= p.log_eps ? 1.f : 0.f));
+              h[k] = gk * inv_mix;
+              sh = fmaf(sm[k], h[k], sh);
+            }
+#pragma unroll
+            for (int k = 0; k < A; ++k) dz[k] = sm[k] * (h[k] - sh);
+            c1 = logf(fmaxf(sel, p.log_eps)) * adv;
           }
-          float dz[A];
-#pragma unroll
-          for (int k = 0; k < A; ++k) dz[k] = sm[k] * (h[k] - sh);
           if (lane == 0) {
-            l1 += logf(fmaxf(sel, p.log_eps)) * adv;
+            l1 += c1;
             l2 += -p.beta * ent;
             lv += 0.5f * (yr - v) * (yr - v);
 #pragma unroll

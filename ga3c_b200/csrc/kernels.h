@@ -55,6 +55,7 @@ struct HeadsArgs {
   float* loss;                 // [4] (cost_p_1, cost_p_2, cost_v, 0) partial sums, same slab scheme
   int64_t gp_stride;
   int train;
+  int log_softmax;             // Config.USE_LOG_SOFTMAX
 };
 int heads_grid(int batch, int num_sms);          // CTAs (= slabs written) of a training launch
 int launch_heads(const HeadsArgs& args, int num_sms, cudaStream_t stream);

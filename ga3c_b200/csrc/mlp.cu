@@ -279,11 +279,29 @@ __global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, cons
         float sel = 0.f, ent = 0.f, sh = 0.f;
         for (int j = 0; j < A; ++j) {
           const float sm = expf(z[1 + j] - mx) * inv_den;
-          const float p = (sm + net.min_policy) * inv_mix;
+          const float p = net.log_softmax ? sm : (sm + net.min_policy) * inv_mix;
           if (valid && s.p_out != nullptr) s.p_out[(size_t)(row0 + r) * A + j] = p;
           if (TRAIN && valid) sel = fmaf(p, s.a[(size_t)(row0 + r) * A + j], sel);
         }
-        if (TRAIN) {
+        if (TRAIN && net.log_softmax) {
+          // Config.USE_LOG_SOFTMAX (NetworkVP_discrate.py:64-71): dz_j = -adv (a_j - s_j sum(a)) + beta s_j (lsm_j - sum(lsm s))
+          const float lden = logf(den);
+          float sa = 0.f, sla = 0.f;
+          for (int j = 0; j < A; ++j) {
+            const float lsm = (z[1 + j] - mx) - lden;
+            const float av = valid ? s.a[(size_t)(row0 + r) * A + j] : 0.f;
+            ent = fmaf(lsm, expf(z[1 + j] - mx) * inv_den, ent);
+            sa += av;
+            sla = fmaf(lsm, av, sla);
+          }
+          for (int j = 0; j < A; ++j) {
+            const float lsm = (z[1 + j] - mx) - lden;
+            const float sm = expf(z[1 + j] - mx) * inv_den;
+            const float av = valid ? s.a[(size_t)(row0 + r) * A + j] : 0.f;
+            z[1 + j] = valid ? -adv * (av - sm * sa) + s.beta * sm * (lsm - ent) : 0.f;
+          }
+          if (valid) { l1 = sla * adv; l2 = -s.beta * ent; }
+        } else if (TRAIN) {
           const float coef = (valid && sel >= net.log_eps) ? adv / sel : 0.f;
           // two sweeps: sh = sum_j sm_j h_j first, then dz_j = sm_j (h_j - sh)
           for (int j = 0; j < A; ++j) {

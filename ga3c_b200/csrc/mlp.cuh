@@ -31,6 +31,7 @@ struct MlpNet {
   int wp_off, bp_off;   // logits_p   (fork_vp: logits_p/out_x)
   int wy_off, by_off;   // fork_vp: logits_p/out_y
   float log_eps, min_policy;
+  int log_softmax;      // DISCRATE: Config.USE_LOG_SOFTMAX
 };
 
 struct MlpStepArgs {

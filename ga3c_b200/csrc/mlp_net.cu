@@ -130,7 +130,7 @@ extern "C" int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out) {
   const int S = cfg->state_dim, A = cfg->num_actions;
   MlpNet& net = n->net;
   net.kind = cfg->kind; net.state_dim = S; net.num_actions = A;
-  net.log_eps = cfg->log_epsilon; net.min_policy = cfg->min_policy;
+  net.log_eps = cfg->log_epsilon; net.min_policy = cfg->min_policy; net.log_softmax = cfg->use_log_softmax != 0;
 
   auto add = [&](const std::string& scope, int k, int width, int live) {    // dense_layer: 'w' [k, width] then 'b' [width]
     MlpParam w{scope + "/w:0", 0, (int64_t)k * width, 2, {k, width, 0, 0}, live};

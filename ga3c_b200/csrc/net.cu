@@ -119,7 +119,7 @@ int set_error(const std::string& m) { g_err = m; return -1; }     // for the oth
 const char* kernel_name(int kid) { return (kid >= 0 && kid < K_COUNT) ? kKernelNames[kid] : nullptr; }
 }
 extern "C" const char* ga3c_last_error(void) { return g_err.c_str(); }
-extern "C" int ga3c_abi_version(void) { return 1; }
+extern "C" int ga3c_abi_version(void) { return 2; }
 
 extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
   if (!cfg || !out) return fail_msg("ga3c_create: null argument");
@@ -325,7 +325,7 @@ static HeadsArgs heads_args(ga3c_net* n, int batch, int splits) {
   h.wp = n->w + n->off(P_PW); h.bp = n->w + n->off(P_PB);
   h.wv = n->w + n->off(P_VW); h.bv = n->w + n->off(P_VB);
   h.batch = batch; h.num_actions = n->cfg.num_actions;
-  h.log_eps = n->cfg.log_epsilon; h.min_policy = n->cfg.min_policy;
+  h.log_eps = n->cfg.log_epsilon; h.min_policy = n->cfg.min_policy; h.log_softmax = n->cfg.use_log_softmax != 0;
   return h;
 }
 

@@ -34,7 +34,7 @@ class _MlpNetwork:
         self.model_name = model_name
         self.num_actions = int(num_actions)
         self.state_dim = int(np.prod(state_dim)) if not isinstance(state_dim, int) else state_dim
-        for knob in ("USE_LOG_SOFTMAX", "DUAL_RMSPROP", "USE_GRAD_CLIP"):
+        for knob in ("DUAL_RMSPROP", "USE_GRAD_CLIP"):
             if getattr(cfg, knob, False):
                 raise NotImplementedError(f"Config.{knob}=True is not built yet (SURVEY.md 8f F4)")
         self.learning_rate = cfg.LEARNING_RATE_START
@@ -54,7 +54,8 @@ class _MlpNetwork:
                                   dense_width=(C.c_int32 * 8)(*dense[:8]),
                                   rmsprop_decay=cfg.RMSPROP_DECAY, rmsprop_momentum=cfg.RMSPROP_MOMENTUM,
                                   rmsprop_epsilon=cfg.RMSPROP_EPSILON, log_epsilon=cfg.LOG_EPSILON,
-                                  min_policy=cfg.MIN_POLICY)
+                                  min_policy=cfg.MIN_POLICY,
+                                  use_log_softmax=int(bool(getattr(cfg, 'USE_LOG_SOFTMAX', False))))
         if self.KIND == _capi.MLP_DISCRATE and len(dense) > 8:
             raise ValueError("Config.DENSE_LAYERS: at most 8 entries")
         h = C.c_void_p()

@@ -58,7 +58,7 @@ class Network:
         self.state_dim = int(np.prod(state_dim)) if not isinstance(state_dim, int) else state_dim
         if self.state_dim != STATE_DIM:
             raise ValueError(f"conv NetworkVP expects state_dim = 84*84*4 = {STATE_DIM}, got {self.state_dim}")
-        for knob in ("USE_LOG_SOFTMAX", "DUAL_RMSPROP", "USE_GRAD_CLIP"):
+        for knob in ("DUAL_RMSPROP", "USE_GRAD_CLIP"):
             if getattr(cfg, knob, False):
                 raise NotImplementedError(f"Config.{knob}=True is not built yet (SURVEY.md 8f F4)")
 
@@ -77,7 +77,7 @@ class Network:
         c = _capi.ga3c_config(device=self._ordinal, num_actions=self.num_actions, max_batch=self._max_batch,
                               rmsprop_decay=cfg.RMSPROP_DECAY, rmsprop_momentum=cfg.RMSPROP_MOMENTUM,
                               rmsprop_epsilon=cfg.RMSPROP_EPSILON, log_epsilon=cfg.LOG_EPSILON,
-                              min_policy=cfg.MIN_POLICY)
+                              min_policy=cfg.MIN_POLICY, use_log_softmax=int(bool(getattr(cfg, 'USE_LOG_SOFTMAX', False))))
         h = C.c_void_p()
         _capi.check(self._lib.ga3c_create(C.byref(c), C.byref(h)), "ga3c_create")
         self._h = h

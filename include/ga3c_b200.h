@@ -44,6 +44,7 @@ typedef struct ga3c_config {
   float   rmsprop_epsilon;   /* Config.RMSPROP_EPSILON  (0.1)  -- inside the sqrt             */
   float   log_epsilon;       /* Config.LOG_EPSILON      (1e-6)                                */
   float   min_policy;        /* Config.MIN_POLICY       (0.0)                                 */
+  int32_t use_log_softmax;   /* Config.USE_LOG_SOFTMAX  (False): NetworkVP_discrate.py:64-71  */
 } ga3c_config;
 
 const char* ga3c_last_error(void);
@@ -169,6 +170,7 @@ typedef struct ga3c_mlp_config {
   int32_t n_dense;           /* DISCRATE: len(Config.DENSE_LAYERS), 1..8; FORK_VP: ignored             */
   int32_t dense_width[8];    /* DISCRATE: Config.DENSE_LAYERS (each 1..256, the last <= 128)           */
   float   rmsprop_decay, rmsprop_momentum, rmsprop_epsilon, log_epsilon, min_policy;
+  int32_t use_log_softmax;   /* DISCRATE only (the fork's NetworkVP has no softmax at all)                          */
 } ga3c_mlp_config;
 int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out);
 int ga3c_mlp_destroy(ga3c_mlp* net);

@@ -76,7 +76,7 @@ def _sigmoid(z):
     return 1.0 / (1.0 + np.exp(-z))
 
 
-def forward(params, x, kind: str, *, dtype=np.float64, min_policy=0.0, keep=False):
+def forward(params, x, kind: str, *, dtype=np.float64, min_policy=0.0, keep=False, use_log_softmax=False):
     """-> p [B,A], v [B] (and the activations with keep=True)."""
     P = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
     h = np.asarray(x, dtype=dtype)
@@ -98,18 +98,19 @@ def forward(params, x, kind: str, *, dtype=np.float64, min_policy=0.0, keep=Fals
         s = np.exp(z)
         s = s / s.sum(axis=1, keepdims=True)
         a_n = s.shape[1]
-        p = (s + min_policy) / (1.0 + min_policy * a_n)
-        f.update(s=s)
+        p = s if use_log_softmax else (s + min_policy) / (1.0 + min_policy * a_n)      # NetworkVP_discrate.py:64-74
+        f.update(s=s, lsm=np.log(s))
     f["p"] = p
     return (p, v, f) if keep else (p, v)
 
 
-def loss_and_grads(params, x, y_r, a, kind: str, *, beta=0.01, log_eps=1e-6, min_policy=0.0, dtype=np.float64):
+def loss_and_grads(params, x, y_r, a, kind: str, *, beta=0.01, log_eps=1e-6, min_policy=0.0, dtype=np.float64,
+                   use_log_softmax=False):
     """-> ({cost_p_1, cost_p_2, cost_p, cost_v, cost_all}, {name: grad}) ; dead variables get no entry."""
     P = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
     y_r = np.asarray(y_r, dtype=dtype)
     a = np.asarray(a, dtype=dtype)
-    p, v, f = forward(params, x, kind, dtype=dtype, min_policy=min_policy, keep=True)
+    p, v, f = forward(params, x, kind, dtype=dtype, min_policy=min_policy, keep=True, use_log_softmax=use_log_softmax)
     adv = y_r - v                                   # stop_gradient(v) inside cost_p_1
     cost_v = 0.5 * np.sum((y_r - v) ** 2)
     dv = v - y_r
@@ -142,6 +143,11 @@ def loss_and_grads(params, x, y_r, a, kind: str, *, beta=0.01, log_eps=1e-6, min
         gk = -a * coef[:, None] + beta * (lg + (p >= log_eps))          # d cost_all / d p
         hk = gk * inv_mix                                               # d / d softmax
         dz = s * (hk - np.sum(s * hk, axis=1, keepdims=True))
+        if use_log_softmax:                                                 # NetworkVP_discrate.py:64-71
+            lsm = f["lsm"]
+            c1 = np.sum(np.sum(lsm * a, axis=1) * adv)
+            c2 = np.sum(-beta * np.sum(lsm * s, axis=1))
+            dz = -adv[:, None] * (a - s * a.sum(axis=1, keepdims=True)) + beta * s * (lsm - np.sum(lsm * s, axis=1, keepdims=True))
         grads["logits_p/w:0"] = h.T @ dz
         grads["logits_p/b:0"] = dz.sum(axis=0)
         dh = dz @ P["logits_p/w:0"].T

@@ -130,7 +130,7 @@ def _col2im(dcols, b, h, k, s, lo, hi, n_out, c):
 # --------------------------------------------------------------------------------------
 # forward
 # --------------------------------------------------------------------------------------
-def forward(params, x, *, dtype=np.float64, quant=None, min_policy=0.0, keep=False):
+def forward(params, x, *, dtype=np.float64, quant=None, min_policy=0.0, keep=False, use_log_softmax=False):
     """A2/A3/A4 forward.  x: [B, 28224] (flat NHWC).  Returns (p [B,A], v [B]) or a cache dict."""
     b = x.shape[0]
     xq = _q(x.reshape(b, H, W, C), quant, dtype)
@@ -152,9 +152,11 @@ def forward(params, x, *, dtype=np.float64, quant=None, min_policy=0.0, keep=Fal
     s = e / e.sum(axis=1, keepdims=True)
     a_n = z.shape[1]
     p = (s + dtype(min_policy)) / (dtype(1.0) + dtype(min_policy) * a_n)  # NetworkVP_discrate.py:73-74
+    if use_log_softmax:
+        p = s                                                              # NetworkVP_discrate.py:65 (no MIN_POLICY mix)
     if not keep:
         return p, v
-    return dict(x=xq, col1=col1, n1=n1, col2=col2, n2=n2, flat=flat, d1=d1, v=v, z=z, s=s, p=p,
+    return dict(x=xq, col1=col1, n1=n1, col2=col2, n2=n2, flat=flat, d1=d1, v=v, z=z, s=s, p=p, lsm=zs - np.log(e.sum(axis=1, keepdims=True)),
                 w11=w11, w12=w12, w1=w1)
 
 
@@ -176,11 +178,21 @@ def losses_from_heads(p, v, y_r, a, beta, log_eps, v_stop=None):
                 cost_all=cost_p + cost_v)
 
 
+def losses_from_log_softmax(lsm, s, v, y_r, a, beta, v_stop=None):
+    """Config.USE_LOG_SOFTMAX branch, NetworkVP_discrate.py:64-71: log_softmax instead of log(max(softmax, eps))."""
+    adv = y_r - (v if v_stop is None else v_stop)
+    cost_p_1_agg = ((lsm * a).sum(axis=1) * adv).sum()
+    cost_p_2_agg = (-beta * (lsm * s).sum(axis=1)).sum()
+    cost_p = -(cost_p_1_agg + cost_p_2_agg)
+    cost_v = 0.5 * ((y_r - v) ** 2).sum()
+    return dict(cost_p_1=cost_p_1_agg, cost_p_2=cost_p_2_agg, cost_p=cost_p, cost_v=cost_v, cost_all=cost_p + cost_v)
+
+
 def loss_and_grads(params, x, y_r, a, *, beta=0.01, log_eps=1e-6, min_policy=0.0,
-                   dtype=np.float64, quant=None, keep=False):
+                   dtype=np.float64, quant=None, keep=False, use_log_softmax=False):
     """A5 minus the optimizer: returns (losses dict, grads dict keyed like params); with keep=True
     also the forward cache extended by the backward intermediates dd1 / dn2 / dn1 / dz / dv."""
-    f = forward(params, x, dtype=dtype, quant=quant, min_policy=min_policy, keep=True)
+    f = forward(params, x, dtype=dtype, quant=quant, min_policy=min_policy, keep=True, use_log_softmax=use_log_softmax)
     b = x.shape[0]
     y_r = np.asarray(y_r, dtype=dtype)
     a = np.asarray(a, dtype=dtype)
@@ -198,6 +210,11 @@ def loss_and_grads(params, x, y_r, a, *, beta=0.01, log_eps=1e-6, min_policy=0.0
          + beta * (np.log(np.maximum(p, log_eps)) + (p >= log_eps)))
     h = g / (dtype(1.0) + dtype(min_policy) * a_n)
     dz = s * (h - (s * h).sum(axis=1, keepdims=True))
+    if use_log_softmax:
+        # d/dz of -(sum_a lsm a) adv - (-beta sum lsm s):  -adv (a - s sum(a)) + beta s (lsm - sum(lsm s))
+        lsm = f["lsm"]
+        losses = losses_from_log_softmax(lsm, s, v, y_r, a, beta)
+        dz = -adv[:, None] * (a - s * a.sum(axis=1, keepdims=True)) + beta * s * (lsm - (lsm * s).sum(axis=1, keepdims=True))
     wp = params["logits_p/w:0"].astype(dtype)
     wv = params["logits_v/w:0"].astype(dtype)
     grads = {
@@ -246,10 +263,10 @@ def rmsprop_update(params, grads, ms, mom, *, lr, rho=0.99, mu=0.0, eps=0.1, dty
     return new_p, new_ms, new_mom
 
 
-def train_step(params, ms, mom, x, y_r, a, *, lr, beta=0.01, log_eps=1e-6, min_policy=0.0,
+def train_step(params, ms, mom, x, y_r, a, *, lr, beta=0.01, log_eps=1e-6, min_policy=0.0, use_log_softmax=False,
                rho=0.99, mu=0.0, eps=0.1, dtype=np.float64, quant=None):
     losses, grads = loss_and_grads(params, x, y_r, a, beta=beta, log_eps=log_eps,
-                                   min_policy=min_policy, dtype=dtype, quant=quant)
+                                   min_policy=min_policy, dtype=dtype, quant=quant, use_log_softmax=use_log_softmax)
     p2, ms2, mom2 = rmsprop_update(params, grads, ms, mom, lr=lr, rho=rho, mu=mu, eps=eps, dtype=dtype)
     return losses, grads, p2, ms2, mom2
 

@@ -24,7 +24,7 @@ def err(got, ref):
     return d, d / max(s, 1e-30)
 
 
-def layer_report(net, params, x, y_r, a, *, beta=0.01, log_eps=1e-6, min_policy=0.0):
+def layer_report(net, params, x, y_r, a, *, beta=0.01, log_eps=1e-6, min_policy=0.0, use_log_softmax=False):
     """Runs predict + forward_backward on `net` (weights := params) and compares every stored
     activation, every gradient and the loss sums with the bf16-rounding-point oracle (fp64 accumulate).
     Returns {name: (abs_err, rel_err)}."""
@@ -33,7 +33,8 @@ def layer_report(net, params, x, y_r, a, *, beta=0.01, log_eps=1e-6, min_policy=
     rep = {}
     p, v = net.predict_p_and_v(x)
     losses_ref, grads_ref, f = onp.loss_and_grads(params, x, y_r, a, beta=beta, log_eps=log_eps,
-                                                  min_policy=min_policy, quant="bf16", keep=True)
+                                                  min_policy=min_policy, quant="bf16", keep=True,
+                                                  use_log_softmax=use_log_softmax)
     rep["p"] = err(p, f["p"])
     rep["v"] = err(v, f["v"])
     net.keep_dn1(True)          # dn1 is consumed on chip by the fused conv backward; ask for a copy

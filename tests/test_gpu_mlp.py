@@ -111,6 +111,27 @@ def test_min_policy_mix(mlp):
         assert err(grads[k], g_ref)[1] <= TOL_GRAD_REL, k
 
 
+def test_log_softmax_knob(mlp):
+    """Config.USE_LOG_SOFTMAX = True (NetworkVP_discrate.py:64-71): exact log_softmax, no MIN_POLICY mix, no epsilon floor."""
+    class Cfg(mlp._DefaultConfig):
+        USE_LOG_SOFTMAX = True
+        MIN_POLICY = 0.05                  # ignored by this branch
+    kind, s, a, b = "discrate", 4, 2, 500
+    params, x, y_r, act = make_case(kind, s, a, b, seed=5)
+    net = make_net(mlp, kind, s, a, config=Cfg)
+    net.set_variables(params)
+    p, v = net.predict_p_and_v(x)
+    p_ref, v_ref = om.forward(params, x, kind, use_log_softmax=True)
+    assert err(p, p_ref)[0] <= TOL_PV and err(v, v_ref)[0] <= TOL_PV
+    losses = net.losses(x, y_r, act)
+    losses_ref, grads_ref = om.loss_and_grads(params, x, y_r, act, kind, beta=0.01, use_log_softmax=True)
+    for k in ("cost_p_1", "cost_p_2", "cost_v", "cost_all"):
+        assert abs(losses[k] - losses_ref[k]) <= 2e-5 * b, (k, losses[k], losses_ref[k])
+    grads = net.get_gradients()
+    for k, g_ref in grads_ref.items():
+        assert err(grads[k], g_ref)[1] <= TOL_GRAD_REL, (k, err(grads[k], g_ref))
+
+
 @pytest.mark.parametrize("kind,s,a", CASES)
 def test_train_steps_match_oracle(mlp, kind, s, a):
     """Three opt.minimize steps: weights, ms slot, global_step; gradient-less variables untouched (bit-identical)."""

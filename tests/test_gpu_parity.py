@@ -85,6 +85,21 @@ def test_min_policy_and_active_epsilon_floor(ga3c):
     check_report(rep)
 
 
+def test_log_softmax_knob(ga3c):
+    """Config.USE_LOG_SOFTMAX = True (NetworkVP_discrate.py:64-71): log_softmax losses, plain softmax policy (MIN_POLICY and
+    the epsilon floor do not apply); every activation, gradient and loss sum against the oracle's same branch."""
+    class Cfg(ga3c.Config):
+        USE_LOG_SOFTMAX = True
+        MIN_POLICY = 0.02
+    params, x, y_r, a = make_case(40, seed=13)
+    params["logits_p/w:0"] *= 6.0
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=64, config=Cfg)
+    rep = layer_report(net, params, x, y_r, a, beta=0.05, use_log_softmax=True)
+    check_report(rep)
+    p, _ = net.predict_p_and_v(x)
+    assert np.allclose(p.sum(axis=1), 1.0, atol=1e-5)
+
+
 def test_golden_network_b4(ga3c, golden_dir):
     """The committed B=4 fixture (tests/golden/network_b4.npz, oracle/gen_golden.py)."""
     g = np.load(os.path.join(golden_dir, "network_b4.npz"))

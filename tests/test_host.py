@@ -70,6 +70,23 @@ def test_parse_device():
         _parse_device("cpu:0")
 
 
+def test_annealing_matches_server_loop():
+    """Server.py:168-175: linear in the episode count, clamped at ANNEALING_EPISODE_COUNT - 1."""
+    from ga3c_b200 import Config
+    from ga3c_b200.config import annealed
+
+    class Cfg(Config):
+        LEARNING_RATE_START, LEARNING_RATE_END = 3e-4, 1e-4
+        BETA_START, BETA_END = 0.01, 0.002
+        ANNEALING_EPISODE_COUNT = 1000
+    for ep in (0, 1, 500, 999, 1000, 50000):
+        lr_mult = (Cfg.LEARNING_RATE_END - Cfg.LEARNING_RATE_START) / Cfg.ANNEALING_EPISODE_COUNT
+        beta_mult = (Cfg.BETA_END - Cfg.BETA_START) / Cfg.ANNEALING_EPISODE_COUNT
+        step = min(ep, Cfg.ANNEALING_EPISODE_COUNT - 1)
+        assert annealed(Cfg, ep) == (Cfg.LEARNING_RATE_START + lr_mult * step, Cfg.BETA_START + beta_mult * step)
+    assert annealed(Config, 12345) == (Config.LEARNING_RATE_START, Config.BETA_START)     # START == END by default
+
+
 def test_config_matches_reference_defaults():
     """Every knob the path reads has the reference's default (Config.py)."""
     from ga3c_b200 import Config

@@ -140,6 +140,44 @@ def test_backward_finite_differences(small):
             assert abs(fd - grads[k][idx]) <= 1e-6 * max(1.0, abs(fd)), (k, idx, fd, grads[k][idx])
 
 
+def test_log_softmax_branch_finite_differences_and_torch(small):
+    """Config.USE_LOG_SOFTMAX (NetworkVP_discrate.py:64-71): analytic backward against finite differences (advantage frozen,
+    tf.stop_gradient) and against torch autograd on log_softmax / softmax of the oracle's own logits."""
+    params, x, y_r, a = small
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    a = a.astype(np.float64) * 0.7 + 0.05                     # not one-hot: exercises the sum(a) term
+    losses, grads, f = onp.loss_and_grads(p64, x, y_r, a, beta=0.03, use_log_softmax=True, keep=True)
+    p, _ = onp.forward(p64, x, use_log_softmax=True)
+    assert np.allclose(p.sum(axis=1), 1.0) and np.array_equal(p, f["s"])
+    v0 = f["v"]
+
+    def cost(pm):
+        g = onp.forward(pm, x, keep=True, use_log_softmax=True)
+        return onp.losses_from_log_softmax(g["lsm"], g["s"], g["v"], y_r.astype(np.float64), a, 0.03, v_stop=v0)["cost_all"]
+
+    rng = np.random.default_rng(9)
+    for k in p64:
+        for _ in range(3):
+            idx = tuple(int(rng.integers(0, s)) for s in p64[k].shape)
+            if grads[k][idx] == 0.0:
+                continue
+            h = 1e-7                                            # small: a ReLU kink inside (-h, h) spoils the difference
+            pp = {n: v.copy() for n, v in p64.items()}; pp[k][idx] += h
+            pm = {n: v.copy() for n, v in p64.items()}; pm[k][idx] -= h
+            fd = (cost(pp) - cost(pm)) / (2 * h)
+            assert abs(fd - grads[k][idx]) <= 1e-6 * max(1.0, abs(fd)), (k, idx, fd, grads[k][idx])
+    z = torch.tensor(f["z"], requires_grad=True)
+    v = torch.tensor(f["v"], requires_grad=True)
+    yr, at = torch.tensor(y_r.astype(np.float64)), torch.tensor(a)
+    lsm, sm = torch.log_softmax(z, dim=1), torch.softmax(z, dim=1)
+    c1 = ((lsm * at).sum(1) * (yr - v.detach())).sum()
+    c2 = (-0.03 * (lsm * sm).sum(1)).sum()
+    total = -(c1 + c2) + 0.5 * ((yr - v) ** 2).sum()
+    total.backward()
+    assert abs(float(total) - losses["cost_all"]) <= 1e-10 * max(1.0, abs(losses["cost_all"]))
+    assert np.abs(z.grad.numpy() - f["dz"]).max() <= 1e-12 and np.abs(v.grad.numpy() - f["dv"]).max() <= 1e-12
+
+
 def test_rmsprop_tf_semantics():
     """eps inside the sqrt, ms initialised to 1.0."""
     w = {"w": np.array([1.0, -2.0], dtype=np.float32)}

@@ -95,3 +95,23 @@ def test_discrate_dead_layers_keep_their_values():
     for name in om.dead_params("discrate"):
         assert np.array_equal(p2[name], params[name]) and np.array_equal(ms2[name], ms[name])
     assert not np.array_equal(p2["dense1_4_p/w:0"], params["dense1_4_p/w:0"])
+
+
+def test_discrate_log_softmax_branch_matches_torch():
+    """Config.USE_LOG_SOFTMAX (NetworkVP_discrate.py:64-71) against torch autograd."""
+    kind, s, a = "discrate", 4, 2
+    params, x, y_r, act = _case(kind, s, a, b=11, seed=8)
+    losses, grads = om.loss_and_grads(params, x, y_r, act, kind, beta=0.02, use_log_softmax=True)
+    tp = {k: torch.tensor(v.astype(np.float64), requires_grad=True) for k, v in params.items()}
+    tx, tyr, ta = (torch.tensor(np.asarray(t, dtype=np.float64)) for t in (x, y_r, act))
+    h = torch.sigmoid(tx @ tp["dense1_4_p/w:0"] + tp["dense1_4_p/b:0"])
+    v = (h @ tp["logits_v/w:0"] + tp["logits_v/b:0"])[:, 0]
+    z = h @ tp["logits_p/w:0"] + tp["logits_p/b:0"]
+    lsm, sm = torch.log_softmax(z, 1), torch.softmax(z, 1)
+    c1 = ((lsm * ta).sum(1) * (tyr - v.detach())).sum()
+    c2 = (-0.02 * (lsm * sm).sum(1)).sum()
+    total = -(c1 + c2) + 0.5 * ((tyr - v) ** 2).sum()
+    total.backward()
+    assert abs(float(total) - losses["cost_all"]) <= 1e-10 * max(1.0, abs(losses["cost_all"]))
+    for k, g in grads.items():
+        assert np.abs(tp[k].grad.numpy() - g).max() <= 1e-11, k
