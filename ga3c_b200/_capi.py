@@ -49,6 +49,8 @@ SIGNATURES = {
     "ga3c_dp_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ga3c_dp_attach": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "ga3c_dp_detach": (C.c_int, [C.c_void_p]),
+    "ga3c_dp_attach_local": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "ga3c_dp_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "ga3c_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,
                                   C.c_void_p, C.c_void_p]),
     "ga3c_predict_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

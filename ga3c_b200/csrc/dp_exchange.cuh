@@ -25,6 +25,7 @@ constexpr int DPC_DONE = 512;         // [8] x 64 B   single-kernel exchange: sl
 constexpr int DPC_CTR_DONE = 1024;    // u32 block counters of this rank's own grids
 constexpr int DPC_CTR_RED = 1028;
 constexpr int DPC_CTR_BIG = 1032;
+constexpr int DPC_ERR = 1040;         // u32: set when a wait gave up (a rank died or fell out of step): ga3c_dp_error
 constexpr int DPC_BIGREADY = 2048;    // [8] x 64 B   dense_bwd of the step complete on rank r
 constexpr int DPC_BIGDONE = 2560;     // [8] x 64 B   rank r's dense1/w slice stored everywhere
 constexpr int DPC_CB = 4096;          // [8][DP_MAX_CB] u64: column block cb of rank r's small gradients published
@@ -39,6 +40,16 @@ __device__ __forceinline__ uint64_t dp_ld_flag(const void* p) {
 __device__ __forceinline__ void dp_st_flag(void* p, uint64_t v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
+// Every cross-rank wait is bounded (about a second of polling): a rank that died or was called a different number of times
+// must not hang the others' GPUs for ever.  On expiry the waiter raises the error word of its own comm block and carries on;
+// the host sees it through ga3c_dp_error (results of that step are garbage).
+constexpr unsigned int DP_SPIN_LIMIT = 1u << 22;
+// error bits: 1 "gradients ready" (single-kernel exchange), 2 "done" (single-kernel), 4 dense_bwd-done flags of the
+// exchange CTAs, 8 small-tensor LL data, 16 dense1/w slices landed
+__device__ __forceinline__ void dp_wait_flag(const void* p, unsigned long long want, void* err, unsigned int bit) {
+  for (unsigned int i = 0; dp_ld_flag(p) < want; ++i)
+    if (i > DP_SPIN_LIMIT) { atomicOr(static_cast<unsigned int*>(err), bit); break; }
+}
 // LL wire format: a float4 travels as two 16-byte stores {x, flag, y, flag} {z, flag, w, flag}
 __device__ __forceinline__ void dp_ll_store(void* dst, const float4& v, uint32_t flag) {
   asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"l"(dst), "r"(__float_as_uint(v.x)), "r"(flag),
@@ -46,9 +57,11 @@ __device__ __forceinline__ void dp_ll_store(void* dst, const float4& v, uint32_t
   asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"l"(static_cast<uint8_t*>(dst) + 16),
                "r"(__float_as_uint(v.z)), "r"(flag), "r"(__float_as_uint(v.w)), "r"(flag) : "memory");
 }
-__device__ __forceinline__ float4 dp_ll_load(const void* src, uint32_t flag) {      // spins until all four flags match
+__device__ __forceinline__ float4 dp_ll_load(const void* src, uint32_t flag, void* err) {   // spins until all four flags match
   uint32_t a0, f0, a1, f1, a2, f2, a3, f3;
+  unsigned int spins = 0;
   do {
+    if (++spins > DP_SPIN_LIMIT) { atomicOr(static_cast<unsigned int*>(err), 8u); break; }
     asm volatile("ld.relaxed.sys.global.v4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(a0), "=r"(f0), "=r"(a1), "=r"(f1) : "l"(src) : "memory");
     asm volatile("ld.relaxed.sys.global.v4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(a2), "=r"(f2), "=r"(a3), "=r"(f3)
                  : "l"(static_cast<const uint8_t*>(src) + 16) : "memory");
@@ -130,7 +143,7 @@ __device__ __forceinline__ void dp_big_exchange(const DpBigArgs& d, int cta, int
   uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
   if (cta == 0 && tid < d.world) dp_st_flag(d.peer[tid] + d.comm_offset + DPC_BIGREADY + 64 * d.rank, d.step);
   if (tid < d.world) {
-    while (dp_ld_flag(my_comm + DPC_BIGREADY + 64 * tid) < d.step) { }
+    dp_wait_flag(my_comm + DPC_BIGREADY + 64 * tid, d.step, my_comm + DPC_ERR, 4u);
     __threadfence_system();
   }
   __syncthreads();

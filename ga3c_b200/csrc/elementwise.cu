@@ -303,8 +303,7 @@ __global__ void __launch_bounds__(512) rmsprop_dp_kernel(RmsPropDpArgs d) {
     st_flag(reinterpret_cast<uint64_t*>(d.peer[threadIdx.x] + d.comm_offset + 64 * d.rank), d.step);   // my gradients are final
   }
   if ((int)threadIdx.x < d.world) {
-    const uint64_t* f = reinterpret_cast<const uint64_t*>(my_comm + 64 * threadIdx.x);
-    while (ld_flag(f) < d.step) { }
+    dp_wait_flag(my_comm + DPC_READY + 64 * threadIdx.x, d.step, my_comm + DPC_ERR, 1u);
     __threadfence_system();
   }
   __syncthreads();
@@ -367,8 +366,7 @@ __global__ void __launch_bounds__(512) rmsprop_dp_kernel(RmsPropDpArgs d) {
   }
   __syncthreads();
   if (last && (int)threadIdx.x < d.world) {
-    const uint64_t* f = reinterpret_cast<const uint64_t*>(my_comm + DPC_DONE + 64 * threadIdx.x);
-    while (ld_flag(f) < d.step) { }
+    dp_wait_flag(my_comm + DPC_DONE + 64 * threadIdx.x, d.step, my_comm + DPC_ERR, 2u);
     __threadfence_system();
   }
   if (last) evt_mark(evt_i, 65, blockIdx.x);
@@ -455,7 +453,7 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_small_kernel(RmsPropDpA
         const float4 v = q == d.rank ? acc
                                      : dp_ll_load(d.peer[d.rank] + recv_offset +
                                                       ((int64_t)(d.step & 1) * DP_WORLD_MAX + q) * r.out_floats * 8 + (int64_t)j * 8,
-                                                  flag);
+                                                  flag, my_comm + DPC_ERR);
         g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
       }
     evt_mark(evt_i, 63, 0);
@@ -466,11 +464,23 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_small_kernel(RmsPropDpA
   }
   evt_mark(evt_i, 64, 0);
   if (cb == 0 && (int)threadIdx.x < d.world) {
-    while (dp_ld_flag(my_comm + DPC_BIGDONE + 64 * threadIdx.x) < d.step) { }
+    dp_wait_flag(my_comm + DPC_BIGDONE + 64 * threadIdx.x, d.step, my_comm + DPC_ERR, 16u);
     __threadfence_system();
   }
   evt_mark(evt_i, 65, 0);
   trace_mark(K_RMSPROP, 2);
+}
+
+// CUDA loads a kernel lazily at its first launch, and that load can wait for running kernels to finish.  A rank whose
+// exchange CTAs are already spinning on a peer would then block the very launch the peer needs (ranks that share a
+// process), so every kernel of the exchange is loaded when the ranks attach.
+int configure_dp() {
+  cudaFuncAttributes a;
+  int r;
+  if ((r = (int)cudaFuncGetAttributes(&a, dp_small_kernel<false>))) return r;
+  if ((r = (int)cudaFuncGetAttributes(&a, dp_small_kernel<true>))) return r;
+  if ((r = (int)cudaFuncGetAttributes(&a, rmsprop_dp_kernel<false>))) return r;
+  return (int)cudaFuncGetAttributes(&a, rmsprop_dp_kernel<true>);
 }
 
 int launch_dp_small(const RmsPropDpArgs& d, int64_t recv_offset, cudaStream_t stream) {

@@ -114,6 +114,7 @@ int launch_rmsprop_dp(const RmsPropDpArgs& a, int num_sms, cudaStream_t stream);
 // rank's receive buffer, identical RMSProp on every rank; returns only when every rank's dense1/w slice has landed.
 // a.red is required; recv_offset: byte offset in the slab of the receive buffers [2][DP_MAX_WORLD][small prefix * 8 B].
 int launch_dp_small(const RmsPropDpArgs& a, int64_t recv_offset, cudaStream_t stream);
+int configure_dp();     // load the exchange kernels now (not lazily at their first launch)
 int launch_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cudaStream_t stream);
 int launch_returns(const double* rewards, const int64_t* seg_offsets, int n_segments, const double* terminal,
                    double discount, int flags, double rmin, double rmax, double* out, cudaStream_t stream);

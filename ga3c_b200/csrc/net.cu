@@ -63,6 +63,7 @@ struct ga3c_net {
   // data parallel over peer memory (single node, <= 8 ranks)
   int dp_rank = 0, dp_world = 1;
   uint8_t* dp_peer[DP_MAX_WORLD] = {};   // slab base of every rank as mapped in this process (own slab at dp_rank)
+  bool dp_ipc[DP_MAX_WORLD] = {};        // mapped with cudaIpcOpenMemHandle (to be closed on detach)
   uint64_t dp_step = 0;
   int dp_exch = 20;                // exchange CTAs appended to the conv backward launch (GA3C_DP_EXCH_CTAS)
   int cur_exch = 0;                // ... of the step being enqueued (0 outside the overlapped data-parallel step)
@@ -113,6 +114,7 @@ enum { P_C11W = 0, P_C11B, P_C12W, P_C12B, P_D1W, P_D1B, P_VW, P_VB, P_PW, P_PB,
 
 static int alloc_workspace(ga3c_net* n, int max_batch);
 static int trace_attach_all(unsigned long long* buf);
+static int dp_attach_finish(ga3c_net* n, int32_t rank, int32_t world);
 
 namespace ga3c {
 int set_error(const std::string& m) { g_err = m; return -1; }     // for the other host files (mlp_net.cu)
@@ -491,8 +493,8 @@ extern "C" int ga3c_dp_export(ga3c_net* n, void* handle_out) {
 extern "C" int ga3c_dp_detach(ga3c_net* n) {
   if (!n) return 0;
   for (int r = 0; r < DP_MAX_WORLD; ++r)
-    if (n->dp_peer[r] && n->dp_peer[r] != n->slab) cudaIpcCloseMemHandle(n->dp_peer[r]);
-  for (int r = 0; r < DP_MAX_WORLD; ++r) n->dp_peer[r] = nullptr;
+    if (n->dp_peer[r] && n->dp_ipc[r]) cudaIpcCloseMemHandle(n->dp_peer[r]);
+  for (int r = 0; r < DP_MAX_WORLD; ++r) { n->dp_peer[r] = nullptr; n->dp_ipc[r] = false; }
   n->dp_world = 1; n->dp_rank = 0;
   return 0;
 }
@@ -514,11 +516,55 @@ extern "C" int ga3c_dp_attach(ga3c_net* n, int32_t rank, int32_t world, const vo
       return fail("cudaIpcOpenMemHandle (peer-to-peer access between the ranks' GPUs is required)", e);
     }
     n->dp_peer[r] = static_cast<uint8_t*>(p);
+    n->dp_ipc[r] = true;
   }
+  return dp_attach_finish(n, rank, world);
+}
+
+// ranks that live in ONE process (tests; a host that drives several GPUs from one process): the peers' slabs are ordinary
+// device pointers, no IPC handles involved.  peers[r] is rank r's handle (peers[rank] == net).
+extern "C" int ga3c_dp_attach_local(ga3c_net* n, int32_t rank, int32_t world, ga3c_net* const* peers) {
+  if (!n || !peers) return fail_msg("ga3c_dp_attach_local: null argument");
+  if (world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world || peers[rank] != n)
+    return fail_msg("ga3c_dp_attach_local: need 0 <= rank < world <= 8 and peers[rank] == net");
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaDeviceSynchronize());
+  ga3c_dp_detach(n);
+  for (int r = 0; r < world; ++r) {
+    if (!peers[r] || peers[r]->arena_floats != n->arena_floats) { ga3c_dp_detach(n); return fail_msg("ga3c_dp_attach_local: peers must be handles of the same network"); }
+    if (peers[r]->cfg.device != n->cfg.device) {
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, n->cfg.device, peers[r]->cfg.device);
+      if (!can) { ga3c_dp_detach(n); return fail_msg("ga3c_dp_attach_local: no peer access between the devices"); }
+      cudaError_t e = cudaDeviceEnablePeerAccess(peers[r]->cfg.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ga3c_dp_detach(n); return fail("cudaDeviceEnablePeerAccess", e); }
+      cudaGetLastError();
+    }
+    n->dp_peer[r] = peers[r]->slab;
+  }
+  return dp_attach_finish(n, rank, world);
+}
+
+static int dp_attach_finish(ga3c_net* n, int32_t rank, int32_t world) {
   n->dp_rank = rank; n->dp_world = world; n->dp_step = 0;
   if (const char* e = getenv("GA3C_DP_EXCH_CTAS")) n->dp_exch = atoi(e);     // 0: single exchange kernel at the end of the step
   if (n->dp_exch < 0 || n->dp_exch > n->num_sms / 2) n->dp_exch = 0;
   CK(cudaMemset(n->slab + n->xbuf_off, 0, n->slab_bytes - (size_t)n->xbuf_off));
+  CKL(configure_dp());
+  return 0;
+}
+
+// 0: every cross-rank wait of the exchange kernels completed; 1: one gave up (a rank died, or the ranks' train calls fell out
+// of step) and the weights can no longer be trusted.  Synchronises the device.
+extern "C" int ga3c_dp_error(ga3c_net* n, int32_t* error_out) {
+  if (!n || !error_out) return fail_msg("ga3c_dp_error: null argument");
+  *error_out = 0;
+  if (n->dp_world <= 1) return 0;
+  CK(cudaSetDevice(n->cfg.device));
+  CK(cudaDeviceSynchronize());
+  unsigned int e = 0;
+  CK(cudaMemcpy(&e, n->slab + n->comm_off + DPC_ERR, 4, cudaMemcpyDeviceToHost));
+  *error_out = (int32_t)e;
   return 0;
 }
 

@@ -337,6 +337,7 @@ class Network:
         return list(self._table.keys())
 
     def _download(self, which: int) -> np.ndarray:
+        self.dp_check()
         out = np.empty(self._arena_floats, dtype=np.float32)
         with self._lock:
             _capi.check(self._lib.ga3c_arena_download(self._h, which, out.ctypes.data, out.size), "ga3c_arena_download")
@@ -416,6 +417,15 @@ class Network:
                        {k: z[k.replace(":0", "/RMSProp_1:0")] for k in names})
         self._lib.ga3c_set_global_step(self._h, int(z["step:0"]))
         return self._get_episode_from_filename(filename)
+
+    def dp_check(self):
+        """Raises if a cross-rank wait of the data-parallel exchange gave up (a rank died or the ranks' train() calls fell
+        out of step): every such wait is bounded so that nothing hangs, but the replicas are no longer in sync."""
+        err = C.c_int32(0)
+        _capi.check(self._lib.ga3c_dp_error(self._h, C.byref(err)), "ga3c_dp_error")
+        if err.value:
+            raise _capi.Ga3cError(f"data-parallel exchange timed out waiting for a peer rank (wait bits {err.value:#x}, "
+                                  "dp_exchange.cuh): replicas are out of sync")
 
     # ------------------------------------------------------------------ introspection (tests / profiling)
     def launch_count(self) -> int:

@@ -100,6 +100,54 @@ def test_log_softmax_knob(ga3c):
     assert np.allclose(p.sum(axis=1), 1.0, atol=1e-5)
 
 
+def test_data_parallel_exchange_two_ranks_on_one_gpu(ga3c, monkeypatch):
+    """The fused data-parallel step (dp_exchange.cuh: dense1/w on exchange CTAs of the conv backward launch, LL push of the
+    small tensors) with BOTH ranks on one device: two handles attached to each other with ga3c_dp_attach_local, each on its
+    own stream, each training on its row shard.  After 3 steps the replicas are bit-identical and equal the oracle's
+    single-process steps on the concatenated batch (what a single ThreadTrainer would have computed).  The grids are small
+    (12 rows per rank), so both ranks' kernels are resident together; every cross-rank wait is bounded, so a scheduling
+    surprise fails the test instead of hanging the GPU."""
+    import ctypes as C
+    import torch
+    from ga3c_b200 import _capi
+    monkeypatch.setenv("GA3C_DP_EXCH_CTAS", "4")
+    world, b = 2, 12
+    rng = np.random.default_rng(17)
+    params = onp.init_params(rng, 6)
+    nets = [ga3c.Network("gpu:0", f"dp{r}", 6, max_batch=32, data_parallel=False) for r in range(world)]
+    lib = _capi.load()
+    handles = (C.c_void_p * world)(*[n._h.value for n in nets])
+    try:
+        for n in nets:
+            n.set_variables(params)
+        for r, n in enumerate(nets):
+            _capi.check(lib.ga3c_dp_attach_local(n._h, r, world, handles), "ga3c_dp_attach_local")
+        streams = [torch.cuda.Stream() for _ in nets]
+        ms, mom = onp.rmsprop_init(params)
+        ref = params
+        for step in range(3):
+            x = onp.synth_frames(rng, world * b)
+            y_r, a = onp.synth_targets(rng, world * b)
+            dev = [[torch.as_tensor(t[r * b:(r + 1) * b]).cuda() for t in (x, y_r, a)] for r in range(world)]
+            torch.cuda.synchronize()
+            for r, n in enumerate(nets):         # asynchronous: both ranks' kernels must be in flight together
+                n.train_device(*dev[r], stream=streams[r])
+            torch.cuda.synchronize()
+            _, _, ref, ms, mom = onp.train_step(ref, ms, mom, x, y_r, a, lr=nets[0].learning_rate, beta=nets[0].beta, quant="bf16")
+            ref = {k: v.astype(np.float32) for k, v in ref.items()}
+        for n in nets:
+            n.dp_check()
+        w = [n.get_variables() for n in nets]
+        m = [n.get_slots()[0] for n in nets]
+        for k in params:
+            assert np.array_equal(w[0][k], w[1][k]) and np.array_equal(m[0][k], m[1][k]), k     # replicas bit-identical
+            assert np.abs(w[0][k] - ref[k]).max() <= 3 * TOL_W_ABS, (k, np.abs(w[0][k] - ref[k]).max())
+        assert nets[0].get_global_step() == 3
+    finally:
+        for n in nets:
+            lib.ga3c_dp_detach(n._h)
+
+
 def test_golden_network_b4(ga3c, golden_dir):
     """The committed B=4 fixture (tests/golden/network_b4.npz, oracle/gen_golden.py)."""
     g = np.load(os.path.join(golden_dir, "network_b4.npz"))
