@@ -24,7 +24,6 @@ constexpr int RC = 16;               // reduction chunk
 constexpr int HLD = 49;              // row pitch of the head matrix / logits tile (odd: conflict-free column walks)
 constexpr int NT = 256;              // threads of the weight-gradient / reduce kernels
 constexpr int FT = 512;              // threads of the fused kernel: 16 warps x 4 rows = one 64-row tile
-constexpr int RT = MLP_TM / (FT / 32);   // rows per thread (4)
 constexpr int HW = 48;               // head matrix columns held in shared memory (>= MLP_MAX_OUT, zero padded)
 constexpr float PI_F = 3.14159265358979323846f;
 
@@ -51,12 +50,13 @@ __device__ __forceinline__ int head_b_index(const MlpNet& net, int j) {
 // One 64-row x (128 * JH)-column product through the CTA:  out[r][c] = sum_q in_s[r][q] * Wq[q][c], q < kred, with
 //   TRANS = false:  Wq[q][c] = Wg[q * ldw + c]        (forward:        W is [k][n], q = k, c = n)
 //   TRANS = true :  Wq[q][c] = Wg[c * ldw + q]        (data gradient:  W is [k][n], q = n, c = k)
-// Thread (ty = warp, tx = lane) owns rows ty*4 .. ty*4+3 and columns tx*4 .. tx*4+3 (+128 with JH = 2): 16 warps, four per
+// Thread (ty = warp, tx = lane) owns rows ty*RT .. ty*RT+RT-1 (RT = 4: 64-row tiles; RT = 1: 16-row tiles for small
+// batches, where 64-row tiles would leave most SMs idle) and columns tx*4 .. tx*4+3 (+128 with JH = 2): 16 warps, four per
 // scheduler (two 8-row warps per scheduler left the FMA pipe idle 45 % of the time: nothing to switch to on a shared-memory
 // wait).  The weight chunk [16][<= 256] of step q0+16 is fetched into registers while chunk q0 is being consumed.
 // epi(r, c0, v[4]) receives the finished sums of 4 consecutive columns, turns them into what the next pass reads and
 // stores whatever goes to HBM; the result lands in out_s.  in_s must be zero (finite) up to round_up16(kred).
-template <bool TRANS, int JH, class Epi>
+template <bool TRANS, int JH, int RT, class Epi>
 __device__ __forceinline__ void tile_pass(const float* in_s, float* out_s, float* Wc, int kred, const float* __restrict__ Wg,
                                           int ldw, int nout, Epi epi) {
   const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
@@ -150,8 +150,11 @@ __device__ __forceinline__ void store_row4(float* base, int64_t row, int n, int 
   }
 }
 
-template <bool TRAIN>
+template <bool TRAIN, int RT>
 __global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, const MlpStepArgs s) {
+  constexpr int TM = (FT / 32) * RT;       // rows per tile (64 or 16)
+  constexpr int TPR = FT / TM;             // threads per row in the head stages (8 or 32)
+  constexpr int NJ = (HW + TPR - 1) / TPR; // head columns per thread
   extern __shared__ __align__(16) float smem[];
   float* buf0 = smem;
   float* buf1 = buf0 + MLP_TM * LD;
@@ -172,13 +175,13 @@ __global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, cons
   }
   if (tid < 48) hb[tid] = tid < n_out ? __ldg(s.w + head_b_index(net, tid)) : 0.f;
 
-  const int ntiles = (B + MLP_TM - 1) / MLP_TM;
+  const int ntiles = (B + TM - 1) / TM;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int row0 = tile * MLP_TM;
+    const int row0 = tile * TM;
     __syncthreads();                       // the previous tile is fully consumed (and Wh / hb are staged)
     {
       const int Sp = round_up16(S);
-      for (int idx = tid; idx < MLP_TM * Sp; idx += FT) {
+      for (int idx = tid; idx < TM * Sp; idx += FT) {
         const int r = idx / Sp, c = idx - r * Sp;
         buf0[r * LD + c] = (row0 + r < B && c < S) ? s.x[(size_t)(row0 + r) * S + c] : 0.f;
       }
@@ -204,26 +207,27 @@ __global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, cons
         }
         if (TRAIN && row0 + r < B) store_row4(out_g, row0 + r, L.n, c0, v);
       };
-      if (L.n > 128) tile_pass<false, 2>(cur, nxt, Wc, L.k, s.w + L.w_off, L.n, L.n, epi);
-      else tile_pass<false, 1>(cur, nxt, Wc, L.k, s.w + L.w_off, L.n, L.n, epi);
+      if (L.n > 128) tile_pass<false, 2, RT>(cur, nxt, Wc, L.k, s.w + L.w_off, L.n, L.n, epi);
+      else tile_pass<false, 1, RT>(cur, nxt, Wc, L.k, s.w + L.w_off, L.n, L.n, epi);
       float* t = cur; cur = nxt; nxt = t;
     }
     __syncthreads();                       // h = cur[64][hid] is complete
 
-    // ---- head logits: thread (row, jq) sums columns jq, jq + 8, ... of h Wh ----
+    // ---- head logits: thread (row, jq) sums columns jq, jq + TPR, ... of h Wh ----
     {
-      const int row = tid >> 3, jq = tid & 7;
-      float z[HW / 8];
+      const int row = tid / TPR, jq = tid % TPR;
+      float z[NJ];
 #pragma unroll
-      for (int jj = 0; jj < HW / 8; ++jj) z[jj] = 0.f;
+      for (int jj = 0; jj < NJ; ++jj) z[jj] = 0.f;
       for (int k = 0; k < hid; ++k) {
         const float h = cur[row * LD + k];
 #pragma unroll
-        for (int jj = 0; jj < HW / 8; ++jj) z[jj] = fmaf(h, Wh[k * HLD + jq + 8 * jj], z[jj]);
+        for (int jj = 0; jj < NJ; ++jj)
+          if (jq + TPR * jj < HW) z[jj] = fmaf(h, Wh[k * HLD + jq + TPR * jj], z[jj]);
       }
 #pragma unroll
-      for (int jj = 0; jj < HW / 8; ++jj) {
-        const int j = jq + 8 * jj;
+      for (int jj = 0; jj < NJ; ++jj) {
+        const int j = jq + TPR * jj;
         if (j < n_out) lg[row * HLD + j] = z[jj] + hb[j];
       }
     }
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, cons
 
     // ---- per row: p, v, loss terms, dlogits ----
     float l1 = 0.f, l2 = 0.f, lv = 0.f;
-    if (tid < MLP_TM) {
+    if (tid < TM) {
       const int r = tid;
       const bool valid = row0 + r < B;
       float* z = lg + r * HLD;
@@ -337,20 +341,27 @@ __global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, cons
     if (!TRAIN) continue;
 
     // loss sums of the tile, fixed order: warp tree, then warp 0 + warp 1
-    if (tid < MLP_TM) {
+    constexpr int RW = (TM + 31) / 32;     // warps that hold rows (threads beyond TM contribute zeros)
+    if (tid < 32 * RW) {
       l1 = warp_sum(l1); l2 = warp_sum(l2); lv = warp_sum(lv);
       if ((tid & 31) == 0) { red[(tid >> 5) * 4 + 0] = l1; red[(tid >> 5) * 4 + 1] = l2; red[(tid >> 5) * 4 + 2] = lv; }
     }
     __syncthreads();                       // dlogits tile + loss partials visible
-    if (tid < 4) s.loss_part[(size_t)tile * 4 + tid] = tid < 3 ? red[tid] + red[4 + tid] : 0.f;
+    if (tid < 4) {
+      float t = 0.f;
+      if (tid < 3)
+#pragma unroll
+        for (int w = 0; w < RW; ++w) t += red[w * 4 + tid];
+      s.loss_part[(size_t)tile * 4 + tid] = t;
+    }
 
     // ---- gradient w.r.t. the last hidden pre-activation: dz = (dlogits Wh^T) * act'(h) ----
     {
       const MlpLayerDesc L = net.L[NL - 1];
-      const int row = tid >> 3, kq = tid & 7;
+      const int row = tid / TPR, kq = tid % TPR;
       const int hp = round_up16(hid);
       float* dz_g = s.dz[NL - 1];
-      for (int k = kq; k < hp; k += 8) {
+      for (int k = kq; k < hp; k += TPR) {
         float d = 0.f;
         if (k < hid) {
           for (int j = 0; j < n_out; ++j) d = fmaf(lg[row * HLD + j], Wh[k * HLD + j], d);
@@ -382,8 +393,8 @@ __global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, cons
         }
         if (valid) store_row4(dz_g, row0 + r, Lp.n, c0, v);
       };
-      if (Lp.n > 128) tile_pass<true, 2>(cur, nxt, Wc, L.n, s.w + L.w_off, L.n, Lp.n, epi);
-      else tile_pass<true, 1>(cur, nxt, Wc, L.n, s.w + L.w_off, L.n, Lp.n, epi);
+      if (Lp.n > 128) tile_pass<true, 2, RT>(cur, nxt, Wc, L.n, s.w + L.w_off, L.n, Lp.n, epi);
+      else tile_pass<true, 1, RT>(cur, nxt, Wc, L.n, s.w + L.w_off, L.n, Lp.n, epi);
       float* t = cur; cur = nxt; nxt = t;
     }
   }
@@ -520,20 +531,30 @@ int total_wgrad_tiles(const MlpNet& net) {
 GA3C_TRACE_ATTACH(trace_attach_mlp)
 
 int configure_mlp() {
-  int r = (int)cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM);
-  if (r) return r;
-  return (int)cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM);
+  int r;
+  if ((r = (int)cudaFuncSetAttribute(mlp_fused_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM))) return r;
+  if ((r = (int)cudaFuncSetAttribute(mlp_fused_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM))) return r;
+  if ((r = (int)cudaFuncSetAttribute(mlp_fused_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM))) return r;
+  return (int)cudaFuncSetAttribute(mlp_fused_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM);
 }
 
+// rows per tile: 64, or 16 when 64-row tiles would occupy less than half of the SMs
+int mlp_tile_rows(int batch, int num_sms) { return (batch + MLP_TM - 1) / MLP_TM * 2 < num_sms ? 16 : MLP_TM; }
+
 int mlp_fused_grid(int batch, int num_sms) {
-  const int tiles = (batch + MLP_TM - 1) / MLP_TM;
+  const int tm = mlp_tile_rows(batch, num_sms);
+  const int tiles = (batch + tm - 1) / tm;
   return tiles < num_sms ? tiles : num_sms;
 }
 
 int launch_mlp_fused(const MlpNet& net, const MlpStepArgs& args, int num_sms, cudaStream_t stream) {
   const dim3 grid(mlp_fused_grid(args.batch, num_sms));
-  if (args.train) return launch_pdl(mlp_fused_kernel<true>, grid, dim3(FT), FUSED_SMEM, stream, net, args);
-  return launch_pdl(mlp_fused_kernel<false>, grid, dim3(FT), FUSED_SMEM, stream, net, args);
+  if (mlp_tile_rows(args.batch, num_sms) == 16) {
+    if (args.train) return launch_pdl(mlp_fused_kernel<true, 1>, grid, dim3(FT), FUSED_SMEM, stream, net, args);
+    return launch_pdl(mlp_fused_kernel<false, 1>, grid, dim3(FT), FUSED_SMEM, stream, net, args);
+  }
+  if (args.train) return launch_pdl(mlp_fused_kernel<true, 4>, grid, dim3(FT), FUSED_SMEM, stream, net, args);
+  return launch_pdl(mlp_fused_kernel<false, 4>, grid, dim3(FT), FUSED_SMEM, stream, net, args);
 }
 
 int mlp_wgrad_splits(const MlpNet& net, int batch, int num_sms) {

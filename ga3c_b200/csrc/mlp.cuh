@@ -44,11 +44,12 @@ struct MlpStepArgs {
   float* act[MLP_MAX_LAYERS];           // train: layer outputs [B, n_l]
   float* dz[MLP_MAX_LAYERS];            // train: gradients w.r.t. the pre-activations [B, n_l]
   float* dlogits;                       // train: [B, n_out_ld]
-  float* loss_part;                     // train: [tiles][4] (cost_p_1, cost_p_2, cost_v, 0) per 64-row tile
+  float* loss_part;                     // train: [tiles][4] (cost_p_1, cost_p_2, cost_v, 0) per batch tile (mlp_tile_rows)
 };
 
 int configure_mlp();
 int mlp_fused_grid(int batch, int num_sms);
+int mlp_tile_rows(int batch, int num_sms);       // 64, or 16 for small batches; loss_part has one row per tile
 // forward (+ heads, loss, and the whole data-gradient chain when args.train) in one persistent kernel
 int launch_mlp_fused(const MlpNet& net, const MlpStepArgs& args, int num_sms, cudaStream_t stream);
 

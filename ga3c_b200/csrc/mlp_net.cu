@@ -87,7 +87,7 @@ static int alloc_workspace(ga3c_mlp* n, int max_batch) {
     CK(cudaMalloc((void**)&n->dz[l], mb * n->net.L[l].n * 4));
   }
   CK(cudaMalloc((void**)&n->dlogits, mb * n->net.n_out_ld * 4));
-  CK(cudaMalloc((void**)&n->loss_part, ((mb + MLP_TM - 1) / MLP_TM) * 4 * 4));
+  CK(cudaMalloc((void**)&n->loss_part, ((mb + 15) / 16) * 4 * 4));      // one row per batch tile, tiles of >= 16 rows
   n->cfg.max_batch = max_batch;
   return 0;
 }
@@ -300,8 +300,9 @@ extern "C" int ga3c_mlp_forward_backward(ga3c_mlp* n, const float* x, const floa
   LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(n->net, s, n->num_sms, st));
   const int splits = mlp_wgrad_splits(n->net, batch, n->num_sms);
   LAUNCH(n, K_MLP_WGRAD, st, launch_mlp_wgrad(n->net, s, n->part, n->live_floats, splits, st));
+  const int tm = mlp_tile_rows(batch, n->num_sms);
   LAUNCH(n, K_MLP_REDUCE, st, launch_mlp_reduce(n->part, n->live_floats, splits, n->g, (int)n->live_floats, n->loss_part,
-                                                (batch + MLP_TM - 1) / MLP_TM, loss, st));
+                                                (batch + tm - 1) / tm, loss, st));
   return 0;
 }
 
