@@ -105,6 +105,87 @@ int launch_rmsprop(const RmsPropArgs& a, cudaStream_t stream) {
   return launch_pdl(rmsprop_kernel<false>, dim3(grid), dim3(256), 0, stream, a);
 }
 
+// ---- Config.USE_GRAD_CLIP: tf.clip_by_average_norm per variable (NetworkVP_discrate.py:118-121) --------------
+//   g' = g * clip / max(||g||_2 / n, clip),  n = number of elements of the variable        [TF-SEMANTICS]
+// Three launches over the finished gradient arena: per-chunk sums of squares (one block per 4096 elements of one tensor,
+// fixed-order block reduction), one warp per tensor turning the chunk sums into a scale, RMSProp with the scale of the
+// tensor an element belongs to.  Fixed summation order: bit-reproducible.
+constexpr int CLIP_CHUNK = 4096;
+__global__ void __launch_bounds__(256) grad_sqnorm_kernel(ClipArgs c) {
+  __shared__ float wsum[8];
+  griddep_launch();
+  griddep_wait(K_RMSPROP);
+  const int t = blockIdx.y;
+  const int64_t lo = (int64_t)blockIdx.x * CLIP_CHUNK;
+  if (lo >= c.count[t]) return;
+  const int64_t hi = lo + CLIP_CHUNK < c.count[t] ? lo + CLIP_CHUNK : c.count[t];
+  const float* g = c.g + c.offset[t];
+  float s = 0.f;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) s = fmaf(g[i], g[i], s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += wsum[w];
+    c.chunk_ss[(int64_t)t * c.max_chunks + blockIdx.x] = tot;
+  }
+}
+
+__global__ void __launch_bounds__(32 * CLIP_MAX_TENSORS) clip_scale_kernel(ClipArgs c) {
+  griddep_launch();
+  griddep_wait(K_RMSPROP);
+  const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (t >= c.n_tensors) return;
+  const int nch = (int)((c.count[t] + CLIP_CHUNK - 1) / CLIP_CHUNK);
+  float s = 0.f;
+  for (int i = lane; i < nch; i += 32) s += c.chunk_ss[(int64_t)t * c.max_chunks + i];
+  s = warp_sum(s);
+  if (lane == 0) c.scale[t] = c.clip / fmaxf(sqrtf(s) / (float)c.count[t], c.clip);
+}
+
+template <bool HAS_MOM>
+__global__ void __launch_bounds__(256) rmsprop_clip_kernel(RmsPropArgs a, ClipArgs c) {
+  griddep_launch();
+  griddep_wait(K_RMSPROP);
+  const int64_t n4 = a.n_floats >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int64_t e = i << 2;
+    float sc = 0.f;                       // alignment gaps between tensors hold zeros
+#pragma unroll
+    for (int t = 0; t < CLIP_MAX_TENSORS; ++t)
+      if (t < c.n_tensors && e >= c.offset[t] && e < c.offset[t] + c.count[t]) sc = c.scale[t];
+    float4 g = reinterpret_cast<const float4*>(a.g)[i];
+    // a float4 never straddles two tensors' live elements with different scales unless a count is not a multiple of 4: then
+    // the tail elements belong to the gap (zeros), so one scale per float4 is exact
+    g.x *= sc; g.y *= sc; g.z *= sc; g.w *= sc;
+    float4 w = reinterpret_cast<float4*>(a.w)[i];
+    float4 ms = reinterpret_cast<float4*>(a.ms)[i];
+    float4 mo = HAS_MOM ? reinterpret_cast<float4*>(a.mom)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    rms_update<HAS_MOM>(a, g, w, ms, mo);
+    reinterpret_cast<float4*>(a.w)[i] = w;
+    reinterpret_cast<float4*>(a.ms)[i] = ms;
+    if (HAS_MOM) reinterpret_cast<float4*>(a.mom)[i] = mo;
+    if (a.w1_count > 0 && e >= a.w1_offset && e < a.w1_offset + a.w1_count)
+      reinterpret_cast<uint2*>(a.w1_shadow)[(e - a.w1_offset) >> 2] = make_uint2(pack_bf16(w.x, w.y), pack_bf16(w.z, w.w));
+  }
+  trace_mark(K_RMSPROP, 2);
+}
+
+int clip_chunks(int64_t max_count) { return (int)((max_count + CLIP_CHUNK - 1) / CLIP_CHUNK); }
+
+int launch_rmsprop_clipped(const RmsPropArgs& a, const ClipArgs& c, cudaStream_t stream) {
+  int r;
+  if ((r = launch_pdl(grad_sqnorm_kernel, dim3(c.max_chunks, c.n_tensors), dim3(256), 0, stream, c))) return r;
+  if ((r = launch_pdl(clip_scale_kernel, dim3(1), dim3(32 * CLIP_MAX_TENSORS), 0, stream, c))) return r;
+  const int64_t n4 = a.n_floats >> 2;
+  const int grid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+  if (a.momentum != 0.f) return launch_pdl(rmsprop_clip_kernel<true>, dim3(grid), dim3(256), 0, stream, a, c);
+  return launch_pdl(rmsprop_clip_kernel<false>, dim3(grid), dim3(256), 0, stream, a, c);
+}
+
 // ---- single-GPU step tail: grad_reduce + RMSProp in one launch -------------------------------------------
 // Blocks [0, n_red) sum the gradient-partial slabs of 32 float4 columns exactly like grad_reduce_kernel (same order,
 // same bits), store the reduced gradient and apply RMSProp to those columns; the remaining blocks update dense1/w,

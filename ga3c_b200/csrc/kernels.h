@@ -95,6 +95,19 @@ struct RmsPropArgs {
   float lr, decay, momentum, eps;
 };
 int launch_rmsprop(const RmsPropArgs& a, cudaStream_t stream);
+// Config.USE_GRAD_CLIP: tf.clip_by_average_norm per variable, then RMSProp (3 launches: chunk sums of squares, per-tensor
+// scale, update).  offset / count: the variables' element ranges in the arena; chunk_ss: [n_tensors][max_chunks] scratch,
+// max_chunks = clip_chunks(largest count); scale: [n_tensors] scratch.
+constexpr int CLIP_MAX_TENSORS = 24;
+struct ClipArgs {
+  const float* g;
+  int n_tensors, max_chunks;
+  int64_t offset[CLIP_MAX_TENSORS], count[CLIP_MAX_TENSORS];
+  float clip;
+  float *chunk_ss, *scale;
+};
+int clip_chunks(int64_t max_count);
+int launch_rmsprop_clipped(const RmsPropArgs& a, const ClipArgs& c, cudaStream_t stream);
 // grad_reduce + RMSProp in one launch (single-GPU step; r.out must be a.g, r.out_floats the small-tensor prefix)
 int launch_rmsprop_reduce(const RmsPropArgs& a, const GradReduceArgs& r, cudaStream_t stream);
 // data-parallel RMSProp over peer memory: rank r owns arena slice r; it sums that slice of every rank's gradient

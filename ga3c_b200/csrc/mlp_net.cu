@@ -51,6 +51,7 @@ struct ga3c_mlp {
   int64_t arena_floats = 0, live_floats = 0;   // live tensors are packed first; [live_floats, arena_floats) is never updated
   float *w = nullptr, *g = nullptr, *ms = nullptr, *mom = nullptr;
   float* part = nullptr;                 // [MLP_MAX_SPLITS][live_floats] weight-gradient partial arenas
+  float *clip_ss = nullptr, *clip_scale = nullptr;   // Config.USE_GRAD_CLIP scratch
   // workspace for max_batch rows
   float* act[MLP_MAX_LAYERS] = {};
   float* dz[MLP_MAX_LAYERS] = {};
@@ -95,6 +96,7 @@ static int alloc_workspace(ga3c_mlp* n, int max_batch) {
 extern "C" int ga3c_mlp_destroy(ga3c_mlp* n) {
   if (!n) return 0;
   cudaFree(n->w); cudaFree(n->g); cudaFree(n->ms); cudaFree(n->mom); cudaFree(n->part);
+  cudaFree(n->clip_ss); cudaFree(n->clip_scale);
   free_workspace(n);
   for (cudaEvent_t e : n->tev) cudaEventDestroy(e);
   delete n;
@@ -200,6 +202,20 @@ extern "C" int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out) {
   e = cudaMalloc((void**)&n->part, (size_t)MLP_MAX_SPLITS * n->live_floats * 4);
   if (e != cudaSuccess) { ga3c_mlp_destroy(n); return fail("cudaMalloc", e); }
   cudaMemset(n->part, 0, (size_t)MLP_MAX_SPLITS * n->live_floats * 4);
+  if (cfg->use_grad_clip) {
+    for (const MlpParam& p : n->params)
+      if (!p.live) {     // opt.compute_gradients yields (None, var) and tf.clip_by_average_norm(None, ..) raises
+        ga3c_mlp_destroy(n);
+        return set_error("ga3c_mlp_create: USE_GRAD_CLIP with gradient-less variables (NetworkVP_discrate.py:55 builds every "
+                         "DENSE_LAYERS entry from x): the reference graph cannot be built either");
+      }
+    if ((int)n->params.size() > CLIP_MAX_TENSORS) { ga3c_mlp_destroy(n); return set_error("ga3c_mlp_create: too many variables for USE_GRAD_CLIP"); }
+    int64_t mx = 0;
+    for (const MlpParam& p : n->params) mx = p.count > mx ? p.count : mx;
+    e = cudaMalloc((void**)&n->clip_ss, n->params.size() * clip_chunks(mx) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&n->clip_scale, n->params.size() * sizeof(float));
+    if (e != cudaSuccess) { ga3c_mlp_destroy(n); return fail("cudaMalloc", e); }
+  }
   if (int r = alloc_workspace(n, cfg->max_batch)) { ga3c_mlp_destroy(n); return r; }
   if (int r = configure_mlp()) { ga3c_mlp_destroy(n); return fail("cudaFuncSetAttribute", (cudaError_t)r); }
   e = cudaDeviceSynchronize();
@@ -314,6 +330,20 @@ extern "C" int ga3c_mlp_apply_rmsprop(ga3c_mlp* n, float lr, void* stream) {
   a.n_floats = n->live_floats;           // the gradient-less variables behind the live prefix are never touched
   a.w1_offset = n->live_floats; a.w1_count = 0;
   a.lr = lr; a.decay = n->cfg.rmsprop_decay; a.momentum = n->cfg.rmsprop_momentum; a.eps = n->cfg.rmsprop_epsilon;
+  if (n->cfg.use_grad_clip) {            // tf.clip_by_average_norm per variable (NetworkVP.py:138-141, NetworkVP_discrate.py:118-121)
+    ClipArgs c{};
+    c.g = n->g; c.n_tensors = (int)n->params.size();
+    int64_t mx = 0;
+    for (int i = 0; i < c.n_tensors; ++i) {
+      c.offset[i] = n->params[i].offset; c.count[i] = n->params[i].count;
+      mx = c.count[i] > mx ? c.count[i] : mx;
+    }
+    c.max_chunks = clip_chunks(mx); c.clip = n->cfg.grad_clip_norm; c.chunk_ss = n->clip_ss; c.scale = n->clip_scale;
+    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_clipped(a, c, (cudaStream_t)stream));
+    n->launches += 2;
+    if (n->cfg.kind == GA3C_MLP_FORK_VP) n->global_step += 1;     // the fork's NetworkVP passes global_step, _discrate does not
+    return 0;
+  }
   LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop(a, (cudaStream_t)stream));
   n->global_step += 1;                   // opt.minimize(..., global_step=self.global_step)
   return 0;

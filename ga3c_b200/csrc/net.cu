@@ -78,6 +78,7 @@ struct ga3c_net {
   int64_t gp_stride = 0;
   int gp_heads_grid = 0;           // slabs the heads kernel of the current step wrote
   float* loss_out = nullptr;       // caller's loss buffer of the current step (may be null)
+  float *clip_ss = nullptr, *clip_scale = nullptr;   // Config.USE_GRAD_CLIP scratch: chunk sums of squares, per-tensor scale
   bool keep_dn1 = false;           // tests: also store dn1 (which otherwise never leaves the SM) to the workspace
   int64_t global_step = 0;
   int64_t launches = 0;
@@ -121,7 +122,7 @@ int set_error(const std::string& m) { g_err = m; return -1; }     // for the oth
 const char* kernel_name(int kid) { return (kid >= 0 && kid < K_COUNT) ? kKernelNames[kid] : nullptr; }
 }
 extern "C" const char* ga3c_last_error(void) { return g_err.c_str(); }
-extern "C" int ga3c_abi_version(void) { return 2; }
+extern "C" int ga3c_abi_version(void) { return 3; }
 
 extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
   if (!cfg || !out) return fail_msg("ga3c_create: null argument");
@@ -187,6 +188,11 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
   e = cudaMalloc((void**)&n->gpart, (size_t)2 * n->num_sms * n->gp_stride * sizeof(float));
   if (e != cudaSuccess) { ga3c_destroy(n); return fail("cudaMalloc", e); }
   cudaMemset(n->gpart, 0, (size_t)2 * n->num_sms * n->gp_stride * sizeof(float));
+  if (cfg->use_grad_clip) {
+    e = cudaMalloc((void**)&n->clip_ss, (size_t)P_COUNT * clip_chunks((int64_t)FLAT * FC) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&n->clip_scale, P_COUNT * sizeof(float));
+    if (e != cudaSuccess) { ga3c_destroy(n); return fail("cudaMalloc", e); }
+  }
   if (int r = alloc_workspace(n, cfg->max_batch)) { ga3c_destroy(n); return r; }
   cudaMemset(n->w, 0, ab); cudaMemset(n->g, 0, ab); cudaMemset(n->mom, 0, ab);
   cudaMemset(n->w1_shadow, 0, (size_t)FLAT * FC * 2);
@@ -238,6 +244,7 @@ extern "C" int ga3c_destroy(ga3c_net* n) {
   ga3c_dp_detach(n);
   cudaFree(n->slab);
   cudaFree(n->gpart);
+  cudaFree(n->clip_ss); cudaFree(n->clip_scale);
   if (n->trace) { trace_attach_all(nullptr); cudaFree(n->trace); }
   free_workspace(n);
   for (cudaEvent_t e : n->tev) cudaEventDestroy(e);
@@ -454,10 +461,26 @@ static RmsPropArgs rmsprop_args(ga3c_net* n, float lr) {
   return a;
 }
 
+static ClipArgs clip_args(ga3c_net* n) {
+  ClipArgs c{};
+  c.g = n->g; c.n_tensors = P_COUNT; c.max_chunks = clip_chunks((int64_t)FLAT * FC);
+  for (int i = 0; i < P_COUNT; ++i) { c.offset[i] = n->params[i].offset; c.count[i] = n->params[i].count; }
+  c.clip = n->cfg.grad_clip_norm; c.chunk_ss = n->clip_ss; c.scale = n->clip_scale;
+  return c;
+}
+
 static int apply_rmsprop_impl(ga3c_net* n, float lr, void* stream, const GradReduceArgs* red) {
   if (!n) return fail_msg("ga3c_apply_rmsprop: null handle");
   CK(cudaSetDevice(n->cfg.device));
   RmsPropArgs a = rmsprop_args(n, lr);
+  if (n->cfg.use_grad_clip) {
+    // clip_by_average_norm needs the whole (reduced) gradient of a variable: local arena only (single GPU, or after the
+    // host's NCCL allreduce in dp_mode 'nccl')
+    if (n->dp_world > 1) return fail_msg("ga3c_apply_rmsprop: USE_GRAD_CLIP is not available with the peer-memory exchange");
+    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_clipped(a, clip_args(n), (cudaStream_t)stream));
+    n->launches += 2;
+    return 0;          // NetworkVP_discrate.py:121: apply_gradients without global_step -- the step counter stays put
+  }
   if (n->dp_world > 1) {
     // fused reduce-scatter(grads) -> RMSProp on this rank's slice -> all-gather(weights) over peer memory
     RmsPropDpArgs d{};
@@ -571,6 +594,10 @@ extern "C" int ga3c_dp_error(ga3c_net* n, int32_t* error_out) {
 static int train_step_impl(ga3c_net* n, const void* x, bool x_u8, const float* yr, const float* a, int32_t batch, float lr,
                            float beta, float* loss, void* stream) {
   if (int r = fb_head_impl(n, x, x_u8, yr, a, batch, beta, loss, stream, false)) return r;
+  if (n->cfg.use_grad_clip) {
+    if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, true)) return r;
+    return apply_rmsprop_impl(n, lr, stream, nullptr);
+  }
   if (n->dp_world > 1 && n->dp_exch > 0) {
     // overlapped exchange (dp_exchange.cuh): dense1/w moves between the ranks on exchange CTAs of the conv backward
     // launch; the small tensors follow in dp_small, which also holds the step open until every slice has landed

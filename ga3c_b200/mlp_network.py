@@ -34,7 +34,7 @@ class _MlpNetwork:
         self.model_name = model_name
         self.num_actions = int(num_actions)
         self.state_dim = int(np.prod(state_dim)) if not isinstance(state_dim, int) else state_dim
-        for knob in ("DUAL_RMSPROP", "USE_GRAD_CLIP"):
+        for knob in ("DUAL_RMSPROP",):
             if getattr(cfg, knob, False):
                 raise NotImplementedError(f"Config.{knob}=True is not built yet (SURVEY.md 8f F4)")
         self.learning_rate = cfg.LEARNING_RATE_START
@@ -55,7 +55,9 @@ class _MlpNetwork:
                                   rmsprop_decay=cfg.RMSPROP_DECAY, rmsprop_momentum=cfg.RMSPROP_MOMENTUM,
                                   rmsprop_epsilon=cfg.RMSPROP_EPSILON, log_epsilon=cfg.LOG_EPSILON,
                                   min_policy=cfg.MIN_POLICY,
-                                  use_log_softmax=int(bool(getattr(cfg, 'USE_LOG_SOFTMAX', False))))
+                                  use_log_softmax=int(bool(getattr(cfg, 'USE_LOG_SOFTMAX', False))),
+                              use_grad_clip=int(bool(getattr(cfg, 'USE_GRAD_CLIP', False))),
+                              grad_clip_norm=float(getattr(cfg, 'GRAD_CLIP_NORM', 40.0)))
         if self.KIND == _capi.MLP_DISCRATE and len(dense) > 8:
             raise ValueError("Config.DENSE_LAYERS: at most 8 entries")
         h = C.c_void_p()

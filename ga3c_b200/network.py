@@ -58,7 +58,7 @@ class Network:
         self.state_dim = int(np.prod(state_dim)) if not isinstance(state_dim, int) else state_dim
         if self.state_dim != STATE_DIM:
             raise ValueError(f"conv NetworkVP expects state_dim = 84*84*4 = {STATE_DIM}, got {self.state_dim}")
-        for knob in ("DUAL_RMSPROP", "USE_GRAD_CLIP"):
+        for knob in ("DUAL_RMSPROP",):
             if getattr(cfg, knob, False):
                 raise NotImplementedError(f"Config.{knob}=True is not built yet (SURVEY.md 8f F4)")
 
@@ -77,7 +77,9 @@ class Network:
         c = _capi.ga3c_config(device=self._ordinal, num_actions=self.num_actions, max_batch=self._max_batch,
                               rmsprop_decay=cfg.RMSPROP_DECAY, rmsprop_momentum=cfg.RMSPROP_MOMENTUM,
                               rmsprop_epsilon=cfg.RMSPROP_EPSILON, log_epsilon=cfg.LOG_EPSILON,
-                              min_policy=cfg.MIN_POLICY, use_log_softmax=int(bool(getattr(cfg, 'USE_LOG_SOFTMAX', False))))
+                              min_policy=cfg.MIN_POLICY, use_log_softmax=int(bool(getattr(cfg, 'USE_LOG_SOFTMAX', False))),
+                              use_grad_clip=int(bool(getattr(cfg, 'USE_GRAD_CLIP', False))),
+                              grad_clip_norm=float(getattr(cfg, 'GRAD_CLIP_NORM', 40.0)))
         h = C.c_void_p()
         _capi.check(self._lib.ga3c_create(C.byref(c), C.byref(h)), "ga3c_create")
         self._h = h
@@ -123,6 +125,8 @@ class Network:
             self.dp_mode = dp_mode or os.environ.get("GA3C_DP", "fused")
             if self.dp_mode not in ("fused", "nccl"):
                 raise ValueError(f"dp_mode must be 'fused' or 'nccl', got {self.dp_mode!r}")
+        if self.dp_mode == "fused" and getattr(cfg, "USE_GRAD_CLIP", False):
+            self.dp_mode = "nccl"        # the per-variable norm needs the whole reduced gradient: allreduce first, clip locally
         if self.dp_mode == "fused":
             import torch.distributed as dist
             n = self._lib.ga3c_dp_handle_bytes()

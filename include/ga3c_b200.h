@@ -45,6 +45,11 @@ typedef struct ga3c_config {
   float   log_epsilon;       /* Config.LOG_EPSILON      (1e-6)                                */
   float   min_policy;        /* Config.MIN_POLICY       (0.0)                                 */
   int32_t use_log_softmax;   /* Config.USE_LOG_SOFTMAX  (False): NetworkVP_discrate.py:64-71  */
+  int32_t use_grad_clip;     /* Config.USE_GRAD_CLIP    (False): tf.clip_by_average_norm per variable before RMSProp
+                              * (NetworkVP_discrate.py:118-121).  As in that file, global_step is then NOT advanced
+                              * (its apply_gradients call has no global_step argument).  Not available with the
+                              * peer-memory exchange (ga3c_dp_attach): the norm needs the whole reduced gradient.   */
+  float   grad_clip_norm;    /* Config.GRAD_CLIP_NORM   (40.0)                                */
 } ga3c_config;
 
 const char* ga3c_last_error(void);
@@ -177,6 +182,10 @@ typedef struct ga3c_mlp_config {
   int32_t dense_width[8];    /* DISCRATE: Config.DENSE_LAYERS (each 1..256, the last <= 128)           */
   float   rmsprop_decay, rmsprop_momentum, rmsprop_epsilon, log_epsilon, min_policy;
   int32_t use_log_softmax;   /* DISCRATE only (the fork's NetworkVP has no softmax at all)                          */
+  int32_t use_grad_clip;     /* Config.USE_GRAD_CLIP: FORK_VP advances global_step (NetworkVP.py:141), DISCRATE does
+                              * not (NetworkVP_discrate.py:121); DISCRATE with gradient-less variables is refused, as
+                              * the reference graph cannot be built (clip_by_average_norm(None))                    */
+  float   grad_clip_norm;
 } ga3c_mlp_config;
 int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out);
 int ga3c_mlp_destroy(ga3c_mlp* net);

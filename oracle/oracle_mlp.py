@@ -169,11 +169,15 @@ def loss_and_grads(params, x, y_r, a, kind: str, *, beta=0.01, log_eps=1e-6, min
 
 
 def train_step(params, ms, mom, x, y_r, a, kind: str, *, lr, beta=0.01, log_eps=1e-6, min_policy=0.0,
-               rho=0.99, mu=0.0, eps=0.1, dtype=np.float32):
+               rho=0.99, mu=0.0, eps=0.1, dtype=np.float32, grad_clip=None):
     """One opt.minimize step; dead variables and their slots are left untouched.  -> (losses, grads, params', ms', mom')"""
     from . import oracle_np as onp
     losses, grads = loss_and_grads(params, x, y_r, a, kind, beta=beta, log_eps=log_eps, min_policy=min_policy, dtype=np.float64)
     live = {k: params[k] for k in grads}
+    if grad_clip is not None:              # tf.clip_by_average_norm per variable (NetworkVP.py:138-141)
+        if len(grads) != len(params):
+            raise ValueError("USE_GRAD_CLIP with gradient-less variables: tf.clip_by_average_norm(None, ..) raises in the reference")
+        grads = {k: onp.clip_by_average_norm(g, grad_clip) for k, g in grads.items()}
     p2, ms2, mom2 = onp.rmsprop_update(live, grads, {k: ms[k] for k in grads}, {k: mom[k] for k in grads},
                                        lr=lr, rho=rho, mu=mu, eps=eps, dtype=dtype)
     out_p, out_ms, out_mom = dict(params), dict(ms), dict(mom)

@@ -263,11 +263,20 @@ def rmsprop_update(params, grads, ms, mom, *, lr, rho=0.99, mu=0.0, eps=0.1, dty
     return new_p, new_ms, new_mom
 
 
-def train_step(params, ms, mom, x, y_r, a, *, lr, beta=0.01, log_eps=1e-6, min_policy=0.0, use_log_softmax=False,
+def clip_by_average_norm(g, clip_norm):
+    """tf.clip_by_average_norm (Config.USE_GRAD_CLIP, NetworkVP_discrate.py:118-121): t * clip / max(||t||_2 / n, clip), n = the
+    number of elements of t.  [TF-SEMANTICS]"""
+    g = np.asarray(g)
+    avg = np.sqrt((g.astype(np.float64) ** 2).sum()) / g.size
+    return g * g.dtype.type(clip_norm / max(avg, clip_norm))
+
+
+def train_step(params, ms, mom, x, y_r, a, *, lr, beta=0.01, log_eps=1e-6, min_policy=0.0, use_log_softmax=False, grad_clip=None,
                rho=0.99, mu=0.0, eps=0.1, dtype=np.float64, quant=None):
     losses, grads = loss_and_grads(params, x, y_r, a, beta=beta, log_eps=log_eps,
                                    min_policy=min_policy, dtype=dtype, quant=quant, use_log_softmax=use_log_softmax)
-    p2, ms2, mom2 = rmsprop_update(params, grads, ms, mom, lr=lr, rho=rho, mu=mu, eps=eps, dtype=dtype)
+    applied = grads if grad_clip is None else {k: clip_by_average_norm(g, grad_clip) for k, g in grads.items()}
+    p2, ms2, mom2 = rmsprop_update(params, applied, ms, mom, lr=lr, rho=rho, mu=mu, eps=eps, dtype=dtype)
     return losses, grads, p2, ms2, mom2
 
 

@@ -132,6 +132,48 @@ def test_log_softmax_knob(mlp):
         assert err(grads[k], g_ref)[1] <= TOL_GRAD_REL, (k, err(grads[k], g_ref))
 
 
+def test_grad_clip_knob(mlp):
+    """Config.USE_GRAD_CLIP: the fork's NetworkVP clips per variable and advances global_step (NetworkVP.py:138-141);
+    NetworkVP_discrate with its default gradient-less layers cannot build that graph (clip_by_average_norm(None)) and is
+    refused; with a single dense layer it clips and leaves global_step alone (NetworkVP_discrate.py:118-121)."""
+    clip = 1e-3
+    class Cfg(mlp._DefaultConfig):
+        USE_GRAD_CLIP = True
+        GRAD_CLIP_NORM = clip
+    class Cfg1(Cfg):
+        DENSE_LAYERS = (10,)
+    with pytest.raises(Exception):
+        make_net(mlp, "discrate", 4, 2, config=Cfg)
+    for kind, s, a, cfg, steps_counted in (("fork_vp", 3, 1, Cfg, True), ("discrate", 4, 2, Cfg1, False)):
+        b = 300
+        rng = np.random.default_rng(3)
+        net = make_net(mlp, kind, s, a, config=cfg)
+        params = net.get_variables()
+        x = rng.uniform(-1, 1, size=(b, s)).astype(np.float32)
+        y_r = rng.uniform(-1, 1, size=b).astype(np.float32)
+        act = (rng.uniform(-1, 1, size=(b, a)).astype(np.float32) if kind == "fork_vp"
+               else np.eye(a, dtype=np.float32)[rng.integers(0, a, size=b)])
+        ref_p = {k: v.copy() for k, v in params.items()}
+        ref_ms = {k: np.ones_like(v) for k, v in params.items()}
+        ref_mom = {k: np.zeros_like(v) for k, v in params.items()}
+        for _ in range(2):
+            net.train(x, y_r, act, None, None, 0)
+            if kind == "fork_vp":
+                _, grads, ref_p, ref_ms, ref_mom = om.train_step(ref_p, ref_ms, ref_mom, x, y_r, act, kind, lr=3e-4, grad_clip=clip)
+            else:          # oracle_mlp's 'discrate' is the default 4-layer graph; restate the single live layer by renaming
+                q = {k.replace("dense1_1_p", "dense1_4_p"): v for k, v in ref_p.items()}
+                qms = {k.replace("dense1_1_p", "dense1_4_p"): v for k, v in ref_ms.items()}
+                qmom = {k.replace("dense1_1_p", "dense1_4_p"): v for k, v in ref_mom.items()}
+                _, grads, q, qms, qmom = om.train_step(q, qms, qmom, x, y_r, act, kind, lr=3e-4, grad_clip=clip)
+                ref_p, ref_ms, ref_mom = ({k.replace("dense1_4_p", "dense1_1_p"): v for k, v in d.items()} for d in (q, qms, qmom))
+        avg = [np.sqrt((g.astype(np.float64) ** 2).sum()) / g.size for g in grads.values()]
+        assert max(avg) > clip > min(avg), avg
+        w = net.get_variables()
+        for k in w:
+            assert err(w[k], ref_p[k])[0] <= TOL_W_ABS, (kind, k, err(w[k], ref_p[k]))
+        assert net.get_global_step() == (2 if steps_counted else 0)
+
+
 @pytest.mark.parametrize("kind,s,a", CASES)
 def test_train_steps_match_oracle(mlp, kind, s, a):
     """Three opt.minimize steps: weights, ms slot, global_step; gradient-less variables untouched (bit-identical)."""

@@ -148,6 +148,32 @@ def test_data_parallel_exchange_two_ranks_on_one_gpu(ga3c, monkeypatch):
             lib.ga3c_dp_detach(n._h)
 
 
+def test_grad_clip_knob(ga3c):
+    """Config.USE_GRAD_CLIP = True (NetworkVP_discrate.py:118-121): tf.clip_by_average_norm per variable before RMSProp, with a
+    threshold small enough to be active on some variables and not on others; as in the reference file the step counter is
+    not advanced (apply_gradients is called without global_step)."""
+    clip = 2e-5
+    class Cfg(ga3c.Config):
+        USE_GRAD_CLIP = True
+        GRAD_CLIP_NORM = clip
+    params, x, y_r, a = make_case(48, seed=19)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=64, config=Cfg)
+    net.set_variables(params)
+    ms, mom = onp.rmsprop_init(params)
+    ref = params
+    for step in range(2):
+        net.train(x, y_r, a, None, None, 0)
+        _, grads, ref, ms, mom = onp.train_step(ref, ms, mom, x, y_r, a, lr=net.learning_rate, beta=net.beta, quant="bf16",
+                                                grad_clip=clip)
+        ref = {k: v.astype(np.float32) for k, v in ref.items()}
+    avg = {k: np.sqrt((g.astype(np.float64) ** 2).sum()) / g.size for k, g in grads.items()}
+    assert any(v > clip for v in avg.values()) and any(v < clip for v in avg.values()), avg
+    got = net.get_variables()
+    for k in got:
+        assert np.abs(got[k] - ref[k]).max() <= TOL_W_ABS, (k, np.abs(got[k] - ref[k]).max())
+    assert net.get_global_step() == 0
+
+
 def test_golden_network_b4(ga3c, golden_dir):
     """The committed B=4 fixture (tests/golden/network_b4.npz, oracle/gen_golden.py)."""
     g = np.load(os.path.join(golden_dir, "network_b4.npz"))

@@ -178,6 +178,18 @@ def test_log_softmax_branch_finite_differences_and_torch(small):
     assert np.abs(z.grad.numpy() - f["dz"]).max() <= 1e-12 and np.abs(v.grad.numpy() - f["dv"]).max() <= 1e-12
 
 
+def test_clip_by_average_norm_known_answers():
+    """tf.clip_by_average_norm: t * clip / max(||t|| / n, clip)  [TF-SEMANTICS]."""
+    g = np.array([[3.0, 4.0]], dtype=np.float32)                       # ||g|| = 5, n = 2 -> average norm 2.5
+    assert np.allclose(onp.clip_by_average_norm(g, 1.0), g / 2.5)
+    assert np.array_equal(onp.clip_by_average_norm(g, 2.5), g)         # at the threshold: unchanged
+    assert np.array_equal(onp.clip_by_average_norm(g, 40.0), g)        # Config.GRAD_CLIP_NORM = 40: never active in practice
+    assert onp.clip_by_average_norm(g, 1.0).dtype == np.float32
+    t = torch.tensor(g)
+    ref = t * 1.0 / torch.maximum(torch.linalg.vector_norm(t) / t.numel(), torch.tensor(1.0))
+    assert np.allclose(onp.clip_by_average_norm(g, 1.0), ref.numpy())
+
+
 def test_rmsprop_tf_semantics():
     """eps inside the sqrt, ms initialised to 1.0."""
     w = {"w": np.array([1.0, -2.0], dtype=np.float32)}
