@@ -487,7 +487,12 @@ def run_ours(args, rank, local_rank, world):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu capture
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(top)
-    roof = dict(rf_train[top], kernel=top, traffic=traffic, peak_source=pk["source"],
+    in_step = None
+    if tr_train.get(top):
+        bound_t, work_t = kernel_work(top, B, True)
+        peak_t = pk["hbm"] if bound_t == "hbm" else pk["tensor_sustained"]
+        in_step = round(work_t / (tr_train[top] * 1e-6) / (1e9 if bound_t == "hbm" else 1e12) / peak_t, 4)
+    roof = dict(rf_train[top], kernel=top, traffic=traffic, peak_source=pk["source"], frac_in_step=in_step,
                 note="achieved = algorithmic bytes (or flops) per launch / CUDA-event duration of that kernel, "
                      "measured in this run on the launch stream",
                 kernels_train=rf_train, kernels_predict=rf_pred,
@@ -505,6 +510,7 @@ def run_ours(args, rank, local_rank, world):
            "roofline": roof,
            "e2e": {"value": world * B * k_e2e / s_train_e2e, "unit": "frames/s",
                    "h2d_bytes_per_step": B * (STATE_DIM + 1 + NUM_ACTIONS) * 4, "d2h_bytes_per_step": 16,
+                   "h2d_gbs_per_gpu": round(B * (STATE_DIM + 1 + NUM_ACTIONS) * 4 * k_e2e / s_train_e2e / 1e9, 2),
                    "steps": k_e2e, "api": "Network.train(x, y_r, a, x2, done, trainer_id) on pinned host numpy"},
            "pps": {"value": pps, "unit": "predictions/s", "batch": PB, "ms_per_step": ms_pred / K,
                    "e2e": {"value": world * PB * k_e2e / s_pred_e2e, "unit": "predictions/s",

@@ -86,7 +86,7 @@ constexpr int FB_SMEM = FB_OFF_TSLOT + 16 + 128;                 // incl. slack 
 static_assert(FB_SMEM <= 232448, "shared memory budget of one CTA per SM");
 constexpr int FB_TMEM_COLS = 512, TM_W11 = 0, TM_W12 = 64, TM_D12 = 192;   // 2x32 | 4x32 | 2x64 columns
 
-template <bool U8>       // U8: frames are uint8 [B,28224] (x = k/128 - 1 applied on the fly), else fp32
+template <bool U8, bool DP>   // U8: frames are uint8 [B,28224] (x = k/128 - 1 applied on the fly), else fp32; DP: the grid carries exchange CTAs
 __global__ void __launch_bounds__(FB_THREADS, 1)
 conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, const uint16_t* __restrict__ dn2,
                 const float* __restrict__ w12, uint16_t* __restrict__ dn1_out, float* __restrict__ g_w11,
@@ -94,7 +94,7 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
                 int n_conv, const DpBigArgs dp) {
   // data parallel: CTAs [n_conv, gridDim.x) are exchange CTAs -- they move dense1/w (final since dense_bwd, the launch
   // this one depends on) between the ranks while CTAs [0, n_conv) compute the conv gradients (dp_exchange.cuh)
-  if ((int)blockIdx.x >= n_conv) {
+  if (DP && (int)blockIdx.x >= n_conv) {
     griddep_launch();
     griddep_wait(K_DP_BIG);
     dp_big_exchange(dp, (int)blockIdx.x - n_conv, (int)gridDim.x - n_conv);
@@ -110,7 +110,7 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
   float* red = reinterpret_cast<float*>(smem + FB_OFF_RED);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   EvtLog evt_i = evt_open();                                      // pipeline event log of CTA 0 (ga3c_evt_*), off unless attached
-  const int stride = n_conv;
+  const int stride = DP ? (int)gridDim.x - dp.n_exch : (int)gridDim.x;
   const int n_frames = ((int)blockIdx.x < batch) ? (batch - 1 - (int)blockIdx.x) / stride + 1 : 0;
   const int n_chunks = n_frames * PW_NCHUNK;                       // chunk stream of this CTA: q = k * 21 + c, warp q % 6
   auto frame_of = [&](int k) { return (size_t)(blockIdx.x + k * stride); };
@@ -458,9 +458,13 @@ GA3C_EVT_ATTACH(evt_attach_conv_bwd)
 int conv_bwd_grid(int batch, int num_sms, int n_exch) { return min(batch, num_sms - n_exch); }
 
 int configure_conv_bwd_fused() {
-  cudaError_t e = cudaFuncSetAttribute(conv_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(conv_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
   if (e != cudaSuccess) return (int)e;
-  return (int)cudaFuncSetAttribute(conv_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+  e = cudaFuncSetAttribute(conv_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(conv_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaFuncSetAttribute(conv_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
 }
 
 int launch_conv_bwd(const void* x, bool x_u8, const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1_out,
@@ -470,11 +474,10 @@ int launch_conv_bwd(const void* x, bool x_u8, const uint16_t* n1, const uint16_t
   if (dp != nullptr) d = *dp;
   const int n_conv = conv_bwd_grid(batch, num_sms, d.n_exch);
   const dim3 grid(n_conv + d.n_exch);
-  if (x_u8)
-    return launch_pdl(conv_bwd_kernel<true>, grid, dim3(FB_THREADS), FB_SMEM, stream, x, n1, dn2,
-                      w12, dn1_out, g_w11, g_b11, g_w12, g_b12, gp_stride, batch, n_conv, d);
-  return launch_pdl(conv_bwd_kernel<false>, grid, dim3(FB_THREADS), FB_SMEM, stream, x, n1, dn2,
-                    w12, dn1_out, g_w11, g_b11, g_w12, g_b12, gp_stride, batch, n_conv, d);
+  auto kernel = d.n_exch > 0 ? (x_u8 ? conv_bwd_kernel<true, true> : conv_bwd_kernel<false, true>)
+                             : (x_u8 ? conv_bwd_kernel<true, false> : conv_bwd_kernel<false, false>);
+  return launch_pdl(kernel, grid, dim3(FB_THREADS), FB_SMEM, stream, x, n1, dn2, w12, dn1_out, g_w11, g_b11, g_w12, g_b12,
+                    gp_stride, batch, n_conv, d);
 }
 
 }  // namespace ga3c
