@@ -12,6 +12,9 @@ Pinned against the REAL reference (imported, unmodified):
 Self-pins (oracle_np output frozen so later edits cannot drift silently; the reference cannot run
 its TensorFlow graph here, so these are NOT reference outputs -- parity unpinned):
   network_b4.npz    forward / losses / gradient digests / one RMSProp step at B=4, seed 12345
+  mlp_b6.npz        the config-4 MLPs (fork NetworkVP S=3 A=1, NetworkVP_discrate S=4 A=2) at B=6: inputs, p / v, the five
+                    loss scalars and every gradient, computed by a torch-autograd restatement of the reference graph lines
+                    (gen_mlp below, fp64) -- a second, independent statement for oracle_mlp.py and the CUDA path to meet
 """
 from __future__ import annotations
 
@@ -148,13 +151,63 @@ def gen_network():
     print("network_b4.npz")
 
 
+def gen_mlp():
+    """torch restatement of NetworkVP.py:79-105 (+ :175-210) and NetworkVP_discrate.py:52-85, autograd for the backward."""
+    import torch
+    from . import oracle_mlp as om
+    out = {}
+    for kind, s, a in (("fork_vp", 3, 1), ("discrate", 4, 2)):
+        rng = np.random.default_rng(2024)
+        params = om.init_params(rng, kind, s, a)
+        b = 6
+        x = rng.uniform(-1, 1, size=(b, s)).astype(np.float32)
+        y_r = rng.uniform(-1, 1, size=b).astype(np.float32)
+        act = (rng.uniform(-1, 1, size=(b, a)).astype(np.float32) if kind == "fork_vp"
+               else np.eye(a, dtype=np.float32)[rng.integers(0, a, size=b)])
+        tp = {k: torch.tensor(v.astype(np.float64), requires_grad=True) for k, v in params.items()}
+        tx, tyr, ta = (torch.tensor(np.asarray(t, dtype=np.float64)) for t in (x, y_r, act))
+        beta, eps = 0.01, 1e-6
+        def dense(h, name, func):
+            z = h @ tp[name + "/w:0"] + tp[name + "/b:0"]
+            return func(z) if func is not None else z
+        if kind == "fork_vp":
+            h = dense(tx, "dense11_p", None); h = dense(h, "dense12_p", None); h = dense(h, "dense13_p", None)
+            h = dense(h, "dense14_p", torch.sigmoid); h = dense(h, "dense1", torch.sigmoid)
+            v = dense(h, "logits_v", None)[:, 0]
+            ox = dense(h, "logits_p/out_x", torch.sigmoid) - 0.5
+            oy = dense(h, "logits_p/out_y", torch.sigmoid) - 0.5
+            p = torch.atan2(oy, ox) / np.pi
+            c1 = ((p * ta).sum(1) * (tyr - v.detach())).sum()
+            c2 = (-beta * (p * p).sum(1)).sum()
+        else:
+            h = dense(tx, "dense1_4_p", torch.sigmoid)          # every DENSE_LAYERS entry reads x; the last one is live
+            v = dense(h, "logits_v", None)[:, 0]
+            p = torch.softmax(dense(h, "logits_p", None), dim=1)
+            c1 = (torch.log(torch.clamp((p * ta).sum(1), min=eps)) * (tyr - v.detach())).sum()
+            c2 = (-beta * (torch.log(torch.clamp(p, min=eps)) * p).sum(1)).sum()
+        cv = 0.5 * ((tyr - v) ** 2).sum()
+        total = -(c1 + c2) + cv
+        total.backward()
+        out[f"{kind}_x"], out[f"{kind}_yr"], out[f"{kind}_a"] = x, y_r, act
+        out[f"{kind}_p"], out[f"{kind}_v"] = p.detach().numpy(), v.detach().numpy()
+        out[f"{kind}_losses"] = np.array([float(c1), float(c2), float(-(c1 + c2)), float(cv), float(total)])
+        for k, t in tp.items():                 # weights are om.init_params(default_rng(2024), kind, s, a): not stored
+            if t.grad is not None:
+                out[f"{kind}_grad_{k}"] = t.grad.numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(GOLD, "mlp_b6.npz"), **out)
+    print("mlp_b6.npz")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if "--mlp-only" in sys.argv:
+        return gen_mlp()
     ProcessAgent, Config, Experience = import_reference_agent()
     gen_returns(ProcessAgent, Config, Experience)
     gen_sampling(ProcessAgent, Config)
     gen_convert(ProcessAgent, Experience)
     gen_network()
+    gen_mlp()
 
 
 if __name__ == "__main__":

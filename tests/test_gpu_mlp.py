@@ -92,6 +92,29 @@ def test_losses_and_gradients_match_oracle(mlp, kind, s, a, batch):
         assert r <= TOL_GRAD_REL or d <= 1e-6, (k, d, r)
 
 
+@pytest.mark.parametrize("kind,s,a", [("fork_vp", 3, 1), ("discrate", 4, 2)])
+def test_golden_fixture(mlp, kind, s, a, golden_dir):
+    """The committed fixture tests/golden/mlp_b6.npz (torch-autograd restatement, oracle/gen_golden.py: gen_mlp)."""
+    import os
+    g = np.load(os.path.join(golden_dir, "mlp_b6.npz"))
+    params = om.init_params(np.random.default_rng(2024), kind, s, a)            # as oracle/gen_golden.py: gen_mlp drew them
+    grads_ref = {k[len(kind) + 6:]: g[k] for k in g.files if k.startswith(kind + "_grad_")}
+    x, y_r, act = g[kind + "_x"], g[kind + "_yr"], g[kind + "_a"]
+    net = make_net(mlp, kind, s, a)
+    net.set_variables(params)
+    net.beta = 0.01
+    p, v = net.predict_p_and_v(x)
+    assert err(p, g[kind + "_p"])[0] <= TOL_PV and err(v, g[kind + "_v"])[0] <= TOL_PV
+    l = net.losses(x, y_r, act)
+    got = np.array([l[k] for k in ("cost_p_1", "cost_p_2", "cost_p", "cost_v", "cost_all")])
+    assert np.abs(got - g[kind + "_losses"]).max() <= 2e-5 * x.shape[0]
+    grads = net.get_gradients()
+    assert set(grads) == set(grads_ref)
+    for k, g_ref in grads_ref.items():
+        d, r = err(grads[k], g_ref)
+        assert r <= TOL_GRAD_REL or d <= 1e-6, (k, d, r)
+
+
 def test_min_policy_mix(mlp):
     """MIN_POLICY > 0 (NetworkVP_discrate.py:69-71): p = (softmax + m) / (1 + m A)."""
     class Cfg(mlp._DefaultConfig):

@@ -115,3 +115,26 @@ def test_discrate_log_softmax_branch_matches_torch():
     assert abs(float(total) - losses["cost_all"]) <= 1e-10 * max(1.0, abs(losses["cost_all"]))
     for k, g in grads.items():
         assert np.abs(tp[k].grad.numpy() - g).max() <= 1e-11, k
+
+
+def _golden_case(g, kind):
+    s_, a_ = (3, 1) if kind == "fork_vp" else (4, 2)
+    params = om.init_params(np.random.default_rng(2024), kind, s_, a_)          # as oracle/gen_golden.py: gen_mlp drew them
+    grads = {k[len(kind) + 6:]: g[k] for k in g.files if k.startswith(kind + "_grad_")}
+    return params, g[kind + "_x"], g[kind + "_yr"], g[kind + "_a"], grads
+
+
+@pytest.mark.parametrize("kind", ["fork_vp", "discrate"])
+def test_oracle_matches_golden_fixture(kind, golden_dir):
+    """tests/golden/mlp_b6.npz: a torch-autograd restatement of the reference graph lines (oracle/gen_golden.py: gen_mlp)."""
+    import os
+    g = np.load(os.path.join(golden_dir, "mlp_b6.npz"))
+    params, x, y_r, act, grads_ref = _golden_case(g, kind)
+    p, v = om.forward(params, x, kind)
+    assert np.abs(p - g[kind + "_p"]).max() <= 1e-12 and np.abs(v - g[kind + "_v"]).max() <= 1e-12
+    losses, grads = om.loss_and_grads(params, x, y_r, act, kind, beta=0.01)
+    got = np.array([losses[k] for k in ("cost_p_1", "cost_p_2", "cost_p", "cost_v", "cost_all")])
+    assert np.allclose(got, g[kind + "_losses"], rtol=1e-11, atol=1e-13)
+    assert set(grads) == set(grads_ref)                      # gradient-less variables have no entry on either side
+    for k in grads:
+        assert np.abs(grads[k] - grads_ref[k]).max() <= 1e-6 * max(1.0, np.abs(grads_ref[k]).max()), k   # fixture is float32
