@@ -6,29 +6,14 @@
 #include "../../include/ga3c_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "host_util.h"
 #include "mlp.cuh"
 
-namespace ga3c {
-int set_error(const std::string& m);   // net.cu (thread-local message behind ga3c_last_error)
-}
 using namespace ga3c;
 
 namespace {
 
-int fail(const char* where, cudaError_t e) {
-  set_error(std::string(where) + ": " + cudaGetErrorString(e));
-  return (int)e ? (int)e : -1;
-}
-#define CK(call)                                            \
-  do {                                                      \
-    cudaError_t _e = (call);                                \
-    if (_e != cudaSuccess) return fail(#call, _e);          \
-  } while (0)
-#define CKL(call)                                           \
-  do {                                                      \
-    int _r = (call);                                        \
-    if (_r != 0) return fail(#call, (cudaError_t)_r);       \
-  } while (0)
+int fail(const char* where, cudaError_t e) { return fail_cuda(where, e); }
 
 struct MlpParam {
   std::string name;
@@ -57,23 +42,9 @@ struct ga3c_mlp {
   float* dz[MLP_MAX_LAYERS] = {};
   float* dlogits = nullptr;
   float* loss_part = nullptr;
-  int64_t global_step = 0, launches = 0;
-  std::vector<cudaEvent_t> tev;
-  std::vector<int> tkid;
-  int tcursor = 0;
+  int64_t global_step = 0;
+  LaunchLog log;                         // launch counter + per-kernel CUDA-event timing (ga3c_mlp_timing_*)
 };
-
-#define LAUNCH(net, kid, st, call)                                                        \
-  do {                                                                                    \
-    const bool _t = !(net)->tev.empty() && (size_t)(2 * (net)->tcursor + 1) < (net)->tev.size(); \
-    if (_t) CK(cudaEventRecord((net)->tev[2 * (net)->tcursor], (st)));                    \
-    CKL(call);                                                                            \
-    if (_t) {                                                                             \
-      CK(cudaEventRecord((net)->tev[2 * (net)->tcursor + 1], (st)));                      \
-      (net)->tkid[(net)->tcursor++] = (kid);                                              \
-    }                                                                                     \
-    (net)->launches++;                                                                    \
-  } while (0)
 
 static void free_workspace(ga3c_mlp* n) {
   for (int l = 0; l < MLP_MAX_LAYERS; ++l) { cudaFree(n->act[l]); cudaFree(n->dz[l]); n->act[l] = n->dz[l] = nullptr; }
@@ -98,7 +69,7 @@ extern "C" int ga3c_mlp_destroy(ga3c_mlp* n) {
   cudaFree(n->w); cudaFree(n->g); cudaFree(n->ms); cudaFree(n->mom); cudaFree(n->part);
   cudaFree(n->clip_ss); cudaFree(n->clip_scale);
   free_workspace(n);
-  for (cudaEvent_t e : n->tev) cudaEventDestroy(e);
+  n->log.clear();
   delete n;
   return 0;
 }
@@ -277,7 +248,7 @@ extern "C" int ga3c_mlp_arena_download(ga3c_mlp* n, int which, float* host, int6
 
 extern "C" int64_t ga3c_mlp_global_step(const ga3c_mlp* n) { return n ? n->global_step : -1; }
 extern "C" int ga3c_mlp_set_global_step(ga3c_mlp* n, int64_t s) { if (!n) return -1; n->global_step = s; return 0; }
-extern "C" int64_t ga3c_mlp_launch_count(const ga3c_mlp* n) { return n ? n->launches : 0; }
+extern "C" int64_t ga3c_mlp_launch_count(const ga3c_mlp* n) { return n ? n->log.launches : 0; }
 
 static int check_batch(ga3c_mlp* n, int batch, const char* who) {
   if (!n) return set_error(std::string(who) + ": null handle");
@@ -340,7 +311,7 @@ extern "C" int ga3c_mlp_apply_rmsprop(ga3c_mlp* n, float lr, void* stream) {
     }
     c.max_chunks = clip_chunks(mx); c.clip = n->cfg.grad_clip_norm; c.chunk_ss = n->clip_ss; c.scale = n->clip_scale;
     LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_clipped(a, c, (cudaStream_t)stream));
-    n->launches += 2;
+    n->log.launches += 2;
     if (n->cfg.kind == GA3C_MLP_FORK_VP) n->global_step += 1;     // the fork's NetworkVP passes global_step, _discrate does not
     return 0;
   }
@@ -359,25 +330,12 @@ extern "C" int ga3c_mlp_timing_enable(ga3c_mlp* n, int32_t max_records) {
   if (!n || max_records < 0) return set_error("ga3c_mlp_timing_enable: bad argument");
   CK(cudaSetDevice(n->cfg.device));
   CK(cudaDeviceSynchronize());
-  for (cudaEvent_t e : n->tev) cudaEventDestroy(e);
-  n->tev.clear(); n->tkid.clear(); n->tcursor = 0;
-  n->tev.resize((size_t)2 * max_records);
-  n->tkid.assign((size_t)max_records, 0);
-  for (auto& e : n->tev) CK(cudaEventCreate(&e));
-  return 0;
+  return n->log.enable(max_records);
 }
 
 extern "C" int ga3c_mlp_timing_collect(ga3c_mlp* n, double* total_ms, int64_t* counts, int32_t n_kernels) {
   if (!n || !total_ms || !counts || n_kernels < K_COUNT) return set_error("ga3c_mlp_timing_collect: bad argument");
   CK(cudaSetDevice(n->cfg.device));
   CK(cudaDeviceSynchronize());
-  for (int k = 0; k < n_kernels; ++k) { total_ms[k] = 0.0; counts[k] = 0; }
-  for (int r = 0; r < n->tcursor; ++r) {
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, n->tev[2 * r], n->tev[2 * r + 1]));
-    total_ms[n->tkid[r]] += ms;
-    counts[n->tkid[r]] += 1;
-  }
-  n->tcursor = 0;
-  return 0;
+  return n->log.collect(total_ms, reinterpret_cast<long long*>(counts), n_kernels);
 }

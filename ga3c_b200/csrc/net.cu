@@ -9,6 +9,7 @@
 #include "../../include/ga3c_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "host_util.h"
 #include "mlp.cuh"
 #include "dp_exchange.cuh"
 
@@ -18,22 +19,8 @@ namespace {
 
 thread_local std::string g_err;
 
-int fail(const char* where, cudaError_t e) {
-  g_err = std::string(where) + ": " + cudaGetErrorString(e);
-  return (int)e ? (int)e : -1;
-}
+int fail(const char* where, cudaError_t e) { return fail_cuda(where, e); }
 int fail_msg(const std::string& m) { g_err = m; return -1; }
-
-#define CK(call)                                            \
-  do {                                                      \
-    cudaError_t _e = (call);                                \
-    if (_e != cudaSuccess) return fail(#call, _e);          \
-  } while (0)
-#define CKL(call)                                           \
-  do {                                                      \
-    int _r = (call);                                        \
-    if (_r != 0) return fail(#call, (cudaError_t)_r);       \
-  } while (0)
 
 struct ParamDesc {
   std::string name;
@@ -81,14 +68,10 @@ struct ga3c_net {
   float *clip_ss = nullptr, *clip_scale = nullptr;   // Config.USE_GRAD_CLIP scratch: chunk sums of squares, per-tensor scale
   bool keep_dn1 = false;           // tests: also store dn1 (which otherwise never leaves the SM) to the workspace
   int64_t global_step = 0;
-  int64_t launches = 0;
+  LaunchLog log;                   // launch counter + per-kernel CUDA-event timing (ga3c_timing_*)
   int last_batch = 0;
-  // per-kernel CUDA-event timing (ga3c_timing_*): record r uses events 2r (before) and 2r+1 (after)
   unsigned long long* evt = nullptr;       // pipeline event log of CTA 0 (ga3c_evt_*), device memory
   unsigned long long* trace = nullptr;     // [K_COUNT][TRACE_SLOTS] globaltimer stamps (ga3c_trace_*), device memory
-  std::vector<cudaEvent_t> tev;
-  std::vector<int> tkid;
-  int tcursor = 0;
 
   int64_t off(int i) const { return params[i].offset; }
 };
@@ -97,19 +80,6 @@ struct ga3c_net {
 static const char* const kKernelNames[K_COUNT] = {"conv_fwd", "dense_fwd", "heads", "dense_wgrad", "dense_bwd",
                                                   "conv_bwd", "conv11_wgrad", "rmsprop", "grad_reduce",
                                                   "mlp_fused", "mlp_wgrad", "mlp_reduce", "dp_big"};
-
-// launch one kernel of the path; when timing is enabled bracket it with events on the same stream
-#define LAUNCH(net, kid, st, call)                                                        \
-  do {                                                                                    \
-    const bool _t = !(net)->tev.empty() && (size_t)(2 * (net)->tcursor + 1) < (net)->tev.size(); \
-    if (_t) CK(cudaEventRecord((net)->tev[2 * (net)->tcursor], (st)));                    \
-    CKL(call);                                                                            \
-    if (_t) {                                                                             \
-      CK(cudaEventRecord((net)->tev[2 * (net)->tcursor + 1], (st)));                      \
-      (net)->tkid[(net)->tcursor++] = (kid);                                              \
-    }                                                                                     \
-    (net)->launches++;                                                                    \
-  } while (0)
 
 enum { P_C11W = 0, P_C11B, P_C12W, P_C12B, P_D1W, P_D1B, P_VW, P_VB, P_PW, P_PB, P_COUNT };
 
@@ -247,7 +217,7 @@ extern "C" int ga3c_destroy(ga3c_net* n) {
   cudaFree(n->clip_ss); cudaFree(n->clip_scale);
   if (n->trace) { trace_attach_all(nullptr); cudaFree(n->trace); }
   free_workspace(n);
-  for (cudaEvent_t e : n->tev) cudaEventDestroy(e);
+  n->log.clear();
   delete n;
   return 0;
 }
@@ -289,7 +259,7 @@ extern "C" int ga3c_arena_upload(ga3c_net* n, int which, const float* host, int6
   CK(cudaMemcpy(dst, host, (size_t)nf * 4, cudaMemcpyHostToDevice));
   if (which == 0) {
     CKL(launch_f32_to_bf16(n->w + n->off(P_D1W), n->w1_shadow, (int64_t)FLAT * FC, 0));
-    n->launches++;
+    n->log.launches++;
     CK(cudaDeviceSynchronize());
   }
   return 0;
@@ -478,7 +448,7 @@ static int apply_rmsprop_impl(ga3c_net* n, float lr, void* stream, const GradRed
     // host's NCCL allreduce in dp_mode 'nccl')
     if (n->dp_world > 1) return fail_msg("ga3c_apply_rmsprop: USE_GRAD_CLIP is not available with the peer-memory exchange");
     LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_clipped(a, clip_args(n), (cudaStream_t)stream));
-    n->launches += 2;
+    n->log.launches += 2;
     return 0;          // NetworkVP_discrate.py:121: apply_gradients without global_step -- the step counter stays put
   }
   if (n->dp_world > 1) {
@@ -679,15 +649,10 @@ extern "C" int ga3c_keep_dn1(ga3c_net* n, int32_t on) {
   return 0;
 }
 
-extern "C" int64_t ga3c_launch_count(const ga3c_net* n) { return n ? n->launches : 0; }
+extern "C" int64_t ga3c_launch_count(const ga3c_net* n) { return n ? n->log.launches : 0; }
 
 extern "C" int ga3c_kernel_count(void) { return K_COUNT; }
 extern "C" const char* ga3c_kernel_name(int kid) { return (kid >= 0 && kid < K_COUNT) ? kKernelNames[kid] : nullptr; }
-
-static void timing_free(ga3c_net* n) {
-  for (cudaEvent_t e : n->tev) cudaEventDestroy(e);
-  n->tev.clear(); n->tkid.clear(); n->tcursor = 0;
-}
 
 // ---- step timeline trace --------------------------------------------------------------------------
 static int trace_attach_all(unsigned long long* buf) {
@@ -754,24 +719,12 @@ extern "C" int ga3c_timing_enable(ga3c_net* n, int32_t max_records) {
   if (!n || max_records < 0) return fail_msg("ga3c_timing_enable: bad argument");
   CK(cudaSetDevice(n->cfg.device));
   CK(cudaDeviceSynchronize());
-  timing_free(n);
-  n->tev.resize((size_t)2 * max_records);
-  n->tkid.assign((size_t)max_records, 0);
-  for (auto& e : n->tev) CK(cudaEventCreate(&e));
-  return 0;
+  return n->log.enable(max_records);
 }
 
 extern "C" int ga3c_timing_collect(ga3c_net* n, double* total_ms, int64_t* counts, int32_t n_kernels) {
   if (!n || !total_ms || !counts || n_kernels < K_COUNT) return fail_msg("ga3c_timing_collect: bad argument");
   CK(cudaSetDevice(n->cfg.device));
   CK(cudaDeviceSynchronize());
-  for (int k = 0; k < n_kernels; ++k) { total_ms[k] = 0.0; counts[k] = 0; }
-  for (int r = 0; r < n->tcursor; ++r) {
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, n->tev[2 * r], n->tev[2 * r + 1]));
-    total_ms[n->tkid[r]] += ms;
-    counts[n->tkid[r]] += 1;
-  }
-  n->tcursor = 0;
-  return 0;
+  return n->log.collect(total_ms, reinterpret_cast<long long*>(counts), n_kernels);
 }
