@@ -12,7 +12,7 @@ class ga3c_config(C.Structure):
     _fields_ = [("device", C.c_int32), ("num_actions", C.c_int32), ("max_batch", C.c_int32),
                 ("rmsprop_decay", C.c_float), ("rmsprop_momentum", C.c_float), ("rmsprop_epsilon", C.c_float),
                 ("log_epsilon", C.c_float), ("min_policy", C.c_float), ("use_log_softmax", C.c_int32),
-                ("use_grad_clip", C.c_int32), ("grad_clip_norm", C.c_float)]
+                ("use_grad_clip", C.c_int32), ("grad_clip_norm", C.c_float), ("dual_rmsprop", C.c_int32)]
 
 
 class ga3c_mlp_config(C.Structure):
@@ -20,7 +20,7 @@ class ga3c_mlp_config(C.Structure):
                 ("max_batch", C.c_int32), ("n_dense", C.c_int32), ("dense_width", C.c_int32 * 8),
                 ("rmsprop_decay", C.c_float), ("rmsprop_momentum", C.c_float), ("rmsprop_epsilon", C.c_float),
                 ("log_epsilon", C.c_float), ("min_policy", C.c_float), ("use_log_softmax", C.c_int32),
-                ("use_grad_clip", C.c_int32), ("grad_clip_norm", C.c_float)]
+                ("use_grad_clip", C.c_int32), ("grad_clip_norm", C.c_float), ("dual_rmsprop", C.c_int32)]
 
 
 MLP_FORK_VP, MLP_DISCRATE = 0, 1

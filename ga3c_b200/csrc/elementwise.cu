@@ -186,6 +186,54 @@ int launch_rmsprop_clipped(const RmsPropArgs& a, const ClipArgs& c, cudaStream_t
   return launch_pdl(rmsprop_clip_kernel<false>, dim3(grid), dim3(256), 0, stream, a, c);
 }
 
+// ---- Config.DUAL_RMSPROP (NetworkVP_discrate.py:87-98, :124-128) ---------------------------------------------
+template <bool HAS_MOM>
+__global__ void __launch_bounds__(256) rmsprop_dual_kernel(RmsPropDualArgs d) {
+  const RmsPropArgs& a = d.a;
+  griddep_launch();
+  griddep_wait(K_RMSPROP);
+  const int64_t n4 = a.n_floats >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int64_t e = i << 2;
+    const bool skip1 = (e >= d.skip_lo[0] && e < d.skip_hi[0]) || (e >= d.skip_lo[1] && e < d.skip_hi[1]);
+    const bool skip2 = (e >= d.skip_lo[2] && e < d.skip_hi[2]) || (e >= d.skip_lo[3] && e < d.skip_hi[3]);
+    const float4 w0 = reinterpret_cast<float4*>(a.w)[i];
+    float4 w = w0;
+    if (!skip1) {
+      const float4 g = reinterpret_cast<const float4*>(a.g)[i];
+      float4 ms = reinterpret_cast<float4*>(a.ms)[i];
+      float4 mo = HAS_MOM ? reinterpret_cast<float4*>(a.mom)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 w1 = w0;
+      rms_update<HAS_MOM>(a, g, w1, ms, mo);
+      w.x -= w0.x - w1.x; w.y -= w0.y - w1.y; w.z -= w0.z - w1.z; w.w -= w0.w - w1.w;
+      reinterpret_cast<float4*>(a.ms)[i] = ms;
+      if (HAS_MOM) reinterpret_cast<float4*>(a.mom)[i] = mo;
+    }
+    if (!skip2) {
+      const float4 g = reinterpret_cast<const float4*>(d.g2)[i];
+      float4 ms = reinterpret_cast<float4*>(d.ms2)[i];
+      float4 mo = HAS_MOM ? reinterpret_cast<float4*>(d.mom2)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 w2 = w0;
+      rms_update<HAS_MOM>(a, g, w2, ms, mo);
+      w.x -= w0.x - w2.x; w.y -= w0.y - w2.y; w.z -= w0.z - w2.z; w.w -= w0.w - w2.w;
+      reinterpret_cast<float4*>(d.ms2)[i] = ms;
+      if (HAS_MOM) reinterpret_cast<float4*>(d.mom2)[i] = mo;
+    }
+    reinterpret_cast<float4*>(a.w)[i] = w;
+    if (a.w1_count > 0 && e >= a.w1_offset && e < a.w1_offset + a.w1_count)
+      reinterpret_cast<uint2*>(a.w1_shadow)[(e - a.w1_offset) >> 2] = make_uint2(pack_bf16(w.x, w.y), pack_bf16(w.z, w.w));
+  }
+  trace_mark(K_RMSPROP, 2);
+}
+
+int launch_rmsprop_dual(const RmsPropDualArgs& d, cudaStream_t stream) {
+  const int64_t n4 = d.a.n_floats >> 2;
+  const int grid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+  if (d.a.momentum != 0.f) return launch_pdl(rmsprop_dual_kernel<true>, dim3(grid), dim3(256), 0, stream, d);
+  return launch_pdl(rmsprop_dual_kernel<false>, dim3(grid), dim3(256), 0, stream, d);
+}
+
 // ---- single-GPU step tail: grad_reduce + RMSProp in one launch -------------------------------------------
 // Blocks [0, n_red) sum the gradient-partial slabs of 32 float4 columns exactly like grad_reduce_kernel (same order,
 // same bits), store the reduced gradient and apply RMSProp to those columns; the remaining blocks update dense1/w,

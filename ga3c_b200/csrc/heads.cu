@@ -139,21 +139,27 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
             for (int k = 0; k < A; ++k) dz[k] = sm[k] * (h[k] - sh);
             c1 = logf(fmaxf(sel, p.log_eps)) * adv;
           }
+          // Config.DUAL_RMSPROP: part 1 = gradient of cost_p alone, part 2 = of cost_v alone (0: cost_all)
+          const float dvv = p.part == 1 ? 0.f : dv;
+          if (p.part == 2) {
+#pragma unroll
+            for (int k = 0; k < A; ++k) dz[k] = 0.f;
+          }
           if (lane == 0) {
             l1 += c1;
             l2 += -p.beta * ent;
             lv += 0.5f * (yr - v) * (yr - v);
 #pragma unroll
             for (int k = 0; k < A; ++k) dzs[sl][k] = dz[k];
-            dzs[sl][A] = dv;
+            dzs[sl][A] = dvv;
           }
           // dd1[j] = relu'(d1[j]) * (sum_k dz_k Wp[j][k] + dv Wv[j]) for this lane's 8 features
           float da[4], db[4];
           {
             const float4 wa = *reinterpret_cast<const float4*>(&wt[A][4 * lane]);
             const float4 wb = *reinterpret_cast<const float4*>(&wt[A][128 + 4 * lane]);
-            da[0] = dv * wa.x; da[1] = dv * wa.y; da[2] = dv * wa.z; da[3] = dv * wa.w;
-            db[0] = dv * wb.x; db[1] = dv * wb.y; db[2] = dv * wb.z; db[3] = dv * wb.w;
+            da[0] = dvv * wa.x; da[1] = dvv * wa.y; da[2] = dvv * wa.z; da[3] = dvv * wa.w;
+            db[0] = dvv * wb.x; db[1] = dvv * wb.y; db[2] = dvv * wb.z; db[3] = dvv * wb.w;
           }
 #pragma unroll
           for (int k = 0; k < A; ++k) {

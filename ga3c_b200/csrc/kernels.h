@@ -56,6 +56,7 @@ struct HeadsArgs {
   int64_t gp_stride;
   int train;
   int log_softmax;             // Config.USE_LOG_SOFTMAX
+  int part;                    // Config.DUAL_RMSPROP passes: 0 gradient of cost_all, 1 of cost_p alone, 2 of cost_v alone
 };
 int heads_grid(int batch, int num_sms);          // CTAs (= slabs written) of a training launch
 int launch_heads(const HeadsArgs& args, int num_sms, cudaStream_t stream);
@@ -108,6 +109,16 @@ struct ClipArgs {
 };
 int clip_chunks(int64_t max_count);
 int launch_rmsprop_clipped(const RmsPropArgs& a, const ClipArgs& c, cudaStream_t stream);
+// Config.DUAL_RMSPROP: two optimizers with their own slots, both steps taken from the weights the call started with:
+// w <- w - step(g, ms, mom) - step(g2, ms2, mom2).  Elements inside [skip_lo[i], skip_hi[i]) are left alone by optimizer i / 2
+// (i = 0, 1: first optimizer; 2, 3: second): the variables its cost does not reach.
+struct RmsPropDualArgs {
+  RmsPropArgs a;                   // w, g, ms, mom + scalars (+ bf16 shadow range)
+  const float* g2;
+  float *ms2, *mom2;
+  int64_t skip_lo[4], skip_hi[4];
+};
+int launch_rmsprop_dual(const RmsPropDualArgs& d, cudaStream_t stream);
 // grad_reduce + RMSProp in one launch (single-GPU step; r.out must be a.g, r.out_floats the small-tensor prefix)
 int launch_rmsprop_reduce(const RmsPropArgs& a, const GradReduceArgs& r, cudaStream_t stream);
 // data-parallel RMSProp over peer memory: rank r owns arena slice r; it sums that slice of every rank's gradient

@@ -331,7 +331,9 @@ __global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, cons
         }
       }
       if (TRAIN) {
-        z[0] = dv;
+        z[0] = s.part == 1 ? 0.f : dv;                     // Config.DUAL_RMSPROP: cost_p alone does not reach the value head ...
+        if (s.part == 2)
+          for (int j = 1; j < n_out; ++j) z[j] = 0.f;      // ... and cost_v alone not the policy head
         if (valid) {
           float* dl = s.dlogits + (size_t)(row0 + r) * net.n_out_ld;
           for (int j = 0; j < n_out; ++j) dl[j] = z[j];

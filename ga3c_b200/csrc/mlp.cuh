@@ -39,6 +39,7 @@ struct MlpStepArgs {
   const float* x;                       // [B, state_dim]
   const float *yr, *a;                  // train: [B], [B, A]
   int batch, train;
+  int part;                             // Config.DUAL_RMSPROP passes: 0 gradient of cost_all, 1 of cost_p alone, 2 of cost_v alone
   float beta;
   float *p_out, *v_out;                 // may be null in train mode
   float* act[MLP_MAX_LAYERS];           // train: layer outputs [B, n_l]

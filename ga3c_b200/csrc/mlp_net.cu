@@ -37,6 +37,8 @@ struct ga3c_mlp {
   float *w = nullptr, *g = nullptr, *ms = nullptr, *mom = nullptr;
   float* part = nullptr;                 // [MLP_MAX_SPLITS][live_floats] weight-gradient partial arenas
   float *clip_ss = nullptr, *clip_scale = nullptr;   // Config.USE_GRAD_CLIP scratch
+  float *g2 = nullptr, *ms2 = nullptr, *mom2 = nullptr;   // Config.DUAL_RMSPROP: gradient of cost_v, second optimizer's slots
+  int64_t skip_lo[2] = {}, skip_hi[2] = {};          // arena ranges of logits_v/* and of the policy head
   // workspace for max_batch rows
   float* act[MLP_MAX_LAYERS] = {};
   float* dz[MLP_MAX_LAYERS] = {};
@@ -68,6 +70,7 @@ extern "C" int ga3c_mlp_destroy(ga3c_mlp* n) {
   if (!n) return 0;
   cudaFree(n->w); cudaFree(n->g); cudaFree(n->ms); cudaFree(n->mom); cudaFree(n->part);
   cudaFree(n->clip_ss); cudaFree(n->clip_scale);
+  cudaFree(n->g2); cudaFree(n->ms2); cudaFree(n->mom2);
   free_workspace(n);
   n->log.clear();
   delete n;
@@ -158,6 +161,9 @@ extern "C" int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out) {
   net.wv_off = (int)n->params[pv].offset; net.bv_off = (int)n->params[pv + 1].offset;
   net.wp_off = (int)n->params[px].offset; net.bp_off = (int)n->params[px + 1].offset;
   if (py >= 0) { net.wy_off = (int)n->params[py].offset; net.by_off = (int)n->params[py + 1].offset; }
+  n->skip_lo[0] = n->params[pv].offset; n->skip_hi[0] = n->params[pv + 1].offset + n->params[pv + 1].count;
+  const int plast = py >= 0 ? py + 1 : px + 1;      // the policy head's variables are consecutive in the arena
+  n->skip_lo[1] = n->params[px].offset; n->skip_hi[1] = n->params[plast].offset + n->params[plast].count;
 
   const size_t ab = (size_t)n->arena_floats * 4;
   float** arenas[4] = {&n->w, &n->g, &n->ms, &n->mom};
@@ -173,6 +179,17 @@ extern "C" int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out) {
   e = cudaMalloc((void**)&n->part, (size_t)MLP_MAX_SPLITS * n->live_floats * 4);
   if (e != cudaSuccess) { ga3c_mlp_destroy(n); return fail("cudaMalloc", e); }
   cudaMemset(n->part, 0, (size_t)MLP_MAX_SPLITS * n->live_floats * 4);
+  if (cfg->dual_rmsprop) {
+    if (cfg->use_grad_clip) { ga3c_mlp_destroy(n); return set_error("ga3c_mlp_create: DUAL_RMSPROP with USE_GRAD_CLIP is not built"); }
+    float** extra[3] = {&n->g2, &n->ms2, &n->mom2};
+    for (float** a : extra) {
+      e = cudaMalloc((void**)a, ab);
+      if (e != cudaSuccess) { ga3c_mlp_destroy(n); return fail("cudaMalloc", e); }
+      cudaMemset(*a, 0, ab);
+    }
+    std::vector<float> ones((size_t)n->arena_floats, 1.0f);
+    cudaMemcpy(n->ms2, ones.data(), ab, cudaMemcpyHostToDevice);
+  }
   if (cfg->use_grad_clip) {
     for (const MlpParam& p : n->params)
       if (!p.live) {     // opt.compute_gradients yields (None, var) and tf.clip_by_average_norm(None, ..) raises
@@ -222,7 +239,10 @@ extern "C" int ga3c_mlp_param_info(const ga3c_mlp* n, int i, const char** name, 
 extern "C" int64_t ga3c_mlp_arena_floats(const ga3c_mlp* n) { return n ? n->arena_floats : 0; }
 
 static float* arena_of(ga3c_mlp* n, int which) {
-  switch (which) { case 0: return n->w; case 1: return n->g; case 2: return n->ms; case 3: return n->mom; }
+  switch (which) {
+    case 0: return n->w; case 1: return n->g; case 2: return n->ms; case 3: return n->mom;
+    case 4: return n->g2; case 5: return n->ms2; case 6: return n->mom2;      // null unless dual_rmsprop
+  }
   return nullptr;
 }
 
@@ -276,21 +296,27 @@ extern "C" int ga3c_mlp_predict(ga3c_mlp* n, const float* x, int32_t batch, floa
   return 0;
 }
 
-extern "C" int ga3c_mlp_forward_backward(ga3c_mlp* n, const float* x, const float* yr, const float* a, int32_t batch,
-                                         float beta, float* loss, void* stream) {
+static int mlp_fb_impl(ga3c_mlp* n, const float* x, const float* yr, const float* a, int32_t batch, float beta, float* loss,
+                       void* stream, int part, float* g_dst) {
   if (int r = check_batch(n, batch, "ga3c_mlp_forward_backward")) return r;
   if (!x || !yr || !a) return set_error("ga3c_mlp_forward_backward: null buffer");
   CK(cudaSetDevice(n->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   MlpStepArgs s = step_args(n, x, batch);
-  s.yr = yr; s.a = a; s.beta = beta; s.train = 1;
+  s.yr = yr; s.a = a; s.beta = beta; s.train = 1; s.part = part;
   LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(n->net, s, n->num_sms, st));
   const int splits = mlp_wgrad_splits(n->net, batch, n->num_sms);
   LAUNCH(n, K_MLP_WGRAD, st, launch_mlp_wgrad(n->net, s, n->part, n->live_floats, splits, st));
   const int tm = mlp_tile_rows(batch, n->num_sms);
-  LAUNCH(n, K_MLP_REDUCE, st, launch_mlp_reduce(n->part, n->live_floats, splits, n->g, (int)n->live_floats, n->loss_part,
+  LAUNCH(n, K_MLP_REDUCE, st, launch_mlp_reduce(n->part, n->live_floats, splits, g_dst, (int)n->live_floats, n->loss_part,
                                                 (batch + tm - 1) / tm, loss, st));
   return 0;
+}
+
+extern "C" int ga3c_mlp_forward_backward(ga3c_mlp* n, const float* x, const float* yr, const float* a, int32_t batch,
+                                         float beta, float* loss, void* stream) {
+  if (!n) return set_error("ga3c_mlp_forward_backward: null handle");
+  return mlp_fb_impl(n, x, yr, a, batch, beta, loss, stream, 0, n->g);
 }
 
 extern "C" int ga3c_mlp_apply_rmsprop(ga3c_mlp* n, float lr, void* stream) {
@@ -301,6 +327,7 @@ extern "C" int ga3c_mlp_apply_rmsprop(ga3c_mlp* n, float lr, void* stream) {
   a.n_floats = n->live_floats;           // the gradient-less variables behind the live prefix are never touched
   a.w1_offset = n->live_floats; a.w1_count = 0;
   a.lr = lr; a.decay = n->cfg.rmsprop_decay; a.momentum = n->cfg.rmsprop_momentum; a.eps = n->cfg.rmsprop_epsilon;
+  if (n->cfg.dual_rmsprop) return set_error("ga3c_mlp_apply_rmsprop: with DUAL_RMSPROP use ga3c_mlp_train_step (two backward passes)");
   if (n->cfg.use_grad_clip) {            // tf.clip_by_average_norm per variable (NetworkVP.py:138-141, NetworkVP_discrate.py:118-121)
     ClipArgs c{};
     c.g = n->g; c.n_tensors = (int)n->params.size();
@@ -322,6 +349,21 @@ extern "C" int ga3c_mlp_apply_rmsprop(ga3c_mlp* n, float lr, void* stream) {
 
 extern "C" int ga3c_mlp_train_step(ga3c_mlp* n, const float* x, const float* yr, const float* a, int32_t batch, float lr,
                                    float beta, float* loss, void* stream) {
+  if (n && n->cfg.dual_rmsprop) {
+    // Config.DUAL_RMSPROP (NetworkVP.py:107-118, :143-147): cost_p into g, cost_v into g2, both steps from the same weights
+    if (int r = mlp_fb_impl(n, x, yr, a, batch, beta, loss, stream, 1, n->g)) return r;
+    if (int r = mlp_fb_impl(n, x, yr, a, batch, beta, nullptr, stream, 2, n->g2)) return r;
+    RmsPropDualArgs d{};
+    d.a.w = n->w; d.a.ms = n->ms; d.a.mom = n->mom; d.a.g = n->g; d.a.w1_shadow = nullptr;
+    d.a.n_floats = n->live_floats; d.a.w1_offset = n->live_floats; d.a.w1_count = 0;
+    d.a.lr = lr; d.a.decay = n->cfg.rmsprop_decay; d.a.momentum = n->cfg.rmsprop_momentum; d.a.eps = n->cfg.rmsprop_epsilon;
+    d.g2 = n->g2; d.ms2 = n->ms2; d.mom2 = n->mom2;
+    d.skip_lo[0] = n->skip_lo[0]; d.skip_hi[0] = n->skip_hi[0];        // cost_p: not logits_v
+    d.skip_lo[2] = n->skip_lo[1]; d.skip_hi[2] = n->skip_hi[1];        // cost_v: not the policy head
+    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_dual(d, (cudaStream_t)stream));
+    n->global_step += 2;
+    return 0;
+  }
   if (int r = ga3c_mlp_forward_backward(n, x, yr, a, batch, beta, loss, stream)) return r;
   return ga3c_mlp_apply_rmsprop(n, lr, stream);
 }

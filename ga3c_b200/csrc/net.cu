@@ -66,6 +66,7 @@ struct ga3c_net {
   int gp_heads_grid = 0;           // slabs the heads kernel of the current step wrote
   float* loss_out = nullptr;       // caller's loss buffer of the current step (may be null)
   float *clip_ss = nullptr, *clip_scale = nullptr;   // Config.USE_GRAD_CLIP scratch: chunk sums of squares, per-tensor scale
+  float *g2 = nullptr, *ms2 = nullptr, *mom2 = nullptr;   // Config.DUAL_RMSPROP: gradient of cost_v and the second optimizer's slots
   bool keep_dn1 = false;           // tests: also store dn1 (which otherwise never leaves the SM) to the workspace
   int64_t global_step = 0;
   LaunchLog log;                   // launch counter + per-kernel CUDA-event timing (ga3c_timing_*)
@@ -92,7 +93,7 @@ int set_error(const std::string& m) { g_err = m; return -1; }     // for the oth
 const char* kernel_name(int kid) { return (kid >= 0 && kid < K_COUNT) ? kKernelNames[kid] : nullptr; }
 }
 extern "C" const char* ga3c_last_error(void) { return g_err.c_str(); }
-extern "C" int ga3c_abi_version(void) { return 3; }
+extern "C" int ga3c_abi_version(void) { return 4; }
 
 extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
   if (!cfg || !out) return fail_msg("ga3c_create: null argument");
@@ -158,6 +159,17 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
   e = cudaMalloc((void**)&n->gpart, (size_t)2 * n->num_sms * n->gp_stride * sizeof(float));
   if (e != cudaSuccess) { ga3c_destroy(n); return fail("cudaMalloc", e); }
   cudaMemset(n->gpart, 0, (size_t)2 * n->num_sms * n->gp_stride * sizeof(float));
+  if (cfg->dual_rmsprop) {
+    if (cfg->use_grad_clip) { ga3c_destroy(n); return fail_msg("ga3c_create: DUAL_RMSPROP with USE_GRAD_CLIP (clip_by_norm per optimizer) is not built"); }
+    float** extra[3] = {&n->g2, &n->ms2, &n->mom2};
+    for (float** a : extra) {
+      e = cudaMalloc((void**)a, ab);
+      if (e != cudaSuccess) { ga3c_destroy(n); return fail("cudaMalloc", e); }
+      cudaMemset(*a, 0, ab);
+    }
+    std::vector<float> ones((size_t)n->arena_floats, 1.0f);
+    cudaMemcpy(n->ms2, ones.data(), ab, cudaMemcpyHostToDevice);
+  }
   if (cfg->use_grad_clip) {
     e = cudaMalloc((void**)&n->clip_ss, (size_t)P_COUNT * clip_chunks((int64_t)FLAT * FC) * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void**)&n->clip_scale, P_COUNT * sizeof(float));
@@ -215,6 +227,7 @@ extern "C" int ga3c_destroy(ga3c_net* n) {
   cudaFree(n->slab);
   cudaFree(n->gpart);
   cudaFree(n->clip_ss); cudaFree(n->clip_scale);
+  cudaFree(n->g2); cudaFree(n->ms2); cudaFree(n->mom2);
   if (n->trace) { trace_attach_all(nullptr); cudaFree(n->trace); }
   free_workspace(n);
   n->log.clear();
@@ -247,7 +260,10 @@ extern "C" int ga3c_arena_ptrs(ga3c_net* n, float** p, float** g, float** ms, fl
 }
 
 static float* arena_of(ga3c_net* n, int which) {
-  switch (which) { case 0: return n->w; case 1: return n->g; case 2: return n->ms; case 3: return n->mom; }
+  switch (which) {
+    case 0: return n->w; case 1: return n->g; case 2: return n->ms; case 3: return n->mom;
+    case 4: return n->g2; case 5: return n->ms2; case 6: return n->mom2;      // null unless dual_rmsprop
+  }
   return nullptr;
 }
 
@@ -336,7 +352,7 @@ extern "C" int ga3c_predict_u8(ga3c_net* n, const uint8_t* x, int32_t batch, flo
 // gradients of dense1/w, dense1/b, logits_v/*, logits_p/* are final, so their allreduce can start while
 // ga3c_fb_tail computes the conv gradients.
 static int fb_head_impl(ga3c_net* n, const void* x, bool x_u8, const float* yr, const float* a, int32_t batch, float beta,
-                        float* loss, void* stream, bool with_wgrad) {
+                        float* loss, void* stream, bool with_wgrad, int part = 0, bool skip_forward = false) {
   if (int r = check_batch(n, batch, "ga3c_fb_head")) return r;
   if (!x || !yr || !a) return fail_msg("ga3c_fb_head: null buffer");
   CK(cudaSetDevice(n->cfg.device));
@@ -344,18 +360,21 @@ static int fb_head_impl(ga3c_net* n, const void* x, bool x_u8, const float* yr, 
   const float* w = n->w;
   float* g = n->g;
   float* gp = n->gpart;       // small-tensor gradients: per-CTA partial slabs, summed at the end of ga3c_fb_tail
-  LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, x_u8, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
-                                            w + n->off(P_C12B), n->n1, n->n2, batch, n->num_sms, st));
   const int splits = dense_fwd_splits(batch, n->num_sms);
-  LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
+  if (!skip_forward) {        // the second DUAL_RMSPROP pass reuses n1 / n2 / the dense1 partials of the first
+    LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, x_u8, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
+                                              w + n->off(P_C12B), n->n1, n->n2, batch, n->num_sms, st));
+    LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
+  }
   HeadsArgs h = heads_args(n, batch, splits);
-  h.yr = yr; h.a = a; h.beta = beta; h.train = 1; h.dd1 = n->dd1;
+  h.yr = yr; h.a = a; h.beta = beta; h.train = 1; h.dd1 = n->dd1; h.part = part;
   h.g_wp = gp + n->off(P_PW); h.g_bp = gp + n->off(P_PB); h.g_wv = gp + n->off(P_VW); h.g_bv = gp + n->off(P_VB);
   h.g_b1 = gp + n->off(P_D1B); h.loss = gp + n->small_floats; h.gp_stride = n->gp_stride;
   n->gp_heads_grid = heads_grid(batch, n->num_sms);
   n->loss_out = loss;
   LAUNCH(n, K_HEADS, st, launch_heads(h, n->num_sms, st));
-  if (with_wgrad) LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad_tc(n->n2, n->dd1, g + n->off(P_D1W), batch, st));
+  (void)g;
+  if (with_wgrad) LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad_tc(n->n2, n->dd1, n->g + n->off(P_D1W), batch, st));
   n->last_batch = batch;
   return 0;
 }
@@ -367,9 +386,9 @@ extern "C" int ga3c_fb_head(ga3c_net* n, const float* x, const float* yr, const 
 
 // sum of the per-CTA slabs: conv tensors (the first four of the arena) over the conv grids, head tensors and the loss
 // sums over the heads grid
-static GradReduceArgs reduce_args(ga3c_net* n, int batch) {
+static GradReduceArgs reduce_args(ga3c_net* n, int batch, float* g_dst = nullptr) {
   GradReduceArgs r{};
-  r.part = n->gpart; r.stride = n->gp_stride; r.out = n->g; r.out_tail = n->loss_out;
+  r.part = n->gpart; r.stride = n->gp_stride; r.out = g_dst ? g_dst : n->g; r.out_tail = n->loss_out;
   r.out_floats = (int)n->small_floats; r.n_floats = (int)n->small_floats + 4;
   for (int s = 0; s < GR_MAX_SEG; ++s) { r.seg_end[s] = r.n_floats; r.seg_count[s] = n->gp_heads_grid; }
   r.seg_end[0] = (int)n->off(P_D1B); r.seg_count[0] = conv_bwd_grid(batch, n->num_sms, n->cur_exch);
@@ -379,7 +398,7 @@ static GradReduceArgs reduce_args(ga3c_net* n, int batch) {
 // dense1 data gradient and the two conv backward kernels; with `reduce` the slabs are summed into the gradient arena
 // (conv11/*, conv12/*, dense1/b, heads, loss sums), otherwise the caller does it (fused with RMSProp).
 static int fb_tail_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, void* stream, bool with_wgrad, bool reduce,
-                        const DpBigArgs* dp = nullptr) {
+                        const DpBigArgs* dp = nullptr, float* g_dst = nullptr) {
   if (int r = check_batch(n, batch, "ga3c_fb_tail")) return r;
   if (!x) return fail_msg("ga3c_fb_tail: null buffer");
   if (batch != n->last_batch) return fail_msg("ga3c_fb_tail: batch differs from the preceding ga3c_fb_head");
@@ -388,13 +407,13 @@ static int fb_tail_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, vo
   const float* w = n->w;
   float* gp = n->gpart;
   if (with_wgrad)   // dgrad + wgrad tiles of dense1 in one grid
-    LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_bwd_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, n->g + n->off(P_D1W), batch, st));
+    LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_bwd_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, (g_dst ? g_dst : n->g) + n->off(P_D1W), batch, st));
   else
     LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
   LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(x, x_u8, n->n1, n->dn2, w + n->off(P_C12W), n->keep_dn1 ? n->dn1 : nullptr,
                                               gp + n->off(P_C11W), gp + n->off(P_C11B), gp + n->off(P_C12W),
                                               gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, dp, st));
-  if (reduce) LAUNCH(n, K_GRAD_REDUCE, st, launch_grad_reduce(reduce_args(n, batch), st));
+  if (reduce) LAUNCH(n, K_GRAD_REDUCE, st, launch_grad_reduce(reduce_args(n, batch, g_dst), st));
   return 0;
 }
 
@@ -443,6 +462,7 @@ static int apply_rmsprop_impl(ga3c_net* n, float lr, void* stream, const GradRed
   if (!n) return fail_msg("ga3c_apply_rmsprop: null handle");
   CK(cudaSetDevice(n->cfg.device));
   RmsPropArgs a = rmsprop_args(n, lr);
+  if (n->cfg.dual_rmsprop) return fail_msg("ga3c_apply_rmsprop: with DUAL_RMSPROP use ga3c_train_step (two backward passes)");
   if (n->cfg.use_grad_clip) {
     // clip_by_average_norm needs the whole (reduced) gradient of a variable: local arena only (single GPU, or after the
     // host's NCCL allreduce in dp_mode 'nccl')
@@ -563,6 +583,22 @@ extern "C" int ga3c_dp_error(ga3c_net* n, int32_t* error_out) {
 
 static int train_step_impl(ga3c_net* n, const void* x, bool x_u8, const float* yr, const float* a, int32_t batch, float lr,
                            float beta, float* loss, void* stream) {
+  if (n->cfg.dual_rmsprop) {
+    // Config.DUAL_RMSPROP: one forward, two backward passes (cost_p into g, cost_v into g2), one update with both steps
+    if (n->dp_world > 1) return fail_msg("ga3c_train_step: DUAL_RMSPROP is not available with data parallelism");
+    if (int r = fb_head_impl(n, x, x_u8, yr, a, batch, beta, loss, stream, false, 1)) return r;
+    if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, true)) return r;
+    if (int r = fb_head_impl(n, x, x_u8, yr, a, batch, beta, nullptr, stream, false, 2, true)) return r;
+    if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, true, nullptr, n->g2)) return r;
+    RmsPropDualArgs d{};
+    d.a = rmsprop_args(n, lr);
+    d.g2 = n->g2; d.ms2 = n->ms2; d.mom2 = n->mom2;
+    const int skip[4] = {P_VW, P_VB, P_PW, P_PB};          // cost_p does not reach logits_v (stop_gradient), cost_v not logits_p
+    for (int i = 0; i < 4; ++i) { d.skip_lo[i] = n->off(skip[i]); d.skip_hi[i] = n->off(skip[i]) + n->params[skip[i]].count; }
+    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_dual(d, (cudaStream_t)stream));
+    n->global_step += 2;      // both minimize calls advance it (NetworkVP_discrate.py:125-126)
+    return 0;
+  }
   if (int r = fb_head_impl(n, x, x_u8, yr, a, batch, beta, loss, stream, false)) return r;
   if (n->cfg.use_grad_clip) {
     if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, true)) return r;

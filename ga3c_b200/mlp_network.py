@@ -34,9 +34,9 @@ class _MlpNetwork:
         self.model_name = model_name
         self.num_actions = int(num_actions)
         self.state_dim = int(np.prod(state_dim)) if not isinstance(state_dim, int) else state_dim
-        for knob in ("DUAL_RMSPROP",):
-            if getattr(cfg, knob, False):
-                raise NotImplementedError(f"Config.{knob}=True is not built yet (SURVEY.md 8f F4)")
+        self._dual = bool(getattr(cfg, "DUAL_RMSPROP", False))
+        if self._dual and getattr(cfg, "USE_GRAD_CLIP", False):
+            raise NotImplementedError("Config.DUAL_RMSPROP with USE_GRAD_CLIP (clip_by_norm per optimizer) is not built")
         self.learning_rate = cfg.LEARNING_RATE_START
         self.beta = cfg.BETA_START
         self.log_epsilon = cfg.LOG_EPSILON
@@ -57,7 +57,7 @@ class _MlpNetwork:
                                   min_policy=cfg.MIN_POLICY,
                                   use_log_softmax=int(bool(getattr(cfg, 'USE_LOG_SOFTMAX', False))),
                               use_grad_clip=int(bool(getattr(cfg, 'USE_GRAD_CLIP', False))),
-                              grad_clip_norm=float(getattr(cfg, 'GRAD_CLIP_NORM', 40.0)))
+                              grad_clip_norm=float(getattr(cfg, 'GRAD_CLIP_NORM', 40.0)), dual_rmsprop=int(self._dual))
         if self.KIND == _capi.MLP_DISCRATE and len(dense) > 8:
             raise ValueError("Config.DENSE_LAYERS: at most 8 entries")
         h = C.c_void_p()
@@ -280,14 +280,17 @@ class _MlpNetwork:
         g = self._split(self._download(1))
         return {k: v for k, v in g.items() if self._live[k]}
 
-    def get_slots(self):
-        return self._split(self._download(2)), self._split(self._download(3))
+    def get_slots(self, optimizer: int = 0):
+        """(ms, mom) of the RMSProp optimizer; with Config.DUAL_RMSPROP optimizer 0 minimises cost_p and 1 cost_v."""
+        base = 2 if optimizer == 0 else 5
+        return self._split(self._download(base)), self._split(self._download(base + 1))
 
-    def set_slots(self, ms=None, mom=None):
+    def set_slots(self, ms=None, mom=None, optimizer: int = 0):
+        base = 2 if optimizer == 0 else 5
         if ms is not None:
-            self._upload(2, self._join(2, ms))
+            self._upload(base, self._join(base, ms))
         if mom is not None:
-            self._upload(3, self._join(3, mom))
+            self._upload(base + 1, self._join(base + 1, mom))
 
     def _checkpoint_filename(self, episode):
         return 'checkpoints/%s_%08d' % (self.model_name, episode)
@@ -302,6 +305,10 @@ class _MlpNetwork:
         blob = dict(self.get_variables())
         blob.update({k.replace(":0", "/RMSProp:0"): v for k, v in ms.items()})
         blob.update({k.replace(":0", "/RMSProp_1:0"): v for k, v in mom.items()})
+        if self._dual:
+            ms2, mom2 = self.get_slots(1)
+            blob.update({k.replace(":0", "/RMSProp_2:0"): v for k, v in ms2.items()})
+            blob.update({k.replace(":0", "/RMSProp_3:0"): v for k, v in mom2.items()})
         blob["step:0"] = np.array(self.get_global_step(), dtype=np.int64)
         np.savez(fn, **blob)
         return fn
@@ -318,6 +325,9 @@ class _MlpNetwork:
         self.set_variables({k: z[k] for k in names})
         self.set_slots({k: z[k.replace(":0", "/RMSProp:0")] for k in names},
                        {k: z[k.replace(":0", "/RMSProp_1:0")] for k in names})
+        if self._dual and names[0].replace(":0", "/RMSProp_2:0") in z:
+            self.set_slots({k: z[k.replace(":0", "/RMSProp_2:0")] for k in names},
+                           {k: z[k.replace(":0", "/RMSProp_3:0")] for k in names}, optimizer=1)
         self._lib.ga3c_mlp_set_global_step(self._h, int(z["step:0"]))
         return self._get_episode_from_filename(filename)
 

@@ -58,9 +58,9 @@ class Network:
         self.state_dim = int(np.prod(state_dim)) if not isinstance(state_dim, int) else state_dim
         if self.state_dim != STATE_DIM:
             raise ValueError(f"conv NetworkVP expects state_dim = 84*84*4 = {STATE_DIM}, got {self.state_dim}")
-        for knob in ("DUAL_RMSPROP",):
-            if getattr(cfg, knob, False):
-                raise NotImplementedError(f"Config.{knob}=True is not built yet (SURVEY.md 8f F4)")
+        self._dual = bool(getattr(cfg, "DUAL_RMSPROP", False))
+        if self._dual and getattr(cfg, "USE_GRAD_CLIP", False):
+            raise NotImplementedError("Config.DUAL_RMSPROP with USE_GRAD_CLIP (clip_by_norm per optimizer) is not built")
 
         self.learning_rate = cfg.LEARNING_RATE_START      # NetworkVP.py:44
         self.beta = cfg.BETA_START                        # NetworkVP.py:45
@@ -79,7 +79,7 @@ class Network:
                               rmsprop_epsilon=cfg.RMSPROP_EPSILON, log_epsilon=cfg.LOG_EPSILON,
                               min_policy=cfg.MIN_POLICY, use_log_softmax=int(bool(getattr(cfg, 'USE_LOG_SOFTMAX', False))),
                               use_grad_clip=int(bool(getattr(cfg, 'USE_GRAD_CLIP', False))),
-                              grad_clip_norm=float(getattr(cfg, 'GRAD_CLIP_NORM', 40.0)))
+                              grad_clip_norm=float(getattr(cfg, 'GRAD_CLIP_NORM', 40.0)), dual_rmsprop=int(self._dual))
         h = C.c_void_p()
         _capi.check(self._lib.ga3c_create(C.byref(c), C.byref(h)), "ga3c_create")
         self._h = h
@@ -125,6 +125,8 @@ class Network:
             self.dp_mode = dp_mode or os.environ.get("GA3C_DP", "fused")
             if self.dp_mode not in ("fused", "nccl"):
                 raise ValueError(f"dp_mode must be 'fused' or 'nccl', got {self.dp_mode!r}")
+        if self._allreduce.enabled and self._dual:
+            raise NotImplementedError("Config.DUAL_RMSPROP is single-GPU only")
         if self.dp_mode == "fused" and getattr(cfg, "USE_GRAD_CLIP", False):
             self.dp_mode = "nccl"        # the per-variable norm needs the whole reduced gradient: allreduce first, clip locally
         if self.dp_mode == "fused":
@@ -379,14 +381,17 @@ class Network:
         """Gradients left by the last forward_backward (after allreduce when data-parallel)."""
         return self._split(self._download(1))
 
-    def get_slots(self):
-        return self._split(self._download(2)), self._split(self._download(3))
+    def get_slots(self, optimizer: int = 0):
+        """(ms, mom) of the RMSProp optimizer; with Config.DUAL_RMSPROP optimizer 0 minimises cost_p and 1 cost_v."""
+        base = 2 if optimizer == 0 else 5
+        return self._split(self._download(base)), self._split(self._download(base + 1))
 
-    def set_slots(self, ms: dict = None, mom: dict = None):
+    def set_slots(self, ms: dict = None, mom: dict = None, optimizer: int = 0):
+        base = 2 if optimizer == 0 else 5
         if ms is not None:
-            self._upload(2, self._join(2, ms))
+            self._upload(base, self._join(base, ms))
         if mom is not None:
-            self._upload(3, self._join(3, mom))
+            self._upload(base + 1, self._join(base + 1, mom))
 
     def _checkpoint_filename(self, episode):    # NetworkVP.py:267-268
         return 'checkpoints/%s_%08d' % (self.model_name, episode)
@@ -402,6 +407,10 @@ class Network:
         blob = {k: v for k, v in self.get_variables().items()}
         blob.update({k.replace(":0", "/RMSProp:0"): v for k, v in ms.items()})
         blob.update({k.replace(":0", "/RMSProp_1:0"): v for k, v in mom.items()})
+        if self._dual:
+            ms2, mom2 = self.get_slots(1)
+            blob.update({k.replace(":0", "/RMSProp_2:0"): v for k, v in ms2.items()})
+            blob.update({k.replace(":0", "/RMSProp_3:0"): v for k, v in mom2.items()})
         blob["step:0"] = np.array(self.get_global_step(), dtype=np.int64)
         np.savez(fn, **blob)
         return fn
@@ -419,6 +428,9 @@ class Network:
         self.set_variables({k: z[k] for k in names})
         self.set_slots({k: z[k.replace(":0", "/RMSProp:0")] for k in names},
                        {k: z[k.replace(":0", "/RMSProp_1:0")] for k in names})
+        if self._dual and names[0].replace(":0", "/RMSProp_2:0") in z:
+            self.set_slots({k: z[k.replace(":0", "/RMSProp_2:0")] for k in names},
+                           {k: z[k.replace(":0", "/RMSProp_3:0")] for k in names}, optimizer=1)
         self._lib.ga3c_set_global_step(self._h, int(z["step:0"]))
         return self._get_episode_from_filename(filename)
 

@@ -50,6 +50,10 @@ typedef struct ga3c_config {
                               * (its apply_gradients call has no global_step argument).  Not available with the
                               * peer-memory exchange (ga3c_dp_attach): the norm needs the whole reduced gradient.   */
   float   grad_clip_norm;    /* Config.GRAD_CLIP_NORM   (40.0)                                */
+  int32_t dual_rmsprop;      /* Config.DUAL_RMSPROP     (False): cost_p and cost_v minimised by two RMSProp optimizers with
+                              * their own slots (NetworkVP_discrate.py:87-98, :124-128).  TensorFlow runs the two train ops in
+                              * no defined order; here both gradients are taken at the weights the call started with and
+                              * both steps are subtracted; global_step advances by 2.  Single GPU, without USE_GRAD_CLIP. */
 } ga3c_config;
 
 const char* ga3c_last_error(void);
@@ -71,7 +75,8 @@ int     ga3c_param_info(const ga3c_net* net, int index, const char** name, int64
 int64_t ga3c_arena_floats(const ga3c_net* net);
 /* device base pointers of the four arenas (any may be NULL to skip) */
 int ga3c_arena_ptrs(ga3c_net* net, float** params_dev, float** grads_dev, float** ms_dev, float** mom_dev);
-/* host <-> device copies of a whole arena; which: 0 params, 1 grads, 2 ms, 3 mom.  Synchronous.
+/* host <-> device copies of a whole arena; which: 0 params, 1 grads, 2 ms, 3 mom; with dual_rmsprop also 4 / 5 / 6: gradient,
+ * ms, mom of the second optimizer (the one minimising cost_v; 1 / 2 / 3 then belong to cost_p).  Synchronous.
  * Writing params also refreshes the bf16 shadow of dense1/w. */
 int ga3c_arena_upload(ga3c_net* net, int which, const float* host, int64_t n_floats);
 int ga3c_arena_download(ga3c_net* net, int which, float* host, int64_t n_floats);
@@ -186,6 +191,7 @@ typedef struct ga3c_mlp_config {
                               * not (NetworkVP_discrate.py:121); DISCRATE with gradient-less variables is refused, as
                               * the reference graph cannot be built (clip_by_average_norm(None))                    */
   float   grad_clip_norm;
+  int32_t dual_rmsprop;      /* Config.DUAL_RMSPROP, as for the conv net                                            */
 } ga3c_mlp_config;
 int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out);
 int ga3c_mlp_destroy(ga3c_mlp* net);

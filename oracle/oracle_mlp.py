@@ -105,7 +105,7 @@ def forward(params, x, kind: str, *, dtype=np.float64, min_policy=0.0, keep=Fals
 
 
 def loss_and_grads(params, x, y_r, a, kind: str, *, beta=0.01, log_eps=1e-6, min_policy=0.0, dtype=np.float64,
-                   use_log_softmax=False):
+                   use_log_softmax=False, part="all"):
     """-> ({cost_p_1, cost_p_2, cost_p, cost_v, cost_all}, {name: grad}) ; dead variables get no entry."""
     P = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
     y_r = np.asarray(y_r, dtype=dtype)
@@ -151,6 +151,13 @@ def loss_and_grads(params, x, y_r, a, kind: str, *, beta=0.01, log_eps=1e-6, min
         grads["logits_p/w:0"] = h.T @ dz
         grads["logits_p/b:0"] = dz.sum(axis=0)
         dh = dz @ P["logits_p/w:0"].T
+    # Config.DUAL_RMSPROP: part "p" = gradient of cost_p alone (never reaches logits_v), "v" = of cost_v alone
+    if part == "p":
+        dv = np.zeros_like(dv)
+    elif part == "v":
+        dh = np.zeros_like(dh)
+        for k in list(grads):
+            del grads[k]
     grads["logits_v/w:0"] = h.T @ dv[:, None]
     grads["logits_v/b:0"] = np.array([dv.sum()], dtype=dtype)
     dh = dh + dv[:, None] @ P["logits_v/w:0"].T
@@ -162,6 +169,8 @@ def loss_and_grads(params, x, y_r, a, kind: str, *, beta=0.01, log_eps=1e-6, min
         grads[f"{name}/w:0"] = inp.T @ dz
         grads[f"{name}/b:0"] = dz.sum(axis=0)
         dh = dz @ P[f"{name}/w:0"].T
+    if part == "p":
+        del grads["logits_v/w:0"], grads["logits_v/b:0"]
     cost_p = -(c1 + c2)
     losses = dict(cost_p_1=float(c1), cost_p_2=float(c2), cost_p=float(cost_p), cost_v=float(cost_v),
                   cost_all=float(cost_p + cost_v))
@@ -183,3 +192,24 @@ def train_step(params, ms, mom, x, y_r, a, kind: str, *, lr, beta=0.01, log_eps=
     out_p, out_ms, out_mom = dict(params), dict(ms), dict(mom)
     out_p.update(p2); out_ms.update(ms2); out_mom.update(mom2)
     return losses, grads, out_p, out_ms, out_mom
+
+
+def train_step_dual(params, slots_p, slots_v, x, y_r, a, kind: str, *, lr, beta=0.01, log_eps=1e-6, min_policy=0.0,
+                    rho=0.99, mu=0.0, eps=0.1, dtype=np.float32):
+    """Config.DUAL_RMSPROP (NetworkVP.py:107-118, :143-147); semantics as oracle_np.train_step_dual: both gradients at the
+    pre-call weights, w <- w - step_p - step_v, a variable a cost does not reach is skipped by that optimizer."""
+    from . import oracle_np as onp
+    kw = dict(beta=beta, log_eps=log_eps, min_policy=min_policy, dtype=np.float64)
+    losses, gp = loss_and_grads(params, x, y_r, a, kind, part="p", **kw)
+    _, gv = loss_and_grads(params, x, y_r, a, kind, part="v", **kw)
+    new_p = {k: v.astype(dtype) for k, v in params.items()}
+    out = []
+    for g, (ms, mom) in ((gp, slots_p), (gv, slots_v)):
+        p2, ms2, mom2 = onp.rmsprop_update({k: params[k] for k in g}, g, {k: ms[k] for k in g}, {k: mom[k] for k in g},
+                                           lr=lr, rho=rho, mu=mu, eps=eps, dtype=dtype)
+        for k in g:
+            new_p[k] = new_p[k] - (params[k].astype(dtype) - p2[k])
+        nms, nmom = dict(ms), dict(mom)
+        nms.update(ms2); nmom.update(mom2)
+        out.append((nms, nmom))
+    return losses, gp, gv, new_p, out[0], out[1]

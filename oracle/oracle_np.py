@@ -189,7 +189,7 @@ def losses_from_log_softmax(lsm, s, v, y_r, a, beta, v_stop=None):
 
 
 def loss_and_grads(params, x, y_r, a, *, beta=0.01, log_eps=1e-6, min_policy=0.0,
-                   dtype=np.float64, quant=None, keep=False, use_log_softmax=False):
+                   dtype=np.float64, quant=None, keep=False, use_log_softmax=False, part="all"):
     """A5 minus the optimizer: returns (losses dict, grads dict keyed like params); with keep=True
     also the forward cache extended by the backward intermediates dd1 / dn2 / dn1 / dz / dv."""
     f = forward(params, x, dtype=dtype, quant=quant, min_policy=min_policy, keep=True, use_log_softmax=use_log_softmax)
@@ -215,6 +215,14 @@ def loss_and_grads(params, x, y_r, a, *, beta=0.01, log_eps=1e-6, min_policy=0.0
         lsm = f["lsm"]
         losses = losses_from_log_softmax(lsm, s, v, y_r, a, beta)
         dz = -adv[:, None] * (a - s * a.sum(axis=1, keepdims=True)) + beta * s * (lsm - (lsm * s).sum(axis=1, keepdims=True))
+    # Config.DUAL_RMSPROP minimises cost_p and cost_v separately (NetworkVP_discrate.py:87-98, :124-128): part = "p" is the
+    # gradient of cost_p alone (nothing reaches logits_v: stop_gradient), part = "v" that of cost_v alone (nothing reaches logits_p)
+    if part == "p":
+        dv = np.zeros_like(dv)
+    elif part == "v":
+        dz = np.zeros_like(dz)
+    elif part != "all":
+        raise ValueError(part)
     wp = params["logits_p/w:0"].astype(dtype)
     wv = params["logits_v/w:0"].astype(dtype)
     grads = {
@@ -236,6 +244,9 @@ def loss_and_grads(params, x, y_r, a, *, beta=0.01, log_eps=1e-6, min_policy=0.0
     grads["conv11/b:0"] = dn1.sum(axis=0)
     for k in grads:
         grads[k] = grads[k].reshape(params[k].shape)
+    if part != "all":                                        # tf.gradients yields None there: the optimizer skips the variable
+        for k in (("logits_v/w:0", "logits_v/b:0") if part == "p" else ("logits_p/w:0", "logits_p/b:0")):
+            del grads[k]
     if keep:
         f.update(dd1=dd1, dn2=dn2.reshape(b, FLAT), dn1=dn1.reshape(b, H1 * H1 * C1_OUT), dz=dz, dv=dv)
         return losses, grads, f
@@ -278,6 +289,30 @@ def train_step(params, ms, mom, x, y_r, a, *, lr, beta=0.01, log_eps=1e-6, min_p
     applied = grads if grad_clip is None else {k: clip_by_average_norm(g, grad_clip) for k, g in grads.items()}
     p2, ms2, mom2 = rmsprop_update(params, applied, ms, mom, lr=lr, rho=rho, mu=mu, eps=eps, dtype=dtype)
     return losses, grads, p2, ms2, mom2
+
+
+def train_step_dual(params, slots_p, slots_v, x, y_r, a, *, lr, beta=0.01, log_eps=1e-6, min_policy=0.0, use_log_softmax=False,
+                    rho=0.99, mu=0.0, eps=0.1, dtype=np.float64, quant=None):
+    """Config.DUAL_RMSPROP (NetworkVP_discrate.py:87-98, :124-128): train_op = [minimize(cost_p), minimize(cost_v)], two
+    RMSProp optimizers with their own slots.  TensorFlow runs the two train ops of one sess.run in no defined order;
+    this restatement takes the order-independent reading [TF-SEMANTICS]: both gradients at the pre-call weights (the forward
+    pass is shared in the graph), then w <- w - step_p - step_v.  Variables a cost does not reach are skipped by that
+    optimizer (no slot, no decay).  slots_x = (ms, mom) dicts over ALL variables; untouched entries are returned as they came.
+    -> (losses, grads_p, grads_v, params', slots_p', slots_v')"""
+    kw = dict(beta=beta, log_eps=log_eps, min_policy=min_policy, dtype=dtype, quant=quant, use_log_softmax=use_log_softmax)
+    losses, gp = loss_and_grads(params, x, y_r, a, part="p", **kw)
+    _, gv = loss_and_grads(params, x, y_r, a, part="v", **kw)
+    new_p = {k: v.astype(dtype) for k, v in params.items()}
+    out_slots = []
+    for g, (ms, mom) in ((gp, slots_p), (gv, slots_v)):
+        sub = {k: params[k] for k in g}
+        p2, ms2, mom2 = rmsprop_update(sub, g, {k: ms[k] for k in g}, {k: mom[k] for k in g}, lr=lr, rho=rho, mu=mu, eps=eps, dtype=dtype)
+        for k in g:
+            new_p[k] = new_p[k] - (params[k].astype(dtype) - p2[k])
+        nms, nmom = dict(ms), dict(mom)
+        nms.update(ms2); nmom.update(mom2)
+        out_slots.append((nms, nmom))
+    return losses, gp, gv, new_p, out_slots[0], out_slots[1]
 
 
 # --------------------------------------------------------------------------------------

