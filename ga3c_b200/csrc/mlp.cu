@@ -21,6 +21,7 @@ namespace {
 
 constexpr int LD = 260;              // row pitch (floats) of the activation tiles and of the weight chunk: 16-B aligned rows
 constexpr int RC = 16;               // reduction chunk
+constexpr int WS = 3;                // stages of the weight-chunk ring (cp.async)
 constexpr int HLD = 49;              // row pitch of the head matrix / logits tile (odd: conflict-free column walks)
 constexpr int NT = 256;              // threads of the weight-gradient / reduce kernels
 constexpr int FT = 512;              // threads of the fused kernel: 16 warps x 4 rows = one 64-row tile
@@ -28,7 +29,8 @@ constexpr int HW = 48;               // head matrix columns held in shared memor
 constexpr float PI_F = 3.14159265358979323846f;
 
 constexpr size_t FUSED_SMEM =
-    (size_t)(2 * MLP_TM * LD + RC * LD + MLP_MAX_HID * HLD + MLP_TM * HLD + 48 + 32) * sizeof(float);
+    (size_t)(2 * MLP_TM * LD + WS * RC * LD + MLP_MAX_HID * HLD + MLP_TM * HLD + 48 + 32) * sizeof(float);
+static_assert(FUSED_SMEM <= 232448, "shared memory budget of one CTA per SM");
 
 __device__ __forceinline__ int round_up16(int v) { return (v + 15) & ~15; }
 __device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + expf(-z)); }
@@ -53,7 +55,7 @@ __device__ __forceinline__ int head_b_index(const MlpNet& net, int j) {
 // Thread (ty = warp, tx = lane) owns rows ty*RT .. ty*RT+RT-1 (RT = 4: 64-row tiles; RT = 1: 16-row tiles for small
 // batches, where 64-row tiles would leave most SMs idle) and columns tx*4 .. tx*4+3 (+128 with JH = 2): 16 warps, four per
 // scheduler (two 8-row warps per scheduler left the FMA pipe idle 45 % of the time: nothing to switch to on a shared-memory
-// wait).  The weight chunk [16][<= 256] of step q0+16 is fetched into registers while chunk q0 is being consumed.
+// wait).
 // epi(r, c0, v[4]) receives the finished sums of 4 consecutive columns, turns them into what the next pass reads and
 // stores whatever goes to HBM; the result lands in out_s.  in_s must be zero (finite) up to round_up16(kred).
 template <bool TRANS, int JH, int RT, class Epi>
@@ -66,43 +68,55 @@ __device__ __forceinline__ void tile_pass(const float* in_s, float* out_s, float
 #pragma unroll
     for (int j = 0; j < 4 * JH; ++j) acc[i][j] = 0.f;
 
-  constexpr int PF = RC * 256 / FT;      // weight-chunk elements fetched per thread (8)
-  float pre[PF];
-  auto fetch = [&](int q0) {
+  // weight chunks travel global -> shared with cp.async through a ring of WS stages: chunk ci + WS - 1 is in flight while
+  // chunk ci is consumed (one block barrier per chunk).  16-byte copies along contiguous rows in the forward layout when the
+  // row pitch allows it, 4-byte copies otherwise and for the transposed (data-gradient) layout; out-of-range elements are
+  // zero-filled by the copy itself (src-size 0).
+  const bool vec = !TRANS && (ldw & 3) == 0 && (nout & 3) == 0;
+  auto issue = [&](int q0, int stage) {
+    float* dst = Wc + stage * (RC * LD);
     if (!TRANS) {
-      const int c = tid & 255, rh = tid >> 8;            // column c, chunk rows rh, rh + 2, ...
+      if (vec) {
 #pragma unroll
-      for (int i = 0; i < PF; ++i) {
-        const int rr = rh + 2 * i;
-        pre[i] = (q0 + rr < kred && c < nout) ? __ldg(Wg + (size_t)(q0 + rr) * ldw + c) : 0.f;
+        for (int i = 0; i < RC * 64 / FT; ++i) {           // 16 rows x 64 float4
+          const int idx = tid + FT * i, rr = idx >> 6, c = (idx & 63) * 4;
+          const bool ok = q0 + rr < kred && c < nout;
+          cp_async16(smem_u32(dst + rr * LD + c), Wg + (size_t)(ok ? q0 + rr : 0) * ldw + (ok ? c : 0), ok ? 16 : 0);
+        }
+      } else {
+        const int c = tid & 255, rh = tid >> 8;            // column c, chunk rows rh, rh + 2, ...
+#pragma unroll
+        for (int i = 0; i < RC * 256 / FT; ++i) {
+          const int rr = rh + 2 * i;
+          const bool ok = q0 + rr < kred && c < nout;
+          cp_async4(smem_u32(dst + rr * LD + c), Wg + (size_t)(ok ? q0 + rr : 0) * ldw + (ok ? c : 0), ok ? 4 : 0);
+        }
       }
     } else {
-      const int rr = tid & 15, cb = tid >> 4;            // 16 consecutive n of W row c: 64-byte segments
+      const int rr = tid & 15, cb = tid >> 4;              // 16 consecutive n of W row c: 64-byte segments
 #pragma unroll
-      for (int i = 0; i < PF; ++i) {
+      for (int i = 0; i < RC * 256 / FT; ++i) {
         const int c = cb + 32 * i;
-        pre[i] = (q0 + rr < kred && c < nout) ? __ldg(Wg + (size_t)c * ldw + q0 + rr) : 0.f;
+        const bool ok = q0 + rr < kred && c < nout;
+        cp_async4(smem_u32(dst + rr * LD + c), Wg + (size_t)(ok ? c : 0) * ldw + (ok ? q0 + rr : 0), ok ? 4 : 0);
       }
-    }
-  };
-  auto stash = [&]() {
-    if (!TRANS) {
-      const int c = tid & 255, rh = tid >> 8;
-#pragma unroll
-      for (int i = 0; i < PF; ++i) Wc[(rh + 2 * i) * LD + c] = pre[i];
-    } else {
-      const int rr = tid & 15, cb = tid >> 4;
-#pragma unroll
-      for (int i = 0; i < PF; ++i) Wc[rr * LD + cb + 32 * i] = pre[i];
     }
   };
 
-  fetch(0);
-  for (int q0 = 0; q0 < kred; q0 += RC) {
-    __syncthreads();                 // the previous chunk is consumed (first trip: in_s is complete)
-    stash();
-    __syncthreads();
-    if (q0 + RC < kred) fetch(q0 + RC);
+  const int nchunks = (kred + RC - 1) / RC;
+  __syncthreads();                   // in_s is complete and nobody still reads the ring (previous pass)
+#pragma unroll
+  for (int st = 0; st < WS - 1; ++st) {
+    if (st < nchunks) issue(st * RC, st);
+    cp_async_commit();
+  }
+  for (int ci = 0; ci < nchunks; ++ci) {
+    const int q0 = ci * RC;
+    cp_async_wait<WS - 2>();         // this thread's copies of chunk ci have landed ...
+    __syncthreads();                 // ... and everybody's; everybody is also done with chunk ci - 1, whose stage is refilled now
+    if (ci + WS - 1 < nchunks) issue((ci + WS - 1) * RC, (ci + WS - 1) % WS);
+    cp_async_commit();
+    const float* Wst = Wc + (ci % WS) * (RC * LD);
 #pragma unroll
     for (int q4 = 0; q4 < RC / 4; ++q4) {
       float4 a[RT];
@@ -112,7 +126,7 @@ __device__ __forceinline__ void tile_pass(const float* in_s, float* out_s, float
       for (int e = 0; e < 4; ++e) {
         float4 w[JH];
 #pragma unroll
-        for (int h = 0; h < JH; ++h) w[h] = *reinterpret_cast<const float4*>(Wc + (q4 * 4 + e) * LD + tx * 4 + 128 * h);
+        for (int h = 0; h < JH; ++h) w[h] = *reinterpret_cast<const float4*>(Wst + (q4 * 4 + e) * LD + tx * 4 + 128 * h);
 #pragma unroll
         for (int i = 0; i < RT; ++i) {
           const float av = e == 0 ? a[i].x : e == 1 ? a[i].y : e == 2 ? a[i].z : a[i].w;
@@ -159,7 +173,7 @@ __global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, cons
   float* buf0 = smem;
   float* buf1 = buf0 + MLP_TM * LD;
   float* Wc = buf1 + MLP_TM * LD;
-  float* Wh = Wc + RC * LD;                // [hid][HLD] head matrix, columns >= n_out zero
+  float* Wh = Wc + WS * RC * LD;           // [hid][HLD] head matrix, columns >= n_out zero
   float* lg = Wh + MLP_MAX_HID * HLD;      // [64][HLD] logits, then dlogits
   float* hb = lg + MLP_TM * HLD;           // [48] head biases
   float* red = hb + 48;                    // [8 warps][4] loss sums
