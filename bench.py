@@ -382,8 +382,6 @@ def run_ours(args, rank, local_rank, world):
     launches = net.launch_count() - l0
     ms_pred = timed(predict_step, K)
 
-    # ---- per-kernel durations, live, with events on the launch stream (roofline leg) ----
-    net.kernel_timing(K * 10)
     # spread: the same K steps timed in blocks of <= 10 (SURVEY 8d asks for median and best next to the mean)
     blocks = []
     done = 0
@@ -391,6 +389,9 @@ def run_ours(args, rank, local_rank, world):
         nb = min(10, K - done)
         blocks.append(timed(lambda i, d=done: train_step(d + i), nb) / nb)
         done += nb
+
+    # ---- per-kernel durations, live, with events on the launch stream (roofline leg) ----
+    net.kernel_timing(K * 10)
     ms_train_ev = timed(train_step, K)
     kt_train = net.kernel_times()
     net.kernel_timing(K * 3)
