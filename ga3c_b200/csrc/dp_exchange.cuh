@@ -40,10 +40,11 @@ __device__ __forceinline__ uint64_t dp_ld_flag(const void* p) {
 __device__ __forceinline__ void dp_st_flag(void* p, uint64_t v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
-// Every cross-rank wait is bounded (about a second of polling): a rank that died or was called a different number of times
-// must not hang the others' GPUs for ever.  On expiry the waiter raises the error word of its own comm block and carries on;
+// Every cross-rank wait is bounded (2^25 polls of local HBM, some tens of seconds: far beyond any legitimate skew between ranks
+// that train in lock step, short enough for a job to fail instead of hanging): a rank that died or was called a different
+// number of times must not hold the others' GPUs for ever.  On expiry the waiter raises the error word of its own comm block and carries on;
 // the host sees it through ga3c_dp_error (results of that step are garbage).
-constexpr unsigned int DP_SPIN_LIMIT = 1u << 22;
+constexpr unsigned int DP_SPIN_LIMIT = 1u << 25;
 // error bits: 1 "gradients ready" (single-kernel exchange), 2 "done" (single-kernel), 4 dense_bwd-done flags of the
 // exchange CTAs, 8 small-tensor LL data, 16 dense1/w slices landed
 __device__ __forceinline__ void dp_wait_flag(const void* p, unsigned long long want, void* err, unsigned int bit) {

@@ -135,7 +135,7 @@ int ga3c_dp_detach(ga3c_net* net);
 /* ranks living in one process (one host process driving several GPUs, or tests with two handles on one GPU): peers[r] is
  * rank r's handle, peers[rank] == net; the slabs are addressed directly, no IPC handles. */
 int ga3c_dp_attach_local(ga3c_net* net, int32_t rank, int32_t world, ga3c_net* const* peers);
-/* Every cross-rank wait inside the exchange kernels is bounded (about a second).  *error_out != 0 (a mask of the wait sites, dp_exchange.cuh) if one of them gave up since
+/* Every cross-rank wait inside the exchange kernels is bounded (some tens of seconds).  *error_out != 0 (a mask of the wait sites, dp_exchange.cuh) if one of them gave up since
  * the last attach: a rank died or the ranks' train calls fell out of step; the weights can no longer be trusted.  Synchronises. */
 int ga3c_dp_error(ga3c_net* net, int32_t* error_out);
 
