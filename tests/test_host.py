@@ -43,6 +43,32 @@ def test_header_compiles_as_plain_c(tmp_path):
                     str(exe)], check=True)
 
 
+def test_config_struct_layouts_match_the_ctypes_binding(tmp_path):
+    """The C structs of include/ga3c_b200.h and their ctypes mirrors (ga3c_b200/_capi.py) must agree field by field: a
+    silent mismatch would hand the library shifted knobs.  A gcc-compiled probe prints sizeof / offsetof."""
+    import ctypes as C
+    import subprocess
+    from ga3c_b200 import _capi
+    fields = {"ga3c_config": [f for f, _ in _capi.ga3c_config._fields_],
+              "ga3c_mlp_config": [f for f, _ in _capi.ga3c_mlp_config._fields_]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ga3c_b200.h"', 'int main(void){']
+    for st, fs in fields.items():
+        lines.append(f'printf("{st} %zu\\n", sizeof({st}));')
+        for f in fs:
+            lines.append(f'printf("{st}.{f} %zu\\n", offsetof({st}, {f}));')
+    lines.append('return 0;}')
+    c = tmp_path / "probe.c"
+    c.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for st, fs in fields.items():
+        cls = getattr(_capi, st)
+        assert int(out[st]) == C.sizeof(cls), (st, out[st], C.sizeof(cls))
+        for f in fs:
+            assert int(out[f"{st}.{f}"]) == getattr(cls, f).offset, (st, f)
+
+
 def test_no_cpu_fallback_without_gpu():
     """On a box without a GPU constructing a Network must fail loudly, not fall back."""
     import torch
