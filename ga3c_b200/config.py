@@ -36,6 +36,9 @@ class Config:
     MIN_POLICY = 0.0
     USE_LOG_SOFTMAX = False
 
+    # low-dimensional networks -- Config.py:107 (NetworkVP_discrate builds one dense layer per entry, every one from x)
+    DENSE_LAYERS = (10, 10, 10, 10)
+
     # optimizer -- Config.py:111-120, :194-195
     RMSPROP_DECAY = 0.99
     RMSPROP_MOMENTUM = 0.0

@@ -27,25 +27,25 @@ FORK_VP_LAYERS = (("dense11_p", 4, "linear"), ("dense12_p", 256, "linear"), ("de
 DISCRATE_DENSE_LAYERS = (10, 10, 10, 10)                                          # Config.py:107
 
 
-def layers_of(kind: str):
-    """Live hidden layers (name, width, activation) in forward order."""
+def layers_of(kind: str, dense_layers=DISCRATE_DENSE_LAYERS):
+    """Live hidden layers (name, width, activation) in forward order; dense_layers = Config.DENSE_LAYERS ('discrate' only)."""
     if kind == "fork_vp":
         return FORK_VP_LAYERS
     if kind == "discrate":
-        n = len(DISCRATE_DENSE_LAYERS)
-        return ((f"dense1_{n}_p", DISCRATE_DENSE_LAYERS[-1], "sigmoid"),)          # NetworkVP_discrate.py:53-56
+        n = len(dense_layers)
+        return ((f"dense1_{n}_p", dense_layers[-1], "sigmoid"),)                    # NetworkVP_discrate.py:53-56
     raise ValueError(kind)
 
 
-def param_shapes(kind: str, state_dim: int, num_actions: int):
+def param_shapes(kind: str, state_dim: int, num_actions: int, dense_layers=DISCRATE_DENSE_LAYERS):
     """TF variable names in creation order -> shapes (dead 'discrate' layers included)."""
     shapes = {}
     if kind == "discrate":
-        for i, w in enumerate(DISCRATE_DENSE_LAYERS[:-1]):
+        for i, w in enumerate(dense_layers[:-1]):
             shapes[f"dense1_{i + 1}_p/w:0"] = (state_dim, w)
             shapes[f"dense1_{i + 1}_p/b:0"] = (w,)
     fan = state_dim
-    for name, width, _ in layers_of(kind):
+    for name, width, _ in layers_of(kind, dense_layers):
         shapes[f"{name}/w:0"] = (fan, width)
         shapes[f"{name}/b:0"] = (width,)
         fan = width
@@ -61,27 +61,29 @@ def param_shapes(kind: str, state_dim: int, num_actions: int):
     return shapes
 
 
-def dead_params(kind: str):
+def dead_params(kind: str, dense_layers=DISCRATE_DENSE_LAYERS):
     """Variables that exist in the graph but receive no gradient (kept at their initial values)."""
     if kind != "discrate":
         return ()
-    return tuple(f"dense1_{i + 1}_p/{t}:0" for i in range(len(DISCRATE_DENSE_LAYERS) - 1) for t in ("w", "b"))
+    return tuple(f"dense1_{i + 1}_p/{t}:0" for i in range(len(dense_layers) - 1) for t in ("w", "b"))
 
 
-def init_params(rng: np.random.Generator, kind: str, state_dim: int, num_actions: int):
-    return {k: rng.uniform(-0.3, 0.3, size=s).astype(np.float32) for k, s in param_shapes(kind, state_dim, num_actions).items()}
+def init_params(rng: np.random.Generator, kind: str, state_dim: int, num_actions: int, dense_layers=DISCRATE_DENSE_LAYERS):
+    return {k: rng.uniform(-0.3, 0.3, size=s).astype(np.float32)
+            for k, s in param_shapes(kind, state_dim, num_actions, dense_layers).items()}
 
 
 def _sigmoid(z):
     return 1.0 / (1.0 + np.exp(-z))
 
 
-def forward(params, x, kind: str, *, dtype=np.float64, min_policy=0.0, keep=False, use_log_softmax=False):
+def forward(params, x, kind: str, *, dtype=np.float64, min_policy=0.0, keep=False, use_log_softmax=False,
+            dense_layers=DISCRATE_DENSE_LAYERS):
     """-> p [B,A], v [B] (and the activations with keep=True)."""
     P = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
     h = np.asarray(x, dtype=dtype)
     acts = [h]
-    for name, _, act in layers_of(kind):
+    for name, _, act in layers_of(kind, dense_layers):
         z = h @ P[f"{name}/w:0"] + P[f"{name}/b:0"]
         h = _sigmoid(z) if act == "sigmoid" else z
         acts.append(h)
@@ -105,12 +107,13 @@ def forward(params, x, kind: str, *, dtype=np.float64, min_policy=0.0, keep=Fals
 
 
 def loss_and_grads(params, x, y_r, a, kind: str, *, beta=0.01, log_eps=1e-6, min_policy=0.0, dtype=np.float64,
-                   use_log_softmax=False, part="all"):
+                   use_log_softmax=False, part="all", dense_layers=DISCRATE_DENSE_LAYERS):
     """-> ({cost_p_1, cost_p_2, cost_p, cost_v, cost_all}, {name: grad}) ; dead variables get no entry."""
     P = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
     y_r = np.asarray(y_r, dtype=dtype)
     a = np.asarray(a, dtype=dtype)
-    p, v, f = forward(params, x, kind, dtype=dtype, min_policy=min_policy, keep=True, use_log_softmax=use_log_softmax)
+    p, v, f = forward(params, x, kind, dtype=dtype, min_policy=min_policy, keep=True, use_log_softmax=use_log_softmax,
+                      dense_layers=dense_layers)
     adv = y_r - v                                   # stop_gradient(v) inside cost_p_1
     cost_v = 0.5 * np.sum((y_r - v) ** 2)
     dv = v - y_r
@@ -161,7 +164,7 @@ def loss_and_grads(params, x, y_r, a, kind: str, *, beta=0.01, log_eps=1e-6, min
     grads["logits_v/w:0"] = h.T @ dv[:, None]
     grads["logits_v/b:0"] = np.array([dv.sum()], dtype=dtype)
     dh = dh + dv[:, None] @ P["logits_v/w:0"].T
-    layers = layers_of(kind)
+    layers = layers_of(kind, dense_layers)
     for i in range(len(layers) - 1, -1, -1):
         name, _, act = layers[i]
         out, inp = f["acts"][i + 1], f["acts"][i]
@@ -178,10 +181,11 @@ def loss_and_grads(params, x, y_r, a, kind: str, *, beta=0.01, log_eps=1e-6, min
 
 
 def train_step(params, ms, mom, x, y_r, a, kind: str, *, lr, beta=0.01, log_eps=1e-6, min_policy=0.0,
-               rho=0.99, mu=0.0, eps=0.1, dtype=np.float32, grad_clip=None):
+               rho=0.99, mu=0.0, eps=0.1, dtype=np.float32, grad_clip=None, dense_layers=DISCRATE_DENSE_LAYERS):
     """One opt.minimize step; dead variables and their slots are left untouched.  -> (losses, grads, params', ms', mom')"""
     from . import oracle_np as onp
-    losses, grads = loss_and_grads(params, x, y_r, a, kind, beta=beta, log_eps=log_eps, min_policy=min_policy, dtype=np.float64)
+    losses, grads = loss_and_grads(params, x, y_r, a, kind, beta=beta, log_eps=log_eps, min_policy=min_policy, dtype=np.float64,
+                                   dense_layers=dense_layers)
     live = {k: params[k] for k in grads}
     if grad_clip is not None:              # tf.clip_by_average_norm per variable (NetworkVP.py:138-141)
         if len(grads) != len(params):

@@ -181,16 +181,9 @@ def test_grad_clip_knob(mlp):
         ref_mom = {k: np.zeros_like(v) for k, v in params.items()}
         for _ in range(2):
             net.train(x, y_r, act, None, None, 0)
-            if kind == "fork_vp":
-                _, grads, ref_p, ref_ms, ref_mom = om.train_step(ref_p, ref_ms, ref_mom, x, y_r, act, kind, lr=3e-4, grad_clip=clip)
-            else:          # oracle_mlp's 'discrate' is the default 4-layer graph; restate the single live layer by renaming
-                q = {k.replace("dense1_1_p", "dense1_4_p"): v for k, v in ref_p.items()}
-                qms = {k.replace("dense1_1_p", "dense1_4_p"): v for k, v in ref_ms.items()}
-                qmom = {k.replace("dense1_1_p", "dense1_4_p"): v for k, v in ref_mom.items()}
-                _, grads, q, qms, qmom = om.train_step(q, qms, qmom, x, y_r, act, kind, lr=3e-4, grad_clip=clip)
-                ref_p, ref_ms, ref_mom = ({k.replace("dense1_4_p", "dense1_1_p"): v for k, v in d.items()} for d in (q, qms, qmom))
-        p0 = params if kind == "fork_vp" else {k.replace("dense1_1_p", "dense1_4_p"): v for k, v in params.items()}
-        _, raw = om.loss_and_grads(p0, x, y_r, act, kind)               # un-clipped gradients at the initial weights
+            _, grads, ref_p, ref_ms, ref_mom = om.train_step(ref_p, ref_ms, ref_mom, x, y_r, act, kind, lr=3e-4, grad_clip=clip,
+                                                             dense_layers=cfg.DENSE_LAYERS)
+        _, raw = om.loss_and_grads(params, x, y_r, act, kind, dense_layers=cfg.DENSE_LAYERS)   # un-clipped, initial weights
         avg = [np.sqrt((g.astype(np.float64) ** 2).sum()) / g.size for g in raw.values()]
         assert max(avg) > clip, avg                                     # the threshold is active
         w = net.get_variables()
