@@ -113,6 +113,23 @@ class SlabPredictionQueue:
         self._pending.array[aid] = 1
         self._work.release()
 
+    def post_many(self, aids, states):
+        """A process that hosts several agents posts one request per agent in one go: rows states[i] -> agent aids[i].
+        One wake-up for the whole group (the consumer takes every pending row it sees)."""
+        self._states.array[aids] = states
+        self._pending.array[aids] = 1
+        self._work.release()
+
+    def wait_many(self, aids, p_out, v_out, timeout=None, start=0):
+        """Waits for the replies of aids[start:], in order.  Returns how many of `aids` have been collected so far: len(aids)
+        when all replies are in (p_out[i], v_out[i] filled), less after a time-out -- call again with start = that number."""
+        for i in range(start, len(aids)):
+            if not self._wake[int(aids[i])].acquire(True, timeout):
+                return i
+        p_out[...] = self._reply_p.array[aids]
+        v_out[...] = self._reply_v.array[aids]
+        return len(aids)
+
     def wait_q(self, aid):
         return SlabReplySlot(self, aid)
 

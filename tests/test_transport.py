@@ -74,6 +74,30 @@ def test_prediction_queue_contract_single_process():
         q.close()
 
 
+def test_vector_posts_and_waits():
+    """post_many / wait_many: a process hosting several agents posts and collects for all of them in one call each."""
+    q = SlabPredictionQueue(6, S, A, ctx=CTX)
+    try:
+        aids = np.array([4, 1, 5])
+        states = np.stack([np.full(S, i, np.float32) for i in aids])
+        q.post_many(aids, states)
+        buf = np.zeros((6, S), np.float32)
+        ids = q.get_batch(6, buf)
+        assert sorted(ids.tolist()) == [1, 4, 5] and all(buf[k, 0] == i for k, i in enumerate(ids))
+        p_out, v_out = np.zeros((3, A), np.float32), np.zeros(3, np.float32)
+        assert q.wait_many(aids, p_out, v_out, timeout=0.01) == 0         # nothing replied yet
+        q.reply_batch(np.array([4]), np.full((1, A), 4, np.float32), np.array([40], np.float32))
+        got = q.wait_many(aids, p_out, v_out, timeout=0.01)               # agent 4 collected, agent 1 still out: resumable
+        assert got == 1
+        rest = np.array([1, 5])
+        q.reply_batch(rest, np.stack([np.full(A, i, np.float32) for i in rest]), rest.astype(np.float32) * 10)
+        assert q.wait_many(aids, p_out, v_out, timeout=1, start=got) == 3
+        assert np.array_equal(p_out[:, 0], aids) and np.array_equal(v_out, aids * 10.0)
+        assert q.get_batch(6, buf, timeout=0.01) is None
+    finally:
+        q.close()
+
+
 def test_training_queue_contract_and_backpressure():
     tq = SlabTrainingQueue(2, max_rows=6, state_dim=S, num_actions=A, blocks_per_agent=2, ctx=CTX)
     try:

@@ -77,6 +77,49 @@ def agent_worker(wid, aids, pq, tq, wait_qs, stop, counters, uint8, seed):
         counters[2 * wid + 1] = n_train
 
 
+def agent_worker_vec(wid, aids, pq, tq, stop, counters, uint8, seed):
+    """The same agents, stepped as a vector by one process (slab transport only): one gather of k frames, one post, one wait,
+    inverse-CDF sampling for all k agents at once (what np.random.choice does per agent: searchsorted(cumsum(p), u))."""
+    rng = np.random.default_rng(seed)
+    pool = rng.integers(0, 256, size=(32, S), dtype=np.uint8)
+    if not uint8:
+        pool = pool.astype(np.float32) / np.float32(128.0) - np.float32(1.0)
+    aids = np.asarray(aids)
+    k = len(aids)
+    xs = np.zeros((T_MAX, k, S), dtype=pool.dtype)
+    acts = np.zeros((T_MAX, k), dtype=np.int64)
+    p = np.zeros((k, A), np.float32)
+    v = np.zeros(k, np.float32)
+    eye = np.eye(A, dtype=np.float32)
+    disc = GAMMA ** np.arange(T_MAX - 1, -1, -1, dtype=np.float64)
+    done = np.zeros(T_MAX, dtype=bool)
+    tqs = [tq.for_agent(int(a)) for a in aids]
+    parent = os.getppid()
+    t = 0
+    n_pred = n_train = 0
+    while not stop.value and os.getppid() == parent:
+        np.take(pool, rng.integers(0, 32, size=k), axis=0, out=xs[t])
+        pq.post_many(aids, xs[t])
+        got = 0
+        while got < k:
+            got = pq.wait_many(aids, p, v, timeout=1.0, start=got)
+            if got < k and (stop.value or os.getppid() != parent):
+                return
+        cdf = np.cumsum(p.astype(np.float64), axis=1)
+        cdf /= cdf[:, -1:]
+        acts[t] = np.minimum((cdf <= rng.random(k)[:, None]).sum(axis=1), A - 1)          # searchsorted(cdf, u, side='right')
+        n_pred += k
+        t += 1
+        if t == T_MAX:
+            r_last = rng.uniform(-1, 1, size=k)
+            for j in range(k):
+                tqs[j].put((xs[:, j], disc * r_last[j], eye[acts[:, j]], xs[:, j], done))
+            n_train += k * T_MAX
+            t = 0
+        counters[2 * wid] = n_pred
+        counters[2 * wid + 1] = n_train
+
+
 class MiniServer:
     """The three attributes the thread classes use (Server.py:70-150)."""
 
@@ -103,6 +146,8 @@ def main():
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--transport", default="slab", choices=["slab", "queue"])
     ap.add_argument("--uint8", action="store_true", help="agents ship raw uint8 frames (SURVEY 8f F2)")
+    ap.add_argument("--vector-agents", action="store_true",
+                    help="each agent process steps its agents as one numpy vector (slab transport only)")
     ap.add_argument("--predictors", type=int, default=2)
     ap.add_argument("--trainers", type=int, default=2)
     ap.add_argument("--min-train-batch", type=int, default=512, help="Config.TRAINING_MIN_BATCH_SIZE")
@@ -121,9 +166,13 @@ def main():
         pq = SlabPredictionQueue(args.agents, S, A, dtype=dtype, ctx=ctx)
         tq = SlabTrainingQueue(args.agents, T_MAX, S, A, blocks_per_agent=2, dtype=dtype, ctx=ctx)
         agents = []
-        workers = [ctx.Process(target=agent_worker, daemon=True,
-                               args=(w, g, pq, [tq.for_agent(a) for a in g], [pq.wait_q(a) for a in g], stop, counters,
-                                     args.uint8, 1000 * rank + w)) for w, g in enumerate(groups)]
+        if args.vector_agents:
+            workers = [ctx.Process(target=agent_worker_vec, daemon=True,
+                                   args=(w, g, pq, tq, stop, counters, args.uint8, 1000 * rank + w)) for w, g in enumerate(groups)]
+        else:
+            workers = [ctx.Process(target=agent_worker, daemon=True,
+                                   args=(w, g, pq, [tq.for_agent(a) for a in g], [pq.wait_q(a) for a in g], stop, counters,
+                                         args.uint8, 1000 * rank + w)) for w, g in enumerate(groups)]
     else:
         pq, tq = ctx.Queue(maxsize=100), ctx.Queue(maxsize=100)                  # Config.MAX_QUEUE_SIZE
         wait = [ctx.Queue(maxsize=1) for _ in range(args.agents)]
@@ -174,7 +223,7 @@ def main():
         res["job_pps"], res["job_tps_frames"] = float(t[0]), float(t[1])
     if rank == 0:
         out = {"config": f"{args.agents} synthetic agents per GPU in {procs_n} processes, transport={args.transport}, "
-                         f"frames={'uint8' if args.uint8 else 'fp32'}, T_MAX={T_MAX}, predictors={args.predictors}, "
+                         f"frames={'uint8' if args.uint8 else 'fp32'}, {'vectorised agent processes, ' if args.vector_agents else ''}T_MAX={T_MAX}, predictors={args.predictors}, "
                          f"trainers={args.trainers}, TRAINING_MIN_BATCH_SIZE={args.min_train_batch}, {os.cpu_count()} host cores",
                "n_gpus": world, "seconds": round(dt, 2), **{k: round(v, 1) for k, v in res.items()}}
         print(json.dumps(out), flush=True)
