@@ -118,7 +118,8 @@ class SlabPredictionQueue:
         One wake-up for the whole group (the consumer takes every pending row it sees)."""
         self._states.array[aids] = states
         self._pending.array[aids] = 1
-        self._work.release()
+        for _ in range(len(aids)):          # one permit per request, as put() does: consumers return one permit per row taken
+            self._work.release()
 
     def wait_many(self, aids, p_out, v_out, timeout=None, start=0):
         """Waits for the replies of aids[start:], in order.  Returns how many of `aids` have been collected so far: len(aids)
@@ -151,12 +152,20 @@ class SlabPredictionQueue:
         self._cursor = (int(idx[-1]) + 1) % self.num_agents
         return idx
 
+    _POLL = 0.05       # the semaphore is a wake-up hint: a consumer also looks at the bytes every _POLL seconds, so a lost or
+                       # stolen permit costs latency, never a request
+
     def get(self, block=True, timeout=None):
         """-> (agent_id, state copy).  Blocks like Queue.get()."""
+        import queue
+        import time
+        deadline = None if timeout is None else time.monotonic() + timeout
         while True:
-            if not self._work.acquire(block, timeout):
-                import queue
-                raise queue.Empty
+            if block:
+                left = self._POLL if deadline is None else max(0.0, min(self._POLL, deadline - time.monotonic()))
+                self._work.acquire(True, left)
+            else:
+                self._work.acquire(False)
             with self._lock:
                 idx = self._take(1)
                 if idx.size:
@@ -164,23 +173,28 @@ class SlabPredictionQueue:
                     state = self._states.array[aid].copy()
                     self._pending.array[aid] = 0
                     return aid, state
-            # a request seen (and served) by get_batch before its semaphore post arrived: spurious wake-up
+            if not block or (deadline is not None and time.monotonic() >= deadline):
+                raise queue.Empty
 
     def get_batch(self, max_n, out_states, timeout=None):
         """Blocks for the first request, then takes whatever is pending (at most max_n, ThreadPredictor.py:50-55): gathers
         the rows into out_states[:n] and returns the agent ids (int array of length n >= 1), or None on timeout."""
+        import time
+        deadline = None if timeout is None else time.monotonic() + timeout
         while True:
-            if not self._work.acquire(True, timeout):
-                return None
+            left = self._POLL if deadline is None else max(0.0, min(self._POLL, deadline - time.monotonic()))
+            got = self._work.acquire(True, left)
             with self._lock:
                 idx = self._take(max_n)
-                if idx.size == 0:
-                    continue
-                np.take(self._states.array, idx, axis=0, out=out_states[:idx.size])
-                self._pending.array[idx] = 0
-            for _ in range(idx.size - 1):               # keep the semaphore in step with the bytes (best effort)
-                self._work.acquire(False)
-            return idx
+                if idx.size:
+                    np.take(self._states.array, idx, axis=0, out=out_states[:idx.size])
+                    self._pending.array[idx] = 0
+            if idx.size:
+                for _ in range(idx.size - (1 if got else 0)):       # one permit per row taken (best effort)
+                    self._work.acquire(False)
+                return idx
+            if deadline is not None and time.monotonic() >= deadline:
+                return None
 
     def reply_batch(self, ids, p, v):
         """(p[i], v[i]) to agent ids[i]'s wait_q, for a whole batch."""
