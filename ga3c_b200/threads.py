@@ -100,7 +100,34 @@ class ThreadTrainer(Thread):
             return parts[0]
         return tuple(np.concatenate([p[k] for p in parts]) for k in range(5))
 
+    def _run_slab(self, q):
+        """Batch call of ga3c_b200.transport.SlabTrainingQueue: the agents' blocks are gathered straight into pinned arrays
+        (which Network.train copies to the device without another host pass) until the row count exceeds
+        TRAINING_MIN_BATCH_SIZE, exactly where the reference stops concatenating (ThreadTrainer.py:49)."""
+        min_rows = self.config.TRAINING_MIN_BATCH_SIZE
+        cap = min_rows + q.max_rows
+        dtype = q._x.array.dtype
+        try:
+            import torch
+            pin = torch.cuda.is_available()
+            x = torch.empty((cap, q.state_dim), dtype=torch.uint8 if dtype == np.uint8 else torch.float32, pin_memory=pin).numpy()
+        except Exception:
+            x = np.zeros((cap, q.state_dim), dtype=dtype)
+        r = np.zeros(cap, dtype=np.float64)
+        a = np.zeros((cap, q.num_actions), dtype=np.float32)
+        done = np.zeros(cap, dtype=np.bool_)
+        x2 = np.zeros((cap, 0), dtype=dtype)          # the A3C networks ignore next_state (NetworkVP.py:254-257)
+        while not self.exit_flag:
+            n = q.get_batch(min_rows, x, r, a, done, timeout=0.05, stop=lambda: self.exit_flag)
+            if n is None or self.exit_flag:
+                continue
+            if self.config.TRAIN_MODELS:
+                self.server.train_model(x[:n], r[:n], a[:n], x2[:n], done[:n], self.id)
+
     def run(self):
+        q = self.server.training_q
+        if hasattr(q, "get_batch") and not getattr(self.config, "USE_REPLAY_MEMORY", False) and not q.ship_next_state:
+            return self._run_slab(q)
         while not self.exit_flag:
             if getattr(self.config, "USE_REPLAY_MEMORY", False):
                 x, a, r, done, x2 = self.server.replay_q.get()     # ThreadTrainer.py:45-46 (DDPG only)

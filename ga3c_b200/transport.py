@@ -296,23 +296,72 @@ class SlabTrainingQueue:
 
     def get(self, block=True, timeout=None):
         """-> (x_, r_, a_, x2_, done_) copies, like Queue.get()."""
+        import queue
+        import time
+        deadline = None if timeout is None else time.monotonic() + timeout
         while True:
-            if not self._work.acquire(block, timeout):
-                import queue
-                raise queue.Empty
+            if block:
+                self._work.acquire(True, 0.05 if deadline is None else max(0.0, min(0.05, deadline - time.monotonic())))
+            else:
+                self._work.acquire(False)
+            item = None
             with self._lock:
                 idx = np.flatnonzero(self._posted.array.copy())     # snapshot (see SlabPredictionQueue._take)
-                if idx.size == 0:
-                    continue
-                k = int(np.searchsorted(idx, self._cursor)) % idx.size
-                b = int(idx[k])
-                self._cursor = (b + 1) % self._posted.array.size
-                n = int(self._rows.array[b])
-                item = (self._x.array[b, :n].copy(), self._r.array[b, :n].copy(), self._a.array[b, :n].copy(),
-                        self._x2.array[b, :n].copy(), self._done.array[b, :n].copy())
-                self._posted.array[b] = 0
-            self._free[b // self.blocks].release()
-            return item
+                if idx.size:
+                    k = int(np.searchsorted(idx, self._cursor)) % idx.size
+                    b = int(idx[k])
+                    self._cursor = (b + 1) % self._posted.array.size
+                    n = int(self._rows.array[b])
+                    item = (self._x.array[b, :n].copy(), self._r.array[b, :n].copy(), self._a.array[b, :n].copy(),
+                            self._x2.array[b, :n].copy(), self._done.array[b, :n].copy())
+                    self._posted.array[b] = 0
+            if item is not None:
+                self._free[b // self.blocks].release()
+                return item
+            if not block or (deadline is not None and time.monotonic() >= deadline):
+                raise queue.Empty
+
+    def get_batch(self, min_rows, x_out, r_out, a_out, done_out, timeout=None, stop=None):
+        """ThreadTrainer.py:48-59 in one call: blocks for the first item, then keeps taking posted blocks until the row count
+        EXCEEDS min_rows (the reference loops `while batch_size <= TRAINING_MIN_BATCH_SIZE`, however long that takes), copying
+        the rows straight into the caller's (pinned) arrays -- one copy per row instead of get() + np.concatenate + staging.
+        Stops early when the next block would not fit x_out.  `timeout` bounds the wait for the FIRST item only (None is
+        returned when nothing arrived); `stop()` is polled every 50 ms and ends the call with the rows gathered so far."""
+        import time
+        deadline = None if timeout is None else time.monotonic() + timeout
+        cap, n = x_out.shape[0], 0
+        while True:
+            left = 0.05 if deadline is None else max(0.0, min(0.05, deadline - time.monotonic()))
+            got = self._work.acquire(True, left)
+            taken = 0
+            with self._lock:
+                idx = np.flatnonzero(self._posted.array.copy())
+                if idx.size:
+                    k = int(np.searchsorted(idx, self._cursor)) % idx.size
+                    for b in np.concatenate((idx[k:], idx[:k])):
+                        b = int(b)
+                        rows = int(self._rows.array[b])
+                        if n + rows > cap:
+                            break
+                        x_out[n:n + rows] = self._x.array[b, :rows]
+                        r_out[n:n + rows] = self._r.array[b, :rows]
+                        a_out[n:n + rows] = self._a.array[b, :rows]
+                        done_out[n:n + rows] = self._done.array[b, :rows]
+                        self._posted.array[b] = 0
+                        self._free[b // self.blocks].release()
+                        self._cursor = (b + 1) % self._posted.array.size
+                        n += rows
+                        taken += 1
+                        if n > min_rows:
+                            break
+            for _ in range(taken - (1 if got else 0)):          # one permit per block taken (best effort, see get_batch above)
+                self._work.acquire(False)
+            if n > min_rows or (n > 0 and taken == 0 and idx.size > 0):    # enough rows, or the next block does not fit
+                return n
+            if n == 0 and deadline is not None and time.monotonic() >= deadline:
+                return None
+            if stop is not None and stop():
+                return n if n else None
 
     def close(self):
         for s in (self._x, self._x2, self._r, self._a, self._done, self._rows, self._posted):

@@ -124,6 +124,30 @@ def test_training_queue_contract_and_backpressure():
         tq.close()
 
 
+def test_training_queue_get_batch_follows_the_reference_stop_rule():
+    """get_batch: rows are gathered until the count EXCEEDS min_rows (ThreadTrainer.py:49), never beyond the buffer."""
+    tq = SlabTrainingQueue(4, max_rows=5, state_dim=S, num_actions=A, blocks_per_agent=2, ctx=CTX)
+    try:
+        x = np.zeros((12, S), np.float32); r = np.zeros(12); a = np.zeros((12, A), np.float32); d = np.zeros(12, bool)
+        assert tq.get_batch(6, x, r, a, d, timeout=0.02) is None
+        for aid in range(4):
+            n = 3
+            tq.for_agent(aid).put((np.full((n, S), aid, np.float32), np.full(n, aid, np.float64),
+                                   np.eye(A, dtype=np.float32)[[aid % A] * n], None, np.zeros(n, bool)))
+        n = tq.get_batch(6, x, r, a, d, timeout=1)
+        assert n == 9 and sorted(set(r[:n].tolist())) == [0.0, 1.0, 2.0]      # 3 + 3 = 6 does not exceed 6: a third block is taken
+        assert np.array_equal(x[:n, 0], r[:n]) and np.all(a[:n].sum(axis=1) == 1)
+        t0 = time.time()                                                      # one block left: the call keeps waiting for more rows,
+        n = tq.get_batch(6, x, r, a, d, timeout=1, stop=lambda: time.time() - t0 > 0.2)   # as the reference would, until told to stop
+        assert n == 3 and r[0] == 3.0 and tq.empty()
+        for aid in range(4):                                                  # blocks were handed back to their owners
+            tq.for_agent(aid).put((np.zeros((5, S), np.float32), np.zeros(5), np.zeros((5, A), np.float32), None, np.zeros(5, bool)), timeout=1)
+        small = np.zeros((7, S), np.float32)
+        assert tq.get_batch(100, small, r, a, d, timeout=1) == 5              # the second block would not fit 7 rows
+    finally:
+        tq.close()
+
+
 def _agent_proc(aid, pq, tq, n_steps, t_max, out):
     """A ProcessAgent-shaped loop (ProcessAgent.py:102-107, :117-176): predict every step, ship experiences every t_max."""
     rng = np.random.default_rng(aid)
