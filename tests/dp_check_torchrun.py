@@ -1,4 +1,5 @@
-"""Data-parallel parity check, one rank per GPU (launch with torchrun): every rank trains on its row
+"""Test infrastructure (imports the oracle as the checker; launched by tests/test_gpu_parity.py on boxes with >= 2 GPUs, or by hand).
+Data-parallel parity check, one rank per GPU (launch with torchrun): every rank trains on its row
 shard of one global batch; afterwards (1) all replicas hold bit-identical weights and (2) they match
 the oracle's single-process step on the concatenated batch.  Prints 'DP_CHECK OK' on rank 0."""
 import os, sys

@@ -645,6 +645,6 @@ def test_data_parallel_two_gpus_matches_concatenated_batch(ga3c):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (covered on CPU by tests/test_dataparallel.py with gloo)")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tools", "dp_check.py")],
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "dp_check_torchrun.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DP_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -1,6 +1,6 @@
 #!/bin/bash
 # quick GPU iteration: per-layer parity at a few batch sizes, then the bench (no CPU leg), short summary
-timeout 300 python tools/gpu_debug.py 3 33 300 > gpurun_out/debug_iter.log 2>&1; echo "debug rc=$?"
+timeout 300 python tests/gpu_layer_report.py 3 33 300 > gpurun_out/debug_iter.log 2>&1; echo "debug rc=$?"
 grep -E "^---|  p  |  v  |n1 |n2 |dn1|dn2|grad/conv11/w|grad/conv12/w|grad/dense1/w" gpurun_out/debug_iter.log | awk '{printf "%s ", $0; if (NR%10==0) print ""}'; echo
 timeout 400 python bench.py --no-cpu-baseline "$@" > gpurun_out/bench_iter.json 2> gpurun_out/bench_iter.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_iter.err
 python - <<PY
