@@ -203,6 +203,43 @@ def test_agents_in_processes_through_predictor_and_trainer_threads():
         pq.close(); tq.close()
 
 
+def test_trainer_batches_equal_over_queue_and_slab():
+    """The slab batch path of ThreadTrainer forms the same batches as the queue path (= the reference rule: concatenate until
+    the row count exceeds TRAINING_MIN_BATCH_SIZE) from the same item stream."""
+    from ga3c_b200 import Config
+
+    class Cfg(Config):
+        TRAINING_MIN_BATCH_SIZE = 7
+    rng = np.random.default_rng(4)
+    items = []
+    for i in range(9):
+        n = int(rng.integers(1, 5))
+        items.append((rng.random((n, S), dtype=np.float32), rng.random(n), np.eye(A, dtype=np.float32)[rng.integers(0, A, n)],
+                      np.zeros((n, 0), np.float32), rng.random(n) < 0.5))
+    results = {}
+    for mode in ("queue", "slab"):
+        tq = queue.Queue() if mode == "queue" else SlabTrainingQueue(1, max_rows=4, state_dim=S, num_actions=A, blocks_per_agent=16, ctx=CTX)
+        server = FakeServer(tq)
+        th = ThreadTrainer(server, 0, config=Cfg)
+        th.start()
+        put = tq.put if mode == "queue" else tq.for_agent(0).put
+        for it in items:                       # one producer, in order: the slab ring keeps the order of a single agent
+            put(it)
+        deadline = time.time() + 5
+        while sum(t[0].shape[0] for t in server.trained) < sum(it[0].shape[0] for it in items) - 7 and time.time() < deadline:
+            time.sleep(0.01)
+        th.exit_flag = True
+        time.sleep(0.15)
+        results[mode] = server.trained
+        if mode == "slab":
+            tq.close()
+    q, s_ = results["queue"], results["slab"]
+    assert len(q) >= 2 and len(s_) >= len(q)
+    for bq, bs in zip(q, s_):                  # full batches are identical; only a trailing partial batch may differ (stop flag)
+        assert bq[0].shape[0] > 7
+        assert np.array_equal(bq[0], bs[0]) and np.array_equal(bq[1], bs[1]) and np.array_equal(bq[2], bs[2]) and np.array_equal(bq[4], bs[4])
+
+
 @pytest.mark.reference
 def test_reference_threads_run_unmodified_over_the_slab_queues():
     """The reference's own ThreadPredictor / ThreadTrainer (imported from /root/reference) over the slab objects."""
