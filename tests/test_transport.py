@@ -98,6 +98,70 @@ def test_vector_posts_and_waits():
         q.close()
 
 
+def test_prediction_queue_random_traffic_against_a_model():
+    """Random interleavings of put / post_many / get / get_batch / replies (hypothesis): every request is delivered exactly
+    once with the state that was posted, nothing is invented, and the queue ends empty."""
+    from hypothesis import given, settings, strategies as st
+
+    ops = st.lists(st.one_of(st.tuples(st.just("put"), st.integers(0, 11)),
+                             st.tuples(st.just("many"), st.lists(st.integers(0, 11), min_size=1, max_size=5, unique=True)),
+                             st.tuples(st.just("get"), st.just(0)),
+                             st.tuples(st.just("batch"), st.integers(1, 6))), max_size=40)
+
+    @settings(max_examples=60, deadline=None)
+    @given(ops)
+    def run(seq):
+        q = SlabPredictionQueue(12, S, A, ctx=CTX)
+        q._POLL = 0.0                                   # single-threaded model run: never wait for a producer
+        try:
+            outstanding, stamp = {}, 0
+            buf = np.zeros((6, S), np.float32)
+
+            def deliver(aid, state):
+                assert aid in outstanding and state[0] == outstanding.pop(aid)
+                q.reply_batch(np.array([aid]), np.zeros((1, A), np.float32), np.array([state[0]], np.float32))
+                p, v = q.wait_q(aid).get(timeout=1)
+                assert v == state[0]
+
+            for op, arg in seq:
+                if op == "put" and arg not in outstanding:
+                    stamp += 1
+                    outstanding[arg] = float(stamp)
+                    q.put((arg, np.full(S, stamp, np.float32)))
+                elif op == "many":
+                    free = [a for a in arg if a not in outstanding]
+                    if free:
+                        vals = []
+                        for a in free:
+                            stamp += 1
+                            outstanding[a] = float(stamp)
+                            vals.append(np.full(S, stamp, np.float32))
+                        q.post_many(np.array(free), np.stack(vals))
+                elif op == "get":
+                    try:
+                        aid, state = q.get(block=False)
+                    except queue.Empty:
+                        assert not outstanding
+                    else:
+                        deliver(aid, state)
+                elif op == "batch":
+                    ids = q.get_batch(arg, buf, timeout=0.0)
+                    if ids is None:
+                        assert not outstanding
+                    else:
+                        assert 1 <= ids.size <= arg and len(set(ids.tolist())) == ids.size
+                        for k, aid in enumerate(ids):
+                            deliver(int(aid), buf[k].copy())
+            while outstanding:
+                aid, state = q.get(block=False)
+                deliver(aid, state)
+            assert q.empty() and q.get_batch(6, buf, timeout=0.0) is None
+        finally:
+            q.close()
+
+    run()
+
+
 def test_training_queue_contract_and_backpressure():
     tq = SlabTrainingQueue(2, max_rows=6, state_dim=S, num_actions=A, blocks_per_agent=2, ctx=CTX)
     try:
