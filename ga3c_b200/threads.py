@@ -60,7 +60,11 @@ class ThreadPredictor(Thread):
         if hasattr(self.prediction_q, "get_batch"):
             return self._run_slab(self.prediction_q, cap)
         ids = np.zeros(cap, dtype=np.uint16)                      # uint16 as in ThreadPredictor.py:46
-        states = np.zeros((cap, self.state_dim), dtype=np.float32)
+        try:        # pinned, so that Network copies the batch to the device without another host pass
+            import torch
+            states = torch.zeros((cap, self.state_dim), dtype=torch.float32, pin_memory=torch.cuda.is_available()).numpy()
+        except Exception:
+            states = np.zeros((cap, self.state_dim), dtype=np.float32)
         q = self.prediction_q
         while not self.exit_flag:
             ids[0], states[0] = q.get()
