@@ -301,6 +301,71 @@ def run_mlp_section(args, dev, stream, pk, clocks):
 
 
 # ------------------------------------------------------------------------------------------------
+def dp_check(net, rank, local_rank, world, B):
+    """N > 1, before (and outside) the timed region: correctness of the data-parallel step at the benchmarked shape.
+      1. the replicas start identical although no seed was given (rank 0's weights are broadcast at construction);
+      2. two lock-step train steps at B rows per rank on rank-specific data leave bit-identical replicas (small tensors, their
+         RMSProp slots, and the bf16 shadow of dense1/w that every rank holds);
+      3. two steps at 64 rows per rank from the oracle's weights equal the oracle's two steps on the CONCATENATED batch (what a
+         single ThreadTrainer fed all the rows would compute).  The oracle is the checker here, nothing it does is timed.
+    Any failure ends the run with a non-zero exit code."""
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle_np as onp
+    dev = torch.device("cuda", local_rank)
+
+    def replicas_identical():
+        w = net.get_variables()
+        ms, _ = net.get_slots()
+        small = np.concatenate([w[k].ravel() for k in sorted(w) if k != "dense1/w:0"] +
+                               [ms[k].ravel() for k in sorted(ms) if k != "dense1/w:0"])
+        ok = True
+        for arr in (small, net.workspace(6)):
+            t = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+            got = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(got, t)
+            ok = ok and all(torch.equal(got[0], g) for g in got)
+        return ok
+
+    rep = {"world": world}
+    rep["identical_at_start_without_seed"] = replicas_identical()
+    rng = np.random.default_rng(777 + rank)
+    for _ in range(2):
+        x, y_r, a = synth_batch(rng, B)
+        net.train(x, y_r, a, None, None, 0)
+    rep["replicas_identical"] = replicas_identical()
+    rep["rows_per_rank"] = B
+    # oracle leg
+    rows = 64
+    g = np.random.default_rng(4242)
+    params = onp.init_params(g, NUM_ACTIONS)
+    net.set_variables(params)
+    net.set_slots({k: np.ones_like(v) for k, v in params.items()}, {k: np.zeros_like(v) for k, v in params.items()})
+    ms, mom = onp.rmsprop_init(params)
+    ref = params
+    for _ in range(2):
+        x = onp.synth_frames(g, rows * world)
+        y_r, a = onp.synth_targets(g, rows * world, NUM_ACTIONS)
+        net.train(x[rank * rows:(rank + 1) * rows], y_r[rank * rows:(rank + 1) * rows], a[rank * rows:(rank + 1) * rows], None, None, 0)
+        if rank == 0:
+            _, _, ref, ms, mom = onp.train_step(ref, ms, mom, x, y_r, a, lr=net.learning_rate, beta=net.beta, quant="bf16")
+            ref = {k: v.astype(np.float32) for k, v in ref.items()}
+    got = net.get_variables()
+    worst = max(float(np.abs(got[k] - ref[k]).max()) for k in got) if rank == 0 else 0.0
+    rep["replicas_identical_oracle_leg"] = replicas_identical()
+    rep.update(max_abs_vs_oracle=worst, oracle_rows_per_rank=rows, oracle_steps=2, tol=1e-5,
+               oracle="oracle_np.train_step (quant='bf16') on the concatenated batch")
+    net.dp_check()
+    ok = rep["identical_at_start_without_seed"] and rep["replicas_identical"] and rep["replicas_identical_oracle_leg"] and worst <= 1e-5
+    flag = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(flag)
+    rep["ok"] = bool(flag.item() == 0)
+    log(f"[bench] rank {rank} dp_check: {rep}")
+    if not rep["ok"]:
+        raise SystemExit(f"bench.py: data-parallel check FAILED on rank {rank}: {rep}")
+    return rep
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -326,9 +391,18 @@ def run_ours(args, rank, local_rank, world):
 
     B, PB = args.batch, args.predict_batch
     K, W = args.steps, max(args.warmup, 3)
-    net = ga3c_b200.Network(f"gpu:{local_rank}", "bench", NUM_ACTIONS, max_batch=max(B, PB), seed=12345)
+    numa = None
+    if world > 1 and os.environ.get("GA3C_NUMA_BIND", "1") != "0":
+        # threads (and the pinned buffers they first touch) next to this rank's GPU; N = 1 keeps every core for the CPU legs
+        from ga3c_b200.numa import bind_to_gpu
+        numa = bind_to_gpu(local_rank)
+        log(f"[bench] rank {rank} numa: {numa}")
+    # N > 1: no seed, as the reference constructor has none -- every rank draws its own weights and Network makes the
+    # replicas equal rank 0's before the first step (checked below)
+    net = ga3c_b200.Network(f"gpu:{local_rank}", "bench", NUM_ACTIONS, max_batch=max(B, PB), seed=12345 if world == 1 else None)
     pk = peaks()
     stream = torch.cuda.current_stream(dev)
+    dp_report = dp_check(net, rank, local_rank, world, B) if world > 1 else None
 
     # ---- synthetic data: pinned host batches (e2e) and a device ring larger than L2 (value) ----
     rng = np.random.default_rng(12345 + 1000 * rank)
@@ -433,6 +507,25 @@ def run_ours(args, rank, local_rank, world):
     s_train_e2e = e2e(train_e2e, k_e2e)
     s_pred_e2e = e2e(predict_e2e, k_e2e)
 
+    # the drop-in case: the reference's ThreadTrainer hands over PAGEABLE arrays (np.concatenate output, ThreadTrainer.py:54-58)
+    pageable = [tuple(np.array(t.numpy(), copy=True) for t in h) for h in host]
+
+    def train_e2e_pageable(i):
+        x, y_r, a = pageable[i % len(pageable)]
+        net.train(x, y_r, a, None, None, 0, fetch_losses=True)
+
+    train_e2e_pageable(0)
+    s_train_e2e_pg = e2e(train_e2e_pageable, k_e2e)
+
+    # the ceiling of any fp32-contract e2e number: a bare pinned host -> device copy of one batch, all ranks at once
+    def h2d_only(i):
+        hx, _, _ = host[i % len(host)]
+        ring[i % n_ring][0].copy_(hx, non_blocking=True)
+
+    h2d_only(0)
+    s_h2d = e2e(h2d_only, k_e2e)
+    h2d_ceiling_gbs = B * STATE_DIM * 4 * k_e2e / s_h2d / 1e9
+
     # ---- uint8 frame ingestion, reported separately: a different input contract (raw pixels, x = k/128 - 1
     # applied on the GPU; outputs bit-identical to the fp32 path) with 4x fewer H2D and HBM input bytes ----
     hx8 = [(torch.clamp((h[0] + 1.0) * 128.0, 0, 255)).to(torch.uint8).pin_memory() for h in host]
@@ -521,7 +614,13 @@ def run_ours(args, rank, local_rank, world):
            "e2e": {"value": world * B * k_e2e / s_train_e2e, "unit": "frames/s",
                    "h2d_bytes_per_step": B * (STATE_DIM + 1 + NUM_ACTIONS) * 4, "d2h_bytes_per_step": 16,
                    "h2d_gbs_per_gpu": round(B * (STATE_DIM + 1 + NUM_ACTIONS) * 4 * k_e2e / s_train_e2e / 1e9, 2),
-                   "steps": k_e2e, "api": "Network.train(x, y_r, a, x2, done, trainer_id) on pinned host numpy"},
+                   "steps": k_e2e, "api": "Network.train(x, y_r, a, x2, done, trainer_id) on pinned host numpy",
+                   "h2d_ceiling_gbs_per_gpu": round(h2d_ceiling_gbs, 2),
+                   "frac_of_h2d_ceiling": round(B * (STATE_DIM + 1 + NUM_ACTIONS) * 4 * k_e2e / s_train_e2e / 1e9 / h2d_ceiling_gbs, 3),
+                   "ceiling_note": "bare cudaMemcpyAsync of one pinned fp32 batch per step, all ranks at once, same box and run",
+                   "pageable": {"value": world * B * k_e2e / s_train_e2e_pg, "unit": "frames/s",
+                                "api": "the same call on ordinary (pageable) numpy arrays, what the reference's ThreadTrainer hands "
+                                       "over (np.concatenate output): a chunked host copy into pinned staging overlaps the DMA"}},
            "pps": {"value": pps, "unit": "predictions/s", "batch": PB, "ms_per_step": ms_pred / K,
                    "e2e": {"value": world * PB * k_e2e / s_pred_e2e, "unit": "predictions/s",
                            "h2d_bytes_per_step": PB * STATE_DIM * 4, "d2h_bytes_per_step": PB * (NUM_ACTIONS + 1) * 4,
@@ -536,6 +635,10 @@ def run_ours(args, rank, local_rank, world):
                                             "h2d_bytes_per_step": PB * STATE_DIM, "d2h_bytes_per_step": PB * (NUM_ACTIONS + 1) * 4}}},
            "gpu_launches": int(launches),
            "clocks": sampler.summary()}
+    if dp_report is not None:
+        out["dp_check"] = dp_report
+    if numa is not None:
+        out["numa"] = numa
 
     if world == 1 and not args.no_mlp:
         out["mlp"] = run_mlp_section(args, dev, stream, pk, out["clocks"])

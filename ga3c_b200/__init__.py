@@ -8,6 +8,6 @@ without an sm_100 GPU raises.
 """
 from .config import Config  # noqa: F401
 from .network import Network  # noqa: F401
-from .threads import ThreadPredictor, ThreadTrainer  # noqa: F401
+from .threads import LockstepTrainer, ThreadPredictor, ThreadTrainer  # noqa: F401
 
-__all__ = ["Config", "Network", "ThreadPredictor", "ThreadTrainer"]
+__all__ = ["Config", "Network", "ThreadPredictor", "ThreadTrainer", "LockstepTrainer"]

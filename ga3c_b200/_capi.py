@@ -55,6 +55,12 @@ SIGNATURES = {
     "ga3c_dp_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "ga3c_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,
                                   C.c_void_p, C.c_void_p]),
+    "ga3c_arena_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "ga3c_dual_forward_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                                             C.c_void_p, C.c_void_p]),
+    "ga3c_dual_forward_backward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                                                C.c_void_p, C.c_void_p]),
+    "ga3c_dual_apply": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p]),
     "ga3c_predict_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ga3c_forward_backward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
                                            C.c_void_p, C.c_void_p]),

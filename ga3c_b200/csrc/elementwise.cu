@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(32 * CLIP_MAX_TENSORS) clip_scale_kernel(ClipA
   float s = 0.f;
   for (int i = lane; i < nch; i += 32) s += c.chunk_ss[(int64_t)t * c.max_chunks + i];
   s = warp_sum(s);
-  if (lane == 0) c.scale[t] = c.clip / fmaxf(sqrtf(s) / (float)c.count[t], c.clip);
+  if (lane == 0) c.scale[t] = c.clip / fmaxf(c.by_norm ? sqrtf(s) : sqrtf(s) / (float)c.count[t], c.clip);
 }
 
 template <bool HAS_MOM>
@@ -200,8 +200,16 @@ __global__ void __launch_bounds__(256) rmsprop_dual_kernel(RmsPropDualArgs d) {
     const bool skip2 = (e >= d.skip_lo[2] && e < d.skip_hi[2]) || (e >= d.skip_lo[3] && e < d.skip_hi[3]);
     const float4 w0 = reinterpret_cast<float4*>(a.w)[i];
     float4 w = w0;
+    float s1 = 1.f, s2 = 1.f;
+    if (d.scale1 != nullptr) {           // one scale per float4 is exact: tensors start 4-aligned, gaps hold zeros
+      s1 = s2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < CLIP_MAX_TENSORS; ++t)
+        if (t < d.n_tensors && e >= d.t_offset[t] && e < d.t_offset[t] + d.t_count[t]) { s1 = d.scale1[t]; s2 = d.scale2[t]; }
+    }
     if (!skip1) {
-      const float4 g = reinterpret_cast<const float4*>(a.g)[i];
+      float4 g = reinterpret_cast<const float4*>(a.g)[i];
+      g.x *= s1; g.y *= s1; g.z *= s1; g.w *= s1;
       float4 ms = reinterpret_cast<float4*>(a.ms)[i];
       float4 mo = HAS_MOM ? reinterpret_cast<float4*>(a.mom)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 w1 = w0;
@@ -211,7 +219,8 @@ __global__ void __launch_bounds__(256) rmsprop_dual_kernel(RmsPropDualArgs d) {
       if (HAS_MOM) reinterpret_cast<float4*>(a.mom)[i] = mo;
     }
     if (!skip2) {
-      const float4 g = reinterpret_cast<const float4*>(d.g2)[i];
+      float4 g = reinterpret_cast<const float4*>(d.g2)[i];
+      g.x *= s2; g.y *= s2; g.z *= s2; g.w *= s2;
       float4 ms = reinterpret_cast<float4*>(d.ms2)[i];
       float4 mo = HAS_MOM ? reinterpret_cast<float4*>(d.mom2)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 w2 = w0;
@@ -234,11 +243,27 @@ int launch_rmsprop_dual(const RmsPropDualArgs& d, cudaStream_t stream) {
   return launch_pdl(rmsprop_dual_kernel<false>, dim3(grid), dim3(256), 0, stream, d);
 }
 
+int launch_rmsprop_dual_clipped(RmsPropDualArgs d, const ClipArgs& c1, const ClipArgs& c2, cudaStream_t stream) {
+  int r;
+  for (const ClipArgs* c : {&c1, &c2}) {
+    if ((r = launch_pdl(grad_sqnorm_kernel, dim3(c->max_chunks, c->n_tensors), dim3(256), 0, stream, *c))) return r;
+    if ((r = launch_pdl(clip_scale_kernel, dim3(1), dim3(32 * CLIP_MAX_TENSORS), 0, stream, *c))) return r;
+  }
+  d.scale1 = c1.scale; d.scale2 = c2.scale; d.n_tensors = c1.n_tensors;
+  for (int t = 0; t < c1.n_tensors; ++t) { d.t_offset[t] = c1.offset[t]; d.t_count[t] = c1.count[t]; }
+  return launch_rmsprop_dual(d, stream);
+}
+
 // ---- single-GPU step tail: grad_reduce + RMSProp in one launch -------------------------------------------
 // Blocks [0, n_red) sum the gradient-partial slabs of 32 float4 columns exactly like grad_reduce_kernel (same order,
 // same bits), store the reduced gradient and apply RMSProp to those columns; the remaining blocks update dense1/w,
 // one float4 per thread.  w / ms (and mom) do not depend on the preceding kernels, so they are loaded BEFORE the
-// dependency wait and their latency hides under the tail of the backward.
+// dependency wait and their latency hides under the tail of the backward -- but only when a.preload says that this is safe:
+// w / ms were last written by the optimizer launch of the PREVIOUS step, and a prologue is ordered after that launch only if
+// some kernel in between cannot become resident next to it.  With batch >= num_sms the conv kernels of this step occupy every
+// SM with a CTA that takes the SM's whole shared memory, so every CTA of the previous optimizer launch has exited before this
+// kernel can be launched; with smaller batches the whole chain of a step can sit in its prologues while the previous
+// optimizer is still running (back-to-back asynchronous calls), and the loads move behind the wait.
 template <bool HAS_MOM>
 __global__ void __launch_bounds__(GR_LANES * GR_COLS) rmsprop_reduce_kernel(RmsPropArgs a, GradReduceArgs r, int n_red) {
   __shared__ float4 part[GR_LANES][GR_COLS];
@@ -254,13 +279,18 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) rmsprop_reduce_kernel(RmsP
     }
     const bool owner = sl == 0 && j < r.out_floats;
     float4 w = zero, ms = zero, mo = zero;
-    if (owner) {
+    if (owner && a.preload) {
       w = *reinterpret_cast<const float4*>(a.w + j);
       ms = *reinterpret_cast<const float4*>(a.ms + j);
       if (HAS_MOM) mo = *reinterpret_cast<const float4*>(a.mom + j);
     }
     griddep_launch();
     griddep_wait(K_RMSPROP);      // the slabs come from the kernels that precede this one
+    if (owner && !a.preload) {
+      w = *reinterpret_cast<const float4*>(a.w + j);
+      ms = *reinterpret_cast<const float4*>(a.ms + j);
+      if (HAS_MOM) mo = *reinterpret_cast<const float4*>(a.mom + j);
+    }
     float4 acc = zero;
     const float* src = r.part + j;
     for (int i0 = sl; i0 < count; i0 += GR_UNROLL * GR_LANES) {
@@ -301,7 +331,7 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) rmsprop_reduce_kernel(RmsP
     for (int u = 0; u < 2; ++u) {
       const int64_t i = i0 + u * blockDim.x;
       w[u] = ms[u] = mo[u] = zero;
-      if (i < n4) {
+      if (i < n4 && a.preload) {
         w[u] = reinterpret_cast<const float4*>(a.w)[i];
         ms[u] = reinterpret_cast<const float4*>(a.ms)[i];
         if (HAS_MOM) mo[u] = reinterpret_cast<const float4*>(a.mom)[i];
@@ -309,6 +339,17 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) rmsprop_reduce_kernel(RmsP
     }
     griddep_launch();
     griddep_wait(K_RMSPROP);      // dense1/w's gradient comes from the wgrad GEMM
+    if (!a.preload) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t i = i0 + u * blockDim.x;
+        if (i < n4) {
+          w[u] = reinterpret_cast<const float4*>(a.w)[i];
+          ms[u] = reinterpret_cast<const float4*>(a.ms)[i];
+          if (HAS_MOM) mo[u] = reinterpret_cast<const float4*>(a.mom)[i];
+        }
+      }
+    }
     float4 g[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -531,7 +572,7 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_small_kernel(RmsPropDpA
   }
   // w / ms of the small prefix were last written by this kernel one step ago: fetch them before the dependency wait
   float4 w = make_float4(0.f, 0.f, 0.f, 0.f), ms = w, mo = w;
-  if (owner) {
+  if (owner && a.preload) {           // see rmsprop_reduce_kernel for when the early loads are safe
     w = *reinterpret_cast<const float4*>(a.w + j);
     ms = *reinterpret_cast<const float4*>(a.ms + j);
     if (HAS_MOM) mo = *reinterpret_cast<const float4*>(a.mom + j);
@@ -540,6 +581,11 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_small_kernel(RmsPropDpA
   evt_mark(evt_i, 60, 0);
   griddep_wait(K_RMSPROP);            // the slabs come from the conv backward launch that precedes this one
   evt_mark(evt_i, 61, 0);
+  if (owner && !a.preload) {
+    w = *reinterpret_cast<const float4*>(a.w + j);
+    ms = *reinterpret_cast<const float4*>(a.ms + j);
+    if (HAS_MOM) mo = *reinterpret_cast<const float4*>(a.mom + j);
+  }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* src = r.part + j;
   for (int i0 = sl; i0 < count; i0 += GR_UNROLL * GR_LANES) {

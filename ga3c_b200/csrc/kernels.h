@@ -94,6 +94,7 @@ struct RmsPropArgs {
   int64_t n_floats;        // arena size (multiple of 4)
   int64_t w1_offset, w1_count;
   float lr, decay, momentum, eps;
+  int preload;             // the optimizer kernels may load w / ms / mom before their dependency wait (rmsprop_reduce_kernel)
 };
 int launch_rmsprop(const RmsPropArgs& a, cudaStream_t stream);
 // Config.USE_GRAD_CLIP: tf.clip_by_average_norm per variable, then RMSProp (3 launches: chunk sums of squares, per-tensor
@@ -106,6 +107,7 @@ struct ClipArgs {
   int64_t offset[CLIP_MAX_TENSORS], count[CLIP_MAX_TENSORS];
   float clip;
   float *chunk_ss, *scale;
+  int by_norm;                      // 0: tf.clip_by_average_norm (||g|| / n against clip), 1: tf.clip_by_norm (||g|| against clip)
 };
 int clip_chunks(int64_t max_count);
 int launch_rmsprop_clipped(const RmsPropArgs& a, const ClipArgs& c, cudaStream_t stream);
@@ -117,8 +119,15 @@ struct RmsPropDualArgs {
   const float* g2;
   float *ms2, *mom2;
   int64_t skip_lo[4], skip_hi[4];
+  // DUAL_RMSPROP + USE_GRAD_CLIP (NetworkVP_discrate.py:107-117): per-variable tf.clip_by_norm scales of g (scale1) and g2
+  // (scale2), indexed like the tensor table below; null = unclipped
+  const float *scale1, *scale2;
+  int n_tensors;
+  int64_t t_offset[CLIP_MAX_TENSORS], t_count[CLIP_MAX_TENSORS];
 };
 int launch_rmsprop_dual(const RmsPropDualArgs& d, cudaStream_t stream);
+// the same with both gradients clipped first: c1 describes g (d.a.g), c2 describes g2; both by_norm.  5 launches.
+int launch_rmsprop_dual_clipped(RmsPropDualArgs d, const ClipArgs& c1, const ClipArgs& c2, cudaStream_t stream);
 // grad_reduce + RMSProp in one launch (single-GPU step; r.out must be a.g, r.out_floats the small-tensor prefix)
 int launch_rmsprop_reduce(const RmsPropArgs& a, const GradReduceArgs& r, cudaStream_t stream);
 // data-parallel RMSProp over peer memory: rank r owns arena slice r; it sums that slice of every rank's gradient

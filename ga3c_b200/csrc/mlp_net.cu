@@ -37,6 +37,7 @@ struct ga3c_mlp {
   float *w = nullptr, *g = nullptr, *ms = nullptr, *mom = nullptr;
   float* part = nullptr;                 // [MLP_MAX_SPLITS][live_floats] weight-gradient partial arenas
   float *clip_ss = nullptr, *clip_scale = nullptr;   // Config.USE_GRAD_CLIP scratch
+  float *clip_ss2 = nullptr, *clip_scale2 = nullptr; // ... of the second optimizer's gradient (DUAL_RMSPROP + USE_GRAD_CLIP)
   float *g2 = nullptr, *ms2 = nullptr, *mom2 = nullptr;   // Config.DUAL_RMSPROP: gradient of cost_v, second optimizer's slots
   int64_t skip_lo[2] = {}, skip_hi[2] = {};          // arena ranges of logits_v/* and of the policy head
   // workspace for max_batch rows
@@ -69,7 +70,7 @@ static int alloc_workspace(ga3c_mlp* n, int max_batch) {
 extern "C" int ga3c_mlp_destroy(ga3c_mlp* n) {
   if (!n) return 0;
   cudaFree(n->w); cudaFree(n->g); cudaFree(n->ms); cudaFree(n->mom); cudaFree(n->part);
-  cudaFree(n->clip_ss); cudaFree(n->clip_scale);
+  cudaFree(n->clip_ss); cudaFree(n->clip_scale); cudaFree(n->clip_ss2); cudaFree(n->clip_scale2);
   cudaFree(n->g2); cudaFree(n->ms2); cudaFree(n->mom2);
   free_workspace(n);
   n->log.clear();
@@ -180,7 +181,6 @@ extern "C" int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out) {
   if (e != cudaSuccess) { ga3c_mlp_destroy(n); return fail("cudaMalloc", e); }
   cudaMemset(n->part, 0, (size_t)MLP_MAX_SPLITS * n->live_floats * 4);
   if (cfg->dual_rmsprop) {
-    if (cfg->use_grad_clip) { ga3c_mlp_destroy(n); return set_error("ga3c_mlp_create: DUAL_RMSPROP with USE_GRAD_CLIP is not built"); }
     float** extra[3] = {&n->g2, &n->ms2, &n->mom2};
     for (float** a : extra) {
       e = cudaMalloc((void**)a, ab);
@@ -192,7 +192,8 @@ extern "C" int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out) {
   }
   if (cfg->use_grad_clip) {
     for (const MlpParam& p : n->params)
-      if (!p.live) {     // opt.compute_gradients yields (None, var) and tf.clip_by_average_norm(None, ..) raises
+      if (!p.live && !cfg->dual_rmsprop) {     // opt.compute_gradients yields (None, var) and tf.clip_by_average_norm(None, ..) raises;
+                                               // the DUAL_RMSPROP branch filters `if not g is None` (NetworkVP_discrate.py:110,:115)
         ga3c_mlp_destroy(n);
         return set_error("ga3c_mlp_create: USE_GRAD_CLIP with gradient-less variables (NetworkVP_discrate.py:55 builds every "
                          "DENSE_LAYERS entry from x): the reference graph cannot be built either");
@@ -202,6 +203,10 @@ extern "C" int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out) {
     for (const MlpParam& p : n->params) mx = p.count > mx ? p.count : mx;
     e = cudaMalloc((void**)&n->clip_ss, n->params.size() * clip_chunks(mx) * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void**)&n->clip_scale, n->params.size() * sizeof(float));
+    if (e == cudaSuccess && cfg->dual_rmsprop) {
+      e = cudaMalloc((void**)&n->clip_ss2, n->params.size() * clip_chunks(mx) * sizeof(float));
+      if (e == cudaSuccess) e = cudaMalloc((void**)&n->clip_scale2, n->params.size() * sizeof(float));
+    }
     if (e != cudaSuccess) { ga3c_mlp_destroy(n); return fail("cudaMalloc", e); }
   }
   if (int r = alloc_workspace(n, cfg->max_batch)) { ga3c_mlp_destroy(n); return r; }
@@ -360,6 +365,28 @@ extern "C" int ga3c_mlp_train_step(ga3c_mlp* n, const float* x, const float* yr,
     d.g2 = n->g2; d.ms2 = n->ms2; d.mom2 = n->mom2;
     d.skip_lo[0] = n->skip_lo[0]; d.skip_hi[0] = n->skip_hi[0];        // cost_p: not logits_v
     d.skip_lo[2] = n->skip_lo[1]; d.skip_hi[2] = n->skip_hi[1];        // cost_v: not the policy head
+    if (n->cfg.use_grad_clip) {
+      // tf.clip_by_norm per variable and optimizer (NetworkVP.py:127-137, NetworkVP_discrate.py:107-117); the fork's NetworkVP
+      // hands global_step to both apply_gradients calls, NetworkVP_discrate to neither
+      ClipArgs c[2] = {};
+      int64_t mx = 0;
+      for (int w = 0; w < 2; ++w) {
+        c[w].g = w ? n->g2 : n->g;
+        c[w].n_tensors = 0;
+        for (const MlpParam& p : n->params) {
+          if (!p.live) continue;                                       // gradient is None: filtered by the reference
+          c[w].offset[c[w].n_tensors] = p.offset; c[w].count[c[w].n_tensors] = p.count; ++c[w].n_tensors;
+          mx = p.count > mx ? p.count : mx;
+        }
+        c[w].clip = n->cfg.grad_clip_norm; c[w].by_norm = 1;
+        c[w].chunk_ss = w ? n->clip_ss2 : n->clip_ss; c[w].scale = w ? n->clip_scale2 : n->clip_scale;
+      }
+      c[0].max_chunks = c[1].max_chunks = clip_chunks(mx);
+      LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_dual_clipped(d, c[0], c[1], (cudaStream_t)stream));
+      n->log.launches += 4;
+      if (n->cfg.kind == GA3C_MLP_FORK_VP) n->global_step += 2;
+      return 0;
+    }
     LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_dual(d, (cudaStream_t)stream));
     n->global_step += 2;
     return 0;

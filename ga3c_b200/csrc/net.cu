@@ -66,6 +66,7 @@ struct ga3c_net {
   int gp_heads_grid = 0;           // slabs the heads kernel of the current step wrote
   float* loss_out = nullptr;       // caller's loss buffer of the current step (may be null)
   float *clip_ss = nullptr, *clip_scale = nullptr;   // Config.USE_GRAD_CLIP scratch: chunk sums of squares, per-tensor scale
+  float *clip_ss2 = nullptr, *clip_scale2 = nullptr; // ... of the second optimizer's gradient (DUAL_RMSPROP + USE_GRAD_CLIP)
   float *g2 = nullptr, *ms2 = nullptr, *mom2 = nullptr;   // Config.DUAL_RMSPROP: gradient of cost_v and the second optimizer's slots
   bool keep_dn1 = false;           // tests: also store dn1 (which otherwise never leaves the SM) to the workspace
   int64_t global_step = 0;
@@ -93,7 +94,7 @@ int set_error(const std::string& m) { g_err = m; return -1; }     // for the oth
 const char* kernel_name(int kid) { return (kid >= 0 && kid < K_COUNT) ? kKernelNames[kid] : nullptr; }
 }
 extern "C" const char* ga3c_last_error(void) { return g_err.c_str(); }
-extern "C" int ga3c_abi_version(void) { return 4; }
+extern "C" int ga3c_abi_version(void) { return 5; }
 
 extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
   if (!cfg || !out) return fail_msg("ga3c_create: null argument");
@@ -160,7 +161,6 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
   if (e != cudaSuccess) { ga3c_destroy(n); return fail("cudaMalloc", e); }
   cudaMemset(n->gpart, 0, (size_t)2 * n->num_sms * n->gp_stride * sizeof(float));
   if (cfg->dual_rmsprop) {
-    if (cfg->use_grad_clip) { ga3c_destroy(n); return fail_msg("ga3c_create: DUAL_RMSPROP with USE_GRAD_CLIP (clip_by_norm per optimizer) is not built"); }
     float** extra[3] = {&n->g2, &n->ms2, &n->mom2};
     for (float** a : extra) {
       e = cudaMalloc((void**)a, ab);
@@ -173,6 +173,10 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
   if (cfg->use_grad_clip) {
     e = cudaMalloc((void**)&n->clip_ss, (size_t)P_COUNT * clip_chunks((int64_t)FLAT * FC) * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void**)&n->clip_scale, P_COUNT * sizeof(float));
+    if (e == cudaSuccess && cfg->dual_rmsprop) {
+      e = cudaMalloc((void**)&n->clip_ss2, (size_t)P_COUNT * clip_chunks((int64_t)FLAT * FC) * sizeof(float));
+      if (e == cudaSuccess) e = cudaMalloc((void**)&n->clip_scale2, P_COUNT * sizeof(float));
+    }
     if (e != cudaSuccess) { ga3c_destroy(n); return fail("cudaMalloc", e); }
   }
   if (int r = alloc_workspace(n, cfg->max_batch)) { ga3c_destroy(n); return r; }
@@ -226,7 +230,7 @@ extern "C" int ga3c_destroy(ga3c_net* n) {
   ga3c_dp_detach(n);
   cudaFree(n->slab);
   cudaFree(n->gpart);
-  cudaFree(n->clip_ss); cudaFree(n->clip_scale);
+  cudaFree(n->clip_ss); cudaFree(n->clip_scale); cudaFree(n->clip_ss2); cudaFree(n->clip_scale2);
   cudaFree(n->g2); cudaFree(n->ms2); cudaFree(n->mom2);
   if (n->trace) { trace_attach_all(nullptr); cudaFree(n->trace); }
   free_workspace(n);
@@ -265,6 +269,13 @@ static float* arena_of(ga3c_net* n, int which) {
     case 4: return n->g2; case 5: return n->ms2; case 6: return n->mom2;      // null unless dual_rmsprop
   }
   return nullptr;
+}
+
+extern "C" int ga3c_arena_ptr(ga3c_net* n, int which, float** ptr_dev) {
+  if (!n || !ptr_dev) return fail_msg("ga3c_arena_ptr: null argument");
+  *ptr_dev = arena_of(n, which);
+  if (!*ptr_dev) return fail_msg("ga3c_arena_ptr: bad arena id");
+  return 0;
 }
 
 extern "C" int ga3c_arena_upload(ga3c_net* n, int which, const float* host, int64_t nf) {
@@ -450,11 +461,11 @@ static RmsPropArgs rmsprop_args(ga3c_net* n, float lr) {
   return a;
 }
 
-static ClipArgs clip_args(ga3c_net* n) {
+static ClipArgs clip_args(ga3c_net* n, int which = 0) {        // which: 0 the (first) optimizer's gradient, 1 the second one's
   ClipArgs c{};
-  c.g = n->g; c.n_tensors = P_COUNT; c.max_chunks = clip_chunks((int64_t)FLAT * FC);
+  c.g = which ? n->g2 : n->g; c.n_tensors = P_COUNT; c.max_chunks = clip_chunks((int64_t)FLAT * FC);
   for (int i = 0; i < P_COUNT; ++i) { c.offset[i] = n->params[i].offset; c.count[i] = n->params[i].count; }
-  c.clip = n->cfg.grad_clip_norm; c.chunk_ss = n->clip_ss; c.scale = n->clip_scale;
+  c.clip = n->cfg.grad_clip_norm; c.chunk_ss = which ? n->clip_ss2 : n->clip_ss; c.scale = which ? n->clip_scale2 : n->clip_scale;
   return c;
 }
 
@@ -581,23 +592,93 @@ extern "C" int ga3c_dp_error(ga3c_net* n, int32_t* error_out) {
   return 0;
 }
 
+// Config.DUAL_RMSPROP: one forward, two backward passes (cost_p into g, cost_v into g2) ...
+static int dual_forward_backward_impl(ga3c_net* n, const void* x, bool x_u8, const float* yr, const float* a, int32_t batch,
+                                      float beta, float* loss, void* stream) {
+  if (!n || !n->cfg.dual_rmsprop) return fail_msg("ga3c_dual_forward_backward: the handle was not created with dual_rmsprop");
+  if (int r = fb_head_impl(n, x, x_u8, yr, a, batch, beta, loss, stream, false, 1)) return r;
+  if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, true)) return r;
+  if (int r = fb_head_impl(n, x, x_u8, yr, a, batch, beta, nullptr, stream, false, 2, true)) return r;
+  return fb_tail_impl(n, x, x_u8, batch, stream, true, true, nullptr, n->g2);
+}
+// ... and one update that subtracts both optimizers' steps, each taken at the weights the call started with
+static int dual_apply_impl(ga3c_net* n, float lr, void* stream) {
+  if (!n || !n->cfg.dual_rmsprop) return fail_msg("ga3c_dual_apply: the handle was not created with dual_rmsprop");
+  CK(cudaSetDevice(n->cfg.device));
+  RmsPropDualArgs d{};
+  d.a = rmsprop_args(n, lr);
+  d.g2 = n->g2; d.ms2 = n->ms2; d.mom2 = n->mom2;
+  const int skip[4] = {P_VW, P_VB, P_PW, P_PB};          // cost_p does not reach logits_v (stop_gradient), cost_v not logits_p
+  for (int i = 0; i < 4; ++i) { d.skip_lo[i] = n->off(skip[i]); d.skip_hi[i] = n->off(skip[i]) + n->params[skip[i]].count; }
+  if (n->cfg.use_grad_clip) {
+    // NetworkVP_discrate.py:107-117: tf.clip_by_norm per variable and optimizer, then apply_gradients WITHOUT global_step
+    ClipArgs c1 = clip_args(n, 0), c2 = clip_args(n, 1);
+    c1.by_norm = c2.by_norm = 1;
+    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_dual_clipped(d, c1, c2, (cudaStream_t)stream));
+    n->log.launches += 4;
+    return 0;
+  }
+  LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_dual(d, (cudaStream_t)stream));
+  n->global_step += 2;      // both minimize calls advance it (NetworkVP_discrate.py:125-126)
+  return 0;
+}
+extern "C" int ga3c_dual_forward_backward(ga3c_net* n, const float* x, const float* yr, const float* a, int32_t batch, float beta,
+                                          float* loss, void* stream) {
+  return dual_forward_backward_impl(n, x, false, yr, a, batch, beta, loss, stream);
+}
+extern "C" int ga3c_dual_forward_backward_u8(ga3c_net* n, const uint8_t* x, const float* yr, const float* a, int32_t batch,
+                                             float beta, float* loss, void* stream) {
+  return dual_forward_backward_impl(n, x, true, yr, a, batch, beta, loss, stream);
+}
+extern "C" int ga3c_dual_apply(ga3c_net* n, float lr, void* stream) { return dual_apply_impl(n, lr, stream); }
+
+// A rank of a data-parallel job that has no experiences this round still takes part in the exchange (every rank must enter
+// every step: the asynchronous trainer loop of the reference, ThreadTrainer.py:42-62, gives no such guarantee, so the host
+// ticks all ranks in lock step and idle ranks contribute a zero gradient).  No forward / backward kernels run.
+static int train_step_empty(ga3c_net* n, float lr, float* loss, void* stream) {
+  CK(cudaSetDevice(n->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n->cfg.dual_rmsprop || n->cfg.use_grad_clip)
+    return fail_msg("ga3c_train_step: batch 0 is only defined for the peer-memory data-parallel step");
+  n->gp_heads_grid = 0;
+  n->loss_out = loss;
+  n->last_batch = 0;
+  if (n->dp_exch > 0) {
+    CK(cudaMemsetAsync(n->g + n->off(P_D1W), 0, (size_t)FLAT * FC * 4, st));
+    DpBigArgs b{};
+    for (int r = 0; r < n->dp_world; ++r) b.peer[r] = n->dp_peer[r];
+    b.rank = n->dp_rank; b.world = n->dp_world; b.n_exch = n->dp_exch; b.step = ++n->dp_step;
+    b.arena_bytes = (int64_t)n->arena_floats * 4; b.shadow_off = 4 * b.arena_bytes; b.comm_offset = n->comm_off;
+    b.w1_offset = n->off(P_D1W); b.w1_count = (int64_t)FLAT * FC;
+    b.lr = lr; b.decay = n->cfg.rmsprop_decay; b.momentum = n->cfg.rmsprop_momentum; b.eps = n->cfg.rmsprop_epsilon;
+    n->cur_exch = b.n_exch;
+    float* gp = n->gpart;
+    LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(nullptr, false, n->n1, n->dn2, n->w + n->off(P_C12W), nullptr,
+                                                gp + n->off(P_C11W), gp + n->off(P_C11B), gp + n->off(P_C12W),
+                                                gp + n->off(P_C12B), n->gp_stride, 0, n->num_sms, &b, st));
+    RmsPropDpArgs d{};
+    d.base = rmsprop_args(n, lr);
+    for (int q = 0; q < n->dp_world; ++q) d.peer[q] = n->dp_peer[q];
+    d.rank = n->dp_rank; d.world = n->dp_world; d.step = b.step;
+    d.arena_bytes = b.arena_bytes; d.comm_offset = n->comm_off;
+    d.has_red = 1; d.red = reduce_args(n, 0);      // zero slabs in every segment: the sums are 0
+    n->cur_exch = 0;
+    LAUNCH(n, K_RMSPROP, st, launch_dp_small(d, n->xbuf_off, st));
+    n->global_step += 1;
+    return 0;
+  }
+  CK(cudaMemsetAsync(n->g, 0, (size_t)n->arena_floats * 4, st));
+  if (loss) CK(cudaMemsetAsync(loss, 0, 16, st));
+  return apply_rmsprop_impl(n, lr, stream, nullptr);
+}
+
 static int train_step_impl(ga3c_net* n, const void* x, bool x_u8, const float* yr, const float* a, int32_t batch, float lr,
                            float beta, float* loss, void* stream) {
+  if (n && batch == 0 && n->dp_world > 1) return train_step_empty(n, lr, loss, stream);
   if (n->cfg.dual_rmsprop) {
-    // Config.DUAL_RMSPROP: one forward, two backward passes (cost_p into g, cost_v into g2), one update with both steps
-    if (n->dp_world > 1) return fail_msg("ga3c_train_step: DUAL_RMSPROP is not available with data parallelism");
-    if (int r = fb_head_impl(n, x, x_u8, yr, a, batch, beta, loss, stream, false, 1)) return r;
-    if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, true)) return r;
-    if (int r = fb_head_impl(n, x, x_u8, yr, a, batch, beta, nullptr, stream, false, 2, true)) return r;
-    if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, true, nullptr, n->g2)) return r;
-    RmsPropDualArgs d{};
-    d.a = rmsprop_args(n, lr);
-    d.g2 = n->g2; d.ms2 = n->ms2; d.mom2 = n->mom2;
-    const int skip[4] = {P_VW, P_VB, P_PW, P_PB};          // cost_p does not reach logits_v (stop_gradient), cost_v not logits_p
-    for (int i = 0; i < 4; ++i) { d.skip_lo[i] = n->off(skip[i]); d.skip_hi[i] = n->off(skip[i]) + n->params[skip[i]].count; }
-    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_dual(d, (cudaStream_t)stream));
-    n->global_step += 2;      // both minimize calls advance it (NetworkVP_discrate.py:125-126)
-    return 0;
+    if (n->dp_world > 1) return fail_msg("ga3c_train_step: DUAL_RMSPROP is not available with the peer-memory exchange (dp_mode 'nccl' is)");
+    if (int r = dual_forward_backward_impl(n, x, x_u8, yr, a, batch, beta, loss, stream)) return r;
+    return dual_apply_impl(n, lr, stream);
   }
   if (int r = fb_head_impl(n, x, x_u8, yr, a, batch, beta, loss, stream, false)) return r;
   if (n->cfg.use_grad_clip) {
@@ -617,6 +698,7 @@ static int train_step_impl(ga3c_net* n, const void* x, bool x_u8, const float* y
     int r = fb_tail_impl(n, x, x_u8, batch, stream, true, false, &b);
     RmsPropDpArgs d{};
     d.base = rmsprop_args(n, lr);
+    d.base.preload = batch >= n->num_sms;         // see rmsprop_reduce_kernel
     for (int q = 0; q < n->dp_world; ++q) d.peer[q] = n->dp_peer[q];
     d.rank = n->dp_rank; d.world = n->dp_world; d.step = b.step;
     d.arena_bytes = b.arena_bytes; d.comm_offset = n->comm_off;
@@ -632,7 +714,9 @@ static int train_step_impl(ga3c_net* n, const void* x, bool x_u8, const float* y
   if (n->dp_world > 1)            // peers read this rank's gradient arena: the exchange kernel first sums the slabs into it
     return apply_rmsprop_impl(n, lr, stream, &red);
   // single GPU: the slab reduction rides in the optimizer launch
-  LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_reduce(rmsprop_args(n, lr), red, (cudaStream_t)stream));
+  RmsPropArgs ra = rmsprop_args(n, lr);
+  ra.preload = batch >= n->num_sms;               // see rmsprop_reduce_kernel
+  LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_reduce(ra, red, (cudaStream_t)stream));
   n->global_step += 1;   // opt.minimize(..., global_step=self.global_step), NetworkVP_discrate.py:130
   return 0;
 }
@@ -674,6 +758,7 @@ extern "C" int ga3c_workspace_ptr(ga3c_net* n, int which, void** ptr, int64_t* b
     case 3: *ptr = n->dd1; if (bytes) *bytes = b * FC * 2; break;
     case 4: *ptr = n->dn2; if (bytes) *bytes = b * FLAT * 2; break;
     case 5: *ptr = n->dn1; if (bytes) *bytes = b * N1_POS * C1_OUT * 2; break;
+    case 6: *ptr = n->w1_shadow; if (bytes) *bytes = (int64_t)FLAT * FC * 2; break;
     default: return fail_msg("ga3c_workspace_ptr: bad id");
   }
   return 0;

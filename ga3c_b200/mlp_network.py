@@ -35,8 +35,6 @@ class _MlpNetwork:
         self.num_actions = int(num_actions)
         self.state_dim = int(np.prod(state_dim)) if not isinstance(state_dim, int) else state_dim
         self._dual = bool(getattr(cfg, "DUAL_RMSPROP", False))
-        if self._dual and getattr(cfg, "USE_GRAD_CLIP", False):
-            raise NotImplementedError("Config.DUAL_RMSPROP with USE_GRAD_CLIP (clip_by_norm per optimizer) is not built")
         self.learning_rate = cfg.LEARNING_RATE_START
         self.beta = cfg.BETA_START
         self.log_epsilon = cfg.LOG_EPSILON

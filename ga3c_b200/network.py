@@ -59,8 +59,6 @@ class Network:
         if self.state_dim != STATE_DIM:
             raise ValueError(f"conv NetworkVP expects state_dim = 84*84*4 = {STATE_DIM}, got {self.state_dim}")
         self._dual = bool(getattr(cfg, "DUAL_RMSPROP", False))
-        if self._dual and getattr(cfg, "USE_GRAD_CLIP", False):
-            raise NotImplementedError("Config.DUAL_RMSPROP with USE_GRAD_CLIP (clip_by_norm per optimizer) is not built")
 
         self.learning_rate = cfg.LEARNING_RATE_START      # NetworkVP.py:44
         self.beta = cfg.BETA_START                        # NetworkVP.py:45
@@ -121,14 +119,25 @@ class Network:
         if data_parallel is False:
             self._allreduce.enabled = False
         self.dp_mode = None
+        self._allreduce2 = None
         if self._allreduce.enabled:
             self.dp_mode = dp_mode or os.environ.get("GA3C_DP", "fused")
             if self.dp_mode not in ("fused", "nccl"):
                 raise ValueError(f"dp_mode must be 'fused' or 'nccl', got {self.dp_mode!r}")
+        if self.dp_mode == "fused" and (getattr(cfg, "USE_GRAD_CLIP", False) or self._dual):
+            # the per-variable norms need the whole reduced gradient, and DUAL_RMSPROP has two gradient arenas: allreduce
+            # first (NCCL), then clip / update locally
+            self.dp_mode = "nccl"
         if self._allreduce.enabled and self._dual:
-            raise NotImplementedError("Config.DUAL_RMSPROP is single-GPU only")
-        if self.dp_mode == "fused" and getattr(cfg, "USE_GRAD_CLIP", False):
-            self.dp_mode = "nccl"        # the per-variable norm needs the whole reduced gradient: allreduce first, clip locally
+            g2 = C.c_void_p()
+            _capi.check(self._lib.ga3c_arena_ptr(self._h, 4, C.byref(g2)), "ga3c_arena_ptr")
+            with torch.cuda.device(self._tdev):
+                self._grad2_arena = torch.as_tensor(_DevArray(g2.value, self._arena_floats, self), device=self._tdev)
+            self._allreduce2 = GradientAllReduce(self._grad2_arena, self._table["dense1/w:0"][0])
+        if self._allreduce.enabled:
+            # Replicas must START identical: the reference constructor has no seed argument (NetworkVP.py:37), so every rank
+            # drew its own U(+-1/sqrt(fan_in)) weights above.  Rank 0's weights and slots win.
+            self.sync_replicas()
         if self.dp_mode == "fused":
             import torch.distributed as dist
             n = self._lib.ga3c_dp_handle_bytes()
@@ -185,16 +194,28 @@ class Network:
         if rows > self._io_rows:
             self._alloc_io(rows)
 
-    @staticmethod
-    def _stage(arr: np.ndarray, pinned: torch.Tensor, b: int) -> torch.Tensor:
-        """Host source for the H2D copy: the caller's array itself when it already lives in pinned
-        memory (no extra host pass), otherwise a copy into this Network's pinned staging buffer."""
+    _CHUNK_BYTES = 8 << 20
+
+    def _h2d(self, arr: np.ndarray, pinned: torch.Tensor, dst: torch.Tensor, b: int):
+        """Enqueues the host -> device copy of arr[:b] on the current stream.  A pinned caller array is copied as it is; a
+        pageable one (what the reference's ThreadTrainer hands over: np.concatenate output, ThreadTrainer.py:54-58) goes
+        through this Network's pinned staging buffer in chunks, so that the host copy of chunk k+1 (torch's multi-threaded
+        copy, GIL released) overlaps the DMA of chunk k instead of preceding the whole transfer."""
+        src = None
         if arr.flags["C_CONTIGUOUS"] and arr.flags["WRITEABLE"]:
-            t = torch.from_numpy(arr)
-            if t.is_pinned():
-                return t
-        pinned[:b].numpy()[...] = arr
-        return pinned[:b]
+            src = torch.from_numpy(arr)
+            if src.is_pinned():
+                dst[:b].copy_(src, non_blocking=True)
+                return
+        if src is None or arr.nbytes <= self._CHUNK_BYTES:
+            pinned[:b].numpy()[...] = arr
+            dst[:b].copy_(pinned[:b], non_blocking=True)
+            return
+        rows = max(1, self._CHUNK_BYTES // max(1, arr[0].nbytes))
+        for lo in range(0, b, rows):
+            hi = min(b, lo + rows)
+            pinned[lo:hi].copy_(src[lo:hi])
+            dst[lo:hi].copy_(pinned[lo:hi], non_blocking=True)
 
     def __del__(self):
         try:
@@ -232,6 +253,24 @@ class Network:
             _capi.check(fn(self._h, x_dev.data_ptr(), yr_dev.data_ptr(), a_dev.data_ptr(), b, float(self.learning_rate),
                            float(self.beta), loss_ptr, st.cuda_stream), "ga3c_train_step")
             return
+        if b == 0:
+            # lock-step tick of a rank with no experiences (threads.LockstepTrainer): zero contribution to the allreduce
+            self._zero(self._grad_arena, st)
+            if self._dual:
+                self._zero(self._grad2_arena, st)
+        elif self._dual:
+            fb = self._lib.ga3c_dual_forward_backward_u8 if u8 else self._lib.ga3c_dual_forward_backward
+            _capi.check(fb(self._h, x_dev.data_ptr(), yr_dev.data_ptr(), a_dev.data_ptr(), b, float(self.beta), loss_ptr,
+                           st.cuda_stream), "ga3c_dual_forward_backward")
+        if self._dual:
+            for ar in (self._allreduce, self._allreduce2):
+                ar.start_big(st)
+                ar.finish(st)
+            _capi.check(self._lib.ga3c_dual_apply(self._h, float(self.learning_rate), st.cuda_stream), "ga3c_dual_apply")
+            return
+        if b == 0:
+            self._allreduce.start_big(st)
+            self._allreduce.finish(st)
         else:
             # dense1/w (98.8 % of the arena) is final after the head: its allreduce overlaps the conv backward
             head = self._lib.ga3c_fb_head_u8 if u8 else self._lib.ga3c_fb_head
@@ -242,6 +281,27 @@ class Network:
             _capi.check(tail(self._h, x_dev.data_ptr(), b, st.cuda_stream), "ga3c_fb_tail")
             self._allreduce.finish(st)
         _capi.check(self._lib.ga3c_apply_rmsprop(self._h, float(self.learning_rate), st.cuda_stream), "ga3c_apply_rmsprop")
+
+    @staticmethod
+    def _zero(t: torch.Tensor, stream):
+        with torch.cuda.stream(stream):
+            t.zero_()
+
+    def sync_replicas(self, src: int = 0):
+        """Data parallel: make every rank's weights, RMSProp slots and step counter equal rank `src`'s (a collective: every
+        rank calls it).  Run at construction, after load() and available after set_variables() / set_slots() with
+        rank-dependent values."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        which = [0, 2, 3] + ([5, 6] if self._dual else [])
+        for w in which:
+            t = torch.from_numpy(self._download(w)).to(self._tdev)
+            dist.broadcast(t, src=src)
+            self._upload(w, t.cpu().numpy())
+        step = torch.tensor([self.get_global_step()], dtype=torch.int64, device=self._tdev)
+        dist.broadcast(step, src=src)
+        self._lib.ga3c_set_global_step(self._h, int(step.item()))
 
     # ------------------------------------------------------------------ reference API (host numpy)
     def predict_p_and_v(self, x):
@@ -257,9 +317,8 @@ class Network:
         with self._lock:
             self._ensure(b)
             hx, dx = self._io_u8() if x.dtype == np.uint8 else (self._hx, self._dx)
-            src = self._stage(x, hx, b)
             with torch.cuda.stream(self._stream):
-                dx[:b].copy_(src, non_blocking=True)
+                self._h2d(x, hx, dx, b)
                 self.predict_device(dx[:b], self._dp_out[:b], self._dv_out[:b], stream=self._stream)
                 self._hp[:b].copy_(self._dp_out[:b], non_blocking=True)
                 self._hv[:b].copy_(self._dv_out[:b], non_blocking=True)
@@ -281,24 +340,35 @@ class Network:
         x = np.asarray(x)
         b = x.shape[0]
         if b == 0:
-            return None
+            if self.dp_mode is None:
+                return None
+            # data parallel: every rank enters every step; an empty batch contributes a zero gradient (ga3c_train_step with
+            # batch = 0) and this rank applies the same update as the others
+            with self._lock:
+                with torch.cuda.stream(self._stream):
+                    self.train_device(self._dx[:0], self._dyr[:0], self._da[:0],
+                                      loss_out=self._loss_dev if fetch_losses else None, stream=self._stream)
+                self._stream.synchronize()
+            self.dp_check()
+            return dict(cost_p_1=0.0, cost_p_2=0.0, cost_p=0.0, cost_v=0.0, cost_all=0.0) if fetch_losses else None
         x = self._frames(x, self.state_dim)
         y_r = np.asarray(y_r, dtype=np.float32).reshape(b)
         a = np.asarray(a, dtype=np.float32).reshape(b, self.num_actions)
         with self._lock:
             self._ensure(b)
             hx, dx = self._io_u8() if x.dtype == np.uint8 else (self._hx, self._dx)
-            sx = self._stage(x, hx, b)
-            syr = self._stage(y_r, self._hyr, b)
-            sa = self._stage(a, self._ha, b)
             with torch.cuda.stream(self._stream):
-                dx[:b].copy_(sx, non_blocking=True)
-                self._dyr[:b].copy_(syr, non_blocking=True)
-                self._da[:b].copy_(sa, non_blocking=True)
+                self._h2d(y_r, self._hyr, self._dyr, b)
+                self._h2d(a, self._ha, self._da, b)
+                self._h2d(x, hx, dx, b)
                 self.train_device(dx[:b], self._dyr[:b], self._da[:b],
                                   loss_out=self._loss_dev if fetch_losses else None, stream=self._stream)
                 losses = self._loss_dev.cpu() if fetch_losses else None
             self._stream.synchronize()
+        if self.dp_mode == "fused":
+            self._dp_steps = getattr(self, "_dp_steps", 0) + 1
+            if self._dp_steps % 64 == 1:      # a timed-out cross-rank wait leaves garbage weights: fail, do not train on
+                self.dp_check()
         if fetch_losses:
             c1, c2, cv = (float(v) for v in losses[:3])
             self.last_losses = dict(cost_p_1=c1, cost_p_2=c2, cost_p=-(c1 + c2), cost_v=cv, cost_all=-(c1 + c2) + cv)
@@ -378,7 +448,9 @@ class Network:
         self._upload(0, self._join(0, tensors))
 
     def get_gradients(self):
-        """Gradients left by the last forward_backward (after allreduce when data-parallel)."""
+        """Gradients left by the last forward_backward.  Data parallel: dp_mode 'nccl' leaves the allreduced gradient on every
+        rank; dp_mode 'fused' leaves this rank's OWN contribution, except for the slice of dense1/w this rank owns, which
+        holds the sum over ranks (the reduction happens on the owner; only the bf16 shadow of the new weights travels)."""
         return self._split(self._download(1))
 
     def get_slots(self, optimizer: int = 0):
@@ -432,6 +504,8 @@ class Network:
             self.set_slots({k: z[k.replace(":0", "/RMSProp_2:0")] for k in names},
                            {k: z[k.replace(":0", "/RMSProp_3:0")] for k in names}, optimizer=1)
         self._lib.ga3c_set_global_step(self._h, int(z["step:0"]))
+        if self.dp_mode is not None:
+            self.sync_replicas()          # every rank read the same file; make sure of it
         return self._get_episode_from_filename(filename)
 
     def dp_check(self):

@@ -139,3 +139,68 @@ class ThreadTrainer(Thread):
                 x, r, a, x2, done = self._next_batch()
             if self.config.TRAIN_MODELS:
                 self.server.train_model(x, r, a, x2, done, self.id)
+
+
+class LockstepTrainer(ThreadTrainer):
+    """The trainer thread of ONE rank of a data-parallel job (every GPU owns a slice of the agents and its own
+    queues; gradients are summed across the ranks inside `model.train`).
+
+    The reference's trainer is fed asynchronously (ThreadTrainer.py:42-62): it trains whenever its own queue yields a batch.
+    The gradient exchange needs every rank to enter every step, so this thread ticks: each round it gathers what its
+    `training_q` yields within `tick` seconds under the reference's stop rule (rows > TRAINING_MIN_BATCH_SIZE ends the
+    round early), the ranks agree with one tiny host allreduce on (rows in total, anybody leaving?), and then ALL of them
+    call `server.train_model` -- a rank whose round came up empty with a 0-row batch, which contributes a zero gradient and
+    applies the same update as everybody else (`Network.train` -> ga3c_train_step with batch = 0).  Rounds in which no rank
+    has rows are skipped by all; when any rank raises its exit flag all ranks leave after the same number of steps.
+    One LockstepTrainer per rank (Config.TRAINERS = 1 per GPU): two would interleave their steps differently on different
+    ranks.  `group`: a torch.distributed group whose backend takes CPU tensors (gloo); default: a new gloo group over all
+    ranks (a collective call -- construct the trainer on every rank)."""
+
+    def __init__(self, server, id, config=None, group=None, tick=0.002):
+        super().__init__(server, id, config)
+        import torch.distributed as dist
+        self.tick = float(tick)
+        self.group = group if group is not None else (dist.new_group(backend="gloo") if dist.get_backend() != "gloo" else None)
+        self.steps = 0              # exchange steps taken (identical on every rank)
+        self.empty_steps = 0        # ... of which this rank contributed no rows
+
+    def _collect(self, q):
+        import queue as _queue
+        import time
+        parts, rows = [], 0
+        deadline = time.monotonic() + self.tick
+        while rows <= self.config.TRAINING_MIN_BATCH_SIZE:
+            left = deadline - time.monotonic()
+            try:
+                item = q.get(True, left) if left > 0 else q.get(False)
+            except _queue.Empty:
+                break
+            parts.append(item)
+            rows += item[0].shape[0]
+        return parts, rows
+
+    def run(self):
+        import torch
+        import torch.distributed as dist
+        q = self.server.training_q
+        model = self.server.model
+        sdim, na = int(model.state_dim), int(model.num_actions)
+        while True:
+            parts, rows = self._collect(q)
+            flags = torch.tensor([rows, 1 if self.exit_flag else 0], dtype=torch.int64)
+            dist.all_reduce(flags, op=dist.ReduceOp.SUM, group=self.group)
+            if int(flags[1]) > 0:
+                break
+            if int(flags[0]) == 0:
+                continue
+            if not parts:
+                item = (np.zeros((0, sdim), np.float32), np.zeros(0, np.float64), np.zeros((0, na), np.float32),
+                        np.zeros((0, 0), np.float32), np.zeros(0, np.bool_))
+                self.empty_steps += 1
+            elif len(parts) == 1:
+                item = parts[0]
+            else:
+                item = tuple(np.concatenate([p[k] for p in parts]) for k in range(5))
+            self.steps += 1
+            if self.config.TRAIN_MODELS:
+                self.server.train_model(*item, self.id)

@@ -19,17 +19,24 @@ queues; tests/test_transport.py does exactly that where /root/reference is prese
 the batch calls (`get_batch`, `reply_batch`): one gather into a pinned buffer and one reply scatter per batch instead of
 128 queue operations.  Blocking uses OS semaphores (no busy-waiting: 256 agents share the host's cores).
 
-Memory ordering: a producer writes the payload, then the flag byte; x86-64 keeps stores in order and numpy's copies are
-plain stores, so a consumer that sees the flag sees the payload.
+Memory ordering: a producer writes the payload, then the flag byte; x86-64 keeps stores in order (TSO) and numpy's copies
+are plain stores, so a consumer that sees the flag sees the payload.  That is an x86-64 property: on a weakly ordered host
+(aarch64, e.g. Grace-based Blackwell nodes) a consumer on the flag-polling path could see `pending = 1` before the row.  The
+module refuses to import there rather than hand over stale frames (a port needs a release fence after the payload copy and
+an acquire fence after the flag read: take the semaphore permit before touching the row).
 """
 from __future__ import annotations
 
 import mmap
 import multiprocessing as mp
+import platform
 import threading
 from multiprocessing import shared_memory
 
 import numpy as np
+
+if platform.machine().lower() not in ("x86_64", "amd64", "i686", "i386"):      # see "Memory ordering" above
+    raise ImportError(f"ga3c_b200.transport relies on x86-64 store ordering; this host is {platform.machine()!r}")
 
 
 class _Shm:
@@ -99,17 +106,28 @@ class SlabPredictionQueue:
         self._lock = threading.Lock()
 
     # ---- producer side (agent processes) ----
+    def _check_id(self, aid):
+        # ids are rows of the slab: an id outside 0 .. num_agents-1 (e.g. the reference's NETWORK_TESTER_ID = 100 with fewer
+        # agents, ThreadPredictor.py:64-66) must not alias another agent's row through negative / wrapped indexing
+        if not 0 <= int(aid) < self.num_agents:
+            raise IndexError(f"agent id {aid} outside 0..{self.num_agents - 1}: size the slab queue for every producer id")
+
     def put(self, item, block=True, timeout=None):
+        """One outstanding request per agent (wait_q has maxsize 1, ProcessAgent.py:64), so a row is always free when its
+        agent puts: `block` / `timeout` are accepted for Queue compatibility and never needed."""
         aid, state = item
+        self._check_id(aid)
         self._states.array[aid] = np.asarray(state).reshape(-1)
         self._pending.array[aid] = 1
         self._work.release()
 
     def state_row(self, aid):
         """The agent's own row, for environments that render straight into shared memory (then call `post`)."""
+        self._check_id(aid)
         return self._states.array[aid]
 
     def post(self, aid):
+        self._check_id(aid)
         self._pending.array[aid] = 1
         self._work.release()
 
@@ -270,6 +288,8 @@ class SlabTrainingQueue:
 
     def put_from(self, aid, item, block=True, timeout=None):
         x, r, a, x2, done = item
+        if not 0 <= int(aid) < self.num_agents:
+            raise IndexError(f"agent id {aid} outside 0..{self.num_agents - 1}")
         n = int(np.asarray(x).shape[0])
         if n > self.max_rows:
             raise ValueError(f"training item of {n} rows exceeds max_rows={self.max_rows} (Config.TIME_MAX + 1)")

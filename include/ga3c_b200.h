@@ -53,7 +53,9 @@ typedef struct ga3c_config {
   int32_t dual_rmsprop;      /* Config.DUAL_RMSPROP     (False): cost_p and cost_v minimised by two RMSProp optimizers with
                               * their own slots (NetworkVP_discrate.py:87-98, :124-128).  TensorFlow runs the two train ops in
                               * no defined order; here both gradients are taken at the weights the call started with and
-                              * both steps are subtracted; global_step advances by 2.  Single GPU, without USE_GRAD_CLIP. */
+                              * both steps are subtracted; global_step advances by 2.  With USE_GRAD_CLIP each optimizer's
+                              * gradients go through tf.clip_by_norm per variable and global_step stays put
+                              * (NetworkVP_discrate.py:107-117).  Data parallel: dp_mode 'nccl' only (two allreduces).       */
 } ga3c_config;
 
 const char* ga3c_last_error(void);
@@ -75,6 +77,8 @@ int     ga3c_param_info(const ga3c_net* net, int index, const char** name, int64
 int64_t ga3c_arena_floats(const ga3c_net* net);
 /* device base pointers of the four arenas (any may be NULL to skip) */
 int ga3c_arena_ptrs(ga3c_net* net, float** params_dev, float** grads_dev, float** ms_dev, float** mom_dev);
+/* one arena by id (the ids of ga3c_arena_upload below) */
+int ga3c_arena_ptr(ga3c_net* net, int which, float** ptr_dev);
 /* host <-> device copies of a whole arena; which: 0 params, 1 grads, 2 ms, 3 mom; with dual_rmsprop also 4 / 5 / 6: gradient,
  * ms, mom of the second optimizer (the one minimising cost_v; 1 / 2 / 3 then belong to cost_p).  Synchronous.
  * Writing params also refreshes the bf16 shadow of dense1/w. */
@@ -104,6 +108,12 @@ int ga3c_fb_tail(ga3c_net* net, const float* x_dev, int32_t batch, void* stream)
 int ga3c_apply_rmsprop(ga3c_net* net, float learning_rate, void* stream);
 int ga3c_train_step(ga3c_net* net, const float* x_dev, const float* yr_dev, const float* a_dev,
                     int32_t batch, float learning_rate, float beta, float* loss_dev, void* stream);
+/* Config.DUAL_RMSPROP in two halves (handles created with dual_rmsprop): both gradients (cost_p -> arena 1, cost_v -> arena 4),
+ * then the update with both optimizers' steps.  ga3c_train_step is the two back to back; a data-parallel host allreduces
+ * arenas 1 and 4 in between (dp_mode 'nccl'). */
+int ga3c_dual_forward_backward(ga3c_net* net, const float* x_dev, const float* yr_dev, const float* a_dev, int32_t batch,
+                               float beta, float* loss_dev, void* stream);
+int ga3c_dual_apply(ga3c_net* net, float learning_rate, void* stream);
 
 /* ---- uint8 frame ingestion ---------------------------------------------------------
  * Same calls with x8_dev = uint8 [B, 28224]: the raw 0..255 pixels BEFORE the reference's
@@ -118,6 +128,8 @@ int ga3c_fb_head_u8(ga3c_net* net, const uint8_t* x8_dev, const float* yr_dev, c
 int ga3c_fb_tail_u8(ga3c_net* net, const uint8_t* x8_dev, int32_t batch, void* stream);
 int ga3c_train_step_u8(ga3c_net* net, const uint8_t* x8_dev, const float* yr_dev, const float* a_dev,
                        int32_t batch, float learning_rate, float beta, float* loss_dev, void* stream);
+int ga3c_dual_forward_backward_u8(ga3c_net* net, const uint8_t* x8_dev, const float* yr_dev, const float* a_dev, int32_t batch,
+                                  float beta, float* loss_dev, void* stream);
 
 /* ---- data parallel over peer memory (one process per GPU, one node, <= 8 ranks) ---------------------
  * Every rank exports a CUDA IPC handle of its state slab (ga3c_dp_export), the host exchanges the handles
@@ -127,7 +139,9 @@ int ga3c_train_step_u8(ga3c_net* net, const uint8_t* x8_dev, const float* yr_dev
  * apply RMSProp to the slice, store the new weights into every rank's slab; the last block to finish publishes
  * "done" and holds the kernel open until every rank is done, so the next forward sees all slices.  SUM, no averaging:
  * every loss term is a reduce_sum (NetworkVP_discrate.py:61,:83-85).  All ranks must call train the same number
- * of times. */
+ * of times; a rank with nothing to train on calls ga3c_train_step with batch = 0 (buffers may be NULL): it contributes a
+ * zero gradient and applies the same update as everybody else (the host-side lock step that makes the reference's
+ * asynchronous trainer loop, ThreadTrainer.py:42-62, fit this rule is ga3c_b200.threads.LockstepTrainer). */
 int ga3c_dp_handle_bytes(void);
 int ga3c_dp_export(ga3c_net* net, void* handle_out);
 int ga3c_dp_attach(ga3c_net* net, int32_t rank, int32_t world, const void* handles);
@@ -219,7 +233,8 @@ int ga3c_mlp_timing_collect(ga3c_mlp* net, double* total_ms, int64_t* counts, in
 /* ---- introspection for tests / profiling ---------------------------------------------------- */
 /* device pointers to the activation workspace of the last call (bf16 stored as uint16):
  * which: 0 n1 [B,441,16] bf16, 1 n2 [B,3872] bf16, 2 d1 [B,256] fp32, 3 dd1 [B,256] bf16,
- *        4 dn2 [B,3872] bf16, 5 dn1 [B,441,16] bf16 */
+ *        4 dn2 [B,3872] bf16, 5 dn1 [B,441,16] bf16, 6 the bf16 shadow of dense1/w [3872,256] (what the dense1 GEMMs read; in a
+ *        data-parallel job the copy every rank holds, so comparing it across ranks checks the exchange) */
 int ga3c_workspace_ptr(ga3c_net* net, int which, void** ptr_dev, int64_t* bytes);
 /* dn1 (the conv12 data gradient) normally never leaves the SM: the fused conv backward kernel consumes it from shared
  * memory.  on != 0 makes that kernel also store it to the workspace (id 5 above) so that tests can compare it. */

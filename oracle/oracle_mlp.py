@@ -199,9 +199,10 @@ def train_step(params, ms, mom, x, y_r, a, kind: str, *, lr, beta=0.01, log_eps=
 
 
 def train_step_dual(params, slots_p, slots_v, x, y_r, a, kind: str, *, lr, beta=0.01, log_eps=1e-6, min_policy=0.0,
-                    rho=0.99, mu=0.0, eps=0.1, dtype=np.float32):
+                    rho=0.99, mu=0.0, eps=0.1, dtype=np.float32, grad_clip=None):
     """Config.DUAL_RMSPROP (NetworkVP.py:107-118, :143-147); semantics as oracle_np.train_step_dual: both gradients at the
-    pre-call weights, w <- w - step_p - step_v, a variable a cost does not reach is skipped by that optimizer."""
+    pre-call weights, w <- w - step_p - step_v, a variable a cost does not reach is skipped by that optimizer.
+    grad_clip: with USE_GRAD_CLIP each optimizer's gradients go through tf.clip_by_norm per variable (NetworkVP.py:127-137)."""
     from . import oracle_np as onp
     kw = dict(beta=beta, log_eps=log_eps, min_policy=min_policy, dtype=np.float64)
     losses, gp = loss_and_grads(params, x, y_r, a, kind, part="p", **kw)
@@ -209,6 +210,8 @@ def train_step_dual(params, slots_p, slots_v, x, y_r, a, kind: str, *, lr, beta=
     new_p = {k: v.astype(dtype) for k, v in params.items()}
     out = []
     for g, (ms, mom) in ((gp, slots_p), (gv, slots_v)):
+        if grad_clip is not None:
+            g = {k: onp.clip_by_norm(v, grad_clip) for k, v in g.items()}
         p2, ms2, mom2 = onp.rmsprop_update({k: params[k] for k in g}, g, {k: ms[k] for k in g}, {k: mom[k] for k in g},
                                            lr=lr, rho=rho, mu=mu, eps=eps, dtype=dtype)
         for k in g:

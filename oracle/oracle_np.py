@@ -291,8 +291,14 @@ def train_step(params, ms, mom, x, y_r, a, *, lr, beta=0.01, log_eps=1e-6, min_p
     return losses, grads, p2, ms2, mom2
 
 
+def clip_by_norm(g, clip_norm):
+    """tf.clip_by_norm(g, c) [TF-SEMANTICS]: g * c / max(||g||_2, c)  (NetworkVP_discrate.py:109-110, :114-115)."""
+    g = np.asarray(g, dtype=np.float64)
+    return g * clip_norm / max(np.sqrt((g * g).sum()), clip_norm)
+
+
 def train_step_dual(params, slots_p, slots_v, x, y_r, a, *, lr, beta=0.01, log_eps=1e-6, min_policy=0.0, use_log_softmax=False,
-                    rho=0.99, mu=0.0, eps=0.1, dtype=np.float64, quant=None):
+                    rho=0.99, mu=0.0, eps=0.1, dtype=np.float64, quant=None, grad_clip=None):
     """Config.DUAL_RMSPROP (NetworkVP_discrate.py:87-98, :124-128): train_op = [minimize(cost_p), minimize(cost_v)], two
     RMSProp optimizers with their own slots.  TensorFlow runs the two train ops of one sess.run in no defined order;
     this restatement takes the order-independent reading [TF-SEMANTICS]: both gradients at the pre-call weights (the forward
@@ -305,6 +311,8 @@ def train_step_dual(params, slots_p, slots_v, x, y_r, a, *, lr, beta=0.01, log_e
     new_p = {k: v.astype(dtype) for k, v in params.items()}
     out_slots = []
     for g, (ms, mom) in ((gp, slots_p), (gv, slots_v)):
+        if grad_clip is not None:       # DUAL_RMSPROP + USE_GRAD_CLIP: clip_by_norm per variable and optimizer (:107-117)
+            g = {k: clip_by_norm(v, grad_clip) for k, v in g.items()}
         sub = {k: params[k] for k in g}
         p2, ms2, mom2 = rmsprop_update(sub, g, {k: ms[k] for k in g}, {k: mom[k] for k in g}, lr=lr, rho=rho, mu=mu, eps=eps, dtype=dtype)
         for k in g:

@@ -85,3 +85,71 @@ def test_allreduce_is_a_no_op_without_a_process_group():
     assert torch.equal(arena, torch.arange(10, dtype=torch.float32))
     with pytest.raises(ValueError):
         GradientAllReduce(arena, 11)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the lock-step trainer that makes the asynchronous loop (ThreadTrainer.py:42-62) fit the data-parallel step
+class _StubModel:
+    """Stands in for Network in dp mode: records the row count of every train call; an all_reduce inside train plays the
+    gradient exchange (it would dead-lock if the ranks did not enter the same number of steps)."""
+    state_dim, num_actions = 5, 3
+
+    def __init__(self):
+        self.calls = []
+
+    def train(self, x, r, a, x2, done, trainer_id):
+        t = torch.tensor([float(x.shape[0])])
+        dist.all_reduce(t)
+        self.calls.append((int(x.shape[0]), int(t.item())))
+
+
+class _StubServer:
+    def __init__(self):
+        import queue
+        self.model = _StubModel()
+        self.training_q = queue.Queue(maxsize=100)
+
+    def train_model(self, x, r, a, x2, done, trainer_id):
+        self.model.train(x, r, a, x2, done, trainer_id)
+
+
+def _lockstep_worker(rank, world, port, out_dir):
+    import time
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ga3c_b200 import Config, LockstepTrainer
+
+        class Cfg(Config):
+            TRAINING_MIN_BATCH_SIZE = 0
+        srv = _StubServer()
+        th = LockstepTrainer(srv, 0, config=Cfg, tick=0.01)
+        th.start()
+        n_items = 6 if rank == 0 else 2          # rank 1's agents are slow: most of its rounds come up empty
+        for i in range(n_items):
+            rows = 1 + i % 3
+            srv.training_q.put((np.full((rows, 5), rank, np.float32), np.zeros(rows), np.zeros((rows, 3), np.float32),
+                                np.zeros((rows, 0), np.float32), np.zeros(rows, bool)))
+            time.sleep(0.03 if rank == 0 else 0.1)
+        time.sleep(0.3)
+        th.exit_flag = True
+        th.join(timeout=30)
+        assert not th.is_alive()
+        np.save(os.path.join(out_dir, f"calls{rank}.npy"), np.array(srv.model.calls, dtype=np.int64).reshape(-1, 2))
+        np.save(os.path.join(out_dir, f"stats{rank}.npy"), np.array([th.steps, th.empty_steps]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_lockstep_trainer_keeps_ranks_in_step_with_empty_batches(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_lockstep_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    c0, c1 = np.load(tmp_path / "calls0.npy"), np.load(tmp_path / "calls1.npy")
+    s0, s1 = np.load(tmp_path / "stats0.npy"), np.load(tmp_path / "stats1.npy")
+    assert len(c0) == len(c1) == s0[0] == s1[0] and len(c0) >= 1            # same number of exchange steps on both ranks
+    assert np.array_equal(c0[:, 1], c1[:, 1])                                # ... each with the same global row count
+    assert np.array_equal(c0[:, 0] + c1[:, 0], c0[:, 1]) and (c0[:, 1] > 0).all()   # no step without rows anywhere
+    assert c0[:, 0].sum() == sum(1 + i % 3 for i in range(6)) and c1[:, 0].sum() == sum(1 + i % 3 for i in range(2))
+    assert s1[1] >= 1 and (c1[:, 0] == 0).sum() == s1[1]                     # the slow rank ticked with empty batches

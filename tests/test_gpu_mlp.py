@@ -223,6 +223,36 @@ def test_dual_rmsprop_knob(mlp, kind, s, a):
 
 
 @pytest.mark.parametrize("kind,s,a", CASES)
+def test_dual_rmsprop_with_grad_clip(mlp, kind, s, a):
+    """Config.DUAL_RMSPROP + USE_GRAD_CLIP (NetworkVP.py:127-137, NetworkVP_discrate.py:107-117): tf.clip_by_norm per variable
+    and optimizer; variables without a gradient are filtered (`if not g is None`), so NetworkVP_discrate's gradient-less
+    layers are legal here; the fork's NetworkVP passes global_step to both apply_gradients calls, NetworkVP_discrate to none."""
+    clip = 2e-2
+    class Cfg(mlp._DefaultConfig):
+        DUAL_RMSPROP = True
+        USE_GRAD_CLIP = True
+        GRAD_CLIP_NORM = clip
+    b = 400
+    params, x, y_r, act = make_case(kind, s, a, b, seed=37)
+    net = make_net(mlp, kind, s, a, config=Cfg)
+    net.set_variables(params)
+    ones = {k: np.ones_like(v) for k, v in params.items()}
+    zeros = {k: np.zeros_like(v) for k, v in params.items()}
+    ref, sp, sv = params, (ones, zeros), (ones, zeros)
+    for _ in range(2):
+        net.train(x, y_r, act, None, None, 0)
+        _, gp, gv, ref, sp, sv = om.train_step_dual(ref, sp, sv, x, y_r, act, kind, lr=3e-4, beta=0.01, grad_clip=clip)
+    norms = [float(np.sqrt((g.astype(np.float64) ** 2).sum())) for g in list(gp.values()) + list(gv.values())]
+    assert any(v > clip for v in norms), norms                              # the threshold is active
+    w = net.get_variables()
+    for k in w:
+        assert err(w[k], ref[k])[0] <= 2 * TOL_W_ABS, (k, err(w[k], ref[k]))
+    assert net.get_global_step() == (4 if kind == "fork_vp" else 0)
+    for k in om.dead_params(kind):
+        assert np.array_equal(w[k], params[k])
+
+
+@pytest.mark.parametrize("kind,s,a", CASES)
 def test_train_steps_match_oracle(mlp, kind, s, a):
     """Three opt.minimize steps: weights, ms slot, global_step; gradient-less variables untouched (bit-identical)."""
     b = 777

@@ -64,6 +64,59 @@ def test_layers_and_gradients_match_oracle(ga3c, batch):
     check_report(layer_report(net, params, x, y_r, a))
 
 
+def test_layers_and_gradients_match_oracle_b1024(ga3c):
+    """The benchmarked train shape (BASELINE configs[2], B = 1024 per GPU: 7 rounds of frames per persistent conv CTA, split-K
+    factor of that batch): every stored activation, all 10 gradients and the loss sums of the FULL batch against the oracle."""
+    params, x, y_r, a = make_case(1024, seed=1024)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=1024)
+    check_report(layer_report(net, params, x, y_r, a))
+
+
+def test_predict_b4096_full_batch_matches_oracle(ga3c):
+    """The benchmarked predict shape (configs[1], B = 4096): every row of p and v against the oracle."""
+    rng = np.random.default_rng(40960)
+    params = onp.init_params(rng, 6)
+    x = onp.synth_frames(rng, 4096)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=4096)
+    net.set_variables(params)
+    p, v = net.predict_p_and_v(x)
+    pr, vr = onp.forward(params, x, quant="bf16")
+    assert np.abs(p - pr).max() <= TOL_P and np.abs(v - vr).max() <= TOL_V, (np.abs(p - pr).max(), np.abs(v - vr).max())
+
+
+@pytest.mark.parametrize("batch", [8, 32, 160])
+def test_back_to_back_async_steps_equal_synchronised_steps(ga3c, batch):
+    """The asynchronous API (train_device / the C-ABI on one stream, no host synchronisation between calls): N steps enqueued
+    back to back leave bit-identical weights and slots to the same steps with a device synchronisation after each.  With a
+    batch below the SM count every kernel of a step fits next to the previous step's optimizer launch, which is where a
+    prologue that read mutable state before its dependency wait would see a half-applied update."""
+    import torch
+    rng = np.random.default_rng(batch)
+    params = onp.init_params(rng, 6)
+    steps = 12
+    data = [(onp.synth_frames(rng, batch),) + onp.synth_targets(rng, batch) for _ in range(3)]
+    results = []
+    for sync in (True, False):
+        net = ga3c.Network("gpu:0", "t", 6, max_batch=max(batch, 16))
+        net.set_variables(params)
+        dev = [[torch.as_tensor(t).cuda() for t in d] for d in data]
+        p_out = [torch.empty((batch, 6), device="cuda") for _ in range(steps)]
+        v_out = [torch.empty((batch,), device="cuda") for _ in range(steps)]
+        torch.cuda.synchronize()
+        st = torch.cuda.current_stream()
+        for i in range(steps):
+            net.train_device(*dev[i % 3], stream=st)
+            net.predict_device(dev[(i + 1) % 3][0], p_out[i], v_out[i], stream=st)      # predict-after-train on the same stream
+            if sync:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        results.append((net.get_variables(), net.get_slots()[0], [t.cpu().numpy() for t in p_out], [t.cpu().numpy() for t in v_out]))
+    (w0, m0, p0, v0), (w1, m1, p1, v1) = results
+    for k in w0:
+        assert np.array_equal(w0[k], w1[k]) and np.array_equal(m0[k], m1[k]), k
+    assert all(np.array_equal(a_, b_) for a_, b_ in zip(p0, p1)) and all(np.array_equal(a_, b_) for a_, b_ in zip(v0, v1))
+
+
 @pytest.mark.parametrize("num_actions", [1, 2, 18])
 def test_num_actions_range(ga3c, num_actions):
     params, x, y_r, a = make_case(9, num_actions=num_actions, seed=3)
@@ -135,14 +188,28 @@ def test_data_parallel_exchange_two_ranks_on_one_gpu(ga3c, monkeypatch):
             torch.cuda.synchronize()
             _, _, ref, ms, mom = onp.train_step(ref, ms, mom, x, y_r, a, lr=nets[0].learning_rate, beta=nets[0].beta, quant="bf16")
             ref = {k: v.astype(np.float32) for k, v in ref.items()}
+        # a lock-step round in which rank 1 has nothing to train on: it enters the step with batch = 0 (zero gradient) and
+        # applies the same update -- equal to the oracle's step on rank 0's rows alone
+        x = onp.synth_frames(rng, b)
+        y_r, a = onp.synth_targets(rng, b)
+        d0 = [torch.as_tensor(t).cuda() for t in (x, y_r, a)]
+        d1 = [torch.as_tensor(t[:0]).cuda() for t in (x, y_r, a)]
+        torch.cuda.synchronize()
+        nets[0].train_device(*d0, stream=streams[0])
+        nets[1].train_device(*d1, stream=streams[1])
+        torch.cuda.synchronize()
+        _, _, ref, ms, mom = onp.train_step(ref, ms, mom, x, y_r, a, lr=nets[0].learning_rate, beta=nets[0].beta, quant="bf16")
+        ref = {k: v.astype(np.float32) for k, v in ref.items()}
         for n in nets:
             n.dp_check()
         w = [n.get_variables() for n in nets]
         m = [n.get_slots()[0] for n in nets]
+        sh = [n.workspace(6) for n in nets]
+        assert np.array_equal(sh[0], sh[1])                                                     # the bf16 shadow every rank holds
         for k in params:
             assert np.array_equal(w[0][k], w[1][k]) and np.array_equal(m[0][k], m[1][k]), k     # replicas bit-identical
-            assert np.abs(w[0][k] - ref[k]).max() <= 3 * TOL_W_ABS, (k, np.abs(w[0][k] - ref[k]).max())
-        assert nets[0].get_global_step() == 3
+            assert np.abs(w[0][k] - ref[k]).max() <= 4 * TOL_W_ABS, (k, np.abs(w[0][k] - ref[k]).max())
+        assert nets[0].get_global_step() == 4 and nets[1].get_global_step() == 4
     finally:
         for n in nets:
             lib.ga3c_dp_detach(n._h)
@@ -205,6 +272,102 @@ def test_dual_rmsprop_knob(ga3c):
         assert err(g_p[k], gp[k])[1] <= TOL_GRAD_REL, (k, err(g_p[k], gp[k]))
     for k in gv:
         assert err(g_v[k], gv[k])[1] <= TOL_GRAD_REL, (k, err(g_v[k], gv[k]))
+
+
+def test_dual_rmsprop_with_grad_clip(ga3c):
+    """Config.DUAL_RMSPROP + USE_GRAD_CLIP (NetworkVP_discrate.py:107-117): tf.clip_by_norm per variable on each optimizer's
+    gradients (threshold chosen so that it is active on some variables and not on others), two RMSProp steps from the
+    pre-call weights, and no global_step (apply_gradients is called without it)."""
+    clip = 5e-3
+    class Cfg(ga3c.Config):
+        DUAL_RMSPROP = True
+        USE_GRAD_CLIP = True
+        GRAD_CLIP_NORM = clip
+    params, x, y_r, a = make_case(40, seed=31)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=64, config=Cfg)
+    net.set_variables(params)
+    ms, mom = onp.rmsprop_init(params)
+    ref, sp, sv = params, (ms, mom), (ms, mom)
+    for step in range(2):
+        net.train(x, y_r, a, None, None, 0)
+        _, gp, gv, ref, sp, sv = onp.train_step_dual(ref, sp, sv, x, y_r, a, lr=net.learning_rate, beta=net.beta, quant="bf16",
+                                                     grad_clip=clip)
+        ref = {k: v.astype(np.float32) for k, v in ref.items()}
+    norms = [float(np.sqrt((g.astype(np.float64) ** 2).sum())) for g in list(gp.values()) + list(gv.values())]
+    assert any(v > clip for v in norms) and any(v < clip for v in norms), norms
+    w = net.get_variables()
+    for k in w:
+        assert np.abs(w[k] - ref[k]).max() <= 2 * TOL_W_ABS, (k, np.abs(w[k] - ref[k]).max())
+    ms_p, _ = net.get_slots(0)
+    ms_v, _ = net.get_slots(1)
+    for k in w:
+        assert err(ms_p[k] - 0.99 ** 2, sp[0][k] - 0.99 ** 2)[1] <= 2 * TOL_GRAD_REL or np.array_equal(ms_p[k], np.ones_like(ms_p[k])), k
+        assert err(ms_v[k] - 0.99 ** 2, sv[0][k] - 0.99 ** 2)[1] <= 2 * TOL_GRAD_REL or np.array_equal(ms_v[k], np.ones_like(ms_v[k])), k
+    assert net.get_global_step() == 0
+
+
+def test_log_writes_the_reference_scalars(ga3c, tmp_path, monkeypatch):
+    """Network.log (NetworkVP.py:259-265; called by Server.py:149-150 every TENSORBOARD_UPDATE_FREQUENCY steps): a second
+    forward pass that records Pcost_advantage, Pcost_entropy, Pcost, Vcost, LearningRate, Beta -- and leaves the weights,
+    the slots and the step counter alone."""
+    monkeypatch.chdir(tmp_path)
+    params, x, y_r, a = make_case(24, seed=41)
+    net = ga3c.Network("gpu:0", "logtest", 6, max_batch=32)
+    net.set_variables(params)
+    net.learning_rate, net.beta = 1e-4, 0.02
+    net.log(x, y_r, a, 7)
+    net.log(x[:5], y_r[:5], a[:5], 8)
+    rows = [l.strip().split(",") for l in open(tmp_path / "logs" / "logtest" / "scalars.csv")]
+    assert [int(r[0]) for r in rows] == [7, 8] and all(len(r) == 7 for r in rows)
+    l_ref, _ = onp.loss_and_grads(params, x, y_r, a, beta=0.02, quant="bf16")
+    got = [float(v) for v in rows[0][1:]]
+    want = [l_ref["cost_p_1"], l_ref["cost_p_2"], l_ref["cost_p"], l_ref["cost_v"], 1e-4, 0.02]
+    assert np.allclose(got, want, rtol=TOL_LOSS_REL, atol=1e-5), (got, want)
+    w = net.get_variables()
+    assert all(np.array_equal(w[k], params[k]) for k in w) and net.get_global_step() == 0
+
+
+def test_slab_transport_feeds_the_cuda_network(ga3c):
+    """8f F1 on the GPU: agents post uint8 frames into the shared-memory slab queue, ga3c_b200.ThreadPredictor gathers them
+    into its pinned batch and calls the CUDA Network, replies travel back through the slab; the trainer path likewise.  Every
+    reply equals the oracle's prediction for the frame that agent posted."""
+    import time
+    from ga3c_b200.transport import SlabPredictionQueue, SlabTrainingQueue
+    n_agents = 48
+    rng = np.random.default_rng(51)
+    params = onp.init_params(rng, 6)
+    k = rng.integers(0, 256, size=(n_agents, onp.STATE_DIM), dtype=np.uint8)
+    x = k.astype(np.float32) / 128.0 - 1.0
+    y_r, a = onp.synth_targets(rng, n_agents)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=128)
+    net.set_variables(params)
+    pq = SlabPredictionQueue(n_agents, onp.STATE_DIM, 6, dtype=np.uint8)
+    tq = SlabTrainingQueue(n_agents, max_rows=4, state_dim=onp.STATE_DIM, num_actions=6, dtype=np.uint8)
+    srv = _Server(net, n_agents)
+    srv.training_q = tq
+    pred = ga3c.ThreadPredictor(srv, 0, onp.STATE_DIM, pq)
+    class Cfg(ga3c.Config):
+        TRAINING_MIN_BATCH_SIZE = 30
+    tr = ga3c.ThreadTrainer(srv, 0, config=Cfg)
+    pred.start(); tr.start()
+    try:
+        pq.post_many(np.arange(n_agents), k)
+        p = np.zeros((n_agents, 6), np.float32); v = np.zeros(n_agents, np.float32)
+        assert pq.wait_many(np.arange(n_agents), p, v, timeout=60) == n_agents
+        pr, vr = onp.forward(params, x, quant="bf16")
+        assert np.abs(p - pr).max() <= TOL_P and np.abs(v - vr).max() <= TOL_V
+        assert pred.rows == n_agents
+        for i in range(0, n_agents, 4):                                     # 12 agent batches of 4 rows
+            tq.for_agent(i).put((k[i:i + 4], y_r[i:i + 4].astype(np.float64), a[i:i + 4], k[i:i + 4], np.zeros(4, bool)))
+        t0 = time.time()
+        while sum(srv.trained) < 32 and time.time() - t0 < 60:
+            time.sleep(0.01)
+        assert srv.trained and srv.trained[0] == 32                         # 8 x 4 rows: the first count that EXCEEDS 30
+        assert net.get_global_step() >= 1
+    finally:
+        pred.exit_flag = True; tr.exit_flag = True
+        time.sleep(0.2)
+        pq.close(); tq.close()
 
 
 def test_golden_network_b4(ga3c, golden_dir):

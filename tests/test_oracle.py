@@ -227,6 +227,25 @@ def test_clip_by_average_norm_known_answers():
     assert np.allclose(onp.clip_by_average_norm(g, 1.0), ref.numpy())
 
 
+def test_clip_by_norm_known_answers_and_dual_clip_step(small):
+    """tf.clip_by_norm: t * clip / max(||t||, clip) [TF-SEMANTICS]; DUAL_RMSPROP + USE_GRAD_CLIP clips every variable's gradient
+    of each optimizer before its own RMSProp step (NetworkVP_discrate.py:107-117)."""
+    g = np.array([[3.0, 4.0]])
+    assert np.allclose(onp.clip_by_norm(g, 1.0), g / 5.0) and np.array_equal(onp.clip_by_norm(g, 5.0), g)
+    t = torch.tensor(g)
+    assert np.allclose(onp.clip_by_norm(g, 2.0), (t * 2.0 / torch.clamp(torch.linalg.vector_norm(t), min=2.0)).numpy())
+    params, x, y_r, a = small
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    ms, mom = onp.rmsprop_init(p64)
+    clip = 1e-2
+    _, gp, gv, new_p, _, _ = onp.train_step_dual(p64, (ms, mom), (ms, mom), x, y_r, a, lr=1e-2, grad_clip=clip)
+    k = "dense1/b:0"
+    cp, cv = onp.clip_by_norm(gp[k], clip), onp.clip_by_norm(gv[k], clip)
+    assert np.sqrt((gp[k] ** 2).sum()) > clip                           # the clip is active on this variable
+    exp = p64[k] - 1e-2 * cp / np.sqrt(0.99 + 0.01 * cp ** 2 + 0.1) - 1e-2 * cv / np.sqrt(0.99 + 0.01 * cv ** 2 + 0.1)
+    assert np.allclose(new_p[k], exp, rtol=0, atol=1e-14)
+
+
 def test_rmsprop_tf_semantics():
     """eps inside the sqrt, ms initialised to 1.0."""
     w = {"w": np.array([1.0, -2.0], dtype=np.float32)}
@@ -261,3 +280,31 @@ def test_bf16_mode_is_close_to_fp64(small):
     pq, vq = onp.forward(params, x, quant="bf16")
     assert np.abs(p - pq).max() < 5e-3 and np.abs(v - vq).max() < 5e-3
     assert np.abs(p.sum(axis=1) - 1).max() < 1e-12
+
+
+def test_tf_reference_pin(golden_dir):
+    """Opt-in pin against the REAL reference: tests/golden/tf_reference_b4.npz is written by tools/dump_tf_reference.py on a box
+    that has TensorFlow (this build container has none, so the file does not exist yet and the network arithmetic stays
+    'parity unpinned').  When present: the oracle in fp32 must reproduce TensorFlow's fp32 graph -- predictions, the five
+    loss scalars, all ten gradients, and weights / RMSProp slots after one train step -- which settles every [TF-SEMANTICS]
+    assumption at once (SAME padding split, tf.maximum sub-gradient, epsilon inside the sqrt, ms initialised to 1)."""
+    import os
+    path = os.path.join(golden_dir, "tf_reference_b4.npz")
+    if not os.path.exists(path):
+        pytest.skip("no TensorFlow dump committed (tools/dump_tf_reference.py needs a TensorFlow box)")
+    g = np.load(path)
+    from _parity import make_case
+    params, x, y_r, a = make_case(int(g["batch"]))
+    lr, beta = float(g["lr"]), float(g["beta"])
+    p, v = onp.forward(params, x, dtype=np.float32)
+    assert np.abs(p - g["p"]).max() <= 1e-5 and np.abs(v - g["v"]).max() <= 1e-4 * max(1.0, np.abs(g["v"]).max())
+    ms, mom = onp.rmsprop_init(params)
+    losses, grads, p2, ms2, mom2 = onp.train_step(params, ms, mom, x, y_r, a, lr=lr, beta=beta, dtype=np.float32)
+    got = np.array([losses[k] for k in ("cost_p_1", "cost_p_2", "cost_p", "cost_v", "cost_all")])
+    assert np.allclose(got, g["losses"], rtol=1e-4, atol=1e-5)
+    for k in onp.PARAM_NAMES:
+        ref = g["grad_" + k]
+        assert np.abs(grads[k] - ref).max() <= 1e-4 * max(np.abs(ref).max(), 1e-30), k
+        assert np.abs(p2[k] - g["after_" + k]).max() <= 1e-6, k
+        assert np.allclose(ms2[k], g["after_" + k.replace(":0", "/RMSProp:0")], rtol=1e-4), k
+    assert int(g["after_step:0"]) == 1

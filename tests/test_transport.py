@@ -247,12 +247,14 @@ def test_agents_in_processes_through_predictor_and_trainer_threads():
     try:
         for p in procs:
             p.start()
-        res = dict(out.get(timeout=60) for _ in procs)
+        res = dict(out.get(timeout=180) for _ in procs)
         for p in procs:
-            p.join(timeout=10)
+            p.join(timeout=30)
         assert res == {i: 0 for i in range(n_agents)}                    # every reply reached the agent that asked
-        assert pred.rows == n_agents * n_steps and max(server.model.batches) > 1
-        deadline = time.time() + 10
+        # (how many requests share a predictor batch depends on the scheduler, so batch sizes are not asserted here;
+        #  test_prediction_queue_contract_single_process pins the batching rule deterministically)
+        assert pred.rows == n_agents * n_steps and sum(server.model.batches) == pred.rows
+        deadline = time.time() + 60
         while len(server.trained) < n_agents * n_steps // t_max and time.time() < deadline:
             time.sleep(0.01)
         assert len(server.trained) == n_agents * n_steps // t_max
