@@ -150,6 +150,12 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
   griddep_launch();
   evt_mark(evt_i, 50, 0);
   griddep_wait(K_CONV12_BWD);   // dn2 comes from the dense1 data-gradient GEMM that precedes this kernel
+  if (DP && blockIdx.x == 0 && tid < dp.world) {
+    // data parallel: dense_bwd of this rank is complete, i.e. its dense1/w gradient is final -- tell every rank now, a whole
+    // conv backward before the exchange at the end of the step needs it (dp_tail_kernel)
+    __threadfence_system();
+    dp_st_flag(dp.peer[tid] + dp.comm_offset + DPC_BIGREADY + 64 * dp.rank, dp.step);
+  }
   // data-gradient weights as the UMMA B operand (K-major, no swizzle): tap (a, b), k-chunk j (8 co), row n = (py, px, ci)
   for (int i = tid; i < 4 * 4 * 64; i += FB_THREADS) {
     const int tap = i >> 8, j = (i >> 6) & 3, n = i & 63, a = tap >> 1, b = tap & 1, py = n >> 5, px = (n >> 4) & 1, ci = n & 15;
@@ -474,8 +480,8 @@ int launch_conv_bwd(const void* x, bool x_u8, const uint16_t* n1, const uint16_t
   if (dp != nullptr) d = *dp;
   const int n_conv = conv_bwd_grid(batch, num_sms, d.n_exch);
   const dim3 grid(n_conv + d.n_exch);
-  auto kernel = d.n_exch > 0 ? (x_u8 ? conv_bwd_kernel<true, true> : conv_bwd_kernel<false, true>)
-                             : (x_u8 ? conv_bwd_kernel<true, false> : conv_bwd_kernel<false, false>);
+  auto kernel = dp != nullptr ? (x_u8 ? conv_bwd_kernel<true, true> : conv_bwd_kernel<false, true>)
+                              : (x_u8 ? conv_bwd_kernel<true, false> : conv_bwd_kernel<false, false>);
   return launch_pdl(kernel, grid, dim3(FB_THREADS), FB_SMEM, stream, x, n1, dn2, w12, dn1_out, g_w11, g_b11, g_w12, g_b12,
                     gp_stride, batch, n_conv, d);
 }

@@ -553,38 +553,46 @@ GA3C_EVT_ATTACH(evt_attach_elementwise)
 // the step parity: a peer pushes step s + 2 only after it has seen this rank's step s + 1, i.e. after this rank's step-s
 // launch has ended.  Block 0 keeps the launch open until every rank's dense1/w slice (exchange CTAs of the conv backward
 // launch) has landed.
+// The small-tensor instalment in two phases, shared by dp_small_kernel (overlapped exchange) and dp_tail_kernel (exchange at the
+// end of the step).  Phase 1: slab sums of this block's 32 float4 columns, LL push of the sums to every peer.  Phase 2: collect
+// the peers' sums (they have had the time in between to arrive), add in rank order, RMSProp on the local copy.
+struct DpSmallState {
+  float4 w, ms, mo, acc;
+  int j;
+  bool owner;
+};
 template <bool HAS_MOM>
-__global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_small_kernel(RmsPropDpArgs d, int64_t recv_offset) {
-  __shared__ float4 part[GR_LANES][GR_COLS];
+__device__ __forceinline__ void dp_small_phase1(const RmsPropDpArgs& d, int64_t recv_offset, int cb, bool pre_wait_loads, int kid,
+                                                EvtLog& evt_i, DpSmallState& st, float4 (*part)[GR_COLS]) {
   const RmsPropArgs& a = d.base;
   const GradReduceArgs& r = d.red;
-  EvtLog evt_i = evt_open();
   const int col = threadIdx.x & (GR_COLS - 1), sl = threadIdx.x / GR_COLS;
-  const int cb = blockIdx.x;
   const int j = (cb * GR_COLS + col) * 4;
-  const bool owner = sl == 0 && j < r.out_floats;
-  uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
+  st.j = j;
+  st.owner = sl == 0 && j < r.out_floats;
   int count = 0;
   if (j < r.n_floats) {
 #pragma unroll
     for (int s = GR_MAX_SEG - 1; s >= 0; --s)
       if (j < r.seg_end[s]) count = r.seg_count[s];
   }
-  // w / ms of the small prefix were last written by this kernel one step ago: fetch them before the dependency wait
-  float4 w = make_float4(0.f, 0.f, 0.f, 0.f), ms = w, mo = w;
-  if (owner && a.preload) {           // see rmsprop_reduce_kernel for when the early loads are safe
-    w = *reinterpret_cast<const float4*>(a.w + j);
-    ms = *reinterpret_cast<const float4*>(a.ms + j);
-    if (HAS_MOM) mo = *reinterpret_cast<const float4*>(a.mom + j);
-  }
-  griddep_launch();
-  evt_mark(evt_i, 60, 0);
-  griddep_wait(K_RMSPROP);            // the slabs come from the conv backward launch that precedes this one
-  evt_mark(evt_i, 61, 0);
-  if (owner && !a.preload) {
-    w = *reinterpret_cast<const float4*>(a.w + j);
-    ms = *reinterpret_cast<const float4*>(a.ms + j);
-    if (HAS_MOM) mo = *reinterpret_cast<const float4*>(a.mom + j);
+  st.w = make_float4(0.f, 0.f, 0.f, 0.f); st.ms = st.w; st.mo = st.w;
+  auto load_state = [&]() {
+    st.w = *reinterpret_cast<const float4*>(a.w + j);
+    st.ms = *reinterpret_cast<const float4*>(a.ms + j);
+    if (HAS_MOM) st.mo = *reinterpret_cast<const float4*>(a.mom + j);
+  };
+  // w / ms of the small prefix were last written by this kernel one step ago; see rmsprop_reduce_kernel for when the early
+  // loads are safe
+  if (pre_wait_loads) {
+    if (st.owner && a.preload) load_state();
+    griddep_launch();
+    evt_mark(evt_i, 60, 0);
+    griddep_wait(kid);            // the slabs come from the conv backward launch that precedes this one
+    evt_mark(evt_i, 61, 0);
+    if (st.owner && !a.preload) load_state();
+  } else if (st.owner) {
+    load_state();
   }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* src = r.part + j;
@@ -611,8 +619,9 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_small_kernel(RmsPropDpA
       t[0] = acc.x; t[1] = acc.y; t[2] = acc.z; t[3] = acc.w;
     }
   }
+  st.acc = acc;
   evt_mark(evt_i, 62, 0);
-  if (owner) {
+  if (st.owner) {
     // receive buffers: [parity][source rank][small prefix in LL format: 8 bytes per float]
     const uint32_t flag = (uint32_t)d.step;
     const int64_t slot = recv_offset + ((int64_t)(d.step & 1) * DP_WORLD_MAX + d.rank) * r.out_floats * 8 + (int64_t)j * 8;
@@ -621,24 +630,77 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_small_kernel(RmsPropDpA
       if (q < d.world && q != d.rank) dp_ll_store(d.peer[q] + slot, acc, flag);
     *reinterpret_cast<float4*>(r.out + j) = acc;                     // this rank's own gradient (introspection)
     evt_mark(evt_i, 66, 0);
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int q = 0; q < DP_WORLD_MAX; ++q)
-      if (q < d.world) {
-        const float4 v = q == d.rank ? acc
-                                     : dp_ll_load(d.peer[d.rank] + recv_offset +
-                                                      ((int64_t)(d.step & 1) * DP_WORLD_MAX + q) * r.out_floats * 8 + (int64_t)j * 8,
-                                                  flag, my_comm + DPC_ERR);
-        g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
-      }
-    evt_mark(evt_i, 63, 0);
-    rms_update<HAS_MOM>(a, g, w, ms, mo);
-    *reinterpret_cast<float4*>(a.w + j) = w;
-    *reinterpret_cast<float4*>(a.ms + j) = ms;
-    if (HAS_MOM) *reinterpret_cast<float4*>(a.mom + j) = mo;
   }
+}
+template <bool HAS_MOM>
+__device__ __forceinline__ void dp_small_phase2(const RmsPropDpArgs& d, int64_t recv_offset, EvtLog& evt_i, DpSmallState& st) {
+  const RmsPropArgs& a = d.base;
+  const GradReduceArgs& r = d.red;
+  if (!st.owner) return;
+  uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
+  const uint32_t flag = (uint32_t)d.step;
+  const int j = st.j;
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < DP_WORLD_MAX; ++q)
+    if (q < d.world) {
+      const float4 v = q == d.rank ? st.acc
+                                   : dp_ll_load(d.peer[d.rank] + recv_offset +
+                                                    ((int64_t)(d.step & 1) * DP_WORLD_MAX + q) * r.out_floats * 8 + (int64_t)j * 8,
+                                                flag, my_comm + DPC_ERR);
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    }
+  evt_mark(evt_i, 63, 0);
+  rms_update<HAS_MOM>(a, g, st.w, st.ms, st.mo);
+  *reinterpret_cast<float4*>(a.w + j) = st.w;
+  *reinterpret_cast<float4*>(a.ms + j) = st.ms;
+  if (HAS_MOM) *reinterpret_cast<float4*>(a.mom + j) = st.mo;
+}
+
+template <bool HAS_MOM>
+__global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_small_kernel(RmsPropDpArgs d, int64_t recv_offset) {
+  __shared__ float4 part[GR_LANES][GR_COLS];
+  EvtLog evt_i = evt_open();
+  DpSmallState st;
+  uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
+  dp_small_phase1<HAS_MOM>(d, recv_offset, blockIdx.x, true, K_RMSPROP, evt_i, st, part);
+  dp_small_phase2<HAS_MOM>(d, recv_offset, evt_i, st);
   evt_mark(evt_i, 64, 0);
-  if (cb == 0 && (int)threadIdx.x < d.world) {
+  if (blockIdx.x == 0 && (int)threadIdx.x < d.world) {
+    dp_wait_flag(my_comm + DPC_BIGDONE + 64 * threadIdx.x, d.step, my_comm + DPC_ERR, 16u);
+    __threadfence_system();
+  }
+  evt_mark(evt_i, 65, 0);
+  trace_mark(K_RMSPROP, 2);
+}
+
+// ---- data-parallel exchange at the END of the step (default) -----------------------------------------------------------
+// One launch on every SM after the conv backward: blocks [0, n_cb) first sum this rank's slabs for their columns and push the
+// sums to the peers (phase 1 above); then EVERY block takes its share of the dense1/w exchange (dp_big_exchange: reduce-scatter
+// with peer loads, RMSProp on the owned slice, all-gather of the bf16 shadow with peer stores); then the small-tensor blocks
+// collect the peers' sums -- which arrived while the big loop ran -- and update (phase 2).  Block 0 holds the launch open
+// until every rank's dense1/w slice has landed.  Every rank's "dense_bwd done" flag was pushed by CTA 0 of its conv backward
+// launch, a whole conv backward ago, so nobody waits for a peer's gradient; the conv backward itself keeps all the SMs
+// (the overlapped variant gives up 20 of them and pays a whole extra round of frames at B = 1024).
+template <bool HAS_MOM>
+__global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_tail_kernel(RmsPropDpArgs d, DpBigArgs big, int64_t recv_offset, int n_cb) {
+  __shared__ float4 part[GR_LANES][GR_COLS];
+  EvtLog evt_i = evt_open();
+  DpSmallState st;
+  st.owner = false;
+  uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
+  const bool small_block = (int)blockIdx.x < n_cb;
+  if (small_block) {
+    dp_small_phase1<HAS_MOM>(d, recv_offset, blockIdx.x, true, K_RMSPROP, evt_i, st, part);
+  } else {
+    griddep_launch();
+    griddep_wait(K_RMSPROP);
+  }
+  dp_big_exchange(big, (int)blockIdx.x, (int)gridDim.x);
+  evt_mark(evt_i, 67, 0);
+  if (small_block) dp_small_phase2<HAS_MOM>(d, recv_offset, evt_i, st);
+  evt_mark(evt_i, 64, 0);
+  if (blockIdx.x == 0 && (int)threadIdx.x < d.world) {
     dp_wait_flag(my_comm + DPC_BIGDONE + 64 * threadIdx.x, d.step, my_comm + DPC_ERR, 16u);
     __threadfence_system();
   }
@@ -654,6 +716,8 @@ int configure_dp() {
   int r;
   if ((r = (int)cudaFuncGetAttributes(&a, dp_small_kernel<false>))) return r;
   if ((r = (int)cudaFuncGetAttributes(&a, dp_small_kernel<true>))) return r;
+  if ((r = (int)cudaFuncGetAttributes(&a, dp_tail_kernel<false>))) return r;
+  if ((r = (int)cudaFuncGetAttributes(&a, dp_tail_kernel<true>))) return r;
   if ((r = (int)cudaFuncGetAttributes(&a, rmsprop_dp_kernel<false>))) return r;
   return (int)cudaFuncGetAttributes(&a, rmsprop_dp_kernel<true>);
 }
@@ -666,6 +730,15 @@ int launch_dp_small(const RmsPropDpArgs& d, int64_t recv_offset, cudaStream_t st
   return launch_pdl(dp_small_kernel<false>, dim3(n_cb), dim3(GR_LANES * GR_COLS), 0, stream, d, recv_offset);
 }
 
+
+int launch_dp_tail(const RmsPropDpArgs& d, const DpBigArgs& big, int64_t recv_offset, int num_sms, cudaStream_t stream) {
+  const int n_cb = (d.red.n_floats / 4 + GR_COLS - 1) / GR_COLS;
+  if (n_cb > DP_MAX_CB || !d.has_red) return (int)cudaErrorInvalidValue;
+  const int grid = n_cb > num_sms ? n_cb : num_sms;
+  if (d.base.momentum != 0.f)
+    return launch_pdl(dp_tail_kernel<true>, dim3(grid), dim3(GR_LANES * GR_COLS), 0, stream, d, big, recv_offset, n_cb);
+  return launch_pdl(dp_tail_kernel<false>, dim3(grid), dim3(GR_LANES * GR_COLS), 0, stream, d, big, recv_offset, n_cb);
+}
 
 int launch_rmsprop_dp(const RmsPropDpArgs& d, int num_sms, cudaStream_t stream) {
   if (d.base.momentum != 0.f) return launch_pdl(rmsprop_dp_kernel<true>, dim3(num_sms), dim3(512), 0, stream, d);

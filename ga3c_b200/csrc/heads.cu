@@ -30,17 +30,23 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
   __shared__ float loss_s[HD_THREADS / 32][3];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  // The head weights are written by the optimizer launch of the previous step.  A prologue may run while a kernel two or more
+  // launches back is still executing (only code after the wait is ordered transitively, common.cuh), so reading them before
+  // the dependency wait is safe only when something in between cannot be resident next to that optimizer launch: p.preload
+  // (batch >= num_sms: the conv forward in front of this kernel fills every SM, see rmsprop_reduce_kernel).  Otherwise
+  // they are read after the wait.
+  auto load_weights = [&]() {
+    for (int i = tid; i < A1 * FC; i += HD_THREADS) {
+      const int k = i / FC, jx = i - k * FC;
+      wt[k][jx] = (k < A) ? p.wp[jx * A + k] : p.wv[jx];
+    }
+    if (tid < A1) bias_s[tid] = (tid < A) ? p.bp[tid] : p.bv[0];
+    b1s[tid] = p.b1[tid];
+  };
+  if (p.preload) load_weights();
   griddep_launch();
   griddep_wait(K_HEADS);               // d1_part comes from the dense1 GEMM that precedes this kernel
-  // The head weights are written by the optimizer launch of the previous step.  They are read AFTER the dependency wait:
-  // a prologue may run while a kernel two or more launches back is still executing (only code after the wait is ordered
-  // transitively, common.cuh), so a pre-wait read could see the weights mid-update in a back-to-back asynchronous chain.
-  for (int i = tid; i < A1 * FC; i += HD_THREADS) {
-    const int k = i / FC, jx = i - k * FC;
-    wt[k][jx] = (k < A) ? p.wp[jx * A + k] : p.wv[jx];
-  }
-  if (tid < A1) bias_s[tid] = (tid < A) ? p.bp[tid] : p.bv[0];
-  b1s[tid] = p.b1[tid];
+  if (!p.preload) load_weights();
   __syncthreads();
 
   float acc[A1] = {};      // thread j: dWp[j][0..A-1], dWv[j]

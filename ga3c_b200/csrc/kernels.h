@@ -57,6 +57,7 @@ struct HeadsArgs {
   int train;
   int log_softmax;             // Config.USE_LOG_SOFTMAX
   int part;                    // Config.DUAL_RMSPROP passes: 0 gradient of cost_all, 1 of cost_p alone, 2 of cost_v alone
+  int preload;                 // the head weights may be read before the dependency wait (heads.cu)
 };
 int heads_grid(int batch, int num_sms);          // CTAs (= slabs written) of a training launch
 int launch_heads(const HeadsArgs& args, int num_sms, cudaStream_t stream);
@@ -147,6 +148,8 @@ int launch_rmsprop_dp(const RmsPropDpArgs& a, int num_sms, cudaStream_t stream);
 // rank's receive buffer, identical RMSProp on every rank; returns only when every rank's dense1/w slice has landed.
 // a.red is required; recv_offset: byte offset in the slab of the receive buffers [2][DP_MAX_WORLD][small prefix * 8 B].
 int launch_dp_small(const RmsPropDpArgs& a, int64_t recv_offset, cudaStream_t stream);
+// the whole exchange in one launch at the end of the step (default): small tensors as launch_dp_small, dense1/w on every SM
+int launch_dp_tail(const RmsPropDpArgs& a, const DpBigArgs& big, int64_t recv_offset, int num_sms, cudaStream_t stream);
 int configure_dp();     // load the exchange kernels now (not lazily at their first launch)
 int launch_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cudaStream_t stream);
 int launch_returns(const double* rewards, const int64_t* seg_offsets, int n_segments, const double* terminal,

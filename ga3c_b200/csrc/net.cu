@@ -52,7 +52,10 @@ struct ga3c_net {
   uint8_t* dp_peer[DP_MAX_WORLD] = {};   // slab base of every rank as mapped in this process (own slab at dp_rank)
   bool dp_ipc[DP_MAX_WORLD] = {};        // mapped with cudaIpcOpenMemHandle (to be closed on detach)
   uint64_t dp_step = 0;
-  int dp_exch = 20;                // exchange CTAs appended to the conv backward launch (GA3C_DP_EXCH_CTAS)
+  int dp_exch = 20;                // overlapped exchange: exchange CTAs appended to the conv backward launch (GA3C_DP_EXCH_CTAS)
+  int dp_exchange = 0;             // GA3C_DP_EXCHANGE: 0 "tail" (one launch on every SM at the end of the step, default),
+                                   // 1 "overlap" (exchange CTAs inside the conv backward launch + dp_small), 2 "single"
+                                   // (the first version: one kernel that also broadcasts the fp32 weights)
   int cur_exch = 0;                // ... of the step being enqueued (0 outside the overlapped data-parallel step)
   int64_t xbuf_off = 0, comm_off = 0;    // byte offsets in the slab: LL receive buffers [2][8][small prefix * 8 B], comm block
   // workspace
@@ -332,6 +335,7 @@ static HeadsArgs heads_args(ga3c_net* n, int batch, int splits) {
   h.wv = n->w + n->off(P_VW); h.bv = n->w + n->off(P_VB);
   h.batch = batch; h.num_actions = n->cfg.num_actions;
   h.log_eps = n->cfg.log_epsilon; h.min_policy = n->cfg.min_policy; h.log_softmax = n->cfg.use_log_softmax != 0;
+  h.preload = batch >= n->num_sms;
   return h;
 }
 
@@ -571,8 +575,16 @@ extern "C" int ga3c_dp_attach_local(ga3c_net* n, int32_t rank, int32_t world, ga
 
 static int dp_attach_finish(ga3c_net* n, int32_t rank, int32_t world) {
   n->dp_rank = rank; n->dp_world = world; n->dp_step = 0;
-  if (const char* e = getenv("GA3C_DP_EXCH_CTAS")) n->dp_exch = atoi(e);     // 0: single exchange kernel at the end of the step
-  if (n->dp_exch < 0 || n->dp_exch > n->num_sms / 2) n->dp_exch = 0;
+  n->dp_exchange = 0;
+  if (const char* e = getenv("GA3C_DP_EXCHANGE")) {
+    const std::string m(e);
+    if (m == "tail") n->dp_exchange = 0;
+    else if (m == "overlap") n->dp_exchange = 1;
+    else if (m == "single") n->dp_exchange = 2;
+    else return fail_msg("GA3C_DP_EXCHANGE must be tail, overlap or single");
+  }
+  if (const char* e = getenv("GA3C_DP_EXCH_CTAS")) n->dp_exch = atoi(e);
+  if (n->dp_exch < 1 || n->dp_exch > n->num_sms / 2) n->dp_exch = 20;
   CK(cudaMemset(n->slab + n->xbuf_off, 0, n->slab_bytes - (size_t)n->xbuf_off));
   CKL(configure_dp());
   return 0;
@@ -632,6 +644,26 @@ extern "C" int ga3c_dual_forward_backward_u8(ga3c_net* n, const uint8_t* x, cons
 }
 extern "C" int ga3c_dual_apply(ga3c_net* n, float lr, void* stream) { return dual_apply_impl(n, lr, stream); }
 
+static DpBigArgs dp_big_args(ga3c_net* n, float lr, int n_exch) {
+  DpBigArgs b{};
+  for (int r = 0; r < n->dp_world; ++r) b.peer[r] = n->dp_peer[r];
+  b.rank = n->dp_rank; b.world = n->dp_world; b.n_exch = n_exch; b.step = ++n->dp_step;
+  b.arena_bytes = (int64_t)n->arena_floats * 4; b.shadow_off = 4 * b.arena_bytes; b.comm_offset = n->comm_off;
+  b.w1_offset = n->off(P_D1W); b.w1_count = (int64_t)FLAT * FC;
+  b.lr = lr; b.decay = n->cfg.rmsprop_decay; b.momentum = n->cfg.rmsprop_momentum; b.eps = n->cfg.rmsprop_epsilon;
+  return b;
+}
+static RmsPropDpArgs dp_small_args(ga3c_net* n, float lr, int batch, const DpBigArgs& b) {
+  RmsPropDpArgs d{};
+  d.base = rmsprop_args(n, lr);
+  d.base.preload = batch >= n->num_sms;         // see rmsprop_reduce_kernel
+  for (int q = 0; q < n->dp_world; ++q) d.peer[q] = n->dp_peer[q];
+  d.rank = n->dp_rank; d.world = n->dp_world; d.step = b.step;
+  d.arena_bytes = b.arena_bytes; d.comm_offset = n->comm_off;
+  d.has_red = 1; d.red = reduce_args(n, batch);
+  return d;
+}
+
 // A rank of a data-parallel job that has no experiences this round still takes part in the exchange (every rank must enter
 // every step: the asynchronous trainer loop of the reference, ThreadTrainer.py:42-62, gives no such guarantee, so the host
 // ticks all ranks in lock step and idle ranks contribute a zero gradient).  No forward / backward kernels run.
@@ -643,25 +675,24 @@ static int train_step_empty(ga3c_net* n, float lr, float* loss, void* stream) {
   n->gp_heads_grid = 0;
   n->loss_out = loss;
   n->last_batch = 0;
-  if (n->dp_exch > 0) {
+  if (n->dp_exchange == 0) {                      // tail: nothing but the exchange launch; its CTA 0 publishes "gradient final"
     CK(cudaMemsetAsync(n->g + n->off(P_D1W), 0, (size_t)FLAT * FC * 4, st));
-    DpBigArgs b{};
-    for (int r = 0; r < n->dp_world; ++r) b.peer[r] = n->dp_peer[r];
-    b.rank = n->dp_rank; b.world = n->dp_world; b.n_exch = n->dp_exch; b.step = ++n->dp_step;
-    b.arena_bytes = (int64_t)n->arena_floats * 4; b.shadow_off = 4 * b.arena_bytes; b.comm_offset = n->comm_off;
-    b.w1_offset = n->off(P_D1W); b.w1_count = (int64_t)FLAT * FC;
-    b.lr = lr; b.decay = n->cfg.rmsprop_decay; b.momentum = n->cfg.rmsprop_momentum; b.eps = n->cfg.rmsprop_epsilon;
+    const DpBigArgs b = dp_big_args(n, lr, 0);
+    n->cur_exch = 0;
+    const RmsPropDpArgs d = dp_small_args(n, lr, 0, b);    // zero slabs in every segment: the sums are 0
+    LAUNCH(n, K_RMSPROP, st, launch_dp_tail(d, b, n->xbuf_off, n->num_sms, st));
+    n->global_step += 1;
+    return 0;
+  }
+  if (n->dp_exchange == 1) {
+    CK(cudaMemsetAsync(n->g + n->off(P_D1W), 0, (size_t)FLAT * FC * 4, st));
+    const DpBigArgs b = dp_big_args(n, lr, n->dp_exch);
     n->cur_exch = b.n_exch;
     float* gp = n->gpart;
     LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(nullptr, false, n->n1, n->dn2, n->w + n->off(P_C12W), nullptr,
                                                 gp + n->off(P_C11W), gp + n->off(P_C11B), gp + n->off(P_C12W),
                                                 gp + n->off(P_C12B), n->gp_stride, 0, n->num_sms, &b, st));
-    RmsPropDpArgs d{};
-    d.base = rmsprop_args(n, lr);
-    for (int q = 0; q < n->dp_world; ++q) d.peer[q] = n->dp_peer[q];
-    d.rank = n->dp_rank; d.world = n->dp_world; d.step = b.step;
-    d.arena_bytes = b.arena_bytes; d.comm_offset = n->comm_off;
-    d.has_red = 1; d.red = reduce_args(n, 0);      // zero slabs in every segment: the sums are 0
+    const RmsPropDpArgs d = dp_small_args(n, lr, 0, b);
     n->cur_exch = 0;
     LAUNCH(n, K_RMSPROP, st, launch_dp_small(d, n->xbuf_off, st));
     n->global_step += 1;
@@ -685,24 +716,24 @@ static int train_step_impl(ga3c_net* n, const void* x, bool x_u8, const float* y
     if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, true)) return r;
     return apply_rmsprop_impl(n, lr, stream, nullptr);
   }
-  if (n->dp_world > 1 && n->dp_exch > 0) {
+  if (n->dp_world > 1 && n->dp_exchange == 0) {
+    // exchange at the end of the step (dp_tail_kernel): the conv backward keeps every SM; its CTA 0 publishes "dense1/w gradient
+    // final" to the peers as soon as dense_bwd is complete, so that no rank waits for another rank's gradient at the tail
+    const DpBigArgs b = dp_big_args(n, lr, 0);
+    n->cur_exch = 0;
+    if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, false, &b)) return r;
+    const RmsPropDpArgs d = dp_small_args(n, lr, batch, b);
+    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_dp_tail(d, b, n->xbuf_off, n->num_sms, (cudaStream_t)stream));
+    n->global_step += 1;
+    return 0;
+  }
+  if (n->dp_world > 1 && n->dp_exchange == 1) {
     // overlapped exchange (dp_exchange.cuh): dense1/w moves between the ranks on exchange CTAs of the conv backward
     // launch; the small tensors follow in dp_small, which also holds the step open until every slice has landed
-    DpBigArgs b{};
-    for (int r = 0; r < n->dp_world; ++r) b.peer[r] = n->dp_peer[r];
-    b.rank = n->dp_rank; b.world = n->dp_world; b.n_exch = n->dp_exch; b.step = ++n->dp_step;
-    b.arena_bytes = (int64_t)n->arena_floats * 4; b.shadow_off = 4 * b.arena_bytes; b.comm_offset = n->comm_off;
-    b.w1_offset = n->off(P_D1W); b.w1_count = (int64_t)FLAT * FC;
-    b.lr = lr; b.decay = n->cfg.rmsprop_decay; b.momentum = n->cfg.rmsprop_momentum; b.eps = n->cfg.rmsprop_epsilon;
+    const DpBigArgs b = dp_big_args(n, lr, n->dp_exch);
     n->cur_exch = b.n_exch;
     int r = fb_tail_impl(n, x, x_u8, batch, stream, true, false, &b);
-    RmsPropDpArgs d{};
-    d.base = rmsprop_args(n, lr);
-    d.base.preload = batch >= n->num_sms;         // see rmsprop_reduce_kernel
-    for (int q = 0; q < n->dp_world; ++q) d.peer[q] = n->dp_peer[q];
-    d.rank = n->dp_rank; d.world = n->dp_world; d.step = b.step;
-    d.arena_bytes = b.arena_bytes; d.comm_offset = n->comm_off;
-    d.has_red = 1; d.red = reduce_args(n, batch);
+    const RmsPropDpArgs d = dp_small_args(n, lr, batch, b);
     n->cur_exch = 0;
     if (r) return r;
     LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_dp_small(d, n->xbuf_off, (cudaStream_t)stream));

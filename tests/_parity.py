@@ -47,6 +47,24 @@ def layer_report(net, params, x, y_r, a, *, beta=0.01, log_eps=1e-6, min_policy=
     rep["dd1"] = err(net.workspace(3), f["dd1"])
     rep["dn2"] = err(net.workspace(4), f["dn2"])
     rep["dn1"] = err(net.workspace(5), f["dn1"])
+    # Layer-local view of the two masked data gradients: the same oracle arithmetic applied to the CUDA path's OWN stored inputs
+    # (dd1 / dn2 and the activation masks).  A stored activation that sits within an fp32-vs-fp64 accumulation difference of
+    # the ReLU boundary flips its mask bit; the global comparison above then shows that element's whole gradient (and what
+    # it spreads to upstream) as an error although every kernel did its arithmetic right.  At full-size batches (millions of
+    # activations) a handful of such flips is certain; the local view is immune, and `outliers` says how few elements differ.
+    w12q = f["w12"]
+    n1_mask = (net.workspace(0).reshape(b, -1) > 0)
+    n2_mask = (net.workspace(1).reshape(b, -1) > 0)
+    dn2_cuda = net.workspace(4).astype(np.float64).reshape(b * onp.H2 * onp.H2, onp.C2_OUT)
+    dd1_cuda = net.workspace(3).astype(np.float64)
+    dn2_local = onp.bf16_round((dd1_cuda @ f["w1"].T) * n2_mask)
+    dn1_local = onp._col2im(dn2_cuda @ w12q.T, b, onp.H1, onp.C2_K, onp.C2_S, onp.P2_LO, onp.P2_HI, onp.H2, onp.C1_OUT)
+    dn1_local = onp.bf16_round(dn1_local.reshape(b, -1) * n1_mask)
+    rep["dn2_local"] = err(net.workspace(4), dn2_local)
+    rep["dn1_local"] = err(net.workspace(5), dn1_local)
+    for k in ("dn1", "dn2"):
+        got, ref = net.workspace(5 if k == "dn1" else 4).ravel(), np.asarray(f[k], dtype=np.float64).ravel()
+        rep[k + "_outliers"] = (float((np.abs(got - ref) > 2.0 ** -7 * np.abs(ref).max()).mean()), 0.0)
     for k in ("cost_p_1", "cost_p_2", "cost_v", "cost_all"):
         rep["loss/" + k] = err([losses[k]], [losses_ref[k]])
     grads = net.get_gradients()

@@ -44,8 +44,13 @@ def ga3c():
 
 def check_report(rep):
     assert rep["p"][0] <= TOL_P and rep["v"][0] <= TOL_V, rep
-    for k in ("n1", "n2", "dd1", "dn2", "dn1"):
+    for k in ("n1", "n2", "dd1"):
         assert rep[k][1] <= TOL_ACT_REL, (k, rep[k])
+    for k in ("dn2", "dn1"):
+        # masked data gradients: exact against the oracle fed the same stored inputs; against the end-to-end oracle either
+        # within tolerance everywhere, or off only at the rare elements behind a ReLU-boundary flip (tests/_parity.py)
+        assert rep[k + "_local"][1] <= TOL_ACT_REL, (k, rep[k + "_local"])
+        assert rep[k][1] <= TOL_ACT_REL or rep[k + "_outliers"][0] <= 1e-4, (k, rep[k], rep[k + "_outliers"])
     assert rep["d1"][1] <= 1e-3, rep["d1"]
     for k, (d, r) in rep.items():
         if k.startswith("loss/"):
@@ -153,9 +158,11 @@ def test_log_softmax_knob(ga3c):
     assert np.allclose(p.sum(axis=1), 1.0, atol=1e-5)
 
 
-def test_data_parallel_exchange_two_ranks_on_one_gpu(ga3c, monkeypatch):
-    """The fused data-parallel step (dp_exchange.cuh: dense1/w on exchange CTAs of the conv backward launch, LL push of the
-    small tensors) with BOTH ranks on one device: two handles attached to each other with ga3c_dp_attach_local, each on its
+@pytest.mark.parametrize("exchange", ["tail", "overlap"])
+def test_data_parallel_exchange_two_ranks_on_one_gpu(ga3c, monkeypatch, exchange):
+    """The fused data-parallel step (dp_exchange.cuh; "tail": the whole exchange in one launch on every SM at the end of the
+    step; "overlap": dense1/w on exchange CTAs of the conv backward launch, LL push of the small tensors afterwards) with
+    BOTH ranks on one device: two handles attached to each other with ga3c_dp_attach_local, each on its
     own stream, each training on its row shard.  After 3 steps the replicas are bit-identical and equal the oracle's
     single-process steps on the concatenated batch (what a single ThreadTrainer would have computed).  The grids are small
     (12 rows per rank), so both ranks' kernels are resident together; every cross-rank wait is bounded, so a scheduling
@@ -163,6 +170,7 @@ def test_data_parallel_exchange_two_ranks_on_one_gpu(ga3c, monkeypatch):
     import ctypes as C
     import torch
     from ga3c_b200 import _capi
+    monkeypatch.setenv("GA3C_DP_EXCHANGE", exchange)
     monkeypatch.setenv("GA3C_DP_EXCH_CTAS", "4")
     world, b = 2, 12
     rng = np.random.default_rng(17)
