@@ -67,14 +67,15 @@ METRIC = "TPS: A3C training frames/s, NetworkVP 84x84x4 (PPS: predictions/s, in 
 def kernel_work(name, b, train):
     n1, n2, fc = 441 * 16, 3872, 256
     x = STATE_DIM * 4
+    xb = STATE_DIM * 2            # the bf16 copy of the frame conv_fwd leaves for the conv backward (live bytes; stored padded)
     if name == "conv_fwd":
-        return "hbm", b * (x + (n1 * 2 if train else 0) + n2 * 2)
+        return "hbm", b * (x + (n1 * 2 + xb if train else 0) + n2 * 2)
     if name == "conv11_wgrad":
         return "hbm", b * (x + n1 * 2)
     if name == "conv12_bwd":      # split predecessor (GA3C_SPLIT_CONV_BWD)
         return "hbm", b * (n1 * 2 + n2 * 2 + n1 * 2)
-    if name == "conv_bwd":        # fused conv12 dgrad + conv12 wgrad + conv11 wgrad: x, n1, dn2 read once, dn1 stays on chip
-        return "hbm", b * (x + n1 * 2 + n2 * 2)
+    if name == "conv_bwd":        # fused conv12 dgrad + conv12 wgrad + conv11 wgrad: bf16 frame copy, n1, dn2 read once, dn1 stays on chip
+        return "hbm", b * (xb + n1 * 2 + n2 * 2)
     if name == "heads":
         return "hbm", b * (fc * 4 + (fc * 2 + 4 + NUM_ACTIONS * 4 if train else (NUM_ACTIONS + 1) * 4))
     if name == "rmsprop":

@@ -19,6 +19,28 @@ constexpr int XS_W = 88, XS_ROW_BYTES = XS_W * 8, XS_BYTES = XS_W * XS_ROW_BYTES
 // padded conv11 output in shared memory: 24x24 pixels x 16 channels (32 B / pixel), pad (1 before, 2 after)
 constexpr int N1P_W = 24, N1P_BYTES = N1P_W * N1P_W * 32;                            // 18432
 
+// ---- HBM layouts of the training-only activations ---------------------------------------------------------------------
+// The conv backward kernel (conv_bwd_fused.cu) consumes its three inputs as tcgen05 operands exactly as they lie in HBM: the
+// kernels that PRODUCE them write the no-swizzle UMMA layouts (16-byte chunk j of row r at j*LBO + r*16, all rows of a plane
+// contiguous, so a spatial shift is a different descriptor start address), and the consumer only issues bulk copies.
+//   xblk  bf16 copy of the frame as conv_fwd's space-to-depth block matrix Blk (conv_blk.cuh): 22x22 blocks of 4x4 pixels of the
+//         zero-padded 88x88x4 image, row Y*22 + X, 64 elements (dy, dx, c) in 8 chunk planes.  Stored in 4 quarters of 128 rows,
+//         [frame][quarter][plane][128 rows][16 B]; rows >= 484 stay zero (never written)
+//   n1    Blk2: n1 SAME-padded (1 before, 2 after) to 24x24 and cut into 12x12 blocks of 2x2 pixels, row Yb*13 + Xb (column 12
+//         dead), 64 elements (dy, dx, ci) in 8 chunk planes of 160 rows; [frame][plane][160 rows][16 B], borders stay zero
+//   dn2   G: dn2 on a zero-bordered 13x13 grid, row (oy+1)*13 + (ox+1), 32 co in 4 chunk planes of 176 rows;
+//         [frame][plane][176 rows][16 B], borders stay zero
+constexpr int XB_QROWS = 128, XB_QUARTERS = 4, XB_PLANE_BYTES = XB_QROWS * 16, XB_QBYTES = 8 * XB_PLANE_BYTES,
+              XB_FRAME_BYTES = XB_QUARTERS * XB_QBYTES, XB_LIVE_ROWS = 484;                                        // 65,536 B / frame
+constexpr int G_W = 13, G_ROWS = 176, G_LBO = G_ROWS * 16, G_BYTES = 4 * G_LBO;                                 // 11,264 B / frame
+constexpr int B2_ROWS = 160, B2_LBO = B2_ROWS * 16, B2_BYTES = 8 * B2_LBO;                                      // 20,480 B / frame
+// byte offset of channels [8h, 8h+8) of conv11 output pixel (y, x) inside a frame's Blk2 image
+__host__ __device__ constexpr int b2_pixel_offset(int y, int x, int h) {
+  return ((((y + 1) & 1) * 2 + ((x + 1) & 1)) * 2 + h) * B2_LBO + (((y + 1) >> 1) * G_W + ((x + 1) >> 1)) * 16;
+}
+// byte offset of channels [8j, 8j+8) of conv12 output position (oy, ox) inside a frame's G image
+__host__ __device__ constexpr int g_pos_offset(int oy, int ox, int j) { return j * G_LBO + ((oy + 1) * G_W + ox + 1) * 16; }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -108,6 +130,12 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// 1-D bulk copy shared -> global through the TMA engine (bulk async-group completion)
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 

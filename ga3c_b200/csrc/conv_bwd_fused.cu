@@ -4,36 +4,41 @@
 //     dn1  = conv12 data-gradient of dn2, masked by relu'(n1)          (never leaves the SM)
 //     g_w12 = patches(n1)^T dn2 , g_b12 = colsum(dn2)
 //     g_w11 = patches(x)^T dn1  , g_b11 = colsum(dn1)                  (conv11 has no data-gradient: x is the input)
-// bf16 operands, fp32 accumulation in TMEM.  Per frame the kernel reads x (112,896 B fp32), n1 (14,112 B) and dn2
-// (7,744 B) from HBM exactly once and writes nothing; the weight-gradient accumulators stay in TMEM for all frames of
-// the CTA and are stored once into the CTA's slab of the gradient-partial workspace (grad_reduce / rmsprop_reduce add
-// the slabs in a fixed order).
+// bf16 operands, fp32 accumulation in TMEM; the weight-gradient accumulators stay in TMEM for all frames of the CTA and are
+// stored once into the CTA's slab of the gradient-partial workspace (rmsprop_reduce / dp_tail add the slabs in a fixed order).
 //
-// All three products are GEMMs over space-to-depth "block matrices" kept in the no-swizzle UMMA layout with every row
-// contiguous (16-byte chunk j of row r at j*LBO + r*16), so that a spatial shift is a different descriptor start address:
-//   G    dn2 on a zero-bordered 13x13 grid, row (oy+1)*13 + (ox+1), K = 32 co in 4 chunk planes
-//   Blk2 n1, SAME-padded (1 before, 2 after) to 24x24 and cut into 12x12 blocks of 2x2 pixels, row Yb*13 + Xb (column 12
-//        dead), 64 elements (dy, dx, ci) in 8 chunk planes
-//   Blk  x, zero-padded to 88x88 and cut into 22x22 blocks of 4x4 pixels (conv_blk.cuh)
+// Every input arrives in HBM already in the no-swizzle UMMA operand layout it is consumed in (common.cuh): xblk (the bf16
+// block matrix of the frame, written by conv_fwd next to n1), n1 as Blk2, dn2 as G (written by the dense1 data-gradient
+// epilogue).  The kernel therefore has no conversion or re-layout stage at all: two warps issue cp.async.bulk copies, one warp
+// issues UMMAs, the rest run the data-gradient epilogue.  Per frame it reads 63.5 KB + 20 KB (+ 20 KB again, an L2 hit) + 11 KB
+// and writes nothing.  (The first version of this kernel re-read the fp32 frame through a TMA ring and converted it with six
+// warps; it was bound by its 110 small UMMAs per frame.  experiments/conv_bwd_v1_fp32_ring_110_umma.cu.txt.)
+//
+// All three products are GEMMs over space-to-depth block matrices with every row contiguous, so that a spatial shift is a
+// different descriptor start address:
 // conv12 data gradient.  Output pixel (2Yh+py, 2Xh+px) of the padded image gets taps kh = py + 2a, kw = px + 2b from
 //   dn2[Yh - a, Xh - b].  With m = Yh*13 + Xh:   D[m, (py, px, ci)] = sum_{a,b} G[m + 14 - 13a - b, :] . Wd_ab
 //   where Wd_ab[co, (py, px, ci)] = w12[py + 2a, px + 2b, ci, co]: four row-shifted GEMMs, M = 156 (two 128-row tiles, the
 //   second one starting at row 28), N = 64, K = 32 each -> 16 UMMAs.  Row m of D is the whole 2x2 block (Yh, Xh) of dn1.
 // conv12 weight gradient.  kh = 2a + dy, kw = 2b + dx: quadrant (a, b) is  dW_ab[(dy, dx, ci), co] = sum_m Blk2[m + 13a + b]^T
-//   G[m + 14]  over positions m = oy*13 + ox (dead columns hit the zero border of G): A = Blk2 read MN-major, B = G read
-//   MN-major, M = 64, N = 32, K = 144 -> 4 x 9 UMMAs.
-// conv11 weight gradient.  Quadrant (a, b) is dW_ab = sum_m Blk[m + 22a + b]^T dn1[m] over positions m = oy*22 + ox.  A = Blk
-//   read MN-major at row m' + 22a; the b-shift moves to the B side (m' = m + b): dn1 is written twice by the data-gradient
-//   epilogue, planes (0, half) at row m and planes (1, half) at row m + 1, so ONE UMMA per (a, k-step) with N = 32 = (b, cout)
-//   covers both b: 2 x 29 UMMAs (M = 64, N = 32) per frame instead of 4 x 29 -- the frame loop is bound by UMMA count and
-//   operand bytes (every small UMMA costs ~40-80 cycles, microbenchmark in profiles/), not by HBM.
+//   G[m + 14]  over positions m = oy*13 + ox (dead columns hit the zero border of G).  A = Blk2 read MN-major with M = 128 =
+//   (b, dy, dx, ci): the b = 1 half is a second copy of Blk2 moved up by one row (a second bulk copy of the same bytes, 16 B
+//   further on), B = G read MN-major, N = 32, K = 144 -> 2 x 9 UMMAs.
+// conv11 weight gradient.  Quadrant (a, b) is dW_ab = sum_r Blk[r]^T dn1[r - 22a - b] over ALL block rows r (dn1 on the 21 x 22
+//   position grid, zero elsewhere).  A = Blk read MN-major (M = 64), B = dn1 in EIGHT planes (a, b, half): the data-gradient
+//   epilogue writes every dn1 pixel four times, at rows p, p + 1, p + 22, p + 23, so ONE UMMA per k-step with N = 64 =
+//   (a, b, cout) covers all four quadrants: 31 UMMAs (M = 64, N = 64).
+// 65 UMMAs per frame in all.  Every small UMMA occupies the tensor pipe for ~80 cycles whatever its M / N <= 128
+// (profiles/r1h_umma_issue_cost_microbench.txt), so a frame costs ~2.7 us of pipe time against ~2.6 us of HBM time at 1/148 of
+// the measured bandwidth.
 //
-//   warps 0-5    fp32 chunks of x (TMA ring, one independent pipeline per warp) -> bf16 -> Blk
-//   warp  6      one thread issues every UMMA: conv12 of frame k+1 between the conv11 position groups of frame k
-//   warp  7      one thread streams n1 / dn2 of the next frame into a raw staging buffer (cp.async.bulk)
-//   warps 8-11   data-gradient epilogue: TMEM -> relu' mask (n1 from Blk2) -> bf16 -> dn1 operand, bias gradient of conv11;
-//                final store of the TMEM weight-gradient accumulators
-//   warps 12-15  raw staging -> G / Blk2 layouts, bias gradient of conv12
+//   warp  0      Blk quarters of the next frames -> ring of 6 slots (one 16 KB cp.async.bulk each)
+//   warp  1      issues every UMMA: conv12 of frame k+2 after the conv11 gradient of frame k
+//   warp  2      G / Blk2 (two copies) of the next frame, as soon as the epilogue is done with the current ones
+//   warps 4-7    data-gradient epilogue: TMEM -> relu' mask (n1 from Blk2) -> bf16 -> the eight dn1 planes, bias gradient of
+//                conv11; final store of the TMEM weight-gradient accumulators
+//   warps 8-11   bias gradient of conv12 (column sums of G); warp 11 also drains the 28 live rows of the second data-gradient
+//                tile (it shares TMEM lane quarter 3 with warp 7)
 #include "common.cuh"
 #include "kernels.h"
 #include "tcgen05.cuh"
@@ -42,58 +47,47 @@
 
 namespace ga3c {
 
-constexpr int FB_THREADS = 512, FB_AUX_WARPS = 6, FB_ISSUE_WARP = 6, FB_TMA_WARP = 7,
-              FB_EPI_WARP0 = 8, FB_RE_WARP0 = 12;
-static_assert(FB_EPI_WARP0 % 4 == 0, "epilogue warp e must own TMEM lane quarter e");
-constexpr int FBLK_ROWS = 492, FBLK_LBO = FBLK_ROWS * 16, FBLK_BYTES = 8 * FBLK_LBO;     // rows read: <= 16*28 + 23 + 15 = 486
-constexpr int W11_KSTEPS = 29;                                   // 464 >= 462 positions (21 rows x 22, column 21 dead)
-// dn1 operand: 4 planes (b, half) of 8 channels; planes (1, .) hold the SAME rows shifted down by one, so that one UMMA
-// with N = 32 computes both column quadrants b = 0, 1 of the conv11 weight gradient (A = Blk is read once for two)
-constexpr int DN1_ROWS = 16 * W11_KSTEPS, DN1_PLANE = DN1_ROWS * 16, DN1_BUF = 4 * DN1_PLANE;
-constexpr int G_W = 13, G_ROWS = 176, G_LBO = G_ROWS * 16, G_BYTES = 4 * G_LBO;          // rows read: <= 28 + 127 + 14 = 169
-constexpr int B2_ROWS = 160, B2_LBO = B2_ROWS * 16, B2_BYTES = 8 * B2_LBO;               // rows read: <= 143 + 14 = 157
-constexpr int DG_TILE1 = 28;                                     // first row of the second data-gradient tile
-constexpr int DG_ROWS = 12 * G_W;                                // 156 rows of D (12 x 12 blocks + dead column)
-constexpr int W12_KSTEPS = 9;                                    // 144 >= 11 rows x 13 positions
-constexpr int RAW_DN2 = N2_POS * C2_OUT * 2, RAW_N1 = N1_POS * C1_OUT * 2, RAW_BYTES = RAW_DN2 + RAW_N1;   // 7,744 + 14,112
-constexpr int W12D_BYTES = 4 * 4 * 64 * 16;                      // 4 taps x [4 k-chunks (8 co)][64 rows (py, px, ci)][16 B]
+constexpr int FB_THREADS = 384, FB_LOAD_WARP = 0, FB_ISSUE_WARP = 1, FB_C12_WARP = 2, FB_EPI_WARP0 = 4, FB_B12_WARP0 = 8;
+static_assert(FB_EPI_WARP0 % 4 == 0 && FB_B12_WARP0 % 4 == 0, "epilogue warp e must own TMEM lane quarter e");
+constexpr int FB_RING = 6;                                        // Blk quarter slots: one and a half frames
+constexpr int W11_KSTEPS = 31;                                    // 496 >= 484 block rows
+constexpr int DN1_ROWS = 16 * W11_KSTEPS, DN1_PLANE = DN1_ROWS * 16, DN1_BYTES = 8 * DN1_PLANE;        // 63,488
+constexpr int DG_TILE1 = 28;                                      // first row of the second data-gradient tile
+constexpr int DG_ROWS = 12 * G_W;                                 // 156 rows of D (12 x 12 blocks + dead column)
+constexpr int W12_KSTEPS = 9;                                     // 144 >= 11 rows x 13 positions
+constexpr int W12D_BYTES = 4 * 4 * 64 * 16;                       // 4 taps x [4 k-chunks (8 co)][64 rows (py, px, ci)][16 B]
+static_assert(4 * XB_QROWS >= DN1_ROWS && DN1_ROWS >= XB_LIVE_ROWS, "the k-steps must cover every block row");
 
-constexpr int FB_OFF_BLK = 0;
-constexpr int FB_OFF_RING = FB_OFF_BLK + FBLK_BYTES;             //  62,976
-constexpr int FB_RING_BYTES = FB_AUX_WARPS * PW_SLOTS * PW_BYTES; //  64,512: two 4-row slots per aux warp
-constexpr int FB_OFF_DN1 = FB_OFF_RING + FB_RING_BYTES;          // 127,488 (one buffer of four planes)
-constexpr int FB_OFF_G = FB_OFF_DN1 + DN1_BUF;                   // 157,184
-constexpr int FB_OFF_B2 = FB_OFF_G + G_BYTES;                    // 168,448
-constexpr int FB_OFF_W12D = FB_OFF_B2 + B2_BYTES;                // 188,928
-constexpr int FB_OFF_RAW = FB_OFF_W12D + W12D_BYTES;             // 205,312
-constexpr int FB_OFF_RED = FB_OFF_RAW + RAW_BYTES;               // 227,168: [5][16] conv11 + [4][32] conv12 bias partials
+constexpr int FB_OFF_RING = 0;
+constexpr int FB_OFF_DN1 = FB_OFF_RING + FB_RING * XB_QBYTES;     //  98,304
+constexpr int FB_OFF_G = FB_OFF_DN1 + DN1_BYTES;                  // 161,792
+constexpr int FB_OFF_B2 = FB_OFF_G + G_BYTES;                     // 173,056: Blk2, then the copy moved up by one row
+constexpr int FB_OFF_W12D = FB_OFF_B2 + 2 * B2_BYTES;             // 214,016
+constexpr int FB_OFF_RED = FB_OFF_W12D + W12D_BYTES;              // 230,400: [5][16] conv11 + [4][32] conv12 bias partials
 constexpr int RED_B12 = 5 * C1_OUT;
 constexpr int FB_OFF_BAR = FB_OFF_RED + (RED_B12 + 4 * C2_OUT) * 4;
-constexpr int FB_RING = 0;        // [12] TMA chunk of x landed (slot = aux warp * 2 + parity)
-constexpr int FB_BLKRDY = 12;     // [4] Blk rows of conv11 position group i converted, one arrival per chunk (aux -> issuer)
-constexpr int FB_GRP = 16;        // [4] conv11 UMMAs of group i retired (tcgen05.commit)           (-> aux: Blk rows free)
-constexpr int FB_DN1RDY = 20;     //     dn1 operand written, 5 arrivals                            (epilogue -> issuer)
-constexpr int FB_DN1FREE = 22;    //     every conv11 UMMA of the frame retired                     (-> epilogue: operand free)
-constexpr int FB_RAWFULL = 24;    //     n1 / dn2 of a frame landed in the raw buffer               (TMA -> re-layout)
-constexpr int FB_RAWFREE = 25;    //     raw buffer consumed                                        (re-layout -> TMA thread)
-constexpr int FB_C12RDY = 26;     //     G / Blk2 hold the frame                                    (re-layout -> issuer)
-constexpr int FB_MMA12 = 27;      //     conv12 UMMAs of the frame retired (tcgen05.commit)         (-> epilogue)
-constexpr int FB_EPI12 = 28;      //     D drained and Blk2 mask reads done, 5 arrivals             (epilogue -> issuer, re-layout)
-constexpr int FB_DONE = 29;       //     every UMMA of the kernel retired                           (-> final store)
-constexpr int FB_NBAR = 30;
+constexpr int FB_QFULL = 0;       // [6] Blk quarter landed in ring slot i (TMA bytes)
+constexpr int FB_QFREE = 6;       // [6] the conv11 UMMAs that read slot i retired (tcgen05.commit)       (-> loader)
+constexpr int FB_C12RDY = 12;     //     G / Blk2 of a frame landed (TMA bytes)                            (-> issuer, bias warps)
+constexpr int FB_MMA12 = 13;      //     conv12 UMMAs of the frame retired (tcgen05.commit)                (-> epilogue)
+constexpr int FB_EPI12 = 14;      //     D drained, Blk2 mask reads and G column sums done, 8 arrivals     (-> G / Blk2 loader)
+constexpr int FB_DN1RDY = 15;     //     dn1 operand written, 5 arrivals                                   (epilogue -> issuer)
+constexpr int FB_DN1FREE = 16;    //     every conv11 UMMA of the frame retired                            (-> epilogue: operand free)
+constexpr int FB_DONE = 17;       //     every UMMA of the kernel retired                                  (-> final store)
+constexpr int FB_NBAR = 18;
 constexpr int FB_OFF_TSLOT = FB_OFF_BAR + FB_NBAR * 8;
-constexpr int FB_SMEM = FB_OFF_TSLOT + 16 + 128;                 // incl. slack to align the base to 128 B
+constexpr int FB_SMEM = FB_OFF_TSLOT + 16 + 128;                  // incl. slack to align the base to 128 B
 static_assert(FB_SMEM <= 232448, "shared memory budget of one CTA per SM");
-constexpr int FB_TMEM_COLS = 512, TM_W11 = 0, TM_W12 = 64, TM_D12 = 192;   // 2x32 | 4x32 | 2x64 columns
+constexpr int FB_TMEM_COLS = 256, TM_W11 = 0, TM_W12 = 64, TM_D12 = 128;   // 64 | 2x32 | 2x64 columns
 
-template <bool U8, bool DP>   // U8: frames are uint8 [B,28224] (x = k/128 - 1 applied on the fly), else fp32; DP: the grid carries exchange CTAs
+template <bool DP>        // DP: data parallel (CTA 0 publishes "dense1/w gradient final"; the grid may carry exchange CTAs)
 __global__ void __launch_bounds__(FB_THREADS, 1)
-conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, const uint16_t* __restrict__ dn2,
+conv_bwd_kernel(const uint8_t* __restrict__ xblk, const uint8_t* __restrict__ n1b2, const uint8_t* __restrict__ dn2g,
                 const float* __restrict__ w12, uint16_t* __restrict__ dn1_out, float* __restrict__ g_w11,
                 float* __restrict__ g_b11, float* __restrict__ g_w12, float* __restrict__ g_b12, int64_t gp_stride, int batch,
                 int n_conv, const DpBigArgs dp) {
-  // data parallel: CTAs [n_conv, gridDim.x) are exchange CTAs -- they move dense1/w (final since dense_bwd, the launch
-  // this one depends on) between the ranks while CTAs [0, n_conv) compute the conv gradients (dp_exchange.cuh)
+  // data parallel, overlapped exchange: CTAs [n_conv, gridDim.x) are exchange CTAs -- they move dense1/w (final since
+  // dense_bwd, the launch this one depends on) between the ranks while CTAs [0, n_conv) compute the conv gradients
   if (DP && (int)blockIdx.x >= n_conv) {
     griddep_launch();
     griddep_wait(K_DP_BIG);
@@ -104,52 +98,31 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* const smem = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t blk = sbase + FB_OFF_BLK, ring = sbase + FB_OFF_RING, dn1s = sbase + FB_OFF_DN1, gg = sbase + FB_OFF_G,
-                 b2 = sbase + FB_OFF_B2, w12d = sbase + FB_OFF_W12D, raw = sbase + FB_OFF_RAW, bars = sbase + FB_OFF_BAR,
-                 tslot = sbase + FB_OFF_TSLOT;
+  const uint32_t ring = sbase + FB_OFF_RING, dn1s = sbase + FB_OFF_DN1, gg = sbase + FB_OFF_G, b2 = sbase + FB_OFF_B2,
+                 w12d = sbase + FB_OFF_W12D, bars = sbase + FB_OFF_BAR, tslot = sbase + FB_OFF_TSLOT;
   float* red = reinterpret_cast<float*>(smem + FB_OFF_RED);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  EvtLog evt_i = evt_open();                                      // pipeline event log of CTA 0 (ga3c_evt_*), off unless attached
   const int stride = DP ? (int)gridDim.x - dp.n_exch : (int)gridDim.x;
   const int n_frames = ((int)blockIdx.x < batch) ? (batch - 1 - (int)blockIdx.x) / stride + 1 : 0;
-  const int n_chunks = n_frames * PW_NCHUNK;                       // chunk stream of this CTA: q = k * 21 + c, warp q % 6
   auto frame_of = [&](int k) { return (size_t)(blockIdx.x + k * stride); };
   auto bar = [&](int i) { return bars + i * 8; };
-  auto issue_chunk = [&](int q, int slot) {                        // one thread
-    const int k = q / PW_NCHUNK, c = q - k * PW_NCHUNK;
-    constexpr uint32_t bytes = U8 ? PW_BYTES_U8 : PW_BYTES;
-    mbar_expect_tx(bar(FB_RING + slot), bytes);
-    bulk_load(ring + slot * PW_BYTES, static_cast<const uint8_t*>(x) + (frame_of(k) * PW_NCHUNK + c) * bytes, bytes, bar(FB_RING + slot));
-  };
 
   // ---------------- prologue ----------------
   if (tid == 0) {
-    for (int i = 0; i < FB_AUX_WARPS * PW_SLOTS; ++i) mbar_init(bar(FB_RING + i), 1);
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(bar(FB_BLKRDY + i), pw_group_chunks(i));
-      mbar_init(bar(FB_GRP + i), 1);
-    }
-    mbar_init(bar(FB_DN1RDY), 5);
-    mbar_init(bar(FB_DN1FREE), 1);
-    mbar_init(bar(FB_RAWFULL), 1);
-    mbar_init(bar(FB_RAWFREE), 1);
+    for (int i = 0; i < FB_RING; ++i) { mbar_init(bar(FB_QFULL + i), 1); mbar_init(bar(FB_QFREE + i), 1); }
     mbar_init(bar(FB_C12RDY), 1);
     mbar_init(bar(FB_MMA12), 1);
-    mbar_init(bar(FB_EPI12), 5);
+    mbar_init(bar(FB_EPI12), 8);
+    mbar_init(bar(FB_DN1RDY), 5);
+    mbar_init(bar(FB_DN1FREE), 1);
     mbar_init(bar(FB_DONE), 1);
     fence_mbar_init();
   }
   if (warp == FB_EPI_WARP0) tmem_alloc<FB_TMEM_COLS>(tslot);
-  __syncthreads();
-  if (warp < FB_AUX_WARPS && lane == 0)                            // x is an input of the step: stream it before the dependency wait
-    for (int j = 0; j < PW_SLOTS; ++j)
-      if (warp + j * FB_AUX_WARPS < n_chunks) issue_chunk(warp + j * FB_AUX_WARPS, warp * PW_SLOTS + j);
-  // zero once: image borders / slack rows of Blk, dead rows of both dn1 buffers, borders of G and Blk2
-  for (int i = tid; i < FBLK_BYTES / 16; i += FB_THREADS) sts128(blk + i * 16, make_uint4(0, 0, 0, 0));
-  for (int i = tid; i < (FB_OFF_W12D - FB_OFF_DN1) / 16; i += FB_THREADS) sts128(dn1s + i * 16, make_uint4(0, 0, 0, 0));
+  // zero once: rows of the dn1 planes that no pixel is ever written to (dead column, slack)
+  for (int i = tid; i < DN1_BYTES / 16; i += FB_THREADS) sts128(dn1s + i * 16, make_uint4(0, 0, 0, 0));
   griddep_launch();
-  evt_mark(evt_i, 50, 0);
-  griddep_wait(K_CONV12_BWD);   // dn2 comes from the dense1 data-gradient GEMM that precedes this kernel
+  griddep_wait(K_CONV12_BWD);   // every input comes from the kernels that precede this one
   if (DP && blockIdx.x == 0 && tid < dp.world) {
     // data parallel: dense_bwd of this rank is complete, i.e. its dense1/w gradient is final -- tell every rank now, a whole
     // conv backward before the exchange at the end of the step needs it (dp_tail_kernel)
@@ -169,15 +142,12 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tslot));
-  evt_mark(evt_i, 51, 0);
 
-  // Data-gradient epilogue of one 128-row tile for TMEM lane quarter `qt`: rows of the first tile go to warps 8-11, the 28
-  // live rows of the second tile (lanes 100..127) to warp 15, which shares lane quarter 3 with warp 11 and is otherwise idle
-  // once the frame's operands are laid out.
+  // Data-gradient epilogue of one 128-row tile for TMEM lane quarter `qt`: rows of the first tile go to warps 4-7, the 28
+  // live rows of the second tile (lanes 100..127) to warp 11.
   auto dgrad_epilogue = [&](int k, int t, int qt, float (&bacc)[C1_OUT]) {
     const uint32_t tlane = tmem_base + ((uint32_t)(qt * 32) << 16);
     mbar_wait(bar(FB_MMA12), k & 1);
-    evt_mark(evt_i, 40, k);
     tc_fence_after();
     uint16_t* dn1_dst = dn1_out ? dn1_out + frame_of(k) * (N1_POS * C1_OUT) : nullptr;
     // Phase 1: TMEM -> relu' mask -> packed bf16 in registers (one 2x2 block of dn1 per row).  Nothing is written yet: the
@@ -215,25 +185,25 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar(FB_EPI12));                     // D is drained and Blk2 has been read: conv12 of the next frame may start
+    if (lane == 0) mbar_arrive(bar(FB_EPI12));                     // D is drained and Blk2 has been read: the next frame's G / Blk2 may land
     // Phase 2: the operand buffer is free once every conv11 UMMA of frame k-1 has retired
     if (k > 0) mbar_wait(bar(FB_DN1FREE), (k - 1) & 1);
-    evt_mark(evt_i, 41, k);
 #pragma unroll
     for (int cls = 0; cls < 4; ++cls) {
       if (p22[cls] >= 0) {
         const uint4 lo4 = make_uint4(o[cls][0], o[cls][1], o[cls][2], o[cls][3]), hi4 = make_uint4(o[cls][4], o[cls][5], o[cls][6], o[cls][7]);
         const uint32_t dst = dn1s + p22[cls] * 16;
-        sts128(dst, lo4);                                          // planes (b = 0, half): row p
-        sts128(dst + DN1_PLANE, hi4);
-        sts128(dst + 2 * DN1_PLANE + 16, lo4);                     // planes (b = 1, half): row p + 1
-        sts128(dst + 3 * DN1_PLANE + 16, hi4);
+#pragma unroll
+        for (int ab = 0; ab < 4; ++ab) {                           // planes (a, b, half): the pixel's row moved down by 22a + b
+          const uint32_t d = dst + (2 * ab) * DN1_PLANE + (BLK_W * (ab >> 1) + (ab & 1)) * 16;
+          sts128(d, lo4);
+          sts128(d + DN1_PLANE, hi4);
+        }
       }
     }
     fence_proxy_async();                                           // the dn1 operand is read by the tensor core
     __syncwarp();
     if (lane == 0) mbar_arrive(bar(FB_DN1RDY));
-    evt_mark(evt_i, 42, k);
   };
   auto b11_partial = [&](int slot, const float (&bacc)[C1_OUT]) {   // warp-reduce the 16 channel sums of this warp
 #pragma unroll
@@ -245,47 +215,44 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
     }
   };
 
-  if (warp < FB_AUX_WARPS) {
-    // =========================== aux: one chunk pipeline per warp (conv_blk.cuh) ===========================
-    uint32_t lane_off[3];
-    blk_lane_offsets<FBLK_LBO>(lane, lane_off);
-    int j = 0;
-#pragma unroll 1
-    for (int q = warp; q < n_chunks; q += FB_AUX_WARPS, ++j) {
-      const int k = q / PW_NCHUNK, c = q - k * PW_NCHUNK, slot = warp * PW_SLOTS + (j & 1);
-      uint32_t pk[PW_ROWS][3][2];
-      evt_mark(evt_i, 1, q);
-      mbar_wait(bar(FB_RING + slot), (j >> 1) & 1);                 // the chunk has landed
-      evt_mark(evt_i, 3, q);
-      blk_load_rows4<U8>(ring + slot * PW_BYTES, lane, pk);
-      __syncwarp();                                                  // every lane has read its part: the slot is free
-      if (lane == 0 && q + PW_SLOTS * FB_AUX_WARPS < n_chunks) issue_chunk(q + PW_SLOTS * FB_AUX_WARPS, slot);
-      // block rows c, c+1 are rewritten: the last consumer group of frame k-1 that reads them must have retired
-      evt_mark(evt_i, 5, q);
-      if (k > 0) mbar_wait(bar(FB_GRP + pw_last_consumer(c)), (k - 1) & 1);
-      evt_mark(evt_i, 2, q);
-      blk_store_rows4<FBLK_LBO>(blk, c, lane, lane_off, pk);
-      fence_proxy_async();                                           // Blk is read by the tensor core
+  if (warp == FB_LOAD_WARP) {
+    // =========================== Blk quarters -> ring ===========================
+    const int n_q = n_frames * XB_QUARTERS;
+    for (int qg = 0; qg < n_q; ++qg) {
+      const int slot = qg % FB_RING, use = qg / FB_RING;
+      if (use > 0) mbar_wait(bar(FB_QFREE + slot), (use - 1) & 1);
+      if (elect_one()) {
+        const int k = qg >> 2, q = qg & 3;
+        mbar_expect_tx(bar(FB_QFULL + slot), XB_QBYTES);
+        bulk_load(ring + slot * XB_QBYTES, xblk + frame_of(k) * XB_FRAME_BYTES + q * XB_QBYTES, XB_QBYTES, bar(FB_QFULL + slot));
+      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(FB_BLKRDY + pw_first_consumer(c)));
-      evt_mark(evt_i, 4, q);
+    }
+  } else if (warp == FB_C12_WARP) {
+    // =========================== G / Blk2 of the next frame ===========================
+    for (int k = 0; k < n_frames; ++k) {
+      if (k > 0) mbar_wait(bar(FB_EPI12), (k - 1) & 1);            // UMMAs, mask reads and column sums of frame k-1 are done
+      if (elect_one()) {
+        mbar_expect_tx(bar(FB_C12RDY), G_BYTES + 2 * B2_BYTES - 16);
+        bulk_load(gg, dn2g + frame_of(k) * G_BYTES, G_BYTES, bar(FB_C12RDY));
+        bulk_load(b2, n1b2 + frame_of(k) * B2_BYTES, B2_BYTES, bar(FB_C12RDY));
+        bulk_load(b2 + B2_BYTES, n1b2 + frame_of(k) * B2_BYTES + 16, B2_BYTES - 16, bar(FB_C12RDY));   // the same, one row up
+      }
+      __syncwarp();
     }
   } else if (warp == FB_ISSUE_WARP) {
     // =========================== MMA issuer ===========================
     // warp-uniform: all 32 lanes run the loops and wait on the barriers, elect_one() issues
-    constexpr uint32_t idesc_dg = make_idesc_m(128, 64, false, false), idesc_w12 = make_idesc_m(64, C2_OUT, true, true),
-                       idesc_w11 = make_idesc_m(64, 2 * C1_OUT, true, true);
+    constexpr uint32_t idesc_dg = make_idesc_m(128, 64, false, false), idesc_w12 = make_idesc_m(128, C2_OUT, true, true),
+                       idesc_w11 = make_idesc_m(64, 4 * C1_OUT, true, true);
     // descriptor low words of row 0 / k-chunk 0 of every operand; a shift of r rows is + r, a k-chunk plane is + LBO/16
     const uint32_t g_k = desc_ns_lo(gg, G_LBO), wd_k = desc_ns_lo(w12d, 1024);                 // K-major: LBO = plane, SBO = 128
-    const uint32_t g_mn = desc_ns_lo(gg, 128), b2_mn = desc_ns_lo(b2, 128), blk_mn = desc_ns_lo(blk, 128),
+    const uint32_t g_mn = desc_ns_lo(gg, 128), b2_mn = desc_ns_lo(b2, 128), ring_mn = desc_ns_lo(ring, 128),
                    dn1_mn = desc_ns_lo(dn1s, 128);                                             // MN-major: LBO = 128, SBO = plane
-    constexpr uint32_t hi_k = desc_ns_hi(128), hi_g = desc_ns_hi(G_LBO), hi_b2 = desc_ns_hi(B2_LBO), hi_blk = desc_ns_hi(FBLK_LBO),
+    constexpr uint32_t hi_k = desc_ns_hi(128), hi_g = desc_ns_hi(G_LBO), hi_b2 = desc_ns_hi(B2_LBO), hi_ring = desc_ns_hi(XB_PLANE_BYTES),
                        hi_dn1 = desc_ns_hi(DN1_PLANE);
     auto conv12_mmas = [&](int k) {
-      evt_mark(evt_i, 10, k);
-      mbar_wait(bar(FB_C12RDY), k & 1);                            // G / Blk2 hold frame k
-      evt_mark(evt_i, 11, k);
-      if (k > 0) mbar_wait(bar(FB_EPI12), (k - 1) & 1);            // D of frame k-1 has been drained
+      mbar_wait(bar(FB_C12RDY), k & 1);                            // G / Blk2 hold frame k (and D of frame k-1 has been drained)
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -301,102 +268,73 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
 #pragma unroll
         for (int s = 0; s < W12_KSTEPS; ++s)
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            // A: Blk2 rows 16 s + 13 a + b .., B: G rows 16 s + 14 ..; both MN-major
-            tc_mma_bf16_w(tmem_base + TM_W12 + 32 * q, b2_mn + 16 * s + G_W * (q >> 1) + (q & 1), hi_b2, g_mn + 16 * s + G_W + 1, hi_g,
+          for (int a = 0; a < 2; ++a)
+            // A: Blk2 rows 16 s + 13 a .. in 16 planes (b, dy, dx, half), B: G rows 16 s + 14 ..; both MN-major
+            tc_mma_bf16_w(tmem_base + TM_W12 + 32 * a, b2_mn + 16 * s + G_W * a, hi_b2, g_mn + 16 * s + G_W + 1, hi_g,
                           idesc_w12, s ? 1u : acc);
         tc_commit(bar(FB_MMA12));
       }
       __syncwarp();
-      evt_mark(evt_i, 12, k);
     };
-    if (n_frames > 0) conv12_mmas(0);
-    for (int k = 0; k < n_frames; ++k) {
-      evt_mark(evt_i, 13, k);
+    auto conv11_mmas = [&](int k) {
       mbar_wait(bar(FB_DN1RDY), k & 1);
-      evt_mark(evt_i, 14, k);
-#pragma unroll
-      for (int gi = 0; gi < 4; ++gi) {
-        if (gi == 1 && k + 1 < n_frames) conv12_mmas(k + 1);       // one frame ahead of the conv11 gradient
-        mbar_wait(bar(FB_BLKRDY + gi), k & 1);
-        evt_mark(evt_i, 15, k * 4 + gi);
+#pragma unroll 1
+      for (int q = 0; q < XB_QUARTERS; ++q) {
+        const int qg = k * XB_QUARTERS + q, slot = qg % FB_RING;
+        mbar_wait(bar(FB_QFULL + slot), (qg / FB_RING) & 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t acc = k ? 1u : 0u;
-#pragma unroll
-          for (int s = 8 * gi; s < (gi == 3 ? W11_KSTEPS : 8 * gi + 8); ++s)
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-              // A: Blk rows 16 s + 22 a .., B: dn1 rows 16 s .. in the four (b, half) planes; both MN-major
-              tc_mma_bf16_w(tmem_base + TM_W11 + 32 * a, blk_mn + 16 * s + BLK_W * a, hi_blk, dn1_mn + 16 * s, hi_dn1, idesc_w11,
-                            s ? 1u : acc);
-          tc_commit(bar(FB_GRP + gi));
-          if (gi == 3) tc_commit(bar(FB_DN1FREE));
+          const int n_kk = q == 3 ? W11_KSTEPS - 24 : 8;
+          for (int kk = 0; kk < n_kk; ++kk) {
+            const int s = 8 * q + kk;
+            // A: block rows 16 s .. of the quarter slot (8 planes), B: dn1 rows 16 s .. in the eight (a, b, half) planes
+            tc_mma_bf16_w(tmem_base + TM_W11, ring_mn + slot * (XB_QBYTES / 16) + kk * 16, hi_ring, dn1_mn + 16 * s, hi_dn1,
+                          idesc_w11, (k | s) ? 1u : 0u);
+          }
+          tc_commit(bar(FB_QFREE + slot));
+          if (q == 3) tc_commit(bar(FB_DN1FREE));
         }
         __syncwarp();
-        evt_mark(evt_i, 16, k * 4 + gi);
       }
+    };
+    if (n_frames > 0) conv12_mmas(0);
+    if (n_frames > 1) conv12_mmas(1);
+    for (int k = 0; k < n_frames; ++k) {
+      conv11_mmas(k);
+      if (k + 2 < n_frames) conv12_mmas(k + 2);                    // two frames ahead: its epilogue runs under the next conv11 gradient
     }
     if (elect_one()) tc_commit(bar(FB_DONE));
     __syncwarp();
-  } else if (warp == FB_TMA_WARP) {
-    // =========================== n1 / dn2 of the next frame -> raw staging buffer ===========================
-    if (lane == 0) {
-      for (int k = 0; k < n_frames; ++k) {
-        if (k > 0) mbar_wait(bar(FB_RAWFREE), (k - 1) & 1);
-        evt_mark(evt_i, 20, k);
-        mbar_expect_tx(bar(FB_RAWFULL), RAW_BYTES);
-        bulk_load(raw, dn2 + frame_of(k) * FLAT, RAW_DN2, bar(FB_RAWFULL));
-        bulk_load(raw + RAW_DN2, n1 + frame_of(k) * (N1_POS * C1_OUT), RAW_N1, bar(FB_RAWFULL));
-      }
-    }
-  } else if (warp >= FB_RE_WARP0) {
-    // =========================== raw -> G / Blk2, conv12 bias gradient ===========================
-    const int rtid = tid - 32 * FB_RE_WARP0;
-    float bacc = 0.f;                                              // db12 partial: channel rtid & 31, position phase rtid >> 5
-    float bacc11[C1_OUT];                                          // warp 15: db11 partials of the second data-gradient tile
+  } else if (warp >= FB_B12_WARP0) {
+    // =========================== conv12 bias gradient (column sums of G); warp 11: second data-gradient tile ===========================
+    const int rtid = tid - 32 * FB_B12_WARP0;
+    const int co = rtid & 31;
+    const uint32_t col = gg + (co >> 3) * G_LBO + (co & 7) * 2;
+    float bacc = 0.f;                                              // db12 partial: channel rtid & 31, row phase rtid >> 5
+    float bacc11[C1_OUT];                                          // warp 11: db11 partials of the second data-gradient tile
 #pragma unroll
     for (int c = 0; c < C1_OUT; ++c) bacc11[c] = 0.f;
     for (int k = 0; k < n_frames; ++k) {
-      mbar_wait(bar(FB_RAWFULL), k & 1);
-      evt_mark(evt_i, 30, k);
-      if (k > 0) mbar_wait(bar(FB_EPI12), (k - 1) & 1);            // conv12 UMMAs and mask reads of frame k-1 are done
-      evt_mark(evt_i, 31, k);
-      for (int i = rtid; i < N2_POS * 4; i += 128) {               // dn2: 4 chunks of 8 co per position
-        const int pos = i >> 2, j = i & 3, oy = pos / H2, ox = pos - oy * H2;
-        uint32_t r[4];
-        lds128(r, raw + i * 16);
-        sts128(gg + j * G_LBO + ((oy + 1) * G_W + ox + 1) * 16, make_uint4(r[0], r[1], r[2], r[3]));
+      mbar_wait(bar(FB_C12RDY), k & 1);
+      for (int row = rtid >> 5; row < G_ROWS; row += 4) {          // border rows are zero
+        uint16_t v;
+        asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(col + row * 16));
+        bacc += __uint_as_float((uint32_t)v << 16);
       }
-      for (int i = rtid; i < N1_POS * 2; i += 128) {               // n1: 2 chunks of 8 ci per pixel
-        const int p = i >> 1, h = i & 1, y = p / H1, Y = y + 1, X = p - y * H1 + 1;
-        uint32_t r[4];
-        lds128(r, raw + RAW_DN2 + i * 16);
-        sts128(b2 + ((((Y & 1) * 2 + (X & 1)) * 2 + h) * B2_LBO) + ((Y >> 1) * G_W + (X >> 1)) * 16, make_uint4(r[0], r[1], r[2], r[3]));
+      if (warp == FB_B12_WARP0 + 3) {
+        dgrad_epilogue(k, 1, 3, bacc11);                           // arrives on EPI12 / DN1RDY itself
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(FB_EPI12));
       }
-      fence_proxy_async();
-      named_bar_sync(3, 128);
-      if (rtid == 0) mbar_arrive(bar(FB_C12RDY));                  // the UMMAs can go; the bias sums below only read raw
-      evt_mark(evt_i, 32, k);
-      {
-        const int co = rtid & 31;
-        for (int pos = rtid >> 5; pos < N2_POS; pos += 4) {
-          uint16_t v;
-          asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(raw + pos * 64 + co * 2));
-          bacc += __uint_as_float((uint32_t)v << 16);
-        }
-      }
-      named_bar_sync(3, 128);
-      if (rtid == 0) mbar_arrive(bar(FB_RAWFREE));
-      if (warp == FB_RE_WARP0 + 3) dgrad_epilogue(k, 1, 3, bacc11);
     }
     red[RED_B12 + rtid] = bacc;
-    if (warp == FB_RE_WARP0 + 3) b11_partial(4, bacc11);
+    if (warp == FB_B12_WARP0 + 3) b11_partial(4, bacc11);
     named_bar_sync(3, 128);
     if (rtid < C2_OUT)
       g_b12[(int64_t)blockIdx.x * gp_stride + rtid] =
           red[RED_B12 + rtid] + red[RED_B12 + 32 + rtid] + red[RED_B12 + 64 + rtid] + red[RED_B12 + 96 + rtid];
-  } else {
+  } else if (warp >= FB_EPI_WARP0) {
     // =========================== data-gradient epilogue; final store ===========================
     const int ew = warp - FB_EPI_WARP0;                            // TMEM lane quarter
     const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16);
@@ -404,48 +342,51 @@ conv_bwd_kernel(const void* __restrict__ x, const uint16_t* __restrict__ n1, con
 #pragma unroll
     for (int c = 0; c < C1_OUT; ++c) bacc[c] = 0.f;
     for (int k = 0; k < n_frames; ++k) dgrad_epilogue(k, 0, ew, bacc);
-    b11_partial(ew, bacc);                                         // summed with warp 15's after the final block barrier
-    // weight-gradient accumulators: M = 64 rows sit on TMEM lanes 32 w + (0..15) (rows 16 w ..); row = chunk plane * 8 + e
+    b11_partial(ew, bacc);                                         // summed with warp 11's after the final block barrier
     if (n_frames > 0) {
       mbar_wait(bar(FB_DONE), 0);
       tc_fence_after();
       float* const s11 = g_w11 + (int64_t)blockIdx.x * gp_stride;
       float* const s12 = g_w12 + (int64_t)blockIdx.x * gp_stride;
-      const int row = 16 * ew + lane, j = row >> 3, e = row & 7;
+      {
+        // conv11 accumulator: M = 64 rows sit on TMEM lanes 32 w + (0..15) (rows 16 w ..); row = chunk plane * 8 + e;
+        // columns 16 q .. of quadrant q = a*2 + b
+        const int row = 16 * ew + lane, j = row >> 3, e = row & 7;
 #pragma unroll 1
-      for (int q = 0; q < 4; ++q) {                                // q = a*2 + b: accumulator a, columns 16 b ..
-        uint32_t r[16];
-        tc_ld16(tlane + TM_W11 + 32 * (q >> 1) + 16 * (q & 1), r);
-        if (lane < 16) {
-          // conv11 block element: j = dy*2 + (dx>>1), e = (dx&1)*4 + c
-          const int kh = 4 * (q >> 1) + (j >> 1), kw = 4 * (q & 1) + (j & 1) * 2 + (e >> 2), c = e & 3;
-          float4* o = reinterpret_cast<float4*>(s11 + ((kh * 8 + kw) * 4 + c) * C1_OUT);
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc_ld16(tlane + TM_W11 + 16 * q, r);
+          if (lane < 16) {
+            // conv11 block element: j = dy*2 + (dx>>1), e = (dx&1)*4 + c
+            const int kh = 4 * (q >> 1) + (j >> 1), kw = 4 * (q & 1) + (j & 1) * 2 + (e >> 2), c = e & 3;
+            float4* o = reinterpret_cast<float4*>(s11 + ((kh * 8 + kw) * 4 + c) * C1_OUT);
 #pragma unroll
-          for (int n = 0; n < C1_OUT / 4; ++n)
-            o[n] = make_float4(__uint_as_float(r[4 * n]), __uint_as_float(r[4 * n + 1]), __uint_as_float(r[4 * n + 2]),
-                               __uint_as_float(r[4 * n + 3]));
+            for (int n = 0; n < C1_OUT / 4; ++n)
+              o[n] = make_float4(__uint_as_float(r[4 * n]), __uint_as_float(r[4 * n + 1]), __uint_as_float(r[4 * n + 2]),
+                                 __uint_as_float(r[4 * n + 3]));
+          }
         }
       }
+      {
+        // conv12 accumulators (one per a): M = 128, row = lane of the tile = b*64 + plane*8 + e, plane = (dy*2 + dx)*2 + (ci>>3)
+        const int row = 32 * ew + lane, b = row >> 6, j = (row >> 3) & 7, e = row & 7;
 #pragma unroll 1
-      for (int q = 0; q < 4; ++q)
+        for (int a = 0; a < 2; ++a)
 #pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t r[16];
-          tc_ld16(tlane + TM_W12 + 32 * q + 16 * hh, r);
-          if (lane < 16) {
-            // conv12 block element: j = (dy*2 + dx)*2 + (ci>>3), e = ci & 7
-            const int kh = 2 * (q >> 1) + (j >> 2), kw = 2 * (q & 1) + ((j >> 1) & 1), ci = (j & 1) * 8 + e;
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t r[16];
+            tc_ld16(tlane + TM_W12 + 32 * a + 16 * hh, r);
+            const int kh = 2 * a + (j >> 2), kw = 2 * b + ((j >> 1) & 1), ci = (j & 1) * 8 + e;
             float4* o = reinterpret_cast<float4*>(s12 + ((kh * 4 + kw) * C1_OUT + ci) * C2_OUT + 16 * hh);
 #pragma unroll
             for (int n = 0; n < 4; ++n)
               o[n] = make_float4(__uint_as_float(r[4 * n]), __uint_as_float(r[4 * n + 1]), __uint_as_float(r[4 * n + 2]),
                                  __uint_as_float(r[4 * n + 3]));
           }
-        }
+      }
     }
   }
 
-  evt_mark(evt_i, 52, 0);
   tc_fence_before();
   __syncthreads();
   if (tid < C1_OUT)                                                // conv11 bias gradient: the five warp partials in a fixed order
@@ -464,25 +405,21 @@ GA3C_EVT_ATTACH(evt_attach_conv_bwd)
 int conv_bwd_grid(int batch, int num_sms, int n_exch) { return min(batch, num_sms - n_exch); }
 
 int configure_conv_bwd_fused() {
-  cudaError_t e = cudaFuncSetAttribute(conv_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(conv_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(conv_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(conv_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
-  if (e != cudaSuccess) return (int)e;
-  return (int)cudaFuncSetAttribute(conv_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+  return (int)cudaFuncSetAttribute(conv_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
 }
 
-int launch_conv_bwd(const void* x, bool x_u8, const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1_out,
+int launch_conv_bwd(const uint8_t* xblk, const uint8_t* n1b2, const uint8_t* dn2g, const float* w12, uint16_t* dn1_out,
                     float* g_w11, float* g_b11, float* g_w12, float* g_b12, int64_t gp_stride, int batch, int num_sms,
                     const DpBigArgs* dp, cudaStream_t stream) {
   DpBigArgs d{};
   if (dp != nullptr) d = *dp;
   const int n_conv = conv_bwd_grid(batch, num_sms, d.n_exch);
   const dim3 grid(n_conv + d.n_exch);
-  auto kernel = dp != nullptr ? (x_u8 ? conv_bwd_kernel<true, true> : conv_bwd_kernel<false, true>)
-                              : (x_u8 ? conv_bwd_kernel<true, false> : conv_bwd_kernel<false, false>);
-  return launch_pdl(kernel, grid, dim3(FB_THREADS), FB_SMEM, stream, x, n1, dn2, w12, dn1_out, g_w11, g_b11, g_w12, g_b12,
+  if (grid.x == 0) return 0;
+  auto kernel = dp != nullptr ? conv_bwd_kernel<true> : conv_bwd_kernel<false>;
+  return launch_pdl(kernel, grid, dim3(FB_THREADS), FB_SMEM, stream, xblk, n1b2, dn2g, w12, dn1_out, g_w11, g_b11, g_w12, g_b12,
                     gp_stride, batch, n_conv, d);
 }
 

@@ -26,8 +26,10 @@
 //   warps 0-5  (aux)  one independent pipeline per warp: chunk -> bf16 -> Blk, re-arm the slot with the warp's chunk after next
 //   warp  6           one thread issues the UMMAs: conv11 tile i as soon as its Blk rows are converted, conv12 after the
 //                     conv11 epilogues; tcgen05.commit signals TMEM-full / operand-free mbarriers
+//   warp  7           training only: copies every finished quarter of Blk (128 block rows, 8 planes) to HBM with cp.async.bulk --
+//                     the bf16 block matrix the conv backward reads back instead of the fp32 frame (common.cuh: xblk)
 //   warps 8-15        epilogues, two sets of four warps (one TMEM lane quarter each): conv11 tile -> +bias, ReLU -> im2col
-//                     scatter (+ n1 to HBM when training); conv12 tile -> +bias, ReLU -> n2 to HBM
+//                     scatter (+ n1 to HBM in the Blk2 operand layout when training); conv12 tile -> +bias, ReLU -> n2 to HBM
 #include "common.cuh"
 #include "kernels.h"
 #include "tcgen05.cuh"
@@ -35,7 +37,7 @@
 
 namespace ga3c {
 
-constexpr int CF_THREADS = 512, CF_AUX_WARPS = 6, CF_ISSUE_WARP = 6, CF_EPI_WARP0 = 8;     // two epilogue sets: warps 8-11, 12-15
+constexpr int CF_THREADS = 512, CF_AUX_WARPS = 6, CF_ISSUE_WARP = 6, CF_STORE_WARP = 7, CF_EPI_WARP0 = 8;     // two epilogue sets: warps 8-11, 12-15
 static_assert(CF_EPI_WARP0 % 4 == 0, "epilogue warp e must own TMEM lane quarter e");
 constexpr int C11_TILES = 4;                     // 462 output rows (21 x 22, column 21 dead) in 4 x 128
 constexpr int C11_TSTRIDE = 127;                                     // output rows per tile (tile row 127 only feeds row 126)
@@ -57,7 +59,8 @@ constexpr int BAR_T1FREE = 20;       // [4]  conv11 TMEM tile i drained, 4 arriv
 constexpr int BAR_A2RDY = 24;        //      im2col operand of the frame complete, 4 arrivals (epilogue -> issuer)
 constexpr int BAR_MMA2 = 25;         //      conv12 accumulated (tcgen05.commit)            (-> epilogue; im2col operand free)
 constexpr int BAR_T2FREE = 26;       //      conv12 TMEM tile drained, 4 arrivals           (epilogue -> issuer)
-constexpr int CF_NBAR = 27;
+constexpr int BAR_STORED = 27;       // [4]  quarter q of Blk has been read by the bulk stores to HBM (store warp -> aux: rows free)
+constexpr int CF_NBAR = 31;
 constexpr int CF_OFF_TSLOT = CF_OFF_BAR + CF_NBAR * 8;               // 228,696
 constexpr int CF_OFF_XCH = CF_OFF_TSLOT + 16;                        // [2 sets][2][4 warps][16 floats] b-shift exchange across warps
 constexpr int CF_SMEM = CF_OFF_XCH + 1024 + 1024;                    // incl. slack to align the base to 1024 B
@@ -68,7 +71,7 @@ template <bool U8>       // U8: frames are uint8 [B,28224] (x = k/128 - 1 applie
 __global__ void __launch_bounds__(CF_THREADS, 1)
 conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const float* __restrict__ b11,
                 const float* __restrict__ w12, const float* __restrict__ b12,
-                uint16_t* __restrict__ n1_out, uint16_t* __restrict__ n2_out, int batch) {
+                uint8_t* __restrict__ n1_out, uint8_t* __restrict__ xblk_out, uint16_t* __restrict__ n2_out, int batch) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const smem = smem_raw + (sbase - smem_u32(smem_raw));
@@ -100,6 +103,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
     mbar_init(bar(BAR_A2RDY), 8);
     mbar_init(bar(BAR_MMA2), 1);
     mbar_init(bar(BAR_T2FREE), 4);
+    for (int i = 0; i < 4; ++i) mbar_init(bar(BAR_STORED + i), 1);
     fence_mbar_init();
   }
   if (warp == CF_EPI_WARP0) tmem_alloc<CF_TMEM_COLS>(tslot);
@@ -174,7 +178,11 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
       __syncwarp();                                                  // every lane has read its part: the slot is free
       if (lane == 0 && q + PW_SLOTS * CF_AUX_WARPS < n_chunks) issue_chunk(q + PW_SLOTS * CF_AUX_WARPS, slot);
       // block rows c, c+1 are rewritten: the last consumer group of frame k-1 that reads them must have retired
-      if (k > 0) mbar_wait(bar(BAR_C11 + pw_last_consumer(c)), (k - 1) & 1);
+      if (k > 0) {
+        mbar_wait(bar(BAR_C11 + pw_last_consumer(c)), (k - 1) & 1);
+        // ... and the copy of these rows to HBM must have read them (block rows c, c+1 end in quarter pw_last_consumer(c))
+        if (xblk_out != nullptr) mbar_wait(bar(BAR_STORED + pw_last_consumer(c)), (k - 1) & 1);
+      }
       blk_store_rows4<BLK_LBO>(blk, c, lane, lane_off, pk);
       fence_proxy_async();                                           // Blk is read by the tensor core
       __syncwarp();
@@ -222,6 +230,29 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
       __syncwarp();
       evt_mark(evt_i, 18, k);
     }
+  } else if (warp == CF_STORE_WARP) {
+    // =========================== Blk -> HBM (training) ===========================
+    // Quarter q (block rows 128 q ..) is complete when conv11 tile q's rows are (BAR_BLKRDY + q: block rows up to 6 / 12 / 18 /
+    // 21 cover rows 153 / 285 / 417 / 483).  Lane j copies chunk plane j: 2 KB contiguous in shared memory and in HBM
+    // ([frame][quarter][plane][128 rows][16 B]); the last quarter holds 100 live rows, the rest of it stays zero in HBM.
+    if (xblk_out != nullptr) {
+      for (int k = 0; k < n_frames; ++k) {
+        uint8_t* dst = xblk_out + frame_of(k) * XB_FRAME_BYTES;
+#pragma unroll 1
+        for (int q = 0; q < XB_QUARTERS; ++q) {
+          mbar_wait(bar(BAR_BLKRDY + q), k & 1);
+          if (lane < 8) {
+            const uint32_t bytes = q < 3 ? XB_PLANE_BYTES : (XB_LIVE_ROWS - 3 * XB_QROWS) * 16;
+            bulk_store(dst + q * XB_QBYTES + lane * XB_PLANE_BYTES, blk + lane * BLK_LBO + q * XB_PLANE_BYTES, bytes);
+            bulk_commit();
+            bulk_wait_read0();                                     // shared memory has been read: the rows may be overwritten
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_STORED + q));
+        }
+      }
+      if (lane < 8) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // the writes are complete before the kernel ends
+    }
   } else if (warp >= CF_EPI_WARP0) {
     // =========================== epilogues ===========================
     // Two sets of four warps (one TMEM lane quarter each): set 0 drains conv11 tiles 0 and 2, set 1 the conv12 tile of the
@@ -259,7 +290,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
         else mbar_wait(bar(BAR_MMA2), (k - 1) & 1);
       }
       evt_mark(evt_i, 44, k);
-      uint16_t* n1_dst = n1_out ? n1_out + frame_of(k) * (N1_POS * C1_OUT) : nullptr;
+      uint8_t* n1_dst = n1_out ? n1_out + frame_of(k) * B2_BYTES : nullptr;      // Blk2 operand layout (common.cuh)
 #pragma unroll 1
       for (int i = eset; i < C11_TILES; i += 2) {
         mbar_wait(bar(BAR_C11 + i), k & 1);
@@ -304,9 +335,9 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
             }
           }
           if (n1_dst) {
-            uint4* d = reinterpret_cast<uint4*>(n1_dst + p * C1_OUT);
-            d[0] = lo;
-            d[1] = hi;
+            uint8_t* d = n1_dst + b2_pixel_offset(oy, ox, 0);
+            *reinterpret_cast<uint4*>(d) = lo;
+            *reinterpret_cast<uint4*>(d + B2_LBO) = hi;
           }
         }
       }
@@ -337,11 +368,13 @@ int configure_conv_fwd() {
 }
 
 int launch_conv_fwd(const void* x, bool x_u8, const float* w11, const float* b11, const float* w12, const float* b12,
-                    uint16_t* n1_out, uint16_t* n2_out, int batch, int num_sms, cudaStream_t stream) {
+                    uint8_t* n1_out, uint8_t* xblk_out, uint16_t* n2_out, int batch, int num_sms, cudaStream_t stream) {
   const int grid = min(batch, num_sms);
   if (x_u8)
-    return launch_pdl(conv_fwd_kernel<true>, dim3(grid), dim3(CF_THREADS), CF_SMEM, stream, x, w11, b11, w12, b12, n1_out, n2_out, batch);
-  return launch_pdl(conv_fwd_kernel<false>, dim3(grid), dim3(CF_THREADS), CF_SMEM, stream, x, w11, b11, w12, b12, n1_out, n2_out, batch);
+    return launch_pdl(conv_fwd_kernel<true>, dim3(grid), dim3(CF_THREADS), CF_SMEM, stream, x, w11, b11, w12, b12, n1_out, xblk_out,
+                      n2_out, batch);
+  return launch_pdl(conv_fwd_kernel<false>, dim3(grid), dim3(CF_THREADS), CF_SMEM, stream, x, w11, b11, w12, b12, n1_out, xblk_out,
+                    n2_out, batch);
 }
 
 }  // namespace ga3c

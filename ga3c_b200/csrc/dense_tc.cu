@@ -39,8 +39,8 @@ struct EpiPartialF32 {      // raw fp32 tile into part[split][M][N]  (bias + rel
                            __uint_as_float(r[4 * i + 3]));
   }
 };
-struct EpiReluMaskBf16Tc {  // dn2 = acc where n2 > 0 else 0, bf16
-  uint16_t* out; const uint16_t* act; int ldc;
+struct EpiReluMaskBf16Tc {  // dn2 = acc where n2 > 0 else 0, bf16, stored in the G operand layout the conv backward consumes (common.cuh)
+  uint8_t* out; const uint16_t* act; int ldc;
   struct Pre { uint4 a[4]; };     // this thread's 32 activations: fetched while the MMAs are still running
   __device__ __forceinline__ void prefetch(Pre& p, int m, int n, bool ok) const {
     const uint4* a = reinterpret_cast<const uint4*>(act + (size_t)m * ldc + n);
@@ -48,7 +48,9 @@ struct EpiReluMaskBf16Tc {  // dn2 = acc where n2 > 0 else 0, bf16
     for (int i = 0; i < 4; ++i) p.a[i] = ok ? a[i] : make_uint4(0, 0, 0, 0);
   }
   __device__ __forceinline__ void operator()(const Pre& p, int, int m, int n, const uint32_t (&r)[32]) const {
-    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)m * ldc + n);
+    // the 32 columns are the 32 channels of ONE conv12 output position: four 16-byte chunks, one per chunk plane of frame m's G
+    const int pos = n >> 5, oy = pos / H2, ox = pos - oy * H2;
+    uint8_t* dst0 = out + (size_t)m * G_BYTES + g_pos_offset(oy, ox, 0);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint4 av = p.a[i];
@@ -61,7 +63,7 @@ struct EpiReluMaskBf16Tc {  // dn2 = acc where n2 > 0 else 0, bf16
         const float hi = (aw[j] & 0x7FFF0000u) ? __uint_as_float(r[8 * i + 2 * j + 1]) : 0.f;
         o[j] = pack_bf16(lo, hi);
       }
-      dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(dst0 + i * G_LBO) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 };
@@ -305,7 +307,7 @@ int launch_dense_fwd_tc(const uint16_t* n2, const uint16_t* w1bf, float* d1_part
                     EpiPartialF32{d1_part, FC, (int64_t)batch * FC});
 }
 
-int launch_dense_dgrad_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint16_t* dn2, int batch,
+int launch_dense_dgrad_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint8_t* dn2, int batch,
                           cudaStream_t stream) {
   CUtensorMap ta, tb;
   if (make_tmap(&ta, dd1, batch, FC, FC, TC_BM)) return (int)cudaErrorInvalidValue;           // A: [B][256], K inner
@@ -327,7 +329,7 @@ int launch_dense_wgrad_tc(const uint16_t* n2, const uint16_t* dd1, float* g_w1, 
                     EpiPartialF32{g_w1, FC, 0});
 }
 
-int launch_dense_bwd_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint16_t* dn2, float* g_w1, int batch,
+int launch_dense_bwd_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint8_t* dn2, float* g_w1, int batch,
                         cudaStream_t stream) {
   CUtensorMap da, db, wa, wb;
   if (make_tmap(&da, dd1, batch, FC, FC, TC_BM)) return (int)cudaErrorInvalidValue;           // dgrad A: [B][256], K inner

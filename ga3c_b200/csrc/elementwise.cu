@@ -1,5 +1,7 @@
 // HBM-bound elementwise kernels: RMSProp over the flat arena, bf16 shadow refresh, discounted
 // returns, action sampling.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "dp_exchange.cuh"
@@ -591,8 +593,6 @@ __device__ __forceinline__ void dp_small_phase1(const RmsPropDpArgs& d, int64_t 
     griddep_wait(kid);            // the slabs come from the conv backward launch that precedes this one
     evt_mark(evt_i, 61, 0);
     if (st.owner && !a.preload) load_state();
-  } else if (st.owner) {
-    load_state();
   }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const float* src = r.part + j;
@@ -633,13 +633,19 @@ __device__ __forceinline__ void dp_small_phase1(const RmsPropDpArgs& d, int64_t 
   }
 }
 template <bool HAS_MOM>
-__device__ __forceinline__ void dp_small_phase2(const RmsPropDpArgs& d, int64_t recv_offset, EvtLog& evt_i, DpSmallState& st) {
+__device__ __forceinline__ void dp_small_phase2(const RmsPropDpArgs& d, int64_t recv_offset, EvtLog& evt_i, DpSmallState& st,
+                                                bool load) {
   const RmsPropArgs& a = d.base;
   const GradReduceArgs& r = d.red;
   if (!st.owner) return;
   uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
   const uint32_t flag = (uint32_t)d.step;
   const int j = st.j;
+  if (load) {                     // phase 1 ran without the state loads (a block that serves several column blocks)
+    st.w = *reinterpret_cast<const float4*>(a.w + j);
+    st.ms = *reinterpret_cast<const float4*>(a.ms + j);
+    if (HAS_MOM) st.mo = *reinterpret_cast<const float4*>(a.mom + j);
+  }
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int q = 0; q < DP_WORLD_MAX; ++q)
@@ -664,7 +670,7 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_small_kernel(RmsPropDpA
   DpSmallState st;
   uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
   dp_small_phase1<HAS_MOM>(d, recv_offset, blockIdx.x, true, K_RMSPROP, evt_i, st, part);
-  dp_small_phase2<HAS_MOM>(d, recv_offset, evt_i, st);
+  dp_small_phase2<HAS_MOM>(d, recv_offset, evt_i, st, false);
   evt_mark(evt_i, 64, 0);
   if (blockIdx.x == 0 && (int)threadIdx.x < d.world) {
     dp_wait_flag(my_comm + DPC_BIGDONE + 64 * threadIdx.x, d.step, my_comm + DPC_ERR, 16u);
@@ -682,23 +688,42 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_small_kernel(RmsPropDpA
 // until every rank's dense1/w slice has landed.  Every rank's "dense_bwd done" flag was pushed by CTA 0 of its conv backward
 // launch, a whole conv backward ago, so nobody waits for a peer's gradient; the conv backward itself keeps all the SMs
 // (the overlapped variant gives up 20 of them and pays a whole extra round of frames at B = 1024).
+constexpr int DP_TAIL_MAX_SLOTS = 16;      // column blocks one block may serve (grids smaller than n_cb: tests that share a GPU)
 template <bool HAS_MOM>
 __global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_tail_kernel(RmsPropDpArgs d, DpBigArgs big, int64_t recv_offset, int n_cb) {
   __shared__ float4 part[GR_LANES][GR_COLS];
+  __shared__ float4 acc_s[DP_TAIL_MAX_SLOTS][GR_COLS];
   EvtLog evt_i = evt_open();
-  DpSmallState st;
-  st.owner = false;
+  DpSmallState st0;
+  st0.owner = false;
   uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
-  const bool small_block = (int)blockIdx.x < n_cb;
-  if (small_block) {
-    dp_small_phase1<HAS_MOM>(d, recv_offset, blockIdx.x, true, K_RMSPROP, evt_i, st, part);
-  } else {
+  int slot = 0;
+  for (int cb = blockIdx.x; cb < n_cb; cb += gridDim.x, ++slot) {
+    DpSmallState st;
+    dp_small_phase1<HAS_MOM>(d, recv_offset, cb, slot == 0, K_RMSPROP, evt_i, st, part);
+    if (slot == 0) st0 = st;
+    else if (threadIdx.x < GR_COLS) acc_s[slot][threadIdx.x] = st.acc;
+    __syncthreads();                                     // `part` is reused by the next column block
+  }
+  if (slot == 0) {
     griddep_launch();
     griddep_wait(K_RMSPROP);
   }
   dp_big_exchange(big, (int)blockIdx.x, (int)gridDim.x);
   evt_mark(evt_i, 67, 0);
-  if (small_block) dp_small_phase2<HAS_MOM>(d, recv_offset, evt_i, st);
+  slot = 0;
+  for (int cb = blockIdx.x; cb < n_cb; cb += gridDim.x, ++slot) {
+    if (slot == 0) {
+      dp_small_phase2<HAS_MOM>(d, recv_offset, evt_i, st0, false);
+    } else {
+      DpSmallState st;
+      const int col = threadIdx.x & (GR_COLS - 1);
+      st.j = (cb * GR_COLS + col) * 4;
+      st.owner = threadIdx.x < GR_COLS && st.j < d.red.out_floats;
+      st.acc = acc_s[slot][col];
+      dp_small_phase2<HAS_MOM>(d, recv_offset, evt_i, st, true);
+    }
+  }
   evt_mark(evt_i, 64, 0);
   if (blockIdx.x == 0 && (int)threadIdx.x < d.world) {
     dp_wait_flag(my_comm + DPC_BIGDONE + 64 * threadIdx.x, d.step, my_comm + DPC_ERR, 16u);
@@ -734,7 +759,11 @@ int launch_dp_small(const RmsPropDpArgs& d, int64_t recv_offset, cudaStream_t st
 int launch_dp_tail(const RmsPropDpArgs& d, const DpBigArgs& big, int64_t recv_offset, int num_sms, cudaStream_t stream) {
   const int n_cb = (d.red.n_floats / 4 + GR_COLS - 1) / GR_COLS;
   if (n_cb > DP_MAX_CB || !d.has_red) return (int)cudaErrorInvalidValue;
-  const int grid = n_cb > num_sms ? n_cb : num_sms;
+  int grid = n_cb > num_sms ? n_cb : num_sms;
+  if (const char* e = getenv("GA3C_DP_TAIL_CTAS")) {     // tests with several ranks on one GPU leave SMs to the other ranks' kernels
+    const int g = atoi(e);
+    if (g >= (n_cb + DP_TAIL_MAX_SLOTS - 1) / DP_TAIL_MAX_SLOTS && g <= grid) grid = g;
+  }
   if (d.base.momentum != 0.f)
     return launch_pdl(dp_tail_kernel<true>, dim3(grid), dim3(GR_LANES * GR_COLS), 0, stream, d, big, recv_offset, n_cb);
   return launch_pdl(dp_tail_kernel<false>, dim3(grid), dim3(GR_LANES * GR_COLS), 0, stream, d, big, recv_offset, n_cb);

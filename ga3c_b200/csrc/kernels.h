@@ -22,19 +22,20 @@ int configure_conv_fwd();
 int configure_conv_bwd_fused();
 int configure_dense_tc();
 
-// conv_fwd.cu -- x fp32 (or uint8, x_u8: k/128 - 1 applied on the fly) [B,28224] -> n1 bf16 [B,441,16] (optional), n2 bf16 [B,3872]
+// conv_fwd.cu -- x fp32 (or uint8, x_u8: k/128 - 1 applied on the fly) [B,28224] -> n2 bf16 [B,3872]; when training also n1 (bf16, in
+// the Blk2 operand layout) and xblk (the bf16 block matrix of the frame): both are read back by the conv backward (common.cuh)
 int launch_conv_fwd(const void* x, bool x_u8, const float* w11, const float* b11, const float* w12, const float* b12,
-                    uint16_t* n1_out, uint16_t* n2_out, int batch, int num_sms, cudaStream_t stream);
+                    uint8_t* n1_out, uint8_t* xblk_out, uint16_t* n2_out, int batch, int num_sms, cudaStream_t stream);
 
 // dense_tc.cu -- the three dense1 GEMMs (NetworkDNav.py:90 and its autodiff) on tcgen05 / TMEM / TMA.  fwd leaves `splits` raw fp32 partial tiles
 // in d1_part[splits][B][256]; the heads kernel sums them, adds the bias and applies the ReLU.
 int dense_fwd_splits(int batch, int num_sms);
 int launch_dense_fwd_tc(const uint16_t* n2, const uint16_t* w1bf, float* d1_part, int batch, int splits, cudaStream_t stream);
-int launch_dense_dgrad_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint16_t* dn2, int batch,
-                          cudaStream_t stream);
+int launch_dense_dgrad_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint8_t* dn2, int batch,
+                          cudaStream_t stream);       // dn2 in the G operand layout (common.cuh), borders untouched
 int launch_dense_wgrad_tc(const uint16_t* n2, const uint16_t* dd1, float* g_w1, int batch, cudaStream_t stream);
 // dgrad + wgrad tiles in one grid (both only need dd1): the single-GPU / fused-DP step uses this one
-int launch_dense_bwd_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint16_t* dn2, float* g_w1, int batch,
+int launch_dense_bwd_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint8_t* dn2, float* g_w1, int batch,
                         cudaStream_t stream);
 
 // heads.cu -- value / policy heads, softmax, A3C loss and its backward (NetworkVP_discrate.py:60-85)
@@ -70,9 +71,9 @@ struct DpBigArgs;                                // dp_exchange.cuh
 int conv_bwd_grid(int batch, int num_sms, int n_exch = 0);   // conv CTAs (= slabs written); n_exch SMs are left to the exchange CTAs
 // conv_bwd_fused.cu -- conv12 data gradient (dn1, kept on chip; dn1_out: optional copy for tests), conv12 and conv11
 // weight / bias gradients in one kernel on tcgen05
-int launch_conv_bwd(const void* x, bool x_u8, const uint16_t* n1, const uint16_t* dn2, const float* w12, uint16_t* dn1_out,
+int launch_conv_bwd(const uint8_t* xblk, const uint8_t* n1b2, const uint8_t* dn2g, const float* w12, uint16_t* dn1_out,
                     float* g_w11, float* g_b11, float* g_w12, float* g_b12, int64_t gp_stride, int batch, int num_sms,
-                    const DpBigArgs* dp, cudaStream_t stream);   // dp != null: append dp->n_exch exchange CTAs (dense1/w exchange)
+                    const DpBigArgs* dp, cudaStream_t stream);   // dp != null: data parallel (+ dp->n_exch exchange CTAs)
 
 // elementwise.cu
 // out[j] = sum over slabs i < count(j) of part[i * stride + j], j in [0, n_floats): the per-CTA gradient partials of

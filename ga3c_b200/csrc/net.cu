@@ -59,7 +59,10 @@ struct ga3c_net {
   int cur_exch = 0;                // ... of the step being enqueued (0 outside the overlapped data-parallel step)
   int64_t xbuf_off = 0, comm_off = 0;    // byte offsets in the slab: LL receive buffers [2][8][small prefix * 8 B], comm block
   // workspace
-  uint16_t *n1 = nullptr, *n2 = nullptr, *dd1 = nullptr, *dn2 = nullptr, *dn1 = nullptr;
+  uint16_t *n2 = nullptr, *dd1 = nullptr, *dn1 = nullptr;
+  // training-only activations, stored in the UMMA operand layouts the conv backward consumes (common.cuh); their zero borders /
+  // slack rows are never written, so they are cleared once, at allocation
+  uint8_t *n1 = nullptr, *dn2 = nullptr, *xblk = nullptr;
   float* d1 = nullptr;
   float* d1_part = nullptr;        // [splits][B,256] raw split-K partials of dense1 (dense_tc.cu)
   // gradient partials: one slab per CTA of the heads / conv backward kernels, laid out like the small-tensor prefix
@@ -201,16 +204,18 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
 }
 
 static void free_workspace(ga3c_net* n) {
-  cudaFree(n->n1); cudaFree(n->n2); cudaFree(n->d1); cudaFree(n->dd1); cudaFree(n->dn2); cudaFree(n->dn1);
+  cudaFree(n->n1); cudaFree(n->n2); cudaFree(n->d1); cudaFree(n->dd1); cudaFree(n->dn2); cudaFree(n->dn1); cudaFree(n->xblk);
   cudaFree(n->d1_part);
-  n->n1 = n->n2 = n->dd1 = n->dn2 = n->dn1 = nullptr; n->d1 = n->d1_part = nullptr;
+  n->n2 = n->dd1 = n->dn1 = nullptr; n->n1 = n->dn2 = n->xblk = nullptr; n->d1 = n->d1_part = nullptr;
 }
 
 static int alloc_workspace(ga3c_net* n, int max_batch) {
   const size_t mb = (size_t)max_batch;
-  CK(cudaMalloc((void**)&n->n1, mb * N1_POS * C1_OUT * 2)); CK(cudaMalloc((void**)&n->n2, mb * FLAT * 2));
+  CK(cudaMalloc((void**)&n->n1, mb * B2_BYTES)); CK(cudaMalloc((void**)&n->n2, mb * FLAT * 2));
   CK(cudaMalloc((void**)&n->d1, mb * FC * 4)); CK(cudaMalloc((void**)&n->dd1, mb * FC * 2));
-  CK(cudaMalloc((void**)&n->dn2, mb * FLAT * 2)); CK(cudaMalloc((void**)&n->dn1, mb * N1_POS * C1_OUT * 2));
+  CK(cudaMalloc((void**)&n->dn2, mb * G_BYTES)); CK(cudaMalloc((void**)&n->dn1, mb * N1_POS * C1_OUT * 2));
+  CK(cudaMalloc((void**)&n->xblk, mb * XB_FRAME_BYTES));
+  CK(cudaMemset(n->n1, 0, mb * B2_BYTES)); CK(cudaMemset(n->dn2, 0, mb * G_BYTES)); CK(cudaMemset(n->xblk, 0, mb * XB_FRAME_BYTES));
   // splits * batch <= max(batch, 64 * num_sms) rows for every batch (dense_fwd_splits)
   const size_t part_rows = mb > (size_t)64 * n->num_sms ? mb : (size_t)64 * n->num_sms;
   CK(cudaMalloc((void**)&n->d1_part, part_rows * FC * 4));
@@ -346,7 +351,7 @@ static int predict_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, fl
   cudaStream_t st = (cudaStream_t)stream;
   const float* w = n->w;
   LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, x_u8, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
-                                            w + n->off(P_C12B), nullptr, n->n2, batch, n->num_sms, st));
+                                            w + n->off(P_C12B), nullptr, nullptr, n->n2, batch, n->num_sms, st));
   const int splits = dense_fwd_splits(batch, n->num_sms);
   LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
   HeadsArgs h = heads_args(n, batch, splits);
@@ -378,7 +383,7 @@ static int fb_head_impl(ga3c_net* n, const void* x, bool x_u8, const float* yr, 
   const int splits = dense_fwd_splits(batch, n->num_sms);
   if (!skip_forward) {        // the second DUAL_RMSPROP pass reuses n1 / n2 / the dense1 partials of the first
     LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, x_u8, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
-                                              w + n->off(P_C12B), n->n1, n->n2, batch, n->num_sms, st));
+                                              w + n->off(P_C12B), n->n1, n->xblk, n->n2, batch, n->num_sms, st));
     LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
   }
   HeadsArgs h = heads_args(n, batch, splits);
@@ -425,7 +430,7 @@ static int fb_tail_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, vo
     LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_bwd_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, (g_dst ? g_dst : n->g) + n->off(P_D1W), batch, st));
   else
     LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
-  LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(x, x_u8, n->n1, n->dn2, w + n->off(P_C12W), n->keep_dn1 ? n->dn1 : nullptr,
+  LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(n->xblk, n->n1, n->dn2, w + n->off(P_C12W), n->keep_dn1 ? n->dn1 : nullptr,
                                               gp + n->off(P_C11W), gp + n->off(P_C11B), gp + n->off(P_C12W),
                                               gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, dp, st));
   if (reduce) LAUNCH(n, K_GRAD_REDUCE, st, launch_grad_reduce(reduce_args(n, batch, g_dst), st));
@@ -689,7 +694,7 @@ static int train_step_empty(ga3c_net* n, float lr, float* loss, void* stream) {
     const DpBigArgs b = dp_big_args(n, lr, n->dp_exch);
     n->cur_exch = b.n_exch;
     float* gp = n->gpart;
-    LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(nullptr, false, n->n1, n->dn2, n->w + n->off(P_C12W), nullptr,
+    LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(n->xblk, n->n1, n->dn2, n->w + n->off(P_C12W), nullptr,
                                                 gp + n->off(P_C11W), gp + n->off(P_C11B), gp + n->off(P_C12W),
                                                 gp + n->off(P_C12B), n->gp_stride, 0, n->num_sms, &b, st));
     const RmsPropDpArgs d = dp_small_args(n, lr, 0, b);
@@ -783,13 +788,14 @@ extern "C" int ga3c_workspace_ptr(ga3c_net* n, int which, void** ptr, int64_t* b
   if (!n || !ptr) return fail_msg("ga3c_workspace_ptr: null argument");
   const int64_t b = n->last_batch;
   switch (which) {
-    case 0: *ptr = n->n1; if (bytes) *bytes = b * N1_POS * C1_OUT * 2; break;
+    case 0: *ptr = n->n1; if (bytes) *bytes = b * B2_BYTES; break;
     case 1: *ptr = n->n2; if (bytes) *bytes = b * FLAT * 2; break;
     case 2: *ptr = n->d1; if (bytes) *bytes = b * FC * 4; break;
     case 3: *ptr = n->dd1; if (bytes) *bytes = b * FC * 2; break;
-    case 4: *ptr = n->dn2; if (bytes) *bytes = b * FLAT * 2; break;
+    case 4: *ptr = n->dn2; if (bytes) *bytes = b * G_BYTES; break;
     case 5: *ptr = n->dn1; if (bytes) *bytes = b * N1_POS * C1_OUT * 2; break;
     case 6: *ptr = n->w1_shadow; if (bytes) *bytes = (int64_t)FLAT * FC * 2; break;
+    case 7: *ptr = n->xblk; if (bytes) *bytes = b * XB_FRAME_BYTES; break;
     default: return fail_msg("ga3c_workspace_ptr: bad id");
   }
   return 0;

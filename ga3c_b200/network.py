@@ -553,7 +553,10 @@ class Network:
         _capi.check(self._lib.ga3c_keep_dn1(self._h, int(bool(on))), "ga3c_keep_dn1")
 
     def workspace(self, which: int) -> np.ndarray:
-        """Activation workspace of the last call as float32 numpy (bf16 buffers are widened)."""
+        """Activation workspace of the last call as float32 numpy (bf16 buffers are widened), flat in the LOGICAL order of the
+        reference tensors: n1 (0) and dn2 (4) live in HBM in the tcgen05 operand layouts the conv backward consumes
+        (include/ga3c_b200.h, ga3c_workspace_ptr) and are unscrambled here to [B, 21*21*16] / [B, 11*11*32]; 7 = the bf16 copy of
+        the frames, unscrambled to the padded image [B, 88, 88, 4]."""
         ptr, nbytes = C.c_void_p(), C.c_int64()
         _capi.check(self._lib.ga3c_workspace_ptr(self._h, which, C.byref(ptr), C.byref(nbytes)), "ga3c_workspace_ptr")
         torch.cuda.synchronize(self._tdev)
@@ -563,4 +566,21 @@ class Network:
         iface = {"shape": (nbytes.value // 2,), "typestr": "<i2", "data": (ptr.value, False), "version": 2}
         holder = type("H", (), {"__cuda_array_interface__": iface})()
         t = torch.as_tensor(holder, device=self._tdev).view(torch.bfloat16)
-        return t.float().cpu().numpy().copy()
+        flat = t.float().cpu().numpy().copy()
+        if which == 0:            # Blk2: [B][plane = ((Y&1)*2 + (X&1))*2 + h][row = (Y>>1)*13 + (X>>1)][8], Y = y + 1, X = x + 1
+            raw = flat.reshape(-1, 8, 160, 8)
+            y, x, h = np.meshgrid(np.arange(21), np.arange(21), np.arange(2), indexing="ij")
+            plane = (((y + 1) & 1) * 2 + ((x + 1) & 1)) * 2 + h
+            row = ((y + 1) >> 1) * 13 + ((x + 1) >> 1)
+            return raw[:, plane, row, :].reshape(raw.shape[0], -1).ravel()         # [B, y, x, h, 8] = [B, 441 * 16]
+        if which == 4:            # G: [B][plane j][row = (oy+1)*13 + ox+1][8]
+            raw = flat.reshape(-1, 4, 176, 8)
+            oy, ox, j = np.meshgrid(np.arange(11), np.arange(11), np.arange(4), indexing="ij")
+            return raw[:, j, (oy + 1) * 13 + ox + 1, :].reshape(raw.shape[0], -1).ravel()   # [B, oy, ox, j, 8] = [B, 3872]
+        if which == 7:            # xblk: [B][quarter][plane = dy*2 + (dx>>1)][128 rows][(dx&1, c)], block row = Y*22 + X
+            raw = flat.reshape(-1, 4, 8, 128, 8)
+            py, px, c = np.meshgrid(np.arange(88), np.arange(88), np.arange(4), indexing="ij")
+            r = (py >> 2) * 22 + (px >> 2)
+            plane = (py & 3) * 2 + ((px & 3) >> 1)
+            return raw[:, r >> 7, plane, r & 127, (px & 1) * 4 + c].reshape(raw.shape[0], -1).ravel()
+        return flat

@@ -56,7 +56,7 @@ def layer_report(net, params, x, y_r, a, *, beta=0.01, log_eps=1e-6, min_policy=
     n1_mask = (net.workspace(0).reshape(b, -1) > 0)
     n2_mask = (net.workspace(1).reshape(b, -1) > 0)
     dn2_cuda = net.workspace(4).astype(np.float64).reshape(b * onp.H2 * onp.H2, onp.C2_OUT)
-    dd1_cuda = net.workspace(3).astype(np.float64)
+    dd1_cuda = net.workspace(3).astype(np.float64).reshape(b, -1)
     dn2_local = onp.bf16_round((dd1_cuda @ f["w1"].T) * n2_mask)
     dn1_local = onp._col2im(dn2_cuda @ w12q.T, b, onp.H1, onp.C2_K, onp.C2_S, onp.P2_LO, onp.P2_HI, onp.H2, onp.C1_OUT)
     dn1_local = onp.bf16_round(dn1_local.reshape(b, -1) * n1_mask)
