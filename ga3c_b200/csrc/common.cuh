@@ -29,10 +29,10 @@ constexpr int N1P_W = 24, N1P_BYTES = N1P_W * N1P_W * 32;                       
 //   n1    Blk2: n1 SAME-padded (1 before, 2 after) to 24x24 and cut into 12x12 blocks of 2x2 pixels, row Yb*13 + Xb (column 12
 //         dead), 64 elements (dy, dx, ci) in 8 chunk planes of 160 rows; [frame][plane][160 rows][16 B], borders stay zero
 //   dn2   G: dn2 on a zero-bordered 13x13 grid, row (oy+1)*13 + (ox+1), 32 co in 4 chunk planes of 176 rows;
-//         [frame][plane][176 rows][16 B], borders stay zero
+//         [frame][plane][172 rows][16 B], borders stay zero
 constexpr int XB_QROWS = 128, XB_QUARTERS = 4, XB_PLANE_BYTES = XB_QROWS * 16, XB_QBYTES = 8 * XB_PLANE_BYTES,
               XB_FRAME_BYTES = XB_QUARTERS * XB_QBYTES, XB_LIVE_ROWS = 484;                                        // 65,536 B / frame
-constexpr int G_W = 13, G_ROWS = 176, G_LBO = G_ROWS * 16, G_BYTES = 4 * G_LBO;                                 // 11,264 B / frame
+constexpr int G_W = 13, G_ROWS = 172, G_LBO = G_ROWS * 16, G_BYTES = 4 * G_LBO;                                 // 11,008 B / frame
 constexpr int B2_ROWS = 160, B2_LBO = B2_ROWS * 16, B2_BYTES = 8 * B2_LBO;                                      // 20,480 B / frame
 // byte offset of channels [8h, 8h+8) of conv11 output pixel (y, x) inside a frame's Blk2 image
 __host__ __device__ constexpr int b2_pixel_offset(int y, int x, int h) {

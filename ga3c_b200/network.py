@@ -574,7 +574,7 @@ class Network:
             row = ((y + 1) >> 1) * 13 + ((x + 1) >> 1)
             return raw[:, plane, row, :].reshape(raw.shape[0], -1).ravel()         # [B, y, x, h, 8] = [B, 441 * 16]
         if which == 4:            # G: [B][plane j][row = (oy+1)*13 + ox+1][8]
-            raw = flat.reshape(-1, 4, 176, 8)
+            raw = flat.reshape(-1, 4, 172, 8)
             oy, ox, j = np.meshgrid(np.arange(11), np.arange(11), np.arange(4), indexing="ij")
             return raw[:, j, (oy + 1) * 13 + ox + 1, :].reshape(raw.shape[0], -1).ravel()   # [B, oy, ox, j, 8] = [B, 3872]
         if which == 7:            # xblk: [B][quarter][plane = dy*2 + (dx>>1)][128 rows][(dx&1, c)], block row = Y*22 + X

@@ -234,7 +234,7 @@ int ga3c_mlp_timing_collect(ga3c_mlp* net, double* total_ms, int64_t* counts, in
 /* device pointers to the activation workspace of the last call (bf16 stored as uint16):
  * which: 0 n1 bf16 in the Blk2 operand layout [B][8 planes][160 rows][8] (channels 8h.. of pixel (y, x) in plane
  *          (((y+1)&1)*2 + ((x+1)&1))*2 + h, row ((y+1)>>1)*13 + ((x+1)>>1); zero borders), 1 n2 [B,3872] bf16, 2 d1 [B,256] fp32,
- *        3 dd1 [B,256] bf16, 4 dn2 bf16 in the G operand layout [B][4 planes][176 rows][8] (channels 8j.. of position (oy, ox) in
+ *        3 dd1 [B,256] bf16, 4 dn2 bf16 in the G operand layout [B][4 planes][172 rows][8] (channels 8j.. of position (oy, ox) in
  *          plane j, row (oy+1)*13 + ox+1; zero borders), 5 dn1 [B,441,16] bf16 (only with ga3c_keep_dn1), 7 xblk: the bf16
  *          block matrix of the frames [B][4 quarters][8 planes][128 rows][8] that the conv backward reads instead of x, 6 the bf16 shadow of dense1/w [3872,256] (what the dense1 GEMMs read; in a
  *        data-parallel job the copy every rank holds, so comparing it across ranks checks the exchange) */

@@ -309,9 +309,9 @@ def test_dual_rmsprop_with_grad_clip(ga3c):
         assert np.abs(w[k] - ref[k]).max() <= 2 * TOL_W_ABS, (k, np.abs(w[k] - ref[k]).max())
     ms_p, _ = net.get_slots(0)
     ms_v, _ = net.get_slots(1)
-    for k in w:
-        assert err(ms_p[k] - 0.99 ** 2, sp[0][k] - 0.99 ** 2)[1] <= 2 * TOL_GRAD_REL or np.array_equal(ms_p[k], np.ones_like(ms_p[k])), k
-        assert err(ms_v[k] - 0.99 ** 2, sv[0][k] - 0.99 ** 2)[1] <= 2 * TOL_GRAD_REL or np.array_equal(ms_v[k], np.ones_like(ms_v[k])), k
+    for k in w:                                # ms = 0.99^2 + O(g_clipped^2): compared absolutely (fp32 slots)
+        assert np.abs(ms_p[k] - sp[0][k]).max() <= 1e-6 and np.abs(ms_v[k] - sv[0][k]).max() <= 1e-6, k
+    assert np.array_equal(ms_p["logits_v/w:0"], np.ones_like(ms_p["logits_v/w:0"]))      # never touched by the cost_p optimizer
     assert net.get_global_step() == 0
 
 

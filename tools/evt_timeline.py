@@ -6,12 +6,11 @@ import torch
 import ga3c_b200
 from ga3c_b200 import _capi
 
-NAMES = {1: "aux: next chunk", 2: "aux: WAR wait done", 3: "aux: chunk landed", 4: "aux: converted+armed", 5: "aux: loaded+rearmed", 6: "aux: fenced",
-         10: "iss: conv12 begin", 11: "iss: C12RDY passed", 12: "iss: conv12 issued", 13: "iss: frame begin", 14: "iss: DN1RDY passed",
-         15: "iss: BLKRDY passed", 16: "iss: group issued", 17: "iss: A2RDY passed", 18: "iss: conv12 issued", 43: "epi: MMA2 passed",
-         44: "epi: frame begin", 20: "tma: raw issue", 30: "re: RAWFULL passed", 31: "re: EPI12 passed",
-         32: "re: done", 40: "epi: MMA12 passed", 41: "epi: DN1FREE passed", 42: "epi: done", 50: "prologue: at griddep_wait",
-         51: "prologue: done", 52: "role done"}
+NAMES = {1: "ld: next quarter", 2: "ld: slot free", 20: "c12ld: next frame", 21: "c12ld: EPI12 passed",
+         10: "iss: conv12 begin", 11: "iss: C12RDY passed", 12: "iss: conv12 issued", 13: "iss: conv11 begin", 14: "iss: DN1RDY passed",
+         15: "iss: QFULL passed", 16: "iss: quarter issued", 17: "iss: A2RDY passed", 18: "iss: conv12 issued", 43: "epi: D drained",
+         44: "epi: frame begin", 30: "b12: C12RDY passed", 40: "epi: MMA12 passed", 41: "epi: DN1FREE passed", 42: "epi: dn1 written",
+         50: "prologue: at griddep_wait", 53: "prologue: dependency met", 51: "prologue: done", 52: "role done", 54: "epi: DONE passed"}
 tb = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 net = ga3c_b200.Network("gpu:0", "evt", 6, max_batch=tb, seed=1)
 dev = torch.device("cuda:0")
