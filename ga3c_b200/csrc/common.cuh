@@ -130,6 +130,40 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// ---- L2 residency hints --------------------------------------------------------------------------------------------------
+// The step's transient activations (xblk, n1, n2, dn2: ~100 MB at B = 1024) are written by one kernel and read once or twice by
+// a later one; the fp32 frames (115 MB) are streamed exactly once.  Frames are loaded evict_first and the transients stored
+// evict_last, so that the 126 MB L2 keeps what will be read again instead of what will not; the consumers load with evict_first
+// (after that read the data is dead).  The policy is a runtime operand: hints = 0 (GA3C_L2_HINTS=0) passes evict_normal everywhere.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_load_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_hint(void* dst, uint32_t src, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n" ::"l"(dst), "r"(src), "r"(bytes),
+               "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void stg128_hint(void* dst, uint4 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;\n" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
+               : "memory");
+}
 // 1-D bulk copy shared -> global through the TMA engine (bulk async-group completion)
 __device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(src), "r"(bytes) : "memory");

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1)
 conv_bwd_kernel(const uint8_t* __restrict__ xblk, const uint8_t* __restrict__ n1b2, const uint8_t* __restrict__ dn2g,
                 const float* __restrict__ w12, uint16_t* __restrict__ dn1_out, float* __restrict__ g_w11,
                 float* __restrict__ g_b11, float* __restrict__ g_w12, float* __restrict__ g_b12, int64_t gp_stride, int batch,
-                int n_conv, const DpBigArgs dp) {
+                int n_conv, int hints, const DpBigArgs dp) {
   // data parallel, overlapped exchange: CTAs [n_conv, gridDim.x) are exchange CTAs -- they move dense1/w (final since
   // dense_bwd, the launch this one depends on) between the ranks while CTAs [0, n_conv) compute the conv gradients
   if (DP && (int)blockIdx.x >= n_conv) {
@@ -114,6 +114,7 @@ conv_bwd_kernel(const uint8_t* __restrict__ xblk, const uint8_t* __restrict__ n1
   const int n_frames = ((int)blockIdx.x < batch) ? (batch - 1 - (int)blockIdx.x) / stride + 1 : 0;
   auto frame_of = [&](int k) { return (size_t)(blockIdx.x + k * stride); };
   auto bar = [&](int i) { return bars + i * 8; };
+  const uint64_t pol_last_use = (hints & 4) ? l2_policy_evict_first() : l2_policy_normal();    // every input is dead once it has been read
 
   // ---------------- prologue: everything that does not depend on the preceding kernels ----------------
   if (tid == 0) {
@@ -269,7 +270,8 @@ conv_bwd_kernel(const uint8_t* __restrict__ xblk, const uint8_t* __restrict__ n1
       if (elect_one()) {
         const int k = qg >> 2, q = qg & 3;
         mbar_expect_tx(bar(FB_QFULL + slot), XB_QBYTES);
-        bulk_load(ring + slot * XB_QBYTES, xblk + frame_of(k) * XB_FRAME_BYTES + q * XB_QBYTES, XB_QBYTES, bar(FB_QFULL + slot));
+        bulk_load_hint(ring + slot * XB_QBYTES, xblk + frame_of(k) * XB_FRAME_BYTES + q * XB_QBYTES, XB_QBYTES, bar(FB_QFULL + slot),
+                       pol_last_use);
       }
       __syncwarp();
     }
@@ -284,8 +286,8 @@ conv_bwd_kernel(const uint8_t* __restrict__ xblk, const uint8_t* __restrict__ n1
         const uint32_t buf = c12 + p * C12_BYTES;
         mbar_expect_tx(bar(FB_C12RDY + p), 2 * G_BYTES - 16 + B2_BYTES);
         bulk_load(buf, dn2g + frame_of(k) * G_BYTES, G_BYTES, bar(FB_C12RDY + p));
-        bulk_load(buf + C12_G1 + 16, dn2g + frame_of(k) * G_BYTES, G_BYTES - 16, bar(FB_C12RDY + p));   // the same, one row down
-        bulk_load(buf + C12_B2, n1b2 + frame_of(k) * B2_BYTES, B2_BYTES, bar(FB_C12RDY + p));
+        bulk_load_hint(buf + C12_G1 + 16, dn2g + frame_of(k) * G_BYTES, G_BYTES - 16, bar(FB_C12RDY + p), pol_last_use);   // the same, one row down
+        bulk_load_hint(buf + C12_B2, n1b2 + frame_of(k) * B2_BYTES, B2_BYTES, bar(FB_C12RDY + p), pol_last_use);
       }
       __syncwarp();
     }
@@ -484,7 +486,7 @@ int configure_conv_bwd_fused() {
 }
 
 int launch_conv_bwd(const uint8_t* xblk, const uint8_t* n1b2, const uint8_t* dn2g, const float* w12, uint16_t* dn1_out,
-                    float* g_w11, float* g_b11, float* g_w12, float* g_b12, int64_t gp_stride, int batch, int num_sms,
+                    float* g_w11, float* g_b11, float* g_w12, float* g_b12, int64_t gp_stride, int batch, int num_sms, bool x_u8,
                     const DpBigArgs* dp, cudaStream_t stream) {
   DpBigArgs d{};
   if (dp != nullptr) d = *dp;
@@ -493,7 +495,7 @@ int launch_conv_bwd(const uint8_t* xblk, const uint8_t* n1b2, const uint8_t* dn2
   if (grid.x == 0) return 0;
   auto kernel = dp != nullptr ? conv_bwd_kernel<true, false> : (g_evt_attached ? conv_bwd_kernel<false, true> : conv_bwd_kernel<false, false>);
   return launch_pdl(kernel, grid, dim3(FB_THREADS), FB_SMEM, stream, xblk, n1b2, dn2g, w12, dn1_out, g_w11, g_b11, g_w12, g_b12,
-                    gp_stride, batch, n_conv, d);
+                    gp_stride, batch, n_conv, l2_hints(true, x_u8), d);
 }
 
 }  // namespace ga3c

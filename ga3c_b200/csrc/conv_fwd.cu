@@ -71,7 +71,7 @@ template <bool U8>       // U8: frames are uint8 [B,28224] (x = k/128 - 1 applie
 __global__ void __launch_bounds__(CF_THREADS, 1)
 conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const float* __restrict__ b11,
                 const float* __restrict__ w12, const float* __restrict__ b12,
-                uint8_t* __restrict__ n1_out, uint8_t* __restrict__ xblk_out, uint16_t* __restrict__ n2_out, int batch) {
+                uint8_t* __restrict__ n1_out, uint8_t* __restrict__ xblk_out, uint16_t* __restrict__ n2_out, int batch, int hints) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const smem = smem_raw + (sbase - smem_u32(smem_raw));
@@ -85,11 +85,15 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
   const int n_chunks = n_frames * PW_NCHUNK;                         // chunk stream of this CTA: q = k * 21 + c, warp q % 6
   auto frame_of = [&](int k) { return (size_t)(blockIdx.x + k * stride); };
   auto bar = [&](int i) { return bars + i * 8; };
+  // L2 residency (common.cuh): frames are streamed once, the activations written here are read back later in the step
+  const uint64_t pol_stream = (hints & 1) ? l2_policy_evict_first() : l2_policy_normal();
+  const uint64_t pol_keep = (hints & 2) ? l2_policy_evict_last() : l2_policy_normal();
   auto issue_chunk = [&](int q, int slot) {                          // one thread
     const int k = q / PW_NCHUNK, c = q - k * PW_NCHUNK;
     constexpr uint32_t bytes = U8 ? PW_BYTES_U8 : PW_BYTES;
     mbar_expect_tx(bar(BAR_RING + slot), bytes);
-    bulk_load(ring + slot * PW_BYTES, static_cast<const uint8_t*>(x) + (frame_of(k) * PW_NCHUNK + c) * bytes, bytes, bar(BAR_RING + slot));
+    bulk_load_hint(ring + slot * PW_BYTES, static_cast<const uint8_t*>(x) + (frame_of(k) * PW_NCHUNK + c) * bytes, bytes,
+                   bar(BAR_RING + slot), pol_stream);
   };
 
   // ---------------- prologue ----------------
@@ -243,7 +247,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
           mbar_wait(bar(BAR_BLKRDY + q), k & 1);
           if (lane < 8) {
             const uint32_t bytes = q < 3 ? XB_PLANE_BYTES : (XB_LIVE_ROWS - 3 * XB_QROWS) * 16;
-            bulk_store(dst + q * XB_QBYTES + lane * XB_PLANE_BYTES, blk + lane * BLK_LBO + q * XB_PLANE_BYTES, bytes);
+            bulk_store_hint(dst + q * XB_QBYTES + lane * XB_PLANE_BYTES, blk + lane * BLK_LBO + q * XB_PLANE_BYTES, bytes, pol_keep);
             bulk_commit();
             bulk_wait_read0();                                     // shared memory has been read: the rows may be overwritten
           }
@@ -280,7 +284,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
             o[jj] = pack_bf16(fmaxf(__uint_as_float(r[n]) + bias_s[C1_OUT + n], 0.f),
                               fmaxf(__uint_as_float(r[n + 1]) + bias_s[C1_OUT + n + 1], 0.f));
           }
-          dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+          stg128_hint(dst + i, make_uint4(o[0], o[1], o[2], o[3]), pol_keep);
         }
       }
     };
@@ -336,8 +340,8 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
           }
           if (n1_dst) {
             uint8_t* d = n1_dst + b2_pixel_offset(oy, ox, 0);
-            *reinterpret_cast<uint4*>(d) = lo;
-            *reinterpret_cast<uint4*>(d + B2_LBO) = hi;
+            stg128_hint(d, lo, pol_keep);
+            stg128_hint(d + B2_LBO, hi, pol_keep);
           }
         }
       }
@@ -370,11 +374,12 @@ int configure_conv_fwd() {
 int launch_conv_fwd(const void* x, bool x_u8, const float* w11, const float* b11, const float* w12, const float* b12,
                     uint8_t* n1_out, uint8_t* xblk_out, uint16_t* n2_out, int batch, int num_sms, cudaStream_t stream) {
   const int grid = min(batch, num_sms);
+  const int hints = l2_hints(n1_out != nullptr, x_u8);
   if (x_u8)
     return launch_pdl(conv_fwd_kernel<true>, dim3(grid), dim3(CF_THREADS), CF_SMEM, stream, x, w11, b11, w12, b12, n1_out, xblk_out,
-                      n2_out, batch);
+                      n2_out, batch, hints);
   return launch_pdl(conv_fwd_kernel<false>, dim3(grid), dim3(CF_THREADS), CF_SMEM, stream, x, w11, b11, w12, b12, n1_out, xblk_out,
-                    n2_out, batch);
+                    n2_out, batch, hints);
 }
 
 }  // namespace ga3c

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace ga3c {
 
@@ -16,6 +17,16 @@ int trace_attach_elementwise(unsigned long long* buf);
 int evt_attach_conv_fwd(unsigned long long* buf);
 int evt_attach_conv_bwd(unsigned long long* buf);
 int evt_attach_elementwise(unsigned long long* buf);
+
+// L2 residency hints on the conv kernels' loads and stores (common.cuh); GA3C_L2_HINTS=0 switches them off (evict_normal)
+// bit 0: frames loaded evict_first, bit 1: activations stored evict_last, bit 2: the conv backward loads evict_first.
+// Measured at B = 1024 / 4096 (profiles/r2g_l2_hint_sweep.txt): predict gains 3 % from bit 0; the fp32 train step is fastest
+// with none of them (the L2 already keeps what fits), the uint8 train step with all three (-2.5 %).  GA3C_L2_HINTS overrides.
+inline int l2_hints(bool train, bool x_u8) {
+  static const int env = [] { const char* e = getenv("GA3C_L2_HINTS"); return e ? atoi(e) : -1; }();
+  if (env >= 0) return env;
+  return train ? (x_u8 ? 7 : 0) : 1;
+}
 
 // one-time per-process function-attribute setup (dynamic smem opt-in); returns cudaError_t as int
 int configure_conv_fwd();
@@ -72,7 +83,7 @@ int conv_bwd_grid(int batch, int num_sms, int n_exch = 0);   // conv CTAs (= sla
 // conv_bwd_fused.cu -- conv12 data gradient (dn1, kept on chip; dn1_out: optional copy for tests), conv12 and conv11
 // weight / bias gradients in one kernel on tcgen05
 int launch_conv_bwd(const uint8_t* xblk, const uint8_t* n1b2, const uint8_t* dn2g, const float* w12, uint16_t* dn1_out,
-                    float* g_w11, float* g_b11, float* g_w12, float* g_b12, int64_t gp_stride, int batch, int num_sms,
+                    float* g_w11, float* g_b11, float* g_w12, float* g_b12, int64_t gp_stride, int batch, int num_sms, bool x_u8,
                     const DpBigArgs* dp, cudaStream_t stream);   // dp != null: data parallel (+ dp->n_exch exchange CTAs)
 
 // elementwise.cu

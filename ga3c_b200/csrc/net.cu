@@ -432,7 +432,7 @@ static int fb_tail_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, vo
     LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
   LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(n->xblk, n->n1, n->dn2, w + n->off(P_C12W), n->keep_dn1 ? n->dn1 : nullptr,
                                               gp + n->off(P_C11W), gp + n->off(P_C11B), gp + n->off(P_C12W),
-                                              gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, dp, st));
+                                              gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, x_u8, dp, st));
   if (reduce) LAUNCH(n, K_GRAD_REDUCE, st, launch_grad_reduce(reduce_args(n, batch, g_dst), st));
   return 0;
 }
@@ -696,7 +696,7 @@ static int train_step_empty(ga3c_net* n, float lr, float* loss, void* stream) {
     float* gp = n->gpart;
     LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(n->xblk, n->n1, n->dn2, n->w + n->off(P_C12W), nullptr,
                                                 gp + n->off(P_C11W), gp + n->off(P_C11B), gp + n->off(P_C12W),
-                                                gp + n->off(P_C12B), n->gp_stride, 0, n->num_sms, &b, st));
+                                                gp + n->off(P_C12B), n->gp_stride, 0, n->num_sms, false, &b, st));
     const RmsPropDpArgs d = dp_small_args(n, lr, 0, b);
     n->cur_exch = 0;
     LAUNCH(n, K_RMSPROP, st, launch_dp_small(d, n->xbuf_off, st));
