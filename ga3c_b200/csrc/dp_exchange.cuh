@@ -51,6 +51,14 @@ __device__ __forceinline__ void dp_wait_flag(const void* p, unsigned long long w
   for (unsigned int i = 0; dp_ld_flag(p) < want; ++i)
     if (i > DP_SPIN_LIMIT) { atomicOr(static_cast<unsigned int*>(err), bit); break; }
 }
+// the same wait, ending in an ACQUIRE load: what the waiter reads afterwards (the peer's gradients) is ordered behind the flag
+// without a fence.sys -- which would also wait for every remote store this thread block has in flight (~2.7 us measured)
+__device__ __forceinline__ void dp_wait_flag_acquire(const void* p, unsigned long long want, void* err, unsigned int bit) {
+  dp_wait_flag(p, want, err, bit);
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  (void)v;
+}
 // LL wire format: a float4 travels as two 16-byte stores {x, flag, y, flag} {z, flag, w, flag}
 __device__ __forceinline__ void dp_ll_store(void* dst, const float4& v, uint32_t flag) {
   asm volatile("st.relaxed.sys.global.v4.b32 [%0], {%1,%2,%3,%4};\n" ::"l"(dst), "r"(__float_as_uint(v.x)), "r"(flag),
@@ -138,7 +146,7 @@ __device__ __forceinline__ void dp_big_loop(const DpBigArgs& d, long long lo, lo
 
 // Body of an exchange CTA (512 threads).  Called after griddepcontrol.wait: dense_bwd of this rank is complete, i.e. its
 // dense1/w gradient is final and nothing on this rank reads dense1/w or its shadow again before the next forward.
-__device__ __forceinline__ void dp_big_exchange(const DpBigArgs& d, int cta, int n_cta) {
+__device__ __forceinline__ void dp_big_exchange(const DpBigArgs& d, int cta, int n_cta, EvtLog* evt = nullptr) {
   __shared__ int dp_last;
   const int tid = threadIdx.x;
   uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
@@ -148,6 +156,7 @@ __device__ __forceinline__ void dp_big_exchange(const DpBigArgs& d, int cta, int
     __threadfence_system();
   }
   __syncthreads();
+  if (evt) evt_mark(*evt, 70, 0);
 
   const long long n4 = d.w1_count >> 2;
   const long long per = (n4 + d.world - 1) / d.world;
@@ -157,6 +166,7 @@ __device__ __forceinline__ void dp_big_exchange(const DpBigArgs& d, int cta, int
   else if (d.world == 4) dp_big_loop<4, 2>(d, lo, hi, first, stride);
   else if (d.world == 8) dp_big_loop<8, 1>(d, lo, hi, first, stride);
   else dp_big_loop<0, 1>(d, lo, hi, first, stride);
+  if (evt) evt_mark(*evt, 71, 0);
   __syncthreads();
   if (tid == 0) {
     __threadfence_system();            // cumulative over the block's peer stores (observed through the barrier)
@@ -168,6 +178,7 @@ __device__ __forceinline__ void dp_big_exchange(const DpBigArgs& d, int cta, int
       for (int r = 0; r < d.world; ++r) dp_st_flag(d.peer[r] + d.comm_offset + DPC_BIGDONE + 64 * d.rank, d.step);
     }
   }
+  if (evt) evt_mark(*evt, 72, 0);
 }
 
 }  // namespace ga3c

@@ -8,6 +8,10 @@
 
 namespace ga3c {
 
+__device__ __forceinline__ void named_bar_sync_ew(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- gradient-partial reduction ---------------------------------------------------------------------
 // The heads / conv12_bwd / conv11_wgrad kernels leave one slab of partial sums per CTA (a mirror of the small-tensor
 // prefix of the gradient arena + the loss sums).  512 threads = 16 slab lanes x 32 float4 columns: lane l adds slabs
@@ -688,47 +692,127 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_small_kernel(RmsPropDpA
 // until every rank's dense1/w slice has landed.  Every rank's "dense_bwd done" flag was pushed by CTA 0 of its conv backward
 // launch, a whole conv backward ago, so nobody waits for a peer's gradient; the conv backward itself keeps all the SMs
 // (the overlapped variant gives up 20 of them and pays a whole extra round of frames at B = 1024).
-constexpr int DP_TAIL_MAX_SLOTS = 16;      // column blocks one block may serve (grids smaller than n_cb: tests that share a GPU)
+// Both instalments run CONCURRENTLY on different warps of every block (each is a chain of NVLink latencies, not bandwidth):
+//   threads   0-255  small tensors: slab sums of a 32-float4 column block (8 slab lanes), LL push to every peer, collect the
+//                    peers' sums, identical RMSProp update on every rank
+//   threads 256-511  dense1/w: wait (acquire) for every rank's "dense_bwd done" flag -- pushed a whole conv backward ago --, then
+//                    reduce-scatter with peer loads, RMSProp on the owned slice, all-gather of the bf16 shadow with peer stores
+// No fence sits between the two flag hops of the step: the only fence.sys is the one that orders a block's peer stores before
+// the rank's "slice landed" flag (measured at 2 ranks, profiles/r2i_dp_tail_timeline.txt: the first version of this kernel
+// spent 2.7 us in a fence after the flag wait and 3.1 us in the one before the counter, one after the other).
+constexpr int DPT_SMALL = 256, DPT_LANES = DPT_SMALL / GR_COLS;
 template <bool HAS_MOM>
-__global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_tail_kernel(RmsPropDpArgs d, DpBigArgs big, int64_t recv_offset, int n_cb) {
-  __shared__ float4 part[GR_LANES][GR_COLS];
-  __shared__ float4 acc_s[DP_TAIL_MAX_SLOTS][GR_COLS];
+__global__ void __launch_bounds__(512) dp_tail_kernel(RmsPropDpArgs d, DpBigArgs big, int64_t recv_offset, int n_cb) {
+  __shared__ float4 part[DPT_LANES][GR_COLS];
+  __shared__ int dp_last;
+  const RmsPropArgs& a = d.base;
+  const GradReduceArgs& r = d.red;
   EvtLog evt_i = evt_open();
-  DpSmallState st0;
-  st0.owner = false;
+  const int tid = threadIdx.x;
   uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
-  int slot = 0;
-  for (int cb = blockIdx.x; cb < n_cb; cb += gridDim.x, ++slot) {
-    DpSmallState st;
-    dp_small_phase1<HAS_MOM>(d, recv_offset, cb, slot == 0, K_RMSPROP, evt_i, st, part);
-    if (slot == 0) st0 = st;
-    else if (threadIdx.x < GR_COLS) acc_s[slot][threadIdx.x] = st.acc;
-    __syncthreads();                                     // `part` is reused by the next column block
-  }
-  if (slot == 0) {
-    griddep_launch();
-    griddep_wait(K_RMSPROP);
-  }
-  dp_big_exchange(big, (int)blockIdx.x, (int)gridDim.x);
-  evt_mark(evt_i, 67, 0);
-  slot = 0;
-  for (int cb = blockIdx.x; cb < n_cb; cb += gridDim.x, ++slot) {
-    if (slot == 0) {
-      dp_small_phase2<HAS_MOM>(d, recv_offset, evt_i, st0, false);
-    } else {
-      DpSmallState st;
-      const int col = threadIdx.x & (GR_COLS - 1);
-      st.j = (cb * GR_COLS + col) * 4;
-      st.owner = threadIdx.x < GR_COLS && st.j < d.red.out_floats;
-      st.acc = acc_s[slot][col];
-      dp_small_phase2<HAS_MOM>(d, recv_offset, evt_i, st, true);
+  griddep_launch();
+  evt_mark(evt_i, 60, 0);
+  griddep_wait(K_RMSPROP);            // the slabs come from the conv backward launch that precedes this one
+  evt_mark(evt_i, 61, 0);
+  if (tid >= DPT_SMALL) {
+    // ---------------- dense1/w ----------------
+    const int t = tid - DPT_SMALL;
+    if (blockIdx.x == 0 && t < big.world)      // (CTA 0 of the conv backward has published it already, unless this step had no rows)
+      dp_st_flag(big.peer[t] + big.comm_offset + DPC_BIGREADY + 64 * big.rank, big.step);
+    if (t < big.world) dp_wait_flag_acquire(my_comm + DPC_BIGREADY + 64 * t, big.step, my_comm + DPC_ERR, 4u);
+    named_bar_sync_ew(1, 512 - DPT_SMALL);
+    if (t == 0) evt_mark(evt_i, 70, 0);
+    const long long n4 = big.w1_count >> 2;
+    const long long per = (n4 + big.world - 1) / big.world;
+    const long long lo = per * big.rank, hi = lo + per < n4 ? lo + per : n4;
+    const long long stride = (long long)gridDim.x * (512 - DPT_SMALL), first = (long long)blockIdx.x * (512 - DPT_SMALL) + t;
+    if (big.world == 2) dp_big_loop<2, 4>(big, lo, hi, first, stride);
+    else if (big.world == 4) dp_big_loop<4, 2>(big, lo, hi, first, stride);
+    else if (big.world == 8) dp_big_loop<8, 1>(big, lo, hi, first, stride);
+    else dp_big_loop<0, 1>(big, lo, hi, first, stride);
+    if (t == 0) evt_mark(evt_i, 71, 0);
+    named_bar_sync_ew(1, 512 - DPT_SMALL);
+    if (t == 0) {
+      __threadfence_system();            // cumulative over the big-role threads' peer stores (observed through the barrier)
+      unsigned int* ctr = reinterpret_cast<unsigned int*>(my_comm + DPC_CTR_BIG);
+      dp_last = atomicAdd(ctr, 1u) == gridDim.x - 1;
+      if (dp_last) {
+        *ctr = 0;
+        __threadfence_system();
+        for (int q = 0; q < big.world; ++q) dp_st_flag(big.peer[q] + big.comm_offset + DPC_BIGDONE + 64 * big.rank, big.step);
+      }
+      evt_mark(evt_i, 72, 0);
+    }
+  } else {
+    // ---------------- small tensors ----------------
+    const int col = tid & (GR_COLS - 1), sl = tid / GR_COLS;
+    const uint32_t flag = (uint32_t)d.step;
+    for (int cb = blockIdx.x; cb < n_cb; cb += gridDim.x) {
+      const int j = (cb * GR_COLS + col) * 4;
+      const bool owner = sl == 0 && j < r.out_floats;
+      int count = 0;
+      if (j < r.n_floats) {
+#pragma unroll
+        for (int s = GR_MAX_SEG - 1; s >= 0; --s)
+          if (j < r.seg_end[s]) count = r.seg_count[s];
+      }
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* src = r.part + j;
+      for (int i0 = sl; i0 < count; i0 += GR_UNROLL * DPT_LANES) {
+        float4 q[GR_UNROLL];
+#pragma unroll
+        for (int u = 0; u < GR_UNROLL; ++u) {
+          const int i = i0 + u * DPT_LANES;
+          q[u] = i < count ? __ldcg(reinterpret_cast<const float4*>(src + (int64_t)i * r.stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < GR_UNROLL; ++u) { acc.x += q[u].x; acc.y += q[u].y; acc.z += q[u].z; acc.w += q[u].w; }
+      }
+      part[sl][col] = acc;
+      named_bar_sync_ew(2, DPT_SMALL);
+      if (sl == 0 && j < r.n_floats) {
+#pragma unroll
+        for (int l = 1; l < DPT_LANES; ++l) {
+          const float4 q = part[l][col];
+          acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+        }
+        if (j >= r.out_floats && r.out_tail != nullptr) {
+          float* tl = r.out_tail + (j - r.out_floats);
+          tl[0] = acc.x; tl[1] = acc.y; tl[2] = acc.z; tl[3] = acc.w;
+        }
+      }
+      if (tid == 0) evt_mark(evt_i, 62, cb);
+      if (owner) {
+        // receive buffers: [parity][source rank][small prefix in LL format: 8 bytes per float]
+        const int64_t slot = recv_offset + ((int64_t)(d.step & 1) * DP_WORLD_MAX + d.rank) * r.out_floats * 8 + (int64_t)j * 8;
+#pragma unroll
+        for (int q = 0; q < DP_WORLD_MAX; ++q)
+          if (q < d.world && q != d.rank) dp_ll_store(d.peer[q] + slot, acc, flag);
+        *reinterpret_cast<float4*>(r.out + j) = acc;                     // this rank's own gradient (introspection)
+        float4 w = *reinterpret_cast<const float4*>(a.w + j);
+        float4 ms = *reinterpret_cast<const float4*>(a.ms + j);
+        float4 mo = HAS_MOM ? *reinterpret_cast<const float4*>(a.mom + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < DP_WORLD_MAX; ++q)
+          if (q < d.world) {
+            const float4 v = q == d.rank ? acc
+                                         : dp_ll_load(d.peer[d.rank] + recv_offset +
+                                                          ((int64_t)(d.step & 1) * DP_WORLD_MAX + q) * r.out_floats * 8 + (int64_t)j * 8,
+                                                      flag, my_comm + DPC_ERR);
+            g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+          }
+        rms_update<HAS_MOM>(a, g, w, ms, mo);
+        *reinterpret_cast<float4*>(a.w + j) = w;
+        *reinterpret_cast<float4*>(a.ms + j) = ms;
+        if (HAS_MOM) *reinterpret_cast<float4*>(a.mom + j) = mo;
+      }
+      if (tid == 0) evt_mark(evt_i, 64, cb);
+      named_bar_sync_ew(2, DPT_SMALL);                                   // `part` is reused by the next column block
     }
   }
-  evt_mark(evt_i, 64, 0);
-  if (blockIdx.x == 0 && (int)threadIdx.x < d.world) {
-    dp_wait_flag(my_comm + DPC_BIGDONE + 64 * threadIdx.x, d.step, my_comm + DPC_ERR, 16u);
-    __threadfence_system();
-  }
+  __syncthreads();
+  if (blockIdx.x == 0 && tid < d.world) dp_wait_flag_acquire(my_comm + DPC_BIGDONE + 64 * tid, d.step, my_comm + DPC_ERR, 16u);
   evt_mark(evt_i, 65, 0);
   trace_mark(K_RMSPROP, 2);
 }
@@ -762,7 +846,7 @@ int launch_dp_tail(const RmsPropDpArgs& d, const DpBigArgs& big, int64_t recv_of
   int grid = n_cb > num_sms ? n_cb : num_sms;
   if (const char* e = getenv("GA3C_DP_TAIL_CTAS")) {     // tests with several ranks on one GPU leave SMs to the other ranks' kernels
     const int g = atoi(e);
-    if (g >= (n_cb + DP_TAIL_MAX_SLOTS - 1) / DP_TAIL_MAX_SLOTS && g <= grid) grid = g;
+    if (g >= 1 && g <= grid) grid = g;
   }
   if (d.base.momentum != 0.f)
     return launch_pdl(dp_tail_kernel<true>, dim3(grid), dim3(GR_LANES * GR_COLS), 0, stream, d, big, recv_offset, n_cb);
