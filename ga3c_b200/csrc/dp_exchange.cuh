@@ -144,6 +144,40 @@ __device__ __forceinline__ void dp_big_loop(const DpBigArgs& d, long long lo, lo
   }
 }
 
+// The same exchange on a GROUP of `nthreads` threads of a block (thread t of the group, named barrier `bar_id`): the spare warps
+// of every conv backward CTA (conv_bwd_fused.cu) or half of every block of the tail kernel (dp_tail_kernel).  `cta` / `n_cta`:
+// index and number of the groups that share the work; last_smem: one int of shared memory.  Ends with the rank's "slice landed
+// everywhere" flag pushed by the last group to finish.  Waits with acquire loads, no fence between the two flag hops.
+__device__ __forceinline__ void dp_big_group(const DpBigArgs& d, int t, int nthreads, int cta, int n_cta, int bar_id, int* last_smem,
+                                             bool push_ready) {
+  uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
+  if (push_ready && cta == 0 && t < d.world) {
+    __threadfence_system();
+    dp_st_flag(d.peer[t] + d.comm_offset + DPC_BIGREADY + 64 * d.rank, d.step);
+  }
+  if (t < d.world) dp_wait_flag_acquire(my_comm + DPC_BIGREADY + 64 * t, d.step, my_comm + DPC_ERR, 4u);
+  asm volatile("bar.sync %0, %1;\n" ::"r"(bar_id), "r"(nthreads) : "memory");
+  const long long n4 = d.w1_count >> 2;
+  const long long per = (n4 + d.world - 1) / d.world;
+  const long long lo = per * d.rank, hi = lo + per < n4 ? lo + per : n4;
+  const long long stride = (long long)n_cta * nthreads, first = (long long)cta * nthreads + t;
+  if (d.world == 2) dp_big_loop<2, 4>(d, lo, hi, first, stride);
+  else if (d.world == 4) dp_big_loop<4, 2>(d, lo, hi, first, stride);
+  else if (d.world == 8) dp_big_loop<8, 1>(d, lo, hi, first, stride);
+  else dp_big_loop<0, 1>(d, lo, hi, first, stride);
+  asm volatile("bar.sync %0, %1;\n" ::"r"(bar_id), "r"(nthreads) : "memory");
+  if (t == 0) {
+    __threadfence_system();            // cumulative over the group's peer stores (observed through the barrier)
+    unsigned int* ctr = reinterpret_cast<unsigned int*>(my_comm + DPC_CTR_BIG);
+    *last_smem = atomicAdd(ctr, 1u) == (unsigned int)n_cta - 1;
+    if (*last_smem) {
+      *ctr = 0;
+      __threadfence_system();
+      for (int r = 0; r < d.world; ++r) dp_st_flag(d.peer[r] + d.comm_offset + DPC_BIGDONE + 64 * d.rank, d.step);
+    }
+  }
+}
+
 // Body of an exchange CTA (512 threads).  Called after griddepcontrol.wait: dense_bwd of this rank is complete, i.e. its
 // dense1/w gradient is final and nothing on this rank reads dense1/w or its shadow again before the next forward.
 __device__ __forceinline__ void dp_big_exchange(const DpBigArgs& d, int cta, int n_cta, EvtLog* evt = nullptr) {

@@ -717,32 +717,9 @@ __global__ void __launch_bounds__(512) dp_tail_kernel(RmsPropDpArgs d, DpBigArgs
   if (tid >= DPT_SMALL) {
     // ---------------- dense1/w ----------------
     const int t = tid - DPT_SMALL;
-    if (blockIdx.x == 0 && t < big.world)      // (CTA 0 of the conv backward has published it already, unless this step had no rows)
-      dp_st_flag(big.peer[t] + big.comm_offset + DPC_BIGREADY + 64 * big.rank, big.step);
-    if (t < big.world) dp_wait_flag_acquire(my_comm + DPC_BIGREADY + 64 * t, big.step, my_comm + DPC_ERR, 4u);
-    named_bar_sync_ew(1, 512 - DPT_SMALL);
-    if (t == 0) evt_mark(evt_i, 70, 0);
-    const long long n4 = big.w1_count >> 2;
-    const long long per = (n4 + big.world - 1) / big.world;
-    const long long lo = per * big.rank, hi = lo + per < n4 ? lo + per : n4;
-    const long long stride = (long long)gridDim.x * (512 - DPT_SMALL), first = (long long)blockIdx.x * (512 - DPT_SMALL) + t;
-    if (big.world == 2) dp_big_loop<2, 4>(big, lo, hi, first, stride);
-    else if (big.world == 4) dp_big_loop<4, 2>(big, lo, hi, first, stride);
-    else if (big.world == 8) dp_big_loop<8, 1>(big, lo, hi, first, stride);
-    else dp_big_loop<0, 1>(big, lo, hi, first, stride);
-    if (t == 0) evt_mark(evt_i, 71, 0);
-    named_bar_sync_ew(1, 512 - DPT_SMALL);
-    if (t == 0) {
-      __threadfence_system();            // cumulative over the big-role threads' peer stores (observed through the barrier)
-      unsigned int* ctr = reinterpret_cast<unsigned int*>(my_comm + DPC_CTR_BIG);
-      dp_last = atomicAdd(ctr, 1u) == gridDim.x - 1;
-      if (dp_last) {
-        *ctr = 0;
-        __threadfence_system();
-        for (int q = 0; q < big.world; ++q) dp_st_flag(big.peer[q] + big.comm_offset + DPC_BIGDONE + 64 * big.rank, big.step);
-      }
-      evt_mark(evt_i, 72, 0);
-    }
+    // (CTA 0 of the conv backward has published "dense_bwd done" already, unless this step had no rows: publish again)
+    dp_big_group(big, t, 512 - DPT_SMALL, (int)blockIdx.x, (int)gridDim.x, 1, &dp_last, true);
+    if (t == 0) evt_mark(evt_i, 72, 0);
   } else {
     // ---------------- small tensors ----------------
     const int col = tid & (GR_COLS - 1), sl = tid / GR_COLS;

@@ -82,9 +82,20 @@ struct DpBigArgs;                                // dp_exchange.cuh
 int conv_bwd_grid(int batch, int num_sms, int n_exch = 0);   // conv CTAs (= slabs written); n_exch SMs are left to the exchange CTAs
 // conv_bwd_fused.cu -- conv12 data gradient (dn1, kept on chip; dn1_out: optional copy for tests), conv12 and conv11
 // weight / bias gradients in one kernel on tcgen05
+// what warps 12-15 of every conv backward CTA do with dense1/w, whose gradient is final when that kernel starts:
+//   mode 0 nothing; mode 1 RMSProp + bf16 shadow refresh over the whole tensor (single GPU; the pointers are the dense1/w ranges
+//   of the arenas, n4 its size in float4); mode 2 the data-parallel exchange described by the DpBigArgs of the launch
+struct ConvBwdOpt {
+  int mode;
+  const float* g;
+  float *w, *ms, *mom;
+  uint16_t* shadow;
+  long long n4;
+  float lr, decay, momentum, eps;
+};
 int launch_conv_bwd(const uint8_t* xblk, const uint8_t* n1b2, const uint8_t* dn2g, const float* w12, uint16_t* dn1_out,
                     float* g_w11, float* g_b11, float* g_w12, float* g_b12, int64_t gp_stride, int batch, int num_sms, bool x_u8,
-                    const DpBigArgs* dp, cudaStream_t stream);   // dp != null: data parallel (+ dp->n_exch exchange CTAs)
+                    const ConvBwdOpt& opt, const DpBigArgs* dp, cudaStream_t stream);   // dp != null: data parallel (+ dp->n_exch exchange CTAs)
 
 // elementwise.cu
 // out[j] = sum over slabs i < count(j) of part[i * stride + j], j in [0, n_floats): the per-CTA gradient partials of

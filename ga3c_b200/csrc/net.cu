@@ -53,9 +53,14 @@ struct ga3c_net {
   bool dp_ipc[DP_MAX_WORLD] = {};        // mapped with cudaIpcOpenMemHandle (to be closed on detach)
   uint64_t dp_step = 0;
   int dp_exch = 20;                // overlapped exchange: exchange CTAs appended to the conv backward launch (GA3C_DP_EXCH_CTAS)
-  int dp_exchange = 0;             // GA3C_DP_EXCHANGE: 0 "tail" (one launch on every SM at the end of the step, default),
-                                   // 1 "overlap" (exchange CTAs inside the conv backward launch + dp_small), 2 "single"
-                                   // (the first version: one kernel that also broadcasts the fp32 weights)
+  int dp_exchange = 0;             // GA3C_DP_EXCHANGE: 0 "tail" (default: one launch on every SM at the end of the step), 3 "warps" (the
+                                   // dense1/w exchange on the optimizer warps of every conv backward CTA, small tensors + completion
+                                   // in dp_small), 1 "overlap" (exchange CTAs inside the conv backward launch + dp_small), 2
+                                   // "single" (the first version: one kernel that also broadcasts the fp32 weights).  Measured at 2
+                                   // GPUs, B = 1024 per GPU (profiles/r2l_*): tail 0.1196 ms, warps 0.1205, overlap 0.1403
+  int fuse_opt = 0;                // GA3C_FUSE_OPT=1: single GPU, dense1/w updated by the optimizer warps of the conv backward CTAs
+                                   // instead of the launch at the end.  Measured: conv_bwd 26.3 -> 30.6 us, rmsprop 8.9 -> 5.0 us,
+                                   // step 0.1015 -> 0.1032 ms: the conv backward is HBM-bound, the 22 MB cost what they cost alone
   int cur_exch = 0;                // ... of the step being enqueued (0 outside the overlapped data-parallel step)
   int64_t xbuf_off = 0, comm_off = 0;    // byte offsets in the slab: LL receive buffers [2][8][small prefix * 8 B], comm block
   // workspace
@@ -186,6 +191,7 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
     if (e != cudaSuccess) { ga3c_destroy(n); return fail("cudaMalloc", e); }
   }
   if (int r = alloc_workspace(n, cfg->max_batch)) { ga3c_destroy(n); return r; }
+  if (const char* f = getenv("GA3C_FUSE_OPT")) n->fuse_opt = atoi(f) != 0;
   cudaMemset(n->w, 0, ab); cudaMemset(n->g, 0, ab); cudaMemset(n->mom, 0, ab);
   cudaMemset(n->w1_shadow, 0, (size_t)FLAT * FC * 2);
   {  // ms slot starts at 1.0 [TF-SEMANTICS]
@@ -418,7 +424,7 @@ static GradReduceArgs reduce_args(ga3c_net* n, int batch, float* g_dst = nullptr
 // dense1 data gradient and the two conv backward kernels; with `reduce` the slabs are summed into the gradient arena
 // (conv11/*, conv12/*, dense1/b, heads, loss sums), otherwise the caller does it (fused with RMSProp).
 static int fb_tail_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, void* stream, bool with_wgrad, bool reduce,
-                        const DpBigArgs* dp = nullptr, float* g_dst = nullptr) {
+                        const DpBigArgs* dp = nullptr, float* g_dst = nullptr, const ConvBwdOpt* opt = nullptr) {
   if (int r = check_batch(n, batch, "ga3c_fb_tail")) return r;
   if (!x) return fail_msg("ga3c_fb_tail: null buffer");
   if (batch != n->last_batch) return fail_msg("ga3c_fb_tail: batch differs from the preceding ga3c_fb_head");
@@ -432,7 +438,7 @@ static int fb_tail_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, vo
     LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
   LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(n->xblk, n->n1, n->dn2, w + n->off(P_C12W), n->keep_dn1 ? n->dn1 : nullptr,
                                               gp + n->off(P_C11W), gp + n->off(P_C11B), gp + n->off(P_C12W),
-                                              gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, x_u8, dp, st));
+                                              gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, x_u8, opt ? *opt : ConvBwdOpt{}, dp, st));
   if (reduce) LAUNCH(n, K_GRAD_REDUCE, st, launch_grad_reduce(reduce_args(n, batch, g_dst), st));
   return 0;
 }
@@ -583,10 +589,11 @@ static int dp_attach_finish(ga3c_net* n, int32_t rank, int32_t world) {
   n->dp_exchange = 0;
   if (const char* e = getenv("GA3C_DP_EXCHANGE")) {
     const std::string m(e);
-    if (m == "tail") n->dp_exchange = 0;
+    if (m == "warps") n->dp_exchange = 3;
+    else if (m == "tail") n->dp_exchange = 0;
     else if (m == "overlap") n->dp_exchange = 1;
     else if (m == "single") n->dp_exchange = 2;
-    else return fail_msg("GA3C_DP_EXCHANGE must be tail, overlap or single");
+    else return fail_msg("GA3C_DP_EXCHANGE must be warps, tail, overlap or single");
   }
   if (const char* e = getenv("GA3C_DP_EXCH_CTAS")) n->dp_exch = atoi(e);
   if (n->dp_exch < 1 || n->dp_exch > n->num_sms / 2) n->dp_exch = 20;
@@ -680,7 +687,7 @@ static int train_step_empty(ga3c_net* n, float lr, float* loss, void* stream) {
   n->gp_heads_grid = 0;
   n->loss_out = loss;
   n->last_batch = 0;
-  if (n->dp_exchange == 0) {                      // tail: nothing but the exchange launch; its CTA 0 publishes "gradient final"
+  if (n->dp_exchange == 0 || n->dp_exchange == 3) {   // nothing but the exchange launch (dp_tail: both instalments); it publishes "gradient final"
     CK(cudaMemsetAsync(n->g + n->off(P_D1W), 0, (size_t)FLAT * FC * 4, st));
     const DpBigArgs b = dp_big_args(n, lr, 0);
     n->cur_exch = 0;
@@ -696,7 +703,7 @@ static int train_step_empty(ga3c_net* n, float lr, float* loss, void* stream) {
     float* gp = n->gpart;
     LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(n->xblk, n->n1, n->dn2, n->w + n->off(P_C12W), nullptr,
                                                 gp + n->off(P_C11W), gp + n->off(P_C11B), gp + n->off(P_C12W),
-                                                gp + n->off(P_C12B), n->gp_stride, 0, n->num_sms, false, &b, st));
+                                                gp + n->off(P_C12B), n->gp_stride, 0, n->num_sms, false, ConvBwdOpt{}, &b, st));
     const RmsPropDpArgs d = dp_small_args(n, lr, 0, b);
     n->cur_exch = 0;
     LAUNCH(n, K_RMSPROP, st, launch_dp_small(d, n->xbuf_off, st));
@@ -721,6 +728,19 @@ static int train_step_impl(ga3c_net* n, const void* x, bool x_u8, const float* y
     if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, true)) return r;
     return apply_rmsprop_impl(n, lr, stream, nullptr);
   }
+  if (n->dp_world > 1 && n->dp_exchange == 3) {
+    // default: the dense1/w exchange rides on the optimizer warps of the conv backward CTAs (all SMs keep computing conv
+    // gradients); dp_small follows with the small tensors and holds the step open until every rank's slice has landed
+    const DpBigArgs b = dp_big_args(n, lr, 0);
+    n->cur_exch = 0;
+    ConvBwdOpt opt{};
+    opt.mode = 2;
+    if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, false, &b, nullptr, &opt)) return r;
+    const RmsPropDpArgs d = dp_small_args(n, lr, batch, b);
+    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_dp_small(d, n->xbuf_off, (cudaStream_t)stream));
+    n->global_step += 1;
+    return 0;
+  }
   if (n->dp_world > 1 && n->dp_exchange == 0) {
     // exchange at the end of the step (dp_tail_kernel): the conv backward keeps every SM; its CTA 0 publishes "dense1/w gradient
     // final" to the peers as soon as dense_bwd is complete, so that no rank waits for another rank's gradient at the tail
@@ -742,6 +762,22 @@ static int train_step_impl(ga3c_net* n, const void* x, bool x_u8, const float* y
     n->cur_exch = 0;
     if (r) return r;
     LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_dp_small(d, n->xbuf_off, (cudaStream_t)stream));
+    n->global_step += 1;
+    return 0;
+  }
+  if (n->dp_world == 1 && n->fuse_opt) {
+    // single GPU: dense1/w is updated by the optimizer warps of the conv backward CTAs; the launch at the end of the step sums the
+    // slabs and updates the small tensors
+    ConvBwdOpt opt{};
+    opt.mode = 1;
+    opt.g = n->g + n->off(P_D1W); opt.w = n->w + n->off(P_D1W); opt.ms = n->ms + n->off(P_D1W); opt.mom = n->mom + n->off(P_D1W);
+    opt.shadow = n->w1_shadow; opt.n4 = (long long)FLAT * FC / 4;
+    opt.lr = lr; opt.decay = n->cfg.rmsprop_decay; opt.momentum = n->cfg.rmsprop_momentum; opt.eps = n->cfg.rmsprop_epsilon;
+    if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, false, nullptr, nullptr, &opt)) return r;
+    RmsPropArgs ra = rmsprop_args(n, lr);
+    ra.n_floats = n->small_floats;                  // dense1/w is done
+    ra.preload = batch >= n->num_sms;
+    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_rmsprop_reduce(ra, reduce_args(n, batch), (cudaStream_t)stream));
     n->global_step += 1;
     return 0;
   }

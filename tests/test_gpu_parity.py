@@ -158,11 +158,11 @@ def test_log_softmax_knob(ga3c):
     assert np.allclose(p.sum(axis=1), 1.0, atol=1e-5)
 
 
-@pytest.mark.parametrize("exchange", ["tail", "overlap"])
+@pytest.mark.parametrize("exchange", ["warps", "tail", "overlap"])
 def test_data_parallel_exchange_two_ranks_on_one_gpu(ga3c, monkeypatch, exchange):
-    """The fused data-parallel step (dp_exchange.cuh; "tail": the whole exchange in one launch on every SM at the end of the
-    step; "overlap": dense1/w on exchange CTAs of the conv backward launch, LL push of the small tensors afterwards) with
-    BOTH ranks on one device: two handles attached to each other with ga3c_dp_attach_local, each on its
+    """The fused data-parallel step (dp_exchange.cuh; "warps", the default: dense1/w exchanged by the optimizer warps of every
+    conv backward CTA, LL push of the small tensors afterwards; "tail": the whole exchange in one launch at the end of the
+    step; "overlap": dense1/w on extra exchange CTAs of the conv backward launch) with BOTH ranks on one device: two handles attached to each other with ga3c_dp_attach_local, each on its
     own stream, each training on its row shard.  After 3 steps the replicas are bit-identical and equal the oracle's
     single-process steps on the concatenated batch (what a single ThreadTrainer would have computed).  The grids are small
     (12 rows per rank), so both ranks' kernels are resident together; every cross-rank wait is bounded, so a scheduling
