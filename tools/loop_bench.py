@@ -151,6 +151,10 @@ def main():
     ap.add_argument("--predictors", type=int, default=2)
     ap.add_argument("--trainers", type=int, default=2)
     ap.add_argument("--min-train-batch", type=int, default=512, help="Config.TRAINING_MIN_BATCH_SIZE")
+    ap.add_argument("--independent-replicas", action="store_true",
+                    help="N > 1: no gradient exchange, every GPU trains its own replica (round 1's mode); the default is the "
+                         "data-parallel train step driven by ga3c_b200.LockstepTrainer")
+    ap.add_argument("--tick", type=float, default=0.004, help="LockstepTrainer: seconds a rank waits for rows before it ticks")
     args = ap.parse_args()
     rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
     ctx = mp.get_context("fork")
@@ -185,7 +189,7 @@ def main():
 
     import torch
     import ga3c_b200
-    from ga3c_b200 import ThreadPredictor, ThreadTrainer
+    from ga3c_b200 import LockstepTrainer, ThreadPredictor, ThreadTrainer
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
@@ -194,12 +198,14 @@ def main():
     class Cfg(ga3c_b200.Config):
         TRAINING_MIN_BATCH_SIZE = args.min_train_batch
         PREDICTION_BATCH_SIZE = 128
-    # data parallel needs every rank to train in lock step; the asynchronous loop trains whenever a batch is ready, so each
-    # GPU runs an independent replica here (the reference's own multi-trainer mode is asynchronous too)
-    model = ga3c_b200.Network(f"gpu:{local}", "loop", A, max_batch=4096, seed=12345, config=Cfg, data_parallel=False)
+    # N > 1: the data-parallel train step needs every rank to enter every step, the asynchronous loop trains whenever its own
+    # queue yields a batch -- LockstepTrainer bridges the two (one tiny host allreduce per round; a rank whose round came up
+    # empty enters the step with 0 rows).  Replicas start identical (no seed: rank 0's weights are broadcast) and must end so.
+    dp = world > 1 and not args.independent_replicas
+    model = ga3c_b200.Network(f"gpu:{local}", "loop", A, max_batch=4096, seed=None if dp else 12345, config=Cfg, data_parallel=dp)
     server = MiniServer(model, tq, agents)
     preds = [ThreadPredictor(server, i, S, pq, config=Cfg) for i in range(args.predictors)]
-    trains = [ThreadTrainer(server, i, config=Cfg) for i in range(args.trainers)]
+    trains = [LockstepTrainer(server, 0, config=Cfg, tick=args.tick)] if dp else [ThreadTrainer(server, i, config=Cfg) for i in range(args.trainers)]
     for th in preds + trains:
         th.start()
     time.sleep(2.0)                                                               # warm-up
@@ -217,6 +223,26 @@ def main():
     res = {"pps": (r1 - r0) / dt, "tps_frames": (f1 - f0) / dt, "tps_batches": (b1 - b0) / dt,
            "mean_predict_batch": (r1 - r0) / max(pb1 - pb0, 1), "mean_train_batch": (f1 - f0) / max(b1 - b0, 1),
            "agent_side_pps": float(c1[0] - c0[0]) / dt}
+    extra = {}
+    if dp:
+        # stop training on every rank after the same number of steps, then compare the replicas
+        for th in trains:
+            th.exit_flag = True
+        for th in trains:
+            th.join(timeout=60)
+        w = model.get_variables()
+        ms, _ = model.get_slots()
+        flat = torch.from_numpy(np.concatenate([w[k].ravel() for k in sorted(w)] + [ms[k].ravel() for k in sorted(ms)] +
+                                               [model.workspace(6)])).to(f"cuda:{local}")
+        got = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(got, flat)
+        steps = torch.tensor([trains[0].steps, trains[0].empty_steps], dtype=torch.int64, device=f"cuda:{local}")
+        all_steps = [torch.empty_like(steps) for _ in range(world)]
+        dist.all_gather(all_steps, steps)
+        extra = {"data_parallel": "fused peer-memory exchange, LockstepTrainer", "replicas_identical_after_run": bool(all(torch.equal(got[0], g) for g in got)),
+                 "exchange_steps_per_rank": [int(t[0]) for t in all_steps], "empty_steps_per_rank": [int(t[1]) for t in all_steps],
+                 "global_step": model.get_global_step()}
+        model.dp_check()
     if world > 1:
         t = torch.tensor([res["pps"], res["tps_frames"]], dtype=torch.float64, device=f"cuda:{local}")
         dist.all_reduce(t)
@@ -225,7 +251,7 @@ def main():
         out = {"config": f"{args.agents} synthetic agents per GPU in {procs_n} processes, transport={args.transport}, "
                          f"frames={'uint8' if args.uint8 else 'fp32'}, {'vectorised agent processes, ' if args.vector_agents else ''}T_MAX={T_MAX}, predictors={args.predictors}, "
                          f"trainers={args.trainers}, TRAINING_MIN_BATCH_SIZE={args.min_train_batch}, {os.cpu_count()} host cores",
-               "n_gpus": world, "seconds": round(dt, 2), **{k: round(v, 1) for k, v in res.items()}}
+               "n_gpus": world, "seconds": round(dt, 2), **{k: round(v, 1) for k, v in res.items()}, **extra}
         print(json.dumps(out), flush=True)
     for th in preds + trains:
         th.exit_flag = True
