@@ -354,10 +354,14 @@ def dp_check(net, rank, local_rank, world, B):
     got = net.get_variables()
     worst = max(float(np.abs(got[k] - ref[k]).max()) for k in got) if rank == 0 else 0.0
     rep["replicas_identical_oracle_leg"] = replicas_identical()
-    rep.update(max_abs_vs_oracle=worst, oracle_rows_per_rank=rows, oracle_steps=2, tol=1e-5,
+    # tolerance: the single-GPU parity tests hold the weights after a step to 2e-6 at 48 rows; gradients are SUMS over the batch
+    # and a stored bf16 activation now and then rounds the other way than the fp64-accumulating oracle's, so the absolute
+    # error of a step grows with the rows in the batch: 1e-5 up to 128 rows, in proportion beyond (4e-5 at 8 x 64)
+    tol = 1e-5 * max(1.0, world * rows / 128.0)
+    rep.update(max_abs_vs_oracle=worst, oracle_rows_per_rank=rows, oracle_steps=2, tol=tol,
                oracle="oracle_np.train_step (quant='bf16') on the concatenated batch")
     net.dp_check()
-    ok = rep["identical_at_start_without_seed"] and rep["replicas_identical"] and rep["replicas_identical_oracle_leg"] and worst <= 1e-5
+    ok = rep["identical_at_start_without_seed"] and rep["replicas_identical"] and rep["replicas_identical_oracle_leg"] and worst <= tol
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     rep["ok"] = bool(flag.item() == 0)

@@ -90,9 +90,11 @@ constexpr int FB_SMEM = FB_OFF_LAST + 16 + 128;                   // incl. slack
 static_assert(FB_SMEM <= 232448, "shared memory budget of one CTA per SM");
 constexpr int FB_TMEM_COLS = 512, TM_W11 = 0, TM_W12 = 64, TM_D12 = 192;   // 64 | 2x64 | 2x64 columns
 
-// DP: data parallel (CTA 0 publishes "dense1/w gradient final"; the grid may carry exchange CTAs).  EVT: the instantiation with
-// the pipeline event log of CTA 0 (ga3c_evt_*, tools/evt_timeline.py); the production instantiation carries none of it.
-template <bool DP, bool EVT>
+// DPM: 0 single GPU; 1 data parallel, exchange at the end of the step (the default): CTA 0 publishes "dense1/w gradient final" and
+// that is all; 2 data parallel with the exchange inside this launch (exchange CTAs, or the optimizer warps in mode 2).  Separate
+// instantiations: the exchange code costs the conv path 20 registers and a few spills.  EVT: the instantiation with the pipeline
+// event log of CTA 0 (ga3c_evt_*, tools/evt_timeline.py); the production instantiations carry none of it.
+template <int DPM, bool EVT>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 conv_bwd_kernel(const uint8_t* __restrict__ xblk, const uint8_t* __restrict__ n1b2, const uint8_t* __restrict__ dn2g,
                 const float* __restrict__ w12, uint16_t* __restrict__ dn1_out, float* __restrict__ g_w11,
@@ -100,7 +102,8 @@ conv_bwd_kernel(const uint8_t* __restrict__ xblk, const uint8_t* __restrict__ n1
                 int n_conv, int hints, const ConvBwdOpt opt, const DpBigArgs dp) {
   // data parallel, overlapped exchange: CTAs [n_conv, gridDim.x) are exchange CTAs -- they move dense1/w (final since
   // dense_bwd, the launch this one depends on) between the ranks while CTAs [0, n_conv) compute the conv gradients
-  if (DP && (int)blockIdx.x >= n_conv) {
+  constexpr bool DP = DPM != 0;
+  if (DPM == 2 && (int)blockIdx.x >= n_conv) {
     griddep_launch();
     griddep_wait(K_DP_BIG);
     dp_big_exchange(dp, (int)blockIdx.x - n_conv, (int)gridDim.x - n_conv);
@@ -116,7 +119,7 @@ conv_bwd_kernel(const uint8_t* __restrict__ xblk, const uint8_t* __restrict__ n1
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   EvtLog evt_i = EVT ? evt_open() : EvtLog{nullptr, 0};
   auto mark = [&](int id, int arg) { if (EVT) evt_mark(evt_i, id, arg); };
-  const int stride = DP ? (int)gridDim.x - dp.n_exch : (int)gridDim.x;
+  const int stride = DPM == 2 ? (int)gridDim.x - dp.n_exch : (int)gridDim.x;
   const int n_frames = ((int)blockIdx.x < batch) ? (batch - 1 - (int)blockIdx.x) / stride + 1 : 0;
   auto frame_of = [&](int k) { return (size_t)(blockIdx.x + k * stride); };
   auto bar = [&](int i) { return bars + i * 8; };
@@ -413,7 +416,7 @@ conv_bwd_kernel(const uint8_t* __restrict__ xblk, const uint8_t* __restrict__ n1
           sh[i] = make_uint2(pack_bf16(wv[u].x, wv[u].y), pack_bf16(wv[u].z, wv[u].w));
         }
       }
-    } else if (DP && opt.mode == 2) {
+    } else if (DPM == 2 && opt.mode == 2) {
       // data parallel: CTA 0's group publishes "dense_bwd done on this rank", then every group takes its share of the exchange
       dp_big_group(dp, t, FB_OPT_THREADS, (int)blockIdx.x, n_conv, 4, reinterpret_cast<int*>(smem + FB_OFF_LAST), true);
     }
@@ -528,11 +531,13 @@ int evt_attach_conv_bwd(unsigned long long* buf) {
 int conv_bwd_grid(int batch, int num_sms, int n_exch) { return min(batch, num_sms - n_exch); }
 
 int configure_conv_bwd_fused() {
-  cudaError_t e = cudaFuncSetAttribute(conv_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(conv_bwd_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(conv_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+  e = cudaFuncSetAttribute(conv_bwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
   if (e != cudaSuccess) return (int)e;
-  return (int)cudaFuncSetAttribute(conv_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+  e = cudaFuncSetAttribute(conv_bwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaFuncSetAttribute(conv_bwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FB_SMEM);
 }
 
 int launch_conv_bwd(const uint8_t* xblk, const uint8_t* n1b2, const uint8_t* dn2g, const float* w12, uint16_t* dn1_out,
@@ -544,7 +549,8 @@ int launch_conv_bwd(const uint8_t* xblk, const uint8_t* n1b2, const uint8_t* dn2
   const dim3 grid(n_conv + d.n_exch);
   if (grid.x == 0) return 0;
   if (opt.mode == 2 && (dp == nullptr || n_conv == 0)) return (int)cudaErrorInvalidValue;
-  auto kernel = dp != nullptr ? conv_bwd_kernel<true, false> : (g_evt_attached ? conv_bwd_kernel<false, true> : conv_bwd_kernel<false, false>);
+  auto kernel = dp != nullptr ? ((d.n_exch > 0 || opt.mode == 2) ? conv_bwd_kernel<2, false> : conv_bwd_kernel<1, false>)
+                              : (g_evt_attached ? conv_bwd_kernel<0, true> : conv_bwd_kernel<0, false>);
   return launch_pdl(kernel, grid, dim3(FB_THREADS), FB_SMEM, stream, xblk, n1b2, dn2g, w12, dn1_out, g_w11, g_b11, g_w12, g_b12,
                     gp_stride, batch, n_conv, l2_hints(true, x_u8), opt, d);
 }
