@@ -9,5 +9,6 @@ without an sm_100 GPU raises.
 from .config import Config  # noqa: F401
 from .network import Network  # noqa: F401
 from .threads import LockstepTrainer, ThreadPredictor, ThreadTrainer  # noqa: F401
+from .batcher import NativePredictor  # noqa: F401
 
-__all__ = ["Config", "Network", "ThreadPredictor", "ThreadTrainer", "LockstepTrainer"]
+__all__ = ["Config", "Network", "ThreadPredictor", "ThreadTrainer", "LockstepTrainer", "NativePredictor"]

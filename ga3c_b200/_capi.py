@@ -23,6 +23,12 @@ class ga3c_mlp_config(C.Structure):
                 ("use_grad_clip", C.c_int32), ("grad_clip_norm", C.c_float), ("dual_rmsprop", C.c_int32)]
 
 
+class ga3c_batcher_config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("num_agents", C.c_int32), ("state_bytes", C.c_int32), ("x_u8", C.c_int32),
+                ("max_batch", C.c_int32), ("num_actions", C.c_int32), ("states", C.c_void_p), ("pending", C.c_void_p),
+                ("reply_p", C.c_void_p), ("reply_v", C.c_void_p), ("work_sem", C.c_void_p), ("wake_sems", C.POINTER(C.c_void_p))]
+
+
 MLP_FORK_VP, MLP_DISCRATE = 0, 1
 
 # name -> (restype, argtypes); the single source the symbol-export test checks against the header
@@ -61,6 +67,13 @@ SIGNATURES = {
     "ga3c_dual_forward_backward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
                                                 C.c_void_p, C.c_void_p]),
     "ga3c_dual_apply": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p]),
+    "ga3c_lock": (C.c_int, [C.c_void_p]),
+    "ga3c_unlock": (C.c_int, [C.c_void_p]),
+    "ga3c_batcher_create": (C.c_int, [C.c_void_p, C.POINTER(ga3c_batcher_config), C.POINTER(C.c_void_p)]),
+    "ga3c_batcher_start": (C.c_int, [C.c_void_p]),
+    "ga3c_batcher_stop": (C.c_int, [C.c_void_p]),
+    "ga3c_batcher_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "ga3c_batcher_destroy": (C.c_int, [C.c_void_p]),
     "ga3c_predict_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ga3c_forward_backward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
                                            C.c_void_p, C.c_void_p]),

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -81,6 +82,7 @@ struct ga3c_net {
   float *g2 = nullptr, *ms2 = nullptr, *mom2 = nullptr;   // Config.DUAL_RMSPROP: gradient of cost_v and the second optimizer's slots
   bool keep_dn1 = false;           // tests: also store dn1 (which otherwise never leaves the SM) to the workspace
   int64_t global_step = 0;
+  std::mutex mtx;                  // ga3c_lock / ga3c_unlock
   LaunchLog log;                   // launch counter + per-kernel CUDA-event timing (ga3c_timing_*)
   int last_batch = 0;
   unsigned long long* evt = nullptr;       // pipeline event log of CTA 0 (ga3c_evt_*), device memory
@@ -250,6 +252,17 @@ extern "C" int ga3c_destroy(ga3c_net* n) {
   free_workspace(n);
   n->log.clear();
   delete n;
+  return 0;
+}
+
+extern "C" int ga3c_lock(ga3c_net* n) {
+  if (!n) return fail_msg("ga3c_lock: null handle");
+  n->mtx.lock();
+  return 0;
+}
+extern "C" int ga3c_unlock(ga3c_net* n) {
+  if (!n) return fail_msg("ga3c_unlock: null handle");
+  n->mtx.unlock();
   return 0;
 }
 

@@ -47,6 +47,22 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
+class _HandleLock:
+    """`with lock:` on the handle's own mutex (ga3c_lock / ga3c_unlock): shared with the native predictor batcher, which runs
+    outside the interpreter.  ctypes releases the GIL while a thread waits for it."""
+
+    def __init__(self, lib, handle):
+        self._lib, self._h = lib, handle
+
+    def __enter__(self):
+        self._lib.ga3c_lock(self._h)
+        return self
+
+    def __exit__(self, *exc):
+        self._lib.ga3c_unlock(self._h)
+        return False
+
+
 class Network:
     def __init__(self, device, model_name, num_actions, state_dim=STATE_DIM, *, config=None, max_batch=None,
                  seed=None, data_parallel=None, dp_mode=None):
@@ -69,7 +85,6 @@ class Network:
             raise _capi.Ga3cError("no CUDA device visible: ga3c_b200 has no CPU fallback")
         self._ordinal = _parse_device(device)
         self._tdev = torch.device("cuda", self._ordinal)
-        self._lock = threading.Lock()
         self._max_batch = int(max_batch or max(getattr(cfg, "PREDICTION_BATCH_SIZE", 128), 128))
 
         c = _capi.ga3c_config(device=self._ordinal, num_actions=self.num_actions, max_batch=self._max_batch,
@@ -81,6 +96,7 @@ class Network:
         h = C.c_void_p()
         _capi.check(self._lib.ga3c_create(C.byref(c), C.byref(h)), "ga3c_create")
         self._h = h
+        self._lock = _HandleLock(self._lib, self._h)
 
         # name -> (offset, shape) table in TF creation order
         self._table = {}

@@ -230,6 +230,38 @@ int64_t ga3c_mlp_launch_count(const ga3c_mlp* net);
 int ga3c_mlp_timing_enable(ga3c_mlp* net, int32_t max_records);
 int ga3c_mlp_timing_collect(ga3c_mlp* net, double* total_ms, int64_t* counts, int32_t n_kernels);
 
+/* ---- serialisation ---------------------------------------------------------------------------------
+ * A handle is not re-entrant (one activation workspace).  Whoever drives it from several threads -- the reference calls
+ * predict_p_and_v and train from PREDICTORS + TRAINERS threads without locks (Server.py:123-134) -- takes this mutex around
+ * [enqueue ... stream synchronise]: the Python Network does, and so does the native batcher below. */
+int ga3c_lock(ga3c_net* net);
+int ga3c_unlock(ga3c_net* net);
+
+/* ---- native predictor batcher ----------------------------------------------------------
+ * ThreadPredictor.run (ThreadPredictor.py:45-66) as a thread inside the library, over the shared-memory slab of
+ * ga3c_b200.transport.SlabPredictionQueue: wait for a request (work_sem), take every pending row (at most max_batch, round
+ * robin), copy those rows from the page-locked, device-mapped state slab into the batch with ONE kernel (no host gather, no
+ * staging copy), ga3c_predict[_u8], write (p, v) into the agents' reply rows and post their semaphores -- the `wait_q.put` of
+ * ThreadPredictor.py:63.  The interpreter is never entered.  All pointers are HOST pointers into memory shared with the
+ * agent processes; semaphores are POSIX sem_t* (what multiprocessing.Semaphore wraps: SemLock.handle).
+ * state_bytes: bytes per state row (28224 for uint8 frames, 112896 for float32), a multiple of 16. */
+typedef struct ga3c_batcher ga3c_batcher;
+typedef struct ga3c_batcher_config {
+  int32_t device, num_agents, state_bytes, x_u8, max_batch, num_actions;
+  void*    states;      /* [num_agents][state_bytes]; registered with cudaHostRegister for the batcher's lifetime */
+  uint8_t* pending;     /* [num_agents]: 1 = a request is posted in that agent's row                              */
+  float*   reply_p;     /* [num_agents][num_actions]                                                              */
+  float*   reply_v;     /* [num_agents]                                                                           */
+  void*    work_sem;    /* sem_t*: one permit per posted request (a wake-up hint; the pending bytes are the truth) */
+  void**   wake_sems;   /* sem_t* [num_agents]: posted when the agent's reply row is filled                       */
+} ga3c_batcher_config;
+int ga3c_batcher_create(ga3c_net* net, const ga3c_batcher_config* cfg, ga3c_batcher** out);
+int ga3c_batcher_start(ga3c_batcher* b);
+int ga3c_batcher_stop(ga3c_batcher* b);
+/* batches / rows served since creation; *error != 0 (and a non-zero return with ga3c_last_error) if the thread gave up */
+int ga3c_batcher_stats(ga3c_batcher* b, int64_t* batches, int64_t* rows, int32_t* error);
+int ga3c_batcher_destroy(ga3c_batcher* b);
+
 /* ---- introspection for tests / profiling ---------------------------------------------------- */
 /* device pointers to the activation workspace of the last call (bf16 stored as uint16):
  * which: 0 n1 bf16 in the Blk2 operand layout [B][8 planes][160 rows][8] (channels 8h.. of pixel (y, x) in plane

@@ -379,6 +379,51 @@ def test_slab_transport_feeds_the_cuda_network(ga3c):
         pq.close(); tq.close()
 
 
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_native_predictor_batcher_over_the_slab(ga3c, dtype):
+    """The predictor loop inside the library (ga3c_batcher_*, ga3c_b200.NativePredictor): requests posted into the slab are
+    gathered from the page-locked state rows by a kernel, predicted, and answered on the agents' own wait_q -- every reply equals
+    the oracle's prediction for the frame that agent posted, over several rounds, while a trainer thread trains on the same
+    network (the handle's mutex serialises them)."""
+    import time
+    from ga3c_b200.transport import SlabPredictionQueue
+    n_agents, rounds = 200, 4
+    rng = np.random.default_rng(61)
+    params = onp.init_params(rng, 6)
+    net = ga3c.Network("gpu:0", "t", 6, max_batch=128)
+    net.set_variables(params)
+    net.learning_rate = 0.0                              # weights stay put, so every round is checkable
+    pq = SlabPredictionQueue(n_agents, onp.STATE_DIM, 6, dtype=dtype)
+    srv = _Server(net, n_agents)
+    pred = ga3c.NativePredictor(srv, 0, pq)
+    pred.start()
+    stop = threading.Event()
+    xt = onp.synth_frames(rng, 32)
+    yt, at = onp.synth_targets(rng, 32)
+
+    def trainer():
+        while not stop.is_set():
+            net.train(xt, yt, at, None, None, 0)
+    th = threading.Thread(target=trainer)
+    th.start()
+    try:
+        for r in range(rounds):
+            k = rng.integers(0, 256, size=(n_agents, onp.STATE_DIM), dtype=np.uint8)
+            x = k.astype(np.float32) / 128.0 - 1.0
+            pq.post_many(np.arange(n_agents), k if dtype == np.uint8 else x)
+            p = np.zeros((n_agents, 6), np.float32); v = np.zeros(n_agents, np.float32)
+            assert pq.wait_many(np.arange(n_agents), p, v, timeout=60) == n_agents
+            pr, vr = onp.forward(params, x, quant="bf16")
+            assert np.abs(p - pr).max() <= TOL_P and np.abs(v - vr).max() <= TOL_V, (r, np.abs(p - pr).max())
+        assert pred.rows == n_agents * rounds and pred.batches >= 2 * rounds      # 200 pending rows: at least two batches of <= 128
+        assert not pq._pending.array.any()
+    finally:
+        stop.set(); th.join()
+        pred.exit_flag = True
+        pred.close()
+        pq.close()
+
+
 def test_golden_network_b4(ga3c, golden_dir):
     """The committed B=4 fixture (tests/golden/network_b4.npz, oracle/gen_golden.py)."""
     g = np.load(os.path.join(golden_dir, "network_b4.npz"))

@@ -149,6 +149,9 @@ def main():
     ap.add_argument("--vector-agents", action="store_true",
                     help="each agent process steps its agents as one numpy vector (slab transport only)")
     ap.add_argument("--predictors", type=int, default=2)
+    ap.add_argument("--native-predictor", action="store_true",
+                    help="the predictor loop inside the C library (ga3c_b200.NativePredictor, slab transport only) instead of "
+                         "--predictors Python threads")
     ap.add_argument("--trainers", type=int, default=2)
     ap.add_argument("--min-train-batch", type=int, default=512, help="Config.TRAINING_MIN_BATCH_SIZE")
     ap.add_argument("--independent-replicas", action="store_true",
@@ -189,7 +192,7 @@ def main():
 
     import torch
     import ga3c_b200
-    from ga3c_b200 import LockstepTrainer, ThreadPredictor, ThreadTrainer
+    from ga3c_b200 import LockstepTrainer, NativePredictor, ThreadPredictor, ThreadTrainer
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
@@ -204,7 +207,10 @@ def main():
     dp = world > 1 and not args.independent_replicas
     model = ga3c_b200.Network(f"gpu:{local}", "loop", A, max_batch=4096, seed=None if dp else 12345, config=Cfg, data_parallel=dp)
     server = MiniServer(model, tq, agents)
-    preds = [ThreadPredictor(server, i, S, pq, config=Cfg) for i in range(args.predictors)]
+    if args.native_predictor:
+        preds = [NativePredictor(server, 0, pq, config=Cfg)]
+    else:
+        preds = [ThreadPredictor(server, i, S, pq, config=Cfg) for i in range(args.predictors)]
     trains = [LockstepTrainer(server, 0, config=Cfg, tick=args.tick)] if dp else [ThreadTrainer(server, i, config=Cfg) for i in range(args.trainers)]
     for th in preds + trains:
         th.start()
@@ -249,7 +255,7 @@ def main():
         res["job_pps"], res["job_tps_frames"] = float(t[0]), float(t[1])
     if rank == 0:
         out = {"config": f"{args.agents} synthetic agents per GPU in {procs_n} processes, transport={args.transport}, "
-                         f"frames={'uint8' if args.uint8 else 'fp32'}, {'vectorised agent processes, ' if args.vector_agents else ''}T_MAX={T_MAX}, predictors={args.predictors}, "
+                         f"frames={'uint8' if args.uint8 else 'fp32'}, {'vectorised agent processes, ' if args.vector_agents else ''}T_MAX={T_MAX}, predictors={'native (C library)' if args.native_predictor else args.predictors}, "
                          f"trainers={args.trainers}, TRAINING_MIN_BATCH_SIZE={args.min_train_batch}, {os.cpu_count()} host cores",
                "n_gpus": world, "seconds": round(dt, 2), **{k: round(v, 1) for k, v in res.items()}, **extra}
         print(json.dumps(out), flush=True)
