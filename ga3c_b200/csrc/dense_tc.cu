@@ -241,6 +241,10 @@ static int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
+int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  return make_tmap(map, base, rows, cols, ld, box_rows);       // for dense_heads.cu
+}
+
 template <int BN, int STAGES>
 constexpr int tc_smem() { return STAGES * (TC_A_STAGE + BN * TC_BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024; }
 

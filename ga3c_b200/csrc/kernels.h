@@ -12,11 +12,13 @@ int trace_attach_conv_bwd_fused(unsigned long long* buf);
 int trace_attach_dense_tc(unsigned long long* buf);
 int trace_attach_heads(unsigned long long* buf);
 int trace_attach_elementwise(unsigned long long* buf);
+int trace_attach_dense_heads(unsigned long long* buf);
 
 // pipeline event log of CTA 0 (debug): attach a zeroed [16 warps][1024][2] uint64 buffer (or nullptr)
 int evt_attach_conv_fwd(unsigned long long* buf);
 int evt_attach_conv_bwd(unsigned long long* buf);
 int evt_attach_elementwise(unsigned long long* buf);
+int evt_attach_dense_heads(unsigned long long* buf);
 
 // L2 residency hints on the conv kernels' loads and stores (common.cuh); GA3C_L2_HINTS=0 switches them off (evict_normal)
 // bit 0: frames loaded evict_first, bit 1: activations stored evict_last, bit 2: the conv backward loads evict_first.
@@ -73,6 +75,13 @@ struct HeadsArgs {
 };
 int heads_grid(int batch, int num_sms);          // CTAs (= slabs written) of a training launch
 int launch_heads(const HeadsArgs& args, int num_sms, cudaStream_t stream);
+
+// dense_heads.cu -- dense1 forward (cluster split-K, partial tiles reduced over distributed shared memory) with the heads, the
+// loss and its backward as its epilogue: replaces launch_dense_fwd_tc + launch_heads (args.d1_part / n_split are not used).
+// In training it writes dense_heads_ctas(batch) slabs.
+int configure_dense_heads();
+int dense_heads_ctas(int batch);
+int launch_dense_heads(const uint16_t* n2, const uint16_t* w1bf, const HeadsArgs& args, cudaStream_t stream);
 
 // conv_bwd_fused.cu
 // Weight / bias gradients are per-CTA partial sums: CTA i stores into slab i (g_* point into slab 0, slabs are

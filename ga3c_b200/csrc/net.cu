@@ -59,6 +59,10 @@ struct ga3c_net {
                                    // in dp_small), 1 "overlap" (exchange CTAs inside the conv backward launch + dp_small), 2
                                    // "single" (the first version: one kernel that also broadcasts the fp32 weights).  Measured at 2
                                    // GPUs, B = 1024 per GPU (profiles/r2l_*): tail 0.1196 ms, warps 0.1205, overlap 0.1403
+  int fuse_heads = 0;              // GA3C_FUSE_HEADS=1: dense1 forward + heads as ONE cluster launch (dense_heads.cu: split-K over a
+                                   // thread-block cluster, partial tiles reduced over distributed shared memory).  Parity-green, but
+                                   // measured slower at B = 1024 (step 0.1015 -> 0.1077 ms, profiles/r2r_*): 64 CTAs run the heads of
+                                   // 16 samples each in two serial rounds where the separate kernel runs 128 CTAs of one round
   int fuse_opt = 0;                // GA3C_FUSE_OPT=1: single GPU, dense1/w updated by the optimizer warps of the conv backward CTAs
                                    // instead of the launch at the end.  Measured: conv_bwd 26.3 -> 30.6 us, rmsprop 8.9 -> 5.0 us,
                                    // step 0.1015 -> 0.1032 ms: the conv backward is HBM-bound, the 22 MB cost what they cost alone
@@ -194,6 +198,7 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
   }
   if (int r = alloc_workspace(n, cfg->max_batch)) { ga3c_destroy(n); return r; }
   if (const char* f = getenv("GA3C_FUSE_OPT")) n->fuse_opt = atoi(f) != 0;
+  if (const char* f = getenv("GA3C_FUSE_HEADS")) n->fuse_heads = atoi(f) != 0;
   cudaMemset(n->w, 0, ab); cudaMemset(n->g, 0, ab); cudaMemset(n->mom, 0, ab);
   cudaMemset(n->w1_shadow, 0, (size_t)FLAT * FC * 2);
   {  // ms slot starts at 1.0 [TF-SEMANTICS]
@@ -201,7 +206,7 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
     cudaMemcpy(n->ms, ones.data(), ab, cudaMemcpyHostToDevice);
   }
   int r;
-  if ((r = configure_conv_fwd()) || (r = configure_conv_bwd_fused()) || (r = configure_dense_tc())) {
+  if ((r = configure_conv_fwd()) || (r = configure_conv_bwd_fused()) || (r = configure_dense_tc()) || (r = configure_dense_heads())) {
     ga3c_destroy(n);
     return fail("cudaFuncSetAttribute", (cudaError_t)r);
   }
@@ -363,6 +368,11 @@ static HeadsArgs heads_args(ga3c_net* n, int batch, int splits) {
   return h;
 }
 
+// dense1 forward + heads in one cluster launch (dense_heads.cu) while its slabs fit the gradient-partial workspace
+static bool fused_heads(const ga3c_net* n, int batch) {
+  return n->fuse_heads && !n->cfg.dual_rmsprop && dense_heads_ctas(batch) <= 2 * n->num_sms;
+}
+
 static int predict_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, float* p_out, float* v_out, void* stream) {
   if (int r = check_batch(n, batch, "ga3c_predict")) return r;
   if (!x || !p_out || !v_out) return fail_msg("ga3c_predict: null buffer");
@@ -372,10 +382,14 @@ static int predict_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, fl
   LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, x_u8, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
                                             w + n->off(P_C12B), nullptr, nullptr, n->n2, batch, n->num_sms, st));
   const int splits = dense_fwd_splits(batch, n->num_sms);
-  LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
   HeadsArgs h = heads_args(n, batch, splits);
   h.p_out = p_out; h.v_out = v_out; h.train = 0;
-  LAUNCH(n, K_HEADS, st, launch_heads(h, n->num_sms, st));
+  if (fused_heads(n, batch)) {
+    LAUNCH(n, K_DENSE_FWD, st, launch_dense_heads(n->n2, n->w1_shadow, h, st));
+  } else {
+    LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
+    LAUNCH(n, K_HEADS, st, launch_heads(h, n->num_sms, st));
+  }
   n->last_batch = batch;
   return 0;
 }
@@ -400,18 +414,20 @@ static int fb_head_impl(ga3c_net* n, const void* x, bool x_u8, const float* yr, 
   float* g = n->g;
   float* gp = n->gpart;       // small-tensor gradients: per-CTA partial slabs, summed at the end of ga3c_fb_tail
   const int splits = dense_fwd_splits(batch, n->num_sms);
+  const bool fused = fused_heads(n, batch);
   if (!skip_forward) {        // the second DUAL_RMSPROP pass reuses n1 / n2 / the dense1 partials of the first
     LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, x_u8, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
                                               w + n->off(P_C12B), n->n1, n->xblk, n->n2, batch, n->num_sms, st));
-    LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
+    if (!fused) LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
   }
   HeadsArgs h = heads_args(n, batch, splits);
   h.yr = yr; h.a = a; h.beta = beta; h.train = 1; h.dd1 = n->dd1; h.part = part;
   h.g_wp = gp + n->off(P_PW); h.g_bp = gp + n->off(P_PB); h.g_wv = gp + n->off(P_VW); h.g_bv = gp + n->off(P_VB);
   h.g_b1 = gp + n->off(P_D1B); h.loss = gp + n->small_floats; h.gp_stride = n->gp_stride;
-  n->gp_heads_grid = heads_grid(batch, n->num_sms);
+  n->gp_heads_grid = fused ? dense_heads_ctas(batch) : heads_grid(batch, n->num_sms);
   n->loss_out = loss;
-  LAUNCH(n, K_HEADS, st, launch_heads(h, n->num_sms, st));
+  if (fused) LAUNCH(n, K_DENSE_FWD, st, launch_dense_heads(n->n2, n->w1_shadow, h, st));
+  else LAUNCH(n, K_HEADS, st, launch_heads(h, n->num_sms, st));
   (void)g;
   if (with_wgrad) LAUNCH(n, K_DENSE_WGRAD, st, launch_dense_wgrad_tc(n->n2, n->dd1, n->g + n->off(P_D1W), batch, st));
   n->last_batch = batch;
@@ -865,7 +881,7 @@ extern "C" const char* ga3c_kernel_name(int kid) { return (kid >= 0 && kid < K_C
 static int trace_attach_all(unsigned long long* buf) {
   int r;
   if ((r = trace_attach_conv_fwd(buf)) || (r = trace_attach_conv_bwd_fused(buf)) || (r = trace_attach_dense_tc(buf)) ||
-      (r = trace_attach_heads(buf)) || (r = trace_attach_elementwise(buf)) || (r = trace_attach_mlp(buf)))
+      (r = trace_attach_heads(buf)) || (r = trace_attach_dense_heads(buf)) || (r = trace_attach_elementwise(buf)) || (r = trace_attach_mlp(buf)))
     return r;
   return 0;
 }
@@ -903,6 +919,7 @@ extern "C" int ga3c_evt_begin(ga3c_net* n) {
   CKL(evt_attach_conv_fwd(n->evt));
   CKL(evt_attach_conv_bwd(n->evt));
   CKL(evt_attach_elementwise(n->evt));
+  CKL(evt_attach_dense_heads(n->evt));
   return 0;
 }
 
@@ -913,6 +930,7 @@ extern "C" int ga3c_evt_end(ga3c_net* n, uint64_t* records, int32_t cap, int32_t
   CKL(evt_attach_conv_fwd(nullptr));
   CKL(evt_attach_conv_bwd(nullptr));
   CKL(evt_attach_elementwise(nullptr));
+  CKL(evt_attach_dense_heads(nullptr));
   std::vector<uint64_t> all((size_t)2 * 16384);
   CK(cudaMemcpy(all.data(), n->evt, all.size() * 8, cudaMemcpyDeviceToHost));
   int32_t c = 0;
