@@ -91,6 +91,11 @@ struct DpBigArgs {
   long long arena_bytes, shadow_off, comm_offset;
   long long w1_offset, w1_count;    // dense1/w inside the arena, in floats (multiples of 4)
   float lr, decay, momentum, eps;
+  // pushed != 0: the peers' gradient slices were pushed into this rank's receive buffers by their dense1 wgrad epilogues
+  // (dense_tc.cu EpiWgradPush): [2 parities][world][per float4 in LL format] at bigrecv_off of the slab.  The reduce reads
+  // local memory only and needs no "gradient final" flags.
+  int pushed;
+  long long bigrecv_off;
 };
 
 // reduce-scatter + RMSProp + all-gather over float4 indices [lo, hi) of dense1/w, strided over the exchange CTAs.  The loop is
@@ -144,27 +149,107 @@ __device__ __forceinline__ void dp_big_loop(const DpBigArgs& d, long long lo, lo
   }
 }
 
+// one attempt at an LL float4: true when all four flags carry `flag`
+__device__ __forceinline__ bool dp_ll_try(const void* src, uint32_t flag, float4& v) {
+  uint32_t a0, f0, a1, f1, a2, f2, a3, f3;
+  asm volatile("ld.relaxed.sys.global.v4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(a0), "=r"(f0), "=r"(a1), "=r"(f1) : "l"(src) : "memory");
+  asm volatile("ld.relaxed.sys.global.v4.b32 {%0,%1,%2,%3}, [%4];\n" : "=r"(a2), "=r"(f2), "=r"(a3), "=r"(f3)
+               : "l"(static_cast<const uint8_t*>(src) + 16) : "memory");
+  v = make_float4(__uint_as_float(a0), __uint_as_float(a1), __uint_as_float(a2), __uint_as_float(a3));
+  return f0 == flag && f1 == flag && f2 == flag && f3 == flag;
+}
+
+// dp_big_loop with the peers' contributions taken from the LOCAL receive buffers they were pushed into (DpBigArgs::pushed)
+template <int W, int U>
+__device__ __forceinline__ void dp_big_loop_pushed(const DpBigArgs& d, long long lo, long long hi, long long first, long long stride) {
+  const long long base4 = d.w1_offset >> 2;
+  const float one_m_rho = 1.f - d.decay;
+  uint8_t* mine = d.peer[d.rank];
+  float4* w_own = reinterpret_cast<float4*>(mine) + base4;
+  float4* g_own = reinterpret_cast<float4*>(mine + d.arena_bytes) + base4;
+  float4* ms_own = reinterpret_cast<float4*>(mine + 2 * d.arena_bytes) + base4;
+  float4* mom_own = reinterpret_cast<float4*>(mine + 3 * d.arena_bytes) + base4;
+  const bool has_mom = d.momentum != 0.f;
+  constexpr int NW = W > 0 ? W : DP_WORLD_MAX;
+  const long long per = hi - lo > 0 ? ((d.w1_count >> 2) + d.world - 1) / d.world : 1;
+  const uint32_t flag = (uint32_t)d.step;
+  const uint8_t* recv = mine + d.bigrecv_off + (long long)(d.step & 1) * d.world * per * 32;
+  for (long long i0 = lo + first; i0 < hi; i0 += U * stride) {
+    float4 q[U][NW], w[U], ms[U];
+    bool ok[U][NW];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+#pragma unroll
+      for (int r = 0; r < NW; ++r) {
+        ok[u][r] = true;
+        q[u][r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < hi && (W > 0 || r < d.world)) {
+          if (r == d.rank) q[u][r] = dp_ld_f4(g_own + i);
+          else ok[u][r] = dp_ll_try(recv + ((long long)r * per + (i - lo)) * 32, flag, q[u][r]);
+        }
+      }
+      if (i < hi) { w[u] = w_own[i]; ms[u] = ms_own[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= hi) continue;
+#pragma unroll
+      for (int r = 0; r < NW; ++r)            // normally every contribution arrived long ago; otherwise wait for it (bounded)
+        if (!ok[u][r]) q[u][r] = dp_ll_load(recv + ((long long)r * per + (i - lo)) * 32, flag, mine + d.comm_offset + DPC_ERR);
+      float4 g = q[u][0];
+#pragma unroll
+      for (int r = 1; r < NW; ++r) { g.x += q[u][r].x; g.y += q[u][r].y; g.z += q[u][r].z; g.w += q[u][r].w; }   // rank order
+      float4 mo = has_mom ? mom_own[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#define GA3C_RMS(c)                                                          \
+  ms[u].c = d.decay * ms[u].c + one_m_rho * g.c * g.c;                       \
+  mo.c = d.momentum * mo.c + d.lr * g.c / sqrtf(ms[u].c + d.eps);            \
+  w[u].c -= mo.c;
+      GA3C_RMS(x) GA3C_RMS(y) GA3C_RMS(z) GA3C_RMS(w)
+#undef GA3C_RMS
+      ms_own[i] = ms[u];
+      if (has_mom) mom_own[i] = mo;
+      g_own[i] = g;                    // the reduced gradient of the owned slice (introspection)
+      const uint2 sh = make_uint2(pack_bf16(w[u].x, w[u].y), pack_bf16(w[u].z, w[u].w));
+      w_own[i] = w[u];
+#pragma unroll
+      for (int r = 0; r < NW; ++r)
+        if (W > 0 || r < d.world) reinterpret_cast<uint2*>(d.peer[r] + d.shadow_off)[i] = sh;
+    }
+  }
+}
+
 // The same exchange on a GROUP of `nthreads` threads of a block (thread t of the group, named barrier `bar_id`): the spare warps
 // of every conv backward CTA (conv_bwd_fused.cu) or half of every block of the tail kernel (dp_tail_kernel).  `cta` / `n_cta`:
 // index and number of the groups that share the work; last_smem: one int of shared memory.  Ends with the rank's "slice landed
 // everywhere" flag pushed by the last group to finish.  Waits with acquire loads, no fence between the two flag hops.
+template <bool PUSH_CAPABLE = true>      // false: compiled without the pushed-slices variant (leaner: the side-stream kernel)
 __device__ __forceinline__ void dp_big_group(const DpBigArgs& d, int t, int nthreads, int cta, int n_cta, int bar_id, int* last_smem,
                                              bool push_ready) {
   uint8_t* my_comm = d.peer[d.rank] + d.comm_offset;
+  const long long n4 = d.w1_count >> 2;
+  const long long per = (n4 + d.world - 1) / d.world;
+  const long long lo = per * d.rank, hi = lo + per < n4 ? lo + per : n4;
+  const long long stride = (long long)n_cta * nthreads, first = (long long)cta * nthreads + t;
+  if (PUSH_CAPABLE && d.pushed) {
+    // the peers' slices sit in this rank's receive buffers, every float4 carrying the step number: nothing to wait for here
+    if (d.world == 2) dp_big_loop_pushed<2, 4>(d, lo, hi, first, stride);
+    else if (d.world == 4) dp_big_loop_pushed<4, 2>(d, lo, hi, first, stride);
+    else if (d.world == 8) dp_big_loop_pushed<8, 1>(d, lo, hi, first, stride);
+    else dp_big_loop_pushed<0, 1>(d, lo, hi, first, stride);
+  } else {
   if (push_ready && cta == 0 && t < d.world) {
     __threadfence_system();
     dp_st_flag(d.peer[t] + d.comm_offset + DPC_BIGREADY + 64 * d.rank, d.step);
   }
   if (t < d.world) dp_wait_flag_acquire(my_comm + DPC_BIGREADY + 64 * t, d.step, my_comm + DPC_ERR, 4u);
   asm volatile("bar.sync %0, %1;\n" ::"r"(bar_id), "r"(nthreads) : "memory");
-  const long long n4 = d.w1_count >> 2;
-  const long long per = (n4 + d.world - 1) / d.world;
-  const long long lo = per * d.rank, hi = lo + per < n4 ? lo + per : n4;
-  const long long stride = (long long)n_cta * nthreads, first = (long long)cta * nthreads + t;
   if (d.world == 2) dp_big_loop<2, 4>(d, lo, hi, first, stride);
   else if (d.world == 4) dp_big_loop<4, 2>(d, lo, hi, first, stride);
   else if (d.world == 8) dp_big_loop<8, 1>(d, lo, hi, first, stride);
   else dp_big_loop<0, 1>(d, lo, hi, first, stride);
+  }
   asm volatile("bar.sync %0, %1;\n" ::"r"(bar_id), "r"(nthreads) : "memory");
   if (t == 0) {
     __threadfence_system();            // cumulative over the group's peer stores (observed through the barrier)

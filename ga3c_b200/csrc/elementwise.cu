@@ -668,7 +668,7 @@ __device__ __forceinline__ void dp_small_phase2(const RmsPropDpArgs& d, int64_t 
 }
 
 template <bool HAS_MOM>
-__global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_small_kernel(RmsPropDpArgs d, int64_t recv_offset) {
+__global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_small_kernel(RmsPropDpArgs d, int64_t recv_offset, int wait_big) {
   __shared__ float4 part[GR_LANES][GR_COLS];
   EvtLog evt_i = evt_open();
   DpSmallState st;
@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) dp_small_kernel(RmsPropDpA
   dp_small_phase1<HAS_MOM>(d, recv_offset, blockIdx.x, true, K_RMSPROP, evt_i, st, part);
   dp_small_phase2<HAS_MOM>(d, recv_offset, evt_i, st, false);
   evt_mark(evt_i, 64, 0);
-  if (blockIdx.x == 0 && (int)threadIdx.x < d.world) {
+  if (wait_big && blockIdx.x == 0 && (int)threadIdx.x < d.world) {     // (the side-stream exchange waits for the slices itself)
     dp_wait_flag(my_comm + DPC_BIGDONE + 64 * threadIdx.x, d.step, my_comm + DPC_ERR, 16u);
     __threadfence_system();
   }
@@ -794,6 +794,56 @@ __global__ void __launch_bounds__(512) dp_tail_kernel(RmsPropDpArgs d, DpBigArgs
   trace_mark(K_RMSPROP, 2);
 }
 
+// ---- the dense1/w exchange as a kernel of its own, on a side stream (GA3C_DP_EXCHANGE=side, the default) -------------------------
+// 128-thread blocks without shared memory: small enough to be resident NEXT TO the conv backward CTAs of this step and the conv
+// forward CTAs of the next one (both leave ~12 K registers and 1,500 thread slots per SM), so the whole chain of NVLink latencies
+// -- wait for every rank's "dense_bwd done" flag, pull the slices, RMSProp, push the bf16 shadow, fence, "slice landed" flags, wait
+// for every rank's -- runs under kernels that do not depend on it.  The next launch that reads the shadow (dense_fwd) waits for
+// this kernel's completion event; block 0 ends only when every rank's slice has landed in THIS rank's slab.
+// By default it is launched behind an event recorded after dense_bwd (its own gradient is final by stream order) and publishes
+// that to the peers itself: it then only ever waits for OTHER GPUs, never for a kernel of its own GPU that might not find room
+// on an SM next to it (a spinning kernel that waits for a kernel it keeps from being resident is a deadlock).
+__global__ void __launch_bounds__(128, 6) dp_big_side_kernel(DpBigArgs big, int push_ready) {      // <= 85 registers: 11 K per block
+  trace_mark(K_DP_BIG, 0);
+  int dp_last = 0;      // thread 0's only.  NO shared memory: next to a conv CTA an SM has room for the reserved 1 KB of a block and no more
+  dp_big_group<false>(big, (int)threadIdx.x, 128, (int)blockIdx.x, (int)gridDim.x, 1, &dp_last, push_ready != 0);
+  __syncthreads();
+  trace_mark(K_DP_BIG, 1);             // (trace row of this kernel: first/last block started, own slice done, all slices landed)
+  uint8_t* my_comm = big.peer[big.rank] + big.comm_offset;
+  if (blockIdx.x == 0 && (int)threadIdx.x < big.world)
+    dp_wait_flag_acquire(my_comm + DPC_BIGDONE + 64 * threadIdx.x, big.step, my_comm + DPC_ERR, 16u);
+  if (blockIdx.x == 0) {
+    __syncthreads();
+    trace_mark(K_DP_BIG, 2);
+  }
+}
+int launch_dp_big_side(const DpBigArgs& big, bool push_ready, int num_sms, cudaStream_t side_stream) {
+  int grid = num_sms;
+  if (const char* e = getenv("GA3C_DP_SIDE_CTAS")) {     // tests with several ranks on one GPU leave room for the other ranks' kernels
+    const int g = atoi(e);
+    if (g >= 1 && g <= grid) grid = g;
+  }
+  dp_big_side_kernel<<<grid, 128, 0, side_stream>>>(big, push_ready ? 1 : 0);
+  return (int)cudaGetLastError();
+}
+
+// a rank with no rows this step (ga3c_train_step with batch 0) pushes ZERO gradient slices, so that the owners' reduce finds a
+// contribution from every rank in its receive buffers
+__global__ void __launch_bounds__(256) dp_push_zero_kernel(WgradPush push, long long n4) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += stride) {
+    const int q = (int)(i4 / push.per4);
+    if (q == push.rank) continue;
+    dp_ll_store(push.peer[q] + push.recv_off + (((long long)(push.flag & 1u) * push.world + push.rank) * push.per4 + (i4 - (long long)q * push.per4)) * 32,
+                zero, push.flag);
+  }
+}
+int launch_dp_push_zero(const WgradPush& push, long long n4, cudaStream_t stream) {
+  dp_push_zero_kernel<<<148, 256, 0, stream>>>(push, n4);
+  return (int)cudaGetLastError();
+}
+
 // CUDA loads a kernel lazily at its first launch, and that load can wait for running kernels to finish.  A rank whose
 // exchange CTAs are already spinning on a peer would then block the very launch the peer needs (ranks that share a
 // process), so every kernel of the exchange is loaded when the ranks attach.
@@ -802,18 +852,19 @@ int configure_dp() {
   int r;
   if ((r = (int)cudaFuncGetAttributes(&a, dp_small_kernel<false>))) return r;
   if ((r = (int)cudaFuncGetAttributes(&a, dp_small_kernel<true>))) return r;
+  if ((r = (int)cudaFuncGetAttributes(&a, dp_big_side_kernel))) return r;
   if ((r = (int)cudaFuncGetAttributes(&a, dp_tail_kernel<false>))) return r;
   if ((r = (int)cudaFuncGetAttributes(&a, dp_tail_kernel<true>))) return r;
   if ((r = (int)cudaFuncGetAttributes(&a, rmsprop_dp_kernel<false>))) return r;
   return (int)cudaFuncGetAttributes(&a, rmsprop_dp_kernel<true>);
 }
 
-int launch_dp_small(const RmsPropDpArgs& d, int64_t recv_offset, cudaStream_t stream) {
+int launch_dp_small(const RmsPropDpArgs& d, int64_t recv_offset, cudaStream_t stream, bool wait_big) {
   const int n_cb = (d.red.n_floats / 4 + GR_COLS - 1) / GR_COLS;
   if (n_cb > DP_MAX_CB || !d.has_red) return (int)cudaErrorInvalidValue;
   if (d.base.momentum != 0.f)
-    return launch_pdl(dp_small_kernel<true>, dim3(n_cb), dim3(GR_LANES * GR_COLS), 0, stream, d, recv_offset);
-  return launch_pdl(dp_small_kernel<false>, dim3(n_cb), dim3(GR_LANES * GR_COLS), 0, stream, d, recv_offset);
+    return launch_pdl(dp_small_kernel<true>, dim3(n_cb), dim3(GR_LANES * GR_COLS), 0, stream, d, recv_offset, wait_big ? 1 : 0);
+  return launch_pdl(dp_small_kernel<false>, dim3(n_cb), dim3(GR_LANES * GR_COLS), 0, stream, d, recv_offset, wait_big ? 1 : 0);
 }
 
 

@@ -48,8 +48,16 @@ int launch_dense_dgrad_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint1
                           cudaStream_t stream);       // dn2 in the G operand layout (common.cuh), borders untouched
 int launch_dense_wgrad_tc(const uint16_t* n2, const uint16_t* dd1, float* g_w1, int batch, cudaStream_t stream);
 // dgrad + wgrad tiles in one grid (both only need dd1): the single-GPU / fused-DP step uses this one
+// data parallel, exchange at the end of the step: where the dense1/w gradient tiles push the slices this rank does not own
+// (dense_tc.cu EpiWgradPush; receive buffers [2 parities][world][per4 float4 in LL format] at recv_off of every slab)
+struct WgradPush {
+  uint8_t* peer[8];
+  int rank, world;
+  long long per4, recv_off;
+  unsigned int flag;         // the step number; parity = flag & 1
+};
 int launch_dense_bwd_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint8_t* dn2, float* g_w1, int batch,
-                        cudaStream_t stream);
+                        const WgradPush* push, cudaStream_t stream);
 
 // heads.cu -- value / policy heads, softmax, A3C loss and its backward (NetworkVP_discrate.py:60-85)
 struct HeadsArgs {
@@ -179,9 +187,13 @@ int launch_rmsprop_dp(const RmsPropDpArgs& a, int num_sms, cudaStream_t stream);
 // second instalment of the overlapped exchange (dp_exchange.cuh): slab reduction of the small tensors, LL push into every
 // rank's receive buffer, identical RMSProp on every rank; returns only when every rank's dense1/w slice has landed.
 // a.red is required; recv_offset: byte offset in the slab of the receive buffers [2][DP_MAX_WORLD][small prefix * 8 B].
-int launch_dp_small(const RmsPropDpArgs& a, int64_t recv_offset, cudaStream_t stream);
+// wait_big: block 0 also holds the launch open until every rank's dense1/w slice has landed (the overlapped modes)
+int launch_dp_small(const RmsPropDpArgs& a, int64_t recv_offset, cudaStream_t stream, bool wait_big);
 // the whole exchange in one launch at the end of the step (default): small tensors as launch_dp_small, dense1/w on every SM
 int launch_dp_tail(const RmsPropDpArgs& a, const DpBigArgs& big, int64_t recv_offset, int num_sms, cudaStream_t stream);
+// the dense1/w exchange alone, on a side stream, resident next to the conv kernels (elementwise.cu dp_big_side_kernel)
+int launch_dp_big_side(const DpBigArgs& big, bool push_ready, int num_sms, cudaStream_t side_stream);
+int launch_dp_push_zero(const WgradPush& push, long long n4, cudaStream_t stream);   // a rank without rows: zero slices to the owners
 int configure_dp();     // load the exchange kernels now (not lazily at their first launch)
 int launch_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, cudaStream_t stream);
 int launch_returns(const double* rewards, const int64_t* seg_offsets, int n_segments, const double* terminal,

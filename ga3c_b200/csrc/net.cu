@@ -54,7 +54,9 @@ struct ga3c_net {
   bool dp_ipc[DP_MAX_WORLD] = {};        // mapped with cudaIpcOpenMemHandle (to be closed on detach)
   uint64_t dp_step = 0;
   int dp_exch = 20;                // overlapped exchange: exchange CTAs appended to the conv backward launch (GA3C_DP_EXCH_CTAS)
-  int dp_exchange = 0;             // GA3C_DP_EXCHANGE: 0 "tail" (default: one launch on every SM at the end of the step), 3 "warps" (the
+  int dp_exchange = 4;             // GA3C_DP_EXCHANGE: 4 "side" (default: dense1/w exchanged by a small-footprint kernel on a side stream
+                                   // that is resident next to the conv backward of this step and the conv forward of the next;
+                                   // small tensors in dp_small), 0 "tail" (one launch on every SM at the end of the step), 3 "warps" (the
                                    // dense1/w exchange on the optimizer warps of every conv backward CTA, small tensors + completion
                                    // in dp_small), 1 "overlap" (exchange CTAs inside the conv backward launch + dp_small), 2
                                    // "single" (the first version: one kernel that also broadcasts the fp32 weights).  Measured at 2
@@ -68,6 +70,15 @@ struct ga3c_net {
                                    // step 0.1015 -> 0.1032 ms: the conv backward is HBM-bound, the 22 MB cost what they cost alone
   int cur_exch = 0;                // ... of the step being enqueued (0 outside the overlapped data-parallel step)
   int64_t xbuf_off = 0, comm_off = 0;    // byte offsets in the slab: LL receive buffers [2][8][small prefix * 8 B], comm block
+  int64_t bigrecv_off = 0;               // ... and the LL receive buffers of the pushed dense1/w gradient slices [2][(n4 + 8) * 32 B]
+  int dp_push = 0;                       // GA3C_DP_PUSH=1 (with GA3C_DP_EXCHANGE=tail): slices pushed by the dense1 wgrad epilogues in the
+                                         // LL format instead of pulled by their owners.  Measured at 2 GPUs: 0.1463 vs 0.1181 ms per
+                                         // step -- scattered 16-byte stores across NVLink from the GEMM epilogue triple its time
+  cudaStream_t dp_stream = nullptr;      // GA3C_DP_EXCHANGE=side: the dense1/w exchange runs here, next to the conv kernels
+  cudaEvent_t dp_big_done = nullptr;     // ... and whatever reads the dense1/w shadow next waits for this
+  bool dp_big_pending = false;
+  cudaEvent_t dp_grad_ready = nullptr;   // recorded behind dense_bwd: the side stream waits for it
+  const DpBigArgs* dp_side = nullptr;    // set while a side-mode step is enqueued: fb_tail_impl launches the exchange behind dense_bwd
   // workspace
   uint16_t *n2 = nullptr, *dd1 = nullptr, *dn1 = nullptr;
   // training-only activations, stored in the UMMA operand layouts the conv backward consumes (common.cuh); their zero borders /
@@ -164,7 +175,8 @@ extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
   const size_t shadow_bytes = (size_t)FLAT * FC * 2;
   n->xbuf_off = (int64_t)(4 * ab + shadow_bytes);
   n->comm_off = n->xbuf_off + 2 * (int64_t)DP_MAX_WORLD * n->small_floats * 8;
-  n->slab_bytes = (size_t)n->comm_off + DP_COMM_BYTES;
+  n->bigrecv_off = (n->comm_off + DP_COMM_BYTES + 127) / 128 * 128;
+  n->slab_bytes = (size_t)n->bigrecv_off + 2 * ((size_t)FLAT * FC / 4 + DP_MAX_WORLD) * 32;
   GA3C_ALLOC(n->slab, n->slab_bytes);
 #undef GA3C_ALLOC
   n->w = reinterpret_cast<float*>(n->slab);
@@ -368,6 +380,13 @@ static HeadsArgs heads_args(ga3c_net* n, int batch, int splits) {
   return h;
 }
 
+// data parallel, side-stream exchange: the bf16 shadow of dense1/w is complete when the exchange kernel of the previous step is
+static int wait_dp_big(ga3c_net* n, cudaStream_t st) {
+  // (not cleared: predict and train may come on different streams, and each of them has to see the exchange complete)
+  if (n->dp_big_pending) CK(cudaStreamWaitEvent(st, n->dp_big_done, 0));
+  return 0;
+}
+
 // dense1 forward + heads in one cluster launch (dense_heads.cu) while its slabs fit the gradient-partial workspace
 static bool fused_heads(const ga3c_net* n, int batch) {
   return n->fuse_heads && !n->cfg.dual_rmsprop && dense_heads_ctas(batch) <= 2 * n->num_sms;
@@ -381,6 +400,7 @@ static int predict_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, fl
   const float* w = n->w;
   LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, x_u8, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
                                             w + n->off(P_C12B), nullptr, nullptr, n->n2, batch, n->num_sms, st));
+  if (int r = wait_dp_big(n, st)) return r;
   const int splits = dense_fwd_splits(batch, n->num_sms);
   HeadsArgs h = heads_args(n, batch, splits);
   h.p_out = p_out; h.v_out = v_out; h.train = 0;
@@ -418,6 +438,7 @@ static int fb_head_impl(ga3c_net* n, const void* x, bool x_u8, const float* yr, 
   if (!skip_forward) {        // the second DUAL_RMSPROP pass reuses n1 / n2 / the dense1 partials of the first
     LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, x_u8, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
                                               w + n->off(P_C12B), n->n1, n->xblk, n->n2, batch, n->num_sms, st));
+    if (int r = wait_dp_big(n, st)) return r;
     if (!fused) LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
   }
   HeadsArgs h = heads_args(n, batch, splits);
@@ -452,6 +473,16 @@ static GradReduceArgs reduce_args(ga3c_net* n, int batch, float* g_dst = nullptr
 
 // dense1 data gradient and the two conv backward kernels; with `reduce` the slabs are summed into the gradient arena
 // (conv11/*, conv12/*, dense1/b, heads, loss sums), otherwise the caller does it (fused with RMSProp).
+static WgradPush wgrad_push(const ga3c_net* n, uint64_t step) {
+  WgradPush p{};
+  for (int r = 0; r < n->dp_world; ++r) p.peer[r] = n->dp_peer[r];
+  p.rank = n->dp_rank; p.world = n->dp_world;
+  p.per4 = ((long long)FLAT * FC / 4 + n->dp_world - 1) / n->dp_world;
+  p.recv_off = n->bigrecv_off;
+  p.flag = (unsigned int)step;
+  return p;
+}
+
 static int fb_tail_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, void* stream, bool with_wgrad, bool reduce,
                         const DpBigArgs* dp = nullptr, float* g_dst = nullptr, const ConvBwdOpt* opt = nullptr) {
   if (int r = check_batch(n, batch, "ga3c_fb_tail")) return r;
@@ -461,10 +492,23 @@ static int fb_tail_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, vo
   cudaStream_t st = (cudaStream_t)stream;
   const float* w = n->w;
   float* gp = n->gpart;
-  if (with_wgrad)   // dgrad + wgrad tiles of dense1 in one grid
-    LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_bwd_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, (g_dst ? g_dst : n->g) + n->off(P_D1W), batch, st));
-  else
+  if (with_wgrad) {   // dgrad + wgrad tiles of dense1 in one grid
+    WgradPush push{};
+    const bool pushed = dp != nullptr && dp->pushed;
+    if (pushed) push = wgrad_push(n, dp->step);
+    LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_bwd_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, (g_dst ? g_dst : n->g) + n->off(P_D1W), batch,
+                                                     pushed ? &push : nullptr, st));
+  } else
     LAUNCH(n, K_DENSE_DGRAD, st, launch_dense_dgrad_tc(n->dd1, n->w1_shadow, n->n2, n->dn2, batch, st));
+  if (n->dp_side != nullptr) {
+    // side-stream exchange of dense1/w: its gradient is final behind this point of the stream
+    CK(cudaEventRecord(n->dp_grad_ready, st));
+    CK(cudaStreamWaitEvent(n->dp_stream, n->dp_grad_ready, 0));
+    CKL(launch_dp_big_side(*n->dp_side, true, n->num_sms, n->dp_stream));
+    n->log.launches++;
+    CK(cudaEventRecord(n->dp_big_done, n->dp_stream));
+    n->dp_big_pending = true;
+  }
   LAUNCH(n, K_CONV12_BWD, st, launch_conv_bwd(n->xblk, n->n1, n->dn2, w + n->off(P_C12W), n->keep_dn1 ? n->dn1 : nullptr,
                                               gp + n->off(P_C11W), gp + n->off(P_C11B), gp + n->off(P_C12W),
                                               gp + n->off(P_C12B), n->gp_stride, batch, n->num_sms, x_u8, opt ? *opt : ConvBwdOpt{}, dp, st));
@@ -560,6 +604,13 @@ extern "C" int ga3c_dp_export(ga3c_net* n, void* handle_out) {
 
 extern "C" int ga3c_dp_detach(ga3c_net* n) {
   if (!n) return 0;
+  if (n->dp_stream) {
+    cudaStreamSynchronize(n->dp_stream);
+    cudaStreamDestroy(n->dp_stream);
+    cudaEventDestroy(n->dp_big_done);
+    cudaEventDestroy(n->dp_grad_ready);
+    n->dp_stream = nullptr; n->dp_big_done = nullptr; n->dp_big_pending = false;
+  }
   for (int r = 0; r < DP_MAX_WORLD; ++r)
     if (n->dp_peer[r] && n->dp_ipc[r]) cudaIpcCloseMemHandle(n->dp_peer[r]);
   for (int r = 0; r < DP_MAX_WORLD; ++r) { n->dp_peer[r] = nullptr; n->dp_ipc[r] = false; }
@@ -615,19 +666,29 @@ extern "C" int ga3c_dp_attach_local(ga3c_net* n, int32_t rank, int32_t world, ga
 
 static int dp_attach_finish(ga3c_net* n, int32_t rank, int32_t world) {
   n->dp_rank = rank; n->dp_world = world; n->dp_step = 0;
-  n->dp_exchange = 0;
+  n->dp_exchange = 4;
   if (const char* e = getenv("GA3C_DP_EXCHANGE")) {
     const std::string m(e);
-    if (m == "warps") n->dp_exchange = 3;
+    if (m == "side") n->dp_exchange = 4;
+    else if (m == "warps") n->dp_exchange = 3;
     else if (m == "tail") n->dp_exchange = 0;
     else if (m == "overlap") n->dp_exchange = 1;
     else if (m == "single") n->dp_exchange = 2;
-    else return fail_msg("GA3C_DP_EXCHANGE must be warps, tail, overlap or single");
+    else return fail_msg("GA3C_DP_EXCHANGE must be side, warps, tail, overlap or single");
   }
+  if (const char* e = getenv("GA3C_DP_PUSH")) n->dp_push = atoi(e) != 0;
   if (const char* e = getenv("GA3C_DP_EXCH_CTAS")) n->dp_exch = atoi(e);
   if (n->dp_exch < 1 || n->dp_exch > n->num_sms / 2) n->dp_exch = 20;
   CK(cudaMemset(n->slab + n->xbuf_off, 0, n->slab_bytes - (size_t)n->xbuf_off));
   CKL(configure_dp());
+  if (!n->dp_stream) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    CK(cudaStreamCreateWithPriority(&n->dp_stream, cudaStreamNonBlocking, hi));
+    CK(cudaEventCreateWithFlags(&n->dp_big_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&n->dp_grad_ready, cudaEventDisableTiming));
+  }
+  n->dp_big_pending = false;
   return 0;
 }
 
@@ -692,6 +753,8 @@ static DpBigArgs dp_big_args(ga3c_net* n, float lr, int n_exch) {
   b.arena_bytes = (int64_t)n->arena_floats * 4; b.shadow_off = 4 * b.arena_bytes; b.comm_offset = n->comm_off;
   b.w1_offset = n->off(P_D1W); b.w1_count = (int64_t)FLAT * FC;
   b.lr = lr; b.decay = n->cfg.rmsprop_decay; b.momentum = n->cfg.rmsprop_momentum; b.eps = n->cfg.rmsprop_epsilon;
+  b.pushed = n->dp_exchange == 0 && n->dp_push;       // exchange at the end of the step: slices pushed by the wgrad epilogues
+  b.bigrecv_off = n->bigrecv_off;
   return b;
 }
 static RmsPropDpArgs dp_small_args(ga3c_net* n, float lr, int batch, const DpBigArgs& b) {
@@ -716,10 +779,30 @@ static int train_step_empty(ga3c_net* n, float lr, float* loss, void* stream) {
   n->gp_heads_grid = 0;
   n->loss_out = loss;
   n->last_batch = 0;
+  if (n->dp_exchange == 4) {          // side-stream exchange: it publishes "gradient final" itself; dp_small with zero slabs
+    CK(cudaMemsetAsync(n->g + n->off(P_D1W), 0, (size_t)FLAT * FC * 4, st));
+    DpBigArgs b = dp_big_args(n, lr, 0);
+    b.pushed = 0;
+    n->cur_exch = 0;
+    CK(cudaEventRecord(n->dp_grad_ready, st));                    // the zeroed gradient is in place
+    CK(cudaStreamWaitEvent(n->dp_stream, n->dp_grad_ready, 0));
+    CKL(launch_dp_big_side(b, true, n->num_sms, n->dp_stream));
+    n->log.launches++;
+    CK(cudaEventRecord(n->dp_big_done, n->dp_stream));
+    n->dp_big_pending = true;
+    const RmsPropDpArgs d = dp_small_args(n, lr, 0, b);
+    LAUNCH(n, K_RMSPROP, st, launch_dp_small(d, n->xbuf_off, st, false));
+    n->global_step += 1;
+    return 0;
+  }
   if (n->dp_exchange == 0 || n->dp_exchange == 3) {   // nothing but the exchange launch (dp_tail: both instalments); it publishes "gradient final"
     CK(cudaMemsetAsync(n->g + n->off(P_D1W), 0, (size_t)FLAT * FC * 4, st));
     const DpBigArgs b = dp_big_args(n, lr, 0);
     n->cur_exch = 0;
+    if (b.pushed) {
+      CKL(launch_dp_push_zero(wgrad_push(n, b.step), (long long)FLAT * FC / 4, st));
+      n->log.launches++;
+    }
     const RmsPropDpArgs d = dp_small_args(n, lr, 0, b);    // zero slabs in every segment: the sums are 0
     LAUNCH(n, K_RMSPROP, st, launch_dp_tail(d, b, n->xbuf_off, n->num_sms, st));
     n->global_step += 1;
@@ -735,7 +818,7 @@ static int train_step_empty(ga3c_net* n, float lr, float* loss, void* stream) {
                                                 gp + n->off(P_C12B), n->gp_stride, 0, n->num_sms, false, ConvBwdOpt{}, &b, st));
     const RmsPropDpArgs d = dp_small_args(n, lr, 0, b);
     n->cur_exch = 0;
-    LAUNCH(n, K_RMSPROP, st, launch_dp_small(d, n->xbuf_off, st));
+    LAUNCH(n, K_RMSPROP, st, launch_dp_small(d, n->xbuf_off, st, true));
     n->global_step += 1;
     return 0;
   }
@@ -757,6 +840,24 @@ static int train_step_impl(ga3c_net* n, const void* x, bool x_u8, const float* y
     if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, true)) return r;
     return apply_rmsprop_impl(n, lr, stream, nullptr);
   }
+  if (n->dp_world > 1 && n->dp_exchange == 4) {
+    // default: the conv backward keeps every SM; the exchange of dense1/w is launched behind dense_bwd on the side stream and
+    // runs next to it (and next to the conv forward of the following step); dp_small follows the conv
+    // backward on this stream with the small tensors.  dense_fwd of the next call waits for the exchange's completion event.
+    DpBigArgs b = dp_big_args(n, lr, 0);
+    b.pushed = 0;
+    n->cur_exch = 0;
+    // (launched behind an event after dense_bwd, NOT on a flag the conv backward would publish: at batch >= 148 a spinning side
+    //  grid that got its blocks resident first kept conv_bwd CTA 0 -- the publisher -- off its SM, and the step timed out)
+    n->dp_side = &b;
+    const int r = fb_tail_impl(n, x, x_u8, batch, stream, true, false);
+    n->dp_side = nullptr;
+    if (r) return r;
+    RmsPropDpArgs d = dp_small_args(n, lr, batch, b);
+    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_dp_small(d, n->xbuf_off, (cudaStream_t)stream, false));
+    n->global_step += 1;
+    return 0;
+  }
   if (n->dp_world > 1 && n->dp_exchange == 3) {
     // default: the dense1/w exchange rides on the optimizer warps of the conv backward CTAs (all SMs keep computing conv
     // gradients); dp_small follows with the small tensors and holds the step open until every rank's slice has landed
@@ -766,7 +867,7 @@ static int train_step_impl(ga3c_net* n, const void* x, bool x_u8, const float* y
     opt.mode = 2;
     if (int r = fb_tail_impl(n, x, x_u8, batch, stream, true, false, &b, nullptr, &opt)) return r;
     const RmsPropDpArgs d = dp_small_args(n, lr, batch, b);
-    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_dp_small(d, n->xbuf_off, (cudaStream_t)stream));
+    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_dp_small(d, n->xbuf_off, (cudaStream_t)stream, true));
     n->global_step += 1;
     return 0;
   }
@@ -790,7 +891,7 @@ static int train_step_impl(ga3c_net* n, const void* x, bool x_u8, const float* y
     const RmsPropDpArgs d = dp_small_args(n, lr, batch, b);
     n->cur_exch = 0;
     if (r) return r;
-    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_dp_small(d, n->xbuf_off, (cudaStream_t)stream));
+    LAUNCH(n, K_RMSPROP, (cudaStream_t)stream, launch_dp_small(d, n->xbuf_off, (cudaStream_t)stream, true));
     n->global_step += 1;
     return 0;
   }

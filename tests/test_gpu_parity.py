@@ -158,11 +158,12 @@ def test_log_softmax_knob(ga3c):
     assert np.allclose(p.sum(axis=1), 1.0, atol=1e-5)
 
 
-@pytest.mark.parametrize("exchange", ["warps", "tail", "overlap"])
+@pytest.mark.parametrize("exchange", ["side", "tail", "warps", "overlap"])
 def test_data_parallel_exchange_two_ranks_on_one_gpu(ga3c, monkeypatch, exchange):
-    """The fused data-parallel step (dp_exchange.cuh; "warps", the default: dense1/w exchanged by the optimizer warps of every
-    conv backward CTA, LL push of the small tensors afterwards; "tail": the whole exchange in one launch at the end of the
-    step; "overlap": dense1/w on extra exchange CTAs of the conv backward launch) with BOTH ranks on one device: two handles attached to each other with ga3c_dp_attach_local, each on its
+    """The fused data-parallel step (dp_exchange.cuh; "side", the default: dense1/w exchanged by a small-footprint kernel on a
+    side stream next to the conv kernels, LL push of the small tensors after the conv backward; "tail": the whole exchange in
+    one launch at the end of the step; "warps": dense1/w on the optimizer warps of every conv backward CTA; "overlap": on extra
+    exchange CTAs of the conv backward launch) with BOTH ranks on one device: two handles attached to each other with ga3c_dp_attach_local, each on its
     own stream, each training on its row shard.  After 3 steps the replicas are bit-identical and equal the oracle's
     single-process steps on the concatenated batch (what a single ThreadTrainer would have computed).  The grids are small
     (12 rows per rank), so both ranks' kernels are resident together; every cross-rank wait is bounded, so a scheduling
@@ -173,6 +174,7 @@ def test_data_parallel_exchange_two_ranks_on_one_gpu(ga3c, monkeypatch, exchange
     monkeypatch.setenv("GA3C_DP_EXCHANGE", exchange)
     monkeypatch.setenv("GA3C_DP_EXCH_CTAS", "4")
     monkeypatch.setenv("GA3C_DP_TAIL_CTAS", "8")      # both ranks share this GPU: leave SMs for the other rank's conv kernels
+    monkeypatch.setenv("GA3C_DP_SIDE_CTAS", "8")
     world, b = 2, 12
     rng = np.random.default_rng(17)
     params = onp.init_params(rng, 6)
