@@ -113,6 +113,9 @@ SIGNATURES = {
     "ga3c_mlp_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,
                                       C.c_void_p, C.c_void_p]),
     "ga3c_mlp_launch_count": (C.c_int64, [C.c_void_p]),
+    "ga3c_mlp_workspace_ptr": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
+    "ga3c_debug_tf32x3_gemm": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "ga3c_mlp_timing_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "ga3c_mlp_timing_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
 }

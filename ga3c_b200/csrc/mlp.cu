@@ -194,17 +194,22 @@ __global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, cons
     const int row0 = tile * TM;
     __syncthreads();                       // the previous tile is fully consumed (and Wh / hb are staged)
     {
-      const int Sp = round_up16(S);
+      // the tile's input: x, or (tensor-core mode, MlpStepArgs::phase) what the GEMM launches before this one left in HBM
+      const float* src = s.phase == 2 ? s.act[s.tc_hi - 1] : s.phase == 3 ? s.dz[s.tc_lo - 1] : s.x;
+      const int W = s.phase == 2 ? net.L[s.tc_hi - 1].n : s.phase == 3 ? net.L[s.tc_lo - 1].n : S;
+      const int Sp = round_up16(W);
       for (int idx = tid; idx < TM * Sp; idx += FT) {
         const int r = idx / Sp, c = idx - r * Sp;
-        buf0[r * LD + c] = (row0 + r < B && c < S) ? s.x[(size_t)(row0 + r) * S + c] : 0.f;
+        buf0[r * LD + c] = (row0 + r < B && c < W) ? src[(size_t)(row0 + r) * W + c] : 0.f;
       }
     }
     float* cur = buf0;
     float* nxt = buf1;
+    const int l_first = s.phase == 2 ? s.tc_hi : 0;                 // forward layers [l_first, l_end)
+    const int l_end = s.phase == 1 ? s.tc_lo : s.phase == 3 ? 0 : NL;
 
     // ---- forward: out_l = act(in_l W_l + b_l)  (NetworkVP.py:194-210) ----
-    for (int l = 0; l < NL; ++l) {
+    for (int l = l_first; l < l_end; ++l) {
       const MlpLayerDesc L = net.L[l];
       const float* bias = s.w + L.b_off;
       float* out_g = TRAIN ? s.act[l] : nullptr;
@@ -225,6 +230,8 @@ __global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, cons
       else tile_pass<false, 1, RT>(cur, nxt, Wc, L.k, s.w + L.w_off, L.n, L.n, epi);
       float* t = cur; cur = nxt; nxt = t;
     }
+    if (s.phase == 1) continue;            // the wide layers follow as GEMM launches
+    if (s.phase != 3) {
     __syncthreads();                       // h = cur[64][hid] is complete
 
     // ---- head logits: thread (row, jq) sums columns jq, jq + TPR, ... of h Wh ----
@@ -388,9 +395,12 @@ __global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, cons
       }
     }
     { float* t = cur; cur = nxt; nxt = t; }
+    }   // phase != 3
 
     // ---- data-gradient chain: dz_{l-1} = (dz_l W_l^T) * act'(out_{l-1}) ----
-    for (int l = NL - 1; l >= 1; --l) {
+    const int l_top = s.phase == 3 ? s.tc_lo - 1 : NL - 1;          // the chain starts from dz[l_top] (in `cur`) ...
+    const int l_stop = s.phase == 2 ? (s.tc_hi > 1 ? s.tc_hi : 1) : 1;   // ... and ends with dz[l_stop - 1]
+    for (int l = l_top; l >= l_stop; --l) {
       const MlpLayerDesc L = net.L[l];
       const MlpLayerDesc Lp = net.L[l - 1];
       const float* out_prev = s.act[l - 1];
@@ -437,6 +447,7 @@ __global__ void __launch_bounds__(NT) mlp_wgrad_kernel(const MlpNet net, const M
     t -= tk * tn;
   }
   if (l > NL) return;
+  if (l >= s.tc_lo && l < s.tc_hi) return;          // tensor-core mode: this layer's dW / db come from mlp_tc.cu
   const int k0 = (t / tn) * WT, n0 = (t % tn) * WT;
   const float* in = l == 0 ? s.x : s.act[l - 1];
   const int ld_in = K;
@@ -583,8 +594,8 @@ int mlp_wgrad_splits(const MlpNet& net, int batch, int num_sms) {
 }
 
 int launch_mlp_wgrad(const MlpNet& net, const MlpStepArgs& args, float* part, int64_t part_stride, int splits,
-                     cudaStream_t stream) {
-  int rows = (args.batch + splits - 1) / splits;
+                     cudaStream_t stream, int rows_per_split) {
+  int rows = rows_per_split > 0 ? rows_per_split : (args.batch + splits - 1) / splits;
   rows = (rows + RC - 1) / RC * RC;
   const dim3 grid(total_wgrad_tiles(net), splits);
   return launch_pdl(mlp_wgrad_kernel, grid, dim3(NT), 0, stream, net, args, part, part_stride, rows);

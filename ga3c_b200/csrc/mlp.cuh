@@ -10,7 +10,7 @@ constexpr int MLP_MAX_WIDTH = 256;    // of any layer and of the state
 constexpr int MLP_MAX_HID = 128;      // width of the last hidden layer (the one the heads read)
 constexpr int MLP_MAX_OUT = 1 + 2 * 18;
 constexpr int MLP_TM = 64;            // batch rows per tile
-constexpr int MLP_MAX_SPLITS = 32;    // batch splits of the weight-gradient pass (partial arenas)
+constexpr int MLP_MAX_SPLITS = 64;    // batch splits of the weight-gradient pass (partial arenas)
 constexpr int MLP_ACT_LINEAR = 0, MLP_ACT_SIGMOID = 1;
 constexpr int MLP_KIND_FORK_VP = 0, MLP_KIND_DISCRATE = 1;
 
@@ -46,6 +46,10 @@ struct MlpStepArgs {
   float* dz[MLP_MAX_LAYERS];            // train: gradients w.r.t. the pre-activations [B, n_l]
   float* dlogits;                       // train: [B, n_out_ld]
   float* loss_part;                     // train: [tiles][4] (cost_p_1, cost_p_2, cost_v, 0) per batch tile (mlp_tile_rows)
+  // Tensor-core mode (mlp_tc.cu): the wide layers [tc_lo, tc_hi) run as 3xTF32 GEMM launches between three launches of the fused
+  // kernel.  phase 0: everything (tc_lo = tc_hi = 0).  phase 1: x -> layers [0, tc_lo).  phase 2: act[tc_hi - 1] -> layers
+  // [tc_hi, n_layers), heads, loss, data gradients down to dz[tc_hi - 1].  phase 3: dz[tc_lo - 1] -> data gradients down to dz[0].
+  int phase, tc_lo, tc_hi;
 };
 
 int configure_mlp();
@@ -56,12 +60,24 @@ int launch_mlp_fused(const MlpNet& net, const MlpStepArgs& args, int num_sms, cu
 
 // all weight / bias gradients in one grid: split s of tile t writes part[s][arena layout]
 int mlp_wgrad_splits(const MlpNet& net, int batch, int num_sms);
+// rows_per_split: 0 = derive from splits; tensor-core mode passes its own (a multiple of 32) and skips layers [tc_lo, tc_hi)
 int launch_mlp_wgrad(const MlpNet& net, const MlpStepArgs& args, float* part, int64_t part_stride, int splits,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int rows_per_split = 0);
 // g[i] = sum_s part[s][i] (fixed order) over the live prefix; loss[0..3] = sum over tiles (fixed order)
 int launch_mlp_reduce(const float* part, int64_t part_stride, int splits, float* g, int live_floats, const float* loss_part,
                       int tiles, float* loss_out, cudaStream_t stream);
 
 int trace_attach_mlp(unsigned long long* buf);
+
+// ---- mlp_tc.cu: wide layers on tcgen05 (kind::tf32, 3xTF32 split: fp32-equivalent) ----------------------------------------------
+bool mlp_tc_layer_ok(const MlpLayerDesc& L);
+// (k, n multiples of 4; fp32 row-major matrices, W = [k][n])
+int launch_mlp_tc_fwd(const float* W, const float* bias, int k, int n, int act, const float* in, float* out, int batch,
+                      cudaStream_t stream);                                        // out = act(in x W + bias)
+int launch_mlp_tc_dgrad(const float* W, int k, int n, const float* dz, const float* out_prev, int prev_act, float* dz_prev,
+                        int batch, cudaStream_t stream);                           // dz_prev = (dz x W^T) * act'(out_prev)
+int launch_mlp_tc_wgrad(int k, int n, const float* in, const float* dz, int batch, int splits, int rows_per_split, float* part_w,
+                        float* part_b, int64_t part_stride, cudaStream_t stream);  // split s: in^T x dz, colsum(dz) of its rows
+int trace_attach_mlp_tc(unsigned long long* buf);
 
 }  // namespace ga3c

@@ -46,6 +46,8 @@ struct ga3c_mlp {
   float* dlogits = nullptr;
   float* loss_part = nullptr;
   int64_t global_step = 0;
+  // tensor-core mode (mlp_tc.cu): the run of wide layers [tc_lo, tc_hi) as 3xTF32 GEMMs for training batches >= tc_min_batch
+  int tc_lo = 0, tc_hi = 0, tc_min_batch = 4096;
   LaunchLog log;                         // launch counter + per-kernel CUDA-event timing (ga3c_mlp_timing_*)
 };
 
@@ -137,6 +139,17 @@ extern "C" int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out) {
     net.L[0].k = S; net.L[0].n = cfg->dense_width[cfg->n_dense - 1]; net.L[0].act = MLP_ACT_SIGMOID;
   }
   net.hid = net.L[net.n_layers - 1].n;
+  {  // the first run of consecutive layers wide enough for 128 x BN tensor-core tiles (fork NetworkVP: 256 -> 256, 256 -> 100)
+    int lo = 0;
+    while (lo < net.n_layers && !(mlp_tc_layer_ok(net.L[lo]) && net.L[lo].n >= 100)) ++lo;
+    int hi = lo;
+    while (hi < net.n_layers && mlp_tc_layer_ok(net.L[hi]) && net.L[hi].n >= 100) ++hi;
+    if (lo >= 1 && hi > lo) { n->tc_lo = lo; n->tc_hi = hi; }       // (layer 0 reads x: never wide here)
+    if (const char* e = getenv("GA3C_MLP_TC")) {                     // 0: never; N > 0: from training batches of N rows
+      const int v = atoi(e);
+      if (v <= 0) n->tc_lo = n->tc_hi = 0; else n->tc_min_batch = v;
+    }
+  }
   const int pv = add("logits_v", net.hid, 1, 1);
   int px, py = -1;
   if (cfg->kind == GA3C_MLP_FORK_VP) {
@@ -275,6 +288,33 @@ extern "C" int64_t ga3c_mlp_global_step(const ga3c_mlp* n) { return n ? n->globa
 extern "C" int ga3c_mlp_set_global_step(ga3c_mlp* n, int64_t s) { if (!n) return -1; n->global_step = s; return 0; }
 extern "C" int64_t ga3c_mlp_launch_count(const ga3c_mlp* n) { return n ? n->log.launches : 0; }
 
+// kernel-level test entry for the 3xTF32 tensor-core GEMMs of mlp_tc.cu (all pointers device, fp32 row-major):
+//   mode 0  out [m, n] = act(a [m, k] x b [k, n] + aux [n])                       (forward)
+//   mode 1  out [m, k] = (a [m, n] x b [k, n]^T) * act'(aux [m, k])               (data gradient)
+//   mode 2  out [splits][k, n] = a [m, k]^T x b [m, n] per batch split of rows_per_split rows (weight gradient)
+extern "C" int ga3c_debug_tf32x3_gemm(int32_t mode, const float* a, const float* b, const float* aux, float* out, int32_t m,
+                                      int32_t k, int32_t nn, int32_t act, int32_t splits, int32_t rows_per_split, void* stream) {
+  if (!a || !b || !out || m < 1 || k < 4 || nn < 4 || k > 256 || nn > 256 || (k & 3) || (nn & 3))
+    return set_error("ga3c_debug_tf32x3_gemm: bad argument (k, n multiples of 4 up to 256)");
+  cudaStream_t st = (cudaStream_t)stream;
+  int r = 0;
+  if (mode == 0) r = launch_mlp_tc_fwd(b, aux, k, nn, act, a, out, m, st);
+  else if (mode == 1) r = launch_mlp_tc_dgrad(b, k, nn, a, aux, act, out, m, st);
+  else if (mode == 2) {
+    if (splits < 1 || rows_per_split < 32 || rows_per_split % 32) return set_error("ga3c_debug_tf32x3_gemm: rows_per_split must be a multiple of 32");
+    r = launch_mlp_tc_wgrad(k, nn, a, b, m, splits, rows_per_split, out, nullptr, (int64_t)k * nn, st);
+  } else return set_error("ga3c_debug_tf32x3_gemm: mode must be 0, 1 or 2");
+  if (r) return fail("ga3c_debug_tf32x3_gemm", (cudaError_t)r);
+  return 0;
+}
+extern "C" int ga3c_mlp_workspace_ptr(ga3c_mlp* n, int32_t which, int32_t layer, void** ptr, int32_t* width) {
+  if (!n || !ptr || !width) return set_error("ga3c_mlp_workspace_ptr: null argument");
+  if (which < 0 || which > 1 || layer < 0 || layer >= n->net.n_layers) return set_error("ga3c_mlp_workspace_ptr: bad matrix id");
+  *ptr = which == 0 ? n->act[layer] : n->dz[layer];
+  *width = n->net.L[layer].n;
+  return 0;
+}
+
 static int check_batch(ga3c_mlp* n, int batch, const char* who) {
   if (!n) return set_error(std::string(who) + ": null handle");
   if (batch < 1 || batch > n->cfg.max_batch)
@@ -309,10 +349,42 @@ static int mlp_fb_impl(ga3c_mlp* n, const float* x, const float* yr, const float
   cudaStream_t st = (cudaStream_t)stream;
   MlpStepArgs s = step_args(n, x, batch);
   s.yr = yr; s.a = a; s.beta = beta; s.train = 1; s.part = part;
+  const int tm = mlp_tile_rows(batch, n->num_sms);
+  if (n->tc_hi > n->tc_lo && batch >= n->tc_min_batch) {
+    // the wide layers as 3xTF32 tensor-core GEMMs over the activations the fused kernel keeps in HBM anyway
+    const MlpNet& net = n->net;
+    const int lo = n->tc_lo, hi = n->tc_hi;
+    s.tc_lo = lo; s.tc_hi = hi;
+    s.phase = 1;
+    LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(net, s, n->num_sms, st));
+    for (int l = lo; l < hi; ++l)
+      LAUNCH(n, K_MLP_TC, st, launch_mlp_tc_fwd(n->w + net.L[l].w_off, n->w + net.L[l].b_off, net.L[l].k, net.L[l].n, net.L[l].act,
+                                                n->act[l - 1], n->act[l], batch, st));
+    s.phase = 2;
+    LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(net, s, n->num_sms, st));
+    for (int l = hi - 1; l >= lo; --l)
+      LAUNCH(n, K_MLP_TC, st, launch_mlp_tc_dgrad(n->w + net.L[l].w_off, net.L[l].k, net.L[l].n, n->dz[l], n->act[l - 1],
+                                                  net.L[l - 1].act, n->dz[l - 1], batch, st));
+    if (lo >= 2) {
+      s.phase = 3;
+      LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(net, s, n->num_sms, st));
+    }
+    const int splits = MLP_MAX_SPLITS;
+    int rows = (batch + splits - 1) / splits;
+    rows = (rows + 31) / 32 * 32;
+    LAUNCH(n, K_MLP_WGRAD, st, launch_mlp_wgrad(net, s, n->part, n->live_floats, splits, st, rows));
+    for (int l = lo; l < hi; ++l) {
+      LAUNCH(n, K_MLP_TC, st, launch_mlp_tc_wgrad(net.L[l].k, net.L[l].n, n->act[l - 1], n->dz[l], batch, splits, rows,
+                                                  n->part + net.L[l].w_off, n->part + net.L[l].b_off, n->live_floats, st));
+      n->log.launches++;                 // (+ the bias column sums)
+    }
+    LAUNCH(n, K_MLP_REDUCE, st, launch_mlp_reduce(n->part, n->live_floats, splits, g_dst, (int)n->live_floats, n->loss_part,
+                                                  (batch + tm - 1) / tm, loss, st));
+    return 0;
+  }
   LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(n->net, s, n->num_sms, st));
   const int splits = mlp_wgrad_splits(n->net, batch, n->num_sms);
   LAUNCH(n, K_MLP_WGRAD, st, launch_mlp_wgrad(n->net, s, n->part, n->live_floats, splits, st));
-  const int tm = mlp_tile_rows(batch, n->num_sms);
   LAUNCH(n, K_MLP_REDUCE, st, launch_mlp_reduce(n->part, n->live_floats, splits, g_dst, (int)n->live_floats, n->loss_part,
                                                 (batch + tm - 1) / tm, loss, st));
   return 0;

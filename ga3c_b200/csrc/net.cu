@@ -109,7 +109,7 @@ struct ga3c_net {
 
 static const char* const kKernelNames[K_COUNT] = {"conv_fwd", "dense_fwd", "heads", "dense_wgrad", "dense_bwd",
                                                   "conv_bwd", "conv11_wgrad", "rmsprop", "grad_reduce",
-                                                  "mlp_fused", "mlp_wgrad", "mlp_reduce", "dp_big"};
+                                                  "mlp_fused", "mlp_wgrad", "mlp_reduce", "dp_big", "mlp_tc"};
 
 enum { P_C11W = 0, P_C11B, P_C12W, P_C12B, P_D1W, P_D1B, P_VW, P_VB, P_PW, P_PB, P_COUNT };
 
@@ -982,7 +982,7 @@ extern "C" const char* ga3c_kernel_name(int kid) { return (kid >= 0 && kid < K_C
 static int trace_attach_all(unsigned long long* buf) {
   int r;
   if ((r = trace_attach_conv_fwd(buf)) || (r = trace_attach_conv_bwd_fused(buf)) || (r = trace_attach_dense_tc(buf)) ||
-      (r = trace_attach_heads(buf)) || (r = trace_attach_dense_heads(buf)) || (r = trace_attach_elementwise(buf)) || (r = trace_attach_mlp(buf)))
+      (r = trace_attach_heads(buf)) || (r = trace_attach_dense_heads(buf)) || (r = trace_attach_elementwise(buf)) || (r = trace_attach_mlp(buf)) || (r = trace_attach_mlp_tc(buf)))
     return r;
   return 0;
 }

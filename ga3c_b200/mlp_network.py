@@ -330,6 +330,17 @@ class _MlpNetwork:
         return self._get_episode_from_filename(filename)
 
     # ------------------------------------------------------------------ introspection
+    def workspace(self, which: int, layer: int, batch: int) -> np.ndarray:
+        """Parity tests: output (which = 0) or pre-activation gradient (1) of live hidden layer `layer` for the first `batch`
+        rows of the last forward/backward, as a host array."""
+        ptr, width = C.c_void_p(), C.c_int32()
+        _capi.check(self._lib.ga3c_mlp_workspace_ptr(self._h, int(which), int(layer), C.byref(ptr), C.byref(width)),
+                    "ga3c_mlp_workspace_ptr")
+        torch.cuda.synchronize(self._tdev)
+        iface = {"shape": (int(batch) * width.value,), "typestr": "<f4", "data": (ptr.value, False), "version": 2}
+        holder = type("H", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device=self._tdev).cpu().numpy().reshape(int(batch), width.value).copy()
+
     def launch_count(self) -> int:
         return int(self._lib.ga3c_mlp_launch_count(self._h))
 

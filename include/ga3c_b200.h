@@ -226,6 +226,16 @@ int ga3c_mlp_apply_rmsprop(ga3c_mlp* net, float learning_rate, void* stream);
 int ga3c_mlp_train_step(ga3c_mlp* net, const float* x_dev, const float* yr_dev, const float* a_dev, int32_t batch,
                         float learning_rate, float beta, float* loss_dev, void* stream);
 int64_t ga3c_mlp_launch_count(const ga3c_mlp* net);
+/* parity tests: device pointer to a training-workspace matrix of the last forward/backward, fp32 row-major [batch][*width].
+ * which: 0 output of live hidden layer `layer`, 1 gradient w.r.t. that layer's pre-activation. */
+int ga3c_mlp_workspace_ptr(ga3c_mlp* net, int32_t which, int32_t layer, void** ptr, int32_t* width);
+/* kernel-level test entry for the 3xTF32 tensor-core GEMMs behind the wide MLP layers (device pointers, fp32 row-major;
+ * k, n multiples of 4 up to 256):
+ *   mode 0  out [m, n] = act(a [m, k] x b [k, n] + aux [n])                    act: 0 linear, 1 sigmoid
+ *   mode 1  out [m, k] = (a [m, n] x b [k, n]^T) * act'(aux [m, k])
+ *   mode 2  out [splits][k, n] = a [m, k]^T x b [m, n] over each batch split of rows_per_split (multiple of 32) rows */
+int ga3c_debug_tf32x3_gemm(int32_t mode, const float* a, const float* b, const float* aux, float* out, int32_t m, int32_t k,
+                           int32_t n, int32_t act, int32_t splits, int32_t rows_per_split, void* stream);
 /* per-kernel event timing, as ga3c_timing_* (kernel ids are shared: ga3c_kernel_name) */
 int ga3c_mlp_timing_enable(ga3c_mlp* net, int32_t max_records);
 int ga3c_mlp_timing_collect(ga3c_mlp* net, double* total_ms, int64_t* counts, int32_t n_kernels);

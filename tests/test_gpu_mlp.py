@@ -297,6 +297,33 @@ def test_full_size_batch_and_reproducibility(mlp):
         assert err(g1[k], g_ref)[1] <= TOL_GRAD_REL, (k, err(g1[k], g_ref))
 
 
+@pytest.mark.parametrize("s,a", [(3, 1), (4, 2)])
+@pytest.mark.parametrize("batch", [33, 128, 1000, 4097])
+def test_tensor_core_wide_layers_match_oracle_and_the_fp32_path(mlp, monkeypatch, s, a, batch):
+    """The 256 -> 256 and 256 -> 100 layers of the fork NetworkVP as 3xTF32 tcgen05 GEMMs (mlp_tc.cu; taken from 4096 training rows
+    on, forced here from 1 row): same tolerances against the oracle as the fp32 FMA path, and close to that path itself."""
+    kind = "fork_vp"
+    params, x, y_r, act = make_case(kind, s, a, batch, seed=11)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GA3C_MLP_TC", mode)          # read at construction: 1 = tensor cores from 1 row, 0 = never
+        net = make_net(mlp, kind, s, a, max_batch=batch)
+        net.set_variables(params)
+        net.beta = 0.01
+        n0 = net.launch_count()
+        out[mode] = (net.losses(x, y_r, act), net.get_gradients(), net.launch_count() - n0)
+    assert out["1"][2] > out["0"][2] == 3, (out["1"][2], out["0"][2])      # the GEMM launches really ran
+    losses_ref, grads_ref = om.loss_and_grads(params, x, y_r, act, kind, beta=0.01)
+    losses, grads, _ = out["1"]
+    for k in ("cost_p_1", "cost_p_2", "cost_v", "cost_all"):
+        assert abs(losses[k] - losses_ref[k]) <= 2e-5 * max(batch, abs(losses_ref[k])), (k, losses[k], losses_ref[k])
+    for k, g_ref in grads_ref.items():
+        d, r = err(grads[k], g_ref)
+        assert r <= TOL_GRAD_REL or d <= 1e-6, (k, d, r)
+        d, r = err(grads[k], out["0"][1][k])
+        assert r <= TOL_GRAD_REL or d <= 1e-6, ("vs fp32 path", k, d, r)
+
+
 def test_batch_sum_is_additive(mlp):
     """Size-independent property: every loss term and gradient is a SUM over the batch (NetworkVP_discrate.py:61,:83-85), so
     the gradient of a concatenated batch equals the sum of the parts' gradients."""
