@@ -152,6 +152,40 @@ __device__ __forceinline__ void tile_pass(const float* in_s, float* out_s, float
     }
 }
 
+// Data gradient into a NARROW layer (nout <= 8 columns; fork NetworkVP: 256 -> 4): tile_pass would compute 128 columns for them.
+// TPR threads share a row: each sums every TPR-th term of the nout dot products, a shuffle tree adds them, lane 0 of the group
+// finishes the row.  out[r][c] = sum_q in_s[r][q] * Wg[c * ldw + q], q < kred (the transposed weight layout of tile_pass<true>).
+template <int RT, class Epi>
+__device__ __forceinline__ void narrow_dgrad_pass(const float* in_s, float* out_s, int kred, const float* __restrict__ Wg, int ldw,
+                                                  int nout, Epi epi) {
+  constexpr int TM = (FT / 32) * RT, TPR = FT / TM;        // 8 threads per row (64-row tiles) or 32 (16-row tiles)
+  const int tid = threadIdx.x, row = tid / TPR, part = tid % TPR;
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+  __syncthreads();                   // in_s is complete
+  for (int q = part; q < kred; q += TPR) {
+    const float a = in_s[row * LD + q];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < nout) acc[c] = fmaf(a, __ldg(Wg + (size_t)c * ldw + q), acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int o = TPR / 2; o >= 1; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+  if (part == 0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (4 * h >= nout) break;
+      float v[4] = {acc[4 * h], acc[4 * h + 1], acc[4 * h + 2], acc[4 * h + 3]};
+      epi(row, 4 * h, v);
+      *reinterpret_cast<float4*>(out_s + row * LD + 4 * h) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    for (int c = (nout + 3) & ~3; c < 16; c += 4) *reinterpret_cast<float4*>(out_s + row * LD + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 // store 4 consecutive columns c0.. of row `row` of a [B][n] matrix (n need not be a multiple of 4)
 __device__ __forceinline__ void store_row4(float* base, int64_t row, int n, int c0, const float (&v)[4]) {
   float* dst = base + row * n + c0;
@@ -198,9 +232,22 @@ __global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, cons
       const float* src = s.phase == 2 ? s.act[s.tc_hi - 1] : s.phase == 3 ? s.dz[s.tc_lo - 1] : s.x;
       const int W = s.phase == 2 ? net.L[s.tc_hi - 1].n : s.phase == 3 ? net.L[s.tc_lo - 1].n : S;
       const int Sp = round_up16(W);
-      for (int idx = tid; idx < TM * Sp; idx += FT) {
-        const int r = idx / Sp, c = idx - r * Sp;
-        buf0[r * LD + c] = (row0 + r < B && c < W) ? src[(size_t)(row0 + r) * W + c] : 0.f;
+      if ((W & 3) == 0 && s.phase != 0) {
+        // wide HBM matrices: 16-byte loads, all of a thread's loads in flight (scalar loads in a rolled loop cost one memory
+        // latency per 512 floats of the tile: 112 us of a 242 us launch, measured)
+        const int S4 = Sp >> 2, n4 = TM * S4;
+#pragma unroll 8
+        for (int idx = tid; idx < n4; idx += FT) {
+          const int r = idx / S4, c = (idx - r * S4) * 4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row0 + r < B && c < W) v = __ldcs(reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * W + c));
+          *reinterpret_cast<float4*>(buf0 + r * LD + c) = v;
+        }
+      } else {
+        for (int idx = tid; idx < TM * Sp; idx += FT) {
+          const int r = idx / Sp, c = idx - r * Sp;
+          buf0[r * LD + c] = (row0 + r < B && c < W) ? src[(size_t)(row0 + r) * W + c] : 0.f;
+        }
       }
     }
     float* cur = buf0;
@@ -420,6 +467,7 @@ __global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, cons
         if (valid) store_row4(dz_g, row0 + r, Lp.n, c0, v);
       };
       if (Lp.n > 128) tile_pass<true, 2, RT>(cur, nxt, Wc, L.n, s.w + L.w_off, L.n, Lp.n, epi);
+      else if (Lp.n <= 8) narrow_dgrad_pass<RT>(cur, nxt, L.n, s.w + L.w_off, L.n, Lp.n, epi);
       else tile_pass<true, 1, RT>(cur, nxt, Wc, L.n, s.w + L.w_off, L.n, Lp.n, epi);
       float* t = cur; cur = nxt; nxt = t;
     }
@@ -447,7 +495,7 @@ __global__ void __launch_bounds__(NT) mlp_wgrad_kernel(const MlpNet net, const M
     t -= tk * tn;
   }
   if (l > NL) return;
-  if (l >= s.tc_lo && l < s.tc_hi) return;          // tensor-core mode: this layer's dW / db come from mlp_tc.cu
+  if ((s.wgrad_skip >> l) & 1u) return;              // tensor-core mode: this matrix's dW / db come from the kernels of mlp_tc.cu
   const int k0 = (t / tn) * WT, n0 = (t % tn) * WT;
   const float* in = l == 0 ? s.x : s.act[l - 1];
   const int ld_in = K;
@@ -517,6 +565,59 @@ __global__ void __launch_bounds__(NT) mlp_wgrad_kernel(const MlpNet net, const M
     if (k0 == 0 && ty == 0) out[b_off + col] = bs[j];
   }
   trace_mark(K_MLP_WGRAD, 2);
+}
+
+// Head matrices (logits_v | logits_p [| out_y]: n_out <= 4 columns) for large batches: dW[k][j] = sum_r h[r][k] dlogits[r][j],
+// db[j] = sum_r dlogits[r][j] per batch split, streaming h once: 1024 threads = 16 row groups x 64 columns of h, the row groups
+// added in a fixed order.  (The 64 x 64 tile kernel above spends 157 us on this 64 x 3 product at B = 65,536.)
+__global__ void __launch_bounds__(1024) mlp_heads_wgrad_kernel(const MlpNet net, const float* __restrict__ h,
+                                                                const float* __restrict__ dl, int batch, int rows_per_split,
+                                                                float* part, int64_t part_stride) {
+  __shared__ float red[16][8][64];
+  griddep_launch();
+  griddep_wait(K_MLP_WGRAD);
+  const int rg = threadIdx.x >> 6, c = threadIdx.x & 63, k = blockIdx.y * 64 + c;
+  const int hid = net.hid, J = net.n_out, ld = net.n_out_ld;
+  const int r0 = blockIdx.x * rows_per_split, r1 = min(batch, r0 + rows_per_split);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
+  if (k < hid) {
+    constexpr int U = 4;
+    int r = r0 + rg;
+    for (; r + 16 * (U - 1) < r1; r += 16 * U) {
+      float4 d[U];
+      float hv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        d[u] = __ldg(reinterpret_cast<const float4*>(dl + (size_t)(r + 16 * u) * ld));
+        hv[u] = __ldcs(h + (size_t)(r + 16 * u) * hid + k);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc[0] = fmaf(d[u].x, hv[u], acc[0]); acc[1] = fmaf(d[u].y, hv[u], acc[1]);
+        acc[2] = fmaf(d[u].z, hv[u], acc[2]); acc[3] = fmaf(d[u].w, hv[u], acc[3]);
+        bs[0] += d[u].x; bs[1] += d[u].y; bs[2] += d[u].z; bs[3] += d[u].w;
+      }
+    }
+    for (; r < r1; r += 16) {
+      const float4 d = __ldg(reinterpret_cast<const float4*>(dl + (size_t)r * ld));
+      const float hv = h[(size_t)r * hid + k];
+      acc[0] = fmaf(d.x, hv, acc[0]); acc[1] = fmaf(d.y, hv, acc[1]); acc[2] = fmaf(d.z, hv, acc[2]); acc[3] = fmaf(d.w, hv, acc[3]);
+      bs[0] += d.x; bs[1] += d.y; bs[2] += d.z; bs[3] += d.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { red[rg][j][c] = acc[j]; red[rg][4 + j][c] = bs[j]; }
+  __syncthreads();
+  if (rg == 0 && k < hid) {
+    float* out = part + (size_t)blockIdx.x * part_stride;
+    for (int j = 0; j < J; ++j) {
+      float t = 0.f, b = 0.f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) { t += red[g][j][c]; b += red[g][4 + j][c]; }
+      out[head_w_index(net, k, j)] = t;
+      if (k == 0) out[head_b_index(net, j)] = b;
+    }
+  }
 }
 
 // ---- partial arenas -> gradient arena; per-tile loss sums -> loss[4] -----------------------------------------
@@ -599,6 +700,14 @@ int launch_mlp_wgrad(const MlpNet& net, const MlpStepArgs& args, float* part, in
   rows = (rows + RC - 1) / RC * RC;
   const dim3 grid(total_wgrad_tiles(net), splits);
   return launch_pdl(mlp_wgrad_kernel, grid, dim3(NT), 0, stream, net, args, part, part_stride, rows);
+}
+
+bool mlp_heads_wgrad_ok(const MlpNet& net) { return net.n_out <= 4 && net.n_out_ld == 4; }
+int launch_mlp_heads_wgrad(const MlpNet& net, const MlpStepArgs& args, float* part, int64_t part_stride, int splits,
+                           int rows_per_split, cudaStream_t stream) {
+  const dim3 grid(splits, (net.hid + 63) / 64);
+  return launch_pdl(mlp_heads_wgrad_kernel, grid, dim3(1024), 0, stream, net, (const float*)args.act[net.n_layers - 1],
+                    (const float*)args.dlogits, args.batch, rows_per_split, part, part_stride);
 }
 
 int launch_mlp_reduce(const float* part, int64_t part_stride, int splits, float* g, int live_floats, const float* loss_part,

@@ -50,6 +50,7 @@ struct MlpStepArgs {
   // kernel.  phase 0: everything (tc_lo = tc_hi = 0).  phase 1: x -> layers [0, tc_lo).  phase 2: act[tc_hi - 1] -> layers
   // [tc_hi, n_layers), heads, loss, data gradients down to dz[tc_hi - 1].  phase 3: dz[tc_lo - 1] -> data gradients down to dz[0].
   int phase, tc_lo, tc_hi;
+  unsigned wgrad_skip;                  // bit l: mlp_wgrad leaves layer l's dW / db to launch_mlp_tc_wgrad / launch_mlp_skinny_wgrad
 };
 
 int configure_mlp();
@@ -63,6 +64,10 @@ int mlp_wgrad_splits(const MlpNet& net, int batch, int num_sms);
 // rows_per_split: 0 = derive from splits; tensor-core mode passes its own (a multiple of 32) and skips layers [tc_lo, tc_hi)
 int launch_mlp_wgrad(const MlpNet& net, const MlpStepArgs& args, float* part, int64_t part_stride, int splits,
                      cudaStream_t stream, int rows_per_split = 0);
+// the head matrices' dW / db by a streaming kernel (n_out <= 4; large batches: bit n_layers of MlpStepArgs::wgrad_skip)
+bool mlp_heads_wgrad_ok(const MlpNet& net);
+int launch_mlp_heads_wgrad(const MlpNet& net, const MlpStepArgs& args, float* part, int64_t part_stride, int splits,
+                           int rows_per_split, cudaStream_t stream);
 // g[i] = sum_s part[s][i] (fixed order) over the live prefix; loss[0..3] = sum over tiles (fixed order)
 int launch_mlp_reduce(const float* part, int64_t part_stride, int splits, float* g, int live_floats, const float* loss_part,
                       int tiles, float* loss_out, cudaStream_t stream);
@@ -78,6 +83,9 @@ int launch_mlp_tc_dgrad(const float* W, int k, int n, const float* dz, const flo
                         int batch, cudaStream_t stream);                           // dz_prev = (dz x W^T) * act'(out_prev)
 int launch_mlp_tc_wgrad(int k, int n, const float* in, const float* dz, int batch, int splits, int rows_per_split, float* part_w,
                         float* part_b, int64_t part_stride, cudaStream_t stream);  // split s: in^T x dz, colsum(dz) of its rows
+// dW = in^T x dz for a layer with fan-in k <= 4 (k = 0: none) and db = colsum(dz), per batch split: streaming kernel, no tiles
+int launch_mlp_skinny_wgrad(int k, int n, const float* in, const float* dz, int batch, int splits, int rows_per_split,
+                            float* part_w, float* part_b, int64_t part_stride, cudaStream_t stream);
 int trace_attach_mlp_tc(unsigned long long* buf);
 
 }  // namespace ga3c

@@ -139,11 +139,11 @@ extern "C" int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out) {
     net.L[0].k = S; net.L[0].n = cfg->dense_width[cfg->n_dense - 1]; net.L[0].act = MLP_ACT_SIGMOID;
   }
   net.hid = net.L[net.n_layers - 1].n;
-  {  // the first run of consecutive layers wide enough for 128 x BN tensor-core tiles (fork NetworkVP: 256 -> 256, 256 -> 100)
+  {  // the first run of consecutive layers wide enough for 128 x BN tensor-core tiles (fork NetworkVP: 256 -> 256 -> 100 -> 64)
     int lo = 0;
-    while (lo < net.n_layers && !(mlp_tc_layer_ok(net.L[lo]) && net.L[lo].n >= 100)) ++lo;
+    while (lo < net.n_layers && !mlp_tc_layer_ok(net.L[lo])) ++lo;
     int hi = lo;
-    while (hi < net.n_layers && mlp_tc_layer_ok(net.L[hi]) && net.L[hi].n >= 100) ++hi;
+    while (hi < net.n_layers && mlp_tc_layer_ok(net.L[hi])) ++hi;
     if (lo >= 1 && hi > lo) { n->tc_lo = lo; n->tc_hi = hi; }       // (layer 0 reads x: never wide here)
     if (const char* e = getenv("GA3C_MLP_TC")) {                     // 0: never; N > 0: from training batches of N rows
       const int v = atoi(e);
@@ -372,11 +372,25 @@ static int mlp_fb_impl(ga3c_mlp* n, const float* x, const float* yr, const float
     const int splits = MLP_MAX_SPLITS;
     int rows = (batch + splits - 1) / splits;
     rows = (rows + 31) / 32 * 32;
-    LAUNCH(n, K_MLP_WGRAD, st, launch_mlp_wgrad(net, s, n->part, n->live_floats, splits, st, rows));
-    for (int l = lo; l < hi; ++l) {
-      LAUNCH(n, K_MLP_TC, st, launch_mlp_tc_wgrad(net.L[l].k, net.L[l].n, n->act[l - 1], n->dz[l], batch, splits, rows,
-                                                  n->part + net.L[l].w_off, n->part + net.L[l].b_off, n->live_floats, st));
-      n->log.launches++;                 // (+ the bias column sums)
+    // weight gradients: tensor-core layers by GEMM (+ a streaming pass for the bias), fan-in <= 4 layers by the streaming kernel
+    // alone, whatever is left (the head matrix) by the tile kernel
+    for (int l = 0; l < net.n_layers; ++l)
+      if ((l >= lo && l < hi) || net.L[l].k <= 4) s.wgrad_skip |= 1u << l;
+    if (mlp_heads_wgrad_ok(net)) {
+      s.wgrad_skip |= 1u << net.n_layers;
+      LAUNCH(n, K_MLP_WGRAD, st, launch_mlp_heads_wgrad(net, s, n->part, n->live_floats, splits, rows, st));
+    }
+    if (s.wgrad_skip != (2u << net.n_layers) - 1u)
+      LAUNCH(n, K_MLP_WGRAD, st, launch_mlp_wgrad(net, s, n->part, n->live_floats, splits, st, rows));
+    for (int l = 0; l < net.n_layers; ++l) {
+      if (!((s.wgrad_skip >> l) & 1u)) continue;
+      const bool tc = l >= lo && l < hi;
+      const float* in = l == 0 ? x : n->act[l - 1];
+      if (tc)
+        LAUNCH(n, K_MLP_TC, st, launch_mlp_tc_wgrad(net.L[l].k, net.L[l].n, in, n->dz[l], batch, splits, rows,
+                                                    n->part + net.L[l].w_off, n->part + net.L[l].b_off, n->live_floats, st));
+      LAUNCH(n, K_MLP_WGRAD, st, launch_mlp_skinny_wgrad(tc ? 0 : net.L[l].k, net.L[l].n, in, n->dz[l], batch, splits, rows,
+                                                         n->part + net.L[l].w_off, n->part + net.L[l].b_off, n->live_floats, st));
     }
     LAUNCH(n, K_MLP_REDUCE, st, launch_mlp_reduce(n->part, n->live_floats, splits, g_dst, (int)n->live_floats, n->loss_part,
                                                   (batch + tm - 1) / tm, loss, st));

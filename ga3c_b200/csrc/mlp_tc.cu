@@ -243,22 +243,62 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
 static_assert(t3_half<256>() % (16 * 32 * T3_SPLIT_WARPS) == 0 && t3_half<128>() % (16 * 32 * T3_SPLIT_WARPS) == 0,
               "the splitters cover a stage in whole rounds");
 
-// bias gradients of the tensor-core layers: db[n] = sum over the rows of a batch split of dz[:, n], into the partial arenas
-__global__ void __launch_bounds__(256) mlp_colsum_kernel(const float* __restrict__ dz, int batch, int N, int rows_per_split,
-                                                         float* part_b, int64_t part_stride) {
+// Weight gradient of a layer with fan-in K <= 4 (the state and the 4-wide first layer of the fork NetworkVP; K = 0: none) and the
+// bias gradient of any layer, per batch split: dW[k][n] = sum_r in[r][k] dz[r][n], db[n] = sum_r dz[r][n].  Pure streaming --
+// dz is read once, coalesced -- where a 64 x 64 tile kernel would spend its time on zero padding.  1024 threads = 16 row groups
+// x 64 columns (the loop is bound by memory latency: rows in flight are what counts); the row groups are added in a fixed order.
+constexpr int SK_RG = 16;
+template <int K>
+__global__ void __launch_bounds__(64 * SK_RG) mlp_skinny_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dz,
+                                                                      int batch, int N, int rows_per_split, float* part_w,
+                                                                      float* part_b, int64_t part_stride) {
+  __shared__ float red[SK_RG][K + 1][64];
   griddep_launch();
   griddep_wait(K_MLP_TC);
-  const int n = threadIdx.x;
-  if (n >= N) return;
+  const int rg = threadIdx.x >> 6, c = threadIdx.x & 63, n = blockIdx.y * 64 + c;
   const int r0 = blockIdx.x * rows_per_split, r1 = min(batch, r0 + rows_per_split);
-  float s[4] = {0.f, 0.f, 0.f, 0.f};
-  int r = r0;
-  for (; r + 4 <= r1; r += 4) {
+  float acc[K + 1];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) s[u] += dz[(size_t)(r + u) * N + n];
+  for (int k = 0; k <= K; ++k) acc[k] = 0.f;
+  if (n < N) {
+    constexpr int U = 4;
+    int r = r0 + rg;
+    for (; r + SK_RG * (U - 1) < r1; r += SK_RG * U) {
+      float d[U], x[U][K > 0 ? K : 1];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        d[u] = __ldcs(dz + (size_t)(r + SK_RG * u) * N + n);
+#pragma unroll
+        for (int k = 0; k < K; ++k) x[u][k] = __ldg(in + (size_t)(r + SK_RG * u) * K + k);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = fmaf(x[u][k], d[u], acc[k]);
+        acc[K] += d[u];
+      }
+    }
+    for (; r < r1; r += SK_RG) {
+      const float d = dz[(size_t)r * N + n];
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] = fmaf(__ldg(in + (size_t)r * K + k), d, acc[k]);
+      acc[K] += d;
+    }
   }
-  for (; r < r1; ++r) s[0] += dz[(size_t)r * N + n];
-  part_b[(size_t)blockIdx.x * part_stride + n] = (s[0] + s[1]) + (s[2] + s[3]);
+#pragma unroll
+  for (int k = 0; k <= K; ++k) red[rg][k][c] = acc[k];
+  __syncthreads();
+  if (rg == 0 && n < N) {
+    float* pw = part_w + (size_t)blockIdx.x * part_stride;
+#pragma unroll
+    for (int k = 0; k <= K; ++k) {
+      float t = 0.f;
+#pragma unroll
+      for (int g = 0; g < SK_RG; ++g) t += red[g][k][c];
+      if (k < K) pw[(size_t)k * N + n] = t;
+      else part_b[(size_t)blockIdx.x * part_stride + n] = t;
+    }
+  }
 }
 
 // 2-D fp32 row-major matrix [rows][cols] (ld floats between rows), box = 32 inner x box_rows, 128-B swizzle (of 32-byte chunks
@@ -334,8 +374,8 @@ int launch_mlp_tc_dgrad(const float* W, int k, int n, const float* dz, const flo
   return launch_gemm3<128, false, false>(ta, tb, batch, k, kblocks, kblocks, 1, epi, stream);
 }
 
-// dW [k, n] = in [B, k]^T x dz [B, n] and db = colsum(dz): batch split s into part_w / part_b + s * part_stride (every split
-// writes its whole tile, zeros if it has no rows)
+// dW [k, n] = in [B, k]^T x dz [B, n]: batch split s into part_w + s * part_stride (every split writes its whole tile, zeros
+// if it has no rows); the bias gradient comes from launch_mlp_skinny_wgrad with k = 0
 int launch_mlp_tc_wgrad(int k, int n, const float* in, const float* dz, int batch, int splits, int rows_per_split, float* part_w,
                         float* part_b, int64_t part_stride, cudaStream_t stream) {
   CUtensorMap ta, tb;
@@ -347,8 +387,21 @@ int launch_mlp_tc_wgrad(int k, int n, const float* in, const float* dz, int batc
   int r;
   if (n > 128) r = launch_gemm3<256, true, true>(ta, tb, k, n, kblocks, per, splits, epi, stream);
   else r = launch_gemm3<128, true, true>(ta, tb, k, n, kblocks, per, splits, epi, stream);
-  if (r || part_b == nullptr) return r;
-  return launch_pdl(mlp_colsum_kernel, dim3(splits), dim3(256), 0, stream, dz, batch, n, rows_per_split, part_b, part_stride);
+  (void)part_b;
+  return r;
+}
+
+int launch_mlp_skinny_wgrad(int k, int n, const float* in, const float* dz, int batch, int splits, int rows_per_split,
+                            float* part_w, float* part_b, int64_t part_stride, cudaStream_t stream) {
+  const dim3 grid(splits, (n + 63) / 64), block(64 * SK_RG);
+  switch (k) {
+    case 0: return launch_pdl(mlp_skinny_wgrad_kernel<0>, grid, block, 0, stream, in, dz, batch, n, rows_per_split, part_w, part_b, part_stride);
+    case 1: return launch_pdl(mlp_skinny_wgrad_kernel<1>, grid, block, 0, stream, in, dz, batch, n, rows_per_split, part_w, part_b, part_stride);
+    case 2: return launch_pdl(mlp_skinny_wgrad_kernel<2>, grid, block, 0, stream, in, dz, batch, n, rows_per_split, part_w, part_b, part_stride);
+    case 3: return launch_pdl(mlp_skinny_wgrad_kernel<3>, grid, block, 0, stream, in, dz, batch, n, rows_per_split, part_w, part_b, part_stride);
+    case 4: return launch_pdl(mlp_skinny_wgrad_kernel<4>, grid, block, 0, stream, in, dz, batch, n, rows_per_split, part_w, part_b, part_stride);
+  }
+  return (int)cudaErrorInvalidValue;
 }
 
 }  // namespace ga3c
