@@ -153,22 +153,38 @@ __device__ __forceinline__ void tile_pass(const float* in_s, float* out_s, float
 }
 
 // Data gradient into a NARROW layer (nout <= 8 columns; fork NetworkVP: 256 -> 4): tile_pass would compute 128 columns for them.
-// TPR threads share a row: each sums every TPR-th term of the nout dot products, a shuffle tree adds them, lane 0 of the group
-// finishes the row.  out[r][c] = sum_q in_s[r][q] * Wg[c * ldw + q], q < kred (the transposed weight layout of tile_pass<true>).
+// The nout x kred weights are staged in shared memory (the chunk ring is idle here; straight from global every term of the
+// dot products waited out an L2 latency: 133 us for this pass at B = 65,536, measured).  TPR threads share a row: each sums every
+// TPR-th term of the dot products, a shuffle tree adds them, lane 0 of the group finishes the row.
+//   out[r][c] = sum_q in_s[r][q] * Wg[c * ldw + q], q < kred   (the transposed weight layout of tile_pass<true>)
 template <int RT, class Epi>
-__device__ __forceinline__ void narrow_dgrad_pass(const float* in_s, float* out_s, int kred, const float* __restrict__ Wg, int ldw,
-                                                  int nout, Epi epi) {
+__device__ __forceinline__ void narrow_dgrad_pass(const float* in_s, float* out_s, float* Wc, int kred, const float* __restrict__ Wg,
+                                                  int ldw, int nout, Epi epi) {
   constexpr int TM = (FT / 32) * RT, TPR = FT / TM;        // 8 threads per row (64-row tiles) or 32 (16-row tiles)
   const int tid = threadIdx.x, row = tid / TPR, part = tid % TPR;
+  __syncthreads();                   // in_s is complete, nobody reads the ring any more
+  for (int idx = tid; idx < 8 * kred; idx += FT) {
+    const int c = idx / kred, q = idx - c * kred;
+    Wc[c * LD + q] = c < nout ? __ldg(Wg + (size_t)c * ldw + q) : 0.f;
+  }
+  __syncthreads();
   float acc[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-  __syncthreads();                   // in_s is complete
-  for (int q = part; q < kred; q += TPR) {
-    const float a = in_s[row * LD + q];
+  if (nout <= 4) {
+#pragma unroll 4
+    for (int q = part; q < kred; q += TPR) {
+      const float a = in_s[row * LD + q];
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      if (c < nout) acc[c] = fmaf(a, __ldg(Wg + (size_t)c * ldw + q), acc[c]);
+      for (int c = 0; c < 4; ++c) acc[c] = fmaf(a, Wc[c * LD + q], acc[c]);
+    }
+  } else {
+#pragma unroll 4
+    for (int q = part; q < kred; q += TPR) {
+      const float a = in_s[row * LD + q];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = fmaf(a, Wc[c * LD + q], acc[c]);
+    }
   }
 #pragma unroll
   for (int c = 0; c < 8; ++c)
@@ -467,7 +483,7 @@ __global__ void __launch_bounds__(FT, 1) mlp_fused_kernel(const MlpNet net, cons
         if (valid) store_row4(dz_g, row0 + r, Lp.n, c0, v);
       };
       if (Lp.n > 128) tile_pass<true, 2, RT>(cur, nxt, Wc, L.n, s.w + L.w_off, L.n, Lp.n, epi);
-      else if (Lp.n <= 8) narrow_dgrad_pass<RT>(cur, nxt, L.n, s.w + L.w_off, L.n, Lp.n, epi);
+      else if (Lp.n <= 8) narrow_dgrad_pass<RT>(cur, nxt, Wc, L.n, s.w + L.w_off, L.n, Lp.n, epi);
       else tile_pass<true, 1, RT>(cur, nxt, Wc, L.n, s.w + L.w_off, L.n, Lp.n, epi);
       float* t = cur; cur = nxt; nxt = t;
     }

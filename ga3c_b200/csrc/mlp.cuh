@@ -10,7 +10,7 @@ constexpr int MLP_MAX_WIDTH = 256;    // of any layer and of the state
 constexpr int MLP_MAX_HID = 128;      // width of the last hidden layer (the one the heads read)
 constexpr int MLP_MAX_OUT = 1 + 2 * 18;
 constexpr int MLP_TM = 64;            // batch rows per tile
-constexpr int MLP_MAX_SPLITS = 64;    // batch splits of the weight-gradient pass (partial arenas)
+constexpr int MLP_MAX_SPLITS = 74;    // batch splits of the weight-gradient pass (partial arenas); 2 x 74 GEMM CTAs = one per SM
 constexpr int MLP_ACT_LINEAR = 0, MLP_ACT_SIGMOID = 1;
 constexpr int MLP_KIND_FORK_VP = 0, MLP_KIND_DISCRATE = 1;
 

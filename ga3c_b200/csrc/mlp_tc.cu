@@ -24,28 +24,35 @@ namespace ga3c {
 
 namespace {
 
-constexpr int T3_BK = 32;                          // floats of K per stage: one 128-byte swizzle row
+// A stage is 16 floats of K (two UMMA k-steps): fine-grained on purpose.  The chain TMA -> split -> UMMA of one stage is ~2 us
+// long against ~0.5 us of tensor time, and what hides it is stages in flight per SM: 96 KB of stages per CTA, TWO CTAs per SM
+// (2 x 256 TMEM columns), which also lets one CTA's epilogue run under the other's main loop.  (32-float stages, one CTA per
+// SM: 3 us per 32 floats of K, tensor pipe 25 % busy -- profiles/r3h.)
+constexpr int T3_BK = 16;                          // floats of K per stage: one 64-byte swizzle row (K-major operands)
 constexpr int T3_THREADS = 448, T3_SPLIT_WARP0 = 6, T3_SPLIT_WARPS = 8;
-constexpr int T3_A_BYTES = TC_BM * T3_BK * 4;      // 16 KB
+constexpr int T3_A_BYTES = TC_BM * T3_BK * 4;      // 8 KB
+constexpr int T3_MN_BOX = 32 * T3_BK * 4;          // one MN-major TMA box: 32 floats of M / N x 16 k-rows = 2 KB
 
 template <int BN>
 constexpr int t3_half() { return T3_A_BYTES + BN * T3_BK * 4; }      // hi (or lo) operands of one stage
-template <int BN>
-constexpr int t3_stages() { return BN >= 256 ? 2 : 3; }
-template <int BN>
-constexpr int t3_smem() { return t3_stages<BN>() * 2 * t3_half<BN>() + (3 * t3_stages<BN>() + 1) * 8 + 16 + 1024; }
+// DEEP = false: 96 KB of stages, two CTAs per SM (forward / data gradient: hundreds of tiles); DEEP = true: 192 KB, one CTA per SM
+// (weight gradient: at most one CTA per SM anyway, each streaming a long K = batch range -- stages in flight is all it has)
+template <int BN, bool DEEP>
+constexpr int t3_stages() { return (BN >= 256 ? 2 : 3) * (DEEP ? 2 : 1); }
+template <int BN, bool DEEP>
+constexpr int t3_smem() { return t3_stages<BN, DEEP>() * 2 * t3_half<BN>() + (3 * t3_stages<BN, DEEP>() + 1) * 8 + 16 + 1024; }
 
 // instruction descriptor, kind::tf32: D = f32, A = B = tf32
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n, bool a_mn, bool b_mn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(m >> 4) << 24);
 }
-// Shared-memory descriptor of an fp32 operand.  K-major: SWIZZLE_128B, rows of 128 B (32 floats of K), 8-row atoms: SBO = 1024.
-// MN-major: 32-bit operands can only be transposed from the SWIZZLE_128B_BASE32B layout (layout type 1: 32-byte chunks swizzled
-// within 128 B, pattern period 4 rows; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atom = 4 k-rows x 128 B (32 floats of M / N),
-// SBO = 512 between k-atoms, LBO = 4096 between the 32-wide atoms (one TMA box each).
+// Shared-memory descriptor of an fp32 operand.  K-major: SWIZZLE_64B (layout type 4), rows of 64 B (16 floats of K), 8-row atoms:
+// SBO = 512.  MN-major: 32-bit operands can only be transposed from the SWIZZLE_128B_BASE32B layout (layout type 1: 32-byte
+// chunks swizzled within 128 B, pattern period 4 rows; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atom = 4 k-rows x 128 B (32
+// floats of M / N), SBO = 512 between k-atoms, LBO = 2048 between the 32-wide atoms (one TMA box of 16 k-rows each).
 __device__ __forceinline__ uint64_t make_desc_f32(uint32_t saddr, bool mn_major) {
-  const uint64_t lbo = mn_major ? (4096u >> 4) : 1u, sbo = mn_major ? (512u >> 4) : (1024u >> 4), type = mn_major ? 1ull : 2ull;
+  const uint64_t lbo = mn_major ? (uint64_t)(T3_MN_BOX >> 4) : 1u, sbo = 512u >> 4, type = mn_major ? 1ull : 4ull;
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (type << 61);
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
@@ -58,64 +65,49 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
       : "memory");
 }
 
-// ---- epilogues: one thread owns output row m and 32 consecutive columns n .. n + 31 (n, N multiples of 4) -------------------
+// ---- epilogues -------------------------------------------------------------------------------------------------------------------
+// A warp drains 32 rows x 32 columns of the accumulator (tcgen05.ld: one row per lane), turns the chunk around through a swizzled
+// 4 KB staging tile in shared memory, and finishes it in the COALESCED domain: 8 lanes per row, one float4 each, so every global
+// access of the warp is four whole 128-byte lines.  (One row per lane straight to global -- 32 lines touched by every store
+// instruction -- made the epilogue 40 % of the forward GEMM and 60 % of the data-gradient GEMM, measured.)  The functors below see
+// (row m, column n .. n + 3, the accumulator float4); n, N are multiples of 4.  load() fetches what the chunk's 8 float4 need from
+// global memory BEFORE any of them is stored (loads issued between stores would each wait out a memory latency).
 struct Epi3Fwd {         // out = act(acc + b)
   const float* bias; float* out; int N, act;
-  __device__ __forceinline__ void operator()(int, int m, int n, const uint32_t (&r)[32], bool zero) const {
-    float* dst = out + (size_t)m * N + n;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (n + 4 * i >= N) break;
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n) + i);
-      float v[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        v[e] += zero ? 0.f : __uint_as_float(r[4 * i + e]);
-        if (act == MLP_ACT_SIGMOID) v[e] = 1.f / (1.f + expf(-v[e]));
-      }
-      reinterpret_cast<float4*>(dst)[i] = make_float4(v[0], v[1], v[2], v[3]);
+  __device__ __forceinline__ float4 load(int, int n) const { return __ldg(reinterpret_cast<const float4*>(bias + n)); }
+  __device__ __forceinline__ void operator()(int, int m, int n, float4 v, const float4 b) const {
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    if (act == MLP_ACT_SIGMOID) {
+      v.x = 1.f / (1.f + expf(-v.x)); v.y = 1.f / (1.f + expf(-v.y)); v.z = 1.f / (1.f + expf(-v.z)); v.w = 1.f / (1.f + expf(-v.w));
     }
+    *reinterpret_cast<float4*>(out + (size_t)m * N + n) = v;
   }
 };
 struct Epi3Dgrad {       // dz_prev = acc * act'(out_prev)
   const float* out_prev; float* dz; int N, act;
-  __device__ __forceinline__ void operator()(int, int m, int n, const uint32_t (&r)[32], bool zero) const {
-    float* dst = dz + (size_t)m * N + n;
-    const float4* op = reinterpret_cast<const float4*>(out_prev + (size_t)m * N + n);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (n + 4 * i >= N) break;
-      float v[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = zero ? 0.f : __uint_as_float(r[4 * i + e]);
-      if (act == MLP_ACT_SIGMOID) {
-        const float4 o = op[i];
-        v[0] *= o.x * (1.f - o.x); v[1] *= o.y * (1.f - o.y); v[2] *= o.z * (1.f - o.z); v[3] *= o.w * (1.f - o.w);
-      }
-      reinterpret_cast<float4*>(dst)[i] = make_float4(v[0], v[1], v[2], v[3]);
+  __device__ __forceinline__ float4 load(int m, int n) const {
+    return act == MLP_ACT_SIGMOID ? __ldcs(reinterpret_cast<const float4*>(out_prev + (size_t)m * N + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __device__ __forceinline__ void operator()(int, int m, int n, float4 v, const float4 o) const {
+    if (act == MLP_ACT_SIGMOID) {
+      v.x *= o.x * (1.f - o.x); v.y *= o.y * (1.f - o.y); v.z *= o.z * (1.f - o.z); v.w *= o.w * (1.f - o.w);
     }
+    *reinterpret_cast<float4*>(dz + (size_t)m * N + n) = v;
   }
 };
 struct Epi3Wgrad {       // raw tile into partial arena `split` (part points at the layer's weights in arena 0)
   float* part; int64_t part_stride; int N;
-  __device__ __forceinline__ void operator()(int split, int m, int n, const uint32_t (&r)[32], bool zero) const {
-    float* dst = part + (size_t)split * part_stride + (size_t)m * N + n;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (n + 4 * i >= N) break;
-      reinterpret_cast<float4*>(dst)[i] =
-          zero ? make_float4(0.f, 0.f, 0.f, 0.f)
-               : make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                             __uint_as_float(r[4 * i + 3]));
-    }
+  __device__ __forceinline__ float4 load(int, int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void operator()(int split, int m, int n, float4 v, const float4) const {
+    *reinterpret_cast<float4*>(part + (size_t)split * part_stride + (size_t)m * N + n) = v;
   }
 };
 
-template <int BN, bool A_MN, bool B_MN, class Epi>
-__global__ void __launch_bounds__(T3_THREADS, 1)
+template <int BN, bool A_MN, bool B_MN, bool DEEP, class Epi>
+__global__ void __launch_bounds__(T3_THREADS, 2)
 gemm3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int M, int N, int k_blocks,
-             int k_blocks_per_split, const Epi epi) {
-  constexpr int STAGES = t3_stages<BN>(), HALF = t3_half<BN>(), STAGE = 2 * HALF;
+             int k_blocks_per_split, const Epi epi, int dbg) {
+  constexpr int STAGES = t3_stages<BN, DEEP>(), HALF = t3_half<BN>(), STAGE = 2 * HALF;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* const smem = smem_raw + (sbase - smem_u32(smem_raw));
@@ -155,13 +147,13 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         mbar_expect_tx(bar_full(s), HALF);
         if (A_MN) {
 #pragma unroll
-          for (int j = 0; j < TC_BM / 32; ++j) tma_load_2d(sa + j * 4096, &tm_a, m0 + 32 * j, kb * T3_BK, bar_full(s));
+          for (int j = 0; j < TC_BM / 32; ++j) tma_load_2d(sa + j * T3_MN_BOX, &tm_a, m0 + 32 * j, kb * T3_BK, bar_full(s));
         } else {
           tma_load_2d(sa, &tm_a, kb * T3_BK, m0, bar_full(s));
         }
         if (B_MN) {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &tm_b, n0 + 32 * j, kb * T3_BK, bar_full(s));
+          for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * T3_MN_BOX, &tm_b, n0 + 32 * j, kb * T3_BK, bar_full(s));
         } else {
           tma_load_2d(sb, &tm_b, kb * T3_BK, n0, bar_full(s));
         }
@@ -180,8 +172,9 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         const uint64_t a_lo = make_desc_f32(sa + HALF, A_MN), b_lo = make_desc_f32(sb + HALF, B_MN);
 #pragma unroll
         for (int k = 0; k < T3_BK / 8; ++k) {
-          // advance K by 8: +32 B inside the 128-B swizzle row (K-major), +1 k-atom = 1024 B (MN-major)
+          // advance K by 8: +32 B inside the 64-B swizzle row (K-major), +2 k-atoms = 1024 B (MN-major)
           const uint64_t ka = (uint64_t)((A_MN ? 1024u : 32u) * k >> 4), kbv = (uint64_t)((B_MN ? 1024u : 32u) * k >> 4);
+          if (dbg & 2) continue;
           tc_mma_tf32(tmem_base, a_lo + ka, b_hi + kbv, idesc, (it > 0 || k > 0) ? 1u : 0u);      // small terms first
           tc_mma_tf32(tmem_base, a_hi + ka, b_lo + kbv, idesc, 1u);
           tc_mma_tf32(tmem_base, a_hi + ka, b_hi + kbv, idesc, 1u);
@@ -194,18 +187,47 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     __syncwarp();
   } else if (warp < T3_SPLIT_WARP0) {
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int m = m0 + q * 32 + lane;
     const bool zero = kb1 <= kb0;                 // an empty split still writes its (zero) tile
     if (!zero) {
-      mbar_wait(bar_done, 0);
+      mbar_wait(bar_done, 0);                     // every UMMA has retired: the accumulator is final and the stages are free
       tc_fence_after();
     }
+    const uint32_t stg = sbase + (uint32_t)(warp - 2) * 4096u;      // staging tile of this warp, in stage 0
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
+      const int n = n0 + c * 32;
+      if (n >= N) break;
       uint32_t r[32];
       if (!zero) tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
-      const int n = n0 + c * 32;
-      if (m < M && n < N) epi(split, m, n, r, zero);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {               // own row, 16-byte chunk j at chunk position j ^ (row & 7): conflict-free both ways
+        const uint32_t dst = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
+        if (zero) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};\n" ::"r"(dst), "r"(0u) : "memory");
+        else asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(dst), "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]),
+                          "r"(r[4 * j + 3]) : "memory");
+      }
+      __syncwarp();
+      if (!(dbg & 4)) {
+        const int ch = lane & 7, nn = n + ch * 4, mrow0 = m0 + q * 32 + (lane >> 3);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {             // two rounds of 4 rows per lane (register budget of two CTAs per SM)
+          float4 aux[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int m = mrow0 + 4 * (4 * h + i);
+            aux[i] = (m < M && nn < N) ? epi.load(m, nn) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = 4 * (4 * h + i) + (lane >> 3), m = mrow0 + 4 * (4 * h + i);
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"(stg + row * 128 + ((ch ^ (row & 7)) << 4)) : "memory");
+            if (m < M && nn < N) epi(split, m, nn, v, aux[i]);
+          }
+        }
+      }
+      __syncwarp();
     }
   } else {
     const int t = threadIdx.x - 32 * T3_SPLIT_WARP0;      // 0 .. 255
@@ -214,6 +236,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       mbar_wait(bar_full(s), (it / STAGES) & 1);           // TMA bytes landed
       float4* hi = reinterpret_cast<float4*>(smem + s * STAGE);
       float4* lo = reinterpret_cast<float4*>(smem + s * STAGE + HALF);
+      if (!(dbg & 1))
 #pragma unroll
       for (int i = 0; i < HALF / 16 / (32 * T3_SPLIT_WARPS); ++i) {
         const int idx = t + 32 * T3_SPLIT_WARPS * i;
@@ -240,6 +263,8 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     tmem_dealloc<BN>(tmem_base);
   }
 }
+static_assert(2 * (t3_smem<256, false>() + 1024) <= 233472 && 2 * (t3_smem<128, false>() + 1024) <= 233472, "two CTAs per SM");
+static_assert(t3_smem<256, true>() <= 232448 && t3_smem<128, true>() <= 232448, "shared memory budget of one CTA");
 static_assert(t3_half<256>() % (16 * 32 * T3_SPLIT_WARPS) == 0 && t3_half<128>() % (16 * 32 * T3_SPLIT_WARPS) == 0,
               "the splitters cover a stage in whole rounds");
 
@@ -301,8 +326,8 @@ __global__ void __launch_bounds__(64 * SK_RG) mlp_skinny_wgrad_kernel(const floa
   }
 }
 
-// 2-D fp32 row-major matrix [rows][cols] (ld floats between rows), box = 32 inner x box_rows, 128-B swizzle (of 32-byte chunks
-// for an operand that is consumed MN-major); out-of-bounds
+// 2-D fp32 row-major matrix [rows][cols] (ld floats between rows).  K-major operand: box = 16 inner x box_rows, 64-B swizzle;
+// MN-major operand: box = 32 inner x 16 rows, 128-B swizzle of 32-byte chunks.  Out-of-bounds
 // elements read as zero, so ragged M / N / K tails need no special casing in the kernel
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -323,24 +348,31 @@ int make_tmap_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t co
   if (!enc) return (int)cudaErrorNotSupported;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * 4};
-  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t box[2] = {mn_major ? 32u : (cuuint32_t)T3_BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
-template <int BN, bool A_MN, bool B_MN, class Epi>
+static int t3_debug() { static const int v = [] { const char* e = getenv("GA3C_T3_DEBUG"); return e ? atoi(e) : 0; }(); return v; }
+
+template <int BN, bool A_MN, bool B_MN, bool DEEP = false, class Epi>
 int launch_gemm3(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int k_blocks, int per, int splits, const Epi& epi,
                  cudaStream_t stream) {
-  static const int configured = (int)cudaFuncSetAttribute(gemm3_kernel<BN, A_MN, B_MN, Epi>,
-                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, t3_smem<BN>());
+  static const int configured = [] {
+    int r = (int)cudaFuncSetAttribute(gemm3_kernel<BN, A_MN, B_MN, DEEP, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      t3_smem<BN, DEEP>());
+    if (r) return r;       // two CTAs per SM need the full shared-memory carveout
+    return (int)cudaFuncSetAttribute(gemm3_kernel<BN, A_MN, B_MN, DEEP, Epi>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared);
+  }();
   if (configured) return configured;
   const dim3 grid((M + TC_BM - 1) / TC_BM, (N + BN - 1) / BN, splits);
-  return launch_pdl(gemm3_kernel<BN, A_MN, B_MN, Epi>, grid, dim3(T3_THREADS), (size_t)t3_smem<BN>(), stream, ta, tb, M, N,
-                    k_blocks, per, epi);
+  return launch_pdl(gemm3_kernel<BN, A_MN, B_MN, DEEP, Epi>, grid, dim3(T3_THREADS), (size_t)t3_smem<BN, DEEP>(), stream, ta, tb, M, N,
+                    k_blocks, per, epi, t3_debug());
 }
 
 }  // namespace
@@ -385,8 +417,8 @@ int launch_mlp_tc_wgrad(int k, int n, const float* in, const float* dz, int batc
   const int per = rows_per_split / T3_BK;
   const Epi3Wgrad epi{part_w, part_stride, n};
   int r;
-  if (n > 128) r = launch_gemm3<256, true, true>(ta, tb, k, n, kblocks, per, splits, epi, stream);
-  else r = launch_gemm3<128, true, true>(ta, tb, k, n, kblocks, per, splits, epi, stream);
+  if (n > 128) r = launch_gemm3<256, true, true, true>(ta, tb, k, n, kblocks, per, splits, epi, stream);
+  else r = launch_gemm3<128, true, true, true>(ta, tb, k, n, kblocks, per, splits, epi, stream);
   (void)part_b;
   return r;
 }
