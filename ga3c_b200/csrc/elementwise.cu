@@ -270,8 +270,9 @@ int launch_rmsprop_dual_clipped(RmsPropDualArgs d, const ClipArgs& c1, const Cli
 // SM with a CTA that takes the SM's whole shared memory, so every CTA of the previous optimizer launch has exited before this
 // kernel can be launched; with smaller batches the whole chain of a step can sit in its prologues while the previous
 // optimizer is still running (back-to-back asynchronous calls), and the loads move behind the wait.
+constexpr int RR_U = 3;      // float4 per thread in the dense1/w blocks of rmsprop_reduce_kernel
 template <bool HAS_MOM>
-__global__ void __launch_bounds__(GR_LANES * GR_COLS) rmsprop_reduce_kernel(RmsPropArgs a, GradReduceArgs r, int n_red) {
+__global__ void __launch_bounds__(GR_LANES * GR_COLS, 2) rmsprop_reduce_kernel(RmsPropArgs a, GradReduceArgs r, int n_red) {
   __shared__ float4 part[GR_LANES][GR_COLS];
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   if ((int)blockIdx.x < n_red) {
@@ -329,12 +330,14 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) rmsprop_reduce_kernel(RmsP
       }
     }
   } else {
-    // two float4 per thread, a block apart (coalesced): the whole grid is resident in one wave
-    const int64_t i0 = (r.out_floats >> 2) + (int64_t)(blockIdx.x - n_red) * (2 * blockDim.x) + threadIdx.x;
+    // RR_U float4 per thread, a block apart (coalesced).  RR_U = 3 keeps the whole grid -- 113 slab blocks + 162 of these at
+    // B = 1024 -- inside ONE wave of 2 blocks per SM (52 registers x 512 threads); with two per thread the grid was 357 blocks
+    // against 296 slots, and the 61 stragglers of the second wave cost the step ~3 us (profiles/r3c_step_trace_n1.md)
+    const int64_t i0 = (r.out_floats >> 2) + (int64_t)(blockIdx.x - n_red) * (RR_U * blockDim.x) + threadIdx.x;
     const int64_t n4 = a.n_floats >> 2;
-    float4 w[2], ms[2], mo[2];
+    float4 w[RR_U], ms[RR_U], mo[RR_U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < RR_U; ++u) {
       const int64_t i = i0 + u * blockDim.x;
       w[u] = ms[u] = mo[u] = zero;
       if (i < n4 && a.preload) {
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) rmsprop_reduce_kernel(RmsP
     griddep_wait(K_RMSPROP);      // dense1/w's gradient comes from the wgrad GEMM
     if (!a.preload) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < RR_U; ++u) {
         const int64_t i = i0 + u * blockDim.x;
         if (i < n4) {
           w[u] = reinterpret_cast<const float4*>(a.w)[i];
@@ -356,14 +359,14 @@ __global__ void __launch_bounds__(GR_LANES * GR_COLS) rmsprop_reduce_kernel(RmsP
         }
       }
     }
-    float4 g[2];
+    float4 g[RR_U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < RR_U; ++u) {
       const int64_t i = i0 + u * blockDim.x;
       g[u] = i < n4 ? reinterpret_cast<const float4*>(a.g)[i] : zero;
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < RR_U; ++u) {
       const int64_t i = i0 + u * blockDim.x;
       if (i < n4) {
         rms_update<HAS_MOM>(a, g[u], w[u], ms[u], mo[u]);
@@ -383,7 +386,7 @@ int launch_rmsprop_reduce(const RmsPropArgs& a, const GradReduceArgs& r, cudaStr
   constexpr int T = GR_LANES * GR_COLS;
   const int n_red = (r.n_floats / 4 + GR_COLS - 1) / GR_COLS;
   const int64_t rest4 = (a.n_floats - r.out_floats) >> 2;
-  const int grid = n_red + (int)((rest4 + 2 * T - 1) / (2 * T));
+  const int grid = n_red + (int)((rest4 + RR_U * T - 1) / (RR_U * T));
   if (a.momentum != 0.f) return launch_pdl(rmsprop_reduce_kernel<true>, dim3(grid), dim3(T), 0, stream, a, r, n_red);
   return launch_pdl(rmsprop_reduce_kernel<false>, dim3(grid), dim3(T), 0, stream, a, r, n_red);
 }
