@@ -106,9 +106,16 @@ struct EpiReluMaskBf16Tc {  // dn2 = acc where n2 > 0 else 0, bf16, stored in th
   }
 };
 
+// gate (dense1 forward, data parallel with the side-stream exchange): the B operand is the bf16 shadow of dense1/w, whose slices
+// the ranks' exchange kernels of the PREVIOUS step store into this rank's slab.  Instead of a stream-level event wait in front
+// of this launch (which takes the launch out of the programmatic-dependent-launch chain: +3.6 us per step, measured) the TMA
+// producer warp looks at the "slice of rank r landed everywhere" flags in this rank's own comm block -- pushed there long ago in
+// the normal case -- before its first load.  The exchange grid it might wait for only ever waits for other GPUs and has been
+// resident since the previous step's conv backward, so the wait cannot keep it off an SM.
 template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tm_a, const CUtensorMap& tm_b, int M, int N, int k_blocks,
-                                             int k_blocks_per_split, const Epi& epi, int bx, int by, int bz) {
+                                             int k_blocks_per_split, const Epi& epi, int bx, int by, int bz,
+                                             const DpGate* gate = nullptr) {
   constexpr int B_STAGE = BN * TC_BK * 2;
   constexpr int STAGE = TC_A_STAGE + B_STAGE;
   extern __shared__ uint8_t smem_raw[];
@@ -144,6 +151,12 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tm_a, const CUte
   // producer and issuer run warp-uniform (all lanes loop and wait, elect_one() issues): descriptors and TMA coordinates
   // stay in uniform registers instead of going through R2UR inside an ELECT retry loop
   if (warp == 0) {
+    if (gate != nullptr && gate->flags != nullptr) {
+      if (lane < gate->world)
+        dp_wait_flag_acquire(gate->flags + 64 * lane, gate->step, gate->err, 16u);
+      __syncwarp();
+      asm volatile("fence.proxy.async;\n" ::: "memory");      // the shadow was written through the generic proxy, TMA reads it
+    }
     for (int kb = kb0; kb < kb1; ++kb) {
       const int it = kb - kb0, s = it % STAGES;
       mbar_wait(bars + (STAGES + s) * 8, ((it / STAGES) & 1) ^ 1);          // slot free
@@ -215,9 +228,9 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tm_a, const CUte
 template <int BN, int STAGES, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int M, int N,
-               int k_blocks, int k_blocks_per_split, Epi epi) {
+               int k_blocks, int k_blocks_per_split, Epi epi, const DpGate gate) {
   gemm_tc_body<BN, STAGES, A_MN, B_MN, Epi>(tm_a, tm_b, M, N, k_blocks, k_blocks_per_split, epi, blockIdx.x, blockIdx.y,
-                                            blockIdx.z);
+                                            blockIdx.z, &gate);
 }
 
 // dense1 backward in ONE launch: both GEMMs only need dd1, so their tiles share a grid.  Blocks [0, n_dg) are the
@@ -337,7 +350,8 @@ int dense_fwd_splits(int batch, int num_sms) {
   return (kblocks + per - 1) / per;                               // no empty splits
 }
 
-int launch_dense_fwd_tc(const uint16_t* n2, const uint16_t* w1bf, float* d1_part, int batch, int splits, cudaStream_t stream) {
+int launch_dense_fwd_tc(const uint16_t* n2, const uint16_t* w1bf, float* d1_part, int batch, int splits, cudaStream_t stream,
+                        const DpGate* gate) {
   CUtensorMap ta, tb;
   if (make_tmap(&ta, n2, batch, FLAT, FLAT, TC_BM)) return (int)cudaErrorInvalidValue;        // A: [B][3872], K inner
   if (make_tmap(&tb, w1bf, FLAT, FC, FC, 64)) return (int)cudaErrorInvalidValue;              // B: [3872][256], N inner
@@ -346,7 +360,7 @@ int launch_dense_fwd_tc(const uint16_t* n2, const uint16_t* w1bf, float* d1_part
   dim3 grid((batch + TC_BM - 1) / TC_BM, FC / FWD_BN, splits);
   return launch_pdl(gemm_tc_kernel<FWD_BN, FWD_ST, false, true, EpiPartialF32>, grid, dim3(TC_THREADS),
                     tc_smem<FWD_BN, FWD_ST>(), stream, ta, tb, batch, (int)FC, kblocks, per,
-                    EpiPartialF32{d1_part, FC, (int64_t)batch * FC});
+                    EpiPartialF32{d1_part, FC, (int64_t)batch * FC}, gate ? *gate : DpGate{});
 }
 
 int launch_dense_dgrad_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint8_t* dn2, int batch,
@@ -357,7 +371,7 @@ int launch_dense_dgrad_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint1
   dim3 grid((batch + TC_BM - 1) / TC_BM, (FLAT + DG_BN - 1) / DG_BN, 1);
   return launch_pdl(gemm_tc_kernel<DG_BN, DG_ST, false, false, EpiReluMaskBf16Tc>, grid, dim3(TC_THREADS),
                     tc_smem<DG_BN, DG_ST>(), stream, ta, tb, batch, (int)FLAT, FC / TC_BK, FC / TC_BK,
-                    EpiReluMaskBf16Tc{dn2, n2, FLAT});
+                    EpiReluMaskBf16Tc{dn2, n2, FLAT}, DpGate{});
 }
 
 int launch_dense_wgrad_tc(const uint16_t* n2, const uint16_t* dd1, float* g_w1, int batch, cudaStream_t stream) {
@@ -368,7 +382,7 @@ int launch_dense_wgrad_tc(const uint16_t* n2, const uint16_t* dd1, float* g_w1, 
   dim3 grid((FLAT + TC_BM - 1) / TC_BM, FC / WG_BN, 1);
   return launch_pdl(gemm_tc_kernel<WG_BN, WG_ST, true, true, EpiPartialF32>, grid, dim3(TC_THREADS),
                     tc_smem<WG_BN, WG_ST>(), stream, ta, tb, (int)FLAT, (int)FC, kblocks, kblocks,
-                    EpiPartialF32{g_w1, FC, 0});
+                    EpiPartialF32{g_w1, FC, 0}, DpGate{});
 }
 
 int launch_dense_bwd_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint8_t* dn2, float* g_w1, int batch,

@@ -43,7 +43,16 @@ int launch_conv_fwd(const void* x, bool x_u8, const float* w11, const float* b11
 // dense_tc.cu -- the three dense1 GEMMs (NetworkDNav.py:90 and its autodiff) on tcgen05 / TMEM / TMA.  fwd leaves `splits` raw fp32 partial tiles
 // in d1_part[splits][B][256]; the heads kernel sums them, adds the bias and applies the ReLU.
 int dense_fwd_splits(int batch, int num_sms);
-int launch_dense_fwd_tc(const uint16_t* n2, const uint16_t* w1bf, float* d1_part, int batch, int splits, cudaStream_t stream);
+// data parallel, side-stream exchange: flags = this rank's comm block + DPC_BIGDONE ([world] x 64 B, u64 step numbers), see
+// gemm_tc_body (dense_tc.cu).  flags == nullptr: no gate.
+struct DpGate {
+  const uint8_t* flags;
+  void* err;                        // this rank's error word (bit 16 on a wait that gave up)
+  unsigned long long step;          // every flag must have reached this step
+  int world;
+};
+int launch_dense_fwd_tc(const uint16_t* n2, const uint16_t* w1bf, float* d1_part, int batch, int splits, cudaStream_t stream,
+                        const DpGate* gate = nullptr);
 int launch_dense_dgrad_tc(const uint16_t* dd1, const uint16_t* w1bf, const uint16_t* n2, uint8_t* dn2, int batch,
                           cudaStream_t stream);       // dn2 in the G operand layout (common.cuh), borders untouched
 int launch_dense_wgrad_tc(const uint16_t* n2, const uint16_t* dd1, float* g_w1, int batch, cudaStream_t stream);

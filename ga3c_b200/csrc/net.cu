@@ -386,6 +386,21 @@ static int wait_dp_big(ga3c_net* n, cudaStream_t st) {
   if (n->dp_big_pending) CK(cudaStreamWaitEvent(st, n->dp_big_done, 0));
   return 0;
 }
+// ... or, by default (GA3C_DP_GATE=0 brings the event wait back), when dense_fwd's TMA producer has seen every rank's "slice
+// landed everywhere" flag of the last exchanged step in this rank's comm block (DpGate, dense_tc.cu): no stream operation between
+// conv_fwd and dense_fwd, so the launch chain stays programmatic
+static bool dp_gated(const ga3c_net* n) {
+  static const bool on = [] { const char* e = getenv("GA3C_DP_GATE"); return !e || atoi(e) != 0; }();
+  return on && n->dp_big_pending && n->dp_world > 1;
+}
+static DpGate dp_gate(const ga3c_net* n) {
+  DpGate g{};
+  if (dp_gated(n)) {
+    uint8_t* comm = n->dp_peer[n->dp_rank] + n->comm_off;
+    g.flags = comm + DPC_BIGDONE; g.err = comm + DPC_ERR; g.step = n->dp_step; g.world = n->dp_world;
+  }
+  return g;
+}
 
 // dense1 forward + heads in one cluster launch (dense_heads.cu) while its slabs fit the gradient-partial workspace
 static bool fused_heads(const ga3c_net* n, int batch) {
@@ -400,14 +415,17 @@ static int predict_impl(ga3c_net* n, const void* x, bool x_u8, int32_t batch, fl
   const float* w = n->w;
   LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, x_u8, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
                                             w + n->off(P_C12B), nullptr, nullptr, n->n2, batch, n->num_sms, st));
-  if (int r = wait_dp_big(n, st)) return r;
+  const bool fused_p = fused_heads(n, batch);
+  const DpGate gate = fused_p ? DpGate{} : dp_gate(n);
+  if (gate.flags == nullptr)
+    if (int r = wait_dp_big(n, st)) return r;
   const int splits = dense_fwd_splits(batch, n->num_sms);
   HeadsArgs h = heads_args(n, batch, splits);
   h.p_out = p_out; h.v_out = v_out; h.train = 0;
-  if (fused_heads(n, batch)) {
+  if (fused_p) {
     LAUNCH(n, K_DENSE_FWD, st, launch_dense_heads(n->n2, n->w1_shadow, h, st));
   } else {
-    LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
+    LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st, &gate));
     LAUNCH(n, K_HEADS, st, launch_heads(h, n->num_sms, st));
   }
   n->last_batch = batch;
@@ -438,8 +456,10 @@ static int fb_head_impl(ga3c_net* n, const void* x, bool x_u8, const float* yr, 
   if (!skip_forward) {        // the second DUAL_RMSPROP pass reuses n1 / n2 / the dense1 partials of the first
     LAUNCH(n, K_CONV_FWD, st, launch_conv_fwd(x, x_u8, w + n->off(P_C11W), w + n->off(P_C11B), w + n->off(P_C12W),
                                               w + n->off(P_C12B), n->n1, n->xblk, n->n2, batch, n->num_sms, st));
-    if (int r = wait_dp_big(n, st)) return r;
-    if (!fused) LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st));
+    const DpGate gate = fused ? DpGate{} : dp_gate(n);
+    if (gate.flags == nullptr)
+      if (int r = wait_dp_big(n, st)) return r;
+    if (!fused) LAUNCH(n, K_DENSE_FWD, st, launch_dense_fwd_tc(n->n2, n->w1_shadow, n->d1_part, batch, splits, st, &gate));
   }
   HeadsArgs h = heads_args(n, batch, splits);
   h.yr = yr; h.a = a; h.beta = beta; h.train = 1; h.dd1 = n->dd1; h.part = part;
