@@ -641,20 +641,41 @@ __global__ void __launch_bounds__(NT) mlp_reduce_kernel(const float* part, int64
                                                         const float* loss_part, int tiles, float* loss_out) {
   griddep_launch();
   griddep_wait(K_MLP_REDUCE);
-  const int i = blockIdx.x * NT + threadIdx.x;
+  // four adjacent lanes share one float4 of the arena: lane q adds its quarter of the splits in split order (RU loads in flight),
+  // then (q0 + q1) + (q2 + q3) by two shuffles -- a fixed order.  (One thread per float4 walking all 74 splits with one load per
+  // memory latency made this kernel 27 us at B = 65,536.)
+  constexpr int RU = 8;
+  const int i = (blockIdx.x * NT + threadIdx.x) >> 2, q4 = threadIdx.x & 3;
+  const int per = (splits + 3) >> 2, s_lo = q4 * per, s_hi = min(splits, s_lo + per);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i < n4) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int sp = 0; sp < splits; ++sp) {
-      const float4 q = __ldcg(reinterpret_cast<const float4*>(part + (size_t)sp * part_stride) + i);
-      acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+    for (int sp0 = s_lo; sp0 < s_hi; sp0 += RU) {
+      float4 q[RU];
+#pragma unroll
+      for (int u = 0; u < RU; ++u)
+        q[u] = sp0 + u < s_hi ? __ldcg(reinterpret_cast<const float4*>(part + (size_t)(sp0 + u) * part_stride) + i)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < RU; ++u) { acc.x += q[u].x; acc.y += q[u].y; acc.z += q[u].z; acc.w += q[u].w; }
     }
-    reinterpret_cast<float4*>(g)[i] = acc;
   }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+  }
+  if (i < n4 && q4 == 0) reinterpret_cast<float4*>(g)[i] = acc;
   if (blockIdx.x == 0 && threadIdx.x < 128 && loss_out != nullptr) {
     // warp c sums component c: lane adds tiles lane, lane + 32, ... in order, then the fixed shuffle tree
     const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float v = 0.f;
-    for (int t = lane; t < tiles; t += 32) v += __ldcg(loss_part + (size_t)t * 4 + c);
+    for (int t0 = lane; t0 < tiles; t0 += 32 * RU) {           // same order as a plain loop, RU loads in flight
+      float q[RU];
+#pragma unroll
+      for (int u = 0; u < RU; ++u) q[u] = t0 + 32 * u < tiles ? __ldcg(loss_part + (size_t)(t0 + 32 * u) * 4 + c) : 0.f;
+#pragma unroll
+      for (int u = 0; u < RU; ++u) v += q[u];
+    }
     v = warp_sum(v);
     if (lane == 0) loss_out[c] = v;
   }
@@ -729,7 +750,7 @@ int launch_mlp_heads_wgrad(const MlpNet& net, const MlpStepArgs& args, float* pa
 int launch_mlp_reduce(const float* part, int64_t part_stride, int splits, float* g, int live_floats, const float* loss_part,
                       int tiles, float* loss_out, cudaStream_t stream) {
   const int n4 = live_floats / 4;
-  const int grid = (n4 + NT - 1) / NT;
+  const int grid = (4 * n4 + NT - 1) / NT;          // four lanes per float4
   return launch_pdl(mlp_reduce_kernel, dim3(grid < 1 ? 1 : grid), dim3(NT), 0, stream, part, part_stride, splits, g, n4,
                     loss_part, tiles, loss_out);
 }

@@ -88,4 +88,14 @@ int launch_mlp_skinny_wgrad(int k, int n, const float* in, const float* dz, int 
                             float* part_w, float* part_b, int64_t part_stride, cudaStream_t stream);
 int trace_attach_mlp_tc(unsigned long long* buf);
 
+// ---- mlp_stream.cu: the narrow ends of the fork NetworkVP in tensor-core mode as streaming passes (instead of phases 1 / 2 / 3 of
+// the fused tile kernel) ----
+bool mlp_stream_ok(const MlpNet& net, int tc_lo, int tc_hi);
+int launch_mlp_front_fwd(const MlpNet& net, const MlpStepArgs& args, int num_sms, cudaStream_t stream);   // x -> act[0], act[1]
+// act[last] -> v, p (when the pointers are set); args.train: loss_part rows (one per block: mlp_heads_loss_rows), dlogits, dz[last]
+int launch_mlp_heads(const MlpNet& net, const MlpStepArgs& args, int num_sms, cudaStream_t stream);
+int mlp_heads_loss_rows(int batch, int num_sms);
+int launch_mlp_front_bwd(const MlpNet& net, const MlpStepArgs& args, int num_sms, cudaStream_t stream);   // dz[1] -> dz[0]
+int trace_attach_mlp_stream(unsigned long long* buf);
+
 }  // namespace ga3c

@@ -1,6 +1,7 @@
 // C-ABI host layer of the low-dimensional MLP networks (ga3c_mlp_*, include/ga3c_b200.h): handle, arenas, workspace and
 // the launch sequences.  Kernels: mlp.cu (+ the arena RMSProp of elementwise.cu).
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/ga3c_b200.h"
@@ -48,6 +49,7 @@ struct ga3c_mlp {
   int64_t global_step = 0;
   // tensor-core mode (mlp_tc.cu): the run of wide layers [tc_lo, tc_hi) as 3xTF32 GEMMs for training batches >= tc_min_batch
   int tc_lo = 0, tc_hi = 0, tc_min_batch = 4096;
+  bool stream_ok = false, stream_ok_pending = false;                // ... with the narrow ends as streaming passes (mlp_stream.cu; GA3C_MLP_STREAM=0: fused-kernel phases)
   LaunchLog log;                         // launch counter + per-kernel CUDA-event timing (ga3c_mlp_timing_*)
 };
 
@@ -64,7 +66,9 @@ static int alloc_workspace(ga3c_mlp* n, int max_batch) {
     CK(cudaMalloc((void**)&n->dz[l], mb * n->net.L[l].n * 4));
   }
   CK(cudaMalloc((void**)&n->dlogits, mb * n->net.n_out_ld * 4));
-  CK(cudaMalloc((void**)&n->loss_part, ((mb + 15) / 16) * 4 * 4));      // one row per batch tile, tiles of >= 16 rows
+  // one row per batch tile (tiles of >= 16 rows), or one per block of the streaming heads kernel (mlp_heads_loss_rows <= 8 per SM)
+  const size_t loss_rows = std::max((mb + 15) / 16, (size_t)n->num_sms * 64);
+  CK(cudaMalloc((void**)&n->loss_part, loss_rows * 4 * 4));
   n->cfg.max_batch = max_batch;
   return 0;
 }
@@ -149,6 +153,8 @@ extern "C" int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out) {
       const int v = atoi(e);
       if (v <= 0) n->tc_lo = n->tc_hi = 0; else n->tc_min_batch = v;
     }
+    const char* es = getenv("GA3C_MLP_STREAM");
+    n->stream_ok_pending = !(es && atoi(es) == 0);
   }
   const int pv = add("logits_v", net.hid, 1, 1);
   int px, py = -1;
@@ -178,6 +184,7 @@ extern "C" int ga3c_mlp_create(const ga3c_mlp_config* cfg, ga3c_mlp** out) {
   n->skip_lo[0] = n->params[pv].offset; n->skip_hi[0] = n->params[pv + 1].offset + n->params[pv + 1].count;
   const int plast = py >= 0 ? py + 1 : px + 1;      // the policy head's variables are consecutive in the arena
   n->skip_lo[1] = n->params[px].offset; n->skip_hi[1] = n->params[plast].offset + n->params[plast].count;
+  n->stream_ok = n->stream_ok_pending && n->tc_hi > n->tc_lo && mlp_stream_ok(net, n->tc_lo, n->tc_hi);
 
   const size_t ab = (size_t)n->arena_floats * 4;
   float** arenas[4] = {&n->w, &n->g, &n->ms, &n->mom};
@@ -337,6 +344,17 @@ extern "C" int ga3c_mlp_predict(ga3c_mlp* n, const float* x, int32_t batch, floa
   cudaStream_t st = (cudaStream_t)stream;
   MlpStepArgs s = step_args(n, x, batch);
   s.p_out = p_out; s.v_out = v_out; s.train = 0;
+  if (n->stream_ok && batch >= n->tc_min_batch) {
+    // large batches: front as a streaming pass, the wide layers as 3xTF32 GEMMs, heads as a streaming pass (the layer outputs go
+    // through the training workspace; the handle mutex of the host layer serialises predict and train)
+    const MlpNet& net = n->net;
+    LAUNCH(n, K_MLP_FUSED, st, launch_mlp_front_fwd(net, s, n->num_sms, st));
+    for (int l = n->tc_lo; l < n->tc_hi; ++l)
+      LAUNCH(n, K_MLP_TC, st, launch_mlp_tc_fwd(n->w + net.L[l].w_off, n->w + net.L[l].b_off, net.L[l].k, net.L[l].n, net.L[l].act,
+                                                n->act[l - 1], n->act[l], batch, st));
+    LAUNCH(n, K_MLP_FUSED, st, launch_mlp_heads(net, s, n->num_sms, st));
+    return 0;
+  }
   LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(n->net, s, n->num_sms, st));
   return 0;
 }
@@ -355,19 +373,23 @@ static int mlp_fb_impl(ga3c_mlp* n, const float* x, const float* yr, const float
     const MlpNet& net = n->net;
     const int lo = n->tc_lo, hi = n->tc_hi;
     s.tc_lo = lo; s.tc_hi = hi;
+    const bool streamed = n->stream_ok;       // narrow ends as streaming passes (mlp_stream.cu) instead of fused-kernel phases
     s.phase = 1;
-    LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(net, s, n->num_sms, st));
+    if (streamed) LAUNCH(n, K_MLP_FUSED, st, launch_mlp_front_fwd(net, s, n->num_sms, st));
+    else LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(net, s, n->num_sms, st));
     for (int l = lo; l < hi; ++l)
       LAUNCH(n, K_MLP_TC, st, launch_mlp_tc_fwd(n->w + net.L[l].w_off, n->w + net.L[l].b_off, net.L[l].k, net.L[l].n, net.L[l].act,
                                                 n->act[l - 1], n->act[l], batch, st));
     s.phase = 2;
-    LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(net, s, n->num_sms, st));
+    if (streamed) LAUNCH(n, K_MLP_FUSED, st, launch_mlp_heads(net, s, n->num_sms, st));
+    else LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(net, s, n->num_sms, st));
     for (int l = hi - 1; l >= lo; --l)
       LAUNCH(n, K_MLP_TC, st, launch_mlp_tc_dgrad(n->w + net.L[l].w_off, net.L[l].k, net.L[l].n, n->dz[l], n->act[l - 1],
                                                   net.L[l - 1].act, n->dz[l - 1], batch, st));
     if (lo >= 2) {
       s.phase = 3;
-      LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(net, s, n->num_sms, st));
+      if (streamed) LAUNCH(n, K_MLP_FUSED, st, launch_mlp_front_bwd(net, s, n->num_sms, st));
+      else LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(net, s, n->num_sms, st));
     }
     const int splits = MLP_MAX_SPLITS;
     int rows = (batch + splits - 1) / splits;
@@ -393,7 +415,7 @@ static int mlp_fb_impl(ga3c_mlp* n, const float* x, const float* yr, const float
                                                          n->part + net.L[l].w_off, n->part + net.L[l].b_off, n->live_floats, st));
     }
     LAUNCH(n, K_MLP_REDUCE, st, launch_mlp_reduce(n->part, n->live_floats, splits, g_dst, (int)n->live_floats, n->loss_part,
-                                                  (batch + tm - 1) / tm, loss, st));
+                                                  streamed ? mlp_heads_loss_rows(batch, n->num_sms) : (batch + tm - 1) / tm, loss, st));
     return 0;
   }
   LAUNCH(n, K_MLP_FUSED, st, launch_mlp_fused(n->net, s, n->num_sms, st));

@@ -1002,7 +1002,7 @@ extern "C" const char* ga3c_kernel_name(int kid) { return (kid >= 0 && kid < K_C
 static int trace_attach_all(unsigned long long* buf) {
   int r;
   if ((r = trace_attach_conv_fwd(buf)) || (r = trace_attach_conv_bwd_fused(buf)) || (r = trace_attach_dense_tc(buf)) ||
-      (r = trace_attach_heads(buf)) || (r = trace_attach_dense_heads(buf)) || (r = trace_attach_elementwise(buf)) || (r = trace_attach_mlp(buf)) || (r = trace_attach_mlp_tc(buf)))
+      (r = trace_attach_heads(buf)) || (r = trace_attach_dense_heads(buf)) || (r = trace_attach_elementwise(buf)) || (r = trace_attach_mlp(buf)) || (r = trace_attach_mlp_tc(buf)) || (r = trace_attach_mlp_stream(buf)))
     return r;
   return 0;
 }
