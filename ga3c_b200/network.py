@@ -63,6 +63,38 @@ class _HandleLock:
         return False
 
 
+class _TrainSlot:
+    """Staging of ONE trainer thread.  The reference runs Config.TRAINERS (= 2, Config.py:59) ThreadTrainers that call
+    Network.train concurrently (ThreadTrainer.py:42-62, Server.py:141-150): call k+1's host -> device copy goes into the other
+    slot, on that slot's own stream, while call k's kernels run and its caller waits for them -- PCIe never idles between
+    steps.  Slot = trainer_id % 2; a slot is used by one call at a time (its lock)."""
+
+    def __init__(self, tdev):
+        self.lock = threading.Lock()
+        self.tdev = tdev
+        self.rows = 0
+        self.rows8 = 0
+        with torch.cuda.device(tdev):
+            self.stream = torch.cuda.Stream(device=tdev)
+            self.ready = torch.cuda.Event()
+
+    def buffers(self, rows: int, num_actions: int, u8: bool):
+        with torch.cuda.device(self.tdev):
+            if rows > self.rows:
+                self.hyr = torch.empty((rows,), dtype=torch.float32, pin_memory=True)
+                self.ha = torch.empty((rows, num_actions), dtype=torch.float32, pin_memory=True)
+                self.dyr = torch.empty((rows,), dtype=torch.float32, device=self.tdev)
+                self.da = torch.empty((rows, num_actions), dtype=torch.float32, device=self.tdev)
+                self.hx = torch.empty((rows, STATE_DIM), dtype=torch.float32, pin_memory=True)
+                self.dx = torch.empty((rows, STATE_DIM), dtype=torch.float32, device=self.tdev)
+                self.rows = rows
+            if u8 and rows > self.rows8:
+                self.hx8 = torch.empty((rows, STATE_DIM), dtype=torch.uint8, pin_memory=True)
+                self.dx8 = torch.empty((rows, STATE_DIM), dtype=torch.uint8, device=self.tdev)
+                self.rows8 = rows
+        return (self.hx8, self.dx8) if u8 else (self.hx, self.dx)
+
+
 class Network:
     def __init__(self, device, model_name, num_actions, state_dim=STATE_DIM, *, config=None, max_batch=None,
                  seed=None, data_parallel=None, dp_mode=None):
@@ -115,6 +147,7 @@ class Network:
             self._stream = torch.cuda.Stream(device=self._tdev)
             self._loss_dev = torch.zeros(4, dtype=torch.float32, device=self._tdev)
         self._alloc_io(self._max_batch)
+        self._train_slots = [_TrainSlot(self._tdev) for _ in range(2)]     # staging per trainer thread, allocated on first use
 
         # variable init: U(-d, d), d = 1/sqrt(fan_in)  (NetworkVP.py:214-217, NetworkDNav.py:258-261)
         rng = np.random.default_rng(seed)
@@ -370,17 +403,23 @@ class Network:
         x = self._frames(x, self.state_dim)
         y_r = np.asarray(y_r, dtype=np.float32).reshape(b)
         a = np.asarray(a, dtype=np.float32).reshape(b, self.num_actions)
-        with self._lock:
-            self._ensure(b)
-            hx, dx = self._io_u8() if x.dtype == np.uint8 else (self._hx, self._dx)
-            with torch.cuda.stream(self._stream):
-                self._h2d(y_r, self._hyr, self._dyr, b)
-                self._h2d(a, self._ha, self._da, b)
+        slot = self._train_slots[int(trainer_id) % len(self._train_slots) if isinstance(trainer_id, (int, np.integer)) else 0]
+        with slot.lock:
+            # this call's inputs travel on the slot's stream, outside the handle lock: under the kernels of the other trainer's call
+            hx, dx = slot.buffers(b, self.num_actions, x.dtype == np.uint8)
+            with torch.cuda.stream(slot.stream):
+                self._h2d(y_r, slot.hyr, slot.dyr, b)
+                self._h2d(a, slot.ha, slot.da, b)
                 self._h2d(x, hx, dx, b)
-                self.train_device(dx[:b], self._dyr[:b], self._da[:b],
-                                  loss_out=self._loss_dev if fetch_losses else None, stream=self._stream)
-                losses = self._loss_dev.cpu() if fetch_losses else None
-            self._stream.synchronize()
+                slot.ready.record(slot.stream)
+            with self._lock:
+                self._ensure(b)
+                self._stream.wait_event(slot.ready)
+                with torch.cuda.stream(self._stream):
+                    self.train_device(dx[:b], slot.dyr[:b], slot.da[:b],
+                                      loss_out=self._loss_dev if fetch_losses else None, stream=self._stream)
+                    losses = self._loss_dev.cpu() if fetch_losses else None
+                self._stream.synchronize()
         if self.dp_mode == "fused":
             self._dp_steps = getattr(self, "_dp_steps", 0) + 1
             if self._dp_steps % 64 == 1:      # a timed-out cross-rank wait leaves garbage weights: fail, do not train on

@@ -297,13 +297,16 @@ def test_full_size_batch_and_reproducibility(mlp):
         assert err(g1[k], g_ref)[1] <= TOL_GRAD_REL, (k, err(g1[k], g_ref))
 
 
-@pytest.mark.parametrize("s,a", [(3, 1), (4, 2)])
+@pytest.mark.parametrize("s,a,stream", [(3, 1, "1"), (3, 1, "0"), (4, 2, "1")])
 @pytest.mark.parametrize("batch", [33, 128, 1000, 4097])
-def test_tensor_core_wide_layers_match_oracle_and_the_fp32_path(mlp, monkeypatch, s, a, batch):
-    """The 256 -> 256 and 256 -> 100 layers of the fork NetworkVP as 3xTF32 tcgen05 GEMMs (mlp_tc.cu; taken from 4096 training rows
-    on, forced here from 1 row): same tolerances against the oracle as the fp32 FMA path, and close to that path itself."""
+def test_tensor_core_wide_layers_match_oracle_and_the_fp32_path(mlp, monkeypatch, s, a, stream, batch):
+    """The 256 -> 256, 256 -> 100 and 100 -> 64 layers of the fork NetworkVP as 3xTF32 tcgen05 GEMMs (mlp_tc.cu; taken from 4096
+    rows on, forced here from 1 row): same tolerances against the oracle as the fp32 FMA path, and close to that path itself --
+    predictions, losses and gradients.  With one action the narrow ends are the streaming kernels of mlp_stream.cu
+    (GA3C_MLP_STREAM=0: the fused kernel's phases); with two actions always the fused kernel's phases."""
     kind = "fork_vp"
     params, x, y_r, act = make_case(kind, s, a, batch, seed=11)
+    monkeypatch.setenv("GA3C_MLP_STREAM", stream)
     out = {}
     for mode in ("1", "0"):
         monkeypatch.setenv("GA3C_MLP_TC", mode)          # read at construction: 1 = tensor cores from 1 row, 0 = never
@@ -311,10 +314,18 @@ def test_tensor_core_wide_layers_match_oracle_and_the_fp32_path(mlp, monkeypatch
         net.set_variables(params)
         net.beta = 0.01
         n0 = net.launch_count()
-        out[mode] = (net.losses(x, y_r, act), net.get_gradients(), net.launch_count() - n0)
+        pv = net.predict_p_and_v(x)
+        n1 = net.launch_count()
+        out[mode] = (net.losses(x, y_r, act), net.get_gradients(), net.launch_count() - n1, pv, n1 - n0)
     assert out["1"][2] > out["0"][2] == 3, (out["1"][2], out["0"][2])      # the GEMM launches really ran
+    streamed = a == 1 and stream == "1"
+    assert out["0"][4] == 1 and out["1"][4] == (5 if streamed else 1), (out["1"][4], out["0"][4])   # predict: front, 3 GEMMs, heads
+    p_ref, v_ref = om.forward(params, x, kind)
+    for mode in ("1", "0"):
+        p, v = out[mode][3]
+        assert err(p, p_ref)[0] <= TOL_PV and err(v, v_ref)[0] <= TOL_PV, (mode, err(p, p_ref), err(v, v_ref))
     losses_ref, grads_ref = om.loss_and_grads(params, x, y_r, act, kind, beta=0.01)
-    losses, grads, _ = out["1"]
+    losses, grads, _, _, _ = out["1"]
     for k in ("cost_p_1", "cost_p_2", "cost_v", "cost_all"):
         assert abs(losses[k] - losses_ref[k]) <= 2e-5 * max(batch, abs(losses_ref[k])), (k, losses[k], losses_ref[k])
     for k, g_ref in grads_ref.items():

@@ -802,6 +802,41 @@ def test_concurrent_predict_and_train_threads(ga3c):
     assert net.get_global_step() == 60
 
 
+def test_two_trainer_threads_with_their_own_staging_slots(ga3c):
+    """Config.TRAINERS = 2 ThreadTrainers call train concurrently (ThreadTrainer.py:42-62): each trainer_id stages its batch in
+    its own slot on its own copy stream, the steps themselves are serialised.  With both threads feeding the SAME batch the
+    result cannot depend on the interleaving: it must equal 2 x 6 sequential steps, bit for bit -- a copy racing a step that
+    still reads the slot would show up as different weights."""
+    params, x, y_r, a = make_case(96, seed=8)
+    pageable = (np.array(x, copy=True), np.array(y_r, dtype=np.float64), np.array(a, copy=True))   # y_r as float64 (ProcessAgent.py:99)
+    nets = []
+    for threads in (1, 2):
+        net = ga3c.Network("gpu:0", f"slots{threads}", 6, max_batch=96)
+        net.set_variables(params)
+        errs = []
+
+        def trainer(tid, steps):
+            try:
+                for i in range(steps):
+                    net.train(*(pageable if i % 2 else (x, y_r, a)), None, None, tid)
+            except Exception as e:      # noqa
+                errs.append(e)
+
+        if threads == 1:
+            trainer(0, 12)
+        else:
+            ts = [threading.Thread(target=trainer, args=(tid, 6)) for tid in (0, 1)]
+            [t.start() for t in ts]
+            [t.join() for t in ts]
+        assert not errs, errs
+        assert net.get_global_step() == 12
+        nets.append(net)
+    w1, w2 = nets[0].get_variables(), nets[1].get_variables()
+    assert all(np.array_equal(w1[k], w2[k]) for k in w1)
+    (ms1, _), (ms2, _) = nets[0].get_slots(), nets[1].get_slots()
+    assert all(np.array_equal(ms1[k], ms2[k]) for k in ms1)
+
+
 # ------------------------------------------------------------------------------------------------
 def test_checkpoint_round_trip(ga3c, tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
