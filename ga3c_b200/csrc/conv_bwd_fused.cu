@@ -146,17 +146,6 @@ conv_bwd_kernel(const uint8_t* __restrict__ xblk, const uint8_t* __restrict__ n1
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tslot));
-  griddep_launch();
-  mark(50, 0);
-  griddep_wait(K_CONV12_BWD);   // every input comes from the kernels that precede this one
-  mark(53, 0);
-  if (DP && opt.mode != 2 && blockIdx.x == 0 && tid < dp.world) {
-    // data parallel: dense_bwd of this rank is complete, i.e. its dense1/w gradient is final -- tell every rank now, a whole
-    // conv backward before the exchange at the end of the step needs it (dp_tail_kernel)
-    __threadfence_system();
-    dp_st_flag(dp.peer[tid] + dp.comm_offset + DPC_BIGREADY + 64 * dp.rank, dp.step);
-  }
-
   // data-gradient weights as the UMMA B operand (K-major, no swizzle): tap (a, b), k-chunk j (8 co), row n = (py, px, ci).
   // Warps 3..11 (the loaders and the issuer are already at work); the issuer waits for FB_W12DRDY before its first UMMA.
   auto build_w12d = [&]() {
@@ -190,6 +179,23 @@ conv_bwd_kernel(const uint8_t* __restrict__ xblk, const uint8_t* __restrict__ n1
     if (lane == 0) mbar_arrive(bar(FB_W12DRDY));
     mark(51, 0);
   };
+  // With batch >= the number of SMs the weights can be laid out BEFORE the dependency wait (3 us that used to sit between the wait
+  // and the first UMMA, profiles/r2e_evt_*): a CTA of this launch exists only once every CTA of dense_bwd has started, hence of
+  // heads, dense_fwd and conv_fwd of this step; the 148 conv_fwd CTAs take a whole SM each, so by then no block of the previous
+  // optimizer launch -- the last writer of conv12/w -- is left anywhere (the same argument as RmsPropArgs::preload).
+  const bool w12d_early = (hints & 8) != 0;
+  if (w12d_early && warp >= 3 && warp <= 11) build_w12d();
+  griddep_launch();
+  mark(50, 0);
+  griddep_wait(K_CONV12_BWD);   // every input comes from the kernels that precede this one
+  mark(53, 0);
+  if (DP && opt.mode != 2 && blockIdx.x == 0 && tid < dp.world) {
+    // data parallel: dense_bwd of this rank is complete, i.e. its dense1/w gradient is final -- tell every rank now, a whole
+    // conv backward before the exchange at the end of the step needs it (dp_tail_kernel)
+    __threadfence_system();
+    dp_st_flag(dp.peer[tid] + dp.comm_offset + DPC_BIGREADY + 64 * dp.rank, dp.step);
+  }
+
 
   // Data-gradient epilogue of one 128-row tile for TMEM lane quarter `qt`: rows of the first tile go to warps 4-7, the 28
   // live rows of the second tile (lanes 100..127) to warp 11.
@@ -422,7 +428,7 @@ conv_bwd_kernel(const uint8_t* __restrict__ xblk, const uint8_t* __restrict__ n1
     }
   } else if (warp == FB_T1_WARP) {
     // =========================== second data-gradient tile ===========================
-    build_w12d();
+    if (!w12d_early) build_w12d();
     float bacc11[C1_OUT];
 #pragma unroll
     for (int c = 0; c < C1_OUT; ++c) bacc11[c] = 0.f;
@@ -431,7 +437,7 @@ conv_bwd_kernel(const uint8_t* __restrict__ xblk, const uint8_t* __restrict__ n1
   } else if (warp == 3 || warp >= 8) {
     // =========================== conv12 bias gradient: column sums of G ===========================
     // warp -> chunk plane j (8 channels), lane -> row phase: 16-byte rows, conflict-free; border rows are zero
-    build_w12d();
+    if (!w12d_early) build_w12d();
     const int j = warp == 3 ? 3 : warp - 8;
     float acc8[8];
 #pragma unroll
@@ -459,7 +465,7 @@ conv_bwd_kernel(const uint8_t* __restrict__ xblk, const uint8_t* __restrict__ n1
     }
   } else {
     // =========================== data-gradient epilogue; final store ===========================
-    build_w12d();
+    if (!w12d_early) build_w12d();
     const int ew = warp - FB_EPI_WARP0;                            // TMEM lane quarter
     const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16);
     float bacc[C1_OUT];                                            // db11 partials of this thread's pixels
@@ -552,7 +558,7 @@ int launch_conv_bwd(const uint8_t* xblk, const uint8_t* n1b2, const uint8_t* dn2
   auto kernel = dp != nullptr ? ((d.n_exch > 0 || opt.mode == 2) ? conv_bwd_kernel<2, false> : conv_bwd_kernel<1, false>)
                               : (g_evt_attached ? conv_bwd_kernel<0, true> : conv_bwd_kernel<0, false>);
   return launch_pdl(kernel, grid, dim3(FB_THREADS), FB_SMEM, stream, xblk, n1b2, dn2g, w12, dn1_out, g_w11, g_b11, g_w12, g_b12,
-                    gp_stride, batch, n_conv, l2_hints(true, x_u8), opt, d);
+                    gp_stride, batch, n_conv, l2_hints(true, x_u8) | (batch >= num_sms ? 8 : 0), opt, d);
 }
 
 }  // namespace ga3c
