@@ -220,6 +220,18 @@ __device__ __forceinline__ void trace_mark(int kid, int what) {      // what: 0 
     }
   }
 }
+// the same stamp by whichever single thread the caller names (kernels whose thread 0 does not wait for the dependency)
+__device__ __forceinline__ void trace_mark_by(int kid, int what, bool me) {
+  if (me) {
+    unsigned long long* t = g_trace;
+    if (t != nullptr) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(now));
+      atomicMin(t + kid * TRACE_SLOTS + 2 * what, now);
+      atomicMax(t + kid * TRACE_SLOTS + 2 * what + 1, now);
+    }
+  }
+}
 __device__ __forceinline__ void griddep_wait(int kid) {
   trace_mark(kid, 0);
   asm volatile("griddepcontrol.wait;\n" ::: "memory");
