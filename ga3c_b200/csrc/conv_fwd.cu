@@ -68,7 +68,9 @@ constexpr int CF_SMEM = CF_OFF_XCH + 1024 + 1024;                    // incl. sl
 static_assert(CF_SMEM <= 232448, "shared memory budget of one CTA per SM");
 constexpr int CF_TMEM_COLS = 256, TMEM_C12 = 128;                    // conv11 tiles at columns 0,32,64,96; conv12 at 128..159
 
-template <bool U8>       // U8: frames are uint8 [B,28224] (x = k/128 - 1 applied on the fly), else fp32
+// U8: frames are uint8 [B,28224] (x = k/128 - 1 applied on the fly), else fp32.  EVT: the instantiation with the pipeline event log
+// of CTA 0 (ga3c_evt_*, tools/evt_conv_fwd_prologue.py); the production instantiations carry none of it.
+template <bool U8, bool EVT>
 __global__ void __launch_bounds__(CF_THREADS, 1)
 conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const float* __restrict__ b11,
                 const float* __restrict__ w12, const float* __restrict__ b12,
@@ -80,7 +82,8 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
                  wq = sbase + CF_OFF_WQ, lut = sbase + CF_OFF_LUT, bars = sbase + CF_OFF_BAR, tslot = sbase + CF_OFF_TSLOT;
   float* bias_s = reinterpret_cast<float*>(smem + CF_OFF_BIAS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  EvtLog evt_i = evt_open();                                      // pipeline event log of CTA 0 (ga3c_evt_*), off unless attached
+  EvtLog evt_i = EVT ? evt_open() : EvtLog{nullptr, 0};          // pipeline event log of CTA 0 (ga3c_evt_*): EVT instantiation only
+  auto mark = [&](int id, int arg) { if (EVT) evt_mark(evt_i, id, arg); };
   const int stride = gridDim.x;
   const int n_frames = ((int)blockIdx.x < batch) ? (batch - 1 - (int)blockIdx.x) / stride + 1 : 0;
   const int n_chunks = n_frames * PW_NCHUNK;                         // chunk stream of this CTA: q = k * 21 + c, warp q % 6
@@ -98,7 +101,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
   };
 
   // ---------------- prologue ----------------
-  evt_mark(evt_i, 60, 0);
+  mark(60, 0);
   if (tid == 0) {
     for (int i = 0; i < CF_AUX_WARPS * PW_SLOTS; ++i) mbar_init(bar(BAR_RING + i), 1);
     for (int i = 0; i < 4; ++i) {
@@ -114,7 +117,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
   }
   if (warp == CF_EPI_WARP0) tmem_alloc<CF_TMEM_COLS>(tslot);
   __syncthreads();
-  evt_mark(evt_i, 61, 0);
+  mark(61, 0);
   if (warp < CF_AUX_WARPS && lane == 0)                              // x is an input of the step: stream it before the dependency wait
     for (int j = 0; j < PW_SLOTS; ++j)
       if (warp + j * CF_AUX_WARPS < n_chunks) issue_chunk(warp + j * CF_AUX_WARPS, warp * PW_SLOTS + j);
@@ -141,7 +144,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
   }
   fence_proxy_async();          // the zeroed operand regions are read by the tensor core (async proxy)
   __syncthreads();              // Blk is zeroed before the aux warps write frame 0 into it; the scatter table is complete
-  evt_mark(evt_i, 62, 0);
+  mark(62, 0);
   griddep_launch();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tslot));
@@ -152,7 +155,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
     trace_mark_by(K_CONV_FWD, 0, tid == CF_AUX_WARPS * 32);
     asm volatile("griddepcontrol.wait;\n" ::: "memory");       // the weights below come from the optimizer kernel that precedes this one in the stream
     trace_mark_by(K_CONV_FWD, 1, tid == CF_AUX_WARPS * 32);
-    evt_mark(evt_i, 63, 0);
+    mark(63, 0);
     const int t = tid - CF_AUX_WARPS * 32;                        // 0 .. 319; every load of a thread is in flight before its first store
     float4 q12[8];
     float2 q11[8];
@@ -196,7 +199,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
     tc_fence_before();
     named_bar_sync(4, CF_THREADS - CF_AUX_WARPS * 32);
     tc_fence_after();
-    evt_mark(evt_i, 64, 0);
+    mark(64, 0);
   }
 
   if (warp < CF_AUX_WARPS) {
@@ -233,7 +236,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
 #pragma unroll
       for (int i = 0; i < C11_TILES; ++i) {
         mbar_wait(bar(BAR_BLKRDY + i), k & 1);                       // the Blk rows this tile reads hold frame k
-        evt_mark(evt_i, 15, k * 4 + i);
+        mark(15, k * 4 + i);
         if (k > 0) mbar_wait(bar(BAR_T1FREE + i), (k - 1) & 1);      // its accumulator of frame k-1 has been drained
         tc_fence_after();
         if (elect_one()) {
@@ -246,10 +249,10 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
           tc_commit(bar(BAR_C11 + i));
         }
         __syncwarp();
-        evt_mark(evt_i, 16, k * 4 + i);
+        mark(16, k * 4 + i);
       }
       mbar_wait(bar(BAR_A2RDY), k & 1);                              // every conv11 output of frame k sits in the im2col operand
-      evt_mark(evt_i, 17, k);
+      mark(17, k);
       if (k > 0) mbar_wait(bar(BAR_T2FREE), (k - 1) & 1);
       tc_fence_after();
       if (elect_one()) {
@@ -263,7 +266,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
         tc_commit(bar(BAR_MMA2));
       }
       __syncwarp();
-      evt_mark(evt_i, 18, k);
+      mark(18, k);
     }
   } else if (warp == CF_STORE_WARP) {
     // =========================== Blk -> HBM (training) ===========================
@@ -296,7 +299,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
     const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16);
     auto conv12_epilogue = [&](int k) {                              // TMEM -> +bias, ReLU, bf16 -> n2[frame k]
       mbar_wait(bar(BAR_MMA2), k & 1);
-      evt_mark(evt_i, 43, k);
+      mark(43, k);
       tc_fence_after();
       uint32_t r[32];
       tc_ld32(tlane + TMEM_C12, r);
@@ -324,12 +327,12 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
         if (eset == 1) conv12_epilogue(k - 1);
         else mbar_wait(bar(BAR_MMA2), (k - 1) & 1);
       }
-      evt_mark(evt_i, 44, k);
+      mark(44, k);
       uint8_t* n1_dst = n1_out ? n1_out + frame_of(k) * B2_BYTES : nullptr;      // Blk2 operand layout (common.cuh)
 #pragma unroll 1
       for (int i = eset; i < C11_TILES; i += 2) {
         mbar_wait(bar(BAR_C11 + i), k & 1);
-        evt_mark(evt_i, 40, k * 4 + i);
+        mark(40, k * 4 + i);
         tc_fence_after();
         uint32_t r[32];                                              // [0,16): b = 0 part of row m ; [16,32): b = 1 part, owed to row m-1
         tc_ld32(tlane + 32 * i, r);
@@ -379,7 +382,7 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
       fence_proxy_async();                                           // the scatter is read by the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(BAR_A2RDY));
-      evt_mark(evt_i, 42, k);
+      mark(42, k);
     }
     if (n_frames > 0 && eset == 1) conv12_epilogue(n_frames - 1);
   }
@@ -394,23 +397,30 @@ conv_fwd_kernel(const void* __restrict__ x, const float* __restrict__ w11, const
 }
 
 GA3C_TRACE_ATTACH(trace_attach_conv_fwd)
-GA3C_EVT_ATTACH(evt_attach_conv_fwd)
+static bool g_evt_attached_cf = false;     // host side: the event-log instantiation is launched only while a log is attached
+int evt_attach_conv_fwd(unsigned long long* buf) {
+  g_evt_attached_cf = buf != nullptr;
+  return (int)cudaMemcpyToSymbol(g_evt, &buf, sizeof(buf));
+}
 
 int configure_conv_fwd() {
-  cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM);
   if (e != cudaSuccess) return (int)e;
-  return (int)cudaFuncSetAttribute(conv_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM);
+  e = cudaFuncSetAttribute(conv_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(conv_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaFuncSetAttribute(conv_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF_SMEM);
 }
 
 int launch_conv_fwd(const void* x, bool x_u8, const float* w11, const float* b11, const float* w12, const float* b12,
                     uint8_t* n1_out, uint8_t* xblk_out, uint16_t* n2_out, int batch, int num_sms, cudaStream_t stream) {
   const int grid = min(batch, num_sms);
   const int hints = l2_hints(n1_out != nullptr, x_u8);
-  if (x_u8)
-    return launch_pdl(conv_fwd_kernel<true>, dim3(grid), dim3(CF_THREADS), CF_SMEM, stream, x, w11, b11, w12, b12, n1_out, xblk_out,
-                      n2_out, batch, hints);
-  return launch_pdl(conv_fwd_kernel<false>, dim3(grid), dim3(CF_THREADS), CF_SMEM, stream, x, w11, b11, w12, b12, n1_out, xblk_out,
-                    n2_out, batch, hints);
+  auto kernel = x_u8 ? (g_evt_attached_cf ? conv_fwd_kernel<true, true> : conv_fwd_kernel<true, false>)
+                     : (g_evt_attached_cf ? conv_fwd_kernel<false, true> : conv_fwd_kernel<false, false>);
+  return launch_pdl(kernel, dim3(grid), dim3(CF_THREADS), CF_SMEM, stream, x, w11, b11, w12, b12, n1_out, xblk_out, n2_out, batch,
+                    hints);
 }
 
 }  // namespace ga3c

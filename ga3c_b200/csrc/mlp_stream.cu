@@ -6,7 +6,7 @@
 // ~30 us of HBM time (profiles/r3e_mlp_launches_before.md).  Here each of them is a plain streaming pass: rows are independent,
 // weights live in registers / shared memory, every HBM byte is touched once and coalesced.
 //   mlp_front_fwd   act[0] = f0(x W0 + b0), act[1] = f1(act[0] W1 + b1)             thread = 4 columns of one row
-//   mlp_heads       logits = h Wh + bh -> v, p = atan2(..)/pi, loss terms, dlogits, dz[last] = (dlogits Wh^T) f'(h)   warp = one row
+//   mlp_heads       logits = h Wh + bh -> v, p = atan2(..)/pi, loss terms, dlogits, dz[last] = (dlogits Wh^T) f'(h)   warp = four rows
 //   mlp_front_bwd   dz[0] = (dz[1] W1^T) f0'(act[0])                                warp = one row
 // Loss terms: every warp adds the terms of its rows in row order, every block its warps in warp order into one row of loss_part;
 // mlp_reduce adds the rows in a fixed order (bit-reproducible, as the tile kernel's per-tile sums are).
@@ -60,13 +60,17 @@ __global__ void __launch_bounds__(ST_THREADS) mlp_front_fwd_kernel(const MlpNet 
     float xv[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) xv[k] = k < S ? __ldg(x + (size_t)r * S + k) : 0.f;
+    // every aligned quad of lanes belongs to one row (threads per row is a multiple of 4): lane q of the quad computes h0[q]
+    // -- one sigmoid instead of four -- and the quad exchanges the four values
     float h0[4];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
+    {
+      const int nq = tid & 3;
       float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) acc = fmaf(xv[k], w0s[k][n], acc);
-      h0[n] = n < N0 ? act_(acc + b0s[n], L0.act) : 0.f;
+      for (int k = 0; k < 4; ++k) acc = fmaf(xv[k], w0s[k][nq], acc);
+      const float mine = nq < N0 ? act_(acc + b0s[nq], L0.act) : 0.f;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) h0[n] = __shfl_sync(0xffffffffu, mine, (tid & 28) + n);
     }
     if (c0 == 0) {
       if (N0 == 4) *reinterpret_cast<float4*>(act0 + (size_t)r * 4) = make_float4(h0[0], h0[1], h0[2], h0[3]);
@@ -87,13 +91,15 @@ __global__ void __launch_bounds__(ST_THREADS) mlp_front_fwd_kernel(const MlpNet 
 }
 
 // ---- heads, loss, dlogits, gradient w.r.t. the last hidden pre-activation ---------------------------------------------------------------
-// One warp per row, HU rows in flight per warp.  hid <= 128: lane l holds h[l], h[l + 32], ...; the three logits are warp sums; every
-// lane then runs the (scalar) head arithmetic of NetworkVP.py:175-192 on identical values -- ~60 instructions, cheaper than moving
-// the row to one lane and back -- and finishes its own columns of dz.  A = 1 (n_out = 3).
+// One warp per group of HU = 4 rows.  hid <= 128: lane l holds h[l], h[l + 32], ... of each row; the three logits of a row are warp
+// sums (every lane gets them).  The scalar head arithmetic of NetworkVP.py:175-192 (two sigmoids, atan2, the loss terms, dlogits:
+// ~100 instructions) then runs ONCE per row -- lane l works on row l & 3 -- and the three dlogits of each row are handed to the
+// whole warp by shuffles for the lanes' own columns of dz.  (Every lane doing every row's scalar part made the kernel
+// instruction-bound: 60 % issue-active, 35 us at B = 65,536.)  A = 1 (n_out = 3).
 template <bool TRAIN>
 __global__ void __launch_bounds__(ST_THREADS) mlp_heads_kernel(const MlpNet net, const MlpStepArgs s, const float* __restrict__ h,
                                                                 float* __restrict__ dz_out) {
-  constexpr int HU = 2, KMAX = MLP_MAX_HID / 32;
+  constexpr int HU = 4, KMAX = MLP_MAX_HID / 32;
   const int lane = threadIdx.x & 31, warp = blockIdx.x * ST_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * ST_WARPS;
   const int hid = net.hid, B = s.batch;
   const int last_act = net.L[net.n_layers - 1].act;
@@ -108,7 +114,8 @@ __global__ void __launch_bounds__(ST_THREADS) mlp_heads_kernel(const MlpNet net,
     wh[i][2] = k < hid ? __ldg(s.w + net.wy_off + k) : 0.f;
   }
   bh[0] = __ldg(s.w + net.bv_off); bh[1] = __ldg(s.w + net.bp_off); bh[2] = __ldg(s.w + net.by_off);
-  float l1 = 0.f, l2 = 0.f, lv = 0.f;
+  const int my = lane & (HU - 1);                                  // the row of the group whose scalar part this lane computes
+  float l1 = 0.f, l2 = 0.f, lv = 0.f;                             // loss terms of the rows this lane owns (lanes 0 .. HU-1 count)
   for (int r0 = warp * HU; r0 < B; r0 += nwarps * HU) {
     float hv[HU][KMAX];
 #pragma unroll
@@ -118,54 +125,70 @@ __global__ void __launch_bounds__(ST_THREADS) mlp_heads_kernel(const MlpNet net,
         const int k = lane + 32 * i;
         hv[u][i] = (r0 + u < B && k < hid) ? __ldcs(h + (size_t)(r0 + u) * hid + k) : 0.f;
       }
+    const int r = r0 + my;
+    const bool valid = r < B;
+    float yr = 0.f, av = 0.f;
+    if (TRAIN && valid) { yr = __ldg(s.yr + r); av = __ldg(s.a + r); }
+    float z0 = 0.f, z1 = 0.f, z2 = 0.f;                            // logits of row `my`
 #pragma unroll
     for (int u = 0; u < HU; ++u) {
-      const int r = r0 + u;
-      if (r >= B) break;                                         // warp-uniform
-      float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
       for (int i = 0; i < KMAX; ++i) {
-        z0 = fmaf(hv[u][i], wh[i][0], z0); z1 = fmaf(hv[u][i], wh[i][1], z1); z2 = fmaf(hv[u][i], wh[i][2], z2);
+        a0 = fmaf(hv[u][i], wh[i][0], a0); a1 = fmaf(hv[u][i], wh[i][1], a1); a2 = fmaf(hv[u][i], wh[i][2], a2);
       }
-      z0 = warp_allsum(z0) + bh[0]; z1 = warp_allsum(z1) + bh[1]; z2 = warp_allsum(z2) + bh[2];
-      const float v = z0;
-      const float ox = sigmoid_(z1), oy = sigmoid_(z2);
-      const float X = ox - 0.5f, Y = oy - 0.5f;
-      const float p = atan2f(Y, X) / PI_F;
-      if (lane == 0) {
-        if (s.v_out != nullptr) s.v_out[r] = v;
-        if (s.p_out != nullptr) s.p_out[r] = p;
-      }
-      if (TRAIN) {
-        const float yr = __ldg(s.yr + r), av = __ldg(s.a + r);
-        const float adv = yr - v;                                // stop_gradient(v) inside cost_p_1
-        const float dp = -av * adv + 2.f * s.beta * p;
-        const float inv = 1.f / (PI_F * (X * X + Y * Y));
-        float d0 = s.part == 1 ? 0.f : v - yr;                   // Config.DUAL_RMSPROP: cost_p alone does not reach the value head ...
-        float d1 = dp * (-Y * inv) * ox * (1.f - ox);
-        float d2 = dp * (X * inv) * oy * (1.f - oy);
-        if (s.part == 2) { d1 = 0.f; d2 = 0.f; }                 // ... and cost_v alone not the policy head
+      a0 = warp_allsum(a0); a1 = warp_allsum(a1); a2 = warp_allsum(a2);
+      if (u == my) { z0 = a0 + bh[0]; z1 = a1 + bh[1]; z2 = a2 + bh[2]; }
+    }
+    const float v = z0;
+    const float ox = sigmoid_(z1), oy = sigmoid_(z2);
+    const float X = ox - 0.5f, Y = oy - 0.5f;
+    const float p = atan2f(Y, X) / PI_F;
+    if (lane < HU && valid) {
+      if (s.v_out != nullptr) s.v_out[r] = v;
+      if (s.p_out != nullptr) s.p_out[r] = p;
+    }
+    if (TRAIN) {
+      const float adv = yr - v;                                    // stop_gradient(v) inside cost_p_1
+      const float dp = -av * adv + 2.f * s.beta * p;
+      const float inv = 1.f / (PI_F * (X * X + Y * Y));
+      float d0 = s.part == 1 ? 0.f : v - yr;                       // Config.DUAL_RMSPROP: cost_p alone does not reach the value head ...
+      float d1 = dp * (-Y * inv) * ox * (1.f - ox);
+      float d2 = dp * (X * inv) * oy * (1.f - oy);
+      if (s.part == 2) { d1 = 0.f; d2 = 0.f; }                     // ... and cost_v alone not the policy head
+      if (lane < HU && valid) {
         l1 += (p * av) * adv;
         l2 += -s.beta * (p * p);
         lv += 0.5f * (yr - v) * (yr - v);
-        if (lane == 0) *reinterpret_cast<float4*>(s.dlogits + (size_t)r * net.n_out_ld) = make_float4(d0, d1, d2, 0.f);
+        *reinterpret_cast<float4*>(s.dlogits + (size_t)r * net.n_out_ld) = make_float4(d0, d1, d2, 0.f);
+      }
 #pragma unroll
-        for (int i = 0; i < KMAX; ++i) {
-          const int k = lane + 32 * i;
-          if (k < hid) {
-            float d = fmaf(d0, wh[i][0], 0.f);
-            d = fmaf(d1, wh[i][1], d);
-            d = fmaf(d2, wh[i][2], d);
-            if (last_act == MLP_ACT_SIGMOID) d *= hv[u][i] * (1.f - hv[u][i]);
-            dz_out[(size_t)r * hid + k] = d;
+      for (int u = 0; u < HU; ++u) {
+        const float e0 = __shfl_sync(0xffffffffu, d0, u), e1 = __shfl_sync(0xffffffffu, d1, u), e2 = __shfl_sync(0xffffffffu, d2, u);
+        if (r0 + u < B) {
+#pragma unroll
+          for (int i = 0; i < KMAX; ++i) {
+            const int k = lane + 32 * i;
+            if (k < hid) {
+              float d = fmaf(e0, wh[i][0], 0.f);
+              d = fmaf(e1, wh[i][1], d);
+              d = fmaf(e2, wh[i][2], d);
+              if (last_act == MLP_ACT_SIGMOID) d *= hv[u][i] * (1.f - hv[u][i]);
+              dz_out[(size_t)(r0 + u) * hid + k] = d;
+            }
           }
         }
       }
     }
   }
-  if (TRAIN) {                                                  // one row of loss_part per block: its warps in warp order
-    __shared__ float red[ST_WARPS][3];
-    if (lane == 0) { red[threadIdx.x >> 5][0] = l1; red[threadIdx.x >> 5][1] = l2; red[threadIdx.x >> 5][2] = lv; }
+  if (TRAIN) {                                                  // one row of loss_part per block: lanes 0 .. HU-1 of a warp in lane
+    __shared__ float red[ST_WARPS][3];                          // order, then the warps in warp order
+    float t1 = l1, t2 = l2, tv = lv;
+#pragma unroll
+    for (int u = 1; u < HU; ++u) {
+      t1 += __shfl_sync(0xffffffffu, l1, u); t2 += __shfl_sync(0xffffffffu, l2, u); tv += __shfl_sync(0xffffffffu, lv, u);
+    }
+    if (lane == 0) { red[threadIdx.x >> 5][0] = t1; red[threadIdx.x >> 5][1] = t2; red[threadIdx.x >> 5][2] = tv; }
     __syncthreads();
     if (threadIdx.x < 4) {
       float t = 0.f;
@@ -239,7 +262,8 @@ bool mlp_stream_ok(const MlpNet& net, int tc_lo, int tc_hi) {
   if (net.kind != MLP_KIND_FORK_VP || net.num_actions != 1 || net.n_out != 3 || net.n_out_ld != 4) return false;
   if (tc_lo != 2 || tc_hi != net.n_layers || net.hid > MLP_MAX_HID) return false;
   const MlpLayerDesc &L0 = net.L[0], &L1 = net.L[1];
-  return L0.k <= 4 && L0.n <= 4 && L1.k == L0.n && L1.n <= 256 && L1.n % 4 == 0 && ST_THREADS % (L1.n / 4) == 0 &&
+  // L1.n a multiple of 128: a warp of mlp_front_fwd never spans two rows (its quad shuffles run in warp-uniform code)
+  return L0.k <= 4 && L0.n <= 4 && L1.k == L0.n && L1.n <= 256 && L1.n % 128 == 0 && ST_THREADS % (L1.n / 4) == 0 &&
          (L0.w_off & 3) == 0 && (L1.w_off & 3) == 0 && (L1.b_off & 3) == 0;
 }
 
@@ -255,10 +279,10 @@ int launch_mlp_front_fwd(const MlpNet& net, const MlpStepArgs& s, int num_sms, c
 }
 
 // rows of loss_part the heads kernel writes (one per block); the grid depends on the batch alone
-int mlp_heads_loss_rows(int batch, int num_sms) { return stream_grid(batch, ST_WARPS * 2 * 4, num_sms); }
+int mlp_heads_loss_rows(int batch, int num_sms) { return stream_grid(batch, ST_WARPS * 4 * 2, num_sms); }
 
 int launch_mlp_heads(const MlpNet& net, const MlpStepArgs& s, int num_sms, cudaStream_t stream) {
-  const int grid = stream_grid(s.batch, ST_WARPS * 2 * 4, num_sms);
+  const int grid = stream_grid(s.batch, ST_WARPS * 4 * 2, num_sms);
   const float* h = s.act[net.n_layers - 1];
   if (s.train) return launch_pdl(mlp_heads_kernel<true>, dim3(grid), dim3(ST_THREADS), 0, stream, net, s, h, s.dz[net.n_layers - 1]);
   return launch_pdl(mlp_heads_kernel<false>, dim3(grid), dim3(ST_THREADS), 0, stream, net, s, h, (float*)nullptr);
