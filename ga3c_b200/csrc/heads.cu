@@ -49,7 +49,9 @@ __global__ void __launch_bounds__(HD_THREADS) heads_kernel(HeadsArgs p) {
         float4 fb = *reinterpret_cast<const float4*>(&hs.b1s[128 + 4 * lane]);
         {
           float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
-#pragma unroll 4
+          // the partial tiles sit in L2; every load of a pass is in flight before the first add (the training batch's 9 splits
+          // in one pass: one L2 round trip instead of three), the adds stay in split order
+#pragma unroll 9
           for (int sp = 0; sp < p.n_split; ++sp) {
             const float* src = p.d1_part + ((size_t)sp * p.batch + b) * FC;
             const float4 qa = *reinterpret_cast<const float4*>(src + 4 * lane);

@@ -153,3 +153,41 @@ def test_lockstep_trainer_keeps_ranks_in_step_with_empty_batches(tmp_path):
     assert np.array_equal(c0[:, 0] + c1[:, 0], c0[:, 1]) and (c0[:, 1] > 0).all()   # no step without rows anywhere
     assert c0[:, 0].sum() == sum(1 + i % 3 for i in range(6)) and c1[:, 0].sum() == sum(1 + i % 3 for i in range(2))
     assert s1[1] >= 1 and (c1[:, 0] == 0).sum() == s1[1]                     # the slow rank ticked with empty batches
+
+
+def test_dp_check_criterion_separates_a_broken_exchange_from_rounding_flips():
+    """bench.oracle_distance, the criterion of the N > 1 bench's dp_check: weights two oracle steps away from the start pass when
+    they differ from the reference by what ONE rounding flip of a dense1 output does (one entry of dense1/b by lr * dd1, its
+    column of dense1/w by ~1e-6 -- the 2.8e-5 that the first, rows-proportional tolerance tripped over at world = 4), and fail
+    when a rank's rows are missing from the gradient sum or counted twice."""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    from bench import oracle_distance
+    world, rows = 4, 16
+
+    def two_steps(select):
+        g = np.random.default_rng(4242)
+        p0 = onp.init_params(g, 6)
+        ms, mom = onp.rmsprop_init(p0)
+        w = p0
+        for _ in range(2):
+            x = onp.synth_frames(g, rows * world)
+            y_r, a = onp.synth_targets(g, rows * world, 6)
+            idx = select(np.arange(rows * world))
+            _, _, w, ms, mom = onp.train_step(w, ms, mom, x[idx], y_r[idx], a[idx], lr=3e-4, beta=0.01, quant="bf16")
+            w = {k: v.astype(np.float32) for k, v in w.items()}
+        return p0, w
+
+    start, ref = two_steps(lambda i: i)
+    assert oracle_distance(ref, ref, start)["ok"]
+    flipped = {k: v.copy() for k, v in ref.items()}
+    flipped["dense1/b:0"][17] += 2.8e-5
+    flipped["dense1/w:0"][:, 17] += 1e-6
+    rep = oracle_distance(flipped, ref, start)
+    assert rep["ok"] and rep["worst_tensor"] == "dense1/b:0" and rep["max_abs_vs_oracle"] > 2e-5, rep
+    _, lost = two_steps(lambda i: i[:rows * (world - 1)])                                # the last rank never arrived
+    _, twice = two_steps(lambda i: np.r_[i[:rows * (world - 1)], i[rows * (world - 2):rows * (world - 1)]])   # rank 2 counted twice
+    for bad in (lost, twice):
+        rep = oracle_distance(bad, ref, start)
+        assert not rep["ok"] and rep["rel_l2_of_update"] > 0.2 and rep["entries_beyond_1e5"] > 10000, rep
