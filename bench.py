@@ -583,6 +583,25 @@ def run_ours(args, rank, local_rank, world):
     train_e2e_pageable(0)
     s_train_e2e_pg = e2e(train_e2e_pageable, k_e2e)
     s_train_e2e_pg_2t = e2e_threads(train_e2e_pageable_t, k_e2e) if world == 1 else None
+    # how the pageable array reaches the pinned staging buffer (Network._h2d): the library's worker threads with streaming
+    # stores (ga3c_stage_h2d, the default), the same with plain stores, or torch's copy from the calling thread
+    pg_variants = {}
+    if world == 1:
+        saved = {k: os.environ.get(k) for k in ("GA3C_COPY_THREADS", "GA3C_COPY_NT")}
+        try:
+            for name, threads, nt in (("torch_copy_from_the_caller", 0, 1), ("native_4_threads", 4, 1), ("native_8_threads", 8, 1),
+                                      ("native_12_threads", 12, 1), ("native_8_threads_plain_stores", 8, 0)):
+                os.environ["GA3C_COPY_THREADS"], os.environ["GA3C_COPY_NT"] = str(threads), str(nt)
+                train_e2e_pageable(0)
+                one = e2e(train_e2e_pageable, k_e2e)
+                two = e2e_threads(train_e2e_pageable_t, k_e2e)
+                pg_variants[name] = {"two_trainers": round(B * k_e2e / two), "single_caller": round(B * k_e2e / one)}
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
 
     # the ceiling of any fp32-contract e2e number: a bare pinned host -> device copy of one batch, all ranks at once
     def h2d_only(i):
@@ -703,7 +722,10 @@ def run_ours(args, rank, local_rank, world):
                    "pageable": {"value": world * B * k_e2e / (s_train_e2e_pg_2t or s_train_e2e_pg), "unit": "frames/s",
                                 "single_caller": world * B * k_e2e / s_train_e2e_pg,
                                 "api": "the same calls on ordinary (pageable) numpy arrays, what the reference's ThreadTrainer hands "
-                                       "over (np.concatenate output): a chunked host copy into pinned staging overlaps the DMA"}},
+                                       "over (np.concatenate output): a chunked host copy into pinned staging (ga3c_stage_h2d: "
+                                       "worker threads of the library, streaming stores) overlaps the DMA",
+                                "copy_threads": ga3c_b200.Network._copy_threads(),
+                                "variants_frames_per_s": pg_variants}},
            "pps": {"value": pps, "unit": "predictions/s", "batch": PB, "ms_per_step": ms_pred / K,
                    "e2e": {"value": world * PB * k_e2e / s_pred_e2e, "unit": "predictions/s",
                            "h2d_bytes_per_step": PB * STATE_DIM * 4, "d2h_bytes_per_step": PB * (NUM_ACTIONS + 1) * 4,

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libga3c_b200.so")
+LIB_PATH = os.environ.get("GA3C_LIB") or os.path.join(_HERE, "_lib", "libga3c_b200.so")     # GA3C_LIB: A/B runs of two builds on one box
 
 
 class ga3c_config(C.Structure):
@@ -57,6 +57,7 @@ SIGNATURES = {
     "ga3c_dp_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ga3c_dp_attach": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "ga3c_dp_detach": (C.c_int, [C.c_void_p]),
+    "ga3c_stage_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
     "ga3c_dp_attach_local": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "ga3c_dp_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "ga3c_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,

@@ -19,6 +19,7 @@ int evt_attach_conv_fwd(unsigned long long* buf);
 int evt_attach_conv_bwd(unsigned long long* buf);
 int evt_attach_elementwise(unsigned long long* buf);
 int evt_attach_dense_heads(unsigned long long* buf);
+int evt_attach_dense_tc(unsigned long long* buf);      // records only in a -DGA3C_DENSE_EVT build
 
 // L2 residency hints on the conv kernels' loads and stores (common.cuh); GA3C_L2_HINTS=0 switches them off (evict_normal)
 // bit 0: frames loaded evict_first, bit 1: activations stored evict_last, bit 2: the conv backward loads evict_first.

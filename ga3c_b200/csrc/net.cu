@@ -122,7 +122,7 @@ int set_error(const std::string& m) { g_err = m; return -1; }     // for the oth
 const char* kernel_name(int kid) { return (kid >= 0 && kid < K_COUNT) ? kKernelNames[kid] : nullptr; }
 }
 extern "C" const char* ga3c_last_error(void) { return g_err.c_str(); }
-extern "C" int ga3c_abi_version(void) { return 5; }
+extern "C" int ga3c_abi_version(void) { return 6; }
 
 extern "C" int ga3c_create(const ga3c_config* cfg, ga3c_net** out) {
   if (!cfg || !out) return fail_msg("ga3c_create: null argument");
@@ -1037,10 +1037,16 @@ extern "C" int ga3c_evt_begin(ga3c_net* n) {
   CK(cudaDeviceSynchronize());
   if (!n->evt) CK(cudaMalloc((void**)&n->evt, (size_t)2 * 16384 * 8));
   CK(cudaMemset(n->evt, 0, (size_t)2 * 16384 * 8));
-  CKL(evt_attach_conv_fwd(n->evt));
-  CKL(evt_attach_conv_bwd(n->evt));
-  CKL(evt_attach_elementwise(n->evt));
-  CKL(evt_attach_dense_heads(n->evt));
+  // the kernels share the 16 warp regions of one buffer: GA3C_EVT_DENSE=1 (tools/evt_dense.py, a -DGA3C_DENSE_EVT build) leaves them
+  // to the dense1 GEMMs
+  if (getenv("GA3C_EVT_DENSE") == nullptr) {
+    CKL(evt_attach_conv_fwd(n->evt));
+    CKL(evt_attach_conv_bwd(n->evt));
+    CKL(evt_attach_elementwise(n->evt));
+    CKL(evt_attach_dense_heads(n->evt));
+  } else {
+    CKL(evt_attach_dense_tc(n->evt));
+  }
   return 0;
 }
 
@@ -1052,6 +1058,7 @@ extern "C" int ga3c_evt_end(ga3c_net* n, uint64_t* records, int32_t cap, int32_t
   CKL(evt_attach_conv_bwd(nullptr));
   CKL(evt_attach_elementwise(nullptr));
   CKL(evt_attach_dense_heads(nullptr));
+  CKL(evt_attach_dense_tc(nullptr));
   std::vector<uint64_t> all((size_t)2 * 16384);
   CK(cudaMemcpy(all.data(), n->evt, all.size() * 8, cudaMemcpyDeviceToHost));
   int32_t c = 0;

@@ -245,18 +245,40 @@ class Network:
 
     _CHUNK_BYTES = 8 << 20
 
+    @staticmethod
+    def _copy_threads() -> int:
+        """Worker threads of ga3c_stage_h2d for one pageable array: GA3C_COPY_THREADS, else half of this rank's share of the
+        cores this process may run on, between 2 and 8 (0: the interpreter-side chunked copy)."""
+        env = os.environ.get("GA3C_COPY_THREADS")
+        if env is not None:
+            return max(0, int(env))
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 2)
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        return max(2, min(8, cores // (2 * ranks)))
+
     def _h2d(self, arr: np.ndarray, pinned: torch.Tensor, dst: torch.Tensor, b: int):
         """Enqueues the host -> device copy of arr[:b] on the current stream.  A pinned caller array is copied as it is; a
         pageable one (what the reference's ThreadTrainer hands over: np.concatenate output, ThreadTrainer.py:54-58) goes
-        through this Network's pinned staging buffer in chunks, so that the host copy of chunk k+1 (torch's multi-threaded
-        copy, GIL released) overlaps the DMA of chunk k instead of preceding the whole transfer."""
+        through this Network's pinned staging buffer in chunks, so that the host copy of chunk k+1 overlaps the DMA of chunk k
+        instead of preceding the whole transfer: by the library's worker threads with streaming stores (ga3c_stage_h2d, no
+        interpreter involved), or with GA3C_COPY_THREADS=0 by torch's copy from this thread."""
         src = None
         if arr.flags["C_CONTIGUOUS"] and arr.flags["WRITEABLE"]:
             src = torch.from_numpy(arr)
             if src.is_pinned():
                 dst[:b].copy_(src, non_blocking=True)
                 return
-        if src is None or arr.nbytes <= self._CHUNK_BYTES:
+        if arr.nbytes <= self._CHUNK_BYTES or not arr.flags["C_CONTIGUOUS"]:
+            pinned[:b].numpy()[...] = arr
+            dst[:b].copy_(pinned[:b], non_blocking=True)
+            return
+        threads = self._copy_threads()
+        if threads > 0:
+            st = torch.cuda.current_stream(self._tdev)
+            _capi.check(self._lib.ga3c_stage_h2d(dst.data_ptr(), pinned.data_ptr(), arr.ctypes.data, arr[:b].nbytes,
+                                                 self._CHUNK_BYTES, threads, st.cuda_stream), "ga3c_stage_h2d")
+            return
+        if src is None:
             pinned[:b].numpy()[...] = arr
             dst[:b].copy_(pinned[:b], non_blocking=True)
             return

@@ -272,6 +272,18 @@ int ga3c_batcher_stop(ga3c_batcher* b);
 int ga3c_batcher_stats(ga3c_batcher* b, int64_t* batches, int64_t* rows, int32_t* error);
 int ga3c_batcher_destroy(ga3c_batcher* b);
 
+/* ---- host staging of pageable caller arrays ------------------------------------------------------------
+ * ThreadTrainer hands Network.train ordinary numpy arrays (np.concatenate output, ThreadTrainer.py:54-58); a cudaMemcpyAsync
+ * from pageable memory runs at a fraction of the PCIe rate.  ga3c_stage_h2d copies `bytes` from `src` (any host memory) into the
+ * page-locked `staging` buffer with `threads` worker threads of the library (non-temporal stores, 512 KB pieces claimed in
+ * address order; threads <= 1: the calling thread alone) and enqueues cudaMemcpyAsync(dst_dev + off, staging + off) on `stream`
+ * for every chunk of `chunk_bytes` (0: 8 MB) as soon as the chunk is in place, so the DMA of chunk k runs under the host copy of
+ * chunk k + 1.  Returns once the host copy is complete and every DMA is enqueued; `staging` must stay untouched until the
+ * stream has passed them.  dst_dev == NULL: host copy only (no CUDA call is made).  One job at a time per process: concurrent
+ * callers queue.  Needs no handle. */
+int ga3c_stage_h2d(void* dst_dev, void* staging, const void* src, int64_t bytes, int64_t chunk_bytes, int32_t threads,
+                   void* stream);
+
 /* ---- introspection for tests / profiling ---------------------------------------------------- */
 /* device pointers to the activation workspace of the last call (bf16 stored as uint16):
  * which: 0 n1 bf16 in the Blk2 operand layout [B][8 planes][160 rows][8] (channels 8h.. of pixel (y, x) in plane

@@ -267,3 +267,35 @@ def test_thread_trainer_matches_reference_class():
     assert len(t1) == len(t2)
     for a, b in zip(t1, t2):
         assert all(np.array_equal(a[k], b[k]) for k in range(3)) and a[3] == b[3]
+
+
+def test_stage_h2d_host_copy_is_exact_for_ragged_sizes_and_thread_counts():
+    """ga3c_stage_h2d (include/ga3c_b200.h) with dst_dev = NULL is the host half alone: the pageable -> staging copy by the
+    library's worker threads in 512 KB pieces with streaming stores.  Byte-exact for sizes that are not multiples of the
+    piece, the chunk or 64 bytes, for unaligned source and destination, for every thread count, and for concurrent callers
+    (the two trainer threads of the reference's Server queue on one job at a time)."""
+    import threading
+    from ga3c_b200 import _capi
+    lib = _capi.load()
+    rng = np.random.default_rng(5)
+    for nbytes, so, do, threads, chunk in ((0, 0, 0, 4, 0), (1, 0, 0, 4, 0), (63, 1, 3, 2, 0), (512 * 1024, 0, 0, 3, 0),
+                                           (512 * 1024 + 1, 5, 0, 3, 1 << 20), (3 * 1024 * 1024 + 77, 0, 9, 8, 1 << 20),
+                                           (9 * 1024 * 1024 + 13, 3, 1, 5, 0), (20 * 1024 * 1024, 0, 0, 1, 0),
+                                           (20 * 1024 * 1024 + 5, 7, 64, 32, 2 << 20)):
+        src = rng.integers(0, 256, size=nbytes + so + 64, dtype=np.uint8)
+        dst = np.full(nbytes + do + 128, 0xAB, dtype=np.uint8)
+        rc = lib.ga3c_stage_h2d(None, dst.ctypes.data + do, src.ctypes.data + so, nbytes, chunk, threads, None)
+        assert rc == 0, lib.ga3c_last_error()
+        assert np.array_equal(dst[do:do + nbytes], src[so:so + nbytes]), (nbytes, so, do, threads)
+        assert (dst[:do] == 0xAB).all() and (dst[do + nbytes:] == 0xAB).all()       # nothing outside the range is touched
+    assert lib.ga3c_stage_h2d(None, None, None, 16, 0, 2, None) != 0 and b"null buffer" in lib.ga3c_last_error()
+
+    srcs = [rng.integers(0, 256, size=6 * 1024 * 1024 + 11 * i, dtype=np.uint8) for i in range(4)]
+    dsts = [np.zeros_like(s) for s in srcs]
+    def call(i):
+        for _ in range(5):
+            assert lib.ga3c_stage_h2d(None, dsts[i].ctypes.data, srcs[i].ctypes.data, srcs[i].nbytes, 1 << 20, 2 + i, None) == 0
+    ts = [threading.Thread(target=call, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert all(np.array_equal(d, s) for d, s in zip(dsts, srcs))
