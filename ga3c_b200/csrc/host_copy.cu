@@ -71,7 +71,9 @@ struct Job {
 
 class Pool {
  public:
-  static Pool& get() { static Pool p; return p; }
+  // never destroyed: a trainer thread may still be inside a job when the process exits (daemon threads), and a static destructor
+  // joining the workers underneath it would race with that call; the OS reaps the workers with the process
+  static Pool& get() { static Pool* p = new Pool; return *p; }
 
   // copies the whole job; `on_chunk(c)` is called by the calling thread, in order, as soon as chunk c is complete
   template <class F>
@@ -108,14 +110,6 @@ class Pool {
 
  private:
   Pool() = default;
-  ~Pool() {
-    {
-      std::lock_guard<std::mutex> l(m_);
-      stop_ = true;
-    }
-    cv_.notify_all();
-    for (auto& t : threads_) t.join();
-  }
 
   void ensure_workers(int n) {
     while ((int)threads_.size() < n) {
