@@ -20,11 +20,12 @@ import numpy as np
 import torch
 
 from . import _capi
+from ._arena import ArenaNetworkMixin
 from .config import Config as _DefaultConfig
 from .network import _parse_device
 
 
-class _MlpNetwork:
+class _MlpNetwork(ArenaNetworkMixin):
     KIND = None
 
     def __init__(self, device, model_name, num_actions, state_dim, *, config=None, max_batch=None, seed=None):
@@ -167,15 +168,6 @@ class _MlpNetwork:
             self._stream.synchronize()
             return [self._hp[:b].numpy().copy(), self._hv[:b].numpy().copy()]
 
-    def predict_single(self, x):            # NetworkVP.py:237-238
-        return self.predict_p(x[None, :])[0]
-
-    def predict_v(self, x):                 # NetworkVP.py:240-242
-        return self.predict_p_and_v(x)[1]
-
-    def predict_p(self, x):                 # NetworkVP.py:244-246
-        return self.predict_p_and_v(x)[0]
-
     def _stage_train(self, x, y_r, a):
         x = self._rows(x)
         b = x.shape[0]
@@ -220,21 +212,9 @@ class _MlpNetwork:
             self._stream.synchronize()
         return self._loss_dict(l)
 
-    def log(self, x, y_r, a, training_step, feed_dict=None):
-        """NetworkVP.py:259-265: the summary scalars, appended to logs/<model_name>/scalars.csv."""
-        l = self.losses(x, y_r, a)
-        os.makedirs(os.path.join("logs", self.model_name), exist_ok=True)
-        with open(os.path.join("logs", self.model_name, "scalars.csv"), "a") as f:
-            f.write(f"{training_step},{l['cost_p_1']},{l['cost_p_2']},{l['cost_p']},{l['cost_v']},"
-                    f"{self.learning_rate},{self.beta}\n")
-
     # ------------------------------------------------------------------ variables / checkpoints
     def get_global_step(self):
         return int(self._lib.ga3c_mlp_global_step(self._h))
-
-    def get_variables_names(self):
-        """TF creation order (trainable_variables, NetworkVP.py:284-285), gradient-less ones included."""
-        return list(self._table.keys())
 
     def live_variables(self):
         return [k for k in self._table if self._live[k]]
@@ -250,84 +230,13 @@ class _MlpNetwork:
         with self._lock:
             _capi.check(self._lib.ga3c_mlp_arena_upload(self._h, which, arena.ctypes.data, arena.size), "ga3c_mlp_arena_upload")
 
-    def _split(self, arena):
-        return {k: arena[o:o + int(np.prod(s))].reshape(s).copy() for k, (o, s) in self._table.items()}
-
-    def _join(self, which, tensors):
-        arena = self._download(which)
-        for k, v in tensors.items():
-            o, s = self._table[k]
-            v = np.asarray(v, dtype=np.float32)
-            if v.shape != tuple(s):
-                raise ValueError(f"{k}: expected shape {s}, got {v.shape}")
-            arena[o:o + v.size] = v.ravel()
-        return arena
-
-    def get_variable_value(self, name):
-        o, s = self._table[name]
-        return self._download(0)[o:o + int(np.prod(s))].reshape(s).copy()
-
-    def get_variables(self):
-        return self._split(self._download(0))
-
-    def set_variables(self, tensors):
-        self._upload(0, self._join(0, tensors))
-
     def get_gradients(self):
         """Gradients of the last forward_backward; live variables only (the others have none)."""
         g = self._split(self._download(1))
         return {k: v for k, v in g.items() if self._live[k]}
 
-    def get_slots(self, optimizer: int = 0):
-        """(ms, mom) of the RMSProp optimizer; with Config.DUAL_RMSPROP optimizer 0 minimises cost_p and 1 cost_v."""
-        base = 2 if optimizer == 0 else 5
-        return self._split(self._download(base)), self._split(self._download(base + 1))
-
-    def set_slots(self, ms=None, mom=None, optimizer: int = 0):
-        base = 2 if optimizer == 0 else 5
-        if ms is not None:
-            self._upload(base, self._join(base, ms))
-        if mom is not None:
-            self._upload(base + 1, self._join(base + 1, mom))
-
-    def _checkpoint_filename(self, episode):
-        return 'checkpoints/%s_%08d' % (self.model_name, episode)
-
-    def _get_episode_from_filename(self, filename):
-        return int(re.split(r'/|_|\.', filename)[2])
-
-    def save(self, episode):
-        fn = self._checkpoint_filename(episode) + ".npz"
-        os.makedirs(os.path.dirname(fn), exist_ok=True)
-        ms, mom = self.get_slots()
-        blob = dict(self.get_variables())
-        blob.update({k.replace(":0", "/RMSProp:0"): v for k, v in ms.items()})
-        blob.update({k.replace(":0", "/RMSProp_1:0"): v for k, v in mom.items()})
-        if self._dual:
-            ms2, mom2 = self.get_slots(1)
-            blob.update({k.replace(":0", "/RMSProp_2:0"): v for k, v in ms2.items()})
-            blob.update({k.replace(":0", "/RMSProp_3:0"): v for k, v in mom2.items()})
-        blob["step:0"] = np.array(self.get_global_step(), dtype=np.int64)
-        np.savez(fn, **blob)
-        return fn
-
-    def load(self):
-        d = os.path.dirname(self._checkpoint_filename(episode=0))
-        if getattr(self.config, "LOAD_EPISODE", 0) > 0:
-            filename = self._checkpoint_filename(self.config.LOAD_EPISODE)
-        else:
-            cands = sorted(f for f in os.listdir(d) if f.startswith(self.model_name + "_") and f.endswith(".npz"))
-            filename = os.path.join(d, cands[-1][:-4])
-        z = np.load(filename + ".npz")
-        names = self.get_variables_names()
-        self.set_variables({k: z[k] for k in names})
-        self.set_slots({k: z[k.replace(":0", "/RMSProp:0")] for k in names},
-                       {k: z[k.replace(":0", "/RMSProp_1:0")] for k in names})
-        if self._dual and names[0].replace(":0", "/RMSProp_2:0") in z:
-            self.set_slots({k: z[k.replace(":0", "/RMSProp_2:0")] for k in names},
-                           {k: z[k.replace(":0", "/RMSProp_3:0")] for k in names}, optimizer=1)
-        self._lib.ga3c_mlp_set_global_step(self._h, int(z["step:0"]))
-        return self._get_episode_from_filename(filename)
+    def _set_global_step(self, step: int):
+        self._lib.ga3c_mlp_set_global_step(self._h, int(step))
 
     # ------------------------------------------------------------------ introspection
     def workspace(self, which: int, layer: int, batch: int) -> np.ndarray:

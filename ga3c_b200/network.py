@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import _capi
+from ._arena import ArenaNetworkMixin
 from .config import Config as _DefaultConfig
 
 STATE_DIM = 84 * 84 * 4
@@ -95,7 +96,7 @@ class _TrainSlot:
         return (self.hx8, self.dx8) if u8 else (self.hx, self.dx)
 
 
-class Network:
+class Network(ArenaNetworkMixin):
     def __init__(self, device, model_name, num_actions, state_dim=STATE_DIM, *, config=None, max_batch=None,
                  seed=None, data_parallel=None, dp_mode=None):
         cfg = config or _DefaultConfig
@@ -396,15 +397,6 @@ class Network:
             self._stream.synchronize()
             return [self._hp[:b].numpy().copy(), self._hv[:b].numpy().copy()]
 
-    def predict_single(self, x):            # NetworkVP.py:237-238
-        return self.predict_p(x[None, :])[0]
-
-    def predict_v(self, x):                 # NetworkVP.py:240-242
-        return self.predict_p_and_v(x)[1]
-
-    def predict_p(self, x):                 # NetworkVP.py:244-246
-        return self.predict_p_and_v(x)[0]
-
     def train(self, x, y_r, a, x2=None, done=None, trainer_id=0, *, fetch_losses=False):
         """NetworkVP.py:254-257.  x2, done, trainer_id are accepted and ignored exactly as the A3C
         networks of the reference ignore them; y_r may arrive as float64 (ProcessAgent.py:99)."""
@@ -472,22 +464,9 @@ class Network:
         c1, c2, cv = (float(v) for v in l[:3])
         return dict(cost_p_1=c1, cost_p_2=c2, cost_p=-(c1 + c2), cost_v=cv, cost_all=-(c1 + c2) + cv)
 
-    def log(self, x, y_r, a, training_step, feed_dict=None):
-        """NetworkVP.py:259-265 writes TensorBoard summaries from a second forward pass.  Here the same
-        scalars (Pcost_advantage, Pcost_entropy, Pcost, Vcost, LearningRate, Beta) are appended to
-        logs/<model_name>/scalars.csv."""
-        l = self.losses(x, y_r, a)
-        os.makedirs(os.path.join("logs", self.model_name), exist_ok=True)
-        with open(os.path.join("logs", self.model_name, "scalars.csv"), "a") as f:
-            f.write(f"{training_step},{l['cost_p_1']},{l['cost_p_2']},{l['cost_p']},{l['cost_v']},"
-                    f"{self.learning_rate},{self.beta}\n")
-
     # ------------------------------------------------------------------ variables / checkpoints
     def get_global_step(self):              # NetworkVP.py:233-235
         return int(self._lib.ga3c_global_step(self._h))
-
-    def get_variables_names(self):          # NetworkVP.py:284-285 (TF creation order)
-        return list(self._table.keys())
 
     def _download(self, which: int) -> np.ndarray:
         self.dp_check()
@@ -501,89 +480,18 @@ class Network:
         with self._lock:
             _capi.check(self._lib.ga3c_arena_upload(self._h, which, arena.ctypes.data, arena.size), "ga3c_arena_upload")
 
-    def _split(self, arena: np.ndarray):
-        return {k: arena[o:o + int(np.prod(s))].reshape(s).copy() for k, (o, s) in self._table.items()}
-
-    def _join(self, which: int, tensors: dict) -> np.ndarray:
-        arena = self._download(which)
-        for k, v in tensors.items():
-            o, s = self._table[k]
-            v = np.asarray(v, dtype=np.float32)
-            if v.shape != tuple(s):
-                raise ValueError(f"{k}: expected shape {s}, got {v.shape}")
-            arena[o:o + v.size] = v.ravel()
-        return arena
-
-    def get_variable_value(self, name):     # NetworkVP.py:287-288
-        o, s = self._table[name]
-        return self._download(0)[o:o + int(np.prod(s))].reshape(s).copy()
-
-    def get_variables(self):
-        return self._split(self._download(0))
-
-    def set_variables(self, tensors: dict):
-        self._upload(0, self._join(0, tensors))
-
     def get_gradients(self):
         """Gradients left by the last forward_backward.  Data parallel: dp_mode 'nccl' leaves the allreduced gradient on every
         rank; dp_mode 'fused' leaves this rank's OWN contribution, except for the slice of dense1/w this rank owns, which
         holds the sum over ranks (the reduction happens on the owner; only the bf16 shadow of the new weights travels)."""
         return self._split(self._download(1))
 
-    def get_slots(self, optimizer: int = 0):
-        """(ms, mom) of the RMSProp optimizer; with Config.DUAL_RMSPROP optimizer 0 minimises cost_p and 1 cost_v."""
-        base = 2 if optimizer == 0 else 5
-        return self._split(self._download(base)), self._split(self._download(base + 1))
+    def _set_global_step(self, step: int):
+        self._lib.ga3c_set_global_step(self._h, int(step))
 
-    def set_slots(self, ms: dict = None, mom: dict = None, optimizer: int = 0):
-        base = 2 if optimizer == 0 else 5
-        if ms is not None:
-            self._upload(base, self._join(base, ms))
-        if mom is not None:
-            self._upload(base + 1, self._join(base + 1, mom))
-
-    def _checkpoint_filename(self, episode):    # NetworkVP.py:267-268
-        return 'checkpoints/%s_%08d' % (self.model_name, episode)
-
-    def _get_episode_from_filename(self, filename):     # NetworkVP.py:270-272
-        return int(re.split(r'/|_|\.', filename)[2])
-
-    def save(self, episode):
-        """NetworkVP.py:274-275: all global variables (weights, RMSProp slots, step), keyed by TF name."""
-        fn = self._checkpoint_filename(episode) + ".npz"
-        os.makedirs(os.path.dirname(fn), exist_ok=True)
-        ms, mom = self.get_slots()
-        blob = {k: v for k, v in self.get_variables().items()}
-        blob.update({k.replace(":0", "/RMSProp:0"): v for k, v in ms.items()})
-        blob.update({k.replace(":0", "/RMSProp_1:0"): v for k, v in mom.items()})
-        if self._dual:
-            ms2, mom2 = self.get_slots(1)
-            blob.update({k.replace(":0", "/RMSProp_2:0"): v for k, v in ms2.items()})
-            blob.update({k.replace(":0", "/RMSProp_3:0"): v for k, v in mom2.items()})
-        blob["step:0"] = np.array(self.get_global_step(), dtype=np.int64)
-        np.savez(fn, **blob)
-        return fn
-
-    def load(self):
-        """NetworkVP.py:277-282: latest checkpoint, or Config.LOAD_EPISODE; returns the episode number."""
-        d = os.path.dirname(self._checkpoint_filename(episode=0))
-        if getattr(self.config, "LOAD_EPISODE", 0) > 0:
-            filename = self._checkpoint_filename(self.config.LOAD_EPISODE)
-        else:
-            cands = sorted(f for f in os.listdir(d) if f.startswith(self.model_name + "_") and f.endswith(".npz"))
-            filename = os.path.join(d, cands[-1][:-4])
-        z = np.load(filename + ".npz")
-        names = self.get_variables_names()
-        self.set_variables({k: z[k] for k in names})
-        self.set_slots({k: z[k.replace(":0", "/RMSProp:0")] for k in names},
-                       {k: z[k.replace(":0", "/RMSProp_1:0")] for k in names})
-        if self._dual and names[0].replace(":0", "/RMSProp_2:0") in z:
-            self.set_slots({k: z[k.replace(":0", "/RMSProp_2:0")] for k in names},
-                           {k: z[k.replace(":0", "/RMSProp_3:0")] for k in names}, optimizer=1)
-        self._lib.ga3c_set_global_step(self._h, int(z["step:0"]))
+    def _after_load(self):
         if self.dp_mode is not None:
             self.sync_replicas()          # every rank read the same file; make sure of it
-        return self._get_episode_from_filename(filename)
 
     def dp_check(self):
         """Raises if a cross-rank wait of the data-parallel exchange gave up (a rank died or the ranks' train() calls fell
