@@ -299,3 +299,98 @@ def test_stage_h2d_host_copy_is_exact_for_ragged_sizes_and_thread_counts():
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert all(np.array_equal(d, s) for d, s in zip(dsts, srcs))
+
+
+def test_arena_mixin_named_tensors_slots_checkpoints_and_log(tmp_path, monkeypatch):
+    """ga3c_b200/_arena.py -- the host plumbing the conv Network and the MLP networks share -- over an in-memory arena (no GPU):
+    the arena as TF-named tensors (get / set, shape errors), both optimizers' slots, the checkpoint round trip with the
+    reference's file naming (NetworkVP.py:267-282: latest checkpoint or Config.LOAD_EPISODE, episode number returned, slots of
+    the second optimizer only with DUAL_RMSPROP) and the scalar log of NetworkVP.py:259-265."""
+    from ga3c_b200._arena import ArenaNetworkMixin
+
+    class Cfg:
+        LOAD_EPISODE = 0
+
+    class Fake(ArenaNetworkMixin):
+        def __init__(self, name, dual=False):
+            self.model_name, self.config, self._dual = name, Cfg, dual
+            self.learning_rate, self.beta = 3e-4, 0.01
+            self._table = {"dense1/w:0": (0, (3, 4)), "dense1/b:0": (64, (4,)), "logits_v/w:0": (128, (4, 1))}
+            self._arenas = {w: np.zeros(192, np.float32) for w in (0, 1, 2, 3, 5, 6)}
+            self._step, self.loaded = 0, 0
+        def _download(self, which): return self._arenas[which].copy()
+        def _upload(self, which, arena): self._arenas[which] = np.asarray(arena, np.float32).copy()
+        def get_global_step(self): return self._step
+        def _set_global_step(self, step): self._step = step
+        def _after_load(self): self.loaded += 1
+        def predict_p_and_v(self, x): return [np.full((len(x), 2), 0.5, np.float32), np.arange(len(x), dtype=np.float32)]
+        def losses(self, x, y_r, a): return dict(cost_p_1=1.0, cost_p_2=2.0, cost_p=-3.0, cost_v=4.0, cost_all=1.0)
+
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(3)
+    net = Fake("m", dual=True)
+    assert net.get_variables_names() == ["dense1/w:0", "dense1/b:0", "logits_v/w:0"]
+    w = {k: rng.standard_normal(s).astype(np.float32) for k, (o, s) in net._table.items()}
+    net.set_variables(w)
+    assert all(np.array_equal(net.get_variables()[k], w[k]) for k in w)
+    assert np.array_equal(net.get_variable_value("dense1/b:0"), w["dense1/b:0"])
+    assert net._arenas[0][12:64].sum() == 0 and net._arenas[0][68:128].sum() == 0          # alignment gaps stay untouched
+    with pytest.raises(ValueError):
+        net.set_variables({"dense1/b:0": np.zeros(5, np.float32)})
+    net.set_variables({"dense1/b:0": np.ones(4)})                                           # a subset; float64 is converted
+    assert np.array_equal(net.get_variables()["dense1/b:0"], np.ones(4, np.float32)) and np.array_equal(net.get_variables()["dense1/w:0"], w["dense1/w:0"])
+    ms = {k: np.full(s, 2.0, np.float32) for k, (o, s) in net._table.items()}
+    mom = {k: np.full(s, 3.0, np.float32) for k, (o, s) in net._table.items()}
+    net.set_slots(ms, mom)
+    net.set_slots({k: v * 10 for k, v in ms.items()}, None, optimizer=1)
+    assert net.get_slots()[0]["dense1/w:0"][0, 0] == 2.0 and net.get_slots()[1]["dense1/w:0"][0, 0] == 3.0
+    assert net.get_slots(1)[0]["dense1/w:0"][0, 0] == 20.0 and net.get_slots(1)[1]["dense1/w:0"][0, 0] == 0.0
+    assert net.predict_v(np.zeros((3, 2)))[2] == 2.0 and net.predict_p(np.zeros((3, 2))).shape == (3, 2)
+    assert net.predict_single(np.zeros(2)).shape == (2,)
+
+    net._step = 77
+    assert net.save(5) == "checkpoints/m_00000005.npz" and net._get_episode_from_filename("checkpoints/m_00000005") == 5
+    net._step = 99
+    net.set_variables({"dense1/b:0": np.full(4, 9.0)})
+    net.save(12)
+    z = np.load("checkpoints/m_00000012.npz")
+    assert {"dense1/w:0", "dense1/w/RMSProp:0", "dense1/w/RMSProp_1:0", "dense1/w/RMSProp_2:0", "dense1/w/RMSProp_3:0", "step:0"} <= set(z.files)
+    other = Fake("m", dual=True)
+    assert other.load() == 12 and other._step == 99 and other.loaded == 1                  # the latest checkpoint
+    assert other.get_variables()["dense1/b:0"][0] == 9.0 and other.get_slots(1)[0]["dense1/w:0"][0, 0] == 20.0
+    Cfg.LOAD_EPISODE = 5
+    try:
+        single = Fake("m", dual=False)
+        assert single.load() == 5 and single._step == 77 and single.get_variables()["dense1/b:0"][0] == 1.0
+        assert single.get_slots(1)[0]["dense1/w:0"][0, 0] == 0.0                            # not DUAL_RMSPROP: second optimizer untouched
+    finally:
+        Cfg.LOAD_EPISODE = 0
+    plain = Fake("p")
+    plain.save(1)
+    assert "dense1/w/RMSProp_2:0" not in np.load("checkpoints/p_00000001.npz").files
+
+    net.log(None, None, None, 1234)
+    net.log(None, None, None, 1235)
+    rows = open("logs/m/scalars.csv").read().strip().splitlines()
+    assert rows[0] == "1234,1.0,2.0,-3.0,4.0,0.0003,0.01" and rows[1].startswith("1235,") and len(rows) == 2
+
+
+def test_copy_threads_for_pageable_staging(monkeypatch):
+    """Network._copy_threads: GA3C_COPY_THREADS wins (0 = the interpreter-side copy); otherwise half of this rank's share of the
+    cores the process may run on, between 2 and 8 (LOCAL_WORLD_SIZE ranks of a torchrun job share the host)."""
+    import ga3c_b200
+    f = ga3c_b200.Network._copy_threads
+    monkeypatch.setenv("GA3C_COPY_THREADS", "0")
+    assert f() == 0
+    monkeypatch.setenv("GA3C_COPY_THREADS", "5")
+    assert f() == 5
+    monkeypatch.delenv("GA3C_COPY_THREADS")
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(32)), raising=False)
+    monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
+    assert f() == 8
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert f() == 2
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "2")
+    assert f() == 8
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(3)), raising=False)
+    assert f() == 2
